@@ -1,0 +1,70 @@
+/* libecp_b200.h - extensions of the drop-in C ABI that only make sense on the device build:
+ * device selection, multi-GPU sharding by shell-pair ownership, a device-resident result, run
+ * statistics.  Everything is plain C (pointers, ints, doubles); no torch / CUDA types.
+ *
+ * Each entry cites the reference interface it extends or replaces.
+ */
+#ifndef LIBECP_B200_H
+#define LIBECP_B200_H 1
+
+#include "libecp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* CUDA device used by handles created afterwards (default 0, or env LIBECP_B200_DEVICE).
+ * The reference has no device notion (no process/device boundary). */
+void libecp_b200_set_device(int device);
+
+/* Restrict a handle to the shell pairs owned by `rank` of `world` (disjoint output blocks per rank,
+ * no data-path collective).  Replaces nothing in the reference (single-threaded loop
+ * nest src/libecp.c:256-397); the union over ranks of what calculateECPIntegrals / the matrix
+ * entry points produce equals the unsharded result block for block. */
+void libecp_b200_set_shard(libECPHandle *h, int rank, int world);
+/* owner rank of the shell pair (global shell indices) under that partition */
+int libecp_b200_pair_owner(int shellA, int shellB, int world);
+
+/* Upper-triangular ECP matrix accumulated on the device (what getIntegrals' callback
+ * src/getIntegrals.c:22-43 builds on the host).  On return *devMatrix is a device pointer to
+ * nAO*nAO doubles owned by the handle (valid until the next call or libECP_free), *nAO its dimension.
+ * Same return codes as calculateECPIntegrals. */
+int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO);
+/* same, then copied into host memory I (row stride rowdim) with += on the upper triangle */
+int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I);
+
+typedef struct {
+  long long nominal_triples;   /* centres x nshells(nshells+1)/2 : the reference's loop domain (src/libecp.c:256-312) */
+  long long executed_triples;  /* survive screening (src/libecp.c:304-320,344) */
+  long long shell_slots, atom_slots, prim_pairs;
+  long long fast_quadratures, fast_failed, fallback_items, type1_fallback_pairs, stale_centre_events;
+  long long kernel_launches, batches;
+  double ms_build, ms_tables, ms_fastT, ms_fallback, ms_link, ms_type1, ms_chi, ms_shift, ms_device_total;
+} libecp_b200_stats_t;
+void libecp_b200_get_stats(libECPHandle *h, libecp_b200_stats_t *out);
+
+/* screening decisions of one centre, for parity tests against the reference's
+ * ScreenedGrid/potentialScreening (src/type2.c:148-180,201-203): arrays of nrShells ints */
+int libecp_b200_screening(libECPHandle *h, int centre, int *end_l /* [L] */, int *start, int *end, int *skip);
+
+/* host table access for bit-exactness tests (reference tables: src/libecp.c:147-198):
+ * names "fac" "dfac" "poly2sph" "omega" "small_x" "small_w" "large_x" "large_w" "bessel" ; returns length */
+int libecp_b200_host_table(libECPHandle *h, const char *name, const double **ptr);
+/* integer tables for tests: "small_oidx" "large_oidx" "small_meta" "dims" "ijk" "ijkIndex" "atomType"; returns count */
+int libecp_b200_host_itable(libECPHandle *h, const char *name, int *out, int cap);
+/* executed triples of the whole job in the reference's loop order, rows (A,s1,la,B,s2,lb,C); host only */
+long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap);
+/* test hook: handles created afterwards build tables + batches only (no device); compute entry points
+ * then fail with -1.  Used by the CPU-only test tier; never a compute fallback. */
+void libecp_b200_set_tables_only(int on);
+/* last batch's device intermediates, tests only: "F" "omegaX" "T" "gamma" "chi" "Q" */
+int libecp_b200_debug_fetch(libECPHandle *h, const char *what, double *dst, long long n);
+
+/* measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator for bench.py) */
+double libecp_b200_fp64_peak(int device, int iters);
+const char *libecp_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,208 @@
+"""ctypes binding of libecp_b200.so - the same C ABI an existing libECP caller links against
+(include/libecp.h, getIntegrals.h, libecp_b200.h).  Python is only the harness language for tests and
+bench.py; there is no Python compute path and no CPU fallback: if the CUDA library is missing or no
+device is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "lib", "libecp_b200.so")
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int)
+CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                       _pd, C.c_void_p)
+
+EXPORTS = [
+    "libECP_init", "calculateECPIntegrals", "libECP_free", "getIntegrals", "cartesianShellOrder",
+    "cartesianShellOrderIndex", "libecp_b200_set_device", "libecp_b200_set_shard", "libecp_b200_pair_owner",
+    "libecp_b200_integrals_device", "libecp_b200_integrals_host", "libecp_b200_get_stats", "libecp_b200_screening",
+    "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
+    "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in (
+        "nominal_triples", "executed_triples", "shell_slots", "atom_slots", "prim_pairs", "fast_quadratures",
+        "fast_failed", "fallback_items", "type1_fallback_pairs", "stale_centre_events", "kernel_launches",
+        "batches")] + [(n, C.c_double) for n in (
+            "ms_build", "ms_tables", "ms_fastT", "ms_fallback", "ms_link", "ms_type1", "ms_chi", "ms_shift",
+            "ms_device_total")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load the product library; fail loudly if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} is missing - run `python -m libecp_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(SO_PATH)
+        L.libECP_init.restype = C.c_void_p
+        L.calculateECPIntegrals.restype = C.c_int
+        L.calculateECPIntegrals.argtypes = [C.c_void_p, CALLBACK, C.c_void_p]
+        L.libECP_free.argtypes = [C.c_void_p]
+        L.libECP_free.restype = None
+        L.getIntegrals.restype = C.c_int
+        L.libecp_b200_set_device.argtypes = [C.c_int]
+        L.libecp_b200_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.libecp_b200_pair_owner.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.libecp_b200_integrals_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _pi]
+        L.libecp_b200_integrals_host.argtypes = [C.c_void_p, C.c_int, _pd]
+        L.libecp_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.libecp_b200_screening.argtypes = [C.c_void_p, C.c_int, _pi, _pi, _pi, _pi]
+        L.libecp_b200_host_table.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_pd)]
+        L.libecp_b200_host_itable.argtypes = [C.c_void_p, C.c_char_p, _pi, C.c_int]
+        L.libecp_b200_triple_list.argtypes = [C.c_void_p, _pi, C.c_longlong]
+        L.libecp_b200_triple_list.restype = C.c_longlong
+        L.libecp_b200_set_tables_only.argtypes = [C.c_int]
+        L.libecp_b200_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, _pd, C.c_longlong]
+        L.libecp_b200_fp64_peak.argtypes = [C.c_int, C.c_int]
+        L.libecp_b200_fp64_peak.restype = C.c_double
+        L.libecp_b200_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def set_device(dev: int) -> None:
+    lib().libecp_b200_set_device(int(dev))
+
+
+def fp64_peak(dev: int = 0, iters: int = 200000) -> float:
+    return float(lib().libecp_b200_fp64_peak(int(dev), int(iters)))
+
+
+def get_integrals(s, tol=1e-12, acc=1e-14, large=1024):
+    """The one-call interface (reference src/getIntegrals.h:7-13) on host buffers; returns the nAO x nAO matrix."""
+    dim = int(s["dim"])
+    I = np.zeros((dim, dim), dtype=np.float64)
+    rc = lib().getIntegrals(C.c_int(s["nat"]), _p(s["geometry"], _pd),
+                            _p(s["shellsECP"], _pi), _p(s["KECP"], _pi), _p(s["lECP"], _pi),
+                            _p(s["nECP"], _pd), _p(s["dECP"], _pd), _p(s["aECP"], _pd),
+                            _p(s["shellsBS"], _pi), _p(s["lBS"], _pi), _p(s["KBS"], _pi),
+                            _p(s["dBS"], _pd), _p(s["aBS"], _pd),
+                            C.c_int(large), C.c_double(tol), C.c_double(acc), C.c_int(dim), _p(I, _pd))
+    if rc != 0:
+        raise RuntimeError("getIntegrals failed: " + (lib().libecp_b200_last_error() or b"").decode())
+    return I
+
+
+class Handle:
+    """libECP_init / calculateECPIntegrals / libECP_free (reference src/libecp.h:15-29) + device extensions."""
+
+    def __init__(self, s, tol=1e-12, acc=1e-14, large=1024, n=0, tables_only=False):
+        L = lib()
+        self.s = s  # keeps the borrowed arrays alive (the handle borrows them, reference src/libecp.c:68-74)
+        if tables_only:
+            L.libecp_b200_set_tables_only(1)
+        try:
+            self.h = L.libECP_init(C.c_int(s["nat"]), _p(s["geometry"], _pd),
+                                   _p(s["shellsECP"], _pi), _p(s["lECP"], _pi), _p(s["KECP"], _pi),
+                                   _p(s["nECP"], _pd), _p(s["dECP"], _pd), _p(s["aECP"], _pd),
+                                   _p(s["shellsBS"], _pi), _p(s["lBS"], _pi), _p(s["KBS"], _pi),
+                                   _p(s["dBS"], _pd), _p(s["aBS"], _pd),
+                                   C.c_int(n), C.c_int(-1), None, C.c_int(large), C.c_double(tol), C.c_double(acc))
+        finally:
+            if tables_only:
+                L.libecp_b200_set_tables_only(0)
+        if not self.h:
+            raise RuntimeError("libECP_init returned NULL: " + (L.libecp_b200_last_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().libECP_free(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_shard(self, rank, world):
+        lib().libecp_b200_set_shard(C.c_void_p(self.h), int(rank), int(world))
+
+    def callbacks(self, keep_blocks=True):
+        recs = []
+
+        def cb(A, s1, la, sha, B, s2, lb, shb, Cc, I, args):
+            n = ((la + 1) * (la + 2) // 2) * ((lb + 1) * (lb + 2) // 2)
+            blk = np.ctypeslib.as_array(I, shape=(n,)).copy() if keep_blocks else None
+            recs.append((A, s1, la, sha, B, s2, lb, shb, Cc, blk))
+
+        rc = lib().calculateECPIntegrals(C.c_void_p(self.h), CALLBACK(cb), None)
+        return rc, recs
+
+    def integrals_host(self):
+        dim = int(self.s["dim"])
+        I = np.zeros((dim, dim), dtype=np.float64)
+        rc = lib().libecp_b200_integrals_host(C.c_void_p(self.h), dim, _p(I, _pd))
+        if rc < 0:
+            raise RuntimeError("device failure: " + (lib().libecp_b200_last_error() or b"").decode())
+        return rc, I
+
+    def integrals_device(self):
+        """Returns (rc, device pointer as int, nAO); the matrix stays in HBM (owned by the handle)."""
+        ptr = C.c_void_p()
+        n = C.c_int()
+        rc = lib().libecp_b200_integrals_device(C.c_void_p(self.h), C.byref(ptr), C.byref(n))
+        if rc < 0:
+            raise RuntimeError("device failure: " + (lib().libecp_b200_last_error() or b"").decode())
+        return rc, ptr.value, n.value
+
+    def stats(self):
+        st = Stats()
+        lib().libecp_b200_get_stats(C.c_void_p(self.h), C.byref(st))
+        return st.asdict()
+
+    def host_table(self, name):
+        ptr = _pd()
+        n = lib().libecp_b200_host_table(C.c_void_p(self.h), name.encode(), C.byref(ptr))
+        return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0)
+
+    def host_itable(self, name):
+        n = lib().libecp_b200_host_itable(C.c_void_p(self.h), name.encode(), None, 0)
+        out = np.zeros(max(n, 1), np.int32)
+        lib().libecp_b200_host_itable(C.c_void_p(self.h), name.encode(), _p(out, _pi), n)
+        return out[:n]
+
+    def screening(self, centre, L):
+        ns = int(self.s["nshells"])
+        endl = np.zeros(max(L, 1), np.int32)
+        st, en, sk = (np.zeros(ns, np.int32) for _ in range(3))
+        rc = lib().libecp_b200_screening(C.c_void_p(self.h), int(centre), _p(endl, _pi), _p(st, _pi), _p(en, _pi),
+                                         _p(sk, _pi))
+        if rc:
+            raise RuntimeError("not an ECP centre")
+        return endl[:L], st, en, sk
+
+    def triple_list(self):
+        n = lib().libecp_b200_triple_list(C.c_void_p(self.h), None, 0)
+        out = np.zeros((max(n, 1), 7), np.int32)
+        lib().libecp_b200_triple_list(C.c_void_p(self.h), _p(out, _pi), n)
+        return out[:n]
+
+    def debug_fetch(self, what, n):
+        out = np.zeros(n, np.float64)
+        rc = lib().libecp_b200_debug_fetch(C.c_void_p(self.h), what.encode(), _p(out, _pd), n)
+        if rc:
+            raise RuntimeError("debug_fetch failed")
+        return out

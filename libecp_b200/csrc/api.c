@@ -1,0 +1,358 @@
+/* api.c - the drop-in C API (include/libecp.h, getIntegrals.h, dimensions.h) on top of the host
+ * builder and the CUDA layer.  Mirrors the reference's entry points:
+ *   libECP_init            src/libecp.c:53-201
+ *   calculateECPIntegrals  src/libecp.c:212-404   (callbacks replayed on the host in the reference's order)
+ *   libECP_free            src/libecp.c:407-444
+ *   getIntegrals           src/getIntegrals.c:45-95
+ *   cartesianShellOrder[Index]  src/dimensions.c:17-57
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../../include/dimensions.h"
+#include "../../include/getIntegrals.h"
+#include "../../include/libecp_b200.h"
+#include "builder.h"
+#include "tables.h"
+
+struct _libECPHandle {
+  EcpTables *tab;
+  EcpDev *dev;
+  EcpBatchBuf *bb;
+  const double *geometry;
+  int nrAtoms, empty;
+  int rank, world;
+  long long maxTriples;
+  double *hostBlocks;
+  size_t hostBlocksCap;
+  libecp_b200_stats_t stats;
+};
+
+static int g_device = -1;
+static int g_tables_only = 0;
+static char g_apierr[256] = "";
+
+static double now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+void libecp_b200_set_device(int device) { g_device = device; }
+void libecp_b200_set_tables_only(int on) { g_tables_only = on; }
+const char *libecp_b200_last_error(void) { return g_apierr[0] ? g_apierr : ecpdev_last_error(); }
+int libecp_b200_pair_owner(int a, int b, int world) { return ecp_pair_owner(a, b, world); }
+double libecp_b200_fp64_peak(int device, int iters) { return ecpdev_fp64_peak_probe(device, iters); }
+
+libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lECP, int *KECP, double *nECP,
+                          double *dECP, double *aECP, int *shellsBS, int *lBS, int *KBS, double *dBS, double *aBS,
+                          int n, int lmax, int *shellOrdering, int largeGridOrder, double tolerance, double accuracy) {
+  (void)lmax;
+  g_apierr[0] = 0;
+  if (n != 0 || shellOrdering != NULL) {
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d / custom shell ordering not supported", n);
+    return NULL;
+  }
+  libECPHandle *h = calloc(1, sizeof(*h));
+  h->nrAtoms = nrAtoms;
+  h->geometry = geometry;
+  h->world = 1;
+  h->maxTriples = 1500000;
+  {
+    const char *e = getenv("LIBECP_B200_BATCH_TRIPLES");
+    if (e && atoll(e) > 0) h->maxTriples = atoll(e);
+  }
+  h->tab = ecp_tables_build(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, shellsBS, lBS, KBS, dBS, aBS,
+                            largeGridOrder, tolerance, accuracy);
+  if (!h->tab) {
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: unsupported shape or Bessel tabulation failed");
+    free(h);
+    return NULL;
+  }
+  if (h->tab->v.nTypes == 0) {
+    h->empty = 1;
+    return h;
+  }
+  if (g_tables_only) { /* test hook: tables + builder without a device; every compute entry point fails */
+    h->bb = ecp_batch_new(h->tab);
+    return h;
+  }
+  int dev = g_device;
+  if (dev < 0) {
+    const char *e = getenv("LIBECP_B200_DEVICE");
+    dev = e ? atoi(e) : 0;
+  }
+  h->dev = ecpdev_create(&h->tab->v, dev);
+  if (!h->dev) { /* no CPU fallback: fail loudly */
+    fprintf(stderr, "libecp_b200: cannot create device context: %s\n", ecpdev_last_error());
+    ecp_tables_free(h->tab);
+    free(h);
+    return NULL;
+  }
+  h->bb = ecp_batch_new(h->tab);
+  return h;
+}
+
+void libECP_free(libECPHandle *h) {
+  if (!h) return;
+  if (h->dev) ecpdev_destroy(h->dev);
+  if (h->bb) ecp_batch_free(h->bb);
+  if (h->tab) ecp_tables_free(h->tab);
+  free(h->hostBlocks);
+  free(h);
+}
+
+void libecp_b200_set_shard(libECPHandle *h, int rank, int world) {
+  h->rank = rank;
+  h->world = world < 1 ? 1 : world;
+}
+
+static void add_stats(libECPHandle *h, const EcpDevStats *st, double msBuild) {
+  libecp_b200_stats_t *s = &h->stats;
+  const EcpBatch *b = &h->bb->b;
+  s->nominal_triples += h->bb->nominal;
+  s->executed_triples += b->nTriples;
+  s->shell_slots += b->nSSlots;
+  s->atom_slots += b->nASlots;
+  s->prim_pairs += b->nPairs;
+  s->fast_quadratures += b->clsWork[h->tab->v.nClasses];
+  s->fast_failed += st->nFastFail;
+  s->fallback_items += st->nFallbackItems;
+  s->type1_fallback_pairs += st->nType1Fail;
+  s->stale_centre_events += st->nStaleCentre;
+  s->kernel_launches += st->launches;
+  s->batches += 1;
+  s->ms_build += msBuild;
+  s->ms_tables += st->ms_tables;
+  s->ms_fastT += st->ms_fastT;
+  s->ms_fallback += st->ms_fallback;
+  s->ms_link += st->ms_link;
+  s->ms_type1 += st->ms_type1;
+  s->ms_chi += st->ms_chi;
+  s->ms_shift += st->ms_shift;
+  s->ms_device_total += st->ms_total;
+}
+
+/* drive all batches; flags as ecpdev_run_batch; cb may be NULL */
+static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
+  int result = 0, centre = 0;
+  memset(&h->stats, 0, sizeof(h->stats));
+  if (h->empty) return 0;
+  if (!h->dev) {
+    fprintf(stderr, "libecp_b200: handle has no device context (tables-only); there is no CPU compute path\n");
+    return -1;
+  }
+  for (;;) {
+    const double t0 = now_ms();
+    const int took = ecp_batch_build(h->tab, h->geometry, &centre, h->maxTriples, h->rank, h->world, cb != NULL, h->bb);
+    const double msBuild = now_ms() - t0;
+    if (took == 0) break;
+    const EcpBatch *b = &h->bb->b;
+    if ((flags & 2) && (size_t)b->outTotal > h->hostBlocksCap) {
+      free(h->hostBlocks);
+      h->hostBlocksCap = (size_t)b->outTotal * 5 / 4 + 1024;
+      h->hostBlocks = malloc(h->hostBlocksCap * sizeof(double));
+    }
+    EcpDevStats st;
+    const int rc = ecpdev_run_batch(h->dev, b, flags, (flags & 2) ? h->hostBlocks : NULL, &st);
+    if (rc) {
+      fprintf(stderr, "libecp_b200: device failure: %s\n", ecpdev_last_error());
+      return -rc;
+    }
+    add_stats(h, &st, msBuild);
+    if (st.err1 && result == 0) result = 1; /* src/libecp.h:23-27 */
+    if (st.err2 && result == 0) result = 2;
+    if (result) break;
+    if (cb) { /* replay in the reference's loop order, type 1 then type 2 (src/libecp.c:332-373) */
+      typedef void (*CallSite)(int, int, int, int, int, int, int, int, int, double *, void *);
+      CallSite call = (CallSite)cb;
+      const EcpBatchBuf *bb = h->bb;
+      for (int k = 0; k < bb->nCanon; k++) {
+        const int nb = IJK_DIM(bb->cnLa[k]) * IJK_DIM(bb->cnLb[k]);
+        double *blk = h->hostBlocks + bb->cnOut[k];
+        call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], 0, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], 0, bb->cnC[k], blk, args);
+        call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], 0, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], 0, bb->cnC[k], blk + nb, args);
+      }
+    }
+  }
+  return result;
+}
+
+int calculateECPIntegrals(libECPHandle *h, ECPCallback cb, void *args) { return run_all(h, 2, cb, args); }
+
+int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
+  if (nAO) *nAO = h->tab->v.nAO;
+  if (h->empty) {
+    if (devMatrix) *devMatrix = NULL;
+    return 0;
+  }
+  if (!h->dev) return -1;
+  int rc = ecpdev_matrix_begin(h->dev);
+  if (rc) return -rc;
+  rc = run_all(h, 1, NULL, NULL);
+  if (devMatrix) *devMatrix = ecpdev_matrix_ptr(h->dev);
+  return rc;
+}
+
+int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
+  const int n = h->tab->v.nAO;
+  void *dm = NULL;
+  const int rc = libecp_b200_integrals_device(h, &dm, NULL);
+  if (rc < 0 || h->empty) return rc;
+  double *M = malloc((size_t)n * n * sizeof(double));
+  const int rc2 = ecpdev_matrix_download(h->dev, M);
+  if (rc2) {
+    free(M);
+    return -rc2;
+  }
+  for (int i = 0; i < n; i++) /* += on the upper triangle, as libECP_callback0 does (src/getIntegrals.c:36-42) */
+    for (int j = i; j < n; j++) I[(size_t)i * rowdim + j] += M[(size_t)i * n + j];
+  free(M);
+  return rc;
+}
+
+int getIntegrals(int nrAtoms, double *geometry, int *shellsECP, int *KECP, int *lECP, double *nECP, double *dECP,
+                 double *aECP, int *shellsBS, int *lBS, int *KBS, double *dBS, double *aBS, int largeGridOrder,
+                 double tolerance, double accuracy, int rowdim, double *I) {
+  libECPHandle *h = libECP_init(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, shellsBS, lBS, KBS, dBS,
+                                aBS, 0, -1, NULL, largeGridOrder, tolerance, accuracy);
+  if (NULL == h) {
+    printf("error initializing libECP\n"); /* src/getIntegrals.c:84-87 */
+    return 1;
+  }
+  libecp_b200_integrals_host(h, rowdim, I); /* the reference ignores the integrate rc as well (src/getIntegrals.c:88) */
+  libECP_free(h);
+  return 0;
+}
+
+void libecp_b200_get_stats(libECPHandle *h, libecp_b200_stats_t *out) { *out = h->stats; }
+
+int libecp_b200_screening(libECPHandle *h, int centre, int *end_l, int *start, int *end, int *skip) {
+  const EcpTables *t = h->tab;
+  if (h->empty || centre < 0 || centre >= h->nrAtoms || t->atomType[centre] < 0) return -1;
+  const EcpType *T = &t->types[t->atomType[centre]];
+  for (int l = 0; l < T->L; l++) end_l[l] = T->endl[l];
+  for (int s = 0; s < t->v.nrShells; s++) {
+    const double *rX = h->geometry + 3 * t->shellAtom[s], *rC = h->geometry + 3 * centre;
+    const double x = rC[0] - rX[0], y = rC[1] - rX[1], z = rC[2] - rX[2];
+    ecp_shell_window(t, T->endLast, t->shellRadius[s], __builtin_sqrt(x * x + y * y + z * z), &start[s], &end[s], &skip[s]);
+  }
+  return 0;
+}
+
+int libecp_b200_host_table(libECPHandle *h, const char *name, const double **ptr) {
+  const EcpTables *t = h->tab;
+  const EcpHostTables *v = &t->v;
+  if (h->empty) return 0;
+  const int cdT = C_DIM(v->tmDim);
+#define RET(p, n) \
+  do {            \
+    *ptr = (p);   \
+    return (n);   \
+  } while (0)
+  if (!strcmp(name, "fac")) RET(t->fac, v->nfac);
+  if (!strcmp(name, "dfac")) RET(t->dfac, v->nfac);
+  if (!strcmp(name, "poly2sph")) RET(t->poly2sph, cdT * L_DIM(v->tmDim));
+  if (!strcmp(name, "omega")) RET(t->omega, v->nomega);
+  if (!strcmp(name, "small_x")) RET(t->small_x, ECP_SMALL_ORDER);
+  if (!strcmp(name, "small_w")) RET(t->small_w, ECP_SMALL_ORDER);
+  if (!strcmp(name, "large_x")) RET(t->large_x, v->largeOrder);
+  if (!strcmp(name, "large_w")) RET(t->large_w, v->largeOrder);
+  if (!strcmp(name, "bessel")) RET(t->besselK, (v->besselLMax + 1) * 1601);
+  if (!strcmp(name, "besselC")) RET(t->besselC, v->besselLMax + 1);
+  if (!strcmp(name, "shellRadius")) RET(t->shellRadius, v->nrShells);
+  if (!strcmp(name, "besselT")) RET(t->besselT, 1601 * v->besselStride);
+  if (!strcmp(name, "small_rs")) RET(t->small_rs, ECP_SMALL_SLOTS);
+  if (!strcmp(name, "small_ws")) RET(t->small_ws, ECP_SMALL_SLOTS);
+  if (!strcmp(name, "large_xs")) RET(t->large_xs, v->largeSlots);
+  if (!strcmp(name, "large_ws")) RET(t->large_ws, v->largeSlots);
+  if (!strcmp(name, "typeUtab")) RET(t->typeUtab, v->nTypes * v->maxLECP * v->nU * ECP_SMALL_SLOTS);
+  if (!strcmp(name, "typeUL")) RET(t->typeUL, v->nTypes * ECP_SMALL_SLOTS);
+#undef RET
+  *ptr = NULL;
+  return 0;
+}
+
+int libecp_b200_host_itable(libECPHandle *h, const char *name, int *out, int cap) {
+  const EcpTables *t = h->tab;
+  const EcpHostTables *v = &t->v;
+  int n = 0;
+  if (h->empty) return 0;
+#define PUT(x)              \
+  do {                      \
+    if (n < cap) out[n] = (x); \
+    n++;                    \
+  } while (0)
+  if (!strcmp(name, "small_oidx"))
+    for (int i = 0; i < ECP_SMALL_SLOTS; i++) PUT(t->small_oidx[i]);
+  else if (!strcmp(name, "large_oidx"))
+    for (int i = 0; i < v->largeSlots; i++) PUT(t->large_oidx[i]);
+  else if (!strcmp(name, "small_meta")) {
+    for (int i = 0; i < ECP_SMALL_LEVELS; i++) PUT(v->small_levPairs[i]);
+    for (int i = 0; i < ECP_SMALL_LEVELS; i++) PUT(v->small_levJ[i]);
+    for (int i = 0; i < ECP_SMALL_LEVELS; i++) PUT(v->small_levN[i]);
+    for (int i = 0; i <= ECP_SMALL_LEVELS; i++) PUT(v->small_levSlot[i]);
+  } else if (!strcmp(name, "dims")) {
+    PUT(v->maxLECP); PUT(v->maxLBS); PUT(v->maxAlpha); PUT(v->maxLambda); PUT(v->tmDim); PUT(v->besselLMax);
+    PUT(v->besselStride); PUT(v->largeOrder); PUT(v->largeSlots); PUT(v->largeLevels); PUT(v->nU); PUT(v->nTypes);
+    PUT(v->nClasses); PUT(v->maxQPerL); PUT(v->nrShells); PUT(v->nAO);
+  } else if (!strcmp(name, "ijk"))
+    for (int i = 0; i < 3 * C_DIM(v->tmDim); i++) PUT(t->ijk[i]);
+  else if (!strcmp(name, "ijkIndex"))
+    for (int i = 0; i < v->ijkDim * v->ijkDim * v->ijkDim; i++) PUT(t->ijkIndex[i]);
+  else if (!strcmp(name, "atomType"))
+    for (int i = 0; i < h->nrAtoms; i++) PUT(t->atomType[i]);
+#undef PUT
+  return n;
+}
+
+/* executed-triple list of the whole job in the reference's loop order (host only; tests):
+ * rows of 7 ints (A, s1, la, B, s2, lb, C); returns the count (fills at most cap rows) */
+long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap) {
+  long long n = 0;
+  int centre = 0;
+  if (h->empty) return 0;
+  EcpBatchBuf *bb = ecp_batch_new(h->tab);
+  while (ecp_batch_build(h->tab, h->geometry, &centre, 1 << 20, h->rank, h->world, 1, bb) > 0)
+    for (int k = 0; k < bb->nCanon; k++, n++)
+      if (n < cap) {
+        int *r = out + 7 * n;
+        r[0] = bb->cnA[k]; r[1] = bb->cnS1[k]; r[2] = bb->cnLa[k]; r[3] = bb->cnB[k];
+        r[4] = bb->cnS2[k]; r[5] = bb->cnLb[k]; r[6] = bb->cnC[k];
+      }
+  ecp_batch_free(bb);
+  return n;
+}
+
+int libecp_b200_debug_fetch(libECPHandle *h, const char *what, double *dst, long long n) {
+  if (h->empty || !h->dev) return -1;
+  return ecpdev_debug_fetch(h->dev, what, dst, n);
+}
+
+/* libint Cartesian ordering (reference src/dimensions.c:17-57) */
+int *cartesianShellOrder(const int am) {
+  int *t = calloc(3 * C_DIM(am), sizeof(int));
+  for (int l = 0; l <= am; l++) {
+    int c = 0;
+    for (int i = 0; i <= l; i++)
+      for (int j = 0; j <= i; j++, c++) {
+        int *e = t + CIJK_INDEX(l, c);
+        e[0] = l - i;
+        e[1] = i - j;
+        e[2] = j;
+      }
+  }
+  return t;
+}
+int *cartesianShellOrderIndex(const int am, int *ijk) {
+  const int dim = am + 1;
+  int *t = calloc(dim * dim * dim, sizeof(int));
+  for (int l = 0; l <= am; l++)
+    for (int c = 0; c < IJK_DIM(l); c++) {
+      const int *e = ijk + CIJK_INDEX(l, c);
+      t[e[0] * dim * dim + e[1] * dim + e[2]] = C_INDEX(l, c);
+    }
+  return t;
+}

@@ -1,0 +1,51 @@
+/* builder.h - host batch builder: replaces the loop nest of calculateECPIntegrals
+ * (reference src/libecp.c:256-397) and the screening of calcF_FM06 (src/type2.c:246-260).
+ * All integer screening decisions (skip flags, windows, executed-triple list) are taken here, on the
+ * host, in double precision with the reference's comparisons - bit-exact by construction. */
+#ifndef ECP_BUILDER_H
+#define ECP_BUILDER_H
+
+#include "tables.h"
+
+typedef struct {
+  EcpBatch b; /* view for the CUDA layer */
+  /* owned storage behind the view */
+  int *asAtom, *asCentre, *asType;
+  double *asR;
+  int64_t *asOmOff;
+  int *ssShell, *ssASlot, *ssStart, *ssEnd;
+  int64_t *ssFOff;
+  int *trA, *trB, *trClass;
+  int64_t *trOut, *trT, *trG, *trPair;
+  int *prTriple;
+  int64_t *prQOff, *prRshOff;
+  int *clsFirst;
+  int64_t *clsWork, *clsElem, *clsOutElem;
+  int capAS, capSS, capTR, capPR;
+  /* canonical (reference loop order) list of the executed triples of this batch, for callback replay */
+  int nCanon, capCanon;
+  int *cnA, *cnS1, *cnB, *cnS2, *cnC, *cnLa, *cnLb;
+  int64_t *cnOut;
+  /* statistics */
+  long long nominal, screenedShells;
+  /* scratch */
+  int *scratchSlot;   /* [nrShells] shell -> shell slot of the current centre, or -1 */
+  int *scratchList;
+} EcpBatchBuf;
+
+EcpBatchBuf *ecp_batch_new(const EcpTables *t);
+void ecp_batch_free(EcpBatchBuf *bb);
+
+/* Build one batch starting at atom index *centre (advanced past the centres consumed).  Stops adding centres
+ * once the batch holds >= maxTriples triples (always takes at least one centre).  Only shell pairs owned by
+ * (rank, world) are emitted (world = 1: everything).  keepCanon != 0 records the canonical list.
+ * Returns the number of centres consumed (0 = no ECP centre left). */
+int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
+                    int keepCanon, EcpBatchBuf *bb);
+
+/* exposed for tests: window of one (centre type, shell radius, distance) (reference src/type2.c:148-180) */
+void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip);
+/* owner rank of a shell pair under the multi-GPU partition */
+int ecp_pair_owner(int shellA, int shellB, int world);
+
+#endif

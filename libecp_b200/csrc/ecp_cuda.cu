@@ -1,0 +1,1163 @@
+/* ecp_cuda.cu - hand-written FP64 sm_100a kernels for the ECP hot path + the thin C-ABI device layer.
+ *
+ * Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+ * (-fmad=false: decisions such as Bessel node index, exponent gates and convergence tests are taken on
+ *  the same doubles as the reference takes them; see ecp_math.h).
+ *
+ * Kernel map (reference code each one replaces, paths relative to /root/reference):
+ *   k_atomslot   S_lm(r_XC) and (-x)^i(-y)^j(-z)^k per (C, atom)          src/util.c:214-243, spherical_harmonics.c
+ *   k_omegaX     Omega_X = sum_mu S_lam,mu Omega per (C, atom)            src/angular_integrals.c:104-142
+ *   k_Ftab       contracted radial table F_lambda(r_n) per (C, shell)     src/type2.c:284-303
+ *   k_fastT      type-2 fast path, PS93 on Fa*Fb*r^N U_l                  src/type2.c:336-381
+ *   k_fallbackT  type-2 large-grid fallback, PSM92 per primitive pair     src/type2.c:417-528
+ *   k_link       gamma = sum Omega_A Omega_B T                            src/type2.c:583-623
+ *   k_t1prep     P, |P|, S_lm(P^) per primitive pair                      src/type1.c:249-252
+ *   k_type1Q     radial Q(N,lambda): PS93 small grid, PSM92 fallback      src/type1.c:94-208
+ *   k_chi        chi = sum (S.poly2sph) Q                                 src/type1.c:266-295
+ *   k_shift      binomial shift to A/B, x4pi / x16pi^2, block + matrix    src/util.c:246-334, getIntegrals.c:22-43
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ecp_dev.h"
+#include "ecp_math.h"
+
+#define KM ECP_KMAX
+#define ROWSTRIDE 37 /* doubles per tabulated point row in shared memory (odd -> conflict-free lane rows) */
+#define ROW_W 0
+#define ROW_CU 1
+#define ROW_EX 2
+#define ROW_RN 3            /* rn[0..KM]  */
+#define ROW_KA (3 + KM + 1) /* Ka[0..KM]  */
+#define ROW_KB (3 + 2 * (KM + 1))
+#if (3 + 3 * (KM + 1)) > ROWSTRIDE
+#error row too small
+#endif
+
+static char g_err[512] = "";
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      snprintf(g_err, sizeof(g_err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return (int)e_;                                                                              \
+    }                                                                                              \
+  } while (0)
+
+/* device-side view of all tables of a handle + the current batch */
+struct DevT {
+  int maxLECP, maxLBS, maxLambda, tmDim, ijkDim, besselStride, nU, pcols;
+  int largeSlots, largeLevels, nClasses, omD2, omD3;
+  double tolerance, accuracy, lnAcc1, lnAcc2;
+  EcpSmallMeta sm;
+  const double *fac, *dfac, *poly2sph, *omega, *binom;
+  const int *ijk, *ijkIndex;
+  const double *small_r, *small_w, *large_x, *large_w;
+  const int16_t *small_oidx;
+  const double *besselT, *besselC;
+  const int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO, *atomMaxL;
+  const double *primD, *primA;
+  const int *typeL, *typeGaussOff, *gaussL;
+  const double *gaussN, *gaussD, *gaussA, *typeUtab, *typeUL;
+  const int *clsLa, *clsLb, *clsL, *clsNq, *clsQOff, *clsQlOff, *qlist, *clsQidxOff;
+  const int16_t *qidx;
+  int nAO;
+};
+struct DevB {
+  int nASlots, nSSlots, nTriples;
+  long long nPairs;
+  const int *asAtom, *asType;
+  const double *asR;
+  const long long *asOmOff;
+  const int *ssShell, *ssASlot, *ssStart, *ssEnd;
+  const long long *ssFOff;
+  const int *trA, *trB, *trClass;
+  const long long *trOut, *trT, *trG, *trPair;
+  const int *prTriple;
+  const long long *prQOff, *prRshOff;
+  const int *clsFirst;
+  const long long *clsWork, *clsElem, *clsOutElem;
+  /* intermediates */
+  double *rshX, *uspX, *omX, *F, *T, *gamma, *chi, *Q, *rshP, *sP, *blocks, *matrix;
+  unsigned char *tfail;
+  int *tflags, *items;
+  int *counters; /* [0] nItems [1] work counter [2] err1 [3] err2 [4] nFastFail [5] nType1Fail [6] stale [7] work2 */
+};
+#define RSHX_STRIDE 121
+#define USPX_STRIDE 216
+
+/* ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int find_class(const long long *prefix, int nc, long long w) {
+  int lo = 0, hi = nc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= w)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+/* ---- per (C, atom) : S_lm(r^_XC) and unit-sphere monomials ---- */
+__global__ void k_atomslot(DevT t, DevB b) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= b.nASlots) return;
+  const double x = b.asR[4 * a], y = b.asR[4 * a + 1], z = b.asR[4 * a + 2];
+  const int lX = t.atomMaxL[b.asAtom[a]];
+  const int lmax = t.maxLECP - 1 + lX; /* reference src/angular_integrals.c:110 */
+  double r, th, ph;
+  ecp_sphcoord(x, y, z, &r, &th, &ph);
+  ecp_rsh(lmax, th, ph, t.fac, t.dfac, b.rshX + (size_t)a * RSHX_STRIDE);
+  /* (-x)^i (-y)^j (-z)^k, reference src/util.c:214-243 */
+  double *u = b.uspX + (size_t)a * USPX_STRIDE;
+  const int dim = lX + 1;
+  double px = 0, py = 0, pz = 0;
+  for (int i = 0; i <= lX; i++) {
+    px = (i == 0) ? 1.0 : -px * x;
+    for (int j = 0; j <= lX - i; j++) {
+      py = (j == 0) ? 1.0 : -py * y;
+      for (int k = 0; k <= lX - i - j; k++) {
+        pz = (k == 0) ? 1.0 : -pz * z;
+        u[i * dim * dim + j * dim + k] = px * py * pz;
+      }
+    }
+  }
+}
+
+/* ---- Omega_X[lambda][(l,m)][C_INDEX(a,c)], one block per atom slot ---- */
+__global__ void k_omegaX(DevT t, DevB b) {
+  const int a = blockIdx.x;
+  const int lX = t.atomMaxL[b.asAtom[a]];
+  const int Lc = t.typeL[b.asType[a]];
+  const int nlam = Lc + lX, nlm = Lc * Lc, ncd = ecp_cd(lX);
+  const double *rsh = b.rshX + (size_t)a * RSHX_STRIDE;
+  double *out = b.omX + b.asOmOff[a];
+  const int total = nlam * nlm * ncd;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = e % ncd, lm = (e / ncd) % nlm, lam = e / (ncd * nlm);
+    double v = 0.0;
+    const double *om = t.omega + ((size_t)lm * t.omD2 + lam * lam) * t.omD3 + c;
+    for (int mu = 0; mu < 2 * lam + 1; mu++) v += rsh[lam * lam + mu] * om[(size_t)mu * t.omD3];
+    out[e] = v;
+  }
+}
+
+/* ---- F_lambda(r_n) per shell slot; one block of 384 threads per slot ---- */
+__global__ void __launch_bounds__(ECP_SMALL_SLOTS) k_Ftab(DevT t, DevB b) {
+  const int ss = blockIdx.x, k = threadIdx.x;
+  const int sh = b.ssShell[ss], as = b.ssASlot[ss];
+  const int Lc = t.typeL[b.asType[as]];
+  const int lmaxA = Lc - 1 + t.shellL[sh];
+  const double dAC = b.asR[4 * as + 3];
+  const int oi = t.small_oidx[k];
+  double acc[KM + 1];
+#pragma unroll
+  for (int i = 0; i <= KM; i++) acc[i] = 0.0;
+  if (oi >= b.ssStart[ss] && oi < b.ssEnd[ss]) { /* exclusive end: src/type2.c:292 */
+    const double r = t.small_r[k];
+    const int p0 = t.shellPrim[sh], np = t.shellK[sh];
+    for (int p = 0; p < np; p++) {
+      const double zeta = t.primA[p0 + p], da = t.primD[p0 + p];
+      double K[KM + 1];
+      ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lmaxA, 2.0 * zeta * dAC * r, K);
+      double e = dAC - r;
+      e = exp(-zeta * e * e);
+#pragma unroll
+      for (int i = 0; i <= KM; i++)
+        if (i <= lmaxA) acc[i] += da * K[i] * e;
+    }
+  }
+  double *F = b.F + (size_t)b.ssFOff[ss] * ECP_SMALL_SLOTS + k;
+#pragma unroll
+  for (int i = 0; i <= KM; i++)
+    if (i <= lmaxA) F[(size_t)i * ECP_SMALL_SLOTS] = acc[i];
+}
+
+/* ---- type-2 fast path: one thread per used quadrature ---- */
+__global__ void k_fastT(DevT t, DevB b, long long nWork) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nWork) return;
+  const int c = find_class(b.clsWork, t.nClasses, w);
+  const int nq = t.clsNq[c];
+  const long long idx = w - b.clsWork[c];
+  const int tri = b.clsFirst[c] + (int)(idx / nq), k = (int)(idx % nq);
+  const int q = t.qlist[t.clsQOff[c] + k];
+  const int l = q & 15, l1 = (q >> 4) & 15, l2 = (q >> 8) & 15, l3 = (q >> 12) & 15;
+  const int sa = b.trA[tri], sb = b.trB[tri];
+  const int type = b.asType[b.ssASlot[sa]];
+  const double *Fa = b.F + ((size_t)b.ssFOff[sa] + l1) * ECP_SMALL_SLOTS;
+  const double *Fb = b.F + ((size_t)b.ssFOff[sb] + l2) * ECP_SMALL_SLOTS;
+  const double *U = t.typeUtab + (((size_t)type * t.maxLECP + l) * t.nU + l3) * ECP_SMALL_SLOTS;
+  const int gs = max(b.ssStart[sa], b.ssStart[sb]), ge = max(b.ssEnd[sa], b.ssEnd[sb]); /* src/libecp.c:315-316 */
+  double res = 0.0;
+  const int rc = ecp_ps93_fastT(Fa, Fb, U, t.small_w, t.small_oidx, &t.sm, gs, ge, t.tolerance, &res, (int *)0);
+  const long long o = b.trT[tri] + k;
+  if (rc) {
+    b.T[o] = 0.0;
+    b.tfail[o] = 1;
+    atomicAdd(&b.counters[4], 1);
+    const int old = atomicOr(&b.tflags[tri], 1 << l);
+    if (!(old & (1 << l))) b.items[atomicAdd(&b.counters[0], 1)] = tri * 8 + l;
+  } else {
+    b.T[o] = res;
+    b.tfail[o] = 0;
+  }
+}
+
+/* ---- shared-memory row helpers for the warp-cooperative quadrature kernels ---- */
+struct WarpSmem {
+  double *rows; /* [32][ROWSTRIDE] */
+  double *sI, *sP, *sQ, *sAcc;
+  int *qk;
+  unsigned char *done;
+};
+__device__ __forceinline__ WarpSmem carve(unsigned char *base, int maxq) {
+  WarpSmem s;
+  s.rows = (double *)base;
+  s.sI = s.rows + 32 * ROWSTRIDE;
+  s.sP = s.sI + maxq;
+  s.sQ = s.sP + maxq;
+  s.sAcc = s.sQ + maxq;
+  s.qk = (int *)(s.sAcc + maxq);
+  s.done = (unsigned char *)(s.qk + maxq);
+  return s;
+}
+static size_t warp_smem_bytes(int maxq) {
+  return (size_t)32 * ROWSTRIDE * 8 + (size_t)maxq * 8 * 4 + (size_t)maxq * 4 + (size_t)maxq + 16;
+}
+
+/* ---- type-2 fallback: one warp per (triple, l) with failed small-grid quadratures ---- */
+__global__ void __launch_bounds__(32) k_fallbackT(DevT t, DevB b, int maxq) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const WarpSmem s = carve(smem_raw, maxq);
+  const int lane = threadIdx.x;
+  const int nItems = b.counters[0];
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(&b.counters[1], 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= nItems) break;
+    const int item = b.items[it];
+    const int tri = item >> 3, l = item & 7;
+    const int c = b.trClass[tri];
+    const int la = t.clsLa[c], lb = t.clsLb[c];
+    const int laC = la + l, lbC = lb + l, lab = la + lb;
+    const int k0 = t.clsQlOff[c * (ECP_MAX_LECP + 1) + l], k1 = t.clsQlOff[c * (ECP_MAX_LECP + 1) + l + 1];
+    const long long tOff = b.trT[tri];
+    const int *ql = t.qlist + t.clsQOff[c];
+    /* gather the failed quadratures of this (triple, l) */
+    int nf = 0;
+    for (int base = k0; base < k1; base += 32) {
+      const int k = base + lane;
+      const int f = (k < k1) && b.tfail[tOff + k];
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (f) s.qk[nf + __popc(m & ((1u << lane) - 1))] = k;
+      nf += __popc(m);
+    }
+    for (int q = lane; q < nf; q += 32) s.sAcc[q] = 0.0;
+    __syncwarp();
+    const int ssa = b.trA[tri], ssb = b.trB[tri];
+    const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
+    const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
+    const double dAC = b.asR[4 * asa + 3], dBC = b.asR[4 * asb + 3];
+    const int type = b.asType[asa];
+    const int g0 = t.typeGaussOff[type], g1 = t.typeGaussOff[type + 1];
+    const int Na = t.shellK[sha], Nb = t.shellK[shb];
+    const double *za = t.primA + t.shellPrim[sha], *ca = t.primD + t.shellPrim[sha];
+    const double *zb = t.primA + t.shellPrim[shb], *cb = t.primD + t.shellPrim[shb];
+    bool failed = false;
+    for (int pa = 0; pa < Na; pa++) {
+      const double s1 = 2.0 * za[pa] * dAC;
+      for (int pb = 0; pb < Nb; pb++) {
+        const double s2 = 2.0 * zb[pb] * dBC;
+        const double Cc = ca[pa] * cb[pb];
+        const double zp = za[pa] + zb[pb];
+        const double P = (za[pa] * dAC + zb[pb] * dBC) / zp;
+        double i1, i2;
+        ecp_fm06_map(zp, P, &i1, &i2);
+        int curChunk = -1;
+        int n = 1;
+        for (int lev = 0; lev <= t.largeLevels; lev++) {
+          /* level 0 = centre point (slot 0); level v>=1 = slots [2^v, 2^(v+1)) */
+          const int sl0 = (lev == 0) ? 0 : (1 << lev), sl1 = (lev == 0) ? 2 : (2 << lev);
+          if (lev > 0) {
+            int alldone = 1;
+            for (int q = lane; q < nf; q += 32) alldone &= s.done[q];
+            if (__all_sync(0xffffffffu, alldone)) break;
+            for (int q = lane; q < nf; q += 32)
+              if (!s.done[q]) { /* q = 2p; p = 2I  (src/gc_integrators.c:56-57) */
+                s.sQ[q] = 2 * s.sP[q];
+                s.sP[q] = 2 * s.sI[q];
+              }
+          }
+          for (int ch = sl0 >> 5; ch <= (sl1 - 1) >> 5; ch++) {
+            if (ch != curChunk) {
+              __syncwarp();
+              /* tabulate 32 slots: r, exponent gate, U_l, K_a, K_b, r^n  (src/type2.c:471-495) */
+              const int slot = ch * 32 + lane;
+              double *row = s.rows + lane * ROWSTRIDE;
+              const double x = t.large_x[slot];
+              const double r = i1 * x + i2;
+              const double d1 = dAC - r, d2 = dBC - r;
+              const double e = -za[pa] * d1 * d1 - zb[pb] * d2 * d2;
+              const bool live = (slot != 1) && (e >= t.lnAcc2);
+              if (slot == 0 && r > dAC && r > dBC && e < t.lnAcc2) atomicAdd(&b.counters[6], 1);
+              if (live) {
+                double Ka[KM + 1], Kb[KM + 1];
+                const double U = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, l, r);
+                ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, laC, s1 * r, Ka);
+                ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lbC, s2 * r, Kb);
+                row[ROW_W] = t.large_w[slot] * i1;
+                row[ROW_CU] = Cc * U;
+                row[ROW_EX] = exp(e);
+                double rn = 1.0;
+#pragma unroll
+                for (int i = 0; i <= KM; i++) {
+                  row[ROW_RN + i] = rn;
+                  rn = r * rn;
+                  row[ROW_KA + i] = (i <= laC) ? Ka[i] : 0.0;
+                  row[ROW_KB + i] = (i <= lbC) ? Kb[i] : 0.0;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 3 + 3 * (KM + 1); i++) row[i] = 0.0;
+              }
+              curChunk = ch;
+              __syncwarp();
+            }
+            const int lo = max(sl0, ch * 32) - ch * 32, hi = min(sl1, ch * 32 + 32) - ch * 32;
+            for (int q = lane; q < nf; q += 32) {
+              if (lev > 0 && s.done[q]) continue;
+              const int qq = ql[s.qk[q]];
+              const int l1 = (qq >> 4) & 15, l2 = (qq >> 8) & 15, l3 = (qq >> 12) & 15;
+              if (lev == 0) {
+                const double *row = s.rows;
+                const double Qv = row[ROW_CU] * row[ROW_RN + l3] * row[ROW_KA + l1] * row[ROW_KB + l2] * row[ROW_EX];
+                const double I0 = row[ROW_W] * Qv;
+                s.sI[q] = I0;
+                s.sP[q] = I0;
+                s.done[q] = 0;
+              } else {
+                double I = s.sI[q];
+                for (int sidx = lo; sidx < hi; sidx += 2) {
+                  const double *rl = s.rows + sidx * ROWSTRIDE, *rr = rl + ROWSTRIDE;
+                  double T = 0.0;
+                  T += rl[ROW_W] * (rl[ROW_CU] * rl[ROW_RN + l3] * rl[ROW_KA + l1] * rl[ROW_KB + l2] * rl[ROW_EX]);
+                  T += rr[ROW_W] * (rr[ROW_CU] * rr[ROW_RN + l3] * rr[ROW_KA + l1] * rr[ROW_KB + l2] * rr[ROW_EX]);
+                  I += T;
+                }
+                s.sI[q] = I;
+              }
+            }
+          }
+          if (lev > 0) {
+            n = 2 * n + 1;
+            for (int q = lane; q < nf; q += 32) {
+              if (s.done[q]) continue;
+              double res;
+              if (ecp_psm92_update(n, 1, t.tolerance, s.sI[q], s.sP[q], s.sQ[q], &res)) {
+                s.sAcc[q] += res; /* T += grid->I, primitive pairs in reference order (src/type2.c:513) */
+                s.done[q] = 1;
+              }
+            }
+          }
+        }
+        int alldone = 1;
+        for (int q = lane; q < nf; q += 32) alldone &= s.done[q];
+        if (!__all_sync(0xffffffffu, alldone)) failed = true;
+        __syncwarp();
+      }
+    }
+    for (int q = lane; q < nf; q += 32) b.T[tOff + s.qk[q]] = s.sAcc[q];
+    if (failed && lane == 0) atomicExch(&b.counters[3], 2);
+    __syncwarp();
+  }
+}
+
+/* ---- link: gamma[p][q], one thread per element ---- */
+__device__ __forceinline__ int deg_of_cindex(int p) {
+  int l = 0;
+  while (ecp_cd(l) <= p) l++;
+  return l;
+}
+__global__ void k_link(DevT t, DevB b, long long nElem) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nElem) return;
+  const int c = find_class(b.clsElem, t.nClasses, w);
+  const int la = t.clsLa[c], lb = t.clsLb[c], L = t.clsL[c];
+  const int cda = ecp_cd(la), cdb = ecp_cd(lb);
+  const long long idx = w - b.clsElem[c];
+  const int tri = b.clsFirst[c] + (int)(idx / (cda * cdb));
+  const int pq = (int)(idx % (cda * cdb)), p = pq / cdb, q = pq % cdb;
+  const int alpha = deg_of_cindex(p), beta = deg_of_cindex(q);
+  const int ssa = b.trA[tri], ssb = b.trB[tri];
+  const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
+  const int lXa = t.atomMaxL[b.asAtom[asa]], lXb = t.atomMaxL[b.asAtom[asb]];
+  const int incA1 = ecp_cd(lXa), incA2 = L * L * incA1;
+  const int incB1 = ecp_cd(lXb), incB2 = L * L * incB1;
+  const double *oA = b.omX + b.asOmOff[asa] + p, *oB = b.omX + b.asOmOff[asb] + q;
+  const double *T = b.T + b.trT[tri];
+  const int16_t *qi = t.qidx + t.clsQidxOff[c];
+  const int d1 = la + L, d2 = lb + L, d3 = la + lb + 1;
+  double g = 0.0;
+  for (int l = 0; l < L; l++) {
+    int ll1 = l - alpha, ll2 = l - beta;
+    const int par1 = (alpha + l) % 2, par2 = (beta + l) % 2;
+    ll1 = (par1 > ll1) ? par1 : ll1;
+    ll2 = (par2 > ll2) ? par2 : ll2;
+    double tmp = 0.0;
+    for (int l1 = ll1; l1 <= la + l; l1 += 2)
+      for (int l2 = ll2; l2 <= lb + l; l2 += 2) {
+        const int k = qi[((l * d1 + l1) * d2 + l2) * d3 + alpha + beta];
+        if (k < 0) continue; /* angular factor identically zero */
+        double factor = 0.0;
+        for (int m = 0; m < 2 * l + 1; m++)
+          factor += oA[(size_t)l1 * incA2 + (l * l + m) * incA1] * oB[(size_t)l2 * incB2 + (l * l + m) * incB1];
+        tmp += factor * T[k];
+      }
+    g += tmp;
+  }
+  b.gamma[b.trG[tri] + pq] = g;
+}
+
+/* ---- type 1, per primitive pair: P = 2(za r_AC + zb r_BC), |P|, S_lm(P^) ---- */
+__global__ void k_t1prep(DevT t, DevB b) {
+  const long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pr >= b.nPairs) return;
+  const int tri = b.prTriple[pr];
+  const int ssa = b.trA[tri], ssb = b.trB[tri];
+  const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
+  const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
+  const int Nb = t.shellK[shb];
+  const int ip = (int)(pr - b.trPair[tri]), pa = ip / Nb, pb = ip % Nb;
+  const double za = t.primA[t.shellPrim[sha] + pa], zb = t.primA[t.shellPrim[shb] + pb];
+  const double *rA = b.asR + 4 * asa, *rB = b.asR + 4 * asb;
+  const double Px = 2.0 * (za * rA[0] + zb * rB[0]);
+  const double Py = 2.0 * (za * rA[1] + zb * rB[1]);
+  const double Pz = 2.0 * (za * rA[2] + zb * rB[2]);
+  double r, th, ph;
+  ecp_sphcoord(Px, Py, Pz, &r, &th, &ph);
+  const int lab = t.shellL[sha] + t.shellL[shb];
+  ecp_rsh(lab, th, ph, t.fac, t.dfac, b.rshP + b.prRshOff[pr]);
+  b.sP[pr] = r;
+}
+
+/* ---- type 1 radial integrals: one warp per primitive pair ---- */
+__global__ void __launch_bounds__(32) k_type1Q(DevT t, DevB b, int maxq) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const WarpSmem s = carve(smem_raw, maxq);
+  const int lane = threadIdx.x;
+  for (;;) {
+    long long pr = 0;
+    if (lane == 0) pr = atomicAdd(&b.counters[7], 1);
+    pr = __shfl_sync(0xffffffffu, pr, 0);
+    if (pr >= b.nPairs) break;
+    const int tri = b.prTriple[pr];
+    const int ssa = b.trA[tri], ssb = b.trB[tri];
+    const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
+    const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
+    const int Nb = t.shellK[shb];
+    const int ip = (int)(pr - b.trPair[tri]), pa = ip / Nb, pb = ip % Nb;
+    const double za = t.primA[t.shellPrim[sha] + pa], zb = t.primA[t.shellPrim[shb] + pb];
+    const double ca = t.primD[t.shellPrim[sha] + pa], cb = t.primD[t.shellPrim[shb] + pb];
+    const double dAC = b.asR[4 * asa + 3], dBC = b.asR[4 * asb + 3];
+    const int type = b.asType[asa];
+    const int Lc = t.typeL[type];
+    const int g0 = t.typeGaussOff[type], g1 = t.typeGaussOff[type + 1];
+    const int lab = t.shellL[sha] + t.shellL[shb];
+    const double sS = b.sP[pr];
+    const int gs = max(b.ssStart[ssa], b.ssStart[ssb]), ge = max(b.ssEnd[ssa], b.ssEnd[ssb]);
+    const double zd2 = -za * dAC * dAC - zb * dBC * dBC; /* src/type1.c:103 */
+    const double z = -za - zb;
+    const double *UL = t.typeUL + (size_t)type * ECP_SMALL_SLOTS;
+    /* quadrature list in the reference's order: N = 0..lab, lambda = N, N-2, ... (src/type1.c:132-135) */
+    int nq = 0;
+    for (int N = 0; N <= lab; N++) nq += N / 2 + 1;
+    for (int q = lane; q < nq; q += 32) {
+      int N = 0, base = 0;
+      while (base + N / 2 + 1 <= q) {
+        base += N / 2 + 1;
+        N++;
+      }
+      s.qk[q] = N | ((N - 2 * (q - base)) << 8);
+      s.done[q] = 0;
+      s.sAcc[q] = 0.0;
+    }
+    __syncwarp();
+    /* ---------- 1. small grid, PS93 (src/type1.c:121-146) ---------- */
+    {
+      const double Cc = ca * cb * exp(zd2);
+      int curChunk = -1;
+      for (int lev = -1; lev < ECP_SMALL_LEVELS; lev++) {
+        /* lev -1 = the three unconditional points (slots 0,2,3) */
+        const int sl0 = (lev < 0) ? 0 : t.sm.levSlot[lev], sl1 = (lev < 0) ? 4 : t.sm.levSlot[lev + 1];
+        if (lev >= 0) {
+          int alldone = 1;
+          for (int q = lane; q < nq; q += 32) alldone &= (s.done[q] != 0);
+          if (__all_sync(0xffffffffu, alldone)) break;
+        }
+        int cnt = 0;
+        for (int ch = sl0 >> 5; ch <= (sl1 - 1) >> 5; ch++) {
+          if (ch != curChunk) {
+            __syncwarp();
+            const int slot = ch * 32 + lane;
+            double *row = s.rows + lane * ROWSTRIDE;
+            const int oi = t.small_oidx[slot];
+            if (oi >= gs && oi < ge) { /* tabulated range is [start,end): src/type1.c:121 */
+              const double r = t.small_r[slot];
+              double K[KM + 1];
+              ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lab, sS * r, K);
+              const double e = (z * r + sS) * r;
+              row[ROW_W] = t.small_w[slot];
+              row[ROW_CU] = UL[slot];
+              row[ROW_EX] = (e >= t.lnAcc1) ? exp(e) : 0.0;
+              row[ROW_KB] = (e >= t.lnAcc1) ? 1.0 : 0.0; /* gate flag */
+              double rn = 1.0;
+#pragma unroll
+              for (int i = 0; i <= KM; i++) {
+                row[ROW_RN + i] = rn;
+                rn = r * rn;
+                row[ROW_KA + i] = (i <= lab) ? K[i] : 0.0;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 3 + 3 * (KM + 1); i++) row[i] = 0.0;
+              row[ROW_W] = (oi >= 0) ? t.small_w[slot] : 0.0;
+            }
+            curChunk = ch;
+            __syncwarp();
+          }
+          const int lo = max(sl0, ch * 32) - ch * 32, hi = min(sl1, ch * 32 + 32) - ch * 32;
+          /* window flags of this level's points (uniform over the warp) */
+          if (lev >= 0)
+            for (int sidx = lo; sidx < hi; sidx += 2) {
+              cnt += (t.small_oidx[ch * 32 + sidx] >= gs);
+              cnt += (t.small_oidx[ch * 32 + sidx + 1] <= ge);
+            }
+          for (int q = lane; q < nq; q += 32) {
+            if (s.done[q]) continue;
+            const int N = s.qk[q] & 255, lam = s.qk[q] >> 8;
+#define T1VAL(rw) ((rw)[ROW_KB] != 0.0 ? Cc * (rw)[ROW_RN + N] * (rw)[ROW_CU] * (rw)[ROW_KA + lam] * (rw)[ROW_EX] : 0.0)
+            if (lev < 0) {
+              const double *r0 = s.rows, *r2 = s.rows + 2 * ROWSTRIDE, *r3 = s.rows + 3 * ROWSTRIDE;
+              const double p = r0[ROW_W] * T1VAL(r0);
+              const double qv = r2[ROW_W] * T1VAL(r2) + r3[ROW_W] * T1VAL(r3);
+              s.sP[q] = p;
+              s.sQ[q] = qv;
+              s.sI[q] = p + qv;
+            } else {
+              double I = s.sI[q];
+              for (int sidx = lo; sidx < hi; sidx += 2) {
+                const double *rl = s.rows + sidx * ROWSTRIDE, *rr = rl + ROWSTRIDE;
+                double T = 0.0;
+                if (t.small_oidx[ch * 32 + sidx] >= gs) T += rl[ROW_W] * T1VAL(rl);
+                if (t.small_oidx[ch * 32 + sidx + 1] <= ge) T += rr[ROW_W] * T1VAL(rr);
+                I += T;
+              }
+              s.sI[q] = I;
+            }
+          }
+        }
+        if (lev >= 0) {
+          for (int q = lane; q < nq; q += 32) {
+            if (s.done[q]) continue;
+            double p = s.sP[q], qv = s.sQ[q], res;
+            if (ecp_ps93_update(t.sm.levJ[lev], t.sm.levN[lev], cnt, t.tolerance, s.sI[q], &p, &qv, &res)) {
+              s.sAcc[q] = res;
+              s.done[q] = 1;
+            }
+            s.sP[q] = p;
+            s.sQ[q] = qv;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    /* ---------- 2. failed ones on the mapped large grid, PSM92 (src/type1.c:149-196) ---------- */
+    int anyfail = 0;
+    for (int q = lane; q < nq; q += 32) anyfail |= (s.done[q] == 0);
+    anyfail = __any_sync(0xffffffffu, anyfail);
+    if (anyfail) {
+      if (lane == 0) atomicAdd(&b.counters[5], 1);
+      const double Cc = ca * cb;
+      const double zp = za + zb;
+      const double P = (za * dAC + zb * dBC) / zp;
+      double i1, i2;
+      ecp_fm06_map(zp, P, &i1, &i2);
+      /* done: 0 = needs large grid, 1 = converged on small grid, 2 = converged on large grid */
+      int curChunk = -1, n = 1;
+      for (int lev = 0; lev <= t.largeLevels; lev++) {
+        const int sl0 = (lev == 0) ? 0 : (1 << lev), sl1 = (lev == 0) ? 2 : (2 << lev);
+        if (lev > 0) {
+          int alldone = 1;
+          for (int q = lane; q < nq; q += 32) alldone &= (s.done[q] != 0);
+          if (__all_sync(0xffffffffu, alldone)) break;
+          for (int q = lane; q < nq; q += 32)
+            if (!s.done[q]) {
+              s.sQ[q] = 2 * s.sP[q];
+              s.sP[q] = 2 * s.sI[q];
+            }
+        }
+        for (int ch = sl0 >> 5; ch <= (sl1 - 1) >> 5; ch++) {
+          if (ch != curChunk) {
+            __syncwarp();
+            const int slot = ch * 32 + lane;
+            double *row = s.rows + lane * ROWSTRIDE;
+            const double x = t.large_x[slot];
+            const double r = i1 * x + i2;
+            const double e = (z * r + sS) * r + zd2; /* src/type1.c:162 */
+            const bool live = (slot != 1) && (e >= t.lnAcc1);
+            if (live) {
+              double K[KM + 1];
+              ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lab, sS * r, K);
+              row[ROW_W] = t.large_w[slot] * i1;
+              row[ROW_CU] = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, Lc, r);
+              row[ROW_EX] = exp(e);
+              double rn = 1.0;
+#pragma unroll
+              for (int i = 0; i <= KM; i++) {
+                row[ROW_RN + i] = rn;
+                rn = r * rn;
+                row[ROW_KA + i] = (i <= lab) ? K[i] : 0.0;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 3 + 3 * (KM + 1); i++) row[i] = 0.0;
+            }
+            curChunk = ch;
+            __syncwarp();
+          }
+          const int lo = max(sl0, ch * 32) - ch * 32, hi = min(sl1, ch * 32 + 32) - ch * 32;
+          for (int q = lane; q < nq; q += 32) {
+            if (s.done[q]) continue;
+            const int N = s.qk[q] & 255, lam = s.qk[q] >> 8;
+#define T1LVAL(rw) (Cc * (rw)[ROW_RN + N] * (rw)[ROW_CU] * (rw)[ROW_KA + lam] * (rw)[ROW_EX])
+            if (lev == 0) {
+              const double I0 = s.rows[ROW_W] * T1LVAL(s.rows);
+              s.sI[q] = I0;
+              s.sP[q] = I0;
+            } else {
+              double I = s.sI[q];
+              for (int sidx = lo; sidx < hi; sidx += 2) {
+                const double *rl = s.rows + sidx * ROWSTRIDE, *rr = rl + ROWSTRIDE;
+                double T = 0.0;
+                T += rl[ROW_W] * T1LVAL(rl);
+                T += rr[ROW_W] * T1LVAL(rr);
+                I += T;
+              }
+              s.sI[q] = I;
+            }
+          }
+        }
+        if (lev > 0) {
+          n = 2 * n + 1;
+          for (int q = lane; q < nq; q += 32) {
+            if (s.done[q]) continue;
+            double res;
+            if (ecp_psm92_update(n, 1, t.tolerance, s.sI[q], s.sP[q], s.sQ[q], &res)) {
+              s.sAcc[q] = res;
+              s.done[q] = 2;
+            }
+          }
+        }
+      }
+      int alldone = 1;
+      for (int q = lane; q < nq; q += 32) alldone &= (s.done[q] != 0);
+      if (!__all_sync(0xffffffffu, alldone) && lane == 0) atomicExch(&b.counters[2], 1);
+      __syncwarp();
+    }
+    /* Q[N][lambda] */
+    double *Qo = b.Q + b.prQOff[pr];
+    for (int q = lane; q < nq; q += 32) {
+      const int N = s.qk[q] & 255, lam = s.qk[q] >> 8;
+      Qo[N * (lab + 1) + lam] = s.sAcc[q];
+    }
+    __syncwarp();
+  }
+}
+
+/* ---- chi[i][j], one thread per element ---- */
+__global__ void k_chi(DevT t, DevB b, long long nElem) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nElem) return;
+  const int c = find_class(b.clsElem, t.nClasses, w);
+  const int la = t.clsLa[c], lb = t.clsLb[c], lab = la + lb;
+  const int cda = ecp_cd(la), cdb = ecp_cd(lb);
+  const long long idx = w - b.clsElem[c];
+  const int tri = b.clsFirst[c] + (int)(idx / (cda * cdb));
+  const int pq = (int)(idx % (cda * cdb)), i = pq / cdb, j = pq % cdb;
+  const int *ei = t.ijk + 3 * i, *ej = t.ijk + 3 * j;
+  const int lx = ei[0] + ej[0], ly = ei[1] + ej[1], lz = ei[2] + ej[2], lmax = lx + ly + lz;
+  const int D = t.ijkDim;
+  const int p = t.ijkIndex[lx * D * D + ly * D + lz];
+  const double *PM = t.poly2sph + (size_t)p * t.pcols;
+  const int ssa = b.trA[tri], ssb = b.trB[tri];
+  const int np = t.shellK[b.ssShell[ssa]] * t.shellK[b.ssShell[ssb]];
+  const long long pr0 = b.trPair[tri];
+  double chi = 0.0;
+  for (int ip = 0; ip < np; ip++) {
+    const double *rsh = b.rshP + b.prRshOff[pr0 + ip];
+    const double *Q = b.Q + b.prQOff[pr0 + ip] + lmax * (lab + 1);
+    for (int l = lmax; l >= 0; l -= 2) {
+      double factor = 0.0;
+      for (int m = 0; m < 2 * l + 1; m++) factor += rsh[l * l + m] * PM[l * l + m];
+      chi += factor * Q[l];
+    }
+  }
+  b.chi[b.trG[tri] + pq] = chi;
+}
+
+/* ---- shift to A/B-centred Cartesians, normalise, write blocks / accumulate matrix ---- */
+__device__ __forceinline__ double shift_one(const DevT &t, const double *G, int cdb, double N, const int *ea,
+                                            const int *eb, const double *uA, int dA, const double *uB, int dB) {
+  const int nb = t.maxLBS + 1, D = t.ijkDim;
+  double I = 0.0;
+  for (int bx = 0; bx <= eb[0]; bx++) {
+    const double bbx = t.binom[eb[0] * nb + bx];
+    for (int by = 0; by <= eb[1]; by++) {
+      const double bby = bbx * t.binom[eb[1] * nb + by];
+      for (int bz = 0; bz <= eb[2]; bz++) {
+        const double bbz = bby * t.binom[eb[2] * nb + bz];
+        double fB = bbz * uB[(eb[0] - bx) * dB * dB + (eb[1] - by) * dB + (eb[2] - bz)];
+        if (fabs(fB) <= t.accuracy) continue; /* src/util.c:318 */
+        fB *= N;
+        const int rb = t.ijkIndex[bx * D * D + by * D + bz];
+        /* J[c1][rb] = sum over alpha terms (src/util.c:270-299) */
+        double J = 0.0;
+        for (int ax = 0; ax <= ea[0]; ax++) {
+          const double bax = t.binom[ea[0] * nb + ax];
+          for (int ay = 0; ay <= ea[1]; ay++) {
+            const double bay = bax * t.binom[ea[1] * nb + ay];
+            for (int az = 0; az <= ea[2]; az++) {
+              const double baz = bay * t.binom[ea[2] * nb + az];
+              const double fA = baz * uA[(ea[0] - ax) * dA * dA + (ea[1] - ay) * dA + (ea[2] - az)];
+              if (fabs(fA) <= t.accuracy) continue; /* src/util.c:286 */
+              const int ra = t.ijkIndex[ax * D * D + ay * D + az];
+              J += fA * G[ra * cdb + rb];
+            }
+          }
+        }
+        I += fB * J;
+      }
+    }
+  }
+  return I;
+}
+
+__global__ void k_shift(DevT t, DevB b, long long nElem, int flags) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nElem) return;
+  const int c = find_class(b.clsOutElem, t.nClasses, w);
+  const int la = t.clsLa[c], lb = t.clsLb[c];
+  const int na = ecp_ijk(la), nb = ecp_ijk(lb), cdb = ecp_cd(lb);
+  const long long idx = w - b.clsOutElem[c];
+  const int tri = b.clsFirst[c] + (int)(idx / (na * nb));
+  const int cc = (int)(idx % (na * nb)), c1 = cc / nb, c2 = cc % nb;
+  const int ssa = b.trA[tri], ssb = b.trB[tri];
+  const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
+  const int dA = t.atomMaxL[b.asAtom[asa]] + 1, dB = t.atomMaxL[b.asAtom[asb]] + 1;
+  const double *uA = b.uspX + (size_t)asa * USPX_STRIDE, *uB = b.uspX + (size_t)asb * USPX_STRIDE;
+  const int *ea = t.ijk + 3 * ecp_cidx(la, c1), *eb = t.ijk + 3 * ecp_cidx(lb, c2);
+  const double n1 = 4.0 * M_PI, n2 = n1 * n1; /* src/libecp.c:234-235 */
+  const double I1 = shift_one(t, b.chi + b.trG[tri], cdb, n1, ea, eb, uA, dA, uB, dB);
+  const double I2 = shift_one(t, b.gamma + b.trG[tri], cdb, n2, ea, eb, uA, dA, uB, dB);
+  if (flags & 2) {
+    double *o = b.blocks + b.trOut[tri];
+    o[cc] = I1;
+    o[na * nb + cc] = I2;
+  }
+  if (flags & 1) {
+    const int row = t.shellAO[b.ssShell[ssa]] + c1, col = t.shellAO[b.ssShell[ssb]] + c2;
+    if (row <= col) atomicAdd(&b.matrix[(size_t)row * t.nAO + col], I1 + I2); /* src/getIntegrals.c:38-40 */
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* FP64 FMA peak probe (roofline denominator when no measured FP64 peak is published) */
+__global__ void k_fp64_probe(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+/* ================================================================================================ */
+/* host side of the device layer */
+struct Buf {
+  void *p;
+  size_t cap;
+};
+struct EcpDev {
+  int device, nSM;
+  cudaStream_t s1, s2;
+  cudaEvent_t ev[12];
+  DevT t;
+  DevB b;
+  int nClasses, maxQPerL, nAO, maxLBS;
+  Buf tab[64];
+  int ntab;
+  Buf asAtom, asType, asR, asOmOff, ssShell, ssASlot, ssStart, ssEnd, ssFOff, trA, trB, trClass, trOut, trT, trG, trPair;
+  Buf prTriple, prQOff, prRshOff, clsFirst, clsWork, clsElem, clsOutElem;
+  Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
+  double *matrix;
+  size_t lastSizes[8];
+};
+
+static int ensure(Buf *b, size_t bytes) {
+  if (bytes <= b->cap && b->p) return 0;
+  if (b->p) cudaFree(b->p);
+  b->p = NULL;
+  b->cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  CK(cudaMalloc(&b->p, want));
+  b->cap = want;
+  return 0;
+}
+template <typename T>
+static const T *upload_const(EcpDev *d, const T *h, size_t n) {
+  Buf *bf = &d->tab[d->ntab++];
+  bf->p = NULL;
+  bf->cap = 0;
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  if (cudaMalloc(&bf->p, bytes) != cudaSuccess) return NULL;
+  bf->cap = bytes;
+  if (n && cudaMemcpy(bf->p, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return NULL;
+  return (const T *)bf->p;
+}
+
+extern "C" const char *ecpdev_last_error(void) { return g_err; }
+
+extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    snprintf(g_err, sizeof(g_err), "libecp_b200: no CUDA device available (this library has no CPU path)");
+    return NULL;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "cudaSetDevice(%d) failed", device);
+    return NULL;
+  }
+  EcpDev *d = (EcpDev *)calloc(1, sizeof(EcpDev));
+  d->device = device;
+  cudaDeviceGetAttribute(&d->nSM, cudaDevAttrMultiProcessorCount, device);
+  cudaStreamCreateWithFlags(&d->s1, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&d->s2, cudaStreamNonBlocking);
+  for (int i = 0; i < 12; i++) cudaEventCreate(&d->ev[i]);
+  DevT &t = d->t;
+  t.maxLECP = h->maxLECP; t.maxLBS = h->maxLBS; t.maxLambda = h->maxLambda; t.tmDim = h->tmDim; t.ijkDim = h->ijkDim;
+  t.besselStride = h->besselStride; t.nU = h->nU; t.pcols = (h->tmDim + 1) * (h->tmDim + 1);
+  t.largeSlots = h->largeSlots; t.largeLevels = h->largeLevels; t.nClasses = h->nClasses;
+  t.omD2 = (h->maxLambda + 1) * (h->maxLambda + 1);
+  t.omD3 = (h->maxAlpha + 1) * (h->maxAlpha + 2) * (h->maxAlpha + 3) / 6;
+  t.tolerance = h->tolerance; t.accuracy = h->accuracy; t.lnAcc1 = h->lnAccuracy1; t.lnAcc2 = h->lnAccuracy2;
+  for (int i = 0; i < ECP_SMALL_LEVELS; i++) {
+    t.sm.levPairs[i] = h->small_levPairs[i];
+    t.sm.levJ[i] = h->small_levJ[i];
+    t.sm.levN[i] = h->small_levN[i];
+    t.sm.levSlot[i] = h->small_levSlot[i];
+  }
+  t.sm.levSlot[ECP_SMALL_LEVELS] = h->small_levSlot[ECP_SMALL_LEVELS];
+  const int cdT = (h->tmDim + 1) * (h->tmDim + 2) * (h->tmDim + 3) / 6;
+  t.fac = upload_const(d, h->fac, h->nfac);
+  t.dfac = upload_const(d, h->dfac, h->nfac);
+  t.poly2sph = upload_const(d, h->poly2sph, (size_t)cdT * t.pcols);
+  t.omega = upload_const(d, h->omega, h->nomega);
+  t.binom = upload_const(d, h->binom, (size_t)(h->maxLBS + 1) * (h->maxLBS + 1));
+  t.ijk = upload_const(d, h->ijk, (size_t)3 * cdT);
+  t.ijkIndex = upload_const(d, h->ijkIndex, (size_t)h->ijkDim * h->ijkDim * h->ijkDim);
+  t.small_r = upload_const(d, h->small_r, ECP_SMALL_SLOTS);
+  t.small_w = upload_const(d, h->small_w, ECP_SMALL_SLOTS);
+  t.small_oidx = upload_const(d, h->small_oidx, ECP_SMALL_SLOTS);
+  t.large_x = upload_const(d, h->large_x, h->largeSlots);
+  t.large_w = upload_const(d, h->large_w, h->largeSlots);
+  t.besselT = upload_const(d, h->besselT, (size_t)1601 * h->besselStride);
+  t.besselC = upload_const(d, h->besselC, h->besselLMax + 1);
+  t.shellL = upload_const(d, h->shellL, h->nrShells);
+  t.shellK = upload_const(d, h->shellK, h->nrShells);
+  t.shellPrim = upload_const(d, h->shellPrim, h->nrShells);
+  t.shellAtom = upload_const(d, h->shellAtom, h->nrShells);
+  t.shellAO = upload_const(d, h->shellAO, h->nrShells);
+  {
+    int *aml = (int *)calloc(h->nrAtoms + 1, sizeof(int));
+    for (int s = 0; s < h->nrShells; s++)
+      if (h->shellL[s] > aml[h->shellAtom[s]]) aml[h->shellAtom[s]] = h->shellL[s];
+    t.atomMaxL = upload_const(d, aml, h->nrAtoms);
+    free(aml);
+  }
+  t.primD = upload_const(d, h->primD, h->nrPrims);
+  t.primA = upload_const(d, h->primA, h->nrPrims);
+  t.typeL = upload_const(d, h->typeL, h->nTypes);
+  t.typeGaussOff = upload_const(d, h->typeGaussOff, h->nTypes + 1);
+  const int ng = h->typeGaussOff[h->nTypes];
+  t.gaussL = upload_const(d, h->gaussL, ng);
+  t.gaussN = upload_const(d, h->gaussN, ng);
+  t.gaussD = upload_const(d, h->gaussD, ng);
+  t.gaussA = upload_const(d, h->gaussA, ng);
+  t.typeUtab = upload_const(d, h->typeUtab, (size_t)h->nTypes * h->maxLECP * h->nU * ECP_SMALL_SLOTS);
+  t.typeUL = upload_const(d, h->typeUL, (size_t)h->nTypes * ECP_SMALL_SLOTS);
+  t.clsLa = upload_const(d, h->clsLa, h->nClasses);
+  t.clsLb = upload_const(d, h->clsLb, h->nClasses);
+  t.clsL = upload_const(d, h->clsL, h->nClasses);
+  t.clsNq = upload_const(d, h->clsNq, h->nClasses);
+  t.clsQOff = upload_const(d, h->clsQOff, h->nClasses + 1);
+  t.clsQlOff = upload_const(d, h->clsQlOff, (size_t)h->nClasses * (ECP_MAX_LECP + 1));
+  t.qlist = upload_const(d, h->qlist, h->nqlist);
+  t.clsQidxOff = upload_const(d, h->clsQidxOff, h->nClasses + 1);
+  t.qidx = upload_const(d, h->qidx, h->nqidx);
+  t.nAO = h->nAO;
+  d->nClasses = h->nClasses;
+  d->maxQPerL = h->maxQPerL;
+  d->nAO = h->nAO;
+  d->maxLBS = h->maxLBS;
+  for (int i = 0; i < d->ntab; i++)
+    if (!d->tab[i].p) {
+      snprintf(g_err, sizeof(g_err), "libecp_b200: table upload %d failed: %s", i, cudaGetErrorString(cudaGetLastError()));
+      ecpdev_destroy(d);
+      return NULL;
+    }
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    ecpdev_destroy(d);
+    return NULL;
+  }
+  return d;
+}
+
+extern "C" void ecpdev_destroy(EcpDev *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < d->ntab; i++)
+    if (d->tab[i].p) cudaFree(d->tab[i].p);
+  Buf *bs[] = {&d->asAtom, &d->asType, &d->asR, &d->asOmOff, &d->ssShell, &d->ssASlot, &d->ssStart, &d->ssEnd,
+               &d->ssFOff, &d->trA, &d->trB, &d->trClass, &d->trOut, &d->trT, &d->trG, &d->trPair, &d->prTriple,
+               &d->prQOff, &d->prRshOff, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
+               &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags,
+               &d->items, &d->counters};
+  for (size_t i = 0; i < sizeof(bs) / sizeof(bs[0]); i++)
+    if (bs[i]->p) cudaFree(bs[i]->p);
+  if (d->matrix) cudaFree(d->matrix);
+  for (int i = 0; i < 12; i++) cudaEventDestroy(d->ev[i]);
+  cudaStreamDestroy(d->s1);
+  cudaStreamDestroy(d->s2);
+  free(d);
+}
+
+extern "C" int ecpdev_matrix_begin(EcpDev *d) {
+  CK(cudaSetDevice(d->device));
+  const size_t bytes = (size_t)d->nAO * d->nAO * sizeof(double);
+  if (!d->matrix) CK(cudaMalloc((void **)&d->matrix, bytes ? bytes : 8));
+  CK(cudaMemsetAsync(d->matrix, 0, bytes, d->s1));
+  return 0;
+}
+extern "C" int ecpdev_matrix_download(EcpDev *d, double *host) {
+  CK(cudaSetDevice(d->device));
+  CK(cudaStreamSynchronize(d->s1));
+  CK(cudaMemcpy(host, d->matrix, (size_t)d->nAO * d->nAO * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" void *ecpdev_matrix_ptr(EcpDev *d) { return d->matrix; }
+extern "C" int ecpdev_sync(EcpDev *d) {
+  CK(cudaSetDevice(d->device));
+  CK(cudaStreamSynchronize(d->s1));
+  CK(cudaStreamSynchronize(d->s2));
+  return 0;
+}
+
+#define UP(buf, field, src, n, T)                                                                         \
+  do {                                                                                                    \
+    int rc_ = ensure(&d->buf, ((n) ? (n) : 1) * sizeof(T));                                               \
+    if (rc_) return rc_;                                                                                  \
+    if (n) CK(cudaMemcpyAsync(d->buf.p, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, d->s1));    \
+    B.field = (const T *)d->buf.p;                                                                        \
+  } while (0)
+#define SCRATCH(buf, field, n, T)                                   \
+  do {                                                              \
+    int rc_ = ensure(&d->buf, ((n) ? (n) : 1) * sizeof(T));         \
+    if (rc_) return rc_;                                            \
+    B.field = (T *)d->buf.p;                                        \
+  } while (0)
+
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double *hostBlocks, EcpDevStats *st) {
+  CK(cudaSetDevice(d->device));
+  DevB &B = d->b;
+  const int nc = d->nClasses;
+  B.nASlots = h->nASlots;
+  B.nSSlots = h->nSSlots;
+  B.nTriples = h->nTriples;
+  B.nPairs = h->nPairs;
+  if (st) memset(st, 0, sizeof(*st));
+  if (h->nTriples == 0) return 0;
+  UP(asAtom, asAtom, h->asAtom, h->nASlots, int);
+  UP(asType, asType, h->asType, h->nASlots, int);
+  UP(asR, asR, h->asR, (size_t)h->nASlots * 4, double);
+  UP(asOmOff, asOmOff, (const long long *)h->asOmOff, h->nASlots, long long);
+  UP(ssShell, ssShell, h->ssShell, h->nSSlots, int);
+  UP(ssASlot, ssASlot, h->ssASlot, h->nSSlots, int);
+  UP(ssStart, ssStart, h->ssStart, h->nSSlots, int);
+  UP(ssEnd, ssEnd, h->ssEnd, h->nSSlots, int);
+  UP(ssFOff, ssFOff, (const long long *)h->ssFOff, h->nSSlots, long long);
+  UP(trA, trA, h->trA, h->nTriples, int);
+  UP(trB, trB, h->trB, h->nTriples, int);
+  UP(trClass, trClass, h->trClass, h->nTriples, int);
+  UP(trOut, trOut, (const long long *)h->trOut, h->nTriples, long long);
+  UP(trT, trT, (const long long *)h->trT, h->nTriples, long long);
+  UP(trG, trG, (const long long *)h->trG, h->nTriples, long long);
+  UP(trPair, trPair, (const long long *)h->trPair, h->nTriples, long long);
+  UP(prTriple, prTriple, h->prTriple, h->nPairs, int);
+  UP(prQOff, prQOff, (const long long *)h->prQOff, h->nPairs, long long);
+  UP(prRshOff, prRshOff, (const long long *)h->prRshOff, h->nPairs, long long);
+  UP(clsFirst, clsFirst, h->clsFirst, nc + 1, int);
+  UP(clsWork, clsWork, (const long long *)h->clsWork, nc + 1, long long);
+  UP(clsElem, clsElem, (const long long *)h->clsElem, nc + 1, long long);
+  UP(clsOutElem, clsOutElem, (const long long *)h->clsOutElem, nc + 1, long long);
+  SCRATCH(rshX, rshX, (size_t)h->nASlots * RSHX_STRIDE, double);
+  SCRATCH(uspX, uspX, (size_t)h->nASlots * USPX_STRIDE, double);
+  SCRATCH(omX, omX, (size_t)h->omTotal, double);
+  SCRATCH(F, F, (size_t)h->fRows * ECP_SMALL_SLOTS, double);
+  SCRATCH(T, T, (size_t)h->tTotal, double);
+  SCRATCH(gamma, gamma, (size_t)h->gTotal, double);
+  SCRATCH(chi, chi, (size_t)h->gTotal, double);
+  SCRATCH(Q, Q, (size_t)h->qTotal, double);
+  SCRATCH(rshP, rshP, (size_t)h->rshTotal, double);
+  SCRATCH(sP, sP, (size_t)h->nPairs, double);
+  SCRATCH(blocks, blocks, (flags & 2) ? (size_t)h->outTotal : 1, double);
+  SCRATCH(tfail, tfail, (size_t)h->tTotal, unsigned char);
+  SCRATCH(tflags, tflags, (size_t)h->nTriples, int);
+  SCRATCH(items, items, (size_t)h->nTriples * 8, int);
+  SCRATCH(counters, counters, 16, int);
+  if ((flags & 1) && !d->matrix) {
+    int rc = ecpdev_matrix_begin(d);
+    if (rc) return rc;
+  }
+  B.matrix = d->matrix;
+  d->lastSizes[0] = (size_t)h->fRows * ECP_SMALL_SLOTS;
+  d->lastSizes[1] = (size_t)h->omTotal;
+  d->lastSizes[2] = (size_t)h->tTotal;
+  d->lastSizes[3] = (size_t)h->gTotal;
+  d->lastSizes[4] = (size_t)h->qTotal;
+  d->lastSizes[5] = (size_t)h->outTotal;
+  CK(cudaMemsetAsync(B.counters, 0, 16 * sizeof(int), d->s1));
+  CK(cudaMemsetAsync(B.tflags, 0, (size_t)h->nTriples * sizeof(int), d->s1));
+  CK(cudaMemsetAsync(B.Q, 0, (size_t)h->qTotal * sizeof(double), d->s1));
+  const DevT &t = d->t;
+  const int maxq1 = 40; /* type-1 quadratures per pair: sum_N (N/2+1) <= 36 for la+lb <= 10 */
+  const int maxq2 = d->maxQPerL > 1 ? d->maxQPerL : 1;
+  const size_t sm1 = warp_smem_bytes(maxq1), sm2 = warp_smem_bytes(maxq2);
+  cudaFuncSetAttribute(k_fallbackT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+  cudaFuncSetAttribute(k_type1Q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+  long long launches = 0;
+  CK(cudaEventRecord(d->ev[0], d->s1));
+  /* per-centre tables */
+  k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
+  k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
+  k_Ftab<<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
+  launches += 3;
+  CK(cudaEventRecord(d->ev[1], d->s1));
+  /* type 1 on the second stream, after the uploads/tables */
+  CK(cudaStreamWaitEvent(d->s2, d->ev[1], 0));
+  CK(cudaEventRecord(d->ev[6], d->s2));
+  k_t1prep<<<nblk(h->nPairs, 128), 128, 0, d->s2>>>(t, B);
+  k_type1Q<<<d->nSM * 24, 32, sm1, d->s2>>>(t, B, maxq1);
+  CK(cudaEventRecord(d->ev[7], d->s2));
+  k_chi<<<nblk(h->clsElem[nc], 128), 128, 0, d->s2>>>(t, B, h->clsElem[nc]);
+  CK(cudaEventRecord(d->ev[8], d->s2));
+  launches += 3;
+  /* type 2 */
+  const long long nWork = h->clsWork[nc];
+  if (nWork > 0) {
+    k_fastT<<<nblk(nWork, 128), 128, 0, d->s1>>>(t, B, nWork);
+    launches++;
+  }
+  CK(cudaEventRecord(d->ev[2], d->s1));
+  if (nWork > 0) {
+    k_fallbackT<<<d->nSM * 24, 32, sm2, d->s1>>>(t, B, maxq2);
+    launches++;
+  }
+  CK(cudaEventRecord(d->ev[3], d->s1));
+  k_link<<<nblk(h->clsElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsElem[nc]);
+  launches++;
+  CK(cudaEventRecord(d->ev[4], d->s1));
+  CK(cudaStreamWaitEvent(d->s1, d->ev[8], 0));
+  k_shift<<<nblk(h->clsOutElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsOutElem[nc], flags);
+  launches++;
+  CK(cudaEventRecord(d->ev[5], d->s1));
+  CK(cudaGetLastError());
+  int hc[16];
+  CK(cudaMemcpyAsync(hc, B.counters, sizeof(hc), cudaMemcpyDeviceToHost, d->s1));
+  if ((flags & 2) && hostBlocks)
+    CK(cudaMemcpyAsync(hostBlocks, B.blocks, (size_t)h->outTotal * sizeof(double), cudaMemcpyDeviceToHost, d->s1));
+  CK(cudaStreamSynchronize(d->s1));
+  CK(cudaStreamSynchronize(d->s2));
+  if (st) {
+    float ms;
+    cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); st->ms_tables = ms;
+    cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]); st->ms_fastT = ms;
+    cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); st->ms_fallback = ms;
+    cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]); st->ms_link = ms;
+    cudaEventElapsedTime(&ms, d->ev[6], d->ev[7]); st->ms_type1 = ms;
+    cudaEventElapsedTime(&ms, d->ev[7], d->ev[8]); st->ms_chi = ms;
+    cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]); st->ms_shift = ms;
+    cudaEventElapsedTime(&ms, d->ev[0], d->ev[5]); st->ms_total = ms;
+    st->nFallbackItems = hc[0];
+    st->nFastFail = hc[4];
+    st->nType1Fail = hc[5];
+    st->nStaleCentre = hc[6];
+    st->launches = launches;
+    st->err1 = hc[2];
+    st->err2 = hc[3];
+  }
+  return 0;
+}
+
+extern "C" int ecpdev_debug_fetch(EcpDev *d, const char *what, double *dst, int64_t n) {
+  CK(cudaSetDevice(d->device));
+  const void *src = NULL;
+  size_t have = 0;
+  if (!strcmp(what, "F")) { src = d->b.F; have = d->lastSizes[0]; }
+  else if (!strcmp(what, "omegaX")) { src = d->b.omX; have = d->lastSizes[1]; }
+  else if (!strcmp(what, "T")) { src = d->b.T; have = d->lastSizes[2]; }
+  else if (!strcmp(what, "gamma")) { src = d->b.gamma; have = d->lastSizes[3]; }
+  else if (!strcmp(what, "chi")) { src = d->b.chi; have = d->lastSizes[3]; }
+  else if (!strcmp(what, "Q")) { src = d->b.Q; have = d->lastSizes[4]; }
+  if (!src) return -1;
+  if ((size_t)n > have) n = (int64_t)have;
+  CK(cudaMemcpy(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" double ecpdev_fp64_peak_probe(int device, int iters) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  int nsm = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = nsm * 8, threads = 256;
+  double *out = NULL;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_fp64_probe<<<blocks, threads>>>(out, 1000);
+  cudaDeviceSynchronize();
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_fp64_probe<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}

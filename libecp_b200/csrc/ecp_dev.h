@@ -1,0 +1,137 @@
+/* ecp_dev.h - internal C ABI between the host C layer (tables.c, builder.c, api.c) and the CUDA layer
+ * (ecp_cuda.cu).  Plain pointers and sizes only.  Not installed; the public headers are include/*.h.
+ *
+ * Vocabulary (follows the reference's domain):
+ *   centre C      ECP-bearing atom                       (src/libecp.c:256)
+ *   atom slot     (C, atom X) with >=1 unskipped shell   -> r_XC, Omega_X, usp_X   (src/libecp.c:278-292)
+ *   shell slot    (C, shell) that survives screening     -> window [start,end], F table (src/type2.c:246-303)
+ *   triple        (shell slot a, shell slot b) of one C  -> chi, gamma, two integral blocks (src/libecp.c:297-376)
+ *   class         (la, lb, L_C): triples of one class share quadrature lists and sizes
+ */
+#ifndef ECP_DEV_H
+#define ECP_DEV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECP_SMALL_ORDER 383  /* PS93 grid, order 128 -> 3*2^7-1 points (src/gc_integrators.c:161)   */
+#define ECP_SMALL_SLOTS 384  /* level-major padded layout, see tables.c:build_small_grid             */
+#define ECP_SMALL_LEVELS 13
+#define ECP_MAX_LBS 5        /* h shells                                                             */
+#define ECP_MAX_LECP 6
+#define ECP_KMAX 10          /* highest Bessel order ever requested: max(la+l, la+lb) <= 10          */
+#define ECP_MAX_CLASSES 256
+
+/* geometry-independent tables, built bit-exactly on the host (tables.c) */
+typedef struct {
+  int maxLECP, maxLBS, maxAlpha, maxLambda, tmDim, ijkDim;
+  int besselLMax;    /* rows in the Bessel table - 1                              */
+  int besselStride;  /* doubles per abscissa in the transposed table              */
+  int largeOrder;    /* 1023                                                      */
+  int largeSlots;    /* 1024                                                      */
+  int largeLevels;   /* 9                                                         */
+  double tolerance, accuracy, lnAccuracy1, lnAccuracy2;
+  const double *fac, *dfac;       int nfac;
+  const int *ijk, *ijkIndex;      /* [3*C_DIM(tmDim)], [ijkDim^3]                  */
+  const double *poly2sph;         /* [C_DIM(tmDim)][L_DIM(tmDim)]                  */
+  const double *omega;            /* [L_DIM(maxLECP)][L_DIM(maxLambda)][C_DIM(maxAlpha)] */
+  int nomega;
+  const double *binom;            /* [(maxLBS+1)^2] n over k                       */
+  /* small grid, level-major padded layout */
+  const double *small_r, *small_w;   /* [384]                                      */
+  const int16_t *small_oidx;         /* [384] original index, -1 for the pad slot  */
+  int small_levPairs[ECP_SMALL_LEVELS], small_levJ[ECP_SMALL_LEVELS], small_levN[ECP_SMALL_LEVELS];
+  int small_levSlot[ECP_SMALL_LEVELS + 1];
+  /* large grid template on (-1,1), level-major padded layout */
+  const double *large_x, *large_w;   /* [1024]                                     */
+  const int16_t *large_oidx;         /* [1024]                                     */
+  /* Bessel table transposed to [1601][besselStride], and C_j */
+  const double *besselT, *besselC;
+  /* basis set */
+  int nrShells, nrPrims, nrAtoms, nAO;
+  const int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO;
+  const double *primD, *primA;
+  /* ECP types (distinct parameter sets) */
+  int nTypes;
+  const int *typeL;                  /* [nTypes]                                   */
+  const int *typeGaussOff;           /* [nTypes+1] into gauss arrays               */
+  const int *gaussL;  const double *gaussN, *gaussD, *gaussA;
+  int nU;                            /* rows N of r^N U_l: max(maxLambda, 2 maxAlpha)+1 */
+  const double *typeUtab;            /* per type [maxLECP][nU][384] slots          */
+  const double *typeUL;              /* per type [384]                             */
+  /* classes */
+  int nClasses;
+  const int *clsLa, *clsLb, *clsL;   /* [nClasses]                                 */
+  const int *clsNq;                  /* used type-2 quadratures per triple         */
+  const int *clsQOff;                /* [nClasses+1] offsets into qlist            */
+  const int *clsQlOff;               /* [nClasses*(ECP_MAX_LECP+1)] start of each l inside the class list */
+  const int *qlist;                  /* packed l | l1<<4 | l2<<8 | l3<<12           */
+  const int *clsQidxOff;             /* [nClasses+1] offsets into qidx             */
+  const int16_t *qidx;               /* [L][la+L][lb+L][la+lb+1] -> position in class list or -1 */
+  int nqlist, nqidx;
+  int maxQPerL;                      /* max used quadratures of any (class,l)      */
+} EcpHostTables;
+
+/* one batch of centres, produced by builder.c */
+typedef struct {
+  /* atom slots */
+  int nASlots;
+  const int *asAtom, *asCentre, *asType;
+  const double *asR;        /* [nASlots][4]: r_XC (x,y,z), d_XC                    */
+  const int64_t *asOmOff;   /* offset (doubles) of Omega_X                         */
+  int64_t omTotal;
+  /* shell slots */
+  int nSSlots;
+  const int *ssShell, *ssASlot, *ssStart, *ssEnd;
+  const int64_t *ssFOff;    /* offset in rows of 384 doubles                       */
+  int64_t fRows;
+  /* triples, sorted by class */
+  int nTriples;
+  const int *trA, *trB;     /* shell slots                                         */
+  const int *trClass;
+  const int64_t *trOut;     /* offset of the (type1,type2) block pair in the block buffer */
+  const int64_t *trT;       /* offset into T                                       */
+  const int64_t *trG;       /* offset into gamma / chi                             */
+  const int64_t *trPair;    /* first type-1 primitive pair                         */
+  int64_t tTotal, gTotal, outTotal, nPairs, qTotal, rshTotal;
+  const int *prTriple;      /* [nPairs] owning triple                              */
+  const int64_t *prQOff;    /* [nPairs] offset into Q                              */
+  const int64_t *prRshOff;  /* [nPairs] offset into rsh                            */
+  /* per class ranges (triples of class c are [clsFirst[c], clsFirst[c+1])) */
+  const int *clsFirst;      /* [nClasses+1]                                        */
+  const int64_t *clsWork;   /* [nClasses+1] prefix of ntriples*nq (fast-T threads) */
+  const int64_t *clsElem;   /* [nClasses+1] prefix of ntriples*C_DIM(la)*C_DIM(lb) */
+  const int64_t *clsOutElem;/* [nClasses+1] prefix of ntriples*IJK(la)*IJK(lb)     */
+} EcpBatch;
+
+typedef struct {
+  double ms_tables, ms_fastT, ms_fallback, ms_link, ms_type1, ms_chi, ms_shift, ms_total;
+  long long nFallbackItems, nFastFail, nType1Fail, nStaleCentre, launches;
+  int err1, err2;
+} EcpDevStats;
+
+typedef struct EcpDev EcpDev;
+
+/* all return 0 on success, else a cudaError_t value (message via ecpdev_last_error) */
+EcpDev *ecpdev_create(const EcpHostTables *t, int device);
+void ecpdev_destroy(EcpDev *d);
+const char *ecpdev_last_error(void);
+/* matrix accumulation target (device resident, nAO x nAO, zeroed) */
+int ecpdev_matrix_begin(EcpDev *d);
+int ecpdev_matrix_download(EcpDev *d, double *host /* nAO*nAO */);
+void *ecpdev_matrix_ptr(EcpDev *d);
+/* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks */
+int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, double *hostBlocks, EcpDevStats *stats);
+int ecpdev_sync(EcpDev *d);
+/* debug access to the intermediates of the last batch (tests only): "F" "omegaX" "T" "gamma" "chi" "Q" "tfail" */
+int ecpdev_debug_fetch(EcpDev *d, const char *what, double *dst, int64_t n);
+/* FP64 FMA peak probe used by bench.py for the roofline denominator: returns TFLOP/s */
+double ecpdev_fp64_peak_probe(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,302 @@
+/* ecp_math.h - per-thread numerical building blocks of the ECP kernels.
+ *
+ * Every function is `__host__ __device__` so that the *same source* the sm_100a kernels execute can be
+ * compiled by g++ into a test-only harness (tests/hostcheck) and compared with the oracle on the CPU
+ * before GPU time is spent.  The product never runs these on the host.
+ *
+ * The arithmetic follows the reference's operation order (file:line cited per function); the CUDA
+ * translation unit is compiled with -fmad=false so that no product-sum is contracted and decisions
+ * (Bessel branch / node index, exponent gates, window cuts, convergence tests) are taken on the same
+ * doubles as the reference takes them.
+ */
+#ifndef ECP_MATH_H
+#define ECP_MATH_H
+
+#include <math.h>
+#include <stdint.h>
+
+#include "ecp_dev.h"
+
+#if defined(__CUDACC__)
+#define ECP_HD __host__ __device__ __forceinline__
+#else
+#define ECP_HD static inline
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* index helpers (reference src/dimensions.h:18-29) */
+ECP_HD int ecp_ld(int l) { return (l + 1) * (l + 1); }
+ECP_HD int ecp_cd(int l) { return (l + 1) * (l + 2) * (l + 3) / 6; }
+ECP_HD int ecp_ijk(int l) { return (l + 1) * (l + 2) / 2; }
+ECP_HD int ecp_cidx(int l, int c) { return ecp_cd(l - 1) + c; }
+
+/* ------------------------------------------------------------------------------------------------
+ * Weighted modified spherical Bessel functions K_0..K_lmax(z) = e^-z M_l(z)
+ * (reference src/bessel.c:101-199).  Table transposed to tabT[index*stride + l].
+ * KM is the compile-time bound on lmax; arrays live in registers (all indices static after unroll).
+ * Returns the branch taken (0 small-z, 1 Taylor, 2 asymptotic).
+ * ---------------------------------------------------------------------------------------------- */
+template <int KM>
+ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double *__restrict__ Cj, int lmax, double z,
+                      double (&K)[KM + 1]) {
+  if (z < 1.0E-7) {
+    if (z <= 0) {
+      K[0] = 1.0;
+#pragma unroll
+      for (int l = 1; l <= KM; l++) K[l] = 0.0;
+    } else {
+      K[0] = 1 - z;
+#pragma unroll
+      for (int l = 1; l <= KM; l++)
+        if (l <= lmax) K[l] = K[l - 1] * z / (2 * l + 1);
+    }
+    return 0;
+  } else if (z < 16.0) {
+    double d[KM + 6];
+    const int maxL = lmax + 5;
+    const int index = (int)floor(z * 100.0 + 0.5);
+    const double dz = z - index / 100.0;
+    const double *row = tabT + (size_t)index * stride;
+    double scale = 1.0;
+#pragma unroll
+    for (int l = 0; l <= KM + 5; l++) d[l] = (l <= maxL) ? row[l] : 0.0;
+#pragma unroll
+    for (int l = 0; l <= KM; l++) K[l] = d[l];
+#pragma unroll
+    for (int i = 1; i <= 5; i++) {
+      const int top = maxL - i;
+      double prev = d[0];
+      d[0] = d[1] - d[0];
+#pragma unroll
+      for (int j = 1; j <= KM + 5 - i; j++) {
+        if (j <= top) {
+          const double cur = d[j];
+          d[j] = Cj[j] * (prev - d[j + 1]) - cur + d[j + 1];
+          prev = cur;
+        }
+      }
+      scale = scale * dz / i;
+#pragma unroll
+      for (int j = 0; j <= KM; j++)
+        if (j <= lmax) K[j] += scale * d[j];
+    }
+    return 1;
+  } else {
+    double A[KM + 1];
+    A[0] = 0.5 / z;
+#pragma unroll
+    for (int l = 0; l <= KM; l++) K[l] = A[0];
+#pragma unroll
+    for (int l = 1; l <= KM; l++) {
+      if (l <= lmax) {
+        double f = l * (l + 1);
+#pragma unroll
+        for (int i = 1; i < l; i++) {
+          K[l] += f * A[i];
+          f *= (l + i + 1) * (l - i);
+        }
+        A[l] = -A[0] * A[l - 1] / l;
+        K[l] += f * A[l];
+      }
+    }
+    return 2;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ECP radial channel U_l(r) = sum_k r^n_k d_k exp(-a_k r^2)   (reference src/ecp.c:41-60)
+ * Integer powers 0..4 are formed by multiplication (pow(r,2.0) == r*r when correctly rounded).
+ * ---------------------------------------------------------------------------------------------- */
+ECP_HD double ecp_rpow(double r, double n) {
+  if (n == 2.0) return r * r;
+  if (n == 1.0) return r;
+  if (n == 0.0) return 1.0;
+  return pow(r, n);
+}
+ECP_HD double ecp_pot_eval(const int *__restrict__ gl, const double *__restrict__ gn, const double *__restrict__ gd,
+                           const double *__restrict__ ga, int g0, int g1, int l, double r) {
+  double v = 0.0;
+  const double r2 = r * r;
+  for (int i = g0; i < g1; i++)
+    if (gl[i] == l) v += ecp_rpow(r, gn[i]) * gd[i] * exp(-ga[i] * r2);
+  return v;
+}
+
+/* Cartesian -> (r, theta, phi) with the reference's axis rules (src/util.c:74-106) */
+ECP_HD void ecp_sphcoord(double x, double y, double z, double *r_, double *theta_, double *phi_) {
+  const double eps = 1.0E-14;
+  const double r = sqrt(x * x + y * y + z * z);
+  double theta, phi;
+  theta = (r < eps) ? 0.0 : acos(z / r);
+  if (fabs(x) < eps) {
+    if (fabs(y) < eps)
+      phi = 0.0;
+    else if (y < 0.0)
+      phi = 1.5 * M_PI;
+    else
+      phi = 0.5 * M_PI;
+  } else {
+    phi = (x > 0.0) ? atan(y / x) : atan(y / x) + M_PI;
+  }
+  *r_ = r;
+  *theta_ = theta;
+  *phi_ = phi;
+}
+
+/* Real spherical harmonics S_lm, l <= lmax <= 2*ECP_MAX_LBS or maxLECP-1+ECP_MAX_LBS (both <= 10),
+ * out[l*l + l + m]  (reference src/spherical_harmonics.c:15-114). */
+#define ECP_RSH_LMAX 10
+ECP_HD void ecp_rsh(int lmax, double theta, double phi, const double *__restrict__ fac,
+                    const double *__restrict__ dfac, double *__restrict__ out) {
+  double P[(ECP_RSH_LMAX + 1) * (ECP_RSH_LMAX + 1)];
+  double s[ECP_RSH_LMAX + 2], c[ECP_RSH_LMAX + 2];
+  const int n = (lmax + 1) * (lmax + 1);
+#define ECP_RS(l, m) ((l) * (l) + (l) + (m))
+  for (int i = 0; i < n; i++) {
+    P[i] = 0.0;
+    out[i] = 0.0;
+  }
+  for (int i = 0; i < lmax + 2; i++) s[i] = c[i] = 0.0;
+  const double x = cos(theta);
+  if (1.0 == x) {
+    for (int l = 0; l <= lmax; l++) P[ECP_RS(l, 0)] = 1.0;
+  } else if (-1.0 == x) {
+    P[ECP_RS(0, 0)] = 1.0;
+    for (int l = 1; l <= lmax; l++) P[ECP_RS(l, 0)] = -P[ECP_RS(l - 1, 0)];
+  } else {
+    s[1] = sqrt(1.0 - x * x);
+    for (int l = 2; l <= lmax; l++) s[l] = s[l - 1] * s[1];
+    for (int l = 0; l <= lmax; l++) {
+      int m = l;
+      if (0 == m)
+        P[ECP_RS(l, 0)] = 1.0;
+      else {
+        P[ECP_RS(l, m)] = s[m] * dfac[2 * m - 1];
+        m = l - 1;
+        P[ECP_RS(l, m)] = x * (2 * m + 1) * P[ECP_RS(l - 1, m)];
+        if (l > 1)
+          for (m = 0; m <= l - 2; m++)
+            P[ECP_RS(l, m)] = (x * (2 * l - 1) * P[ECP_RS(l - 1, m)] - (l + m - 1) * P[ECP_RS(l - 2, m)]) / (l - m);
+      }
+    }
+  }
+  for (int l = 0; l <= lmax; l++) {
+    const double norm0 = sqrt((2.0 * l + 1.0) / (2.0 * M_PI));
+    P[ECP_RS(l, 0)] = norm0 * P[ECP_RS(l, 0)];
+    for (int m = 1; m <= l; m++) {
+      const double norm = sqrt(fac[l - m] / fac[l + m]) * norm0;
+      P[ECP_RS(l, m)] = norm * P[ECP_RS(l, m)];
+    }
+  }
+  if (lmax > 0) {
+    if (0.0 == phi) {
+      for (int m = 0; m <= lmax; m++) {
+        s[m] = 0.0;
+        c[m] = 1.0;
+      }
+    } else {
+      s[1] = sin(phi);
+      c[1] = cos(phi);
+      for (int m = 2; m <= lmax; m++) {
+        s[m] = s[1] * c[m - 1] + c[1] * s[m - 1];
+        c[m] = c[1] * c[m - 1] - s[1] * s[m - 1];
+      }
+    }
+  }
+  for (int l = 0; l <= lmax; l++) {
+    out[ECP_RS(l, 0)] = P[ECP_RS(l, 0)] / sqrt(2.0);
+    for (int m = 1; m <= l; m++) {
+      out[ECP_RS(l, -m)] = P[ECP_RS(l, m)] * s[m];
+      out[ECP_RS(l, +m)] = P[ECP_RS(l, m)] * c[m];
+    }
+  }
+#undef ECP_RS
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Small-grid level structure (PS93), level-major padded slot layout:
+ *   slot 0 = centre point, slot 1 = pad, slots 2,3 = first pair, then level `v` occupies slots
+ *   [levSlot[v], levSlot[v+1]) as (left,right) pairs in the reference's visiting order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int levPairs[ECP_SMALL_LEVELS], levJ[ECP_SMALL_LEVELS], levN[ECP_SMALL_LEVELS], levSlot[ECP_SMALL_LEVELS + 1];
+} EcpSmallMeta;
+
+/* One PS93 level update after the level's points were added to I
+ * (reference src/gc_integrators.c:201-214).  Returns 1 when converged (result in *res). */
+ECP_HD int ecp_ps93_update(int j, int n, int cnt, double tol, double I, double *p, double *q, double *res) {
+  double err = 0.0;
+  *p += (1 - j) * (I - *q);
+  if (0 < cnt) err = 16 * fabs((1 - j) * (*q - 3 * (*p) / 2) + j * (I - 2 * (*q))) / (3 * n);
+  *q = (1 - j) * (*q) + j * I;
+  if (0 == cnt) return 0;
+  if (err < tol) {
+    *res = 16 * (*q) / (3 * n);
+    return 1;
+  }
+  return 0;
+}
+
+/* One PSM92 level update (reference src/gc_integrators.c:73-83).  pTwoIprev = 2*I before the level,
+ * qv = 2*p of the previous level; nNew = 2n+1. */
+ECP_HD int ecp_psm92_update(int nNew, int cnt, double tol, double I, double pv, double qv, double *res) {
+  const double N = nNew + 1.0;
+  const double e = I - pv;
+  if (0 == cnt) return 0;
+  if (16 * e * e <= 3 * N * fabs(I - qv) * tol) {
+    *res = 16 * I / (3 * N);
+    return 1;
+  }
+  return 0;
+}
+
+/* Sequential PS93 quadrature of the type-2 fast path: integrand Fa*Fb*U on slot-ordered rows
+ * (reference src/type2.c:319-322 + src/gc_integrators.c:156-217).  Summation order identical to the
+ * reference's.  rc 0 converged / 1 failed; *npts = evaluated points. */
+ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, const double *__restrict__ Fb, const double *__restrict__ U,
+                          const double *__restrict__ w, const int16_t *__restrict__ oidx, const EcpSmallMeta *meta,
+                          int start, int end, double tol, double *result, int *npts) {
+  double p = w[0] * (Fa[0] * Fb[0] * U[0]);
+  double q = w[2] * (Fa[2] * Fb[2] * U[2]) + w[3] * (Fa[3] * Fb[3] * U[3]);
+  double I = p + q;
+  int np = 3;
+  for (int v = 0; v < ECP_SMALL_LEVELS; v++) {
+    int cnt = 0;
+    const int s0 = meta->levSlot[v], s1 = meta->levSlot[v + 1];
+    for (int s = s0; s < s1; s += 2) {
+      double T = 0.0;
+      if (oidx[s] >= start) {
+        T += w[s] * (Fa[s] * Fb[s] * U[s]);
+        cnt++;
+      }
+      if (oidx[s + 1] <= end) {
+        T += w[s + 1] * (Fa[s + 1] * Fb[s + 1] * U[s + 1]);
+        cnt++;
+      }
+      I += T;
+    }
+    np += cnt;
+    if (ecp_ps93_update(meta->levJ[v], meta->levN[v], cnt, tol, I, &p, &q, result)) {
+      if (npts) *npts = np;
+      return 0;
+    }
+  }
+  if (npts) *npts = np;
+  return 1;
+}
+
+/* FM06 linear map parameters of the large grid for a primitive pair (reference src/gc_integrators.c:316-331):
+ * r = i1*x + i2, w' = w*i1 */
+ECP_HD void ecp_fm06_map(double zeta_p, double P, double *i1, double *i2) {
+  const double sigma = 1.0 / sqrt(zeta_p);
+  const double t = P - 7.0 * sigma;
+  const double rmin = (t > 0.0) ? t : 0.0;
+  const double rmax = P + 9.0 * sigma;
+  *i1 = 0.5 * (rmax - rmin);
+  *i2 = 0.5 * (rmax + rmin);
+}
+
+#endif

@@ -1,0 +1,53 @@
+/* tables.h - host-side, geometry-independent tables of a libECP handle (built once per handle).
+ * All values are computed with the reference's operation order and glibc libm so that what is
+ * uploaded to the device equals the reference's tables bit for bit (tests/test_host_tables.py). */
+#ifndef ECP_TABLES_H
+#define ECP_TABLES_H
+
+#include "ecp_dev.h"
+
+typedef struct {
+  int L, N;       /* max angular momentum (local channel), number of Gaussians */
+  int gaussOff;   /* offset into the flat gauss arrays                        */
+  int endl[ECP_MAX_LECP + 1]; /* cumulative potential cut-off per l < L (src/type2.c:201-203) */
+  int endLast;    /* window cap for basis screening = endl[L-1] (382 if L == 0) */
+} EcpType;
+
+typedef struct {
+  EcpHostTables v; /* view handed to the CUDA layer (pointers into the arrays below) */
+  /* owned storage */
+  double *fac, *dfac, *cart2sph, *poly2sph, *omega, *binom;
+  int *ijk, *ijkIndex;
+  double *small_x, *small_w;   /* original order [383] (screening uses these)   */
+  double *small_rs, *small_ws; /* slot layout [384]                              */
+  int16_t *small_oidx;
+  double *large_x, *large_w;   /* original order [1023]                          */
+  double *large_xs, *large_ws; /* slot layout [1024]                             */
+  int16_t *large_oidx;
+  double *besselK, *besselT, *besselC;
+  int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO;
+  double *shellRadius;
+  int *atomMaxL, *atomFirstShell;
+  /* ECP */
+  int *atomType; /* per atom: type index or -1 */
+  EcpType *types;
+  int *typeL, *typeGaussOff, *gaussL;
+  double *gaussN, *gaussD, *gaussA, *typeUtab, *typeUL;
+  /* classes */
+  int *clsLa, *clsLb, *clsL, *clsNq, *clsQOff, *clsQlOff, *qlist, *clsQidxOff;
+  int16_t *qidx;
+  int clsLookup[ECP_MAX_LBS + 1][ECP_MAX_LBS + 1][ECP_MAX_LECP + 1];
+} EcpTables;
+
+/* returns NULL on unsupported shape / Bessel series failure (reference: src/libecp.c:159-162,181-185) */
+EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shellsECP, const int *lECP,
+                            const int *KECP, const double *nECP, const double *dECP, const double *aECP,
+                            const int *shellsBS, const int *lBS, const int *KBS, const double *dBS, const double *aBS,
+                            int largeGridOrder, double tolerance, double accuracy);
+void ecp_tables_free(EcpTables *t);
+
+/* helpers shared with builder.c */
+double ecp_host_pot_eval(const EcpTables *t, int type, int l, double r);
+int ecp_t2_used(int la, int lb, int l, int l1, int l2, int l3);
+
+#endif

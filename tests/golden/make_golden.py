@@ -1,0 +1,83 @@
+"""Generate the golden fixtures from the UNMODIFIED reference (oracle/_ref/libecp_ref.so, built by
+oracle/Makefile from /root/reference/src).  Run in the build container only (the GPU box has no
+/root/reference); the resulting .npz files are committed.
+
+    python tests/golden/make_golden.py [--big]
+
+Fixtures (float64, exact bytes of the reference's output):
+  <cfg>_matrix.npz   : getIntegrals matrix (upper triangle incl. diagonal as a flat vector `triu`,
+                       dimension `dim`), Σ and Σ|.| checksums, callback count
+  cfg2_blocks.npz    : every callback block of config 2 in call order (keys, block offsets, values)
+  au2_blocks.npz     : same for the first two atoms of the Au20 tetrahedron (two-centre cases, fallback)
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from libecp_b200 import synth  # noqa: E402
+from oracle.refbind import RefLib  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def save_matrix(ref, name, s):
+    t = time.time()
+    I = ref.get_integrals(s)
+    dt = time.time() - t
+    iu = np.triu_indices(s["dim"])
+    assert np.all(np.tril(I, -1) == 0.0)
+    np.savez_compressed(os.path.join(HERE, f"{name}_matrix.npz"), triu=I[iu], dim=s["dim"],
+                        sum=I.sum(), sumabs=np.abs(I).sum(), ref_seconds=dt, nominal=synth.nominal_triples(s))
+    print(f"{name}: dim {s['dim']} sum {I.sum():.15e} sumabs {np.abs(I).sum():.15e}  {dt:.1f}s")
+
+
+def save_digest(ref, name, s):
+    """19000 x 19000 partial matrices are too big to commit: keep row/column sums, checksums and a fixed
+    sample of 40000 non-zero elements (flat index + value)."""
+    t = time.time()
+    M = ref.get_integrals(s)
+    dt = time.time() - t
+    nz = np.flatnonzero(M.ravel())
+    rng = np.random.default_rng(12345)
+    pick = np.sort(rng.choice(nz, size=min(40000, len(nz)), replace=False))
+    np.savez_compressed(os.path.join(HERE, f"{name}_digest.npz"), dim=s["dim"], rowsum=M.sum(1), colsum=M.sum(0),
+                        rowabs=np.abs(M).sum(1), sum=M.sum(), sumabs=np.abs(M).sum(), nnz=len(nz), sample_idx=pick,
+                        sample_val=M.ravel()[pick], ref_seconds=dt, nominal=synth.nominal_triples(s))
+    print(f"{name}: dim {s['dim']} sum {M.sum():.15e} sumabs {np.abs(M).sum():.15e} nnz {len(nz)}  {dt:.1f}s")
+
+
+def save_blocks(ref, name, s):
+    rc, recs = ref.callbacks(s)
+    assert rc == 0
+    keys = np.array([r[:9] for r in recs], np.int32)
+    off = np.cumsum([0] + [len(r[9]) for r in recs])
+    vals = np.concatenate([r[9] for r in recs])
+    np.savez_compressed(os.path.join(HERE, f"{name}_blocks.npz"), keys=keys, off=off, vals=vals)
+    print(f"{name}: {len(recs)} callbacks, {len(vals)} values")
+
+
+def main():
+    ref = RefLib("ref")
+    save_matrix(ref, "cfg1", synth.cfg1())
+    save_matrix(ref, "cfg2", synth.cfg2())
+    save_matrix(ref, "cfg2_L5", synth.cfg2(5))
+    save_matrix(ref, "au2", synth.cfg3(2))
+    save_matrix(ref, "au4", synth.cfg3(4))
+    save_matrix(ref, "cfg4a", synth.cfg4("a"))
+    save_matrix(ref, "cfg4b", synth.cfg4("b"))
+    save_blocks(ref, "cfg1", synth.cfg1())
+    save_blocks(ref, "cfg2", synth.cfg2())
+    save_blocks(ref, "au2", synth.cfg3(2))
+    # config 5: per-centre partial matrices of a 500-atom crystal, four representative centres
+    for c in (0, 1, 288, 289):
+        save_digest(ref, f"cfg5_c{c}", synth.cfg5(500, active=[c]))
+    if "--big" in sys.argv:
+        save_matrix(ref, "cfg3", synth.cfg3(20))
+
+
+if __name__ == "__main__":
+    main()

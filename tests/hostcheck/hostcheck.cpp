@@ -1,0 +1,35 @@
+// hostcheck.cpp - TEST-ONLY: compiles the per-thread device math (libecp_b200/csrc/ecp_math.h) with g++
+// so the functions the sm_100a kernels execute can be compared with the oracle on the CPU tier.
+// Never linked into the product.
+#include "ecp_math.h"
+
+extern "C" {
+int hc_bessel(const double *tabT, int stride, const double *Cj, int lmax, double z, double *K) {
+  double k[ECP_KMAX + 1];
+  for (int i = 0; i <= ECP_KMAX; i++) k[i] = 0.0;
+  int br = ecp_bessel<ECP_KMAX>(tabT, stride, Cj, lmax, z, k);
+  for (int i = 0; i <= lmax; i++) K[i] = k[i];
+  return br;
+}
+void hc_rsh(int lmax, double theta, double phi, const double *fac, const double *dfac, double *out) {
+  ecp_rsh(lmax, theta, phi, fac, dfac, out);
+}
+void hc_sphcoord(const double *v, double *rtp) { ecp_sphcoord(v[0], v[1], v[2], rtp, rtp + 1, rtp + 2); }
+int hc_ps93_fastT(const double *Fa, const double *Fb, const double *U, const double *w, const int *oidx32,
+                  const int *meta /* pairs[13] j[13] n[13] slot[14] */, int start, int end, double tol, double *res,
+                  int *npts) {
+  EcpSmallMeta m;
+  int16_t oidx[ECP_SMALL_SLOTS];
+  for (int i = 0; i < ECP_SMALL_SLOTS; i++) oidx[i] = (int16_t)oidx32[i];
+  for (int i = 0; i < ECP_SMALL_LEVELS; i++) {
+    m.levPairs[i] = meta[i];
+    m.levJ[i] = meta[13 + i];
+    m.levN[i] = meta[26 + i];
+  }
+  for (int i = 0; i <= ECP_SMALL_LEVELS; i++) m.levSlot[i] = meta[39 + i];
+  return ecp_ps93_fastT(Fa, Fb, U, w, oidx, &m, start, end, tol, res, npts);
+}
+double hc_pot_eval(const int *gl, const double *gn, const double *gd, const double *ga, int n, int l, double r) {
+  return ecp_pot_eval(gl, gn, gd, ga, 0, n, l, r);
+}
+}
