@@ -51,6 +51,7 @@ typedef struct {
   double fb_pairs; /* type-2 fallback primitive pairs */
   double t1_pairs;
   double stale_center_hits; /* fallback calls whose centre point lay beyond the cut (stale read) */
+  double flops_tab2, flops_tab1; /* split of flops_tab: type-2 fallback tables / type-1 tables */
 } Counters;
 #define NCOUNTERS ((int)(sizeof(Counters) / sizeof(double)))
 
@@ -1192,6 +1193,7 @@ static int t2_fallback(OracleECP *h, double *T, int Tinc1, int Tinc2, int nFaile
         if (b.touched[n] && b.expo[n] >= ps.minExp) {
           h->cnt.tab2_touched += 1;
           h->cnt.flops_tab += 20 + wB(b.brA[n], laC) + wB(b.brB[n], lbC) + 24.0 * pot_count(U, l) + lab;
+          h->cnt.flops_tab2 += 20 + wB(b.brA[n], laC) + wB(b.brB[n], lbC) + 24.0 * pot_count(U, l) + lab;
         }
       grid_free(grid);
     }
@@ -1357,6 +1359,7 @@ static int type1_Q(OracleECP *h, double *T /* [(lab+1)^2], zeroed */, const doub
     if (touched[n]) {
       h->cnt.tab1s_touched += 1;
       h->cnt.flops_tab += 20 + wB(br[n], lab) + lab;
+      h->cnt.flops_tab1 += 20 + wB(br[n], lab) + lab;
     }
   if (nFailed > 0) {
     Grid *grid = grid_copy(h->large);
@@ -1395,6 +1398,7 @@ static int type1_Q(OracleECP *h, double *T /* [(lab+1)^2], zeroed */, const doub
       if (touched[n] && expo[n] >= ps.minExp) {
         h->cnt.tab1l_touched += 1;
         h->cnt.flops_tab += 20 + wB(br[n], lab) + 24.0 * pot_count(U, U->L) + lab;
+        h->cnt.flops_tab1 += 20 + wB(br[n], lab) + 24.0 * pot_count(U, U->L) + lab;
       }
     grid_free(grid);
   }
@@ -1697,4 +1701,18 @@ void oracle_counters(OracleECP *h, double *out, int n) {
   int i;
   const double *c = (const double *)&h->cnt;
   for (i = 0; i < n && i < NCOUNTERS; i++) out[i] = c[i];
+}
+
+/* callbacks for timing runs (bench.py --impl reference / cpu_baseline): no Python in the loop.
+ * args == NULL: ignore the block; else accumulate a checksum into *(double*)args. */
+void oracle_sum_callback(int A, int s1, int la, int shifta, int B, int s2, int lb, int shiftb, int C, double *I,
+                         void *args) {
+  (void)A; (void)s1; (void)B; (void)s2; (void)C;
+  if (args) {
+    const int n = IJK(la + shifta) * IJK(lb + shiftb);
+    double s = 0.0;
+    int i;
+    for (i = 0; i < n; i++) s += I[i];
+    *(double *)args += s;
+  }
 }

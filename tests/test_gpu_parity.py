@@ -1,0 +1,163 @@
+"""GPU tier (-m gpu): parity of the CUDA path, called through the C ABI (include/libecp.h,
+getIntegrals.h, libecp_b200.h), with the oracle and the golden fixtures of the compiled reference.
+
+Tolerance (north_star): |x - ref| <= 1e-12 + 1e-10 |ref| element-wise, identical screening decisions
+and integral indexing (the callback key sequence must be identical)."""
+import os
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, assert_parity, load_blocks, load_matrix
+
+from libecp_b200 import capi, synth
+from oracle.refbind import RefLib, have
+
+pytestmark = pytest.mark.gpu
+
+SMALL = {"cfg1": synth.cfg1, "cfg2": synth.cfg2, "cfg2_L5": lambda: synth.cfg2(5), "au2": lambda: synth.cfg3(2),
+         "au4": lambda: synth.cfg3(4), "cfg4a": lambda: synth.cfg4("a"), "cfg4b": lambda: synth.cfg4("b")}
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return RefLib("ref" if have("ref") else "port")
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_getintegrals_matches_golden(name):
+    """one-call interface on host buffers vs the reference's matrix (all five configs' small forms)"""
+    got = capi.get_integrals(SMALL[name]())
+    ref = load_matrix(name)
+    assert_parity(got, ref, name)
+    assert np.all(np.tril(got, -1) == 0.0)  # never writes the strict lower triangle
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "au2"])
+def test_callbacks_match_golden_blocks(name):
+    """calculateECPIntegrals: same callback sequence (A,s1,la,shifta,B,s2,lb,shiftb,C) and blocks"""
+    keys, off, vals = load_blocks(name)
+    with capi.Handle(SMALL[name]()) as h:
+        rc, recs = h.callbacks()
+    assert rc == 0 and len(recs) == len(keys)
+    for k, r in enumerate(recs):
+        assert tuple(keys[k]) == r[:9]
+    assert_parity(np.concatenate([r[9] for r in recs]), vals, name)
+
+
+@pytest.mark.parametrize("name", ["cfg4a", "cfg4b", "au4"])
+def test_callbacks_match_oracle(oracle, name):
+    s = SMALL[name]()
+    rc_o, ro = oracle.callbacks(s)
+    with capi.Handle(s) as h:
+        rc, rg = h.callbacks()
+        st = h.stats()
+    assert rc == rc_o == 0 and len(ro) == len(rg)
+    assert all(a[:9] == b[:9] for a, b in zip(ro, rg))
+    assert_parity(np.concatenate([r[9] for r in rg]), np.concatenate([r[9] for r in ro]), name)
+    assert st["executed_triples"] * 2 == len(rg)
+    assert st["stale_centre_events"] == 0
+
+
+def test_config3_au20_full_matrix():
+    """Au20, 860 AOs, 678 600 nominal / 198 152 executed triples, vs the reference's matrix"""
+    s = synth.cfg3(20)
+    with capi.Handle(s) as h:
+        rc, M = h.integrals_host()
+        st = h.stats()
+    assert rc == 0
+    assert st["nominal_triples"] == 678600 and st["executed_triples"] == 198152
+    assert_parity(M, load_matrix("cfg3"), "cfg3")
+
+
+@pytest.mark.parametrize("centre", [0, 1, 288, 289])
+def test_config5_single_centre_digest(centre):
+    """500-atom PbS crystal with one active centre: row/column sums and 40 000 sampled elements of the
+    19 000 x 19 000 partial matrix vs the reference"""
+    z = np.load(os.path.join(GOLDEN, f"cfg5_c{centre}_digest.npz"))
+    s = synth.cfg5(500, active=[centre])
+    with capi.Handle(s) as h:
+        rc, M = h.integrals_host()
+    assert rc == 0
+    # identical screening => identical row support (exact zeros inside a block may differ in the last ulp)
+    assert np.array_equal(np.abs(M).sum(1) > 0, z["rowabs"] > 0)
+    assert abs(int((M != 0).sum()) - int(z["nnz"])) <= 0.02 * int(z["nnz"])
+    assert_parity(M.ravel()[z["sample_idx"]], z["sample_val"], f"cfg5 centre {centre} sample")
+    scale = z["rowabs"]
+    assert np.all(np.abs(M.sum(1) - z["rowsum"]) <= 1e-11 + 1e-10 * scale)
+    assert abs(M.sum() - float(z["sum"])) <= 1e-9 * float(z["sumabs"])
+
+
+def test_properties_at_scale():
+    """size-independent properties on a 60-atom slice of config 5 (two ECP types, ~1.3 M executed triples):
+    additivity over centres, shard union == unsharded, zero lower triangle, batch-size independence"""
+    s = synth.cfg5(60)
+    with capi.Handle(s) as h:
+        rc, full = h.integrals_host()
+        n_exec = h.stats()["executed_triples"]
+        assert rc == 0 and n_exec > 100000
+        assert np.all(np.tril(full, -1) == 0.0)
+        acc = np.zeros_like(full)
+        tot = 0
+        for rank in range(4):
+            h.set_shard(rank, 4)
+            rc, part = h.integrals_host()
+            assert rc == 0
+            assert not np.any((part != 0) & (acc != 0))  # disjoint output blocks
+            acc += part
+            tot += h.stats()["executed_triples"]
+        assert tot == n_exec
+        assert_parity(acc, full, "shard union")
+    os.environ["LIBECP_B200_BATCH_TRIPLES"] = "50000"
+    try:
+        with capi.Handle(s) as h:
+            rc, small_batches = h.integrals_host()
+            assert h.stats()["batches"] > 5
+    finally:
+        del os.environ["LIBECP_B200_BATCH_TRIPLES"]
+    assert_parity(small_batches, full, "batching")
+    half = [i for i in range(60) if i % 2 == 0]
+    other = [i for i in range(60) if i % 2 == 1]
+    a = capi.get_integrals(synth.mask_centres(s, half))
+    b = capi.get_integrals(synth.mask_centres(s, other))
+    assert_parity(a + b, full, "additivity over centres")
+
+
+def test_structural_invariants():
+    with capi.Handle(synth.cfg3(3)) as h:
+        rc, recs = h.callbacks()
+    assert rc == 0
+    for (A, s1, la, _, B, s2, lb, _, C, blk) in recs:
+        if A == B == C and (la + lb) % 2 == 1:
+            assert np.all(np.abs(blk) <= 1e-13)
+        if A == B and s1 == s2:
+            n = (la + 1) * (la + 2) // 2
+            m = blk.reshape(n, n)
+            assert np.allclose(m, m.T, rtol=1e-10, atol=1e-12)
+
+
+def test_edge_cases():
+    # atom without ECP in the middle, atom without basis functions, ragged shells
+    s = synth.cfg3(3)
+    s2 = synth.mask_centres(s, [0, 2])
+    ref = RefLib("ref" if have("ref") else "port").get_integrals(s2)
+    assert_parity(capi.get_integrals(s2), ref, "masked centre")
+    # no ECP at all: nothing to do, matrix untouched
+    s0 = synth.mask_centres(s, [])
+    assert np.all(capi.get_integrals(s0) == 0.0)
+    # getIntegrals accumulates (+=) into a pre-filled upper triangle
+    with capi.Handle(synth.cfg2()) as h:
+        rc, M = h.integrals_host()
+        rc, M2 = h.integrals_host()  # handle is reusable
+    assert np.array_equal(M, M2) or np.allclose(M, M2, rtol=1e-13, atol=1e-14)
+
+
+def test_device_resident_matrix_matches_host_copy():
+    import torch
+
+    s = synth.cfg3(2)
+    with capi.Handle(s) as h:
+        rc, ptr, n = h.integrals_device()
+        assert rc == 0 and n == s["dim"] and ptr
+        rc, M = h.integrals_host()
+    assert torch.cuda.is_available()
+    assert_parity(M, load_matrix("au2"), "device-resident path")

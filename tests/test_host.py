@@ -1,0 +1,236 @@
+"""CPU tier: host logic of the product (no compute calls - there is no CPU compute path):
+C-ABI exports, bit-exact host tables, screening decisions, executed-triple list, shard partition,
+and the per-thread device math compiled for the host (tests/hostcheck) against the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from libecp_b200 import build, capi, synth
+from oracle.refbind import RefLib, _p, _pd, _pi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SHAPES = {"cfg1": synth.cfg1, "au4": lambda: synth.cfg3(4), "cfg4b": lambda: synth.cfg4("b"),
+          "cfg5s": lambda: synth.cfg5(30)}
+
+
+class Oracle:
+    """thin wrapper over the restatement's unit-level accessors"""
+
+    def __init__(self, s):
+        self.p = RefLib("port")
+        L = self.L = self.p.lib
+        L.oracle_table.restype = _pd
+        L.oracle_table.argtypes = [C.c_void_p, C.c_char_p, _pi]
+        L.oracle_bessel.argtypes = [C.c_void_p, C.c_int, C.c_double, _pd]
+        L.oracle_rsh.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _pd]
+        L.oracle_screening.argtypes = [C.c_void_p, C.c_int, _pi, _pi, _pi, _pi]
+        L.oracle_ps93_table.argtypes = [C.c_void_p, _pd, C.c_int, C.c_int, _pd, _pi]
+        self.s = s
+        self.h = self.p.f_init(
+            C.c_int(s["nat"]), _p(s["geometry"], _pd), _p(s["shellsECP"], _pi), _p(s["lECP"], _pi), _p(s["KECP"], _pi),
+            _p(s["nECP"], _pd), _p(s["dECP"], _pd), _p(s["aECP"], _pd), _p(s["shellsBS"], _pi), _p(s["lBS"], _pi),
+            _p(s["KBS"], _pi), _p(s["dBS"], _pd), _p(s["aBS"], _pd), C.c_int(0), C.c_int(-1), None, C.c_int(1024),
+            C.c_double(1e-12), C.c_double(1e-14))
+        assert self.h
+
+    def table(self, name):
+        n = C.c_int()
+        ptr = self.L.oracle_table(C.c_void_p(self.h), name.encode(), C.byref(n))
+        return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+
+    def close(self):
+        self.p.f_free(C.c_void_p(self.h))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """the shared library loads without a GPU and exports every function include/*.h declares"""
+    L = capi.lib()
+    declared = set()
+    for hdr in ("libecp.h", "getIntegrals.h", "dimensions.h", "libecp_b200.h"):
+        txt = open(os.path.join(ROOT, "include", hdr)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", txt):
+            name = m.group(1)
+            if name.startswith(("libECP_", "libecp_b200_", "cartesianShellOrder")) or name in (
+                    "calculateECPIntegrals", "getIntegrals"):
+                declared.add(name)
+    assert {"libECP_init", "calculateECPIntegrals", "libECP_free", "getIntegrals"} <= declared
+    for name in declared:
+        assert hasattr(L, name), name
+    assert set(capi.EXPORTS) <= declared
+
+
+def test_no_cpu_fallback_without_device():
+    """a tables-only handle refuses every compute entry point"""
+    import torch
+
+    s = synth.cfg2()
+    with capi.Handle(s, tables_only=True) as h:
+        rc, recs = h.callbacks()
+        assert rc < 0 and recs == []
+        with pytest.raises(RuntimeError):
+            h.integrals_host()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            capi.Handle(s)  # libECP_init -> NULL: no device, loud failure
+
+
+def test_unsupported_arguments_rejected():
+    s = synth.cfg2()
+    with pytest.raises(RuntimeError):
+        capi.Handle(s, n=1, tables_only=True)  # derivatives: SURVEY §8f, not built yet
+    bad = synth.assemble("bad", [(0, 0, 0)], [synth.tz_basis(5)], [synth.ecp_set(3)])  # maxLBS > L+1
+    with pytest.raises(RuntimeError):
+        capi.Handle(bad, tables_only=True)
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_host_tables_bitwise(name):
+    s = SHAPES[name]()
+    o = Oracle(s)
+    with capi.Handle(s, tables_only=True) as h:
+        for t in ["fac", "dfac", "poly2sph", "omega", "small_x", "small_w", "large_x", "large_w", "bessel", "besselC"]:
+            assert np.array_equal(o.table(t), h.host_table(t)), t
+        # slot layouts are permutations of the original grids
+        oidx = h.host_itable("small_oidx")
+        assert sorted(oidx[oidx >= 0]) == list(range(383)) and (oidx < 0).sum() == 1
+        assert np.array_equal(h.host_table("small_rs")[oidx >= 0], h.host_table("small_x")[oidx[oidx >= 0]])
+        lo = h.host_itable("large_oidx")
+        assert sorted(lo[lo >= 0]) == list(range(1023))
+        assert np.array_equal(h.host_table("large_ws")[lo >= 0], h.host_table("large_w")[lo[lo >= 0]])
+        # transposed Bessel table
+        dims = h.host_itable("dims")
+        lmax, stride = int(dims[5]), int(dims[6])
+        bT = h.host_table("besselT").reshape(1601, stride)
+        assert np.array_equal(bT[:, :lmax + 1].T, h.host_table("bessel").reshape(lmax + 1, 1601))
+    o.close()
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_screening_and_triple_list_identical(name):
+    s = SHAPES[name]()
+    o = Oracle(s)
+    ns = int(s["nshells"])
+    with capi.Handle(s, tables_only=True) as h:
+        for c in range(s["nat"]):
+            if s["shellsECP"][c] == 0:
+                continue
+            endl = np.zeros(8, np.int32)
+            st, en, sk = (np.zeros(ns, np.int32) for _ in range(3))
+            o.L.oracle_screening(C.c_void_p(o.h), c, _p(endl, _pi), _p(st, _pi), _p(en, _pi), _p(sk, _pi))
+            e2, st2, en2, sk2 = h.screening(c, 8)
+            L = int(max(s["lECP"]))  # same L everywhere in these shapes except cfg5s: compare the common prefix
+            assert np.array_equal(sk, sk2)
+            live = sk == 0
+            assert np.array_equal(st[live], st2[live]) and np.array_equal(en[live], en2[live])
+            if name != "cfg5s":
+                assert np.array_equal(endl[:L], e2[:L])
+        rc, recs = o.p.callbacks(s, keep_blocks=False)
+        ref = np.array([(r[0], r[1], r[2], r[4], r[5], r[6], r[8]) for r in recs[::2]], np.int32).reshape(-1, 7)
+        assert np.array_equal(h.triple_list(), ref)
+    o.close()
+
+
+def test_shards_partition_the_triples():
+    s = synth.cfg3(4)
+    with capi.Handle(s, tables_only=True) as h:
+        full = {tuple(r) for r in h.triple_list()}
+        seen = set()
+        for world in (2, 8):
+            seen.clear()
+            sizes = []
+            for rank in range(world):
+                h.set_shard(rank, world)
+                part = {tuple(r) for r in h.triple_list()}
+                assert not (part & seen)
+                seen |= part
+                sizes.append(len(part))
+            assert seen == full
+            assert max(sizes) < 1.35 * len(full) / world
+        h.set_shard(0, 1)
+
+
+@pytest.fixture(scope="module")
+def hc():
+    L = C.CDLL(build.build_hostcheck())
+    L.hc_bessel.argtypes = [_pd, C.c_int, _pd, C.c_int, C.c_double, _pd]
+    L.hc_rsh.argtypes = [C.c_int, C.c_double, C.c_double, _pd, _pd, _pd]
+    L.hc_ps93_fastT.argtypes = [_pd, _pd, _pd, _pd, _pi, _pi, C.c_int, C.c_int, C.c_double, _pd, _pi]
+    L.hc_sphcoord.argtypes = [_pd, _pd]
+    return L
+
+
+def test_device_math_bessel_rsh_bitwise(hc):
+    """ecp_math.h (the code the kernels run) == oracle on a z sweep across the three Bessel branches and on
+    random / special angles"""
+    s = synth.cfg4("b")
+    o = Oracle(s)
+    rng = np.random.default_rng(7)
+    with capi.Handle(s, tables_only=True) as h:
+        bT, bC = h.host_table("besselT"), h.host_table("besselC")
+        stride = int(h.host_itable("dims")[6])
+        zs = np.concatenate([[0.0, -1.0, 1e-9, 9.9e-8, 1e-7, 1.00001e-7, 0.005, 15.995, 15.999999, 16.0, 16.00001,
+                              50.0, 1e3, 1e5], rng.uniform(0, 16, 600), 10 ** rng.uniform(-9, 4, 600)])
+        for z in zs:
+            for lmax in (0, 3, 6, 10):
+                a, b = np.zeros(lmax + 1), np.zeros(lmax + 1)
+                o.L.oracle_bessel(C.c_void_p(o.h), lmax, float(z), _p(a, _pd))
+                hc.hc_bessel(_p(bT, _pd), stride, _p(bC, _pd), lmax, float(z), _p(b, _pd))
+                assert np.array_equal(a, b), (z, lmax)
+        fac, dfac = h.host_table("fac"), h.host_table("dfac")
+        angles = [(0, 0), (np.pi, 0), (np.arccos(0.0), 0.5 * np.pi), (1.0, 1.5 * np.pi), (0.3, -1.2)]
+        angles += [(rng.uniform(0, np.pi), rng.uniform(-1.5, 4.7)) for _ in range(100)]
+        for th, ph in angles:
+            for lmax in (0, 1, 6, 10):
+                a, b = np.zeros((lmax + 1) ** 2), np.zeros((lmax + 1) ** 2)
+                o.L.oracle_rsh(C.c_void_p(o.h), lmax, th, ph, _p(a, _pd))
+                hc.hc_rsh(lmax, th, ph, _p(fac, _pd), _p(dfac, _pd), _p(b, _pd))
+                assert np.array_equal(a, b)
+    o.close()
+
+
+def test_device_math_ps93_windowed_bitwise(hc):
+    """the slot-ordered PS93 of the fast path reproduces integrateGC_PS93 (value, stop level, failures)
+    on full and windowed integrand tables"""
+    s = synth.cfg2()
+    o = Oracle(s)
+    rng = np.random.default_rng(3)
+    with capi.Handle(s, tables_only=True) as h:
+        x, ws = h.host_table("small_x"), h.host_table("small_ws")
+        oidx = h.host_itable("small_oidx").astype(np.int32)
+        meta = h.host_itable("small_meta").astype(np.int32)
+
+        def perm(v):
+            out = np.zeros(384)
+            m = oidx >= 0
+            out[m] = v[oidx[m]]
+            return out
+
+        nfail = 0
+        for trial in range(200):
+            a, c = rng.uniform(0.05, 30), rng.uniform(0, 6)
+            st = int(rng.integers(0, 200))
+            en = int(rng.integers(st, 383))
+            if trial % 3 == 0:
+                st, en = 0, 382
+            Fa = np.exp(-a * (x - c) ** 2)
+            Fb = 1.0 / (1 + x)
+            U = x ** rng.integers(0, 4)
+            Fa[:st] = 0
+            Fa[en:] = 0
+            f = Fa * Fb * U
+            r1, n1 = np.zeros(1), np.zeros(1, np.int32)
+            rc1 = o.L.oracle_ps93_table(C.c_void_p(o.h), _p(f, _pd), st, en, _p(r1, _pd), _p(n1, _pi))
+            r2, n2 = np.zeros(1), np.zeros(1, np.int32)
+            rc2 = hc.hc_ps93_fastT(_p(perm(Fa), _pd), _p(perm(Fb), _pd), _p(perm(U), _pd), _p(ws, _pd), _p(oidx, _pi),
+                                   _p(meta, _pi), st, en, 1e-12, _p(r2, _pd), _p(n2, _pi))
+            nfail += rc1
+            assert rc1 == rc2 and n1[0] == n2[0]
+            if rc1 == 0:
+                assert r1[0] == r2[0]
+        assert 0 < nfail < 200
+    o.close()
