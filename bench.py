@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py - ECP shell-pair x centre triples/s of the B200-native libECP hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg5|cfg3|...]
+
+Workload (config.workload): BASELINE.json configs[4], the 500-heavy-atom PbS-like nanocrystal
+(9.77e9 nominal / ~2e7 executed triples, 19 000 AOs) - the largest configuration, it fits one GPU and is the
+one the multi-GPU target is quoted on.  The Au20 configuration (configs[2], the one the FP64-roofline target is
+quoted on) is measured as `secondary` in the same JSON line at N=1.
+
+A "step" is one full pass of the hot path: host batch build (screening, triple list), H2D of the batch
+arrays, all kernels; `value` leaves the ECP matrix resident in HBM, `e2e` goes through the reference-facing
+getIntegrals-equivalent call on HOST buffers (handle creation + table upload + D2H of the matrix inside the
+timed region).  Under torchrun each rank owns a disjoint set of shell pairs (no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from libecp_b200 import synth  # noqa: E402
+
+METRIC = "ECP shell-pair x centre triples/sec (FP64)"
+UNIT = "nominal triples/s"
+
+
+def make_workload(name):
+    if name == "cfg5":
+        return synth.cfg5(500), "cfg5: 500-atom PbS-like rock-salt nanocrystal, TZ(3)+ECP(4) / TZ(2)+ECP(2), 19000 AOs"
+    if name == "cfg3":
+        return synth.cfg3(20), "cfg3: Au20 tetrahedron, TZ(3)+ECP(4), 860 AOs"
+    if name == "cfg2":
+        return synth.cfg2(), "cfg2: single heavy atom TZ(3)+ECP(4)"
+    if name == "cfg4b":
+        return synth.cfg4("b"), "cfg4b: 2 atoms s-h basis, ECP(6)"
+    if name.startswith("cfg5_"):
+        n = int(name.split("_")[1])
+        return synth.cfg5(n), f"cfg5 slice: first {n} sites of the PbS crystal"
+    raise SystemExit("unknown workload " + name)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation on the host cores
+def _ref_worker(args):
+    """one process = one single-threaded run of the reference restricted to the given ECP centres"""
+    import ctypes as C
+
+    from oracle import refbind
+
+    workload, centres = args
+    kind = "ref" if refbind.have("ref") else "port"
+    lib = refbind.RefLib(kind)
+    port = C.CDLL(refbind.PORT_SO)
+    s_full, _ = make_workload(workload)
+    s = synth.mask_centres(s_full, centres)
+    _p, _pd, _pi = refbind._p, refbind._pd, refbind._pi
+    t0 = time.perf_counter()
+    h = lib.f_init(C.c_int(s["nat"]), _p(s["geometry"], _pd), _p(s["shellsECP"], _pi), _p(s["lECP"], _pi),
+                   _p(s["KECP"], _pi), _p(s["nECP"], _pd), _p(s["dECP"], _pd), _p(s["aECP"], _pd),
+                   _p(s["shellsBS"], _pi), _p(s["lBS"], _pi), _p(s["KBS"], _pi), _p(s["dBS"], _pd), _p(s["aBS"], _pd),
+                   C.c_int(0), C.c_int(-1), None, C.c_int(1024), C.c_double(1e-12), C.c_double(1e-14))
+    chk = C.c_double(0.0)
+    cb = C.cast(port.oracle_sum_callback, C.c_void_p)
+    lib.f_calc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.f_calc(C.c_void_p(h), cb, C.cast(C.pointer(chk), C.c_void_p))
+    lib.f_free(C.c_void_p(h))
+    return time.perf_counter() - t0, rc, chk.value, kind
+
+
+def centre_order(s):
+    """fixed pseudo-random order of the ECP centres (so any prefix is a representative sample)"""
+    cs = np.flatnonzero(s["shellsECP"] > 0)
+    return [int(c) for c in np.random.default_rng(2024).permutation(cs)]
+
+
+def reference_step(pool, workload, s, cores, step, per_proc):
+    order = centre_order(s)
+    n = len(order)
+    jobs = []
+    for p in range(cores):
+        cs = [order[(step * cores * per_proc + p * per_proc + k) % n] for k in range(per_proc)]
+        jobs.append((workload, sorted(set(cs))))
+    t0 = time.perf_counter()
+    res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    ncent = sum(len(j[1]) for j in jobs)
+    ns = int(s["nshells"])
+    nominal = ncent * ns * (ns + 1) // 2
+    return wall, nominal, ncent, res
+
+
+def run_reference(args):
+    import multiprocessing as mp
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    s, desc = make_workload(args.workload)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ncentres = int((s["shellsECP"] > 0).sum())
+    per_proc = 1 if args.workload.startswith("cfg5") else max(1, ncentres // cores)
+    if not args.workload.startswith("cfg5"):
+        cores = min(cores, ncentres)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            reference_step(pool, args.workload, s, cores, w, per_proc)
+        t_tot, nom_tot, ncent_tot, kind = 0.0, 0, 0, "port"
+        for k in range(args.steps):
+            wall, nominal, ncent, res = reference_step(pool, args.workload, s, cores, args.warmup + k, per_proc)
+            t_tot += wall
+            nom_tot += nominal
+            ncent_tot += ncent
+            kind = res[0][3]
+    value = nom_tot / t_tot
+    sample = f"{ncent_tot} ECP centres of {ncentres} ({ncent_tot / args.steps:.0f} per step, one per process), all shell pairs"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
+                         "kind": "reference" if kind == "ref" else "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def falg_per_kernel(workload, executed):
+    """algorithmic flops (touched/used work only, oracle-counted; tests/golden/falg.json, tools/make_falg.py)"""
+    with open(os.path.join(ROOT, "tests", "golden", "falg.json")) as f:
+        fa = json.load(f)
+    if workload in fa:
+        return dict(fa[workload]["flops"]), "exact (instrumented oracle, full run)"
+    if workload.startswith("cfg5"):
+        keys = [k for k in fa if k.startswith("cfg5_c")]
+        ex = sum(fa[k]["executed"] for k in keys)
+        out = {kk: sum(fa[k]["flops"][kk] for k in keys) / ex * executed for kk in fa[keys[0]]["flops"]}
+        return out, f"extrapolated from {len(keys)} sampled centres ({int(ex)} executed triples) by executed-triple count"
+    return None, "no algorithmic-flop count for this workload"
+
+
+KERNEL_OF = {"tables": "ms_tables", "fastT": "ms_fastT", "fallback": "ms_fallback", "link": "ms_link",
+             "type1": "ms_type1", "chi": "ms_chi", "shift": "ms_shift"}
+KERNEL_NAME = {"tables": "k_atomslot+k_omegaX+k_Ftab", "fastT": "k_fastT", "fallback": "k_fallbackT", "link": "k_link",
+               "type1": "k_t1prep+k_type1Q", "chi": "k_chi", "shift": "k_shift"}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def roofline(workload, stats, nsteps, peak_tf):
+    flops, how = falg_per_kernel(workload, stats["executed_triples"])
+    if not flops:
+        return None
+    times = {k: stats[v] for k, v in KERNEL_OF.items()}
+    dom = max(times, key=lambda k: times[k])
+    ach = flops[dom] / (times[dom] * 1e-3) / 1e12 if times[dom] > 0 else 0.0
+    span = stats["ms_device_total"]
+    return {
+        "bound": "fp64", "kernel": KERNEL_NAME[dom], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+        "peak_source": "FP64 FMA probe kernel run by bench.py on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
+                       "vendor figure ~37-40 TFLOP/s)",
+        "algorithmic_flops_per_step": flops["total"], "algorithmic_flops_kernel": flops[dom], "flops_count": how,
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in times.items()},
+        "whole_step_achieved": flops["total"] / (span * 1e-3) / 1e12 if span > 0 else 0.0,
+        "whole_step_frac": (flops["total"] / (span * 1e-3) / 1e12) / peak_tf if span > 0 and peak_tf else None,
+    }
+
+
+def run_b200(args):
+    import torch
+
+    from libecp_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
+    torch.cuda.set_device(local)
+    capi.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    s, desc = make_workload(args.workload)
+    ns = int(s["nshells"])
+    nominal = int((s["shellsECP"] > 0).sum()) * ns * (ns + 1) // 2
+    h = capi.Handle(s)
+    h.set_shard(rank, world)
+    for _ in range(args.warmup):
+        h.integrals_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = None
+    ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc, ptr, n = h.integrals_device()
+        st = h.stats()
+        agg = st if agg is None else {k: agg[k] + v for k, v in st.items()}
+    torch.cuda.synchronize()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = max(ev0.elapsed_time(ev1), 0.0)
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = {k: v / args.steps for k, v in agg.items()}
+    executed_all = sum_over_ranks(stats["executed_triples"])
+    launches = sum_over_ranks(agg["kernel_launches"])
+    value = nominal * args.steps / (ms * 1e-3)
+
+    # ---- e2e: getIntegrals-equivalent on host buffers (handle creation, tables, H2D, kernels, D2H) ----
+    dim = int(s["dim"])
+    host = torch.zeros((dim, dim), dtype=torch.float64).pin_memory().numpy() if dim * dim * 8 < (8 << 30) else np.zeros((dim, dim))
+    e2e_steps = max(1, min(args.steps, 3))
+    import ctypes as C
+
+    def e2e_once():
+        with capi.Handle(s) as hh:
+            hh.set_shard(rank, world)
+            host[:] = 0.0
+            rc_ = capi.lib().libecp_b200_integrals_host(C.c_void_p(hh.h), dim, host.ctypes.data_as(capi._pd))
+            stx = hh.stats()
+        return stx
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        st_e = e2e_once()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e = {"value": nominal / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(sum_over_ranks(st_e["h2d_bytes"] + st_e["tables_h2d_bytes"])),
+           "d2h_bytes_per_step": int(sum_over_ranks(st_e["d2h_bytes"])), "ms_per_step": 1e3 * e2e_s,
+           "note": "libECP_init + integrate + D2H of the matrix + host += per step"}
+
+    # ---- roofline, secondary (Au20) and CPU baseline on rank 0 / N=1 ----
+    line = None
+    if rank == 0:
+        peak_tf = capi.fp64_peak(local, 100000)
+        rl = roofline(args.workload, stats, args.steps, peak_tf) if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "nominal_triples": nominal, "executed_triples": int(executed_all),
+                       "parallelism": f"shell-pair ownership x{world}, no data-path collective",
+                       "l2": "per-step working set (F/T/gamma/chi intermediates, GBs) exceeds the 126 MB L2; no flush needed",
+                       "timed_region": "host batch build + H2D of batch arrays + all kernels; matrix stays in HBM"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "host_ms_build_per_step": stats["ms_build"], "device_ms_per_step": stats["ms_device_total"],
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+        }
+        if rl:
+            line["roofline"] = rl
+    if world == 1 and rank == 0 and not args.no_secondary and args.workload != "cfg3":
+        line["secondary"] = secondary_au20(capi, torch, peak_tf)
+    h.close()
+    if world == 1 and rank == 0 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.workload, s)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def secondary_au20(capi, torch, peak_tf):
+    """Au20 (BASELINE configs[2]): the configuration the FP64-roofline target is quoted on; L2 flushed between steps"""
+    s, desc = make_workload("cfg3")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    steps = 20
+    with capi.Handle(s) as h:
+        for _ in range(3):
+            h.integrals_device()
+        agg, tot = None, 0.0
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            h.integrals_device()
+            tot += time.perf_counter() - t0
+            st = h.stats()
+            agg = st if agg is None else {k: agg[k] + v for k, v in st.items()}
+        stats = {k: v / steps for k, v in agg.items()}
+    rl = roofline("cfg3", stats, steps, peak_tf)
+    ns = int(s["nshells"])
+    nominal = int((s["shellsECP"] > 0).sum()) * ns * (ns + 1) // 2
+    return {"workload": desc, "value": nominal / (tot / steps), "unit": UNIT, "ms_per_step": 1e3 * tot / steps,
+            "device_ms_per_step": stats["ms_device_total"], "host_ms_build_per_step": stats["ms_build"],
+            "executed_triples": int(stats["executed_triples"]), "l2": "flushed (256 MiB write) between steps",
+            "roofline": rl}
+
+
+def cpu_baseline(workload, s):
+    """the reference CPU path on this box's host cores, bounded sample (one ECP centre per core)"""
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ncentres = int((s["shellsECP"] > 0).sum())
+    per_proc = 1 if workload.startswith("cfg5") else max(1, ncentres // cores)
+    if not workload.startswith("cfg5"):
+        cores = min(cores, ncentres)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        wall, nominal, ncent, res = reference_step(pool, workload, s, cores, 0, per_proc)
+    kind = res[0][3]
+    return {"value": nominal / wall, "unit": UNIT, "cores": cores, "kind": "reference" if kind == "ref" else "port",
+            "sample": f"{ncent} of {ncentres} ECP centres (one per process), all shell pairs, {wall:.1f} s wall",
+            "per_core": nominal / wall / cores}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg5")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Au20 secondary measurement")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,8 @@ typedef struct {
   long long shell_slots, atom_slots, prim_pairs;
   long long fast_quadratures, fast_failed, fallback_items, type1_fallback_pairs, stale_centre_events;
   long long kernel_launches, batches;
+  long long h2d_bytes, d2h_bytes;  /* host<->device traffic of the last run (tables_h2d_bytes: once per handle) */
+  long long tables_h2d_bytes;
   double ms_build, ms_tables, ms_fastT, ms_fallback, ms_link, ms_type1, ms_chi, ms_shift, ms_device_total;
 } libecp_b200_stats_t;
 void libecp_b200_get_stats(libECPHandle *h, libecp_b200_stats_t *out);

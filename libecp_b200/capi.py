@@ -31,7 +31,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in (
         "nominal_triples", "executed_triples", "shell_slots", "atom_slots", "prim_pairs", "fast_quadratures",
         "fast_failed", "fallback_items", "type1_fallback_pairs", "stale_centre_events", "kernel_launches",
-        "batches")] + [(n, C.c_double) for n in (
+        "batches", "h2d_bytes", "d2h_bytes", "tables_h2d_bytes")] + [(n, C.c_double) for n in (
             "ms_build", "ms_tables", "ms_fastT", "ms_fallback", "ms_link", "ms_type1", "ms_chi", "ms_shift",
             "ms_device_total")]
 

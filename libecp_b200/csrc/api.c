@@ -124,6 +124,9 @@ static void add_stats(libECPHandle *h, const EcpDevStats *st, double msBuild) {
   s->stale_centre_events += st->nStaleCentre;
   s->kernel_launches += st->launches;
   s->batches += 1;
+  s->h2d_bytes += st->h2dBytes;
+  s->d2h_bytes += st->d2hBytes;
+  s->tables_h2d_bytes = ecpdev_table_bytes(h->dev);
   s->ms_build += msBuild;
   s->ms_tables += st->ms_tables;
   s->ms_fastT += st->ms_fastT;
@@ -203,6 +206,7 @@ int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   if (rc < 0 || h->empty) return rc;
   double *M = malloc((size_t)n * n * sizeof(double));
   const int rc2 = ecpdev_matrix_download(h->dev, M);
+  h->stats.d2h_bytes += (long long)n * n * 8;
   if (rc2) {
     free(M);
     return -rc2;

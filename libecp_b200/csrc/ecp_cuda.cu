@@ -807,6 +807,7 @@ struct EcpDev {
   Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
   double *matrix;
   size_t lastSizes[8];
+  long long tableBytes, batchH2D;
 };
 
 static int ensure(Buf *b, size_t bytes) {
@@ -827,6 +828,7 @@ static const T *upload_const(EcpDev *d, const T *h, size_t n) {
   size_t bytes = (n ? n : 1) * sizeof(T);
   if (cudaMalloc(&bf->p, bytes) != cudaSuccess) return NULL;
   bf->cap = bytes;
+  d->tableBytes += (long long)(n * sizeof(T));
   if (n && cudaMemcpy(bf->p, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return NULL;
   return (const T *)bf->p;
 }
@@ -962,6 +964,7 @@ extern "C" int ecpdev_matrix_download(EcpDev *d, double *host) {
   return 0;
 }
 extern "C" void *ecpdev_matrix_ptr(EcpDev *d) { return d->matrix; }
+extern "C" long long ecpdev_table_bytes(EcpDev *d) { return d->tableBytes; }
 extern "C" int ecpdev_sync(EcpDev *d) {
   CK(cudaSetDevice(d->device));
   CK(cudaStreamSynchronize(d->s1));
@@ -974,6 +977,7 @@ extern "C" int ecpdev_sync(EcpDev *d) {
     int rc_ = ensure(&d->buf, ((n) ? (n) : 1) * sizeof(T));                                               \
     if (rc_) return rc_;                                                                                  \
     if (n) CK(cudaMemcpyAsync(d->buf.p, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, d->s1));    \
+    d->batchH2D += (long long)((size_t)(n) * sizeof(T));                                                  \
     B.field = (const T *)d->buf.p;                                                                        \
   } while (0)
 #define SCRATCH(buf, field, n, T)                                   \
@@ -994,6 +998,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   B.nTriples = h->nTriples;
   B.nPairs = h->nPairs;
   if (st) memset(st, 0, sizeof(*st));
+  d->batchH2D = 0;
   if (h->nTriples == 0) return 0;
   UP(asAtom, asAtom, h->asAtom, h->nASlots, int);
   UP(asType, asType, h->asType, h->nASlots, int);
@@ -1111,6 +1116,8 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
     st->nType1Fail = hc[5];
     st->nStaleCentre = hc[6];
     st->launches = launches;
+    st->h2dBytes = d->batchH2D;
+    st->d2hBytes = (long long)sizeof(hc) + (((flags & 2) && hostBlocks) ? (long long)h->outTotal * 8 : 0);
     st->err1 = hc[2];
     st->err2 = hc[3];
   }

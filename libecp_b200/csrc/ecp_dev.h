@@ -109,7 +109,7 @@ typedef struct {
 
 typedef struct {
   double ms_tables, ms_fastT, ms_fallback, ms_link, ms_type1, ms_chi, ms_shift, ms_total;
-  long long nFallbackItems, nFastFail, nType1Fail, nStaleCentre, launches;
+  long long nFallbackItems, nFastFail, nType1Fail, nStaleCentre, launches, h2dBytes, d2hBytes;
   int err1, err2;
 } EcpDevStats;
 
@@ -126,6 +126,7 @@ void *ecpdev_matrix_ptr(EcpDev *d);
 /* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks */
 int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, double *hostBlocks, EcpDevStats *stats);
 int ecpdev_sync(EcpDev *d);
+long long ecpdev_table_bytes(EcpDev *d);
 /* debug access to the intermediates of the last batch (tests only): "F" "omegaX" "T" "gamma" "chi" "Q" "tfail" */
 int ecpdev_debug_fetch(EcpDev *d, const char *what, double *dst, int64_t n);
 /* FP64 FMA peak probe used by bench.py for the roofline denominator: returns TFLOP/s */
