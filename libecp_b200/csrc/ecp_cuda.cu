@@ -445,239 +445,7 @@ __global__ void k_t1prep(DevT t, DevB b) {
   b.sP[pr] = r;
 }
 
-/* ---- type 1 radial integrals: one warp per primitive pair ---- */
-__global__ void __launch_bounds__(32) k_type1Q(DevT t, DevB b, int maxq) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const WarpSmem s = carve(smem_raw, maxq);
-  const int lane = threadIdx.x;
-  for (;;) {
-    long long pr = 0;
-    if (lane == 0) pr = atomicAdd(&b.counters[7], 1);
-    pr = __shfl_sync(0xffffffffu, pr, 0);
-    if (pr >= b.nPairs) break;
-    const int tri = b.prTriple[pr];
-    const int ssa = b.trA[tri], ssb = b.trB[tri];
-    const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
-    const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
-    const int Nb = t.shellK[shb];
-    const int ip = (int)(pr - b.trPair[tri]), pa = ip / Nb, pb = ip % Nb;
-    const double za = t.primA[t.shellPrim[sha] + pa], zb = t.primA[t.shellPrim[shb] + pb];
-    const double ca = t.primD[t.shellPrim[sha] + pa], cb = t.primD[t.shellPrim[shb] + pb];
-    const double dAC = b.asR[4 * asa + 3], dBC = b.asR[4 * asb + 3];
-    const int type = b.asType[asa];
-    const int Lc = t.typeL[type];
-    const int g0 = t.typeGaussOff[type], g1 = t.typeGaussOff[type + 1];
-    const int lab = t.shellL[sha] + t.shellL[shb];
-    const double sS = b.sP[pr];
-    const int gs = max(b.ssStart[ssa], b.ssStart[ssb]), ge = max(b.ssEnd[ssa], b.ssEnd[ssb]);
-    const double zd2 = -za * dAC * dAC - zb * dBC * dBC; /* src/type1.c:103 */
-    const double z = -za - zb;
-    const double *UL = t.typeUL + (size_t)type * ECP_SMALL_SLOTS;
-    /* quadrature list in the reference's order: N = 0..lab, lambda = N, N-2, ... (src/type1.c:132-135) */
-    int nq = 0;
-    for (int N = 0; N <= lab; N++) nq += N / 2 + 1;
-    for (int q = lane; q < nq; q += 32) {
-      int N = 0, base = 0;
-      while (base + N / 2 + 1 <= q) {
-        base += N / 2 + 1;
-        N++;
-      }
-      s.qk[q] = N | ((N - 2 * (q - base)) << 8);
-      s.done[q] = 0;
-      s.sAcc[q] = 0.0;
-    }
-    __syncwarp();
-    /* ---------- 1. small grid, PS93 (src/type1.c:121-146) ---------- */
-    {
-      const double Cc = ca * cb * exp(zd2);
-      int curChunk = -1;
-      for (int lev = -1; lev < ECP_SMALL_LEVELS; lev++) {
-        /* lev -1 = the three unconditional points (slots 0,2,3) */
-        const int sl0 = (lev < 0) ? 0 : t.sm.levSlot[lev], sl1 = (lev < 0) ? 4 : t.sm.levSlot[lev + 1];
-        if (lev >= 0) {
-          int alldone = 1;
-          for (int q = lane; q < nq; q += 32) alldone &= (s.done[q] != 0);
-          if (__all_sync(0xffffffffu, alldone)) break;
-        }
-        int cnt = 0;
-        for (int ch = sl0 >> 5; ch <= (sl1 - 1) >> 5; ch++) {
-          if (ch != curChunk) {
-            __syncwarp();
-            const int slot = ch * 32 + lane;
-            double *row = s.rows + lane * ROWSTRIDE;
-            const int oi = t.small_oidx[slot];
-            if (oi >= gs && oi < ge) { /* tabulated range is [start,end): src/type1.c:121 */
-              const double r = t.small_r[slot];
-              double K[KM + 1];
-              ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lab, sS * r, K);
-              const double e = (z * r + sS) * r;
-              row[ROW_W] = t.small_w[slot];
-              row[ROW_CU] = UL[slot];
-              row[ROW_EX] = (e >= t.lnAcc1) ? exp(e) : 0.0;
-              row[ROW_KB] = (e >= t.lnAcc1) ? 1.0 : 0.0; /* gate flag */
-              double rn = 1.0;
-#pragma unroll
-              for (int i = 0; i <= KM; i++) {
-                row[ROW_RN + i] = rn;
-                rn = r * rn;
-                row[ROW_KA + i] = (i <= lab) ? K[i] : 0.0;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 3 + 3 * (KM + 1); i++) row[i] = 0.0;
-              row[ROW_W] = (oi >= 0) ? t.small_w[slot] : 0.0;
-            }
-            curChunk = ch;
-            __syncwarp();
-          }
-          const int lo = max(sl0, ch * 32) - ch * 32, hi = min(sl1, ch * 32 + 32) - ch * 32;
-          /* window flags of this level's points (uniform over the warp) */
-          if (lev >= 0)
-            for (int sidx = lo; sidx < hi; sidx += 2) {
-              cnt += (t.small_oidx[ch * 32 + sidx] >= gs);
-              cnt += (t.small_oidx[ch * 32 + sidx + 1] <= ge);
-            }
-          for (int q = lane; q < nq; q += 32) {
-            if (s.done[q]) continue;
-            const int N = s.qk[q] & 255, lam = s.qk[q] >> 8;
-#define T1VAL(rw) ((rw)[ROW_KB] != 0.0 ? Cc * (rw)[ROW_RN + N] * (rw)[ROW_CU] * (rw)[ROW_KA + lam] * (rw)[ROW_EX] : 0.0)
-            if (lev < 0) {
-              const double *r0 = s.rows, *r2 = s.rows + 2 * ROWSTRIDE, *r3 = s.rows + 3 * ROWSTRIDE;
-              const double p = r0[ROW_W] * T1VAL(r0);
-              const double qv = r2[ROW_W] * T1VAL(r2) + r3[ROW_W] * T1VAL(r3);
-              s.sP[q] = p;
-              s.sQ[q] = qv;
-              s.sI[q] = p + qv;
-            } else {
-              double I = s.sI[q];
-              for (int sidx = lo; sidx < hi; sidx += 2) {
-                const double *rl = s.rows + sidx * ROWSTRIDE, *rr = rl + ROWSTRIDE;
-                double T = 0.0;
-                if (t.small_oidx[ch * 32 + sidx] >= gs) T += rl[ROW_W] * T1VAL(rl);
-                if (t.small_oidx[ch * 32 + sidx + 1] <= ge) T += rr[ROW_W] * T1VAL(rr);
-                I += T;
-              }
-              s.sI[q] = I;
-            }
-          }
-        }
-        if (lev >= 0) {
-          for (int q = lane; q < nq; q += 32) {
-            if (s.done[q]) continue;
-            double p = s.sP[q], qv = s.sQ[q], res;
-            if (ecp_ps93_update(t.sm.levJ[lev], t.sm.levN[lev], cnt, t.tolerance, s.sI[q], &p, &qv, &res)) {
-              s.sAcc[q] = res;
-              s.done[q] = 1;
-            }
-            s.sP[q] = p;
-            s.sQ[q] = qv;
-          }
-        }
-      }
-      __syncwarp();
-    }
-    /* ---------- 2. failed ones on the mapped large grid, PSM92 (src/type1.c:149-196) ---------- */
-    int anyfail = 0;
-    for (int q = lane; q < nq; q += 32) anyfail |= (s.done[q] == 0);
-    anyfail = __any_sync(0xffffffffu, anyfail);
-    if (anyfail) {
-      if (lane == 0) atomicAdd(&b.counters[5], 1);
-      const double Cc = ca * cb;
-      const double zp = za + zb;
-      const double P = (za * dAC + zb * dBC) / zp;
-      double i1, i2;
-      ecp_fm06_map(zp, P, &i1, &i2);
-      /* done: 0 = needs large grid, 1 = converged on small grid, 2 = converged on large grid */
-      int curChunk = -1, n = 1;
-      for (int lev = 0; lev <= t.largeLevels; lev++) {
-        const int sl0 = (lev == 0) ? 0 : (1 << lev), sl1 = (lev == 0) ? 2 : (2 << lev);
-        if (lev > 0) {
-          int alldone = 1;
-          for (int q = lane; q < nq; q += 32) alldone &= (s.done[q] != 0);
-          if (__all_sync(0xffffffffu, alldone)) break;
-          for (int q = lane; q < nq; q += 32)
-            if (!s.done[q]) {
-              s.sQ[q] = 2 * s.sP[q];
-              s.sP[q] = 2 * s.sI[q];
-            }
-        }
-        for (int ch = sl0 >> 5; ch <= (sl1 - 1) >> 5; ch++) {
-          if (ch != curChunk) {
-            __syncwarp();
-            const int slot = ch * 32 + lane;
-            double *row = s.rows + lane * ROWSTRIDE;
-            const double x = t.large_x[slot];
-            const double r = i1 * x + i2;
-            const double e = (z * r + sS) * r + zd2; /* src/type1.c:162 */
-            const bool live = (slot != 1) && (e >= t.lnAcc1);
-            if (live) {
-              double K[KM + 1];
-              ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lab, sS * r, K);
-              row[ROW_W] = t.large_w[slot] * i1;
-              row[ROW_CU] = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, Lc, r);
-              row[ROW_EX] = exp(e);
-              double rn = 1.0;
-#pragma unroll
-              for (int i = 0; i <= KM; i++) {
-                row[ROW_RN + i] = rn;
-                rn = r * rn;
-                row[ROW_KA + i] = (i <= lab) ? K[i] : 0.0;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 3 + 3 * (KM + 1); i++) row[i] = 0.0;
-            }
-            curChunk = ch;
-            __syncwarp();
-          }
-          const int lo = max(sl0, ch * 32) - ch * 32, hi = min(sl1, ch * 32 + 32) - ch * 32;
-          for (int q = lane; q < nq; q += 32) {
-            if (s.done[q]) continue;
-            const int N = s.qk[q] & 255, lam = s.qk[q] >> 8;
-#define T1LVAL(rw) (Cc * (rw)[ROW_RN + N] * (rw)[ROW_CU] * (rw)[ROW_KA + lam] * (rw)[ROW_EX])
-            if (lev == 0) {
-              const double I0 = s.rows[ROW_W] * T1LVAL(s.rows);
-              s.sI[q] = I0;
-              s.sP[q] = I0;
-            } else {
-              double I = s.sI[q];
-              for (int sidx = lo; sidx < hi; sidx += 2) {
-                const double *rl = s.rows + sidx * ROWSTRIDE, *rr = rl + ROWSTRIDE;
-                double T = 0.0;
-                T += rl[ROW_W] * T1LVAL(rl);
-                T += rr[ROW_W] * T1LVAL(rr);
-                I += T;
-              }
-              s.sI[q] = I;
-            }
-          }
-        }
-        if (lev > 0) {
-          n = 2 * n + 1;
-          for (int q = lane; q < nq; q += 32) {
-            if (s.done[q]) continue;
-            double res;
-            if (ecp_psm92_update(n, 1, t.tolerance, s.sI[q], s.sP[q], s.sQ[q], &res)) {
-              s.sAcc[q] = res;
-              s.done[q] = 2;
-            }
-          }
-        }
-      }
-      int alldone = 1;
-      for (int q = lane; q < nq; q += 32) alldone &= (s.done[q] != 0);
-      if (!__all_sync(0xffffffffu, alldone) && lane == 0) atomicExch(&b.counters[2], 1);
-      __syncwarp();
-    }
-    /* Q[N][lambda] */
-    double *Qo = b.Q + b.prQOff[pr];
-    for (int q = lane; q < nq; q += 32) {
-      const int N = s.qk[q] & 255, lam = s.qk[q] >> 8;
-      Qo[N * (lab + 1) + lam] = s.sAcc[q];
-    }
-    __syncwarp();
-  }
-}
+#include "ecp_type1.cuh"
 
 /* ---- chi[i][j], one thread per element ---- */
 __global__ void k_chi(DevT t, DevB b, long long nElem) {
@@ -808,6 +576,9 @@ struct EcpDev {
   double *matrix;
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
+  int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
+  Buf t1list, t1mask, t1count;
+  int launchSeq;
 };
 
 static int ensure(Buf *b, size_t bytes) {
@@ -914,6 +685,10 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   t.qidx = upload_const(d, h->qidx, h->nqidx);
   t.nAO = h->nAO;
   d->nClasses = h->nClasses;
+  for (int c = 0; c < h->nClasses; c++) {
+    d->hClsLa[c] = h->clsLa[c];
+    d->hClsLb[c] = h->clsLb[c];
+  }
   d->maxQPerL = h->maxQPerL;
   d->nAO = h->nAO;
   d->maxLBS = h->maxLBS;
@@ -940,7 +715,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
                &d->ssFOff, &d->trA, &d->trB, &d->trClass, &d->trOut, &d->trT, &d->trG, &d->trPair, &d->prTriple,
                &d->prQOff, &d->prRshOff, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
                &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags,
-               &d->items, &d->counters};
+               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count};
   for (size_t i = 0; i < sizeof(bs) / sizeof(bs[0]); i++)
     if (bs[i]->p) cudaFree(bs[i]->p);
   if (d->matrix) cudaFree(d->matrix);
@@ -988,6 +763,34 @@ extern "C" int ecpdev_sync(EcpDev *d) {
   } while (0)
 
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+/* small-grid + large-grid type-1 kernels for one LAB value; each launch group gets its own failure counter */
+template <int LAB>
+static void launch_type1_t(EcpDev *d, const T1Segs &sg, long long listOff, int slot) {
+  const long long n = sg.prefix[sg.nseg];
+  int *cnt = (int *)d->t1count.p + slot;
+  int *list = (int *)d->t1list.p + listOff;
+  unsigned long long *mask = (unsigned long long *)d->t1mask.p;
+  k_type1S<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, sg, cnt, list, mask);
+  k_type1L<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, cnt, list, mask, d->b.counters + 2);
+}
+static void launch_type1(EcpDev *d, int lab, const T1Segs &sg, long long listOff) {
+  const int slot = d->launchSeq++;
+  switch (lab) {
+    case 0: launch_type1_t<0>(d, sg, listOff, slot); break;
+    case 1: launch_type1_t<1>(d, sg, listOff, slot); break;
+    case 2: launch_type1_t<2>(d, sg, listOff, slot); break;
+    case 3: launch_type1_t<3>(d, sg, listOff, slot); break;
+    case 4: launch_type1_t<4>(d, sg, listOff, slot); break;
+    case 5: launch_type1_t<5>(d, sg, listOff, slot); break;
+    case 6: launch_type1_t<6>(d, sg, listOff, slot); break;
+    case 7: launch_type1_t<7>(d, sg, listOff, slot); break;
+    case 8: launch_type1_t<8>(d, sg, listOff, slot); break;
+    case 9: launch_type1_t<9>(d, sg, listOff, slot); break;
+    default: launch_type1_t<10>(d, sg, listOff, slot); break;
+  }
+}
+
 
 extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double *hostBlocks, EcpDevStats *st) {
   CK(cudaSetDevice(d->device));
@@ -1038,6 +841,16 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   SCRATCH(tflags, tflags, (size_t)h->nTriples, int);
   SCRATCH(items, items, (size_t)h->nTriples * 8, int);
   SCRATCH(counters, counters, 16, int);
+  {
+    int rc_ = ensure(&d->t1list, ((size_t)h->nPairs + 1) * sizeof(int));
+    if (rc_) return rc_;
+    rc_ = ensure(&d->t1mask, ((size_t)h->nPairs + 1) * sizeof(unsigned long long));
+    if (rc_) return rc_;
+    rc_ = ensure(&d->t1count, 256 * sizeof(int));
+    if (rc_) return rc_;
+    CK(cudaMemsetAsync(d->t1count.p, 0, 256 * sizeof(int), d->s1));
+    d->launchSeq = 0;
+  }
   if ((flags & 1) && !d->matrix) {
     int rc = ecpdev_matrix_begin(d);
     if (rc) return rc;
@@ -1053,11 +866,9 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   CK(cudaMemsetAsync(B.tflags, 0, (size_t)h->nTriples * sizeof(int), d->s1));
   CK(cudaMemsetAsync(B.Q, 0, (size_t)h->qTotal * sizeof(double), d->s1));
   const DevT &t = d->t;
-  const int maxq1 = 40; /* type-1 quadratures per pair: sum_N (N/2+1) <= 36 for la+lb <= 10 */
   const int maxq2 = d->maxQPerL > 1 ? d->maxQPerL : 1;
-  const size_t sm1 = warp_smem_bytes(maxq1), sm2 = warp_smem_bytes(maxq2);
+  const size_t sm2 = warp_smem_bytes(maxq2);
   cudaFuncSetAttribute(k_fallbackT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-  cudaFuncSetAttribute(k_type1Q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
   long long launches = 0;
   CK(cudaEventRecord(d->ev[0], d->s1));
   /* per-centre tables */
@@ -1070,11 +881,37 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   CK(cudaStreamWaitEvent(d->s2, d->ev[1], 0));
   CK(cudaEventRecord(d->ev[6], d->s2));
   k_t1prep<<<nblk(h->nPairs, 128), 128, 0, d->s2>>>(t, B);
-  k_type1Q<<<d->nSM * 24, 32, sm1, d->s2>>>(t, B, maxq1);
+  { /* type-1 radial integrals: per LAB = la+lb, one thread per primitive pair (ecp_type1.cuh) */
+    long long listOff = 0;
+    for (int lab = 0; lab <= 2 * d->maxLBS; lab++) {
+      T1Segs sg;
+      sg.nseg = 0;
+      sg.prefix[0] = 0;
+      for (int c = 0; c < nc; c++) {
+        if (d->hClsLa[c] + d->hClsLb[c] != lab || h->clsFirst[c + 1] == h->clsFirst[c]) continue;
+        const long long p0 = h->trPair[h->clsFirst[c]];
+        const long long p1 = (h->clsFirst[c + 1] < h->nTriples) ? h->trPair[h->clsFirst[c + 1]] : h->nPairs;
+        if (sg.nseg == T1_MAXSEG) {
+          launch_type1(d, lab, sg, listOff);
+          launches += 2;
+          listOff += sg.prefix[sg.nseg];
+          sg.nseg = 0;
+        }
+        sg.start[sg.nseg] = p0;
+        sg.prefix[sg.nseg + 1] = sg.prefix[sg.nseg] + (p1 - p0);
+        sg.nseg++;
+      }
+      if (sg.nseg) {
+        launch_type1(d, lab, sg, listOff);
+        launches += 2;
+        listOff += sg.prefix[sg.nseg];
+      }
+    }
+  }
   CK(cudaEventRecord(d->ev[7], d->s2));
   k_chi<<<nblk(h->clsElem[nc], 128), 128, 0, d->s2>>>(t, B, h->clsElem[nc]);
   CK(cudaEventRecord(d->ev[8], d->s2));
-  launches += 3;
+  launches += 2;
   /* type 2 */
   const long long nWork = h->clsWork[nc];
   if (nWork > 0) {
@@ -1095,8 +932,9 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   launches++;
   CK(cudaEventRecord(d->ev[5], d->s1));
   CK(cudaGetLastError());
-  int hc[16];
+  int hc[16], hc1[256];
   CK(cudaMemcpyAsync(hc, B.counters, sizeof(hc), cudaMemcpyDeviceToHost, d->s1));
+  CK(cudaMemcpyAsync(hc1, d->t1count.p, sizeof(hc1), cudaMemcpyDeviceToHost, d->s1));
   if ((flags & 2) && hostBlocks)
     CK(cudaMemcpyAsync(hostBlocks, B.blocks, (size_t)h->outTotal * sizeof(double), cudaMemcpyDeviceToHost, d->s1));
   CK(cudaStreamSynchronize(d->s1));
@@ -1113,7 +951,8 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
     cudaEventElapsedTime(&ms, d->ev[0], d->ev[5]); st->ms_total = ms;
     st->nFallbackItems = hc[0];
     st->nFastFail = hc[4];
-    st->nType1Fail = hc[5];
+    st->nType1Fail = 0;
+    for (int i = 0; i < 256; i++) st->nType1Fail += hc1[i];
     st->nStaleCentre = hc[6];
     st->launches = launches;
     st->h2dBytes = d->batchH2D;
