@@ -305,24 +305,32 @@ def run_b200(args):
     import ctypes as C
 
     def e2e_once():
+        host[:] = 0.0  # the caller zeroes I (reference example/ex1.c:160); not part of the timed call
+        barrier()
+        t0_ = time.perf_counter()
         with capi.Handle(s) as hh:
+            t1_ = time.perf_counter()
             hh.set_shard(rank, world)
-            host[:] = 0.0
             rc_ = capi.lib().libecp_b200_integrals_host(C.c_void_p(hh.h), dim, host.ctypes.data_as(capi._pd))
+            t2_ = time.perf_counter()
             stx = hh.stats()
+        t3_ = time.perf_counter()
+        stx["t_init"], stx["t_run"], stx["t_free"], stx["t_all"] = t1_ - t0_, t2_ - t1_, t3_ - t2_, t3_ - t0_
         return stx
 
     e2e_once()
-    barrier()
-    t0 = time.perf_counter()
+    tot_e, parts = 0.0, [0.0, 0.0, 0.0]
     for _ in range(e2e_steps):
         st_e = e2e_once()
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        tot_e += max_over_ranks(st_e["t_all"])
+        parts = [parts[0] + st_e["t_init"], parts[1] + st_e["t_run"], parts[2] + st_e["t_free"]]
+    e2e_s = tot_e / e2e_steps
     e2e = {"value": nominal / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(sum_over_ranks(st_e["h2d_bytes"] + st_e["tables_h2d_bytes"])),
            "d2h_bytes_per_step": int(sum_over_ranks(st_e["d2h_bytes"])), "ms_per_step": 1e3 * e2e_s,
-           "note": "libECP_init + integrate + D2H of the matrix + host += per step"}
+           "note": "libECP_init + integrate + D2H of the matrix + host += + libECP_free per step",
+           "ms_init": 1e3 * parts[0] / e2e_steps, "ms_integrate_d2h": 1e3 * parts[1] / e2e_steps,
+           "ms_free": 1e3 * parts[2] / e2e_steps}
 
     # ---- roofline, secondary (Au20) and CPU baseline on rank 0 / N=1 ----
     line = None

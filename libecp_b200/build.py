@@ -18,8 +18,8 @@ LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libecp_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-CC_FLAGS = ["-O2", "-fPIC", "-Wall", "-Wno-comment", "-ffp-contract=off", "-std=gnu11"]
+              "-Xcompiler", "-fPIC,-fopenmp", "-Xptxas", "-v"]
+CC_FLAGS = ["-O2", "-fPIC", "-Wall", "-Wno-comment", "-ffp-contract=off", "-std=gnu11", "-fopenmp"]
 
 
 def _nvcc() -> str:
@@ -68,7 +68,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
             f.write(out)
     objs.append(cuobj)
     if force or _stale(SO, objs):
-        _run([_nvcc(), "-shared", "-o", SO] + objs + ["-lm"], log)
+        _run([_nvcc(), "-shared", "-o", SO] + objs + ["-lm", "-lgomp"], log)
         _run(["ar", "rcs", os.path.join(LIBDIR, "libecp.a")] + objs, log)
     if verbose:
         print("".join(log))

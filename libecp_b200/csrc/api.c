@@ -204,16 +204,11 @@ int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   void *dm = NULL;
   const int rc = libecp_b200_integrals_device(h, &dm, NULL);
   if (rc < 0 || h->empty) return rc;
-  double *M = malloc((size_t)n * n * sizeof(double));
-  const int rc2 = ecpdev_matrix_download(h->dev, M);
-  h->stats.d2h_bytes += (long long)n * n * 8;
-  if (rc2) {
-    free(M);
-    return -rc2;
-  }
-  for (int i = 0; i < n; i++) /* += on the upper triangle, as libECP_callback0 does (src/getIntegrals.c:36-42) */
-    for (int j = i; j < n; j++) I[(size_t)i * rowdim + j] += M[(size_t)i * n + j];
-  free(M);
+  long long moved = 0;
+  const int rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, &moved);
+  h->stats.d2h_bytes += moved;
+  if (rc2) return -rc2;
+  (void)n;
   return rc;
 }
 

@@ -1,33 +1,40 @@
-/* builder.c - see builder.h */
+/* builder.c - host batch builder (see builder.h).
+ *
+ * Three phases per batch, the two heavy ones parallel over ECP centres (OpenMP):
+ *   (a) per centre: screening windows of every shell (atom-level prune first), list of unskipped shells,
+ *       count of executed triples / primitive pairs per class                       [parallel]
+ *   (b) prefix sums -> slot, table and per-class positions for every centre         [serial, O(centres x classes)]
+ *   (c) per centre: write slots and triples straight into their class-sorted place  [parallel]
+ * The result is independent of the thread count: within a class, triples are ordered by centre and then in
+ * the reference's loop order (A, B>=A, s1, s2; src/libecp.c:278-320).
+ */
 #include "builder.h"
 
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 static int CD(int l) { return (l + 1) * (l + 2) * (l + 3) / 6; }
 static int IJK(int l) { return (l + 1) * (l + 2) / 2; }
 
-static void ensure_aslots(EcpBatchBuf *bb, int need) {
-  if (need <= bb->capAS) return;
-  const int cap = need * 3 / 2 + 1024;
-  bb->asAtom = realloc(bb->asAtom, cap * sizeof(int));
-  bb->asCentre = realloc(bb->asCentre, cap * sizeof(int));
-  bb->asType = realloc(bb->asType, cap * sizeof(int));
-  bb->asR = realloc(bb->asR, (size_t)cap * 4 * sizeof(double));
-  bb->asOmOff = realloc(bb->asOmOff, cap * sizeof(int64_t));
-  bb->capAS = cap;
-}
-static void ensure_sslots(EcpBatchBuf *bb, int need) {
-  if (need <= bb->capSS) return;
-  const int cap = need * 3 / 2 + 1024;
-  bb->ssShell = realloc(bb->ssShell, cap * sizeof(int));
-  bb->ssASlot = realloc(bb->ssASlot, cap * sizeof(int));
-  bb->ssStart = realloc(bb->ssStart, cap * sizeof(int));
-  bb->ssEnd = realloc(bb->ssEnd, cap * sizeof(int));
-  bb->ssFOff = realloc(bb->ssFOff, cap * sizeof(int64_t));
-  bb->capSS = cap;
-}
+typedef struct {
+  int C, type, Lc, nSS, nAS;
+  int *ssShell, *ssStart, *ssEnd, *ssAtom; /* ssAtom: local atom-slot index               */
+  int *asAtom;
+  double *asD;                             /* distance d_XC per local atom slot            */
+  int *clsCount;                           /* executed triples per class                   */
+  long long *clsPairs;                     /* primitive pairs per class                    */
+  long long nTri, outSize, fRows, omSize;
+  int cap;
+} CentreWork;
+
+struct BuilderScratch {
+  CentreWork *cw;
+  int ncw;
+};
 
 EcpBatchBuf *ecp_batch_new(const EcpTables *t) {
   EcpBatchBuf *bb = calloc(1, sizeof(EcpBatchBuf));
@@ -36,9 +43,18 @@ EcpBatchBuf *ecp_batch_new(const EcpTables *t) {
   bb->clsWork = calloc(nc + 2, sizeof(int64_t));
   bb->clsElem = calloc(nc + 2, sizeof(int64_t));
   bb->clsOutElem = calloc(nc + 2, sizeof(int64_t));
-  bb->scratchSlot = malloc((t->v.nrShells + 1) * sizeof(int));
-  bb->scratchList = malloc((t->v.nrShells + 1) * sizeof(int));
   return bb;
+}
+
+static void free_scratch(struct BuilderScratch *s) {
+  if (!s) return;
+  for (int i = 0; i < s->ncw; i++) {
+    CentreWork *w = &s->cw[i];
+    free(w->ssShell); free(w->ssStart); free(w->ssEnd); free(w->ssAtom); free(w->asAtom); free(w->asD);
+    free(w->clsCount); free(w->clsPairs);
+  }
+  free(s->cw);
+  free(s);
 }
 
 void ecp_batch_free(EcpBatchBuf *bb) {
@@ -50,43 +66,35 @@ void ecp_batch_free(EcpBatchBuf *bb) {
   free(bb->clsFirst); free(bb->clsWork); free(bb->clsElem); free(bb->clsOutElem);
   free(bb->cnA); free(bb->cnS1); free(bb->cnB); free(bb->cnS2); free(bb->cnC); free(bb->cnLa); free(bb->cnLb);
   free(bb->cnOut);
-  free(bb->scratchSlot); free(bb->scratchList);
+  free_scratch((struct BuilderScratch *)bb->scratch);
   free(bb);
 }
 
 /* basis-set screening of one shell against the (potential-capped) small grid: first grid point with
- * r >= d-R and last with r <= d+R, searched downwards from the cap exactly as the reference does
- * (src/type2.c:148-180).  The KK-mapped abscissae increase strictly, so the two downward scans are
- * binary searches; the linear form is kept for the first/last few points where rounding could matter. */
+ * r >= d-R and last with r <= d+R (reference src/type2.c:148-180 scans downwards from the cap; the
+ * KK-mapped abscissae increase strictly, so both scans are binary searches with the same result). */
 void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip) {
   const double rmin = dist - radius, rmax = dist + radius;
   const double *r = t->small_x;
-  int j;
-  /* largest j <= endLast with r[j] < rmin  (or -1) */
-  {
-    int lo = -1, hi = endLast; /* invariant: r[lo] < rmin (or lo == -1), answer in [lo, hi] */
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) / 2;
-      if (r[mid] < rmin)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-    *start = lo + 1;
+  int lo = -1, hi = endLast; /* largest j <= endLast with r[j] < rmin (or -1) */
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if (r[mid] < rmin)
+      lo = mid;
+    else
+      hi = mid - 1;
   }
-  /* largest j <= endLast with r[j] <= rmax (or -1) */
-  {
-    int lo = -1, hi = endLast;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) / 2;
-      if (r[mid] <= rmax)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-    j = lo;
+  *start = lo + 1;
+  lo = -1;
+  hi = endLast; /* largest j <= endLast with r[j] <= rmax (or -1) */
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if (r[mid] <= rmax)
+      lo = mid;
+    else
+      hi = mid - 1;
   }
-  *end = j;
+  *end = lo;
   *skip = !(*end >= *start);
 }
 
@@ -104,211 +112,301 @@ static double dist3(const double *a, const double *b) { /* src/util.c:109-116 */
   return sqrt(x * x + y * y + z * z);
 }
 
+/* phase (a) for one centre */
+static void centre_screen(const EcpTables *t, const double *geometry, int C, int rank, int world, CentreWork *w) {
+  const EcpHostTables *v = &t->v;
+  const int nat = v->nrAtoms, nc = v->nClasses, nsh = v->nrShells;
+  if (w->cap < nsh) {
+    w->ssShell = realloc(w->ssShell, nsh * sizeof(int));
+    w->ssStart = realloc(w->ssStart, nsh * sizeof(int));
+    w->ssEnd = realloc(w->ssEnd, nsh * sizeof(int));
+    w->ssAtom = realloc(w->ssAtom, nsh * sizeof(int));
+    w->asAtom = realloc(w->asAtom, (nat + 1) * sizeof(int));
+    w->asD = realloc(w->asD, (nat + 1) * sizeof(double));
+    w->clsCount = realloc(w->clsCount, (nc + 1) * sizeof(int));
+    w->clsPairs = realloc(w->clsPairs, (nc + 1) * sizeof(long long));
+    w->cap = nsh;
+  }
+  w->C = C;
+  w->type = t->atomType[C];
+  const EcpType *T = &t->types[w->type];
+  const int Lc = T->L, endLast = T->endLast;
+  w->Lc = Lc;
+  const double *rC = geometry + 3 * C;
+  const double rcap = (endLast >= 0) ? t->small_x[endLast] : -1.0;
+  int nSS = 0, nAS = 0;
+  long long fRows = 0, omSize = 0;
+  for (int X = 0; X < nat; X++) {
+    const int s0 = t->atomFirstShell[X], s1 = t->atomFirstShell[X + 1];
+    if (s0 == s1 || endLast < 0) continue;
+    const double d = dist3(rC, geometry + 3 * X);
+    /* atom-level prune: d - R > r[cap] for every shell => start = cap+1 > end => skipShell */
+    if (d - t->atomRmax[X] > rcap) continue;
+    int aslot = -1;
+    for (int s = s0; s < s1; s++) {
+      int st, en, sk;
+      ecp_shell_window(t, endLast, t->shellRadius[s], d, &st, &en, &sk);
+      if (sk) continue;
+      if (aslot < 0) {
+        aslot = nAS++;
+        w->asAtom[aslot] = X;
+        w->asD[aslot] = d;
+        omSize += (long long)(Lc + t->atomMaxL[X]) * Lc * Lc * CD(t->atomMaxL[X]);
+      }
+      w->ssShell[nSS] = s;
+      w->ssStart[nSS] = st;
+      w->ssEnd[nSS] = en;
+      w->ssAtom[nSS] = aslot;
+      fRows += Lc + t->shellL[s];
+      nSS++;
+    }
+  }
+  w->nSS = nSS;
+  w->nAS = nAS;
+  w->fRows = fRows;
+  w->omSize = omSize;
+  /* count executed triples per class (canonical enumeration, src/libecp.c:297-320,344) */
+  memset(w->clsCount, 0, (nc + 1) * sizeof(int));
+  memset(w->clsPairs, 0, (nc + 1) * sizeof(long long));
+  long long nTri = 0, outSize = 0;
+  for (int a = 0; a < nSS; a++) {
+    const int sa = w->ssShell[a], la = v->shellL[sa], Ka = v->shellK[sa];
+    const int sta = w->ssStart[a], ena = w->ssEnd[a];
+    const int *lut = &t->clsLookup[la][0][0];
+    for (int b = a; b < nSS; b++) {
+      const int gs = sta > w->ssStart[b] ? sta : w->ssStart[b];
+      const int ge = ena > w->ssEnd[b] ? ena : w->ssEnd[b];
+      if (!(gs < ge)) continue;
+      const int sb = w->ssShell[b];
+      if (world > 1 && ecp_pair_owner(sa, sb, world) != rank) continue;
+      const int lb = v->shellL[sb];
+      const int c = lut[lb * (ECP_MAX_LECP + 1) + Lc];
+      w->clsCount[c]++;
+      w->clsPairs[c] += Ka * v->shellK[sb];
+      outSize += 2 * IJK(la) * IJK(lb);
+      nTri++;
+    }
+  }
+  w->nTri = nTri;
+  w->outSize = outSize;
+}
+
+#define ENSURE(ptr, cap, need, type)                         \
+  do {                                                       \
+    if ((long long)(need) > (long long)(cap))                \
+      (ptr) = (type *)realloc((ptr), (size_t)((need) + 16) * sizeof(type)); \
+  } while (0)
+
 int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
                     int keepCanon, EcpBatchBuf *bb) {
   const EcpHostTables *v = &t->v;
   const int nat = v->nrAtoms, nc = v->nClasses;
-  int nAS = 0, nSS = 0, nTR = 0, consumed = 0;
-  int64_t omTotal = 0, fRows = 0, outTotal = 0;
-  bb->nCanon = 0;
+  struct BuilderScratch *S = (struct BuilderScratch *)bb->scratch;
+  if (!S) bb->scratch = S = calloc(1, sizeof(struct BuilderScratch));
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  /* candidate window of centres: screened in parallel, then as many as fit into maxTriples are taken */
+  const int window = nthreads * 4 > 16 ? nthreads * 4 : 16;
+  int cand[1024], ncand = 0, C = *centre;
+  for (; C < nat && ncand < window && ncand < 1024; C++)
+    if (t->atomType[C] >= 0) cand[ncand++] = C;
+  if (ncand == 0) {
+    *centre = nat;
+    bb->b.nTriples = 0;
+    return 0;
+  }
+  if (S->ncw < ncand) {
+    S->cw = realloc(S->cw, ncand * sizeof(CentreWork));
+    memset(S->cw + S->ncw, 0, (ncand - S->ncw) * sizeof(CentreWork));
+    S->ncw = ncand;
+  }
+  CentreWork *cw = S->cw;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i]);
+
+  /* ---- phase (b): how many centres, and where everything goes ---- */
+  int ntake = 0;
+  long long tri = 0;
+  while (ntake < ncand) {
+    tri += cw[ntake].nTri;
+    ntake++;
+    if (tri >= maxTriples) break;
+  }
+  *centre = (ntake < ncand) ? cand[ntake] : C;
+  long long nAS = 0, nSS = 0, omTotal = 0, fRows = 0, outTotal = 0, nTR = 0, nPairs = 0;
+  long long *asBase = malloc((ntake + 1) * sizeof(long long)), *ssBase = malloc((ntake + 1) * sizeof(long long));
+  long long *omBase = malloc((ntake + 1) * sizeof(long long)), *fBase = malloc((ntake + 1) * sizeof(long long));
+  long long *outBase = malloc((ntake + 1) * sizeof(long long)), *cnBase = malloc((ntake + 1) * sizeof(long long));
+  long long *posCC = malloc((size_t)(nc + 1) * ntake * sizeof(long long));  /* [class][centre] first triple   */
+  long long *pairCC = malloc((size_t)(nc + 1) * ntake * sizeof(long long)); /* [class][centre] first pair     */
+  long long *tBase = malloc((nc + 1) * sizeof(long long)), *gBase = malloc((nc + 1) * sizeof(long long));
+  long long *pairBase = malloc((nc + 2) * sizeof(long long)), *qBase = malloc((nc + 1) * sizeof(long long));
   bb->nominal = 0;
-  bb->screenedShells = 0;
-  /* pass 1: per centre, slots and triples in canonical order (unsorted triple arrays use the tr* buffers
-   * temporarily, then a counting sort by class reorders them) */
-  int *tmpA = NULL, *tmpB = NULL, *tmpC = NULL;
-  int64_t *tmpOut = NULL;
-  int capTmp = 0;
-  int C = *centre;
-  for (; C < nat; C++) {
-    const int type = t->atomType[C];
-    if (type < 0) continue;
-    if (consumed > 0 && nTR >= maxTriples) break;
-    consumed++;
-    const EcpType *T = &t->types[type];
-    const int Lc = T->L, endLast = T->endLast;
-    const double *rC = geometry + 3 * C;
-    const double rcap = (endLast >= 0) ? t->small_x[endLast] : -1.0;
+  for (int i = 0; i < ntake; i++) {
+    asBase[i] = nAS; ssBase[i] = nSS; omBase[i] = omTotal; fBase[i] = fRows; outBase[i] = outTotal; cnBase[i] = nTR;
+    nAS += cw[i].nAS; nSS += cw[i].nSS; omTotal += cw[i].omSize; fRows += cw[i].fRows; outTotal += cw[i].outSize;
+    nTR += cw[i].nTri;
     bb->nominal += (long long)v->nrShells * (v->nrShells + 1) / 2;
-    /* screening: shell slots and atom slots of this centre */
-    const int ss0 = nSS;
-    for (int X = 0; X < nat; X++) {
-      const double d = dist3(rC, geometry + 3 * X);
-      const int s0 = t->atomFirstShell[X], s1 = t->atomFirstShell[X + 1];
-      int aslot = -1;
-      /* atom-level prune: every shell of X lies beyond the potential cut-off */
-      double Rmax = 0.0;
-      for (int s = s0; s < s1; s++)
-        if (t->shellRadius[s] > Rmax) Rmax = t->shellRadius[s];
-      if (endLast < 0 || d - Rmax > rcap) {
-        for (int s = s0; s < s1; s++) bb->scratchSlot[s] = -1;
-        continue;
-      }
-      for (int s = s0; s < s1; s++) {
-        int st, en, sk;
-        ecp_shell_window(t, endLast, t->shellRadius[s], d, &st, &en, &sk);
-        bb->scratchSlot[s] = -1;
-        if (sk) continue;
-        if (aslot < 0) {
-          ensure_aslots(bb, nAS + 1);
-          aslot = nAS++;
-          bb->asAtom[aslot] = X;
-          bb->asCentre[aslot] = C;
-          bb->asType[aslot] = type;
-          /* r_XC = X - C (reference distanceVector(rAC, rC, rA), src/libecp.c:281) */
-          bb->asR[4 * aslot + 0] = geometry[3 * X + 0] - rC[0];
-          bb->asR[4 * aslot + 1] = geometry[3 * X + 1] - rC[1];
-          bb->asR[4 * aslot + 2] = geometry[3 * X + 2] - rC[2];
-          bb->asR[4 * aslot + 3] = d;
-          bb->asOmOff[aslot] = omTotal;
-          omTotal += (int64_t)(Lc + t->atomMaxL[X]) * Lc * Lc * CD(t->atomMaxL[X]);
-        }
-        ensure_sslots(bb, nSS + 1);
-        bb->ssShell[nSS] = s;
-        bb->ssASlot[nSS] = aslot;
-        bb->ssStart[nSS] = st;
-        bb->ssEnd[nSS] = en;
-        bb->ssFOff[nSS] = fRows;
-        fRows += Lc + t->shellL[s];
-        bb->scratchSlot[s] = nSS++;
-      }
+  }
+  bb->screenedShells = nSS;
+  long long tTot = 0, gTot = 0, qTot = 0;
+  bb->clsFirst[0] = 0;
+  bb->clsWork[0] = bb->clsElem[0] = bb->clsOutElem[0] = 0;
+  for (int c = 0; c < nc; c++) {
+    const int la = v->clsLa[c], lb = v->clsLb[c], lab = la + lb;
+    long long n = 0, np = 0;
+    pairBase[c] = nPairs;
+    for (int i = 0; i < ntake; i++) {
+      posCC[(size_t)c * ntake + i] = bb->clsFirst[c] + n;
+      pairCC[(size_t)c * ntake + i] = nPairs + np;
+      n += cw[i].clsCount[c];
+      np += cw[i].clsPairs[c];
     }
-    bb->screenedShells += nSS - ss0;
+    bb->clsFirst[c + 1] = bb->clsFirst[c] + (int)n;
+    bb->clsWork[c + 1] = bb->clsWork[c] + n * v->clsNq[c];
+    bb->clsElem[c + 1] = bb->clsElem[c] + n * CD(la) * CD(lb);
+    bb->clsOutElem[c + 1] = bb->clsOutElem[c] + n * IJK(la) * IJK(lb);
+    tBase[c] = tTot;
+    gBase[c] = gTot;
+    qBase[c] = qTot;
+    tTot += n * v->clsNq[c];
+    gTot += n * CD(la) * CD(lb);
+    qTot += np * (lab + 1) * (lab + 1);
+    nPairs += np;
+  }
+  pairBase[nc] = nPairs;
+  /* storage */
+  ENSURE(bb->asAtom, bb->capAS, nAS, int); ENSURE(bb->asCentre, bb->capAS, nAS, int);
+  ENSURE(bb->asType, bb->capAS, nAS, int); ENSURE(bb->asR, bb->capAS * 4, nAS * 4, double);
+  ENSURE(bb->asOmOff, bb->capAS, nAS, int64_t);
+  if (nAS > bb->capAS) bb->capAS = (int)nAS + 16;
+  ENSURE(bb->ssShell, bb->capSS, nSS, int); ENSURE(bb->ssASlot, bb->capSS, nSS, int);
+  ENSURE(bb->ssStart, bb->capSS, nSS, int); ENSURE(bb->ssEnd, bb->capSS, nSS, int);
+  ENSURE(bb->ssFOff, bb->capSS, nSS, int64_t);
+  if (nSS > bb->capSS) bb->capSS = (int)nSS + 16;
+  ENSURE(bb->trA, bb->capTR, nTR, int); ENSURE(bb->trB, bb->capTR, nTR, int); ENSURE(bb->trClass, bb->capTR, nTR, int);
+  ENSURE(bb->trOut, bb->capTR, nTR, int64_t); ENSURE(bb->trT, bb->capTR, nTR, int64_t);
+  ENSURE(bb->trG, bb->capTR, nTR, int64_t); ENSURE(bb->trPair, bb->capTR, nTR, int64_t);
+  if (nTR > bb->capTR) bb->capTR = (int)nTR + 16;
+  ENSURE(bb->prTriple, bb->capPR, nPairs, int); ENSURE(bb->prQOff, bb->capPR, nPairs, int64_t);
+  ENSURE(bb->prRshOff, bb->capPR, nPairs, int64_t);
+  if (nPairs > bb->capPR) bb->capPR = (int)nPairs + 16;
+  if (keepCanon) {
+    ENSURE(bb->cnA, bb->capCanon, nTR, int); ENSURE(bb->cnS1, bb->capCanon, nTR, int);
+    ENSURE(bb->cnB, bb->capCanon, nTR, int); ENSURE(bb->cnS2, bb->capCanon, nTR, int);
+    ENSURE(bb->cnC, bb->capCanon, nTR, int); ENSURE(bb->cnLa, bb->capCanon, nTR, int);
+    ENSURE(bb->cnLb, bb->capCanon, nTR, int); ENSURE(bb->cnOut, bb->capCanon, nTR, int64_t);
+    if (nTR > bb->capCanon) bb->capCanon = (int)nTR + 16;
+  }
+  bb->nCanon = keepCanon ? (int)nTR : 0;
+
+  /* ---- phase (c): fill, parallel over centres ---- */
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < ntake; i++) {
+    const CentreWork *w = &cw[i];
+    const double *rC = geometry + 3 * w->C;
+    const int Lc = w->Lc;
+    long long om = omBase[i], fr = fBase[i];
+    for (int a = 0; a < w->nAS; a++) {
+      const long long g = asBase[i] + a;
+      const int X = w->asAtom[a];
+      bb->asAtom[g] = X;
+      bb->asCentre[g] = w->C;
+      bb->asType[g] = w->type;
+      /* r_XC = X - C (reference distanceVector(rAC, rC, rA), src/libecp.c:281) */
+      bb->asR[4 * g + 0] = geometry[3 * X + 0] - rC[0];
+      bb->asR[4 * g + 1] = geometry[3 * X + 1] - rC[1];
+      bb->asR[4 * g + 2] = geometry[3 * X + 2] - rC[2];
+      bb->asR[4 * g + 3] = w->asD[a];
+      bb->asOmOff[g] = om;
+      om += (long long)(Lc + t->atomMaxL[X]) * Lc * Lc * CD(t->atomMaxL[X]);
+    }
+    for (int s = 0; s < w->nSS; s++) {
+      const long long g = ssBase[i] + s;
+      bb->ssShell[g] = w->ssShell[s];
+      bb->ssASlot[g] = (int)(asBase[i] + w->ssAtom[s]);
+      bb->ssStart[g] = w->ssStart[s];
+      bb->ssEnd[g] = w->ssEnd[s];
+      bb->ssFOff[g] = fr;
+      fr += Lc + v->shellL[w->ssShell[s]];
+    }
     /* canonical enumeration: A, B>=A, s1, s2 (reference src/libecp.c:278-320); slots of one atom are contiguous */
-    for (int ia = ss0; ia < nSS;) {
-      const int A = v->shellAtom[bb->ssShell[ia]];
+    long long *lpos = calloc(2 * (nc + 1), sizeof(long long)), *lpair = lpos + nc + 1;
+    long long out = outBase[i], cn = cnBase[i];
+    for (int ia = 0; ia < w->nSS;) {
       int ia1 = ia;
-      while (ia1 < nSS && v->shellAtom[bb->ssShell[ia1]] == A) ia1++;
-      for (int ib = ia; ib < nSS;) {
-        const int B = v->shellAtom[bb->ssShell[ib]];
+      while (ia1 < w->nSS && w->ssAtom[ia1] == w->ssAtom[ia]) ia1++;
+      for (int ib = ia; ib < w->nSS;) {
         int ib1 = ib;
-        while (ib1 < nSS && v->shellAtom[bb->ssShell[ib1]] == B) ib1++;
-        for (int a = ia; a < ia1; a++)
-          for (int b = (A == B ? a : ib); b < ib1; b++) {
-            const int gs = bb->ssStart[a] > bb->ssStart[b] ? bb->ssStart[a] : bb->ssStart[b];
-            const int ge = bb->ssEnd[a] > bb->ssEnd[b] ? bb->ssEnd[a] : bb->ssEnd[b];
+        while (ib1 < w->nSS && w->ssAtom[ib1] == w->ssAtom[ib]) ib1++;
+        for (int a = ia; a < ia1; a++) {
+          const int sa = w->ssShell[a], la = v->shellL[sa];
+          for (int b = (ib == ia ? a : ib); b < ib1; b++) {
+            const int gs = w->ssStart[a] > w->ssStart[b] ? w->ssStart[a] : w->ssStart[b];
+            const int ge = w->ssEnd[a] > w->ssEnd[b] ? w->ssEnd[a] : w->ssEnd[b];
             if (!(gs < ge)) continue; /* src/libecp.c:344, identical for both types */
-            const int sa = bb->ssShell[a], sb = bb->ssShell[b];
+            const int sb = w->ssShell[b];
             if (world > 1 && ecp_pair_owner(sa, sb, world) != rank) continue;
-            if (nTR + 1 > capTmp) {
-              capTmp = (nTR + 1) * 3 / 2 + 4096;
-              tmpA = realloc(tmpA, capTmp * sizeof(int));
-              tmpB = realloc(tmpB, capTmp * sizeof(int));
-              tmpC = realloc(tmpC, capTmp * sizeof(int));
-              tmpOut = realloc(tmpOut, capTmp * sizeof(int64_t));
+            const int lb = v->shellL[sb], lab = la + lb;
+            const int c = t->clsLookup[la][lb][Lc];
+            const long long p = posCC[(size_t)c * ntake + i] + lpos[c]++;
+            const long long pr = pairCC[(size_t)c * ntake + i] + lpair[c];
+            const int np = v->shellK[sa] * v->shellK[sb];
+            lpair[c] += np;
+            bb->trA[p] = (int)(ssBase[i] + a);
+            bb->trB[p] = (int)(ssBase[i] + b);
+            bb->trClass[p] = c;
+            bb->trOut[p] = out;
+            bb->trT[p] = tBase[c] + (p - bb->clsFirst[c]) * v->clsNq[c];
+            bb->trG[p] = gBase[c] + (p - bb->clsFirst[c]) * CD(la) * CD(lb);
+            bb->trPair[p] = pr;
+            for (int k = 0; k < np; k++) {
+              bb->prTriple[pr + k] = (int)p;
+              bb->prQOff[pr + k] = qBase[c] + (pr + k - pairBase[c]) * (lab + 1) * (lab + 1);
+              bb->prRshOff[pr + k] = bb->prQOff[pr + k];
             }
-            const int la = v->shellL[sa], lb = v->shellL[sb];
-            tmpA[nTR] = a;
-            tmpB[nTR] = b;
-            tmpC[nTR] = t->clsLookup[la][lb][Lc];
-            tmpOut[nTR] = outTotal;
             if (keepCanon) {
-              const int k = bb->nCanon;
-              if (k + 1 > bb->capCanon) {
-                bb->capCanon = (k + 1) * 3 / 2 + 4096;
-                bb->cnA = realloc(bb->cnA, bb->capCanon * sizeof(int));
-                bb->cnS1 = realloc(bb->cnS1, bb->capCanon * sizeof(int));
-                bb->cnB = realloc(bb->cnB, bb->capCanon * sizeof(int));
-                bb->cnS2 = realloc(bb->cnS2, bb->capCanon * sizeof(int));
-                bb->cnC = realloc(bb->cnC, bb->capCanon * sizeof(int));
-                bb->cnLa = realloc(bb->cnLa, bb->capCanon * sizeof(int));
-                bb->cnLb = realloc(bb->cnLb, bb->capCanon * sizeof(int));
-                bb->cnOut = realloc(bb->cnOut, bb->capCanon * sizeof(int64_t));
-              }
-              bb->cnA[k] = A;
-              bb->cnS1[k] = sa - t->atomFirstShell[A];
-              bb->cnB[k] = B;
-              bb->cnS2[k] = sb - t->atomFirstShell[B];
-              bb->cnC[k] = C;
-              bb->cnLa[k] = la;
-              bb->cnLb[k] = lb;
-              bb->cnOut[k] = outTotal;
-              bb->nCanon = k + 1;
+              const int A = w->asAtom[w->ssAtom[a]], B = w->asAtom[w->ssAtom[b]];
+              bb->cnA[cn] = A;
+              bb->cnS1[cn] = sa - t->atomFirstShell[A];
+              bb->cnB[cn] = B;
+              bb->cnS2[cn] = sb - t->atomFirstShell[B];
+              bb->cnC[cn] = w->C;
+              bb->cnLa[cn] = la;
+              bb->cnLb[cn] = lb;
+              bb->cnOut[cn] = out;
+              cn++;
             }
-            outTotal += 2 * (int64_t)IJK(la) * IJK(lb);
-            nTR++;
+            out += 2 * (long long)IJK(la) * IJK(lb);
           }
+        }
         ib = ib1;
       }
       ia = ia1;
     }
+    free(lpos);
   }
-  *centre = C;
+  free(asBase); free(ssBase); free(omBase); free(fBase); free(outBase); free(cnBase);
+  free(posCC); free(pairCC); free(tBase); free(gBase); free(pairBase); free(qBase);
 
-  /* pass 2: counting sort of the triples by class, then per-triple offsets */
-  if (nTR + 1 > bb->capTR) {
-    bb->capTR = (nTR + 1) * 3 / 2 + 4096;
-    bb->trA = realloc(bb->trA, bb->capTR * sizeof(int));
-    bb->trB = realloc(bb->trB, bb->capTR * sizeof(int));
-    bb->trClass = realloc(bb->trClass, bb->capTR * sizeof(int));
-    bb->trOut = realloc(bb->trOut, bb->capTR * sizeof(int64_t));
-    bb->trT = realloc(bb->trT, bb->capTR * sizeof(int64_t));
-    bb->trG = realloc(bb->trG, bb->capTR * sizeof(int64_t));
-    bb->trPair = realloc(bb->trPair, bb->capTR * sizeof(int64_t));
-  }
-  int *fill = calloc(nc + 2, sizeof(int));
-  memset(bb->clsFirst, 0, (nc + 2) * sizeof(int));
-  for (int i = 0; i < nTR; i++) bb->clsFirst[tmpC[i] + 1]++;
-  for (int c = 0; c < nc; c++) bb->clsFirst[c + 1] += bb->clsFirst[c];
-  for (int i = 0; i < nTR; i++) {
-    const int c = tmpC[i], p = bb->clsFirst[c] + fill[c]++;
-    bb->trA[p] = tmpA[i];
-    bb->trB[p] = tmpB[i];
-    bb->trClass[p] = c;
-    bb->trOut[p] = tmpOut[i];
-  }
-  free(fill);
-  free(tmpA);
-  free(tmpB);
-  free(tmpC);
-  free(tmpOut);
-  int64_t tTot = 0, gTot = 0, nPairs = 0, qTot = 0, rshTot = 0;
-  bb->clsWork[0] = bb->clsElem[0] = bb->clsOutElem[0] = 0;
-  for (int c = 0; c < nc; c++) {
-    const int la = v->clsLa[c], lb = v->clsLb[c], lab = la + lb;
-    const int64_t n = bb->clsFirst[c + 1] - bb->clsFirst[c];
-    bb->clsWork[c + 1] = bb->clsWork[c] + n * v->clsNq[c];
-    bb->clsElem[c + 1] = bb->clsElem[c] + n * CD(la) * CD(lb);
-    bb->clsOutElem[c + 1] = bb->clsOutElem[c] + n * IJK(la) * IJK(lb);
-    for (int i = bb->clsFirst[c]; i < bb->clsFirst[c + 1]; i++) {
-      const int sa = bb->ssShell[bb->trA[i]], sb = bb->ssShell[bb->trB[i]];
-      const int np = v->shellK[sa] * v->shellK[sb];
-      bb->trT[i] = tTot;
-      bb->trG[i] = gTot;
-      bb->trPair[i] = nPairs;
-      tTot += v->clsNq[c];
-      gTot += CD(la) * CD(lb);
-      if (nPairs + np > bb->capPR) {
-        bb->capPR = (int)((nPairs + np) * 3 / 2 + 4096);
-        bb->prTriple = realloc(bb->prTriple, bb->capPR * sizeof(int));
-        bb->prQOff = realloc(bb->prQOff, bb->capPR * sizeof(int64_t));
-        bb->prRshOff = realloc(bb->prRshOff, bb->capPR * sizeof(int64_t));
-      }
-      for (int p = 0; p < np; p++) {
-        bb->prTriple[nPairs] = i;
-        bb->prQOff[nPairs] = qTot;
-        bb->prRshOff[nPairs] = rshTot;
-        qTot += (lab + 1) * (lab + 1);
-        rshTot += (lab + 1) * (lab + 1);
-        nPairs++;
-      }
-    }
-  }
   EcpBatch *b = &bb->b;
-  b->nASlots = nAS;
+  b->nASlots = (int)nAS;
   b->asAtom = bb->asAtom;
   b->asCentre = bb->asCentre;
   b->asType = bb->asType;
   b->asR = bb->asR;
   b->asOmOff = bb->asOmOff;
   b->omTotal = omTotal;
-  b->nSSlots = nSS;
+  b->nSSlots = (int)nSS;
   b->ssShell = bb->ssShell;
   b->ssASlot = bb->ssASlot;
   b->ssStart = bb->ssStart;
   b->ssEnd = bb->ssEnd;
   b->ssFOff = bb->ssFOff;
   b->fRows = fRows;
-  b->nTriples = nTR;
+  b->nTriples = (int)nTR;
   b->trA = bb->trA;
   b->trB = bb->trB;
   b->trClass = bb->trClass;
@@ -321,7 +419,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   b->outTotal = outTotal;
   b->nPairs = nPairs;
   b->qTotal = qTot;
-  b->rshTotal = rshTot;
+  b->rshTotal = qTot;
   b->prTriple = bb->prTriple;
   b->prQOff = bb->prQOff;
   b->prRshOff = bb->prRshOff;
@@ -329,5 +427,5 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   b->clsWork = bb->clsWork;
   b->clsElem = bb->clsElem;
   b->clsOutElem = bb->clsOutElem;
-  return consumed;
+  return ntake;
 }

@@ -28,9 +28,7 @@ typedef struct {
   int64_t *cnOut;
   /* statistics */
   long long nominal, screenedShells;
-  /* scratch */
-  int *scratchSlot;   /* [nrShells] shell -> shell slot of the current centre, or -1 */
-  int *scratchList;
+  void *scratch;      /* per-centre work areas of the parallel builder (builder.c) */
 } EcpBatchBuf;
 
 EcpBatchBuf *ecp_batch_new(const EcpTables *t);

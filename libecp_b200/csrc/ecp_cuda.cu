@@ -25,16 +25,19 @@
 #include "ecp_math.h"
 
 #define KM ECP_KMAX
-#define ROWSTRIDE 37 /* doubles per tabulated point row in shared memory (odd -> conflict-free lane rows) */
+#define ROWSTRIDE 53 /* doubles per tabulated point row in shared memory (odd -> conflict-free lane rows) */
 #define ROW_W 0
 #define ROW_CU 1
 #define ROW_EX 2
 #define ROW_RN 3            /* rn[0..KM]  */
 #define ROW_KA (3 + KM + 1) /* Ka[0..KM]  */
 #define ROW_KB (3 + 2 * (KM + 1))
-#if (3 + 3 * (KM + 1)) > ROWSTRIDE
+#define ROW_D (3 + 3 * (KM + 1)) /* Bessel scratch d[0..KM+5] */
+#define ROW_USED (3 + 3 * (KM + 1))
+#if (ROW_D + KM + 6) > ROWSTRIDE
 #error row too small
 #endif
+#define FB_WARPS 4
 
 static char g_err[512] = "";
 #define CK(call)                                                                                   \
@@ -226,14 +229,14 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, int maxq) {
   return s;
 }
 static size_t warp_smem_bytes(int maxq) {
-  return (size_t)32 * ROWSTRIDE * 8 + (size_t)maxq * 8 * 4 + (size_t)maxq * 4 + (size_t)maxq + 16;
+  return (((size_t)32 * ROWSTRIDE * 8 + (size_t)maxq * 8 * 4 + (size_t)maxq * 4 + (size_t)maxq + 16) + 15) & ~(size_t)15;
 }
 
 /* ---- type-2 fallback: one warp per (triple, l) with failed small-grid quadratures ---- */
-__global__ void __launch_bounds__(32) k_fallbackT(DevT t, DevB b, int maxq) {
+__global__ void __launch_bounds__(32 * FB_WARPS) k_fallbackT(DevT t, DevB b, int maxq, int warpBytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const WarpSmem s = carve(smem_raw, maxq);
-  const int lane = threadIdx.x;
+  const WarpSmem s = carve(smem_raw + (size_t)(threadIdx.x >> 5) * warpBytes, maxq);
+  const int lane = threadIdx.x & 31;
   const int nItems = b.counters[0];
   for (;;) {
     int it = 0;
@@ -306,24 +309,22 @@ __global__ void __launch_bounds__(32) k_fallbackT(DevT t, DevB b, int maxq) {
               const bool live = (slot != 1) && (e >= t.lnAcc2);
               if (slot == 0 && r > dAC && r > dBC && e < t.lnAcc2) atomicAdd(&b.counters[6], 1);
               if (live) {
-                double Ka[KM + 1], Kb[KM + 1];
                 const double U = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, l, r);
-                ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, laC, s1 * r, Ka);
-                ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lbC, s2 * r, Kb);
+                ecp_bessel_mem(t.besselT, t.besselStride, t.besselC, laC, s1 * r, row + ROW_KA, row + ROW_D);
+                ecp_bessel_mem(t.besselT, t.besselStride, t.besselC, lbC, s2 * r, row + ROW_KB, row + ROW_D);
                 row[ROW_W] = t.large_w[slot] * i1;
                 row[ROW_CU] = Cc * U;
                 row[ROW_EX] = exp(e);
                 double rn = 1.0;
-#pragma unroll
-                for (int i = 0; i <= KM; i++) {
+                for (int i = 0; i <= lab; i++) {
                   row[ROW_RN + i] = rn;
                   rn = r * rn;
-                  row[ROW_KA + i] = (i <= laC) ? Ka[i] : 0.0;
-                  row[ROW_KB + i] = (i <= lbC) ? Kb[i] : 0.0;
                 }
               } else {
-#pragma unroll
-                for (int i = 0; i < 3 + 3 * (KM + 1); i++) row[i] = 0.0;
+                row[ROW_W] = row[ROW_CU] = row[ROW_EX] = 0.0;
+                for (int i = 0; i <= lab; i++) row[ROW_RN + i] = 0.0;
+                for (int i = 0; i <= laC; i++) row[ROW_KA + i] = 0.0;
+                for (int i = 0; i <= lbC; i++) row[ROW_KB + i] = 0.0;
               }
               curChunk = ch;
               __syncwarp();
@@ -738,6 +739,55 @@ extern "C" int ecpdev_matrix_download(EcpDev *d, double *host) {
   CK(cudaMemcpy(host, d->matrix, (size_t)d->nAO * d->nAO * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }
+/* host I[i*rowdim + j] += M[i][j] for j >= i (what libECP_callback0 does block by block, reference
+ * src/getIntegrals.c:36-42): upper-triangle row panels are copied D2H into two pinned staging buffers and
+ * added by all host threads while the next panel is in flight. */
+extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, long long *bytes) {
+  CK(cudaSetDevice(d->device));
+  CK(cudaStreamSynchronize(d->s1));
+  const int n = d->nAO;
+  const size_t panelBytes = (size_t)24 << 20;
+  int rowsPer = (int)(panelBytes / ((size_t)n * sizeof(double)));
+  if (rowsPer < 1) rowsPer = 1;
+  if (rowsPer > n) rowsPer = n;
+  double *pin[2] = {NULL, NULL};
+  cudaEvent_t done[2];
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMallocHost((void **)&pin[k], (size_t)rowsPer * n * sizeof(double)));
+    CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+  }
+  const int nPanels = (n + rowsPer - 1) / rowsPer;
+  long long moved = 0;
+  auto issue = [&](int p) -> cudaError_t {
+    const int r0 = p * rowsPer, r1 = (r0 + rowsPer < n) ? r0 + rowsPer : n;
+    const size_t width = (size_t)(n - r0) * sizeof(double); /* columns r0..n-1 cover the upper triangle of the panel */
+    moved += (long long)width * (r1 - r0);
+    cudaError_t e = cudaMemcpy2DAsync(pin[p & 1], width, d->matrix + (size_t)r0 * n + r0, (size_t)n * sizeof(double),
+                                      width, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, d->s1);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(done[p & 1], d->s1);
+  };
+  CK(issue(0));
+  for (int p = 0; p < nPanels; p++) {
+    if (p + 1 < nPanels) CK(issue(p + 1));
+    CK(cudaEventSynchronize(done[p & 1]));
+    const int r0 = p * rowsPer, r1 = (r0 + rowsPer < n) ? r0 + rowsPer : n;
+    const int w = n - r0;
+    const double *src = pin[p & 1];
+#pragma omp parallel for schedule(static)
+    for (int i = r0; i < r1; i++) {
+      const double *sr = src + (size_t)(i - r0) * w;
+      double *dr = host + (size_t)i * rowdim;
+      for (int j = i; j < n; j++) dr[j] += sr[j - r0];
+    }
+  }
+  for (int k = 0; k < 2; k++) {
+    cudaFreeHost(pin[k]);
+    cudaEventDestroy(done[k]);
+  }
+  if (bytes) *bytes = moved;
+  return 0;
+}
 extern "C" void *ecpdev_matrix_ptr(EcpDev *d) { return d->matrix; }
 extern "C" long long ecpdev_table_bytes(EcpDev *d) { return d->tableBytes; }
 extern "C" int ecpdev_sync(EcpDev *d) {
@@ -868,7 +918,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   const DevT &t = d->t;
   const int maxq2 = d->maxQPerL > 1 ? d->maxQPerL : 1;
   const size_t sm2 = warp_smem_bytes(maxq2);
-  cudaFuncSetAttribute(k_fallbackT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+  cudaFuncSetAttribute(k_fallbackT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm2 * FB_WARPS));
   long long launches = 0;
   CK(cudaEventRecord(d->ev[0], d->s1));
   /* per-centre tables */
@@ -920,7 +970,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   }
   CK(cudaEventRecord(d->ev[2], d->s1));
   if (nWork > 0) {
-    k_fallbackT<<<d->nSM * 24, 32, sm2, d->s1>>>(t, B, maxq2);
+    k_fallbackT<<<d->nSM * 4, 32 * FB_WARPS, sm2 * FB_WARPS, d->s1>>>(t, B, maxq2, (int)sm2);
     launches++;
   }
   CK(cudaEventRecord(d->ev[3], d->s1));

@@ -106,6 +106,72 @@ ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double 
   }
 }
 
+/* Same function with run-time order bound and caller-provided storage (shared memory in the kernels):
+ * K[0..lmax] result, d[0..lmax+5] scratch.  No unrolling waste for small lmax, no register arrays.
+ * Operation order identical to ecp_bessel / the reference (the K_j updates are merely interleaved with
+ * the derivative recurrence, each K_j sees the same sequence of additions). */
+ECP_HD int ecp_bessel_mem(const double *__restrict__ tabT, int stride, const double *__restrict__ Cj, int lmax,
+                          double z, double *K, double *d) {
+  if (z < 1.0E-7) {
+    if (z <= 0) {
+      K[0] = 1.0;
+      for (int l = 1; l <= lmax; l++) K[l] = 0.0;
+    } else {
+      double k = 1 - z;
+      K[0] = k;
+      for (int l = 1; l <= lmax; l++) {
+        k = k * z / (2 * l + 1);
+        K[l] = k;
+      }
+    }
+    return 0;
+  } else if (z < 16.0) {
+    const int maxL = lmax + 5;
+    const int index = (int)floor(z * 100.0 + 0.5);
+    const double dz = z - index / 100.0;
+    const double *row = tabT + (size_t)index * stride;
+    double scale = 1.0;
+    for (int l = 0; l <= maxL; l++) {
+      const double v = row[l];
+      d[l] = v;
+      if (l <= lmax) K[l] = v;
+    }
+    for (int i = 1; i <= 5; i++) {
+      const int top = maxL - i;
+      double prev = d[0], next = d[1];
+      const double d0 = next - prev;
+      d[0] = d0;
+      scale = scale * dz / i;
+      K[0] += scale * d0;
+      for (int j = 1; j <= top; j++) {
+        const double cur = next;
+        next = d[j + 1];
+        const double nd = Cj[j] * (prev - next) - cur + next;
+        d[j] = nd;
+        prev = cur;
+        if (j <= lmax) K[j] += scale * nd;
+      }
+    }
+    return 1;
+  } else {
+    double *A = d;
+    A[0] = 0.5 / z;
+    for (int l = 0; l <= lmax; l++) K[l] = A[0];
+    for (int l = 1; l <= lmax; l++) {
+      double f = l * (l + 1);
+      double k = K[l];
+      for (int i = 1; i < l; i++) {
+        k += f * A[i];
+        f *= (l + i + 1) * (l - i);
+      }
+      A[l] = -A[0] * A[l - 1] / l;
+      k += f * A[l];
+      K[l] = k;
+    }
+    return 2;
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * ECP radial channel U_l(r) = sum_k r^n_k d_k exp(-a_k r^2)   (reference src/ecp.c:41-60)
  * Integer powers 0..4 are formed by multiplication (pow(r,2.0) == r*r when correctly rounded).

@@ -575,6 +575,9 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   t->shellRadius = malloc((nsh + 1) * sizeof(double));
   for (int s = 0; s < nsh; s++)
     t->shellRadius[s] = shell_radius(KBS[s], lBS[s], dBS + t->shellPrim[s], aBS + t->shellPrim[s], 1.0E-14);
+  t->atomRmax = calloc(nrAtoms + 1, sizeof(double));
+  for (int s = 0; s < nsh; s++)
+    if (t->shellRadius[s] > t->atomRmax[t->shellAtom[s]]) t->atomRmax[t->shellAtom[s]] = t->shellRadius[s];
 
   /* ---- per ECP type: r^N U_l(r) with the cumulative cut-off, and the local channel
    *      (reference src/type2.c:184-219, src/libecp.c:269-270).  Rows N <= max(maxLambda, 2 maxAlpha) so
@@ -717,7 +720,7 @@ void ecp_tables_free(EcpTables *t) {
   free(t->large_x); free(t->large_w); free(t->large_xs); free(t->large_ws); free(t->large_oidx);
   free(t->besselK); free(t->besselT); free(t->besselC);
   free(t->shellL); free(t->shellK); free(t->shellPrim); free(t->shellAtom); free(t->shellAO);
-  free(t->shellRadius); free(t->atomMaxL); free(t->atomFirstShell);
+  free(t->shellRadius); free(t->atomRmax); free(t->atomMaxL); free(t->atomFirstShell);
   free(t->atomType); free(t->types); free(t->typeL); free(t->typeGaussOff); free(t->gaussL);
   free(t->gaussN); free(t->gaussD); free(t->gaussA); free(t->typeUtab); free(t->typeUL);
   free(t->clsLa); free(t->clsLb); free(t->clsL); free(t->clsNq); free(t->clsQOff); free(t->clsQlOff);

@@ -27,6 +27,7 @@ typedef struct {
   double *besselK, *besselT, *besselC;
   int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO;
   double *shellRadius;
+  double *atomRmax;   /* largest shell radius per atom (atom-level screening prune) */
   int *atomMaxL, *atomFirstShell;
   /* ECP */
   int *atomType; /* per atom: type index or -1 */

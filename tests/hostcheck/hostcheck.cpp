@@ -11,6 +11,10 @@ int hc_bessel(const double *tabT, int stride, const double *Cj, int lmax, double
   for (int i = 0; i <= lmax; i++) K[i] = k[i];
   return br;
 }
+int hc_bessel_mem(const double *tabT, int stride, const double *Cj, int lmax, double z, double *K) {
+  double d[ECP_KMAX + 8];
+  return ecp_bessel_mem(tabT, stride, Cj, lmax, z, K, d);
+}
 void hc_rsh(int lmax, double theta, double phi, const double *fac, const double *dfac, double *out) {
   ecp_rsh(lmax, theta, phi, fac, dfac, out);
 }
