@@ -43,6 +43,8 @@ EcpBatchBuf *ecp_batch_new(const EcpTables *t) {
   bb->clsWork = calloc(nc + 2, sizeof(int64_t));
   bb->clsElem = calloc(nc + 2, sizeof(int64_t));
   bb->clsOutElem = calloc(nc + 2, sizeof(int64_t));
+  bb->clsPairBase = calloc(nc + 2, sizeof(int64_t));
+  bb->clsQBase = calloc(nc + 2, sizeof(int64_t));
   return bb;
 }
 
@@ -61,9 +63,9 @@ void ecp_batch_free(EcpBatchBuf *bb) {
   if (!bb) return;
   free(bb->asAtom); free(bb->asCentre); free(bb->asType); free(bb->asR); free(bb->asOmOff);
   free(bb->ssShell); free(bb->ssASlot); free(bb->ssStart); free(bb->ssEnd); free(bb->ssFOff);
-  free(bb->trA); free(bb->trB); free(bb->trClass); free(bb->trOut); free(bb->trT); free(bb->trG); free(bb->trPair);
-  free(bb->prTriple); free(bb->prQOff); free(bb->prRshOff);
-  free(bb->clsFirst); free(bb->clsWork); free(bb->clsElem); free(bb->clsOutElem);
+  free(bb->trA); free(bb->trB); free(bb->trOut); free(bb->trPair);
+  free(bb->prTriple);
+  free(bb->clsFirst); free(bb->clsWork); free(bb->clsElem); free(bb->clsOutElem); free(bb->clsPairBase); free(bb->clsQBase);
   free(bb->cnA); free(bb->cnS1); free(bb->cnB); free(bb->cnS2); free(bb->cnC); free(bb->cnLa); free(bb->cnLb);
   free(bb->cnOut);
   free_scratch((struct BuilderScratch *)bb->scratch);
@@ -277,6 +279,10 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
     nPairs += np;
   }
   pairBase[nc] = nPairs;
+  for (int c = 0; c <= nc; c++) {
+    bb->clsPairBase[c] = pairBase[c];
+    bb->clsQBase[c] = (c < nc) ? qBase[c] : qTot;
+  }
   /* storage */
   ENSURE(bb->asAtom, bb->capAS, nAS, int); ENSURE(bb->asCentre, bb->capAS, nAS, int);
   ENSURE(bb->asType, bb->capAS, nAS, int); ENSURE(bb->asR, bb->capAS * 4, nAS * 4, double);
@@ -286,12 +292,10 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   ENSURE(bb->ssStart, bb->capSS, nSS, int); ENSURE(bb->ssEnd, bb->capSS, nSS, int);
   ENSURE(bb->ssFOff, bb->capSS, nSS, int64_t);
   if (nSS > bb->capSS) bb->capSS = (int)nSS + 16;
-  ENSURE(bb->trA, bb->capTR, nTR, int); ENSURE(bb->trB, bb->capTR, nTR, int); ENSURE(bb->trClass, bb->capTR, nTR, int);
-  ENSURE(bb->trOut, bb->capTR, nTR, int64_t); ENSURE(bb->trT, bb->capTR, nTR, int64_t);
-  ENSURE(bb->trG, bb->capTR, nTR, int64_t); ENSURE(bb->trPair, bb->capTR, nTR, int64_t);
+  ENSURE(bb->trA, bb->capTR, nTR, int); ENSURE(bb->trB, bb->capTR, nTR, int);
+  ENSURE(bb->trOut, bb->capTR, nTR, int64_t); ENSURE(bb->trPair, bb->capTR, nTR, int64_t);
   if (nTR > bb->capTR) bb->capTR = (int)nTR + 16;
-  ENSURE(bb->prTriple, bb->capPR, nPairs, int); ENSURE(bb->prQOff, bb->capPR, nPairs, int64_t);
-  ENSURE(bb->prRshOff, bb->capPR, nPairs, int64_t);
+  ENSURE(bb->prTriple, bb->capPR, nPairs, int);
   if (nPairs > bb->capPR) bb->capPR = (int)nPairs + 16;
   if (keepCanon) {
     ENSURE(bb->cnA, bb->capCanon, nTR, int); ENSURE(bb->cnS1, bb->capCanon, nTR, int);
@@ -349,7 +353,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
             if (!(gs < ge)) continue; /* src/libecp.c:344, identical for both types */
             const int sb = w->ssShell[b];
             if (world > 1 && ecp_pair_owner(sa, sb, world) != rank) continue;
-            const int lb = v->shellL[sb], lab = la + lb;
+            const int lb = v->shellL[sb];
             const int c = t->clsLookup[la][lb][Lc];
             const long long p = posCC[(size_t)c * ntake + i] + lpos[c]++;
             const long long pr = pairCC[(size_t)c * ntake + i] + lpair[c];
@@ -357,16 +361,9 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
             lpair[c] += np;
             bb->trA[p] = (int)(ssBase[i] + a);
             bb->trB[p] = (int)(ssBase[i] + b);
-            bb->trClass[p] = c;
             bb->trOut[p] = out;
-            bb->trT[p] = tBase[c] + (p - bb->clsFirst[c]) * v->clsNq[c];
-            bb->trG[p] = gBase[c] + (p - bb->clsFirst[c]) * CD(la) * CD(lb);
             bb->trPair[p] = pr;
-            for (int k = 0; k < np; k++) {
-              bb->prTriple[pr + k] = (int)p;
-              bb->prQOff[pr + k] = qBase[c] + (pr + k - pairBase[c]) * (lab + 1) * (lab + 1);
-              bb->prRshOff[pr + k] = bb->prQOff[pr + k];
-            }
+            for (int k = 0; k < np; k++) bb->prTriple[pr + k] = (int)p;
             if (keepCanon) {
               const int A = w->asAtom[w->ssAtom[a]], B = w->asAtom[w->ssAtom[b]];
               bb->cnA[cn] = A;
@@ -409,10 +406,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   b->nTriples = (int)nTR;
   b->trA = bb->trA;
   b->trB = bb->trB;
-  b->trClass = bb->trClass;
   b->trOut = bb->trOut;
-  b->trT = bb->trT;
-  b->trG = bb->trG;
   b->trPair = bb->trPair;
   b->tTotal = tTot;
   b->gTotal = gTot;
@@ -421,11 +415,11 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   b->qTotal = qTot;
   b->rshTotal = qTot;
   b->prTriple = bb->prTriple;
-  b->prQOff = bb->prQOff;
-  b->prRshOff = bb->prRshOff;
   b->clsFirst = bb->clsFirst;
   b->clsWork = bb->clsWork;
   b->clsElem = bb->clsElem;
   b->clsOutElem = bb->clsOutElem;
+  b->clsPairBase = bb->clsPairBase;
+  b->clsQBase = bb->clsQBase;
   return ntake;
 }

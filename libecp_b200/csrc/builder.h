@@ -15,12 +15,11 @@ typedef struct {
   int64_t *asOmOff;
   int *ssShell, *ssASlot, *ssStart, *ssEnd;
   int64_t *ssFOff;
-  int *trA, *trB, *trClass;
-  int64_t *trOut, *trT, *trG, *trPair;
+  int *trA, *trB;
+  int64_t *trOut, *trPair;
   int *prTriple;
-  int64_t *prQOff, *prRshOff;
   int *clsFirst;
-  int64_t *clsWork, *clsElem, *clsOutElem;
+  int64_t *clsWork, *clsElem, *clsOutElem, *clsPairBase, *clsQBase;
   int capAS, capSS, capTR, capPR;
   /* canonical (reference loop order) list of the executed triples of this batch, for callback replay */
   int nCanon, capCanon;

@@ -56,6 +56,9 @@ struct DevT {
   double tolerance, accuracy, lnAcc1, lnAcc2;
   EcpSmallMeta sm;
   const double *fac, *dfac, *poly2sph, *omega, *binom;
+  int shOffStride;
+  const int *shTermOff, *shTermP, *shTermD;
+  const double *shTermBin;
   const int *ijk, *ijkIndex;
   const double *small_r, *small_w, *large_x, *large_w;
   const int16_t *small_oidx;
@@ -76,12 +79,11 @@ struct DevB {
   const long long *asOmOff;
   const int *ssShell, *ssASlot, *ssStart, *ssEnd;
   const long long *ssFOff;
-  const int *trA, *trB, *trClass;
-  const long long *trOut, *trT, *trG, *trPair;
+  const int *trA, *trB;
+  const long long *trOut, *trPair;
   const int *prTriple;
-  const long long *prQOff, *prRshOff;
   const int *clsFirst;
-  const long long *clsWork, *clsElem, *clsOutElem;
+  const long long *clsWork, *clsElem, *clsOutElem, *clsPairBase, *clsQBase;
   /* intermediates */
   double *rshX, *uspX, *omX, *F, *T, *gamma, *chi, *Q, *rshP, *sP, *blocks, *matrix;
   unsigned char *tfail;
@@ -102,6 +104,29 @@ __device__ __forceinline__ int find_class(const long long *prefix, int nc, long 
       hi = mid - 1;
   }
   return lo;
+}
+
+__device__ __forceinline__ int find_class_i(const int *prefix, int nc, int w) {
+  int lo = 0, hi = nc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= w)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+/* per-triple / per-pair offsets are closed forms of the class prefixes (nothing per triple is uploaded for them) */
+__device__ __forceinline__ long long tri_T_off(const DevT &t, const DevB &b, int c, int tri) {
+  return b.clsWork[c] + (long long)(tri - b.clsFirst[c]) * t.clsNq[c];
+}
+__device__ __forceinline__ long long tri_G_off(const DevT &t, const DevB &b, int c, int tri) {
+  return b.clsElem[c] + (long long)(tri - b.clsFirst[c]) * (ecp_cd(t.clsLa[c]) * ecp_cd(t.clsLb[c]));
+}
+__device__ __forceinline__ long long pair_Q_off(const DevT &t, const DevB &b, int c, long long pr) {
+  const int lab1 = t.clsLa[c] + t.clsLb[c] + 1;
+  return b.clsQBase[c] + (pr - b.clsPairBase[c]) * (lab1 * lab1);
 }
 
 /* ---- per (C, atom) : S_lm(r^_XC) and unit-sphere monomials ---- */
@@ -197,7 +222,7 @@ __global__ void k_fastT(DevT t, DevB b, long long nWork) {
   const int gs = max(b.ssStart[sa], b.ssStart[sb]), ge = max(b.ssEnd[sa], b.ssEnd[sb]); /* src/libecp.c:315-316 */
   double res = 0.0;
   const int rc = ecp_ps93_fastT(Fa, Fb, U, t.small_w, t.small_oidx, &t.sm, gs, ge, t.tolerance, &res, (int *)0);
-  const long long o = b.trT[tri] + k;
+  const long long o = w; /* = class T base + (triple - first) * nq + k */
   if (rc) {
     b.T[o] = 0.0;
     b.tfail[o] = 1;
@@ -245,11 +270,11 @@ __global__ void __launch_bounds__(32 * FB_WARPS) k_fallbackT(DevT t, DevB b, int
     if (it >= nItems) break;
     const int item = b.items[it];
     const int tri = item >> 3, l = item & 7;
-    const int c = b.trClass[tri];
+    const int c = find_class_i(b.clsFirst, t.nClasses, tri);
     const int la = t.clsLa[c], lb = t.clsLb[c];
     const int laC = la + l, lbC = lb + l, lab = la + lb;
     const int k0 = t.clsQlOff[c * (ECP_MAX_LECP + 1) + l], k1 = t.clsQlOff[c * (ECP_MAX_LECP + 1) + l + 1];
-    const long long tOff = b.trT[tri];
+    const long long tOff = tri_T_off(t, b, c, tri);
     const int *ql = t.qlist + t.clsQOff[c];
     /* gather the failed quadratures of this (triple, l) */
     int nf = 0;
@@ -400,7 +425,7 @@ __global__ void k_link(DevT t, DevB b, long long nElem) {
   const int incA1 = ecp_cd(lXa), incA2 = L * L * incA1;
   const int incB1 = ecp_cd(lXb), incB2 = L * L * incB1;
   const double *oA = b.omX + b.asOmOff[asa] + p, *oB = b.omX + b.asOmOff[asb] + q;
-  const double *T = b.T + b.trT[tri];
+  const double *T = b.T + tri_T_off(t, b, c, tri);
   const int16_t *qi = t.qidx + t.clsQidxOff[c];
   const int d1 = la + L, d2 = lb + L, d3 = la + lb + 1;
   double g = 0.0;
@@ -421,7 +446,7 @@ __global__ void k_link(DevT t, DevB b, long long nElem) {
       }
     g += tmp;
   }
-  b.gamma[b.trG[tri] + pq] = g;
+  b.gamma[w] = g;
 }
 
 /* ---- type 1, per primitive pair: P = 2(za r_AC + zb r_BC), |P|, S_lm(P^) ---- */
@@ -442,7 +467,7 @@ __global__ void k_t1prep(DevT t, DevB b) {
   double r, th, ph;
   ecp_sphcoord(Px, Py, Pz, &r, &th, &ph);
   const int lab = t.shellL[sha] + t.shellL[shb];
-  ecp_rsh(lab, th, ph, t.fac, t.dfac, b.rshP + b.prRshOff[pr]);
+  ecp_rsh(lab, th, ph, t.fac, t.dfac, b.rshP + pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pr), pr));
   b.sP[pr] = r;
 }
 
@@ -468,81 +493,20 @@ __global__ void k_chi(DevT t, DevB b, long long nElem) {
   const long long pr0 = b.trPair[tri];
   double chi = 0.0;
   for (int ip = 0; ip < np; ip++) {
-    const double *rsh = b.rshP + b.prRshOff[pr0 + ip];
-    const double *Q = b.Q + b.prQOff[pr0 + ip] + lmax * (lab + 1);
+    const long long qo = pair_Q_off(t, b, c, pr0 + ip);
+    const double *rsh = b.rshP + qo;
+    const double *Q = b.Q + qo + lmax * (lab + 1);
     for (int l = lmax; l >= 0; l -= 2) {
       double factor = 0.0;
       for (int m = 0; m < 2 * l + 1; m++) factor += rsh[l * l + m] * PM[l * l + m];
       chi += factor * Q[l];
     }
   }
-  b.chi[b.trG[tri] + pq] = chi;
+  b.chi[w] = chi;
 }
 
 /* ---- shift to A/B-centred Cartesians, normalise, write blocks / accumulate matrix ---- */
-__device__ __forceinline__ double shift_one(const DevT &t, const double *G, int cdb, double N, const int *ea,
-                                            const int *eb, const double *uA, int dA, const double *uB, int dB) {
-  const int nb = t.maxLBS + 1, D = t.ijkDim;
-  double I = 0.0;
-  for (int bx = 0; bx <= eb[0]; bx++) {
-    const double bbx = t.binom[eb[0] * nb + bx];
-    for (int by = 0; by <= eb[1]; by++) {
-      const double bby = bbx * t.binom[eb[1] * nb + by];
-      for (int bz = 0; bz <= eb[2]; bz++) {
-        const double bbz = bby * t.binom[eb[2] * nb + bz];
-        double fB = bbz * uB[(eb[0] - bx) * dB * dB + (eb[1] - by) * dB + (eb[2] - bz)];
-        if (fabs(fB) <= t.accuracy) continue; /* src/util.c:318 */
-        fB *= N;
-        const int rb = t.ijkIndex[bx * D * D + by * D + bz];
-        /* J[c1][rb] = sum over alpha terms (src/util.c:270-299) */
-        double J = 0.0;
-        for (int ax = 0; ax <= ea[0]; ax++) {
-          const double bax = t.binom[ea[0] * nb + ax];
-          for (int ay = 0; ay <= ea[1]; ay++) {
-            const double bay = bax * t.binom[ea[1] * nb + ay];
-            for (int az = 0; az <= ea[2]; az++) {
-              const double baz = bay * t.binom[ea[2] * nb + az];
-              const double fA = baz * uA[(ea[0] - ax) * dA * dA + (ea[1] - ay) * dA + (ea[2] - az)];
-              if (fabs(fA) <= t.accuracy) continue; /* src/util.c:286 */
-              const int ra = t.ijkIndex[ax * D * D + ay * D + az];
-              J += fA * G[ra * cdb + rb];
-            }
-          }
-        }
-        I += fB * J;
-      }
-    }
-  }
-  return I;
-}
-
-__global__ void k_shift(DevT t, DevB b, long long nElem, int flags) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nElem) return;
-  const int c = find_class(b.clsOutElem, t.nClasses, w);
-  const int la = t.clsLa[c], lb = t.clsLb[c];
-  const int na = ecp_ijk(la), nb = ecp_ijk(lb), cdb = ecp_cd(lb);
-  const long long idx = w - b.clsOutElem[c];
-  const int tri = b.clsFirst[c] + (int)(idx / (na * nb));
-  const int cc = (int)(idx % (na * nb)), c1 = cc / nb, c2 = cc % nb;
-  const int ssa = b.trA[tri], ssb = b.trB[tri];
-  const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
-  const int dA = t.atomMaxL[b.asAtom[asa]] + 1, dB = t.atomMaxL[b.asAtom[asb]] + 1;
-  const double *uA = b.uspX + (size_t)asa * USPX_STRIDE, *uB = b.uspX + (size_t)asb * USPX_STRIDE;
-  const int *ea = t.ijk + 3 * ecp_cidx(la, c1), *eb = t.ijk + 3 * ecp_cidx(lb, c2);
-  const double n1 = 4.0 * M_PI, n2 = n1 * n1; /* src/libecp.c:234-235 */
-  const double I1 = shift_one(t, b.chi + b.trG[tri], cdb, n1, ea, eb, uA, dA, uB, dB);
-  const double I2 = shift_one(t, b.gamma + b.trG[tri], cdb, n2, ea, eb, uA, dA, uB, dB);
-  if (flags & 2) {
-    double *o = b.blocks + b.trOut[tri];
-    o[cc] = I1;
-    o[na * nb + cc] = I2;
-  }
-  if (flags & 1) {
-    const int row = t.shellAO[b.ssShell[ssa]] + c1, col = t.shellAO[b.ssShell[ssb]] + c2;
-    if (row <= col) atomicAdd(&b.matrix[(size_t)row * t.nAO + col], I1 + I2); /* src/getIntegrals.c:38-40 */
-  }
-}
+#include "ecp_shift.cuh"
 
 /* ---------------------------------------------------------------------------------------------- */
 /* FP64 FMA peak probe (roofline denominator when no measured FP64 peak is published) */
@@ -571,24 +535,27 @@ struct EcpDev {
   int nClasses, maxQPerL, nAO, maxLBS;
   Buf tab[64];
   int ntab;
-  Buf asAtom, asType, asR, asOmOff, ssShell, ssASlot, ssStart, ssEnd, ssFOff, trA, trB, trClass, trOut, trT, trG, trPair;
-  Buf prTriple, prQOff, prRshOff, clsFirst, clsWork, clsElem, clsOutElem;
+  Buf asAtom, asType, asR, asOmOff, ssShell, ssASlot, ssStart, ssEnd, ssFOff, trA, trB, trOut, trPair;
+  Buf prTriple, clsFirst, clsWork, clsElem, clsOutElem, clsPairBase, clsQBase;
   Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
   double *matrix;
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
-  Buf t1list, t1mask, t1count;
+  Buf t1list, t1mask, t1count, clsJ, Jbuf;
   int launchSeq;
 };
 
+/* scratch buffers come from the device's stream-ordered pool (release threshold raised in ecpdev_create),
+ * so creating / destroying handles back to back does not pay cudaMalloc / cudaFree of gigabytes each time */
+static thread_local cudaStream_t g_allocStream = 0;
 static int ensure(Buf *b, size_t bytes) {
   if (bytes <= b->cap && b->p) return 0;
-  if (b->p) cudaFree(b->p);
+  if (b->p) cudaFreeAsync(b->p, g_allocStream);
   b->p = NULL;
   b->cap = 0;
   size_t want = bytes + bytes / 4 + 256;
-  CK(cudaMalloc(&b->p, want));
+  CK(cudaMallocAsync(&b->p, want, g_allocStream));
   b->cap = want;
   return 0;
 }
@@ -598,10 +565,10 @@ static const T *upload_const(EcpDev *d, const T *h, size_t n) {
   bf->p = NULL;
   bf->cap = 0;
   size_t bytes = (n ? n : 1) * sizeof(T);
-  if (cudaMalloc(&bf->p, bytes) != cudaSuccess) return NULL;
+  if (cudaMallocAsync(&bf->p, bytes, d->s1) != cudaSuccess) return NULL;
   bf->cap = bytes;
   d->tableBytes += (long long)(n * sizeof(T));
-  if (n && cudaMemcpy(bf->p, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return NULL;
+  if (n && cudaMemcpyAsync(bf->p, h, n * sizeof(T), cudaMemcpyHostToDevice, d->s1) != cudaSuccess) return NULL;
   return (const T *)bf->p;
 }
 
@@ -622,6 +589,13 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   cudaDeviceGetAttribute(&d->nSM, cudaDevAttrMultiProcessorCount, device);
   cudaStreamCreateWithFlags(&d->s1, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&d->s2, cudaStreamNonBlocking);
+  { /* keep freed scratch in the pool instead of returning it to the driver */
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   for (int i = 0; i < 12; i++) cudaEventCreate(&d->ev[i]);
   DevT &t = d->t;
   t.maxLECP = h->maxLECP; t.maxLBS = h->maxLBS; t.maxLambda = h->maxLambda; t.tmDim = h->tmDim; t.ijkDim = h->ijkDim;
@@ -643,6 +617,11 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   t.poly2sph = upload_const(d, h->poly2sph, (size_t)cdT * t.pcols);
   t.omega = upload_const(d, h->omega, h->nomega);
   t.binom = upload_const(d, h->binom, (size_t)(h->maxLBS + 1) * (h->maxLBS + 1));
+  t.shOffStride = h->shOffStride;
+  t.shTermOff = upload_const(d, h->shTermOff, (size_t)(h->maxLBS + 1) * h->shOffStride);
+  t.shTermP = upload_const(d, h->shTermP, h->nShTerms);
+  t.shTermD = upload_const(d, h->shTermD, h->nShTerms);
+  t.shTermBin = upload_const(d, h->shTermBin, h->nShTerms);
   t.ijk = upload_const(d, h->ijk, (size_t)3 * cdT);
   t.ijkIndex = upload_const(d, h->ijkIndex, (size_t)h->ijkDim * h->ijkDim * h->ijkDim);
   t.small_r = upload_const(d, h->small_r, ECP_SMALL_SLOTS);
@@ -711,15 +690,17 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   cudaSetDevice(d->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < d->ntab; i++)
-    if (d->tab[i].p) cudaFree(d->tab[i].p);
+    if (d->tab[i].p) cudaFreeAsync(d->tab[i].p, d->s1);
   Buf *bs[] = {&d->asAtom, &d->asType, &d->asR, &d->asOmOff, &d->ssShell, &d->ssASlot, &d->ssStart, &d->ssEnd,
-               &d->ssFOff, &d->trA, &d->trB, &d->trClass, &d->trOut, &d->trT, &d->trG, &d->trPair, &d->prTriple,
-               &d->prQOff, &d->prRshOff, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
+               &d->ssFOff, &d->trA, &d->trB, &d->trOut, &d->trPair, &d->prTriple,
+               &d->clsPairBase, &d->clsQBase, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
                &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags,
-               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count};
+               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count, &d->clsJ, &d->Jbuf};
   for (size_t i = 0; i < sizeof(bs) / sizeof(bs[0]); i++)
-    if (bs[i]->p) cudaFree(bs[i]->p);
-  if (d->matrix) cudaFree(d->matrix);
+    if (bs[i]->p) cudaFreeAsync(bs[i]->p, d->s1);
+  cudaStreamSynchronize(d->s1);
+  if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
+  cudaStreamSynchronize(d->s1);
   for (int i = 0; i < 12; i++) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->s1);
   cudaStreamDestroy(d->s2);
@@ -729,7 +710,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
 extern "C" int ecpdev_matrix_begin(EcpDev *d) {
   CK(cudaSetDevice(d->device));
   const size_t bytes = (size_t)d->nAO * d->nAO * sizeof(double);
-  if (!d->matrix) CK(cudaMalloc((void **)&d->matrix, bytes ? bytes : 8));
+  if (!d->matrix) CK(cudaMallocAsync((void **)&d->matrix, bytes ? bytes : 8, d->s1));
   CK(cudaMemsetAsync(d->matrix, 0, bytes, d->s1));
   return 0;
 }
@@ -778,7 +759,17 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, lo
     for (int i = r0; i < r1; i++) {
       const double *sr = src + (size_t)(i - r0) * w;
       double *dr = host + (size_t)i * rowdim;
-      for (int j = i; j < n; j++) dr[j] += sr[j - r0];
+      /* the ECP matrix is block sparse (a block is non-zero only if both shells reach a common centre):
+       * runs of 32 zeros are skipped so that the caller's matrix is only touched where something is added */
+      int j = i;
+      for (; j + 32 <= n; j += 32) {
+        const double *s32 = sr + (j - r0);
+        int any = 0;
+        for (int k = 0; k < 32; k++) any |= (s32[k] != 0.0);
+        if (any)
+          for (int k = 0; k < 32; k++) dr[j + k] += s32[k];
+      }
+      for (; j < n; j++) dr[j] += sr[j - r0];
     }
   }
   for (int k = 0; k < 2; k++) {
@@ -845,6 +836,7 @@ static void launch_type1(EcpDev *d, int lab, const T1Segs &sg, long long listOff
 extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double *hostBlocks, EcpDevStats *st) {
   CK(cudaSetDevice(d->device));
   DevB &B = d->b;
+  g_allocStream = d->s1;
   const int nc = d->nClasses;
   B.nASlots = h->nASlots;
   B.nSSlots = h->nSSlots;
@@ -864,18 +856,15 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   UP(ssFOff, ssFOff, (const long long *)h->ssFOff, h->nSSlots, long long);
   UP(trA, trA, h->trA, h->nTriples, int);
   UP(trB, trB, h->trB, h->nTriples, int);
-  UP(trClass, trClass, h->trClass, h->nTriples, int);
-  UP(trOut, trOut, (const long long *)h->trOut, h->nTriples, long long);
-  UP(trT, trT, (const long long *)h->trT, h->nTriples, long long);
-  UP(trG, trG, (const long long *)h->trG, h->nTriples, long long);
+  if (flags & 2) UP(trOut, trOut, (const long long *)h->trOut, h->nTriples, long long);
   UP(trPair, trPair, (const long long *)h->trPair, h->nTriples, long long);
   UP(prTriple, prTriple, h->prTriple, h->nPairs, int);
-  UP(prQOff, prQOff, (const long long *)h->prQOff, h->nPairs, long long);
-  UP(prRshOff, prRshOff, (const long long *)h->prRshOff, h->nPairs, long long);
   UP(clsFirst, clsFirst, h->clsFirst, nc + 1, int);
   UP(clsWork, clsWork, (const long long *)h->clsWork, nc + 1, long long);
   UP(clsElem, clsElem, (const long long *)h->clsElem, nc + 1, long long);
   UP(clsOutElem, clsOutElem, (const long long *)h->clsOutElem, nc + 1, long long);
+  UP(clsPairBase, clsPairBase, (const long long *)h->clsPairBase, nc + 1, long long);
+  UP(clsQBase, clsQBase, (const long long *)h->clsQBase, nc + 1, long long);
   SCRATCH(rshX, rshX, (size_t)h->nASlots * RSHX_STRIDE, double);
   SCRATCH(uspX, uspX, (size_t)h->nASlots * USPX_STRIDE, double);
   SCRATCH(omX, omX, (size_t)h->omTotal, double);
@@ -978,8 +967,24 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   launches++;
   CK(cudaEventRecord(d->ev[4], d->s1));
   CK(cudaStreamWaitEvent(d->s1, d->ev[8], 0));
-  k_shift<<<nblk(h->clsOutElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsOutElem[nc], flags);
-  launches++;
+  { /* binomial shift in two passes (ecp_shift.cuh); J[type][c1][q] per triple goes through a scratch buffer */
+    long long clsJ[ECP_MAX_CLASSES + 1];
+    clsJ[0] = 0;
+    for (int c = 0; c < nc; c++) {
+      const int la = d->hClsLa[c], lb = d->hClsLb[c];
+      clsJ[c + 1] = clsJ[c] + (long long)(h->clsFirst[c + 1] - h->clsFirst[c]) * ((la + 1) * (la + 2) / 2) *
+                                  ((lb + 1) * (lb + 2) * (lb + 3) / 6);
+    }
+    int rc_ = ensure(&d->clsJ, (nc + 1) * sizeof(long long));
+    if (rc_) return rc_;
+    rc_ = ensure(&d->Jbuf, (size_t)(2 * clsJ[nc] + 1) * sizeof(double));
+    if (rc_) return rc_;
+    CK(cudaMemcpyAsync(d->clsJ.p, clsJ, (nc + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->s1));
+    k_shiftJ<<<nblk(clsJ[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, clsJ[nc], (double *)d->Jbuf.p);
+    k_shiftI<<<nblk(h->clsOutElem[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, h->clsOutElem[nc],
+                                                              (const double *)d->Jbuf.p, flags);
+  }
+  launches += 2;
   CK(cudaEventRecord(d->ev[5], d->s1));
   CK(cudaGetLastError());
   int hc[16], hc1[256];

@@ -40,6 +40,13 @@ typedef struct {
   const double *omega;            /* [L_DIM(maxLECP)][L_DIM(maxLambda)][C_DIM(maxAlpha)] */
   int nomega;
   const double *binom;            /* [(maxLBS+1)^2] n over k                       */
+  /* binomial-shift term lists per (l, component c) in the reference's loop order (src/util.c:275-283):
+   * terms [shTermOff[l*shOffStride + c], shTermOff[l*shOffStride + c + 1]) */
+  int shOffStride, nShTerms;
+  const int *shTermOff;           /* [(maxLBS+1)*shOffStride]                      */
+  const int *shTermP;             /* C_INDEX of the sub-monomial (alpha_x,alpha_y,alpha_z) */
+  const int *shTermD;             /* (a-alpha) packed dx | dy<<4 | dz<<8           */
+  const double *shTermBin;        /* binomial product                              */
   /* small grid, level-major padded layout */
   const double *small_r, *small_w;   /* [384]                                      */
   const int16_t *small_oidx;         /* [384] original index, -1 for the pad slot  */
@@ -91,20 +98,17 @@ typedef struct {
   /* triples, sorted by class */
   int nTriples;
   const int *trA, *trB;     /* shell slots                                         */
-  const int *trClass;
   const int64_t *trOut;     /* offset of the (type1,type2) block pair in the block buffer */
-  const int64_t *trT;       /* offset into T                                       */
-  const int64_t *trG;       /* offset into gamma / chi                             */
   const int64_t *trPair;    /* first type-1 primitive pair                         */
   int64_t tTotal, gTotal, outTotal, nPairs, qTotal, rshTotal;
   const int *prTriple;      /* [nPairs] owning triple                              */
-  const int64_t *prQOff;    /* [nPairs] offset into Q                              */
-  const int64_t *prRshOff;  /* [nPairs] offset into rsh                            */
   /* per class ranges (triples of class c are [clsFirst[c], clsFirst[c+1])) */
   const int *clsFirst;      /* [nClasses+1]                                        */
   const int64_t *clsWork;   /* [nClasses+1] prefix of ntriples*nq (fast-T threads) */
   const int64_t *clsElem;   /* [nClasses+1] prefix of ntriples*C_DIM(la)*C_DIM(lb) */
   const int64_t *clsOutElem;/* [nClasses+1] prefix of ntriples*IJK(la)*IJK(lb)     */
+  const int64_t *clsPairBase; /* [nClasses+1] prefix of primitive pairs per class  */
+  const int64_t *clsQBase;    /* [nClasses+1] prefix of pairs*(la+lb+1)^2 (offsets into Q / rsh) */
 } EcpBatch;
 
 typedef struct {

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_type1S(DevT t, DevB b, T1Segs segs, int
     t1_load_pair(t, b, segs.start[sg] + (g - segs.prefix[sg]), pp);
     Cc = pp.ca * pp.cb * exp(pp.zd2); /* src/type1.c:113 */
     UL = t.typeUL + (size_t)pp.type * ECP_SMALL_SLOTS;
-    Qo = b.Q + b.prQOff[pp.pr];
+    Qo = b.Q + pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pp.pr), pp.pr);
   }
   double I[NQL], P[NQL], Qv[NQL];
   unsigned open = 0;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128) k_type1L(DevT t, DevB b, const int *failC
     Lc = t.typeL[pp.type];
     g0 = t.typeGaussOff[pp.type];
     g1 = t.typeGaussOff[pp.type + 1];
-    Qo = b.Q + b.prQOff[pp.pr];
+    Qo = b.Q + pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pp.pr), pp.pr);
   }
   double I[NQL], P[NQL], Qv[NQL];
 #pragma unroll

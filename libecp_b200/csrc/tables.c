@@ -549,6 +549,45 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   t->binom = calloc((v->maxLBS + 1) * (v->maxLBS + 1), sizeof(double));
   for (int n = 0; n <= v->maxLBS; n++)
     for (int k = 0; k <= n; k++) t->binom[n * (v->maxLBS + 1) + k] = nk(n, k, t->fac);
+  { /* term lists of the binomial shift (x-A)^a = sum_alpha binom(a,alpha) (C-A)^(a-alpha) x_C^alpha, in the
+     * reference's loop order alpha_x, alpha_y, alpha_z (src/util.c:275-283 / :307-315) */
+    const int os = IJK(v->maxLBS) + 1, D = v->ijkDim;
+    int nt = 0;
+    for (int l = 0; l <= v->maxLBS; l++)
+      for (int c = 0; c < IJK(l); c++) {
+        const int *e = t->ijk + 3 * CIDX(l, c);
+        nt += (e[0] + 1) * (e[1] + 1) * (e[2] + 1);
+      }
+    t->shTermOff = calloc((size_t)(v->maxLBS + 1) * os, sizeof(int));
+    t->shTermP = malloc((nt + 1) * sizeof(int));
+    t->shTermD = malloc((nt + 1) * sizeof(int));
+    t->shTermBin = malloc((nt + 1) * sizeof(double));
+    int k = 0;
+    for (int l = 0; l <= v->maxLBS; l++) {
+      for (int c = 0; c < IJK(l); c++) {
+        const int *e = t->ijk + 3 * CIDX(l, c);
+        t->shTermOff[l * os + c] = k;
+        for (int x = 0; x <= e[0]; x++) {
+          const double bx = nk(e[0], x, t->fac);
+          for (int y = 0; y <= e[1]; y++) {
+            const double by = bx * nk(e[1], y, t->fac);
+            for (int z = 0; z <= e[2]; z++, k++) {
+              t->shTermBin[k] = by * nk(e[2], z, t->fac);
+              t->shTermP[k] = t->ijkIndex[x * D * D + y * D + z];
+              t->shTermD[k] = (e[0] - x) | ((e[1] - y) << 4) | ((e[2] - z) << 8);
+            }
+          }
+        }
+      }
+      for (int c = IJK(l); c < os; c++) t->shTermOff[l * os + c] = k;
+    }
+    v->shOffStride = os;
+    v->nShTerms = nt;
+    v->shTermOff = t->shTermOff;
+    v->shTermP = t->shTermP;
+    v->shTermD = t->shTermD;
+    v->shTermBin = t->shTermBin;
+  }
   build_small_grid(t);
   build_large_grid(t, largeGridOrder);
   if (build_bessel(t, v->maxLECP + v->maxAlpha + 6, accuracy)) {
@@ -715,6 +754,7 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
 void ecp_tables_free(EcpTables *t) {
   if (!t) return;
   free(t->fac); free(t->dfac); free(t->cart2sph); free(t->poly2sph); free(t->omega); free(t->binom);
+  free(t->shTermOff); free(t->shTermP); free(t->shTermD); free(t->shTermBin);
   free(t->ijk); free(t->ijkIndex);
   free(t->small_x); free(t->small_w); free(t->small_rs); free(t->small_ws); free(t->small_oidx);
   free(t->large_x); free(t->large_w); free(t->large_xs); free(t->large_ws); free(t->large_oidx);

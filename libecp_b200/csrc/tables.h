@@ -17,6 +17,8 @@ typedef struct {
   EcpHostTables v; /* view handed to the CUDA layer (pointers into the arrays below) */
   /* owned storage */
   double *fac, *dfac, *cart2sph, *poly2sph, *omega, *binom;
+  int *shTermOff, *shTermP, *shTermD;
+  double *shTermBin;
   int *ijk, *ijkIndex;
   double *small_x, *small_w;   /* original order [383] (screening uses these)   */
   double *small_rs, *small_ws; /* slot layout [384]                              */
