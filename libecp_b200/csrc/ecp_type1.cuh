@@ -198,27 +198,49 @@ __global__ void __launch_bounds__(128) k_type1S(DevT t, DevB b, T1Segs segs, int
     } else {
       cnt += __popc(bal);
       const bool last = (8 * c + 8 == t.sm.levSlot[v + 1]);
+      /* screened windows leave whole chunks without a single in-window point for all four pairs of the warp
+       * (shells far from the centre only see the fine levels): no products, no shuffles then - only the level
+       * bookkeeping, which the reference also performs when cnt == 0 (src/gc_integrators.c:203-208) */
+      const bool anyWin = __any_sync(T1_FULL, inWin);
       int q = 0;
+      if (anyWin) {
 #pragma unroll
-      for (int N = 0; N <= LAB; N++)
+        for (int N = 0; N <= LAB; N++)
 #pragma unroll
-        for (int lam = N; lam >= 0; lam -= 2) {
-          const double val = t1_wval<LAB>(pt, Cc, N, lam);
-          const double v1 = val + __shfl_xor_sync(T1_FULL, val, 1);
-          const double v2 = v1 + __shfl_xor_sync(T1_FULL, v1, 2);
-          const double v4 = v2 + __shfl_xor_sync(T1_FULL, v2, 4);
-          if ((q & 7) == gl) {
-            const int k = q >> 3;
-            double res;
-            I[k] += v4;
-            if (last && (open >> k & 1) &&
-                ecp_ps93_update(t.sm.levJ[v], t.sm.levN[v], cnt, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res;
-              open &= ~(1u << k);
+          for (int lam = N; lam >= 0; lam -= 2) {
+            const double val = t1_wval<LAB>(pt, Cc, N, lam);
+            const double v1 = val + __shfl_xor_sync(T1_FULL, val, 1);
+            const double v2 = v1 + __shfl_xor_sync(T1_FULL, v1, 2);
+            const double v4 = v2 + __shfl_xor_sync(T1_FULL, v2, 4);
+            if ((q & 7) == gl) {
+              const int k = q >> 3;
+              double res;
+              I[k] += v4;
+              if (last && (open >> k & 1) &&
+                  ecp_ps93_update(t.sm.levJ[v], t.sm.levN[v], cnt, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
+                Qo[N * (LAB + 1) + lam] = res;
+                open &= ~(1u << k);
+              }
             }
+            q++;
           }
-          q++;
-        }
+      } else if (last) {
+#pragma unroll
+        for (int N = 0; N <= LAB; N++)
+#pragma unroll
+          for (int lam = N; lam >= 0; lam -= 2) {
+            if ((q & 7) == gl) {
+              const int k = q >> 3;
+              double res;
+              if ((open >> k & 1) &&
+                  ecp_ps93_update(t.sm.levJ[v], t.sm.levN[v], cnt, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
+                Qo[N * (LAB + 1) + lam] = res;
+                open &= ~(1u << k);
+              }
+            }
+            q++;
+          }
+      }
       if (last) {
         v++;
         cnt = 0;
