@@ -243,6 +243,10 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
     torch.cuda.set_device(local)
     capi.set_device(local)
+    # torchrun exports OMP_NUM_THREADS=1; every rank gets its share of the host cores for the batch builder
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    host_threads = max(1, ncores // max(1, world))
+    capi.set_host_threads(host_threads)
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -342,7 +346,8 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "nominal_triples": nominal, "executed_triples": int(executed_all),
-                       "parallelism": f"shell-pair ownership x{world}, no data-path collective",
+                       "parallelism": f"shell-pair (row) ownership x{world}, no data-path collective",
+                       "host_threads_per_rank": host_threads,
                        "l2": "per-step working set (F/T/gamma/chi intermediates, GBs) exceeds the 126 MB L2; no flush needed",
                        "timed_region": "host batch build + H2D of batch arrays + all kernels; matrix stays in HBM"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

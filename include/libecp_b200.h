@@ -16,6 +16,9 @@ extern "C" {
 /* CUDA device used by handles created afterwards (default 0, or env LIBECP_B200_DEVICE).
  * The reference has no device notion (no process/device boundary). */
 void libecp_b200_set_device(int device);
+/* Host threads used by the batch builder and the host-side accumulation (OpenMP); launchers like torchrun
+ * export OMP_NUM_THREADS=1, so a multi-GPU caller hands every rank its share of the cores explicitly. */
+void libecp_b200_set_host_threads(int n);
 
 /* Restrict a handle to the shell pairs owned by `rank` of `world` (disjoint output blocks per rank,
  * no data-path collective).  Replaces nothing in the reference (single-threaded loop

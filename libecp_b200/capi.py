@@ -23,7 +23,7 @@ EXPORTS = [
     "cartesianShellOrderIndex", "libecp_b200_set_device", "libecp_b200_set_shard", "libecp_b200_pair_owner",
     "libecp_b200_integrals_device", "libecp_b200_integrals_host", "libecp_b200_get_stats", "libecp_b200_screening",
     "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
-    "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error",
+    "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
 ]
 
 
@@ -81,6 +81,12 @@ def _p(a, t):
 
 def set_device(dev: int) -> None:
     lib().libecp_b200_set_device(int(dev))
+
+
+def set_host_threads(n: int) -> None:
+    L = lib()
+    L.libecp_b200_set_host_threads.argtypes = [C.c_int]
+    L.libecp_b200_set_host_threads(int(n))
 
 
 def fp64_peak(dev: int = 0, iters: int = 200000) -> float:

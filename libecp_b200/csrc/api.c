@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../../include/dimensions.h"
 #include "../../include/getIntegrals.h"
@@ -41,6 +44,15 @@ static double now_ms(void) {
 }
 
 void libecp_b200_set_device(int device) { g_device = device; }
+/* host threads of the batch builder and of the host-side += (OpenMP).  Launchers such as torchrun export
+ * OMP_NUM_THREADS=1; a multi-GPU caller gives each rank its share of the cores explicitly. */
+void libecp_b200_set_host_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 void libecp_b200_set_tables_only(int on) { g_tables_only = on; }
 const char *libecp_b200_last_error(void) { return g_apierr[0] ? g_apierr : ecpdev_last_error(); }
 int libecp_b200_pair_owner(int a, int b, int world) { return ecp_pair_owner(a, b, world); }
@@ -205,7 +217,16 @@ int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   const int rc = libecp_b200_integrals_device(h, &dm, NULL);
   if (rc < 0 || h->empty) return rc;
   long long moved = 0;
-  const int rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, &moved);
+  unsigned char *owned = NULL;
+  if (h->world > 1) { /* only the AO rows of the shells this rank owns can be non-zero */
+    const EcpHostTables *v = &h->tab->v;
+    owned = calloc(n + 1, 1);
+    for (int s = 0; s < v->nrShells; s++)
+      if (ecp_pair_owner(s, s, h->world) == h->rank)
+        for (int k = 0; k < IJK_DIM(v->shellL[s]); k++) owned[v->shellAO[s] + k] = 1;
+  }
+  const int rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, owned, &moved);
+  free(owned);
   h->stats.d2h_bytes += moved;
   if (rc2) return -rc2;
   (void)n;

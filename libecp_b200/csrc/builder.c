@@ -100,9 +100,14 @@ void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dis
   *skip = !(*end >= *start);
 }
 
+/* Output ownership for the multi-GPU partition: the block of shell pair (a, b), a <= b in global shell order,
+ * belongs to the rank that owns ROW shell a (rows are dealt to ranks by a hash of the shell index).  Owning whole
+ * rows means that a rank's builder enumerates only its rows (work / world) and that its partial matrix has
+ * non-zeros only in the AO rows of its shells (D2H / world). */
 int ecp_pair_owner(int a, int b, int world) {
   if (world <= 1) return 0;
-  uint64_t h = (uint64_t)(uint32_t)a * 0x9E3779B97F4A7C15ull ^ ((uint64_t)(uint32_t)b + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+  const int row = a < b ? a : b;
+  uint64_t h = ((uint64_t)(uint32_t)row + 0x7F4A7C15ull) * 0x9E3779B97F4A7C15ull;
   h ^= h >> 29;
   h *= 0xBF58476D1CE4E5B9ull;
   h ^= h >> 32;
@@ -175,12 +180,12 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
     const int sa = w->ssShell[a], la = v->shellL[sa], Ka = v->shellK[sa];
     const int sta = w->ssStart[a], ena = w->ssEnd[a];
     const int *lut = &t->clsLookup[la][0][0];
+    if (world > 1 && ecp_pair_owner(sa, sa, world) != rank) continue; /* row ownership */
     for (int b = a; b < nSS; b++) {
       const int gs = sta > w->ssStart[b] ? sta : w->ssStart[b];
       const int ge = ena > w->ssEnd[b] ? ena : w->ssEnd[b];
       if (!(gs < ge)) continue;
       const int sb = w->ssShell[b];
-      if (world > 1 && ecp_pair_owner(sa, sb, world) != rank) continue;
       const int lb = v->shellL[sb];
       const int c = lut[lb * (ECP_MAX_LECP + 1) + Lc];
       w->clsCount[c]++;
@@ -347,12 +352,12 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
         while (ib1 < w->nSS && w->ssAtom[ib1] == w->ssAtom[ib]) ib1++;
         for (int a = ia; a < ia1; a++) {
           const int sa = w->ssShell[a], la = v->shellL[sa];
+          if (world > 1 && ecp_pair_owner(sa, sa, world) != rank) continue; /* row ownership */
           for (int b = (ib == ia ? a : ib); b < ib1; b++) {
             const int gs = w->ssStart[a] > w->ssStart[b] ? w->ssStart[a] : w->ssStart[b];
             const int ge = w->ssEnd[a] > w->ssEnd[b] ? w->ssEnd[a] : w->ssEnd[b];
             if (!(gs < ge)) continue; /* src/libecp.c:344, identical for both types */
             const int sb = w->ssShell[b];
-            if (world > 1 && ecp_pair_owner(sa, sb, world) != rank) continue;
             const int lb = v->shellL[sb];
             const int c = t->clsLookup[la][lb][Lc];
             const long long p = posCC[(size_t)c * ntake + i] + lpos[c]++;

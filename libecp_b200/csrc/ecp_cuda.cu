@@ -723,7 +723,8 @@ extern "C" int ecpdev_matrix_download(EcpDev *d, double *host) {
 /* host I[i*rowdim + j] += M[i][j] for j >= i (what libECP_callback0 does block by block, reference
  * src/getIntegrals.c:36-42): upper-triangle row panels are copied D2H into two pinned staging buffers and
  * added by all host threads while the next panel is in flight. */
-extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, long long *bytes) {
+extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned,
+                                         long long *bytes) {
   CK(cudaSetDevice(d->device));
   CK(cudaStreamSynchronize(d->s1));
   const int n = d->nAO;
@@ -731,16 +732,31 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, lo
   int rowsPer = (int)(panelBytes / ((size_t)n * sizeof(double)));
   if (rowsPer < 1) rowsPer = 1;
   if (rowsPer > n) rowsPer = n;
+  /* panels = runs of rows this rank owns (all rows when rowOwned == NULL), at most rowsPer rows each: a sharded
+   * rank's partial matrix is zero outside the AO rows of its shells, so those rows are never transferred */
+  int *pr0 = (int *)malloc((size_t)(n + 1) * sizeof(int)), *pr1 = (int *)malloc((size_t)(n + 1) * sizeof(int));
+  int nPanels = 0;
+  for (int i = 0; i < n;) {
+    if (rowOwned && !rowOwned[i]) {
+      i++;
+      continue;
+    }
+    int j = i;
+    while (j < n && j - i < rowsPer && (!rowOwned || rowOwned[j])) j++;
+    pr0[nPanels] = i;
+    pr1[nPanels] = j;
+    nPanels++;
+    i = j;
+  }
   double *pin[2] = {NULL, NULL};
   cudaEvent_t done[2];
   for (int k = 0; k < 2; k++) {
     CK(cudaMallocHost((void **)&pin[k], (size_t)rowsPer * n * sizeof(double)));
     CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
   }
-  const int nPanels = (n + rowsPer - 1) / rowsPer;
   long long moved = 0;
   auto issue = [&](int p) -> cudaError_t {
-    const int r0 = p * rowsPer, r1 = (r0 + rowsPer < n) ? r0 + rowsPer : n;
+    const int r0 = pr0[p], r1 = pr1[p];
     const size_t width = (size_t)(n - r0) * sizeof(double); /* columns r0..n-1 cover the upper triangle of the panel */
     moved += (long long)width * (r1 - r0);
     cudaError_t e = cudaMemcpy2DAsync(pin[p & 1], width, d->matrix + (size_t)r0 * n + r0, (size_t)n * sizeof(double),
@@ -748,11 +764,11 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, lo
     if (e != cudaSuccess) return e;
     return cudaEventRecord(done[p & 1], d->s1);
   };
-  CK(issue(0));
+  if (nPanels) CK(issue(0));
   for (int p = 0; p < nPanels; p++) {
     if (p + 1 < nPanels) CK(issue(p + 1));
     CK(cudaEventSynchronize(done[p & 1]));
-    const int r0 = p * rowsPer, r1 = (r0 + rowsPer < n) ? r0 + rowsPer : n;
+    const int r0 = pr0[p], r1 = pr1[p];
     const int w = n - r0;
     const double *src = pin[p & 1];
 #pragma omp parallel for schedule(static)
@@ -776,6 +792,8 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, lo
     cudaFreeHost(pin[k]);
     cudaEventDestroy(done[k]);
   }
+  free(pr0);
+  free(pr1);
   if (bytes) *bytes = moved;
   return 0;
 }

@@ -126,7 +126,8 @@ const char *ecpdev_last_error(void);
 /* matrix accumulation target (device resident, nAO x nAO, zeroed) */
 int ecpdev_matrix_begin(EcpDev *d);
 int ecpdev_matrix_download(EcpDev *d, double *host /* nAO*nAO */);
-int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, long long *bytes);
+int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned /* [nAO] or NULL */,
+                              long long *bytes);
 void *ecpdev_matrix_ptr(EcpDev *d);
 /* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks */
 int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, double *hostBlocks, EcpDevStats *stats);

@@ -136,7 +136,7 @@ def test_screening_and_triple_list_identical(name):
 
 
 def test_shards_partition_the_triples():
-    s = synth.cfg3(4)
+    s = synth.cfg5(30)
     with capi.Handle(s, tables_only=True) as h:
         full = {tuple(r) for r in h.triple_list()}
         seen = set()
