@@ -177,6 +177,9 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
       return -rc;
     }
     add_stats(h, &st, msBuild);
+    if (getenv("LIBECP_B200_TRACE"))
+      fprintf(stderr, "[libecp_b200] rank %d batch: %d triples build %.1f ms run_batch wall %.1f ms device %.1f ms\n", h->rank,
+              b->nTriples, msBuild, now_ms() - t0 - msBuild, st.ms_total);
     if (st.err1 && result == 0) result = 1; /* src/libecp.h:23-27 */
     if (st.err2 && result == 0) result = 2;
     if (result) break;
@@ -213,6 +216,7 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
 
 int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   const int n = h->tab->v.nAO;
+  const double tCall = now_ms();
   void *dm = NULL;
   const int rc = libecp_b200_integrals_device(h, &dm, NULL);
   if (rc < 0 || h->empty) return rc;
@@ -225,7 +229,11 @@ int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
       if (ecp_pair_owner(s, s, h->world) == h->rank)
         for (int k = 0; k < IJK_DIM(v->shellL[s]); k++) owned[v->shellAO[s] + k] = 1;
   }
+  const double tA = now_ms();
   const int rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, owned, &moved);
+  if (getenv("LIBECP_B200_TRACE"))
+    fprintf(stderr, "[libecp_b200] rank %d/%d integrals_host: add_to_host %.1f ms (whole call so far %.1f ms)\n", h->rank, h->world,
+            now_ms() - tA, now_ms() - tCall);
   free(owned);
   h->stats.d2h_bytes += moved;
   if (rc2) return -rc2;

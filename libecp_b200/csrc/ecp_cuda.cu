@@ -17,6 +17,7 @@
  *   k_shift      binomial shift to A/B, x4pi / x16pi^2, block + matrix    src/util.c:246-334, getIntegrals.c:22-43
  */
 #include <cuda_runtime.h>
+#include <omp.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -25,6 +26,7 @@
 #include "ecp_math.h"
 
 #define KM ECP_KMAX
+
 #define ROWSTRIDE 53 /* doubles per tabulated point row in shared memory (odd -> conflict-free lane rows) */
 #define ROW_W 0
 #define ROW_CU 1
@@ -508,6 +510,15 @@ __global__ void k_chi(DevT t, DevB b, long long nElem) {
 /* ---- shift to A/B-centred Cartesians, normalise, write blocks / accumulate matrix ---- */
 #include "ecp_shift.cuh"
 
+/* gather M[i][i..n) of the listed rows back to back (one block per row) for a contiguous D2H */
+__global__ void k_pack_rows(const double *__restrict__ M, int n, const int *__restrict__ rows,
+                            const long long *__restrict__ off, long long base, double *__restrict__ out) {
+  const int i = rows[blockIdx.x];
+  double *o = out + (off[blockIdx.x] - base) - i;
+  const double *src = M + (size_t)i * n;
+  for (int j = i + threadIdx.x; j < n; j += blockDim.x) o[j] = src[j];
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* FP64 FMA peak probe (roofline denominator when no measured FP64 peak is published) */
 __global__ void k_fp64_probe(double *out, int iters) {
@@ -542,7 +553,7 @@ struct EcpDev {
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
-  Buf t1list, t1mask, t1count, clsJ, Jbuf;
+  Buf t1list, t1mask, t1count, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
 };
 
@@ -695,7 +706,8 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
                &d->ssFOff, &d->trA, &d->trB, &d->trOut, &d->trPair, &d->prTriple,
                &d->clsPairBase, &d->clsQBase, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
                &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags,
-               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count, &d->clsJ, &d->Jbuf};
+               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits,
+               &d->fbTotals, &d->fbR};
   for (size_t i = 0; i < sizeof(bs) / sizeof(bs[0]); i++)
     if (bs[i]->p) cudaFreeAsync(bs[i]->p, d->s1);
   cudaStreamSynchronize(d->s1);
@@ -732,68 +744,119 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   int rowsPer = (int)(panelBytes / ((size_t)n * sizeof(double)));
   if (rowsPer < 1) rowsPer = 1;
   if (rowsPer > n) rowsPer = n;
-  /* panels = runs of rows this rank owns (all rows when rowOwned == NULL), at most rowsPer rows each: a sharded
-   * rank's partial matrix is zero outside the AO rows of its shells, so those rows are never transferred */
-  int *pr0 = (int *)malloc((size_t)(n + 1) * sizeof(int)), *pr1 = (int *)malloc((size_t)(n + 1) * sizeof(int));
-  int nPanels = 0;
-  for (int i = 0; i < n;) {
-    if (rowOwned && !rowOwned[i]) {
-      i++;
-      continue;
+  (void)rowsPer;
+  /* rows this rank owns (all rows when rowOwned == NULL): a sharded rank's partial matrix is zero outside the AO
+   * rows of its shells, so other rows are never transferred.  The upper-triangle parts M[i][i..n) of the owned
+   * rows are packed back to back on the device (k_pack_rows), moved in panels of ~24 MB with one contiguous copy
+   * each, and added to the caller's matrix by all host threads while the next panel is in flight. */
+  int *rows = (int *)malloc((size_t)(n + 1) * sizeof(int));
+  long long *off = (long long *)malloc((size_t)(n + 2) * sizeof(long long));
+  int nR = 0;
+  long long tot = 0;
+  for (int i = 0; i < n; i++)
+    if (!rowOwned || rowOwned[i]) {
+      rows[nR] = i;
+      off[nR] = tot;
+      tot += n - i;
+      nR++;
     }
-    int j = i;
-    while (j < n && j - i < rowsPer && (!rowOwned || rowOwned[j])) j++;
-    pr0[nPanels] = i;
-    pr1[nPanels] = j;
-    nPanels++;
-    i = j;
+  off[nR] = tot;
+  const long long panelElems = (long long)(panelBytes / sizeof(double)) > n ? (long long)(panelBytes / sizeof(double)) : n;
+  Buf dRows = {NULL, 0}, dOff = {NULL, 0}, dStage[2] = {{NULL, 0}, {NULL, 0}};
+  g_allocStream = d->s1;
+  int rc = ensure(&dRows, (size_t)(nR + 1) * sizeof(int));
+  if (!rc) rc = ensure(&dOff, (size_t)(nR + 2) * sizeof(long long));
+  if (!rc) rc = ensure(&dStage[0], (size_t)panelElems * sizeof(double));
+  if (!rc) rc = ensure(&dStage[1], (size_t)panelElems * sizeof(double));
+  if (rc) return rc;
+  /* pinned staging buffers are kept for the life of the process: cudaMallocHost of tens of MB costs far more
+   * than the transfer itself */
+  static double *s_pin[2] = {NULL, NULL};
+  static size_t s_pinCap = 0;
+  if (s_pinCap < (size_t)panelElems * sizeof(double)) {
+    for (int k = 0; k < 2; k++) {
+      if (s_pin[k]) cudaFreeHost(s_pin[k]);
+      s_pin[k] = NULL;
+      CK(cudaMallocHost((void **)&s_pin[k], (size_t)panelElems * sizeof(double)));
+    }
+    s_pinCap = (size_t)panelElems * sizeof(double);
   }
-  double *pin[2] = {NULL, NULL};
+  double *pin[2] = {s_pin[0], s_pin[1]};
   cudaEvent_t done[2];
   for (int k = 0; k < 2; k++) {
-    CK(cudaMallocHost((void **)&pin[k], (size_t)rowsPer * n * sizeof(double)));
+
     CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
   }
+  if (nR) {
+    CK(cudaMemcpyAsync(dRows.p, rows, (size_t)nR * sizeof(int), cudaMemcpyHostToDevice, d->s1));
+    CK(cudaMemcpyAsync(dOff.p, off, (size_t)(nR + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->s1));
+  }
+  /* panel boundaries in row-list positions */
+  int *pb = (int *)malloc((size_t)(nR + 2) * sizeof(int));
+  int nPanels = 0;
+  for (int k = 0; k < nR;) {
+    int e = k + 1;
+    while (e < nR && off[e + 1] - off[k] <= panelElems) e++;
+    pb[nPanels++] = k;
+    k = e;
+  }
+  pb[nPanels] = nR;
   long long moved = 0;
   auto issue = [&](int p) -> cudaError_t {
-    const int r0 = pr0[p], r1 = pr1[p];
-    const size_t width = (size_t)(n - r0) * sizeof(double); /* columns r0..n-1 cover the upper triangle of the panel */
-    moved += (long long)width * (r1 - r0);
-    cudaError_t e = cudaMemcpy2DAsync(pin[p & 1], width, d->matrix + (size_t)r0 * n + r0, (size_t)n * sizeof(double),
-                                      width, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, d->s1);
+    const int k0 = pb[p], k1 = pb[p + 1];
+    const long long elems = off[k1] - off[k0];
+    k_pack_rows<<<k1 - k0, 256, 0, d->s1>>>(d->matrix, n, (const int *)dRows.p + k0, (const long long *)dOff.p + k0,
+                                           off[k0], (double *)dStage[p & 1].p);
+    moved += elems * (long long)sizeof(double);
+    cudaError_t e = cudaMemcpyAsync(pin[p & 1], dStage[p & 1].p, (size_t)elems * sizeof(double), cudaMemcpyDeviceToHost, d->s1);
     if (e != cudaSuccess) return e;
     return cudaEventRecord(done[p & 1], d->s1);
   };
+  const bool trace = getenv("LIBECP_B200_TRACE") != NULL;
+  double tWait = 0, tAdd = 0, tStart = omp_get_wtime();
   if (nPanels) CK(issue(0));
   for (int p = 0; p < nPanels; p++) {
     if (p + 1 < nPanels) CK(issue(p + 1));
+    const double tw0 = omp_get_wtime();
     CK(cudaEventSynchronize(done[p & 1]));
-    const int r0 = pr0[p], r1 = pr1[p];
-    const int w = n - r0;
+    const double tw1 = omp_get_wtime();
+    tWait += tw1 - tw0;
+    const int k0 = pb[p], k1 = pb[p + 1];
     const double *src = pin[p & 1];
-#pragma omp parallel for schedule(static)
-    for (int i = r0; i < r1; i++) {
-      const double *sr = src + (size_t)(i - r0) * w;
+    const long long base = off[k0];
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int k = k0; k < k1; k++) {
+      const int i = rows[k];
+      const double *sr = src + (off[k] - base) - i; /* sr[j] = M[i][j] for j >= i */
       double *dr = host + (size_t)i * rowdim;
       /* the ECP matrix is block sparse (a block is non-zero only if both shells reach a common centre):
        * runs of 32 zeros are skipped so that the caller's matrix is only touched where something is added */
       int j = i;
       for (; j + 32 <= n; j += 32) {
-        const double *s32 = sr + (j - r0);
+        const double *s32 = sr + j;
         int any = 0;
-        for (int k = 0; k < 32; k++) any |= (s32[k] != 0.0);
+        for (int q = 0; q < 32; q++) any |= (s32[q] != 0.0);
         if (any)
-          for (int k = 0; k < 32; k++) dr[j + k] += s32[k];
+          for (int q = 0; q < 32; q++) dr[j + q] += s32[q];
       }
-      for (; j < n; j++) dr[j] += sr[j - r0];
+      for (; j < n; j++) dr[j] += sr[j];
     }
+    tAdd += omp_get_wtime() - tw1;
   }
+  if (trace)
+    fprintf(stderr, "[libecp_b200] d2h+add: rows %d panels %d bytes %.1f MB setup+alloc %.1f ms wait %.1f ms add %.1f ms threads %d\n",
+            nR, nPanels, moved / 1e6, 0.0, 1e3 * tWait, 1e3 * tAdd, omp_get_max_threads());
+  (void)tStart;
   for (int k = 0; k < 2; k++) {
-    cudaFreeHost(pin[k]);
+
     cudaEventDestroy(done[k]);
+    cudaFreeAsync(dStage[k].p, d->s1);
   }
-  free(pr0);
-  free(pr1);
+  cudaFreeAsync(dRows.p, d->s1);
+  cudaFreeAsync(dOff.p, d->s1);
+  free(rows);
+  free(off);
+  free(pb);
   if (bytes) *bytes = moved;
   return 0;
 }
