@@ -200,7 +200,7 @@ def falg_per_kernel(workload, executed):
 KERNEL_OF = {"tables": "ms_tables", "fastT": "ms_fastT", "fallback": "ms_fallback", "link": "ms_link",
              "type1": "ms_type1", "chi": "ms_chi", "shift": "ms_shift"}
 KERNEL_NAME = {"tables": "k_atomslot+k_omegaX+k_Ftab", "fastT": "k_fastT", "fallback": "k_fallbackT", "link": "k_link",
-               "type1": "k_t1prep+k_type1Q", "chi": "k_chi", "shift": "k_shift"}
+               "type1": "k_t1prep+k_type1S<LAB>+k_type1L<LAB>", "chi": "k_chi", "shift": "k_shiftJ+k_shiftI"}
 
 
 def measured_peaks():
@@ -211,15 +211,25 @@ def measured_peaks():
         return {}
 
 
-def roofline(workload, stats, nsteps, peak_tf):
+def roofline(workload, stats, nsteps, peak_tf, serial_stats=None):
+    """stats: per-step averages of the timed (overlapped, two streams) steps; serial_stats: same from the untimed
+    single-stream pass - its per-kernel event times are each kernel's own duration and pick the dominant kernel"""
     flops, how = falg_per_kernel(workload, stats["executed_triples"])
     if not flops:
         return None
-    times = {k: stats[v] for k, v in KERNEL_OF.items()}
+    ks = serial_stats or stats
+    times = {k: ks[v] for k, v in KERNEL_OF.items()}
     dom = max(times, key=lambda k: times[k])
     ach = flops[dom] / (times[dom] * 1e-3) / 1e12 if times[dom] > 0 else 0.0
     span = stats["ms_device_total"]
+    extra = {}
+    if serial_stats:
+        extra = {"kernel_times": "single-stream pass (CUDA events on the launching stream, no overlap)",
+                 "kernel_ms_per_step_overlapped": {k: round(stats[v], 4) for k, v in KERNEL_OF.items()},
+                 "kernel_share_of_serial_step": {k: round(v / max(sum(times.values()), 1e-9), 4) for k, v in times.items()},
+                 "device_ms_serial_step": round(serial_stats["ms_device_total"], 4)}
     return {
+        **extra,
         "bound": "fp64", "kernel": KERNEL_NAME[dom], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": ach / peak_tf if peak_tf else None, "traffic": None,
         "peak_source": "FP64 FMA probe kernel run by bench.py on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
@@ -299,6 +309,19 @@ def run_b200(args):
     ms = max_over_ranks(ms)
     clocks = sampler.stop() if rank == 0 else None
     stats = {k: v / args.steps for k, v in agg.items()}
+    # per-kernel durations for the roofline: an extra, untimed pass with the type-1 and type-2 kernels on ONE stream
+    # (in the timed steps the two streams overlap, which inflates each kernel's event-to-event time)
+    serial_stats = None
+    if world == 1:
+        h.set_serial_kernels(True)
+        h.integrals_device()
+        sagg = None
+        for _ in range(2):
+            h.integrals_device()
+            st = h.stats()
+            sagg = st if sagg is None else {k: sagg[k] + v for k, v in st.items()}
+        serial_stats = {k: v / 2 for k, v in sagg.items()}
+        h.set_serial_kernels(False)
     executed_all = sum_over_ranks(stats["executed_triples"])
     launches = sum_over_ranks(agg["kernel_launches"])
     value = nominal * args.steps / (ms * 1e-3)
@@ -341,7 +364,7 @@ def run_b200(args):
     line = None
     if rank == 0:
         peak_tf = capi.fp64_peak(local, 100000)
-        rl = roofline(args.workload, stats, args.steps, peak_tf) if world == 1 else None
+        rl = roofline(args.workload, stats, args.steps, peak_tf, serial_stats) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -387,7 +410,17 @@ def secondary_au20(capi, torch, peak_tf):
             st = h.stats()
             agg = st if agg is None else {k: agg[k] + v for k, v in st.items()}
         stats = {k: v / steps for k, v in agg.items()}
-    rl = roofline("cfg3", stats, steps, peak_tf)
+        h.set_serial_kernels(True)
+        h.integrals_device()
+        sagg = None
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda.synchronize()
+            h.integrals_device()
+            st = h.stats()
+            sagg = st if sagg is None else {k: sagg[k] + v for k, v in st.items()}
+        serial_stats = {k: v / 5 for k, v in sagg.items()}
+    rl = roofline("cfg3", stats, steps, peak_tf, serial_stats)
     ns = int(s["nshells"])
     nominal = int((s["shellsECP"] > 0).sum()) * ns * (ns + 1) // 2
     return {"workload": desc, "value": nominal / (tot / steps), "unit": UNIT, "ms_per_step": 1e3 * tot / steps,

@@ -47,6 +47,9 @@ typedef struct {
   double ms_build, ms_tables, ms_fastT, ms_fallback, ms_link, ms_type1, ms_chi, ms_shift, ms_device_total;
 } libecp_b200_stats_t;
 void libecp_b200_get_stats(libECPHandle *h, libecp_b200_stats_t *out);
+/* profiling aid: run the type-1 kernels on the same stream as the type-2 kernels (no overlap), so that the per-kernel
+ * times in the statistics are each kernel's own duration */
+void libecp_b200_set_serial_kernels(libECPHandle *h, int on);
 
 /* screening decisions of one centre, for parity tests against the reference's
  * ScreenedGrid/potentialScreening (src/type2.c:148-180,201-203): arrays of nrShells ints */

@@ -24,6 +24,7 @@ EXPORTS = [
     "libecp_b200_integrals_device", "libecp_b200_integrals_host", "libecp_b200_get_stats", "libecp_b200_screening",
     "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
     "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
+    "libecp_b200_set_serial_kernels",
 ]
 
 
@@ -173,6 +174,11 @@ class Handle:
         if rc < 0:
             raise RuntimeError("device failure: " + (lib().libecp_b200_last_error() or b"").decode())
         return rc, ptr.value, n.value
+
+    def set_serial_kernels(self, on=True):
+        L = lib()
+        L.libecp_b200_set_serial_kernels.argtypes = [C.c_void_p, C.c_int]
+        L.libecp_b200_set_serial_kernels(C.c_void_p(self.h), 1 if on else 0)
 
     def stats(self):
         st = Stats()

@@ -54,6 +54,9 @@ void libecp_b200_set_host_threads(int n) {
 #endif
 }
 void libecp_b200_set_tables_only(int on) { g_tables_only = on; }
+void libecp_b200_set_serial_kernels(libECPHandle *h, int on) {
+  if (h && h->dev) ecpdev_set_serial(h->dev, on);
+}
 const char *libecp_b200_last_error(void) { return g_apierr[0] ? g_apierr : ecpdev_last_error(); }
 int libecp_b200_pair_owner(int a, int b, int world) { return ecp_pair_owner(a, b, world); }
 double libecp_b200_fp64_peak(int device, int iters) { return ecpdev_fp64_peak_probe(device, iters); }

@@ -539,7 +539,8 @@ struct Buf {
 };
 struct EcpDev {
   int device, nSM;
-  cudaStream_t s1, s2;
+  cudaStream_t s1, s2, s2real; /* s2 = type-1 stream; aliases s1 in serial (profiling) mode */
+  int serial;
   cudaEvent_t ev[12];
   DevT t;
   DevB b;
@@ -599,7 +600,9 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   d->device = device;
   cudaDeviceGetAttribute(&d->nSM, cudaDevAttrMultiProcessorCount, device);
   cudaStreamCreateWithFlags(&d->s1, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&d->s2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&d->s2real, cudaStreamNonBlocking);
+  d->s2 = d->s2real;
+  d->serial = getenv("LIBECP_B200_SERIAL") != NULL;
   { /* keep freed scratch in the pool instead of returning it to the driver */
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -622,6 +625,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     t.sm.levSlot[i] = h->small_levSlot[i];
   }
   t.sm.levSlot[ECP_SMALL_LEVELS] = h->small_levSlot[ECP_SMALL_LEVELS];
+  ecp_small_meta_bounds(&t.sm, h->small_oidx);
   const int cdT = (h->tmDim + 1) * (h->tmDim + 2) * (h->tmDim + 3) / 6;
   t.fac = upload_const(d, h->fac, h->nfac);
   t.dfac = upload_const(d, h->dfac, h->nfac);
@@ -715,7 +719,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   cudaStreamSynchronize(d->s1);
   for (int i = 0; i < 12; i++) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->s1);
-  cudaStreamDestroy(d->s2);
+  cudaStreamDestroy(d->s2real);
   free(d);
 }
 
@@ -861,6 +865,8 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   return 0;
 }
 extern "C" void *ecpdev_matrix_ptr(EcpDev *d) { return d->matrix; }
+/* serial = 1: type-1 kernels share the type-2 stream, so the per-kernel event times are not inflated by overlap */
+extern "C" void ecpdev_set_serial(EcpDev *d, int on) { d->serial = on; }
 extern "C" long long ecpdev_table_bytes(EcpDev *d) { return d->tableBytes; }
 extern "C" int ecpdev_sync(EcpDev *d) {
   CK(cudaSetDevice(d->device));
@@ -918,6 +924,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   CK(cudaSetDevice(d->device));
   DevB &B = d->b;
   g_allocStream = d->s1;
+  d->s2 = d->serial ? d->s1 : d->s2real;
   const int nc = d->nClasses;
   B.nASlots = h->nASlots;
   B.nSSlots = h->nSSlots;
@@ -1034,6 +1041,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   launches += 2;
   /* type 2 */
   const long long nWork = h->clsWork[nc];
+  CK(cudaEventRecord(d->ev[9], d->s1)); /* in serial mode the type-1 kernels above sit on this stream too */
   if (nWork > 0) {
     k_fastT<<<nblk(nWork, 128), 128, 0, d->s1>>>(t, B, nWork);
     launches++;
@@ -1078,7 +1086,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   if (st) {
     float ms;
     cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); st->ms_tables = ms;
-    cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]); st->ms_fastT = ms;
+    cudaEventElapsedTime(&ms, d->ev[9], d->ev[2]); st->ms_fastT = ms;
     cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); st->ms_fallback = ms;
     cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]); st->ms_link = ms;
     cudaEventElapsedTime(&ms, d->ev[6], d->ev[7]); st->ms_type1 = ms;

@@ -133,6 +133,7 @@ void *ecpdev_matrix_ptr(EcpDev *d);
 int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, double *hostBlocks, EcpDevStats *stats);
 int ecpdev_sync(EcpDev *d);
 long long ecpdev_table_bytes(EcpDev *d);
+void ecpdev_set_serial(EcpDev *d, int on);
 /* debug access to the intermediates of the last batch (tests only): "F" "omegaX" "T" "gamma" "chi" "Q" "tfail" */
 int ecpdev_debug_fetch(EcpDev *d, const char *what, double *dst, int64_t n);
 /* FP64 FMA peak probe used by bench.py for the roofline denominator: returns TFLOP/s */

@@ -289,7 +289,34 @@ ECP_HD void ecp_rsh(int lmax, double theta, double phi, const double *__restrict
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   int levPairs[ECP_SMALL_LEVELS], levJ[ECP_SMALL_LEVELS], levN[ECP_SMALL_LEVELS], levSlot[ECP_SMALL_LEVELS + 1];
+  /* screening shortcuts: a level (or an 8-slot chunk) has no in-window point for the window [start,end] iff
+   * its largest left index is < start and its smallest right index is > end */
+  short levMaxL[ECP_SMALL_LEVELS], levMinR[ECP_SMALL_LEVELS];
+  short chMaxL[ECP_SMALL_SLOTS / 8], chMinR[ECP_SMALL_SLOTS / 8];
 } EcpSmallMeta;
+
+/* fill the screening shortcuts from the slot -> original-index table */
+ECP_HD void ecp_small_meta_bounds(EcpSmallMeta *m, const int16_t *oidx) {
+  for (int v = 0; v < ECP_SMALL_LEVELS; v++) {
+    int mx = -1, mn = 32767;
+    for (int s = m->levSlot[v]; s < m->levSlot[v + 1]; s += 2) {
+      if (oidx[s] > mx) mx = oidx[s];
+      if (oidx[s + 1] < mn) mn = oidx[s + 1];
+    }
+    m->levMaxL[v] = (short)mx;
+    m->levMinR[v] = (short)mn;
+  }
+  for (int c = 0; c < ECP_SMALL_SLOTS / 8; c++) {
+    int mx = -1, mn = 32767;
+    for (int s = 8 * c; s < 8 * c + 8; s += 2) {
+      if (s < 4) continue; /* slots 0..3: centre, pad, first pair - never window-tested */
+      if (oidx[s] > mx) mx = oidx[s];
+      if (oidx[s + 1] < mn) mn = oidx[s + 1];
+    }
+    m->chMaxL[c] = (short)mx;
+    m->chMinR[c] = (short)mn;
+  }
+}
 
 /* One PS93 level update after the level's points were added to I
  * (reference src/gc_integrators.c:201-214).  Returns 1 when converged (result in *res). */
@@ -331,7 +358,9 @@ ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, const double *__restric
   int np = 3;
   for (int v = 0; v < ECP_SMALL_LEVELS; v++) {
     int cnt = 0;
-    const int s0 = meta->levSlot[v], s1 = meta->levSlot[v + 1];
+    const int s0 = meta->levSlot[v];
+    /* a level without any in-window point only moves the bookkeeping (cnt == 0, src/gc_integrators.c:203-208) */
+    const int s1 = (meta->levMaxL[v] < start && meta->levMinR[v] > end) ? s0 : meta->levSlot[v + 1];
     for (int s = s0; s < s1; s += 2) {
       double T = 0.0;
       if (oidx[s] >= start) {

@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(128) k_type1S(DevT t, DevB b, T1Segs segs, int
     pt.live = false;
     pt.w = 0.0;
     bool inWin = false;
-    if (active && slot != 1) {
+    /* chunks >= 2 whose largest left index is below the window and whose smallest right index is above it hold no
+     * in-window point for this pair: nothing to load or tabulate */
+    const bool possible = active && (c < 2 || t.sm.chMaxL[c] >= pp.gs || t.sm.chMinR[c] <= pp.ge);
+    if (possible && slot != 1) {
       const int oi = t.small_oidx[slot];
       /* the three first points are unconditional (src/gc_integrators.c:175-177); afterwards the left point of a
        * pair needs idx >= start, the right one idx <= end (:190-197) */

@@ -31,6 +31,7 @@ int hc_ps93_fastT(const double *Fa, const double *Fb, const double *U, const dou
     m.levN[i] = meta[26 + i];
   }
   for (int i = 0; i <= ECP_SMALL_LEVELS; i++) m.levSlot[i] = meta[39 + i];
+  ecp_small_meta_bounds(&m, oidx);
   return ecp_ps93_fastT(Fa, Fb, U, w, oidx, &m, start, end, tol, res, npts);
 }
 double hc_pot_eval(const int *gl, const double *gn, const double *gd, const double *ga, int n, int l, double r) {
