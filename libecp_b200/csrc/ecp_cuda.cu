@@ -27,18 +27,25 @@
 
 #define KM ECP_KMAX
 
-#define ROWSTRIDE 53 /* doubles per tabulated point row in shared memory (odd -> conflict-free lane rows) */
+/* row of one tabulated large-grid point in shared memory (k_fallbackT): w, C*U, exp, r^0..r^kR, Ka[0..kK], Kb[0..kK],
+ * kR = 2 maxLBS, kK = maxLBS + maxLECP - 1 of the handle (f/L=4: 24 doubles, h/L=6: 36); the Bessel scratch
+ * d[0..kK+5] stays in (L1-cached) local memory so that it does not cost shared memory, i.e. occupancy.
+ * The stride is made odd so that the 32 lane rows fall into distinct banks. */
 #define ROW_W 0
 #define ROW_CU 1
 #define ROW_EX 2
-#define ROW_RN 3            /* rn[0..KM]  */
-#define ROW_KA (3 + KM + 1) /* Ka[0..KM]  */
-#define ROW_KB (3 + 2 * (KM + 1))
-#define ROW_D (3 + 3 * (KM + 1)) /* Bessel scratch d[0..KM+5] */
-#define ROW_USED (3 + 3 * (KM + 1))
-#if (ROW_D + KM + 6) > ROWSTRIDE
-#error row too small
-#endif
+#define ROW_RN 3            /* rn[0..kR]  */
+struct FbLayout {
+  int rowKA, rowKB, stride;
+};
+static FbLayout fb_layout(int maxLBS, int maxLECP) {
+  const int kR = 2 * maxLBS, kK = maxLBS + maxLECP - 1;
+  FbLayout L;
+  L.rowKA = ROW_RN + kR + 1;
+  L.rowKB = L.rowKA + kK + 1;
+  L.stride = (L.rowKB + kK + 1) | 1;
+  return L;
+}
 #define FB_WARPS 4
 
 static char g_err[512] = "";
@@ -68,11 +75,12 @@ struct DevT {
   const int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO, *atomMaxL;
   const double *primD, *primA;
   const int *typeL, *typeGaussOff, *gaussL;
-  const double *gaussN, *gaussD, *gaussA, *typeUtab, *typeUL;
+  const double *gaussN, *gaussD, *gaussA, *typeUtabT, *typeUL; /* typeUtabT: [type][slot][l][N] */
   const int *clsLa, *clsLb, *clsL, *clsNq, *clsQOff, *clsQlOff, *qlist, *clsQidxOff;
   const int16_t *qidx;
   int nAO;
 };
+struct T1Rec;
 struct DevB {
   int nASlots, nSSlots, nTriples;
   long long nPairs;
@@ -90,10 +98,18 @@ struct DevB {
   double *rshX, *uspX, *omX, *F, *T, *gamma, *chi, *Q, *rshP, *sP, *blocks, *matrix;
   unsigned char *tfail;
   int *tflags, *items;
+  T1Rec *t1rec; /* per primitive pair, written by k_t1prep (ecp_type1.cuh) */
   int *counters; /* [0] nItems [1] work counter [2] err1 [3] err2 [4] nFastFail [5] nType1Fail [6] stale [7] work2 */
 };
 #define RSHX_STRIDE 121
 #define USPX_STRIDE 216
+
+/* small-grid weights / abscissae / original indices in slot order.  Every lane of a warp visits the slots in lock
+ * step, so these reads are warp-uniform: constant memory serves them without touching the LSU pipe.  The small grid
+ * is the same for every handle (order 128, KK map; reference src/type1.c:24,56-58, src/type2.c:60,90-92). */
+__constant__ double c_small_w[ECP_SMALL_SLOTS];
+__constant__ double c_small_r[ECP_SMALL_SLOTS];
+__constant__ int16_t c_small_oidx[ECP_SMALL_SLOTS];
 
 /* ---------------------------------------------------------------------------------------------- */
 __device__ __forceinline__ int find_class(const long long *prefix, int nc, long long w) {
@@ -200,10 +216,11 @@ __global__ void __launch_bounds__(ECP_SMALL_SLOTS) k_Ftab(DevT t, DevB b) {
         if (i <= lmaxA) acc[i] += da * K[i] * e;
     }
   }
-  double *F = b.F + (size_t)b.ssFOff[ss] * ECP_SMALL_SLOTS + k;
+  /* slot-major: F[slot][lambda], lambda = 0..lmaxA (the rows a fast-path quadrature multiplies sit side by side) */
+  double *F = b.F + (size_t)b.ssFOff[ss] * ECP_SMALL_SLOTS + (size_t)k * (lmaxA + 1);
 #pragma unroll
   for (int i = 0; i <= KM; i++)
-    if (i <= lmaxA) F[(size_t)i * ECP_SMALL_SLOTS] = acc[i];
+    if (i <= lmaxA) F[i] = acc[i];
 }
 
 /* ---- type-2 fast path: one thread per used quadrature ---- */
@@ -218,12 +235,15 @@ __global__ void k_fastT(DevT t, DevB b, long long nWork) {
   const int l = q & 15, l1 = (q >> 4) & 15, l2 = (q >> 8) & 15, l3 = (q >> 12) & 15;
   const int sa = b.trA[tri], sb = b.trB[tri];
   const int type = b.asType[b.ssASlot[sa]];
-  const double *Fa = b.F + ((size_t)b.ssFOff[sa] + l1) * ECP_SMALL_SLOTS;
-  const double *Fb = b.F + ((size_t)b.ssFOff[sb] + l2) * ECP_SMALL_SLOTS;
-  const double *U = t.typeUtab + (((size_t)type * t.maxLECP + l) * t.nU + l3) * ECP_SMALL_SLOTS;
+  const int Lc = t.clsL[c];
+  const int strA = Lc + t.clsLa[c], strB = Lc + t.clsLb[c], strU = t.maxLECP * t.nU;
+  const double *Fa = b.F + (size_t)b.ssFOff[sa] * ECP_SMALL_SLOTS + l1;
+  const double *Fb = b.F + (size_t)b.ssFOff[sb] * ECP_SMALL_SLOTS + l2;
+  const double *U = t.typeUtabT + (size_t)type * ECP_SMALL_SLOTS * strU + l * t.nU + l3;
   const int gs = max(b.ssStart[sa], b.ssStart[sb]), ge = max(b.ssEnd[sa], b.ssEnd[sb]); /* src/libecp.c:315-316 */
   double res = 0.0;
-  const int rc = ecp_ps93_fastT(Fa, Fb, U, t.small_w, t.small_oidx, &t.sm, gs, ge, t.tolerance, &res, (int *)0);
+  const int rc = ecp_ps93_fastT(Fa, strA, Fb, strB, U, strU, c_small_w, c_small_oidx, &t.sm, gs, ge, t.tolerance, &res,
+                                (int *)0);
   const long long o = w; /* = class T base + (triple - first) * nq + k */
   if (rc) {
     b.T[o] = 0.0;
@@ -244,10 +264,10 @@ struct WarpSmem {
   int *qk;
   unsigned char *done;
 };
-__device__ __forceinline__ WarpSmem carve(unsigned char *base, int maxq) {
+__device__ __forceinline__ WarpSmem carve(unsigned char *base, int maxq, int stride) {
   WarpSmem s;
   s.rows = (double *)base;
-  s.sI = s.rows + 32 * ROWSTRIDE;
+  s.sI = s.rows + 32 * stride;
   s.sP = s.sI + maxq;
   s.sQ = s.sP + maxq;
   s.sAcc = s.sQ + maxq;
@@ -255,14 +275,15 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, int maxq) {
   s.done = (unsigned char *)(s.qk + maxq);
   return s;
 }
-static size_t warp_smem_bytes(int maxq) {
-  return (((size_t)32 * ROWSTRIDE * 8 + (size_t)maxq * 8 * 4 + (size_t)maxq * 4 + (size_t)maxq + 16) + 15) & ~(size_t)15;
+static size_t warp_smem_bytes(int maxq, int stride) {
+  return (((size_t)32 * stride * 8 + (size_t)maxq * 8 * 4 + (size_t)maxq * 4 + (size_t)maxq + 16) + 15) & ~(size_t)15;
 }
 
 /* ---- type-2 fallback: one warp per (triple, l) with failed small-grid quadratures ---- */
-__global__ void __launch_bounds__(32 * FB_WARPS) k_fallbackT(DevT t, DevB b, int maxq, int warpBytes) {
+__global__ void __launch_bounds__(32 * FB_WARPS, 5) k_fallbackT(DevT t, DevB b, int maxq, int warpBytes, FbLayout fl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const WarpSmem s = carve(smem_raw + (size_t)(threadIdx.x >> 5) * warpBytes, maxq);
+  const WarpSmem s = carve(smem_raw + (size_t)(threadIdx.x >> 5) * warpBytes, maxq, fl.stride);
+  const int ROWSTRIDE = fl.stride, ROW_KA = fl.rowKA, ROW_KB = fl.rowKB;
   const int lane = threadIdx.x & 31;
   const int nItems = b.counters[0];
   for (;;) {
@@ -337,8 +358,12 @@ __global__ void __launch_bounds__(32 * FB_WARPS) k_fallbackT(DevT t, DevB b, int
               if (slot == 0 && r > dAC && r > dBC && e < t.lnAcc2) atomicAdd(&b.counters[6], 1);
               if (live) {
                 const double U = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, l, r);
-                ecp_bessel_mem(t.besselT, t.besselStride, t.besselC, laC, s1 * r, row + ROW_KA, row + ROW_D);
-                ecp_bessel_mem(t.besselT, t.besselStride, t.besselC, lbC, s2 * r, row + ROW_KB, row + ROW_D);
+                /* K_a then K_b through one copy of the Bessel code (instruction-cache footprint) */
+                double dscr[KM + 6];
+#pragma unroll 1
+                for (int ab = 0; ab < 2; ab++)
+                  ecp_bessel_mem(t.besselT, t.besselStride, t.besselC, ab ? lbC : laC, (ab ? s2 : s1) * r,
+                                 row + (ab ? ROW_KB : ROW_KA), dscr);
                 row[ROW_W] = t.large_w[slot] * i1;
                 row[ROW_CU] = Cc * U;
                 row[ROW_EX] = exp(e);
@@ -451,7 +476,9 @@ __global__ void k_link(DevT t, DevB b, long long nElem) {
   b.gamma[w] = g;
 }
 
-/* ---- type 1, per primitive pair: P = 2(za r_AC + zb r_BC), |P|, S_lm(P^) ---- */
+#include "ecp_type1.cuh"
+
+/* ---- type 1, per primitive pair: P = 2(za r_AC + zb r_BC), |P|, S_lm(P^), and the pair record of the radial kernels ---- */
 __global__ void k_t1prep(DevT t, DevB b) {
   const long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pr >= b.nPairs) return;
@@ -462,6 +489,7 @@ __global__ void k_t1prep(DevT t, DevB b) {
   const int Nb = t.shellK[shb];
   const int ip = (int)(pr - b.trPair[tri]), pa = ip / Nb, pb = ip % Nb;
   const double za = t.primA[t.shellPrim[sha] + pa], zb = t.primA[t.shellPrim[shb] + pb];
+  const double ca = t.primD[t.shellPrim[sha] + pa], cb = t.primD[t.shellPrim[shb] + pb];
   const double *rA = b.asR + 4 * asa, *rB = b.asR + 4 * asb;
   const double Px = 2.0 * (za * rA[0] + zb * rB[0]);
   const double Py = 2.0 * (za * rA[1] + zb * rB[1]);
@@ -469,11 +497,27 @@ __global__ void k_t1prep(DevT t, DevB b) {
   double r, th, ph;
   ecp_sphcoord(Px, Py, Pz, &r, &th, &ph);
   const int lab = t.shellL[sha] + t.shellL[shb];
-  ecp_rsh(lab, th, ph, t.fac, t.dfac, b.rshP + pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pr), pr));
+  const long long qoff = pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pr), pr);
+  ecp_rsh(lab, th, ph, t.fac, t.dfac, b.rshP + qoff);
   b.sP[pr] = r;
+  const double dAC = rA[3], dBC = rB[3];
+  T1Rec rec;
+  rec.z = -za - zb;
+  rec.sS = r;
+  rec.zd2 = -za * dAC * dAC - zb * dBC * dBC; /* src/type1.c:103 */
+  rec.CcS = ca * cb * exp(rec.zd2);           /* src/type1.c:113 */
+  rec.CcL = ca * cb;                          /* src/type1.c:151 */
+  const double zp = za + zb;
+  ecp_fm06_map(zp, (za * dAC + zb * dBC) / zp, &rec.i1, &rec.i2);
+  rec.qoff = qoff;
+  rec.type = b.asType[asa];
+  rec.gs = max(b.ssStart[ssa], b.ssStart[ssb]); /* src/libecp.c:315-316 */
+  rec.ge = max(b.ssEnd[ssa], b.ssEnd[ssb]);
+  rec.pad = 0;
+  b.t1rec[pr] = rec;
 }
 
-#include "ecp_type1.cuh"
+#include "ecp_type1_v1.cuh"
 
 /* ---- chi[i][j], one thread per element ---- */
 __global__ void k_chi(DevT t, DevB b, long long nElem) {
@@ -554,8 +598,9 @@ struct EcpDev {
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
-  Buf t1list, t1mask, t1count, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
+  Buf t1list, t1mask, t1count, t1work, t1rec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
+  int t1v1, t1block; /* LIBECP_B200_T1=v1 selects the round-1 type-1 kernels; LIBECP_B200_T1BLOCK = 32/64/128 */
 };
 
 /* scratch buffers come from the device's stream-ordered pool (release threshold raised in ecpdev_create),
@@ -603,6 +648,13 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   cudaStreamCreateWithFlags(&d->s2real, cudaStreamNonBlocking);
   d->s2 = d->s2real;
   d->serial = getenv("LIBECP_B200_SERIAL") != NULL;
+  {
+    const char *e = getenv("LIBECP_B200_T1");
+    d->t1v1 = e && !strcmp(e, "v1");
+    e = getenv("LIBECP_B200_T1BLOCK");
+    d->t1block = e ? atoi(e) : 64;
+    if (d->t1block != 32 && d->t1block != 64 && d->t1block != 96 && d->t1block != 128) d->t1block = 64;
+  }
   { /* keep freed scratch in the pool instead of returning it to the driver */
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -667,7 +719,20 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   t.gaussN = upload_const(d, h->gaussN, ng);
   t.gaussD = upload_const(d, h->gaussD, ng);
   t.gaussA = upload_const(d, h->gaussA, ng);
-  t.typeUtab = upload_const(d, h->typeUtab, (size_t)h->nTypes * h->maxLECP * h->nU * ECP_SMALL_SLOTS);
+  { /* r^N U_l(r_n): host layout [type][l][N][slot] -> device layout [type][slot][l][N] (see k_fastT) */
+    const size_t rows = (size_t)h->maxLECP * h->nU, tot = (size_t)h->nTypes * rows * ECP_SMALL_SLOTS;
+    double *tr = (double *)malloc((tot ? tot : 1) * sizeof(double));
+    for (int ty = 0; ty < h->nTypes; ty++)
+      for (size_t r = 0; r < rows; r++)
+        for (int sl = 0; sl < ECP_SMALL_SLOTS; sl++)
+          tr[((size_t)ty * ECP_SMALL_SLOTS + sl) * rows + r] = h->typeUtab[((size_t)ty * rows + r) * ECP_SMALL_SLOTS + sl];
+    t.typeUtabT = upload_const(d, tr, tot);
+    cudaStreamSynchronize(d->s1); /* tr is pageable: the copy has left it when the stream is idle */
+    free(tr);
+  }
+  cudaMemcpyToSymbolAsync(c_small_w, h->small_w, ECP_SMALL_SLOTS * sizeof(double), 0, cudaMemcpyHostToDevice, d->s1);
+  cudaMemcpyToSymbolAsync(c_small_r, h->small_r, ECP_SMALL_SLOTS * sizeof(double), 0, cudaMemcpyHostToDevice, d->s1);
+  cudaMemcpyToSymbolAsync(c_small_oidx, h->small_oidx, ECP_SMALL_SLOTS * sizeof(int16_t), 0, cudaMemcpyHostToDevice, d->s1);
   t.typeUL = upload_const(d, h->typeUL, (size_t)h->nTypes * ECP_SMALL_SLOTS);
   t.clsLa = upload_const(d, h->clsLa, h->nClasses);
   t.clsLb = upload_const(d, h->clsLb, h->nClasses);
@@ -710,7 +775,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
                &d->ssFOff, &d->trA, &d->trB, &d->trOut, &d->trPair, &d->prTriple,
                &d->clsPairBase, &d->clsQBase, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
                &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags,
-               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits,
+               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count, &d->t1work, &d->t1rec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits,
                &d->fbTotals, &d->fbR};
   for (size_t i = 0; i < sizeof(bs) / sizeof(bs[0]); i++)
     if (bs[i]->p) cudaFreeAsync(bs[i]->p, d->s1);
@@ -892,15 +957,40 @@ extern "C" int ecpdev_sync(EcpDev *d) {
 
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-/* small-grid + large-grid type-1 kernels for one LAB value; each launch group gets its own failure counter */
+/* small-grid + large-grid type-1 kernels for one LAB value; each launch group gets its own work and failure counters.
+ * Persistent groups: the grid is sized to the device (resident blocks of this instantiation), not to the pair count. */
 template <int LAB>
 static void launch_type1_t(EcpDev *d, const T1Segs &sg, long long listOff, int slot) {
   const long long n = sg.prefix[sg.nseg];
   int *cnt = (int *)d->t1count.p + slot;
+  int *work = (int *)d->t1work.p + 2 * slot;
   int *list = (int *)d->t1list.p + listOff;
   unsigned long long *mask = (unsigned long long *)d->t1mask.p;
-  k_type1S<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, sg, cnt, list, mask);
-  k_type1L<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, cnt, list, mask, d->b.counters + 2);
+  if (d->t1v1) {
+    k_type1S_v1<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, sg, cnt, list, mask);
+    k_type1L_v1<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, cnt, list, mask, d->b.counters + 2);
+    return;
+  }
+  const int block = d->t1block;
+  const size_t smem = t1_smem_bytes(LAB, block);
+  static int occS[5] = {0}, occL[5] = {0}; /* resident blocks per SM, per block size 32/64/96/128 */
+  const int bi = block / 32;
+  if (!occS[bi]) {
+    cudaFuncSetAttribute(k_type1S<LAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_type1L<LAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS[bi], k_type1S<LAB>, block, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occL[bi], k_type1L<LAB>, block, smem);
+    if (occS[bi] < 1) occS[bi] = 1;
+    if (occL[bi] < 1) occL[bi] = 1;
+  }
+  const long long groupsPerBlock = block / 8;
+  const long long wantS = (n + groupsPerBlock - 1) / groupsPerBlock;
+  const long long capS = (long long)d->nSM * occS[bi], capL = (long long)d->nSM * occL[bi];
+  k_type1S<LAB><<<(unsigned)(wantS < capS ? wantS : capS), block, smem, d->s2>>>(d->t, d->b, sg, work, cnt, list, mask);
+  /* the number of failed pairs is only known on the device: at most one resident wave, blocks without work leave */
+  const long long wantL = (wantS + 3) / 4 > 1 ? (wantS + 3) / 4 : 1;
+  k_type1L<LAB><<<(unsigned)(wantL < capL ? wantL : capL), block, smem, d->s2>>>(d->t, d->b, work + 1, cnt, list, mask,
+                                                                             d->b.counters + 2);
 }
 static void launch_type1(EcpDev *d, int lab, const T1Segs &sg, long long listOff) {
   const int slot = d->launchSeq++;
@@ -976,6 +1066,12 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
     rc_ = ensure(&d->t1count, 256 * sizeof(int));
     if (rc_) return rc_;
     CK(cudaMemsetAsync(d->t1count.p, 0, 256 * sizeof(int), d->s1));
+    rc_ = ensure(&d->t1work, 512 * sizeof(int));
+    if (rc_) return rc_;
+    CK(cudaMemsetAsync(d->t1work.p, 0, 512 * sizeof(int), d->s1));
+    rc_ = ensure(&d->t1rec, ((size_t)h->nPairs + 1) * sizeof(T1Rec));
+    if (rc_) return rc_;
+    B.t1rec = (T1Rec *)d->t1rec.p;
     d->launchSeq = 0;
   }
   if ((flags & 1) && !d->matrix) {
@@ -994,7 +1090,8 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   CK(cudaMemsetAsync(B.Q, 0, (size_t)h->qTotal * sizeof(double), d->s1));
   const DevT &t = d->t;
   const int maxq2 = d->maxQPerL > 1 ? d->maxQPerL : 1;
-  const size_t sm2 = warp_smem_bytes(maxq2);
+  const FbLayout fbl = fb_layout(d->maxLBS, d->t.maxLECP);
+  const size_t sm2 = warp_smem_bytes(maxq2, fbl.stride);
   cudaFuncSetAttribute(k_fallbackT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm2 * FB_WARPS));
   long long launches = 0;
   CK(cudaEventRecord(d->ev[0], d->s1));
@@ -1048,7 +1145,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   }
   CK(cudaEventRecord(d->ev[2], d->s1));
   if (nWork > 0) {
-    k_fallbackT<<<d->nSM * 4, 32 * FB_WARPS, sm2 * FB_WARPS, d->s1>>>(t, B, maxq2, (int)sm2);
+    k_fallbackT<<<d->nSM * 6, 32 * FB_WARPS, sm2 * FB_WARPS, d->s1>>>(t, B, maxq2, (int)sm2, fbl);
     launches++;
   }
   CK(cudaEventRecord(d->ev[3], d->s1));

@@ -348,12 +348,16 @@ ECP_HD int ecp_psm92_update(int nNew, int cnt, double tol, double I, double pv, 
 
 /* Sequential PS93 quadrature of the type-2 fast path: integrand Fa*Fb*U on slot-ordered rows
  * (reference src/type2.c:319-322 + src/gc_integrators.c:156-217).  Summation order identical to the
- * reference's.  rc 0 converged / 1 failed; *npts = evaluated points. */
-ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, const double *__restrict__ Fb, const double *__restrict__ U,
-                          const double *__restrict__ w, const int16_t *__restrict__ oidx, const EcpSmallMeta *meta,
-                          int start, int end, double tol, double *result, int *npts) {
+ * reference's.  The three rows are strided (element of slot s at Fa[s*sa], Fb[s*sb], U[s*su]): on the device
+ * the tables are slot-major ([slot][lambda] / [slot][l][N]) so that the quadratures of one triple, which sit in
+ * neighbouring lanes and visit the slots in lock step, read neighbouring addresses.
+ * rc 0 converged / 1 failed; *npts = evaluated points. */
+ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
+                          const double *__restrict__ U, int su, const double *__restrict__ w,
+                          const int16_t *__restrict__ oidx, const EcpSmallMeta *meta, int start, int end, double tol,
+                          double *result, int *npts) {
   double p = w[0] * (Fa[0] * Fb[0] * U[0]);
-  double q = w[2] * (Fa[2] * Fb[2] * U[2]) + w[3] * (Fa[3] * Fb[3] * U[3]);
+  double q = w[2] * (Fa[2 * sa] * Fb[2 * sb] * U[2 * su]) + w[3] * (Fa[3 * sa] * Fb[3 * sb] * U[3 * su]);
   double I = p + q;
   int np = 3;
   for (int v = 0; v < ECP_SMALL_LEVELS; v++) {
@@ -364,11 +368,11 @@ ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, const double *__restric
     for (int s = s0; s < s1; s += 2) {
       double T = 0.0;
       if (oidx[s] >= start) {
-        T += w[s] * (Fa[s] * Fb[s] * U[s]);
+        T += w[s] * (Fa[s * sa] * Fb[s * sb] * U[s * su]);
         cnt++;
       }
       if (oidx[s + 1] <= end) {
-        T += w[s + 1] * (Fa[s + 1] * Fb[s + 1] * U[s + 1]);
+        T += w[s + 1] * (Fa[(s + 1) * sa] * Fb[(s + 1) * sb] * U[(s + 1) * su]);
         cnt++;
       }
       I += T;

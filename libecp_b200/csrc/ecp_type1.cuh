@@ -3,20 +3,29 @@
  * Replaces calcQ (reference src/type1.c:94-208) + QIntegrand (:78-88) + the quadrature drivers it calls
  * (src/gc_integrators.c:156-217 PS93, :38-86 PSM92).
  *
- * Mapping: EIGHT LANES PER PRIMITIVE PAIR (four pairs per warp), templated on LAB = la+lb.
- *   - quadrature points are spread across the 8 lanes: every step each lane tabulates ONE grid point of the
+ * Mapping: EIGHT LANES PER PRIMITIVE PAIR (four pairs per warp), templated on LAB = la+lb, PERSISTENT groups.
+ *   - k_t1prep writes one 80-byte record per primitive pair (exponent sum, |P|, prefactors, FM06 map, window, Q offset);
+ *     a group fetches the next pair of its launch from an atomic work counter as soon as its current pair is finished.
+ *     About 15 % of the pairs never converge on the small grid and walk all 48 chunks while the typical pair needs 2-4
+ *     chunks: with a static assignment one such pair kept the other three groups of its warp idle (the round-1 kernels,
+ *     ecp_type1_v1.cuh, spent ~2x the necessary warp-chunks that way).
+ *   - quadrature points are spread across the 8 lanes: every chunk each lane tabulates ONE grid point of the
  *     level-major slot layout (Bessel K_0..K_LAB, r^0..r^LAB, U_L, exp) in registers - only points a level of
  *     the adaptive rule really needs ("touched" points; the reference tabulates the whole window up front,
  *     src/type1.c:121-130);
- *   - the per-point products w*f of all NQ = sum_N (N/2+1) quadratures are reduced over the group with xor
- *     shuffles (pair sums first: T = left + right as in the reference, then across pairs);
- *   - the PS93 / PSM92 state (I,p,q) of quadrature q lives in lane q mod 8 only (static register indices);
- *   - convergence is a ballot over the group; a warp leaves the loop when all four groups are done.
+ *   - the per-point products w*f of all NQ = sum_N (N/2+1) quadratures go through a padded shared-memory tile
+ *     [quadrature][lane]; the lane that owns quadrature q (q mod 8) reads the 8 values back and adds them as
+ *     ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7)): T = left + right as in the reference, then across pairs.  This replaces
+ *     3 double shuffles per quadrature per lane by one store + one load per owned quadrature and makes the level
+ *     update (PS93 / PSM92 state I,p,q of quadrature q lives in lane q mod 8) run on all lanes at once;
+ *   - convergence is a ballot over the group.
  *   k_type1S<LAB>: small 383-point grid, PS93; writes converged Q, records a mask of failed quadratures
  *   k_type1L<LAB>: failed quadratures on the per-pair FM06-mapped 1023-point grid, PSM92
  */
 #ifndef ECP_TYPE1_CUH
 #define ECP_TYPE1_CUH
+
+#include <utility>
 
 #define T1_MAXSEG 24
 struct T1Segs {
@@ -36,39 +45,60 @@ struct T1Point {
 #define T1_NQ(LAB) (((LAB) % 2 == 0) ? ((LAB) / 2 + 1) * ((LAB) / 2 + 1) : ((LAB) / 2 + 1) * ((LAB) / 2 + 2))
 #define T1_FULL 0xffffffffu
 
+/* quadrature q of the loop nest "for N: for lambda = N, N-2, ..." (src/type1.c:132-146) */
+__host__ __device__ constexpr int t1_qN(int q) {
+  int N = 0;
+  while (q >= N / 2 + 1) {
+    q -= N / 2 + 1;
+    N++;
+  }
+  return N;
+}
+__host__ __device__ constexpr int t1_qLam(int q) {
+  int N = 0;
+  while (q >= N / 2 + 1) {
+    q -= N / 2 + 1;
+    N++;
+  }
+  return N - 2 * q;
+}
+
+template <int LAB>
+struct T1Cfg {
+  static constexpr int NQ = T1_NQ(LAB);
+  static constexpr int NQL = (NQ + 7) / 8;
+  static constexpr int ROW = 9;                               /* 8 lane values + 1 pad: conflict-free owner reads */
+  static constexpr int GS = ((NQ * ROW + 7) / 16) * 16 + 8;   /* doubles per group, = 8 mod 16: the two groups of a
+                                                                 half warp store to disjoint banks */
+};
+static size_t t1_smem_bytes(int lab, int block) {
+  const int nq = T1_NQ(lab), gs = ((nq * 9 + 7) / 16) * 16 + 8;
+  return (size_t)(block / 32) * 4 * gs * sizeof(double);
+}
+
 /* w * C * r^N * U * K_lambda * exp(e)  (integrand order of src/type1.c:84) */
 template <int LAB>
 __device__ __forceinline__ double t1_wval(const T1Point<LAB> &p, double Cc, int N, int lam) {
   return p.live ? p.w * (Cc * p.rn[N] * p.u * p.K[lam] * p.ex) : 0.0;
 }
-
-struct T1Pair { /* per-pair parameters, identical in the 8 lanes of a group */
-  long long pr;
-  double za, zb, ca, cb, dAC, dBC, sS, zd2, z;
-  int type, gs, ge;
-};
-
-__device__ __forceinline__ void t1_load_pair(const DevT &t, const DevB &b, long long pr, T1Pair &P) {
-  const int tri = b.prTriple[pr];
-  const int ssa = b.trA[tri], ssb = b.trB[tri];
-  const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
-  const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
-  const int Nb = t.shellK[shb];
-  const int ip = (int)(pr - b.trPair[tri]), pa = ip / Nb, pb = ip % Nb;
-  P.pr = pr;
-  P.za = t.primA[t.shellPrim[sha] + pa];
-  P.zb = t.primA[t.shellPrim[shb] + pb];
-  P.ca = t.primD[t.shellPrim[sha] + pa];
-  P.cb = t.primD[t.shellPrim[shb] + pb];
-  P.dAC = b.asR[4 * asa + 3];
-  P.dBC = b.asR[4 * asb + 3];
-  P.type = b.asType[asa];
-  P.sS = b.sP[pr];
-  P.gs = max(b.ssStart[ssa], b.ssStart[ssb]); /* src/libecp.c:315-316 */
-  P.ge = max(b.ssEnd[ssa], b.ssEnd[ssb]);
-  P.zd2 = -P.za * P.dAC * P.dAC - P.zb * P.dBC * P.dBC; /* src/type1.c:103 */
-  P.z = -P.za - P.zb;
+template <int LAB, int... Q>
+__device__ __forceinline__ void t1_store_vals(const T1Point<LAB> &pt, double Cc, double *dst,
+                                              std::integer_sequence<int, Q...>) {
+  ((dst[Q * T1Cfg<LAB>::ROW] = t1_wval<LAB>(pt, Cc, t1_qN(Q), t1_qLam(Q))), ...);
 }
+
+/* per primitive pair, written by k_t1prep */
+struct __align__(16) T1Rec {
+  double z;        /* -(za + zb)                                   src/type1.c:104 */
+  double sS;       /* |P|, P = 2 (za r_AC + zb r_BC)               src/type1.c:249-250 */
+  double zd2;      /* -za dAC^2 - zb dBC^2                         src/type1.c:103 */
+  double CcS;      /* ca cb exp(zd2)   (small grid)                src/type1.c:113 */
+  double CcL;      /* ca cb            (large grid)                src/type1.c:151 */
+  double i1, i2;   /* FM06 map r = i1 x + i2                       src/gc_integrators.c:316-331 */
+  long long qoff;  /* offset of Q[N][lambda] / S_lm(P^) of the pair */
+  int type, gs;    /* ECP type of the centre; window start         src/libecp.c:315 */
+  int ge, pad;     /* window end                                   src/libecp.c:316 */
+};
 
 template <int LAB>
 __device__ __forceinline__ void t1_fill_point(const DevT &t, double r, double zarg, T1Point<LAB> &p) {
@@ -83,301 +113,311 @@ __device__ __forceinline__ void t1_fill_point(const DevT &t, double r, double za
 
 /* ---------------------------------------------------------------------------------------------- */
 template <int LAB>
-__global__ void __launch_bounds__(128) k_type1S(DevT t, DevB b, T1Segs segs, int *failCount, int *failList,
+__global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_type1S(DevT t, DevB b, T1Segs segs, int *workCtr, int *failCount, int *failList,
                                                 unsigned long long *failMask) {
-  constexpr int NQ = T1_NQ(LAB), NQL = (NQ + 7) / 8;
+  using Cfg = T1Cfg<LAB>;
+  constexpr int NQ = Cfg::NQ, NQL = Cfg::NQL;
+  extern __shared__ __align__(16) double t1_red[];
   const int lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24;
-  const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  bool active = g < segs.prefix[segs.nseg];
-  T1Pair pp;
-  double Cc = 0.0;
+  double *red = t1_red + ((threadIdx.x >> 5) * 4 + (lane >> 3)) * Cfg::GS;
+  const int total = (int)segs.prefix[segs.nseg];
+  bool have = false, drained = false;
+  double z = 0.0, sS = 0.0, Cc = 0.0;
+  int gs = 0, ge = 0;
+  long long pr = 0;
   const double *UL = t.typeUL;
   double *Qo = b.Q;
-  if (active) {
-    int sg = 0;
-    while (segs.prefix[sg + 1] <= g) sg++;
-    t1_load_pair(t, b, segs.start[sg] + (g - segs.prefix[sg]), pp);
-    Cc = pp.ca * pp.cb * exp(pp.zd2); /* src/type1.c:113 */
-    UL = t.typeUL + (size_t)pp.type * ECP_SMALL_SLOTS;
-    Qo = b.Q + pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pp.pr), pp.pr);
-  }
   double I[NQL], P[NQL], Qv[NQL];
-  unsigned open = 0;
+  int qo[NQL]; /* offset of Q[N][lambda] of the quadratures this lane owns (q = 8k + lane) */
 #pragma unroll
   for (int k = 0; k < NQL; k++) {
     I[k] = P[k] = Qv[k] = 0.0;
-    if (active && 8 * k + gl < NQ) open |= 1u << k;
+    const int q = (8 * k + gl < NQ) ? 8 * k + gl : NQ - 1;
+    qo[k] = t1_qN(q) * (LAB + 1) + t1_qLam(q);
   }
-  int v = 4;    /* level being accumulated by chunks >= 2 */
-  int cnt = 0;  /* in-window points of that level */
-  for (int c = 0; c < ECP_SMALL_SLOTS / 8; c++) {
-    if (!__any_sync(T1_FULL, active)) break;
+  unsigned open = 0;
+  int c = 0;   /* chunk of 8 slots the group works on            */
+  int v = 4;   /* level being accumulated by chunks >= 2         */
+  int cnt = 0; /* in-window points of that level so far          */
+  for (;;) {
+    /* ---- a group without a pair takes the next one of this launch ---- */
+    const bool need = !have && !drained;
+    if (__any_sync(T1_FULL, need)) {
+      int g = 0;
+      if (need && gl == 0) g = atomicAdd(workCtr, 1);
+      g = __shfl_sync(T1_FULL, g, gbase);
+      if (need) {
+        if (g < total) {
+          int sg = 0;
+          while (segs.prefix[sg + 1] <= g) sg++;
+          pr = segs.start[sg] + (g - segs.prefix[sg]);
+          const T1Rec rec = b.t1rec[pr];
+          z = rec.z;
+          sS = rec.sS;
+          Cc = rec.CcS;
+          gs = rec.gs;
+          ge = rec.ge;
+          UL = t.typeUL + (size_t)rec.type * ECP_SMALL_SLOTS;
+          Qo = b.Q + rec.qoff;
+          open = 0;
+#pragma unroll
+          for (int k = 0; k < NQL; k++)
+            if (8 * k + gl < NQ) open |= 1u << k;
+          c = 0;
+          v = 4;
+          cnt = 0;
+          have = true;
+        } else {
+          drained = true;
+        }
+      }
+    }
+    if (!__any_sync(T1_FULL, have)) break;
+    /* ---- one chunk: every lane tabulates one slot ---- */
     const int slot = 8 * c + gl;
     T1Point<LAB> pt;
     pt.live = false;
     pt.w = 0.0;
     bool inWin = false;
-    /* chunks >= 2 whose largest left index is below the window and whose smallest right index is above it hold no
-     * in-window point for this pair: nothing to load or tabulate */
-    const bool possible = active && (c < 2 || t.sm.chMaxL[c] >= pp.gs || t.sm.chMinR[c] <= pp.ge);
-    if (possible && slot != 1) {
+    if (have && slot != 1) {
       const int oi = t.small_oidx[slot];
       /* the three first points are unconditional (src/gc_integrators.c:175-177); afterwards the left point of a
        * pair needs idx >= start, the right one idx <= end (:190-197) */
-      inWin = (slot < 4) ? true : ((slot & 1) ? (oi <= pp.ge) : (oi >= pp.gs));
-      if (inWin && oi >= pp.gs && oi < pp.ge) { /* tabulated range [start,end): src/type1.c:121 */
+      inWin = (slot < 4) ? true : ((slot & 1) ? (oi <= ge) : (oi >= gs));
+      if (inWin && oi >= gs && oi < ge) { /* tabulated range [start,end): src/type1.c:121 */
         const double r = t.small_r[slot];
-        const double e = (pp.z * r + pp.sS) * r;
+        const double e = (z * r + sS) * r;
         if (e >= t.lnAcc1) {
           pt.live = true;
           pt.w = t.small_w[slot];
           pt.u = UL[slot];
           pt.ex = exp(e);
-          t1_fill_point<LAB>(t, r, pp.sS * r, pt);
+          t1_fill_point<LAB>(t, r, sS * r, pt);
         }
       }
     }
     const unsigned bal = (__ballot_sync(T1_FULL, inWin) >> gbase) & 0xffu;
-    if (c == 0) {
-      const int cnt0 = __popc(bal & 0x30u), cnt1 = __popc(bal & 0xc0u);
-      int q = 0;
+    /* ---- products of all quadratures -> tile [q][lane]; owner lane q mod 8 reads its rows back ---- */
+    __syncwarp();
+    t1_store_vals<LAB>(pt, Cc, red + gl, std::make_integer_sequence<int, NQ>{});
+    __syncwarp();
+    if (have) {
+      const bool last = (c >= 2) && (8 * c + 8 == t.sm.levSlot[v + 1]);
+      if (c >= 2) cnt += __popc(bal);
 #pragma unroll
-      for (int N = 0; N <= LAB; N++)
-#pragma unroll
-        for (int lam = N; lam >= 0; lam -= 2) {
-          const double val = t1_wval<LAB>(pt, Cc, N, lam);
-          const double v1 = val + __shfl_xor_sync(T1_FULL, val, 1);
-          const double c0 = __shfl_sync(T1_FULL, v1, gbase);
-          const double f0 = __shfl_sync(T1_FULL, v1, gbase + 2);
-          const double a0 = __shfl_sync(T1_FULL, v1, gbase + 4);
-          const double a1 = __shfl_sync(T1_FULL, v1, gbase + 6);
-          if ((q & 7) == gl) {
-            const int k = q >> 3;
-            double res;
-            P[k] = c0;
-            Qv[k] = f0;
-            I[k] = P[k] + Qv[k];
-            I[k] += a0;
-            if ((open >> k & 1) && ecp_ps93_update(t.sm.levJ[0], t.sm.levN[0], cnt0, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res; /* T[l1][l2] += I  (src/type1.c:143) */
-              open &= ~(1u << k);
-            }
-            I[k] += a1;
-            if ((open >> k & 1) && ecp_ps93_update(t.sm.levJ[1], t.sm.levN[1], cnt1, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res;
-              open &= ~(1u << k);
-            }
+      for (int k = 0; k < NQL; k++) {
+        const int q = 8 * k + gl;
+        const double *row = red + (q < NQ ? q : NQ - 1) * Cfg::ROW;
+        const double A = row[0] + row[1], B = row[2] + row[3], Cq = row[4] + row[5], D = row[6] + row[7];
+        double *dst = Qo + qo[k];
+        double res;
+        if (c == 0) {
+          /* slot 0 = centre (p), slots 2,3 = first pair (q), slots 4,5 = level 0, slots 6,7 = level 1 */
+          P[k] = A;
+          Qv[k] = B;
+          I[k] = P[k] + Qv[k];
+          I[k] += Cq;
+          if ((open >> k & 1) &&
+              ecp_ps93_update(t.sm.levJ[0], t.sm.levN[0], __popc(bal & 0x30u), t.tolerance, I[k], &P[k], &Qv[k], &res)) {
+            *dst = res; /* T[l1][l2] += I  (src/type1.c:143) */
+            open &= ~(1u << k);
           }
-          q++;
+          I[k] += D;
+          if ((open >> k & 1) &&
+              ecp_ps93_update(t.sm.levJ[1], t.sm.levN[1], __popc(bal & 0xc0u), t.tolerance, I[k], &P[k], &Qv[k], &res)) {
+            *dst = res;
+            open &= ~(1u << k);
+          }
+        } else if (c == 1) {
+          /* slots 8..11 = level 2, slots 12..15 = level 3 */
+          I[k] += (A + B);
+          if ((open >> k & 1) &&
+              ecp_ps93_update(t.sm.levJ[2], t.sm.levN[2], __popc(bal & 0x0fu), t.tolerance, I[k], &P[k], &Qv[k], &res)) {
+            *dst = res;
+            open &= ~(1u << k);
+          }
+          I[k] += (Cq + D);
+          if ((open >> k & 1) &&
+              ecp_ps93_update(t.sm.levJ[3], t.sm.levN[3], __popc(bal & 0xf0u), t.tolerance, I[k], &P[k], &Qv[k], &res)) {
+            *dst = res;
+            open &= ~(1u << k);
+          }
+        } else {
+          I[k] += ((A + B) + (Cq + D));
+          /* a level without in-window point only moves the bookkeeping, as in the reference (cnt == 0,
+           * src/gc_integrators.c:203-208) */
+          if (last && (open >> k & 1) &&
+              ecp_ps93_update(t.sm.levJ[v], t.sm.levN[v], cnt, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
+            *dst = res;
+            open &= ~(1u << k);
+          }
         }
-    } else if (c == 1) {
-      const int cnt2 = __popc(bal & 0x0fu), cnt3 = __popc(bal & 0xf0u);
-      int q = 0;
-#pragma unroll
-      for (int N = 0; N <= LAB; N++)
-#pragma unroll
-        for (int lam = N; lam >= 0; lam -= 2) {
-          const double val = t1_wval<LAB>(pt, Cc, N, lam);
-          const double v1 = val + __shfl_xor_sync(T1_FULL, val, 1);
-          const double v2 = v1 + __shfl_xor_sync(T1_FULL, v1, 2);
-          const double a2 = __shfl_sync(T1_FULL, v2, gbase);
-          const double a3 = __shfl_sync(T1_FULL, v2, gbase + 4);
-          if ((q & 7) == gl) {
-            const int k = q >> 3;
-            double res;
-            I[k] += a2;
-            if ((open >> k & 1) && ecp_ps93_update(t.sm.levJ[2], t.sm.levN[2], cnt2, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res;
-              open &= ~(1u << k);
-            }
-            I[k] += a3;
-            if ((open >> k & 1) && ecp_ps93_update(t.sm.levJ[3], t.sm.levN[3], cnt3, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res;
-              open &= ~(1u << k);
-            }
-          }
-          q++;
-        }
-    } else {
-      cnt += __popc(bal);
-      const bool last = (8 * c + 8 == t.sm.levSlot[v + 1]);
-      /* screened windows leave whole chunks without a single in-window point for all four pairs of the warp
-       * (shells far from the centre only see the fine levels): no products, no shuffles then - only the level
-       * bookkeeping, which the reference also performs when cnt == 0 (src/gc_integrators.c:203-208) */
-      const bool anyWin = __any_sync(T1_FULL, inWin);
-      int q = 0;
-      if (anyWin) {
-#pragma unroll
-        for (int N = 0; N <= LAB; N++)
-#pragma unroll
-          for (int lam = N; lam >= 0; lam -= 2) {
-            const double val = t1_wval<LAB>(pt, Cc, N, lam);
-            const double v1 = val + __shfl_xor_sync(T1_FULL, val, 1);
-            const double v2 = v1 + __shfl_xor_sync(T1_FULL, v1, 2);
-            const double v4 = v2 + __shfl_xor_sync(T1_FULL, v2, 4);
-            if ((q & 7) == gl) {
-              const int k = q >> 3;
-              double res;
-              I[k] += v4;
-              if (last && (open >> k & 1) &&
-                  ecp_ps93_update(t.sm.levJ[v], t.sm.levN[v], cnt, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
-                Qo[N * (LAB + 1) + lam] = res;
-                open &= ~(1u << k);
-              }
-            }
-            q++;
-          }
-      } else if (last) {
-#pragma unroll
-        for (int N = 0; N <= LAB; N++)
-#pragma unroll
-          for (int lam = N; lam >= 0; lam -= 2) {
-            if ((q & 7) == gl) {
-              const int k = q >> 3;
-              double res;
-              if ((open >> k & 1) &&
-                  ecp_ps93_update(t.sm.levJ[v], t.sm.levN[v], cnt, t.tolerance, I[k], &P[k], &Qv[k], &res)) {
-                Qo[N * (LAB + 1) + lam] = res;
-                open &= ~(1u << k);
-              }
-            }
-            q++;
-          }
       }
       if (last) {
         v++;
         cnt = 0;
       }
+      c++;
     }
-    /* group finished when none of its lanes has an open quadrature */
-    const unsigned ob = (__ballot_sync(T1_FULL, open != 0) >> gbase) & 0xffu;
-    if (!ob) active = false;
-  }
-  /* quadratures that never converged on the small grid -> large grid (src/type1.c:149) */
-  unsigned long long m = 0;
+    /* ---- group finished: all its quadratures converged, or the grid is exhausted ---- */
+    const unsigned ob = (__ballot_sync(T1_FULL, have && open != 0) >> gbase) & 0xffu;
+    const bool fin = have && (ob == 0 || c == ECP_SMALL_SLOTS / 8);
+    if (__any_sync(T1_FULL, fin && ob != 0)) {
+      /* quadratures that never converged on the small grid -> large grid (src/type1.c:149) */
+      unsigned long long m = 0;
+      if (fin) {
 #pragma unroll
-  for (int k = 0; k < NQL; k++)
-    if (open >> k & 1) m |= 1ull << (8 * k + gl);
-  m |= __shfl_xor_sync(T1_FULL, m, 1);
-  m |= __shfl_xor_sync(T1_FULL, m, 2);
-  m |= __shfl_xor_sync(T1_FULL, m, 4);
-  if (m && gl == 0) {
-    failMask[pp.pr] = m;
-    failList[atomicAdd(failCount, 1)] = (int)pp.pr;
+        for (int k = 0; k < NQL; k++)
+          if (open >> k & 1) m |= 1ull << (8 * k + gl);
+      }
+      m |= __shfl_xor_sync(T1_FULL, m, 1);
+      m |= __shfl_xor_sync(T1_FULL, m, 2);
+      m |= __shfl_xor_sync(T1_FULL, m, 4);
+      if (fin && m && gl == 0) {
+        failMask[pr] = m;
+        failList[atomicAdd(failCount, 1)] = (int)pr;
+      }
+    }
+    if (fin) {
+      have = false;
+      open = 0;
+    }
   }
 }
 
 /* ---------------------------------------------------------------------------------------------- */
 template <int LAB>
-__global__ void __launch_bounds__(128) k_type1L(DevT t, DevB b, const int *failCount, const int *failList,
+__global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_type1L(DevT t, DevB b, int *workCtr, const int *failCount, const int *failList,
                                                 const unsigned long long *failMask, int *errFlag) {
-  constexpr int NQ = T1_NQ(LAB), NQL = (NQ + 7) / 8;
+  using Cfg = T1Cfg<LAB>;
+  constexpr int NQ = Cfg::NQ, NQL = Cfg::NQL;
+  extern __shared__ __align__(16) double t1_red[];
   const int lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24;
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  bool active = g < *failCount;
-  T1Pair pp;
-  double Cc = 0.0, i1 = 0.0, i2 = 0.0;
+  double *red = t1_red + ((threadIdx.x >> 5) * 4 + (lane >> 3)) * Cfg::GS;
+  const int total = *failCount;
+  const int nChunks = t.largeSlots / 8;
+  bool have = false, drained = false;
+  double z = 0.0, sS = 0.0, zd2 = 0.0, Cc = 0.0, i1 = 0.0, i2 = 0.0;
   int Lc = 0, g0 = 0, g1 = 0;
   double *Qo = b.Q;
-  unsigned open = 0;
-  if (active) {
-    t1_load_pair(t, b, failList[g], pp);
-    const unsigned long long fm = failMask[pp.pr];
-#pragma unroll
-    for (int k = 0; k < NQL; k++)
-      if (fm >> (8 * k + gl) & 1) open |= 1u << k;
-    Cc = pp.ca * pp.cb; /* src/type1.c:151 */
-    const double zp = pp.za + pp.zb;
-    ecp_fm06_map(zp, (pp.za * pp.dAC + pp.zb * pp.dBC) / zp, &i1, &i2);
-    Lc = t.typeL[pp.type];
-    g0 = t.typeGaussOff[pp.type];
-    g1 = t.typeGaussOff[pp.type + 1];
-    Qo = b.Q + pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pp.pr), pp.pr);
-  }
   double I[NQL], P[NQL], Qv[NQL];
+  int qo[NQL];
 #pragma unroll
-  for (int k = 0; k < NQL; k++) I[k] = P[k] = Qv[k] = 0.0;
+  for (int k = 0; k < NQL; k++) {
+    I[k] = P[k] = Qv[k] = 0.0;
+    const int q = (8 * k + gl < NQ) ? 8 * k + gl : NQ - 1;
+    qo[k] = t1_qN(q) * (LAB + 1) + t1_qLam(q);
+  }
+  unsigned open = 0;
+  int c = 0;
   int lev = 3, n = 7; /* level accumulated by chunks >= 1: slots [2^lev, 2^(lev+1)); n = points before it */
-  const int nChunks = t.largeSlots / 8;
-  for (int c = 0; c < nChunks; c++) {
-    if (!__any_sync(T1_FULL, active)) break;
+  for (;;) {
+    const bool need = !have && !drained;
+    if (__any_sync(T1_FULL, need)) {
+      int g = 0;
+      if (need && gl == 0) g = atomicAdd(workCtr, 1);
+      g = __shfl_sync(T1_FULL, g, gbase);
+      if (need) {
+        if (g < total) {
+          const long long pr = failList[g];
+          const T1Rec rec = b.t1rec[pr];
+          const unsigned long long fm = failMask[pr];
+          z = rec.z;
+          sS = rec.sS;
+          zd2 = rec.zd2;
+          Cc = rec.CcL;
+          i1 = rec.i1;
+          i2 = rec.i2;
+          Lc = t.typeL[rec.type];
+          g0 = t.typeGaussOff[rec.type];
+          g1 = t.typeGaussOff[rec.type + 1];
+          Qo = b.Q + rec.qoff;
+          open = 0;
+#pragma unroll
+          for (int k = 0; k < NQL; k++)
+            if (fm >> (8 * k + gl) & 1) open |= 1u << k;
+          c = 0;
+          lev = 3;
+          n = 7;
+          have = true;
+        } else {
+          drained = true;
+        }
+      }
+    }
+    if (!__any_sync(T1_FULL, have)) break;
     const int slot = 8 * c + gl;
     T1Point<LAB> pt;
     pt.live = false;
     pt.w = 0.0;
-    if (active && slot != 1) {
-      const double r = i1 * t.large_x[slot] + i2;           /* src/gc_integrators.c:326-329 */
-      const double e = (pp.z * r + pp.sS) * r + pp.zd2;     /* src/type1.c:162 */
+    if (have && slot != 1) {
+      const double r = i1 * t.large_x[slot] + i2;   /* src/gc_integrators.c:326-329 */
+      const double e = (z * r + sS) * r + zd2;      /* src/type1.c:162 */
       if (e >= t.lnAcc1) {
         pt.live = true;
         pt.w = t.large_w[slot] * i1;
         pt.u = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, Lc, r);
         pt.ex = exp(e);
-        t1_fill_point<LAB>(t, r, pp.sS * r, pt);
+        t1_fill_point<LAB>(t, r, sS * r, pt);
       }
     }
-    const bool first = (c == 0) || (8 * c == (1 << lev));
-    const bool last = (c == 0) || (8 * c + 8 == (2 << lev));
-    int q = 0;
+    __syncwarp();
+    t1_store_vals<LAB>(pt, Cc, red + gl, std::make_integer_sequence<int, NQ>{});
+    __syncwarp();
+    if (have) {
+      const bool first = (8 * c == (1 << lev));
+      const bool last = (8 * c + 8 == (2 << lev));
 #pragma unroll
-    for (int N = 0; N <= LAB; N++)
-#pragma unroll
-      for (int lam = N; lam >= 0; lam -= 2) {
-        const double val = t1_wval<LAB>(pt, Cc, N, lam);
-        const double v1 = val + __shfl_xor_sync(T1_FULL, val, 1);
-        const double v2 = v1 + __shfl_xor_sync(T1_FULL, v1, 2);
+      for (int k = 0; k < NQL; k++) {
+        const int q = 8 * k + gl;
+        const double *row = red + (q < NQ ? q : NQ - 1) * Cfg::ROW;
+        const double A = row[0] + row[1], B = row[2] + row[3], Cq = row[4] + row[5], D = row[6] + row[7];
+        double *dst = Qo + qo[k];
+        double res;
         if (c == 0) {
           /* slot 0 = centre, slots 2,3 = level 1, slots 4..7 = level 2 */
-          const double c0 = __shfl_sync(T1_FULL, v1, gbase);
-          const double a1 = __shfl_sync(T1_FULL, v1, gbase + 2);
-          const double a2 = __shfl_sync(T1_FULL, v2, gbase + 4);
-          if ((q & 7) == gl) {
-            const int k = q >> 3;
-            double res;
-            I[k] = c0; /* I = w[M] f(M); p = I  (src/gc_integrators.c:49-52) */
-            P[k] = I[k];
-            Qv[k] = 2 * P[k];
-            P[k] = 2 * I[k];
-            I[k] += a1;
-            if ((open >> k & 1) && ecp_psm92_update(3, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res; /* T[l1][l2] += grid->I  (src/type1.c:193) */
-              open &= ~(1u << k);
-            }
-            Qv[k] = 2 * P[k];
-            P[k] = 2 * I[k];
-            I[k] += a2;
-            if ((open >> k & 1) && ecp_psm92_update(7, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res;
-              open &= ~(1u << k);
-            }
+          I[k] = A; /* I = w[M] f(M); p = I  (src/gc_integrators.c:49-52) */
+          P[k] = I[k];
+          Qv[k] = 2 * P[k];
+          P[k] = 2 * I[k];
+          I[k] += B;
+          if ((open >> k & 1) && ecp_psm92_update(3, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
+            *dst = res; /* T[l1][l2] += grid->I  (src/type1.c:193) */
+            open &= ~(1u << k);
+          }
+          Qv[k] = 2 * P[k];
+          P[k] = 2 * I[k];
+          I[k] += (Cq + D);
+          if ((open >> k & 1) && ecp_psm92_update(7, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
+            *dst = res;
+            open &= ~(1u << k);
           }
         } else {
-          const double v4 = v2 + __shfl_xor_sync(T1_FULL, v2, 4);
-          if ((q & 7) == gl) {
-            const int k = q >> 3;
-            double res;
-            if (first) { /* q = 2p; p = 2I  (src/gc_integrators.c:56-57) */
-              Qv[k] = 2 * P[k];
-              P[k] = 2 * I[k];
-            }
-            I[k] += v4;
-            if (last && (open >> k & 1) && ecp_psm92_update(2 * n + 1, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
-              Qo[N * (LAB + 1) + lam] = res;
-              open &= ~(1u << k);
-            }
+          if (first) { /* q = 2p; p = 2I  (src/gc_integrators.c:56-57) */
+            Qv[k] = 2 * P[k];
+            P[k] = 2 * I[k];
+          }
+          I[k] += ((A + B) + (Cq + D));
+          if (last && (open >> k & 1) && ecp_psm92_update(2 * n + 1, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
+            *dst = res;
+            open &= ~(1u << k);
           }
         }
-        q++;
       }
-    if (c > 0 && last) {
-      n = 2 * n + 1;
-      lev++;
+      if (c > 0 && last) {
+        n = 2 * n + 1;
+        lev++;
+      }
+      c++;
     }
-    const unsigned ob = (__ballot_sync(T1_FULL, open != 0) >> gbase) & 0xffu;
-    if (!ob) active = false;
+    const unsigned ob = (__ballot_sync(T1_FULL, have && open != 0) >> gbase) & 0xffu;
+    const bool fin = have && (ob == 0 || c == nChunks);
+    if (fin) {
+      if (ob != 0 && gl == 0) atomicExch(errFlag, 1); /* large grid failed: rc 1 (src/libecp.h:25) */
+      have = false;
+      open = 0;
+    }
   }
-  const unsigned ob = (__ballot_sync(T1_FULL, open != 0) >> gbase) & 0xffu;
-  if (ob && gl == 0) atomicExch(errFlag, 1); /* large grid failed: rc 1 (src/libecp.h:25) */
 }
 
 #endif
