@@ -430,13 +430,22 @@ __global__ void __launch_bounds__(32 * FB_WARPS, 5) k_fallbackT(DevT t, DevB b, 
   }
 }
 
+#include "ecp_fallback.cuh"
+
 /* ---- link: gamma[p][q], one thread per element ---- */
 __device__ __forceinline__ int deg_of_cindex(int p) {
   int l = 0;
   while (ecp_cd(l) <= p) l++;
   return l;
 }
-__global__ void k_link(DevT t, DevB b, long long nElem) {
+/* For one l the admissible (lambda1, lambda2) form a small grid of n1 x n2 <= NMAX x NMAX values (steps of 2).  All
+ * their angular factors sum_m Omega_A Omega_B are accumulated together in registers with m outermost, so that every
+ * Omega element is loaded once per m instead of once per (lambda1, lambda2, m) and the index arithmetic is paid per m,
+ * not per multiply-add (the round-1 kernel issued ~32 instructions per multiply-add).  Each factor is still the sum
+ * over m = 0..2l in that order, multiplied by T and added in the reference's (lambda1, lambda2) order
+ * (src/type2.c:590-617): gamma is bit-identical to the straightforward loop nest. */
+template <int NMAX>
+__global__ void __launch_bounds__(128) k_link(DevT t, DevB b, long long nElem) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nElem) return;
   const int c = find_class(b.clsElem, t.nClasses, w);
@@ -461,16 +470,38 @@ __global__ void k_link(DevT t, DevB b, long long nElem) {
     const int par1 = (alpha + l) % 2, par2 = (beta + l) % 2;
     ll1 = (par1 > ll1) ? par1 : ll1;
     ll2 = (par2 > ll2) ? par2 : ll2;
+    const int n1 = (la + l - ll1) / 2 + 1, n2 = (lb + l - ll2) / 2 + 1; /* lambda1 = ll1 + 2i, lambda2 = ll2 + 2j */
+    double f[NMAX][NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; i++)
+#pragma unroll
+      for (int j = 0; j < NMAX; j++) f[i][j] = 0.0;
+    const double *pa = oA + (size_t)ll1 * incA2 + (size_t)(l * l) * incA1;
+    const double *pb = oB + (size_t)ll2 * incB2 + (size_t)(l * l) * incB1;
+    for (int m = 0; m < 2 * l + 1; m++) {
+      double a[NMAX], bb[NMAX];
+#pragma unroll
+      for (int i = 0; i < NMAX; i++) a[i] = (i < n1) ? pa[(size_t)(2 * i) * incA2] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NMAX; j++) bb[j] = (j < n2) ? pb[(size_t)(2 * j) * incB2] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NMAX; i++)
+#pragma unroll
+        for (int j = 0; j < NMAX; j++)
+          if (i < n1 && j < n2) f[i][j] += a[i] * bb[j];
+      pa += incA1;
+      pb += incB1;
+    }
     double tmp = 0.0;
-    for (int l1 = ll1; l1 <= la + l; l1 += 2)
-      for (int l2 = ll2; l2 <= lb + l; l2 += 2) {
-        const int k = qi[((l * d1 + l1) * d2 + l2) * d3 + alpha + beta];
-        if (k < 0) continue; /* angular factor identically zero */
-        double factor = 0.0;
-        for (int m = 0; m < 2 * l + 1; m++)
-          factor += oA[(size_t)l1 * incA2 + (l * l + m) * incA1] * oB[(size_t)l2 * incB2 + (l * l + m) * incB1];
-        tmp += factor * T[k];
-      }
+    const int16_t *ql = qi + ((l * d1 + ll1) * d2 + ll2) * d3 + alpha + beta;
+#pragma unroll
+    for (int i = 0; i < NMAX; i++)
+#pragma unroll
+      for (int j = 0; j < NMAX; j++)
+        if (i < n1 && j < n2) {
+          const int k = ql[(2 * i * d2 + 2 * j) * d3];
+          if (k >= 0) tmp += f[i][j] * T[k]; /* k < 0: angular factor identically zero */
+        }
     g += tmp;
   }
   b.gamma[w] = g;
@@ -600,6 +631,7 @@ struct EcpDev {
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
   Buf t1list, t1mask, t1count, t1work, t1rec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
+  int fbv1, fbblock, fbocc; /* LIBECP_B200_FB=v1: warp-per-item fallback kernel; _FBBLOCK threads; _FBOCC blocks per SM cap */
   int t1v1, t1block; /* LIBECP_B200_T1=v1 selects the round-1 type-1 kernels; LIBECP_B200_T1BLOCK = 32/64/128 */
 };
 
@@ -651,6 +683,13 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   {
     const char *e = getenv("LIBECP_B200_T1");
     d->t1v1 = e && !strcmp(e, "v1");
+    e = getenv("LIBECP_B200_FB");
+    d->fbv1 = e && !strcmp(e, "v1");
+    e = getenv("LIBECP_B200_FBBLOCK");
+    d->fbblock = e ? atoi(e) : 64;
+    if (d->fbblock != 32 && d->fbblock != 64 && d->fbblock != 128) d->fbblock = 64;
+    e = getenv("LIBECP_B200_FBOCC");
+    d->fbocc = e ? atoi(e) : 0;
     e = getenv("LIBECP_B200_T1BLOCK");
     d->t1block = e ? atoi(e) : 64;
     if (d->t1block != 32 && d->t1block != 64 && d->t1block != 96 && d->t1block != 128) d->t1block = 64;
@@ -1145,11 +1184,42 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   }
   CK(cudaEventRecord(d->ev[2], d->s1));
   if (nWork > 0) {
-    k_fallbackT<<<d->nSM * 6, 32 * FB_WARPS, sm2 * FB_WARPS, d->s1>>>(t, B, maxq2, (int)sm2, fbl);
+    if (d->fbv1) {
+      k_fallbackT<<<d->nSM * 6, 32 * FB_WARPS, sm2 * FB_WARPS, d->s1>>>(t, B, maxq2, (int)sm2, fbl);
+    } else {
+      /* persistent 8-lane groups; Bessel order bound of the instantiation: max(2 maxLBS, maxLBS + maxLECP - 1) */
+      const int km = (2 * d->maxLBS > d->maxLBS + t.maxLECP - 1) ? 2 * d->maxLBS : d->maxLBS + t.maxLECP - 1;
+      const int block = d->fbblock;
+      if (km <= 6) {
+        const size_t smem = fb_smem_bytes<6>(block);
+        static int occ = 0;
+        if (!occ) {
+          cudaFuncSetAttribute(k_fallbackG<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem_bytes<6>(128));
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fallbackG<6>, block, smem);
+          if (occ < 1) occ = 1;
+        }
+        const int per = (d->fbocc > 0 && d->fbocc < occ) ? d->fbocc : occ;
+        k_fallbackG<6><<<d->nSM * per, block, smem, d->s1>>>(t, B);
+      } else {
+        const size_t smem = fb_smem_bytes<10>(block);
+        static int occ = 0;
+        if (!occ) {
+          cudaFuncSetAttribute(k_fallbackG<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem_bytes<10>(128));
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fallbackG<10>, block, smem);
+          if (occ < 1) occ = 1;
+        }
+        const int per = (d->fbocc > 0 && d->fbocc < occ) ? d->fbocc : occ;
+        k_fallbackG<10><<<d->nSM * per, block, smem, d->s1>>>(t, B);
+      }
+    }
     launches++;
   }
   CK(cudaEventRecord(d->ev[3], d->s1));
-  k_link<<<nblk(h->clsElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsElem[nc]);
+  /* admissible lambda values per l: at most (maxLBS + maxLECP - 1) / 2 + 1 */
+  if ((d->maxLBS + t.maxLECP - 1) / 2 + 1 <= 4)
+    k_link<4><<<nblk(h->clsElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsElem[nc]);
+  else
+    k_link<6><<<nblk(h->clsElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsElem[nc]);
   launches++;
   CK(cudaEventRecord(d->ev[4], d->s1));
   CK(cudaStreamWaitEvent(d->s1, d->ev[8], 0));
