@@ -223,38 +223,102 @@ __global__ void __launch_bounds__(ECP_SMALL_SLOTS) k_Ftab(DevT t, DevB b) {
     if (i <= lmaxA) F[i] = acc[i];
 }
 
-/* ---- type-2 fast path: one thread per used quadrature ---- */
-__global__ void k_fastT(DevT t, DevB b, long long nWork) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nWork) return;
+/* ---- type-2 fast path: one thread per used quadrature, two densely packed launches ----
+ * About 7 % of the used quadratures never converge on the small grid and walk their whole window (a few hundred
+ * points) while the typical one stops after 11-31 points; they hold more than half of all evaluated points.  With one
+ * launch the lanes of a warp idle until its longest quadrature is through (16 of 32 lanes active in round 1).
+ * k_fastT runs levels [0, lim) for every used quadrature and appends the unconverged ones - with their (I, p, q) - to a
+ * survivor list (warp-aggregated atomic); k_fastT2 continues exactly those, one per thread, from level lim.
+ * The operations of a quadrature and their order are unchanged. */
+struct FastSurv {
+  EcpPs93State st;
+  long long w;
+};
+struct FastQ { /* operands of one used quadrature */
+  const double *Fa, *Fb, *U;
+  int strA, strB, strU, gs, ge, tri, l;
+};
+__device__ __forceinline__ FastQ fast_load(const DevT &t, const DevB &b, long long w) {
+  FastQ f;
   const int c = find_class(b.clsWork, t.nClasses, w);
   const int nq = t.clsNq[c];
   const long long idx = w - b.clsWork[c];
-  const int tri = b.clsFirst[c] + (int)(idx / nq), k = (int)(idx % nq);
+  f.tri = b.clsFirst[c] + (int)(idx / nq);
+  const int k = (int)(idx % nq);
   const int q = t.qlist[t.clsQOff[c] + k];
-  const int l = q & 15, l1 = (q >> 4) & 15, l2 = (q >> 8) & 15, l3 = (q >> 12) & 15;
-  const int sa = b.trA[tri], sb = b.trB[tri];
+  const int l1 = (q >> 4) & 15, l2 = (q >> 8) & 15, l3 = (q >> 12) & 15;
+  f.l = q & 15;
+  const int sa = b.trA[f.tri], sb = b.trB[f.tri];
   const int type = b.asType[b.ssASlot[sa]];
   const int Lc = t.clsL[c];
-  const int strA = Lc + t.clsLa[c], strB = Lc + t.clsLb[c], strU = t.maxLECP * t.nU;
-  const double *Fa = b.F + (size_t)b.ssFOff[sa] * ECP_SMALL_SLOTS + l1;
-  const double *Fb = b.F + (size_t)b.ssFOff[sb] * ECP_SMALL_SLOTS + l2;
-  const double *U = t.typeUtabT + (size_t)type * ECP_SMALL_SLOTS * strU + l * t.nU + l3;
-  const int gs = max(b.ssStart[sa], b.ssStart[sb]), ge = max(b.ssEnd[sa], b.ssEnd[sb]); /* src/libecp.c:315-316 */
-  double res = 0.0;
-  const int rc = ecp_ps93_fastT(Fa, strA, Fb, strB, U, strU, c_small_w, c_small_oidx, &t.sm, gs, ge, t.tolerance, &res,
-                                (int *)0);
-  const long long o = w; /* = class T base + (triple - first) * nq + k */
-  if (rc) {
-    b.T[o] = 0.0;
-    b.tfail[o] = 1;
+  f.strA = Lc + t.clsLa[c];
+  f.strB = Lc + t.clsLb[c];
+  f.strU = t.maxLECP * t.nU;
+  f.Fa = b.F + (size_t)b.ssFOff[sa] * ECP_SMALL_SLOTS + l1;
+  f.Fb = b.F + (size_t)b.ssFOff[sb] * ECP_SMALL_SLOTS + l2;
+  f.U = t.typeUtabT + (size_t)type * ECP_SMALL_SLOTS * f.strU + f.l * t.nU + l3;
+  f.gs = max(b.ssStart[sa], b.ssStart[sb]); /* src/libecp.c:315-316 */
+  f.ge = max(b.ssEnd[sa], b.ssEnd[sb]);
+  return f;
+}
+__device__ __forceinline__ void fast_store(const DevB &b, long long w, int rc, double res, int tri, int l) {
+  if (rc) { /* failed on the small grid: the (triple, l) item goes to the large-grid fallback */
+    b.T[w] = 0.0;
+    b.tfail[w] = 1;
     atomicAdd(&b.counters[4], 1);
     const int old = atomicOr(&b.tflags[tri], 1 << l);
     if (!(old & (1 << l))) b.items[atomicAdd(&b.counters[0], 1)] = tri * 8 + l;
   } else {
-    b.T[o] = res;
-    b.tfail[o] = 0;
+    b.T[w] = res; /* position = class T base + (triple - first) * nq + k */
+    b.tfail[w] = 0;
   }
+}
+__global__ void __launch_bounds__(128) k_fastT(DevT t, DevB b, long long nWork, int lim, FastSurv *surv, int survCap) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = w < nWork;
+  int rc = 0, tri = 0, l = 0;
+  double res = 0.0;
+  EcpPs93State st;
+  if (valid) {
+    const FastQ f = fast_load(t, b, w);
+    tri = f.tri;
+    l = f.l;
+    rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, c_small_oidx, &t.sm, f.gs, f.ge,
+                               t.tolerance, 0, lim, &st, &res, (int *)0);
+  }
+  /* unconverged after level lim-1: to the survivor list (one atomic per warp) */
+  const bool sv = valid && rc == 2;
+  const unsigned m = __ballot_sync(0xffffffffu, sv);
+  if (m) {
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&b.counters[8], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (sv) {
+      const int pos = base + __popc(m & ((1u << lane) - 1));
+      if (pos < survCap) {
+        surv[pos].st = st;
+        surv[pos].w = w;
+      } else { /* list full: finish here */
+        const FastQ f = fast_load(t, b, w);
+        rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, c_small_oidx, &t.sm, f.gs, f.ge,
+                                   t.tolerance, lim, ECP_SMALL_LEVELS, &st, &res, (int *)0);
+      }
+    }
+  }
+  if (valid && rc != 2) fast_store(b, w, rc, res, tri, l);
+}
+__global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const FastSurv *surv, int survCap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(b.counters[8], survCap);
+  if (i >= n) return;
+  EcpPs93State st = surv[i].st;
+  const long long w = surv[i].w;
+  const FastQ f = fast_load(t, b, w);
+  double res = 0.0;
+  const int rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, c_small_oidx, &t.sm, f.gs,
+                                       f.ge, t.tolerance, lim, ECP_SMALL_LEVELS, &st, &res, (int *)0);
+  fast_store(b, w, rc, res, f.tri, f.l);
 }
 
 /* ---- shared-memory row helpers for the warp-cooperative quadrature kernels ---- */
@@ -438,20 +502,21 @@ __device__ __forceinline__ int deg_of_cindex(int p) {
   while (ecp_cd(l) <= p) l++;
   return l;
 }
-/* For one l the admissible (lambda1, lambda2) form a small grid of n1 x n2 <= NMAX x NMAX values (steps of 2).  All
- * their angular factors sum_m Omega_A Omega_B are accumulated together in registers with m outermost, so that every
- * Omega element is loaded once per m instead of once per (lambda1, lambda2, m) and the index arithmetic is paid per m,
- * not per multiply-add (the round-1 kernel issued ~32 instructions per multiply-add).  Each factor is still the sum
- * over m = 0..2l in that order, multiplied by T and added in the reference's (lambda1, lambda2) order
- * (src/type2.c:590-617): gamma is bit-identical to the straightforward loop nest. */
-template <int NMAX>
-__global__ void __launch_bounds__(128) k_link(DevT t, DevB b, long long nElem) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nElem) return;
-  const int c = find_class(b.clsElem, t.nClasses, w);
-  const int la = t.clsLa[c], lb = t.clsLb[c], L = t.clsL[c];
-  const int cda = ecp_cd(la), cdb = ecp_cd(lb);
-  const long long idx = w - b.clsElem[c];
+/* One launch per (la, lb, L) class, templated on NA = la + 1 and NB = lb + 1: for one l the admissible
+ * lambda1 = ll1, ll1 + 2, ... <= la + l are at most la + 1 values (lambda2: lb + 1).  All their angular factors
+ * sum_m Omega_A Omega_B are accumulated together in registers with m outermost, so that every Omega element is loaded
+ * once per m instead of once per (lambda1, lambda2, m) and the index arithmetic is paid per m, not per multiply-add
+ * (the round-1 kernel issued ~32 instructions per multiply-add).  Each factor is still the sum over m = 0..2l in that
+ * order, multiplied by T and added in the reference's (lambda1, lambda2) order (src/type2.c:590-617): gamma is
+ * bit-identical to the straightforward loop nest. */
+template <int NA, int NB>
+__global__ void __launch_bounds__(128) k_link(DevT t, DevB b, int c) {
+  constexpr int la = NA - 1, lb = NB - 1;
+  constexpr int cda = (la + 1) * (la + 2) * (la + 3) / 6, cdb = (lb + 1) * (lb + 2) * (lb + 3) / 6;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long w = b.clsElem[c] + idx;
+  if (w >= b.clsElem[c + 1]) return;
+  const int L = t.clsL[c];
   const int tri = b.clsFirst[c] + (int)(idx / (cda * cdb));
   const int pq = (int)(idx % (cda * cdb)), p = pq / cdb, q = pq % cdb;
   const int alpha = deg_of_cindex(p), beta = deg_of_cindex(q);
@@ -461,9 +526,9 @@ __global__ void __launch_bounds__(128) k_link(DevT t, DevB b, long long nElem) {
   const int incA1 = ecp_cd(lXa), incA2 = L * L * incA1;
   const int incB1 = ecp_cd(lXb), incB2 = L * L * incB1;
   const double *oA = b.omX + b.asOmOff[asa] + p, *oB = b.omX + b.asOmOff[asb] + q;
-  const double *T = b.T + tri_T_off(t, b, c, tri);
+  const double *T = b.T + b.clsWork[c] + (long long)(tri - b.clsFirst[c]) * t.clsNq[c];
   const int16_t *qi = t.qidx + t.clsQidxOff[c];
-  const int d1 = la + L, d2 = lb + L, d3 = la + lb + 1;
+  const int d2 = lb + L, d3 = la + lb + 1;
   double g = 0.0;
   for (int l = 0; l < L; l++) {
     int ll1 = l - alpha, ll2 = l - beta;
@@ -471,33 +536,32 @@ __global__ void __launch_bounds__(128) k_link(DevT t, DevB b, long long nElem) {
     ll1 = (par1 > ll1) ? par1 : ll1;
     ll2 = (par2 > ll2) ? par2 : ll2;
     const int n1 = (la + l - ll1) / 2 + 1, n2 = (lb + l - ll2) / 2 + 1; /* lambda1 = ll1 + 2i, lambda2 = ll2 + 2j */
-    double f[NMAX][NMAX];
+    double f[NA][NB];
 #pragma unroll
-    for (int i = 0; i < NMAX; i++)
+    for (int i = 0; i < NA; i++)
 #pragma unroll
-      for (int j = 0; j < NMAX; j++) f[i][j] = 0.0;
+      for (int j = 0; j < NB; j++) f[i][j] = 0.0;
     const double *pa = oA + (size_t)ll1 * incA2 + (size_t)(l * l) * incA1;
     const double *pb = oB + (size_t)ll2 * incB2 + (size_t)(l * l) * incB1;
     for (int m = 0; m < 2 * l + 1; m++) {
-      double a[NMAX], bb[NMAX];
+      double a[NA], bb[NB];
 #pragma unroll
-      for (int i = 0; i < NMAX; i++) a[i] = (i < n1) ? pa[(size_t)(2 * i) * incA2] : 0.0;
+      for (int i = 0; i < NA; i++) a[i] = (i < n1) ? pa[(size_t)(2 * i) * incA2] : 0.0;
 #pragma unroll
-      for (int j = 0; j < NMAX; j++) bb[j] = (j < n2) ? pb[(size_t)(2 * j) * incB2] : 0.0;
+      for (int j = 0; j < NB; j++) bb[j] = (j < n2) ? pb[(size_t)(2 * j) * incB2] : 0.0;
 #pragma unroll
-      for (int i = 0; i < NMAX; i++)
+      for (int i = 0; i < NA; i++)
 #pragma unroll
-        for (int j = 0; j < NMAX; j++)
-          if (i < n1 && j < n2) f[i][j] += a[i] * bb[j];
+        for (int j = 0; j < NB; j++) f[i][j] += a[i] * bb[j]; /* rows/columns beyond n1/n2 are never read */
       pa += incA1;
       pb += incB1;
     }
     double tmp = 0.0;
-    const int16_t *ql = qi + ((l * d1 + ll1) * d2 + ll2) * d3 + alpha + beta;
+    const int16_t *ql = qi + ((l * (la + L) + ll1) * d2 + ll2) * d3 + alpha + beta;
 #pragma unroll
-    for (int i = 0; i < NMAX; i++)
+    for (int i = 0; i < NA; i++)
 #pragma unroll
-      for (int j = 0; j < NMAX; j++)
+      for (int j = 0; j < NB; j++)
         if (i < n1 && j < n2) {
           const int k = ql[(2 * i * d2 + 2 * j) * d3];
           if (k >= 0) tmp += f[i][j] * T[k]; /* k < 0: angular factor identically zero */
@@ -506,6 +570,10 @@ __global__ void __launch_bounds__(128) k_link(DevT t, DevB b, long long nElem) {
   }
   b.gamma[w] = g;
 }
+typedef void (*LinkKernel)(DevT, DevB, int);
+#define LINK_ROW(A) {k_link<A, 1>, k_link<A, 2>, k_link<A, 3>, k_link<A, 4>, k_link<A, 5>, k_link<A, 6>}
+static const LinkKernel g_linkKernels[ECP_MAX_LBS + 1][ECP_MAX_LBS + 1] = {LINK_ROW(1), LINK_ROW(2), LINK_ROW(3),
+                                                                           LINK_ROW(4), LINK_ROW(5), LINK_ROW(6)};
 
 #include "ecp_type1.cuh"
 
@@ -629,6 +697,8 @@ struct EcpDev {
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
+  Buf fastSurv;
+  int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
   Buf t1list, t1mask, t1count, t1work, t1rec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
   int fbv1, fbblock, fbocc; /* LIBECP_B200_FB=v1: warp-per-item fallback kernel; _FBBLOCK threads; _FBOCC blocks per SM cap */
@@ -683,6 +753,9 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   {
     const char *e = getenv("LIBECP_B200_T1");
     d->t1v1 = e && !strcmp(e, "v1");
+    e = getenv("LIBECP_B200_FASTLIM");
+    d->fastLim = e ? atoi(e) : 4;
+    if (d->fastLim < 1) d->fastLim = 1;
     e = getenv("LIBECP_B200_FB");
     d->fbv1 = e && !strcmp(e, "v1");
     e = getenv("LIBECP_B200_FBBLOCK");
@@ -814,7 +887,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
                &d->ssFOff, &d->trA, &d->trB, &d->trOut, &d->trPair, &d->prTriple,
                &d->clsPairBase, &d->clsQBase, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
                &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags,
-               &d->items, &d->counters, &d->t1list, &d->t1mask, &d->t1count, &d->t1work, &d->t1rec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits,
+               &d->items, &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count, &d->t1work, &d->t1rec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits,
                &d->fbTotals, &d->fbR};
   for (size_t i = 0; i < sizeof(bs) / sizeof(bs[0]); i++)
     if (bs[i]->p) cudaFreeAsync(bs[i]->p, d->s1);
@@ -1179,8 +1252,19 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   const long long nWork = h->clsWork[nc];
   CK(cudaEventRecord(d->ev[9], d->s1)); /* in serial mode the type-1 kernels above sit on this stream too */
   if (nWork > 0) {
-    k_fastT<<<nblk(nWork, 128), 128, 0, d->s1>>>(t, B, nWork);
+    /* survivors of the first levels: room for a quarter of the quadratures (an overflowing thread finishes in place) */
+    const long long cap64 = nWork / 4 + 1024;
+    const int survCap = cap64 > 0x7fffffff ? 0x7fffffff : (int)cap64;
+    const int lim = (d->fastLim >= ECP_SMALL_LEVELS) ? ECP_SMALL_LEVELS : d->fastLim;
+    int rc_ = ensure(&d->fastSurv, (size_t)survCap * sizeof(FastSurv));
+    if (rc_) return rc_;
+    k_fastT<<<nblk(nWork, 128), 128, 0, d->s1>>>(t, B, nWork, lim, (FastSurv *)d->fastSurv.p, survCap);
     launches++;
+    if (lim < ECP_SMALL_LEVELS) {
+      /* the survivor count lives on the device: the grid covers the list capacity, surplus blocks leave at once */
+      k_fastT2<<<nblk(survCap, 128), 128, 0, d->s1>>>(t, B, lim, (const FastSurv *)d->fastSurv.p, survCap);
+      launches++;
+    }
   }
   CK(cudaEventRecord(d->ev[2], d->s1));
   if (nWork > 0) {
@@ -1215,12 +1299,12 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
     launches++;
   }
   CK(cudaEventRecord(d->ev[3], d->s1));
-  /* admissible lambda values per l: at most (maxLBS + maxLECP - 1) / 2 + 1 */
-  if ((d->maxLBS + t.maxLECP - 1) / 2 + 1 <= 4)
-    k_link<4><<<nblk(h->clsElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsElem[nc]);
-  else
-    k_link<6><<<nblk(h->clsElem[nc], 128), 128, 0, d->s1>>>(t, B, h->clsElem[nc]);
-  launches++;
+  for (int c = 0; c < nc; c++) { /* one launch per class: the (lambda1, lambda2) tile is sized by (la, lb) */
+    const long long ne = h->clsElem[c + 1] - h->clsElem[c];
+    if (ne <= 0) continue;
+    g_linkKernels[d->hClsLa[c]][d->hClsLb[c]]<<<nblk(ne, 128), 128, 0, d->s1>>>(t, B, c);
+    launches++;
+  }
   CK(cudaEventRecord(d->ev[4], d->s1));
   CK(cudaStreamWaitEvent(d->s1, d->ev[8], 0));
   { /* binomial shift in two passes (ecp_shift.cuh); J[type][c1][q] per triple goes through a scratch buffer */

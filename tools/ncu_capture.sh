@@ -14,6 +14,7 @@ for k in "$@"; do
     ncu -i "$rep.ncu-rep" --page raw --csv > "$OUT/$k.raw.csv" 2>/dev/null
     ncu -i "$rep.ncu-rep" --page source --csv > /tmp/src_$k.csv 2>/dev/null
     python tools/ncu_src_top.py /tmp/src_$k.csv 40 > "$OUT/$k.src.txt" 2>&1
+    gzip -c /tmp/src_$k.csv > "$OUT/$k.src.csv.gz"
     rm -f "$rep.ncu-rep" /tmp/src_$k.csv
   else
     echo "no report for $k" > "$OUT/$k.raw.csv"

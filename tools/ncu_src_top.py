@@ -10,7 +10,7 @@ def main(path, n):
     if not rows:
         print("empty")
         return
-    cols = rows[0].keys()
+    cols = [c for c in rows[0].keys() if c]
     samp = next((c for c in cols if "Sampling" in c and "All" in c), None) or next((c for c in cols if "Samples" in c), None)
     src = next((c for c in cols if c.strip() in ("Source", "source")), None)
     inst = next((c for c in cols if "Instructions Executed" in c), None)
