@@ -19,6 +19,9 @@ void libecp_b200_set_device(int device);
 /* Host threads used by the batch builder and the host-side accumulation (OpenMP); launchers like torchrun
  * export OMP_NUM_THREADS=1, so a multi-GPU caller hands every rank its share of the cores explicitly. */
 void libecp_b200_set_host_threads(int n);
+/* libECP_free parks the device scratch / result buffers of a handle for the next handle created on that device (a
+ * caller of getIntegrals creates one handle per call); this returns them to the driver. */
+void libecp_b200_release_cache(void);
 
 /* Restrict a handle to the shell pairs owned by `rank` of `world` (disjoint output blocks per rank,
  * no data-path collective).  Replaces nothing in the reference (single-threaded loop

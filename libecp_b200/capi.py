@@ -24,7 +24,7 @@ EXPORTS = [
     "libecp_b200_integrals_device", "libecp_b200_integrals_host", "libecp_b200_get_stats", "libecp_b200_screening",
     "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
     "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
-    "libecp_b200_set_serial_kernels",
+    "libecp_b200_set_serial_kernels", "libecp_b200_release_cache",
 ]
 
 

@@ -6,6 +6,7 @@
  *   getIntegrals           src/getIntegrals.c:45-95
  *   cartesianShellOrder[Index]  src/dimensions.c:17-57
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,7 +24,8 @@
 struct _libECPHandle {
   EcpTables *tab;
   EcpDev *dev;
-  EcpBatchBuf *bb;
+  struct BuildWorker *worker;
+  EcpBatchBuf *bb, *bb2; /* two batch buffers: batch i+1 is built on a host thread while the GPU works on batch i */
   const double *geometry;
   int nrAtoms, empty;
   int rank, world;
@@ -33,6 +35,9 @@ struct _libECPHandle {
   libecp_b200_stats_t stats;
 };
 
+struct BuildWorker;
+static void worker_free(struct BuildWorker *w);
+static int g_host_threads = 0;
 static int g_device = -1;
 static int g_tables_only = 0;
 static char g_apierr[256] = "";
@@ -47,6 +52,7 @@ void libecp_b200_set_device(int device) { g_device = device; }
 /* host threads of the batch builder and of the host-side += (OpenMP).  Launchers such as torchrun export
  * OMP_NUM_THREADS=1; a multi-GPU caller gives each rank its share of the cores explicitly. */
 void libecp_b200_set_host_threads(int n) {
+  g_host_threads = n;
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);
 #else
@@ -92,6 +98,7 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
   }
   if (g_tables_only) { /* test hook: tables + builder without a device; every compute entry point fails */
     h->bb = ecp_batch_new(h->tab);
+    h->bb2 = ecp_batch_new(h->tab);
     return h;
   }
   int dev = g_device;
@@ -107,27 +114,33 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
     return NULL;
   }
   h->bb = ecp_batch_new(h->tab);
+  h->bb2 = ecp_batch_new(h->tab);
   return h;
 }
 
 void libECP_free(libECPHandle *h) {
   if (!h) return;
+  worker_free(h->worker);
   if (h->dev) ecpdev_destroy(h->dev);
   if (h->bb) ecp_batch_free(h->bb);
+  if (h->bb2) ecp_batch_free(h->bb2);
   if (h->tab) ecp_tables_free(h->tab);
   free(h->hostBlocks);
   free(h);
 }
+
+/* device scratch and result buffers of freed handles are parked for the next handle (ecp_cuda.cu); give them back */
+void libecp_b200_release_cache(void) { ecpdev_release_cache(); }
 
 void libecp_b200_set_shard(libECPHandle *h, int rank, int world) {
   h->rank = rank;
   h->world = world < 1 ? 1 : world;
 }
 
-static void add_stats(libECPHandle *h, const EcpDevStats *st, double msBuild) {
+static void add_stats(libECPHandle *h, const EcpBatchBuf *bb, const EcpDevStats *st, double msBuild) {
   libecp_b200_stats_t *s = &h->stats;
-  const EcpBatch *b = &h->bb->b;
-  s->nominal_triples += h->bb->nominal;
+  const EcpBatch *b = &bb->b;
+  s->nominal_triples += bb->nominal;
   s->executed_triples += b->nTriples;
   s->shell_slots += b->nSSlots;
   s->atom_slots += b->nASlots;
@@ -153,6 +166,82 @@ static void add_stats(libECPHandle *h, const EcpDevStats *st, double msBuild) {
   s->ms_device_total += st->ms_total;
 }
 
+/* the batch builder as a pipeline stage: batch i+1 is built on a helper host thread (OpenMP team inside) while the
+ * calling thread drives the GPU through batch i.  The helper lives as long as the handle (its OpenMP team is reused). */
+typedef struct {
+  libECPHandle *h;
+  EcpBatchBuf *bb;
+  int *centre;
+  int keepCanon, took;
+  double ms;
+} BuildJob;
+static void build_job(BuildJob *j) {
+  const double t0 = now_ms();
+  if (j->h->dev) ecpdev_bind_thread(j->h->dev);
+  j->took = ecp_batch_build(j->h->tab, j->h->geometry, j->centre, j->h->maxTriples, j->h->rank, j->h->world, j->keepCanon,
+                            j->bb);
+  j->ms = now_ms() - t0;
+}
+struct BuildWorker {
+  pthread_t th;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  BuildJob *job; /* posted job, NULL when idle */
+  int done, quit, started;
+};
+static void *worker_main(void *p) {
+  struct BuildWorker *w = p;
+#ifdef _OPENMP
+  if (g_host_threads > 0) omp_set_num_threads(g_host_threads); /* the ICV is per host thread */
+#endif
+  pthread_mutex_lock(&w->mu);
+  for (;;) {
+    while (!w->job && !w->quit) pthread_cond_wait(&w->cv, &w->mu);
+    if (w->quit) break;
+    BuildJob *j = w->job;
+    pthread_mutex_unlock(&w->mu);
+    build_job(j);
+    pthread_mutex_lock(&w->mu);
+    w->job = NULL;
+    w->done = 1;
+    pthread_cond_broadcast(&w->cv);
+  }
+  pthread_mutex_unlock(&w->mu);
+  return NULL;
+}
+static struct BuildWorker *worker_new(void) {
+  struct BuildWorker *w = calloc(1, sizeof(*w));
+  pthread_mutex_init(&w->mu, NULL);
+  pthread_cond_init(&w->cv, NULL);
+  w->started = pthread_create(&w->th, NULL, worker_main, w) == 0;
+  return w;
+}
+static void worker_free(struct BuildWorker *w) {
+  if (!w) return;
+  if (w->started) {
+    pthread_mutex_lock(&w->mu);
+    w->quit = 1;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
+    pthread_join(w->th, NULL);
+  }
+  pthread_mutex_destroy(&w->mu);
+  pthread_cond_destroy(&w->cv);
+  free(w);
+}
+static void worker_post(struct BuildWorker *w, BuildJob *j) {
+  pthread_mutex_lock(&w->mu);
+  w->done = 0;
+  w->job = j;
+  pthread_cond_broadcast(&w->cv);
+  pthread_mutex_unlock(&w->mu);
+}
+static void worker_wait(struct BuildWorker *w) {
+  pthread_mutex_lock(&w->mu);
+  while (!w->done) pthread_cond_wait(&w->cv, &w->mu);
+  pthread_mutex_unlock(&w->mu);
+}
+
 /* drive all batches; flags as ecpdev_run_batch; cb may be NULL */
 static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
   int result = 0, centre = 0;
@@ -162,12 +251,20 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     fprintf(stderr, "libecp_b200: handle has no device context (tables-only); there is no CPU compute path\n");
     return -1;
   }
-  for (;;) {
+  EcpBatchBuf *bufs[2] = {h->bb, h->bb2};
+  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, 0.0};
+  build_job(&job); /* first batch: nothing to overlap with */
+  if (getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] first batch built in %.1f ms\n", job.ms);
+  if (!h->worker) h->worker = worker_new();
+  const int threaded = h->worker->started && !getenv("LIBECP_B200_NO_PIPELINE");
+  for (int i = 0; job.took > 0; i++) {
+    EcpBatchBuf *cur = bufs[i & 1];
+    const double msBuild = job.ms;
     const double t0 = now_ms();
-    const int took = ecp_batch_build(h->tab, h->geometry, &centre, h->maxTriples, h->rank, h->world, cb != NULL, h->bb);
-    const double msBuild = now_ms() - t0;
-    if (took == 0) break;
-    const EcpBatch *b = &h->bb->b;
+    /* next batch on the helper thread (it advances the centre cursor; nobody else reads it meanwhile) */
+    job.bb = bufs[(i + 1) & 1];
+    if (threaded) worker_post(h->worker, &job);
+    const EcpBatch *b = &cur->b;
     if ((flags & 2) && (size_t)b->outTotal > h->hostBlocksCap) {
       free(h->hostBlocks);
       h->hostBlocksCap = (size_t)b->outTotal * 5 / 4 + 1024;
@@ -175,21 +272,25 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     }
     EcpDevStats st;
     const int rc = ecpdev_run_batch(h->dev, b, flags, (flags & 2) ? h->hostBlocks : NULL, &st);
+    if (threaded)
+      worker_wait(h->worker);
+    else
+      build_job(&job);
     if (rc) {
       fprintf(stderr, "libecp_b200: device failure: %s\n", ecpdev_last_error());
       return -rc;
     }
-    add_stats(h, &st, msBuild);
+    add_stats(h, cur, &st, msBuild);
     if (getenv("LIBECP_B200_TRACE"))
-      fprintf(stderr, "[libecp_b200] rank %d batch: %d triples build %.1f ms run_batch wall %.1f ms device %.1f ms\n", h->rank,
-              b->nTriples, msBuild, now_ms() - t0 - msBuild, st.ms_total);
+      fprintf(stderr, "[libecp_b200] rank %d batch: %d triples build %.1f ms (overlapped) run_batch+join wall %.1f ms device %.1f ms\n",
+              h->rank, b->nTriples, msBuild, now_ms() - t0, st.ms_total);
     if (st.err1 && result == 0) result = 1; /* src/libecp.h:23-27 */
     if (st.err2 && result == 0) result = 2;
     if (result) break;
     if (cb) { /* replay in the reference's loop order, type 1 then type 2 (src/libecp.c:332-373) */
       typedef void (*CallSite)(int, int, int, int, int, int, int, int, int, double *, void *);
       CallSite call = (CallSite)cb;
-      const EcpBatchBuf *bb = h->bb;
+      const EcpBatchBuf *bb = cur;
       for (int k = 0; k < bb->nCanon; k++) {
         const int nb = IJK_DIM(bb->cnLa[k]) * IJK_DIM(bb->cnLb[k]);
         double *blk = h->hostBlocks + bb->cnOut[k];

@@ -63,8 +63,8 @@ void ecp_batch_free(EcpBatchBuf *bb) {
   if (!bb) return;
   free(bb->asAtom); free(bb->asCentre); free(bb->asType); free(bb->asR); free(bb->asOmOff);
   free(bb->ssShell); free(bb->ssASlot); free(bb->ssStart); free(bb->ssEnd); free(bb->ssFOff);
-  free(bb->trA); free(bb->trB); free(bb->trOut); free(bb->trPair);
-  free(bb->prTriple);
+  ecpdev_pinned_free(bb->trA); ecpdev_pinned_free(bb->trB); ecpdev_pinned_free(bb->trOut); ecpdev_pinned_free(bb->trPair);
+  ecpdev_pinned_free(bb->prTriple);
   free(bb->clsFirst); free(bb->clsWork); free(bb->clsElem); free(bb->clsOutElem); free(bb->clsPairBase); free(bb->clsQBase);
   free(bb->cnA); free(bb->cnS1); free(bb->cnB); free(bb->cnS2); free(bb->cnC); free(bb->cnLa); free(bb->cnLb);
   free(bb->cnOut);
@@ -204,6 +204,15 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
       (ptr) = (type *)realloc((ptr), (size_t)((need) + 16) * sizeof(type)); \
   } while (0)
 
+/* arrays that are uploaded every batch live in page-locked memory (contents need not survive a regrow) */
+#define ENSURE_PIN(ptr, cap, need, type)                                                        \
+  do {                                                                                          \
+    if ((long long)(need) > (long long)(cap)) {                                                 \
+      ecpdev_pinned_free(ptr);                                                                  \
+      (ptr) = (type *)ecpdev_pinned_alloc((size_t)((need) + (need) / 4 + 16) * sizeof(type));   \
+    }                                                                                           \
+  } while (0)
+
 int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
                     int keepCanon, EcpBatchBuf *bb) {
   const EcpHostTables *v = &t->v;
@@ -297,11 +306,11 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   ENSURE(bb->ssStart, bb->capSS, nSS, int); ENSURE(bb->ssEnd, bb->capSS, nSS, int);
   ENSURE(bb->ssFOff, bb->capSS, nSS, int64_t);
   if (nSS > bb->capSS) bb->capSS = (int)nSS + 16;
-  ENSURE(bb->trA, bb->capTR, nTR, int); ENSURE(bb->trB, bb->capTR, nTR, int);
-  ENSURE(bb->trOut, bb->capTR, nTR, int64_t); ENSURE(bb->trPair, bb->capTR, nTR, int64_t);
-  if (nTR > bb->capTR) bb->capTR = (int)nTR + 16;
-  ENSURE(bb->prTriple, bb->capPR, nPairs, int);
-  if (nPairs > bb->capPR) bb->capPR = (int)nPairs + 16;
+  ENSURE_PIN(bb->trA, bb->capTR, nTR, int); ENSURE_PIN(bb->trB, bb->capTR, nTR, int);
+  ENSURE_PIN(bb->trOut, bb->capTR, nTR, int64_t); ENSURE_PIN(bb->trPair, bb->capTR, nTR, int64_t);
+  if (nTR > bb->capTR) bb->capTR = (int)(nTR + nTR / 4) + 16;
+  ENSURE_PIN(bb->prTriple, bb->capPR, nPairs, int);
+  if (nPairs > bb->capPR) bb->capPR = (int)(nPairs + nPairs / 4) + 16;
   if (keepCanon) {
     ENSURE(bb->cnA, bb->capCanon, nTR, int); ENSURE(bb->cnS1, bb->capCanon, nTR, int);
     ENSURE(bb->cnB, bb->capCanon, nTR, int); ENSURE(bb->cnS2, bb->capCanon, nTR, int);

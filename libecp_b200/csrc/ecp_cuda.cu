@@ -694,6 +694,7 @@ struct EcpDev {
   Buf prTriple, clsFirst, clsWork, clsElem, clsOutElem, clsPairBase, clsQBase;
   Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
   double *matrix;
+  size_t matrixBytes;
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
@@ -731,7 +732,69 @@ static const T *upload_const(EcpDev *d, const T *h, size_t n) {
   return (const T *)bf->p;
 }
 
+/* Page-locked host memory for the batch arrays the builder fills (H2D straight from the builder's output at PCIe
+ * speed instead of through the driver's pageable staging).  Pinning is expensive (~0.3 ms per MB), so blocks are kept
+ * in a small process-wide cache and handed out again to later batches / handles.  Without a usable device (CPU test
+ * tier: tables-only handles) the blocks are plain malloc memory. */
+#include <mutex>
+struct PinBlock {
+  void *p;
+  size_t cap;
+  int inUse, pinned;
+};
+static PinBlock g_pin[128];
+static std::mutex g_pinMu;
+extern "C" void *ecpdev_pinned_alloc(size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pinMu);
+  int best = -1;
+  for (int i = 0; i < 128; i++)
+    if (g_pin[i].p && !g_pin[i].inUse && g_pin[i].cap >= bytes && g_pin[i].cap <= 2 * bytes + (1 << 20) &&
+        (best < 0 || g_pin[i].cap < g_pin[best].cap))
+      best = i;
+  if (best >= 0) {
+    g_pin[best].inUse = 1;
+    return g_pin[best].p;
+  }
+  int slot = -1;
+  for (int i = 0; i < 128 && slot < 0; i++)
+    if (!g_pin[i].p) slot = i;
+  if (slot < 0) /* cache full: evict an idle block */
+    for (int i = 0; i < 128 && slot < 0; i++)
+      if (!g_pin[i].inUse) {
+        if (g_pin[i].pinned) cudaFreeHost(g_pin[i].p); else free(g_pin[i].p);
+        g_pin[i].p = NULL;
+        slot = i;
+      }
+  void *p = NULL;
+  int pinned = 0;
+  if (bytes >= (64 << 10) && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
+    pinned = 1;
+  } else {
+    cudaGetLastError(); /* no device / out of lockable memory: pageable memory works too */
+    p = malloc(bytes ? bytes : 1);
+  }
+  if (slot >= 0) {
+    g_pin[slot].p = p;
+    g_pin[slot].cap = bytes;
+    g_pin[slot].inUse = 1;
+    g_pin[slot].pinned = pinned;
+  }
+  return p; /* (a block that found no registry slot is pageable-or-pinned but untracked: freed as malloc'd below) */
+}
+extern "C" void ecpdev_pinned_free(void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pinMu);
+  for (int i = 0; i < 128; i++)
+    if (g_pin[i].p == p) {
+      g_pin[i].inUse = 0; /* stays cached */
+      return;
+    }
+  free(p);
+}
+
 extern "C" const char *ecpdev_last_error(void) { return g_err; }
+
+static void adopt_cached(EcpDev *d);
 
 extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   int ndev = 0;
@@ -864,6 +927,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   d->maxQPerL = h->maxQPerL;
   d->nAO = h->nAO;
   d->maxLBS = h->maxLBS;
+  adopt_cached(d);
   for (int i = 0; i < d->ntab; i++)
     if (!d->tab[i].p) {
       snprintf(g_err, sizeof(g_err), "libecp_b200: table upload %d failed: %s", i, cudaGetErrorString(cudaGetLastError()));
@@ -877,22 +941,87 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   return d;
 }
 
+/* scratch buffers (and the result matrix) of a destroyed handle are parked per device and adopted by the next handle
+ * created there: a caller that goes through getIntegrals() creates a handle per call, and growing gigabytes of
+ * scratch from the driver costs tens to hundreds of milliseconds each time.  libecp_b200_release_cache() frees them. */
+#define ECP_NBUF 48
+#define ECP_MAXDEV 16
+struct DevCache {
+  int valid;
+  Buf bufs[ECP_NBUF];
+  double *matrix;
+  size_t matrixBytes;
+};
+static DevCache g_devCache[ECP_MAXDEV];
+static std::mutex g_devCacheMu;
+static int collect_bufs(EcpDev *d, Buf **bs) {
+  Buf *list[] = {&d->asAtom, &d->asType, &d->asR, &d->asOmOff, &d->ssShell, &d->ssASlot, &d->ssStart, &d->ssEnd,
+                 &d->ssFOff, &d->trA, &d->trB, &d->trOut, &d->trPair, &d->prTriple, &d->clsPairBase, &d->clsQBase,
+                 &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX, &d->omX, &d->F, &d->T,
+                 &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags, &d->items,
+                 &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count, &d->t1work, &d->t1rec, &d->clsJ,
+                 &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR};
+  const int n = (int)(sizeof(list) / sizeof(list[0]));
+  static_assert(sizeof(list) / sizeof(list[0]) <= ECP_NBUF, "ECP_NBUF too small");
+  for (int i = 0; i < n; i++) bs[i] = list[i];
+  return n;
+}
+static void adopt_cached(EcpDev *d) {
+  if (d->device < 0 || d->device >= ECP_MAXDEV) return;
+  std::lock_guard<std::mutex> lk(g_devCacheMu);
+  DevCache &c = g_devCache[d->device];
+  if (!c.valid) return;
+  Buf *bs[ECP_NBUF];
+  const int n = collect_bufs(d, bs);
+  for (int i = 0; i < n; i++) *bs[i] = c.bufs[i];
+  const size_t bytes = (size_t)d->nAO * d->nAO * sizeof(double);
+  if (c.matrix && c.matrixBytes >= bytes && c.matrixBytes <= 2 * bytes + (1 << 20)) {
+    d->matrix = c.matrix;
+    d->matrixBytes = c.matrixBytes;
+  } else if (c.matrix) {
+    cudaFreeAsync(c.matrix, d->s1);
+  }
+  memset(&c, 0, sizeof(c));
+}
+extern "C" void ecpdev_release_cache(void) {
+  std::lock_guard<std::mutex> lk(g_devCacheMu);
+  for (int dev = 0; dev < ECP_MAXDEV; dev++) {
+    DevCache &c = g_devCache[dev];
+    if (!c.valid) continue;
+    cudaSetDevice(dev);
+    for (int i = 0; i < ECP_NBUF; i++)
+      if (c.bufs[i].p) cudaFree(c.bufs[i].p);
+    if (c.matrix) cudaFree(c.matrix);
+    memset(&c, 0, sizeof(c));
+  }
+}
+
 extern "C" void ecpdev_destroy(EcpDev *d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < d->ntab; i++)
     if (d->tab[i].p) cudaFreeAsync(d->tab[i].p, d->s1);
-  Buf *bs[] = {&d->asAtom, &d->asType, &d->asR, &d->asOmOff, &d->ssShell, &d->ssASlot, &d->ssStart, &d->ssEnd,
-               &d->ssFOff, &d->trA, &d->trB, &d->trOut, &d->trPair, &d->prTriple,
-               &d->clsPairBase, &d->clsQBase, &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX,
-               &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags,
-               &d->items, &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count, &d->t1work, &d->t1rec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits,
-               &d->fbTotals, &d->fbR};
-  for (size_t i = 0; i < sizeof(bs) / sizeof(bs[0]); i++)
-    if (bs[i]->p) cudaFreeAsync(bs[i]->p, d->s1);
-  cudaStreamSynchronize(d->s1);
-  if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
+  Buf *bs[ECP_NBUF];
+  const int n = collect_bufs(d, bs);
+  bool parked = false;
+  if (d->device >= 0 && d->device < ECP_MAXDEV) {
+    std::lock_guard<std::mutex> lk(g_devCacheMu);
+    DevCache &c = g_devCache[d->device];
+    if (!c.valid) {
+      for (int i = 0; i < n; i++) c.bufs[i] = *bs[i];
+      c.matrix = d->matrix;
+      c.matrixBytes = d->matrixBytes;
+      c.valid = 1;
+      parked = true;
+    }
+  }
+  if (!parked) {
+    for (int i = 0; i < n; i++)
+      if (bs[i]->p) cudaFreeAsync(bs[i]->p, d->s1);
+    cudaStreamSynchronize(d->s1);
+    if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
+  }
   cudaStreamSynchronize(d->s1);
   for (int i = 0; i < 12; i++) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->s1);
@@ -903,7 +1032,10 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
 extern "C" int ecpdev_matrix_begin(EcpDev *d) {
   CK(cudaSetDevice(d->device));
   const size_t bytes = (size_t)d->nAO * d->nAO * sizeof(double);
-  if (!d->matrix) CK(cudaMallocAsync((void **)&d->matrix, bytes ? bytes : 8, d->s1));
+  if (!d->matrix) {
+    CK(cudaMallocAsync((void **)&d->matrix, bytes ? bytes : 8, d->s1));
+    d->matrixBytes = bytes ? bytes : 8;
+  }
   CK(cudaMemsetAsync(d->matrix, 0, bytes, d->s1));
   return 0;
 }
@@ -1042,6 +1174,10 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   return 0;
 }
 extern "C" void *ecpdev_matrix_ptr(EcpDev *d) { return d->matrix; }
+/* make the handle's device current on the calling host thread (the builder thread allocates page-locked memory) */
+extern "C" void ecpdev_bind_thread(EcpDev *d) {
+  if (d) cudaSetDevice(d->device);
+}
 /* serial = 1: type-1 kernels share the type-2 stream, so the per-kernel event times are not inflated by overlap */
 extern "C" void ecpdev_set_serial(EcpDev *d, int on) { d->serial = on; }
 extern "C" long long ecpdev_table_bytes(EcpDev *d) { return d->tableBytes; }
@@ -1135,6 +1271,8 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   if (st) memset(st, 0, sizeof(*st));
   d->batchH2D = 0;
   if (h->nTriples == 0) return 0;
+  const bool trace = getenv("LIBECP_B200_TRACE") != NULL;
+  const double tr0 = omp_get_wtime();
   UP(asAtom, asAtom, h->asAtom, h->nASlots, int);
   UP(asType, asType, h->asType, h->nASlots, int);
   UP(asR, asR, h->asR, (size_t)h->nASlots * 4, double);
@@ -1206,6 +1344,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   const size_t sm2 = warp_smem_bytes(maxq2, fbl.stride);
   cudaFuncSetAttribute(k_fallbackT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm2 * FB_WARPS));
   long long launches = 0;
+  const double tr1 = omp_get_wtime();
   CK(cudaEventRecord(d->ev[0], d->s1));
   /* per-centre tables */
   k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
@@ -1332,8 +1471,12 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   CK(cudaMemcpyAsync(hc1, d->t1count.p, sizeof(hc1), cudaMemcpyDeviceToHost, d->s1));
   if ((flags & 2) && hostBlocks)
     CK(cudaMemcpyAsync(hostBlocks, B.blocks, (size_t)h->outTotal * sizeof(double), cudaMemcpyDeviceToHost, d->s1));
+  const double tr2 = omp_get_wtime();
   CK(cudaStreamSynchronize(d->s1));
   CK(cudaStreamSynchronize(d->s2));
+  if (trace)
+    fprintf(stderr, "[libecp_b200]   run_batch: alloc+H2D issue %.2f ms, launches %.2f ms, wait %.2f ms\n", 1e3 * (tr1 - tr0),
+            1e3 * (tr2 - tr1), 1e3 * (omp_get_wtime() - tr2));
   if (st) {
     float ms;
     cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); st->ms_tables = ms;

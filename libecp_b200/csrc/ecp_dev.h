@@ -11,6 +11,7 @@
 #ifndef ECP_DEV_H
 #define ECP_DEV_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -119,6 +120,9 @@ typedef struct {
 
 typedef struct EcpDev EcpDev;
 
+/* page-locked (cached, process-wide) host blocks for the builder's batch arrays; plain memory without a device */
+void *ecpdev_pinned_alloc(size_t bytes);
+void ecpdev_pinned_free(void *p);
 /* all return 0 on success, else a cudaError_t value (message via ecpdev_last_error) */
 EcpDev *ecpdev_create(const EcpHostTables *t, int device);
 void ecpdev_destroy(EcpDev *d);
@@ -129,6 +133,8 @@ int ecpdev_matrix_download(EcpDev *d, double *host /* nAO*nAO */);
 int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned /* [nAO] or NULL */,
                               long long *bytes);
 void *ecpdev_matrix_ptr(EcpDev *d);
+void ecpdev_bind_thread(EcpDev *d);
+void ecpdev_release_cache(void);
 /* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks */
 int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, double *hostBlocks, EcpDevStats *stats);
 int ecpdev_sync(EcpDev *d);
