@@ -702,7 +702,7 @@ struct EcpDev {
   int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
   Buf t1list, t1mask, t1count, t1work, t1rec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
-  int fbv1, fbblock, fbocc; /* LIBECP_B200_FB=v1: warp-per-item fallback kernel; _FBBLOCK threads; _FBOCC blocks per SM cap */
+  int fbv1, fbblock, fbocc, fbminb; /* LIBECP_B200_FB=v1: warp-per-item fallback kernel; _FBBLOCK threads; _FBOCC blocks per SM cap */
   int t1v1, t1block; /* LIBECP_B200_T1=v1 selects the round-1 type-1 kernels; LIBECP_B200_T1BLOCK = 32/64/128 */
 };
 
@@ -824,6 +824,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     e = getenv("LIBECP_B200_FBBLOCK");
     d->fbblock = e ? atoi(e) : 64;
     if (d->fbblock != 32 && d->fbblock != 64 && d->fbblock != 128) d->fbblock = 64;
+    e = getenv("LIBECP_B200_FBMINB");
+    d->fbminb = e ? atoi(e) : 3;
     e = getenv("LIBECP_B200_FBOCC");
     d->fbocc = e ? atoi(e) : 0;
     e = getenv("LIBECP_B200_T1BLOCK");
@@ -1413,27 +1415,26 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
       /* persistent 8-lane groups; Bessel order bound of the instantiation: max(2 maxLBS, maxLBS + maxLECP - 1) */
       const int km = (2 * d->maxLBS > d->maxLBS + t.maxLECP - 1) ? 2 * d->maxLBS : d->maxLBS + t.maxLECP - 1;
       const int block = d->fbblock;
+      void (*kern)(DevT, DevB);
+      size_t smem;
+      int slot;
       if (km <= 6) {
-        const size_t smem = fb_smem_bytes<6>(block);
-        static int occ = 0;
-        if (!occ) {
-          cudaFuncSetAttribute(k_fallbackG<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem_bytes<6>(128));
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fallbackG<6>, block, smem);
-          if (occ < 1) occ = 1;
-        }
-        const int per = (d->fbocc > 0 && d->fbocc < occ) ? d->fbocc : occ;
-        k_fallbackG<6><<<d->nSM * per, block, smem, d->s1>>>(t, B);
+        smem = fb_smem_bytes<6>(block);
+        if (d->fbminb == 4) { kern = k_fallbackG<6, 4>; slot = 0; } else { kern = k_fallbackG<6, 3>; slot = 1; }
       } else {
-        const size_t smem = fb_smem_bytes<10>(block);
-        static int occ = 0;
-        if (!occ) {
-          cudaFuncSetAttribute(k_fallbackG<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem_bytes<10>(128));
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fallbackG<10>, block, smem);
-          if (occ < 1) occ = 1;
-        }
-        const int per = (d->fbocc > 0 && d->fbocc < occ) ? d->fbocc : occ;
-        k_fallbackG<10><<<d->nSM * per, block, smem, d->s1>>>(t, B);
+        smem = fb_smem_bytes<10>(block);
+        kern = k_fallbackG<10, 2>;
+        slot = 2;
       }
+      static int occ[3][5] = {{0}};
+      const int bi = block / 32;
+      if (!occ[slot][bi]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(km <= 6 ? fb_smem_bytes<6>(128) : fb_smem_bytes<10>(128)));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[slot][bi], kern, block, smem);
+        if (occ[slot][bi] < 1) occ[slot][bi] = 1;
+      }
+      const int per = (d->fbocc > 0 && d->fbocc < occ[slot][bi]) ? d->fbocc : occ[slot][bi];
+      kern<<<d->nSM * per, block, smem, d->s1>>>(t, B);
     }
     launches++;
   }

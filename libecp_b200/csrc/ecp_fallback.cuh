@@ -34,8 +34,19 @@ static size_t fb_smem_bytes(int block) {
   return (size_t)(block / 8) * FbCfg<KO>::GROUP * sizeof(double);
 }
 
+/* K_0..K_KO(z) into a shared-memory row; one copy of the Bessel code for both arguments (the kernel is bound by
+ * instruction fetch: keep its footprint small) */
 template <int KO>
-__global__ void __launch_bounds__(128, (KO <= 6 ? 3 : 2)) k_fallbackG(DevT t, DevB b) {
+__device__ __noinline__ void fb_bessel_row(const double *__restrict__ tabT, int stride, const double *__restrict__ Cj,
+                                           int lmax, double z, double *dst) {
+  double K[KO + 1];
+  ecp_bessel<KO>(tabT, stride, Cj, lmax, z, K);
+#pragma unroll
+  for (int i = 0; i <= KO; i++) dst[i] = K[i];
+}
+
+template <int KO, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
   using Cfg = FbCfg<KO>;
   constexpr int RS = Cfg::RS;
   extern __shared__ __align__(16) double fb_smem[];
@@ -91,6 +102,10 @@ __global__ void __launch_bounds__(128, (KO <= 6 ? 3 : 2)) k_fallbackG(DevT t, De
           const int type = b.asType[asa];
           g0 = t.typeGaussOff[type];
           g1 = t.typeGaussOff[type + 1];
+          /* Gaussians of channel l form one run of the type's list (they are stored shell by shell): evaluate only
+           * that run per point (the loop over the others only tests and skips, src/ecp.c:47-57) */
+          while (g0 < g1 && t.gaussL[g0] != l) g0++;
+          while (g1 > g0 && t.gaussL[g1 - 1] != l) g1--;
           Na = t.shellK[sha];
           Nb = t.shellK[shb];
           za = t.primA + t.shellPrim[sha];
@@ -173,13 +188,8 @@ __global__ void __launch_bounds__(128, (KO <= 6 ? 3 : 2)) k_fallbackG(DevT t, De
       if (slot == 0 && r > dAC && r > dBC && e < t.lnAcc2) atomicAdd(&b.counters[6], 1);
       if (live) {
         const double U = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, l, r);
-        double K[KO + 1];
-        ecp_bessel<KO>(t.besselT, t.besselStride, t.besselC, laC, s1 * r, K);
-#pragma unroll
-        for (int i = 0; i <= KO; i++) myrow[(KO + 1) + i] = K[i];
-        ecp_bessel<KO>(t.besselT, t.besselStride, t.besselC, lbC, s2 * r, K);
-#pragma unroll
-        for (int i = 0; i <= KO; i++) myrow[2 * (KO + 1) + i] = K[i];
+        fb_bessel_row<KO>(t.besselT, t.besselStride, t.besselC, laC, s1 * r, myrow + (KO + 1));
+        fb_bessel_row<KO>(t.besselT, t.besselStride, t.besselC, lbC, s2 * r, myrow + 2 * (KO + 1));
         W = t.large_w[slot] * i1;
         CU = Cc * U;
         EX = exp(e);

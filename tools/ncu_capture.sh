@@ -8,7 +8,7 @@ WL=$1; OUT=$2; SKIP=$3; shift 3
 mkdir -p "$OUT"
 for k in "$@"; do
   rep=/tmp/prof_$k
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s "$SKIP" -c 1 -f -o "$rep" \
+  timeout 300 ncu --set full --clock-control none ${NCU_EXTRA:-} --import-source on -k regex:$k -s "$SKIP" -c 1 -f -o "$rep" \
       python bench.py --workload "$WL" --steps 1 --warmup 3 --no-cpu --no-secondary > /dev/null 2>&1
   if [ -f "$rep.ncu-rep" ]; then
     ncu -i "$rep.ncu-rep" --page raw --csv > "$OUT/$k.raw.csv" 2>/dev/null
