@@ -199,8 +199,32 @@ def falg_per_kernel(workload, executed):
 
 KERNEL_OF = {"tables": "ms_tables", "fastT": "ms_fastT", "fallback": "ms_fallback", "link": "ms_link",
              "type1": "ms_type1", "chi": "ms_chi", "shift": "ms_shift"}
-KERNEL_NAME = {"tables": "k_atomslot+k_omegaX+k_Ftab", "fastT": "k_fastT", "fallback": "k_fallbackT", "link": "k_link",
-               "type1": "k_t1prep+k_type1S<LAB>+k_type1L<LAB>", "chi": "k_chi", "shift": "k_shiftJ+k_shiftI"}
+KERNEL_NAME = {"tables": "k_atomslot+k_omegaX+k_Ftab", "fastT": "k_fastT+k_fastT2", "fallback": "k_fallbackG<KO>",
+               "link": "k_link<la+1,lb+1>", "type1": "k_t1prep+k_type1S<LAB>+k_type1L<LAB>", "chi": "k_chi",
+               "shift": "k_shiftJ+k_shiftI"}
+# ncu --set full captures of one launch on Au20 kept under profiles/ (DRAM traffic of the dominant kernel, per launch)
+NCU_FILE = {"fastT": "k_fastT2", "fallback": "k_fallbackG", "link": "k_link", "type1": "k_type1S", "chi": "k_chi",
+            "shift": "k_shiftI", "tables": "k_Ftab"}
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the committed Au20 capture of that kernel (bytes), or None"""
+    import csv
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", f"ncu_full_{NCU_FILE.get(kernel_key, '')}.raw.csv")))[::-1]:
+        try:
+            rows = list(csv.reader(open(path)))
+            names, units, vals = rows[0], rows[1], rows[2]
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = names.index(key)
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1.0)
+                tot += float(vals[i].replace(",", "")) * scale
+            return tot
+        except Exception:
+            continue
+    return None
 
 
 def measured_peaks():
@@ -231,7 +255,10 @@ def roofline(workload, stats, nsteps, peak_tf, serial_stats=None):
     return {
         **extra,
         "bound": "fp64", "kernel": KERNEL_NAME[dom], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+        "frac": ach / peak_tf if peak_tf else None,
+        "traffic": ncu_traffic(dom) if workload == "cfg3" else None,
+        "traffic_note": "DRAM bytes of one launch of the kernel family's main kernel on Au20 from the committed ncu --set full "
+                        "capture (profiles/); null for cfg5, which was not captured under ncu --set full",
         "peak_source": "FP64 FMA probe kernel run by bench.py on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
                        "vendor figure ~37-40 TFLOP/s)",
         "algorithmic_flops_per_step": flops["total"], "algorithmic_flops_kernel": flops[dom], "flops_count": how,

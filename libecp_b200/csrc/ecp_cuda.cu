@@ -8,11 +8,12 @@
  *   k_atomslot   S_lm(r_XC) and (-x)^i(-y)^j(-z)^k per (C, atom)          src/util.c:214-243, spherical_harmonics.c
  *   k_omegaX     Omega_X = sum_mu S_lam,mu Omega per (C, atom)            src/angular_integrals.c:104-142
  *   k_Ftab       contracted radial table F_lambda(r_n) per (C, shell)     src/type2.c:284-303
- *   k_fastT      type-2 fast path, PS93 on Fa*Fb*r^N U_l                  src/type2.c:336-381
- *   k_fallbackT  type-2 large-grid fallback, PSM92 per primitive pair     src/type2.c:417-528
- *   k_link       gamma = sum Omega_A Omega_B T                            src/type2.c:583-623
- *   k_t1prep     P, |P|, S_lm(P^) per primitive pair                      src/type1.c:249-252
- *   k_type1Q     radial Q(N,lambda): PS93 small grid, PSM92 fallback      src/type1.c:94-208
+ *   k_fastT(2)   type-2 fast path, PS93 on Fa*Fb*r^N U_l, two launches    src/type2.c:336-381
+ *   k_fallbackG  type-2 large-grid fallback, PSM92 per primitive pair     src/type2.c:417-528   (ecp_fallback.cuh;
+ *                k_fallbackT is the round-1 warp-per-item version, LIBECP_B200_FB=v1)
+ *   k_link       gamma = sum Omega_A Omega_B T, one launch per class      src/type2.c:583-623
+ *   k_t1prep     P, |P|, S_lm(P^), pair record per primitive pair         src/type1.c:235-252
+ *   k_type1S/L   radial Q(N,lambda): PS93 small grid, PSM92 fallback      src/type1.c:94-208    (ecp_type1.cuh)
  *   k_chi        chi = sum (S.poly2sph) Q                                 src/type1.c:266-295
  *   k_shift      binomial shift to A/B, x4pi / x16pi^2, block + matrix    src/util.c:246-334, getIntegrals.c:22-43
  */
