@@ -9,8 +9,7 @@
  *   k_omegaX     Omega_X = sum_mu S_lam,mu Omega per (C, atom)            src/angular_integrals.c:104-142
  *   k_Ftab       contracted radial table F_lambda(r_n) per (C, shell)     src/type2.c:284-303
  *   k_fastT(2)   type-2 fast path, PS93 on Fa*Fb*r^N U_l, two launches    src/type2.c:336-381
- *   k_fallbackG  type-2 large-grid fallback, PSM92 per primitive pair     src/type2.c:417-528   (ecp_fallback.cuh;
- *                k_fallbackT is the round-1 warp-per-item version, LIBECP_B200_FB=v1)
+ *   k_fallbackG  type-2 large-grid fallback, PSM92 per primitive pair     src/type2.c:417-528   (ecp_fallback.cuh)
  *   k_link       gamma = sum Omega_A Omega_B T, one launch per class      src/type2.c:583-623
  *   k_t1prep     P, |P|, S_lm(P^), pair record per primitive pair         src/type1.c:235-252
  *   k_type1S/L   radial Q(N,lambda): PS93 small grid, PSM92 fallback      src/type1.c:94-208    (ecp_type1.cuh)
@@ -28,26 +27,6 @@
 
 #define KM ECP_KMAX
 
-/* row of one tabulated large-grid point in shared memory (k_fallbackT): w, C*U, exp, r^0..r^kR, Ka[0..kK], Kb[0..kK],
- * kR = 2 maxLBS, kK = maxLBS + maxLECP - 1 of the handle (f/L=4: 24 doubles, h/L=6: 36); the Bessel scratch
- * d[0..kK+5] stays in (L1-cached) local memory so that it does not cost shared memory, i.e. occupancy.
- * The stride is made odd so that the 32 lane rows fall into distinct banks. */
-#define ROW_W 0
-#define ROW_CU 1
-#define ROW_EX 2
-#define ROW_RN 3            /* rn[0..kR]  */
-struct FbLayout {
-  int rowKA, rowKB, stride;
-};
-static FbLayout fb_layout(int maxLBS, int maxLECP) {
-  const int kR = 2 * maxLBS, kK = maxLBS + maxLECP - 1;
-  FbLayout L;
-  L.rowKA = ROW_RN + kR + 1;
-  L.rowKB = L.rowKA + kK + 1;
-  L.stride = (L.rowKB + kK + 1) | 1;
-  return L;
-}
-#define FB_WARPS 4
 
 static char g_err[512] = "";
 #define CK(call)                                                                                   \
@@ -322,179 +301,6 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
   fast_store(b, w, rc, res, f.tri, f.l);
 }
 
-/* ---- shared-memory row helpers for the warp-cooperative quadrature kernels ---- */
-struct WarpSmem {
-  double *rows; /* [32][ROWSTRIDE] */
-  double *sI, *sP, *sQ, *sAcc;
-  int *qk;
-  unsigned char *done;
-};
-__device__ __forceinline__ WarpSmem carve(unsigned char *base, int maxq, int stride) {
-  WarpSmem s;
-  s.rows = (double *)base;
-  s.sI = s.rows + 32 * stride;
-  s.sP = s.sI + maxq;
-  s.sQ = s.sP + maxq;
-  s.sAcc = s.sQ + maxq;
-  s.qk = (int *)(s.sAcc + maxq);
-  s.done = (unsigned char *)(s.qk + maxq);
-  return s;
-}
-static size_t warp_smem_bytes(int maxq, int stride) {
-  return (((size_t)32 * stride * 8 + (size_t)maxq * 8 * 4 + (size_t)maxq * 4 + (size_t)maxq + 16) + 15) & ~(size_t)15;
-}
-
-/* ---- type-2 fallback: one warp per (triple, l) with failed small-grid quadratures ---- */
-__global__ void __launch_bounds__(32 * FB_WARPS, 5) k_fallbackT(DevT t, DevB b, int maxq, int warpBytes, FbLayout fl) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const WarpSmem s = carve(smem_raw + (size_t)(threadIdx.x >> 5) * warpBytes, maxq, fl.stride);
-  const int ROWSTRIDE = fl.stride, ROW_KA = fl.rowKA, ROW_KB = fl.rowKB;
-  const int lane = threadIdx.x & 31;
-  const int nItems = b.counters[0];
-  for (;;) {
-    int it = 0;
-    if (lane == 0) it = atomicAdd(&b.counters[1], 1);
-    it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= nItems) break;
-    const int item = b.items[it];
-    const int tri = item >> 3, l = item & 7;
-    const int c = find_class_i(b.clsFirst, t.nClasses, tri);
-    const int la = t.clsLa[c], lb = t.clsLb[c];
-    const int laC = la + l, lbC = lb + l, lab = la + lb;
-    const int k0 = t.clsQlOff[c * (ECP_MAX_LECP + 1) + l], k1 = t.clsQlOff[c * (ECP_MAX_LECP + 1) + l + 1];
-    const long long tOff = tri_T_off(t, b, c, tri);
-    const int *ql = t.qlist + t.clsQOff[c];
-    /* gather the failed quadratures of this (triple, l) */
-    int nf = 0;
-    for (int base = k0; base < k1; base += 32) {
-      const int k = base + lane;
-      const int f = (k < k1) && b.tfail[tOff + k];
-      const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) s.qk[nf + __popc(m & ((1u << lane) - 1))] = k;
-      nf += __popc(m);
-    }
-    for (int q = lane; q < nf; q += 32) s.sAcc[q] = 0.0;
-    __syncwarp();
-    const int ssa = b.trA[tri], ssb = b.trB[tri];
-    const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
-    const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
-    const double dAC = b.asR[4 * asa + 3], dBC = b.asR[4 * asb + 3];
-    const int type = b.asType[asa];
-    const int g0 = t.typeGaussOff[type], g1 = t.typeGaussOff[type + 1];
-    const int Na = t.shellK[sha], Nb = t.shellK[shb];
-    const double *za = t.primA + t.shellPrim[sha], *ca = t.primD + t.shellPrim[sha];
-    const double *zb = t.primA + t.shellPrim[shb], *cb = t.primD + t.shellPrim[shb];
-    bool failed = false;
-    for (int pa = 0; pa < Na; pa++) {
-      const double s1 = 2.0 * za[pa] * dAC;
-      for (int pb = 0; pb < Nb; pb++) {
-        const double s2 = 2.0 * zb[pb] * dBC;
-        const double Cc = ca[pa] * cb[pb];
-        const double zp = za[pa] + zb[pb];
-        const double P = (za[pa] * dAC + zb[pb] * dBC) / zp;
-        double i1, i2;
-        ecp_fm06_map(zp, P, &i1, &i2);
-        int curChunk = -1;
-        int n = 1;
-        for (int lev = 0; lev <= t.largeLevels; lev++) {
-          /* level 0 = centre point (slot 0); level v>=1 = slots [2^v, 2^(v+1)) */
-          const int sl0 = (lev == 0) ? 0 : (1 << lev), sl1 = (lev == 0) ? 2 : (2 << lev);
-          if (lev > 0) {
-            int alldone = 1;
-            for (int q = lane; q < nf; q += 32) alldone &= s.done[q];
-            if (__all_sync(0xffffffffu, alldone)) break;
-            for (int q = lane; q < nf; q += 32)
-              if (!s.done[q]) { /* q = 2p; p = 2I  (src/gc_integrators.c:56-57) */
-                s.sQ[q] = 2 * s.sP[q];
-                s.sP[q] = 2 * s.sI[q];
-              }
-          }
-          for (int ch = sl0 >> 5; ch <= (sl1 - 1) >> 5; ch++) {
-            if (ch != curChunk) {
-              __syncwarp();
-              /* tabulate 32 slots: r, exponent gate, U_l, K_a, K_b, r^n  (src/type2.c:471-495) */
-              const int slot = ch * 32 + lane;
-              double *row = s.rows + lane * ROWSTRIDE;
-              const double x = t.large_x[slot];
-              const double r = i1 * x + i2;
-              const double d1 = dAC - r, d2 = dBC - r;
-              const double e = -za[pa] * d1 * d1 - zb[pb] * d2 * d2;
-              const bool live = (slot != 1) && (e >= t.lnAcc2);
-              if (slot == 0 && r > dAC && r > dBC && e < t.lnAcc2) atomicAdd(&b.counters[6], 1);
-              if (live) {
-                const double U = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, l, r);
-                /* K_a then K_b through one copy of the Bessel code (instruction-cache footprint) */
-                double dscr[KM + 6];
-#pragma unroll 1
-                for (int ab = 0; ab < 2; ab++)
-                  ecp_bessel_mem(t.besselT, t.besselStride, t.besselC, ab ? lbC : laC, (ab ? s2 : s1) * r,
-                                 row + (ab ? ROW_KB : ROW_KA), dscr);
-                row[ROW_W] = t.large_w[slot] * i1;
-                row[ROW_CU] = Cc * U;
-                row[ROW_EX] = exp(e);
-                double rn = 1.0;
-                for (int i = 0; i <= lab; i++) {
-                  row[ROW_RN + i] = rn;
-                  rn = r * rn;
-                }
-              } else {
-                row[ROW_W] = row[ROW_CU] = row[ROW_EX] = 0.0;
-                for (int i = 0; i <= lab; i++) row[ROW_RN + i] = 0.0;
-                for (int i = 0; i <= laC; i++) row[ROW_KA + i] = 0.0;
-                for (int i = 0; i <= lbC; i++) row[ROW_KB + i] = 0.0;
-              }
-              curChunk = ch;
-              __syncwarp();
-            }
-            const int lo = max(sl0, ch * 32) - ch * 32, hi = min(sl1, ch * 32 + 32) - ch * 32;
-            for (int q = lane; q < nf; q += 32) {
-              if (lev > 0 && s.done[q]) continue;
-              const int qq = ql[s.qk[q]];
-              const int l1 = (qq >> 4) & 15, l2 = (qq >> 8) & 15, l3 = (qq >> 12) & 15;
-              if (lev == 0) {
-                const double *row = s.rows;
-                const double Qv = row[ROW_CU] * row[ROW_RN + l3] * row[ROW_KA + l1] * row[ROW_KB + l2] * row[ROW_EX];
-                const double I0 = row[ROW_W] * Qv;
-                s.sI[q] = I0;
-                s.sP[q] = I0;
-                s.done[q] = 0;
-              } else {
-                double I = s.sI[q];
-                for (int sidx = lo; sidx < hi; sidx += 2) {
-                  const double *rl = s.rows + sidx * ROWSTRIDE, *rr = rl + ROWSTRIDE;
-                  double T = 0.0;
-                  T += rl[ROW_W] * (rl[ROW_CU] * rl[ROW_RN + l3] * rl[ROW_KA + l1] * rl[ROW_KB + l2] * rl[ROW_EX]);
-                  T += rr[ROW_W] * (rr[ROW_CU] * rr[ROW_RN + l3] * rr[ROW_KA + l1] * rr[ROW_KB + l2] * rr[ROW_EX]);
-                  I += T;
-                }
-                s.sI[q] = I;
-              }
-            }
-          }
-          if (lev > 0) {
-            n = 2 * n + 1;
-            for (int q = lane; q < nf; q += 32) {
-              if (s.done[q]) continue;
-              double res;
-              if (ecp_psm92_update(n, 1, t.tolerance, s.sI[q], s.sP[q], s.sQ[q], &res)) {
-                s.sAcc[q] += res; /* T += grid->I, primitive pairs in reference order (src/type2.c:513) */
-                s.done[q] = 1;
-              }
-            }
-          }
-        }
-        int alldone = 1;
-        for (int q = lane; q < nf; q += 32) alldone &= s.done[q];
-        if (!__all_sync(0xffffffffu, alldone)) failed = true;
-        __syncwarp();
-      }
-    }
-    for (int q = lane; q < nf; q += 32) b.T[tOff + s.qk[q]] = s.sAcc[q];
-    if (failed && lane == 0) atomicExch(&b.counters[3], 2);
-    __syncwarp();
-  }
-}
-
 #include "ecp_fallback.cuh"
 
 /* ---- link: gamma[p][q], one thread per element ---- */
@@ -617,8 +423,6 @@ __global__ void k_t1prep(DevT t, DevB b) {
   b.t1rec[pr] = rec;
 }
 
-#include "ecp_type1_v1.cuh"
-
 /* ---- chi[i][j], one thread per element ---- */
 __global__ void k_chi(DevT t, DevB b, long long nElem) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,10 +505,11 @@ struct EcpDev {
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
   Buf fastSurv;
   int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
+  long long survCapEnv; /* LIBECP_B200_SURVCAP: survivor-list capacity override (tests of the overflow path) */
   Buf t1list, t1mask, t1count, t1work, t1rec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
-  int fbv1, fbblock, fbocc, fbminb; /* LIBECP_B200_FB=v1: warp-per-item fallback kernel; _FBBLOCK threads; _FBOCC blocks per SM cap */
-  int t1v1, t1block; /* LIBECP_B200_T1=v1 selects the round-1 type-1 kernels; LIBECP_B200_T1BLOCK = 32/64/128 */
+  int fbblock, fbocc, fbminb; /* tuning knobs of the fallback kernel: LIBECP_B200_FBBLOCK threads, _FBOCC blocks per SM cap, _FBMINB */
+  int t1block;                /* LIBECP_B200_T1BLOCK = 32/64/96/128 threads per block of the type-1 kernels */
 };
 
 /* scratch buffers come from the device's stream-ordered pool (release threshold raised in ecpdev_create),
@@ -815,13 +620,11 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   d->s2 = d->s2real;
   d->serial = getenv("LIBECP_B200_SERIAL") != NULL;
   {
-    const char *e = getenv("LIBECP_B200_T1");
-    d->t1v1 = e && !strcmp(e, "v1");
-    e = getenv("LIBECP_B200_FASTLIM");
+    const char *e = getenv("LIBECP_B200_FASTLIM");
     d->fastLim = e ? atoi(e) : 4;
     if (d->fastLim < 1) d->fastLim = 1;
-    e = getenv("LIBECP_B200_FB");
-    d->fbv1 = e && !strcmp(e, "v1");
+    e = getenv("LIBECP_B200_SURVCAP");
+    d->survCapEnv = e ? atoll(e) : 0;
     e = getenv("LIBECP_B200_FBBLOCK");
     d->fbblock = e ? atoi(e) : 64;
     if (d->fbblock != 32 && d->fbblock != 64 && d->fbblock != 128) d->fbblock = 64;
@@ -1217,11 +1020,6 @@ static void launch_type1_t(EcpDev *d, const T1Segs &sg, long long listOff, int s
   int *work = (int *)d->t1work.p + 2 * slot;
   int *list = (int *)d->t1list.p + listOff;
   unsigned long long *mask = (unsigned long long *)d->t1mask.p;
-  if (d->t1v1) {
-    k_type1S_v1<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, sg, cnt, list, mask);
-    k_type1L_v1<LAB><<<nblk(n * 8, 128), 128, 0, d->s2>>>(d->t, d->b, cnt, list, mask, d->b.counters + 2);
-    return;
-  }
   const int block = d->t1block;
   const size_t smem = t1_smem_bytes(LAB, block);
   static int occS[5] = {0}, occL[5] = {0}; /* resident blocks per SM, per block size 32/64/96/128 */
@@ -1342,10 +1140,6 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   CK(cudaMemsetAsync(B.tflags, 0, (size_t)h->nTriples * sizeof(int), d->s1));
   CK(cudaMemsetAsync(B.Q, 0, (size_t)h->qTotal * sizeof(double), d->s1));
   const DevT &t = d->t;
-  const int maxq2 = d->maxQPerL > 1 ? d->maxQPerL : 1;
-  const FbLayout fbl = fb_layout(d->maxLBS, d->t.maxLECP);
-  const size_t sm2 = warp_smem_bytes(maxq2, fbl.stride);
-  cudaFuncSetAttribute(k_fallbackT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm2 * FB_WARPS));
   long long launches = 0;
   const double tr1 = omp_get_wtime();
   CK(cudaEventRecord(d->ev[0], d->s1));
@@ -1395,7 +1189,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   CK(cudaEventRecord(d->ev[9], d->s1)); /* in serial mode the type-1 kernels above sit on this stream too */
   if (nWork > 0) {
     /* survivors of the first levels: room for a quarter of the quadratures (an overflowing thread finishes in place) */
-    const long long cap64 = nWork / 4 + 1024;
+    const long long cap64 = d->survCapEnv > 0 ? d->survCapEnv : nWork / 4 + 1024;
     const int survCap = cap64 > 0x7fffffff ? 0x7fffffff : (int)cap64;
     const int lim = (d->fastLim >= ECP_SMALL_LEVELS) ? ECP_SMALL_LEVELS : d->fastLim;
     int rc_ = ensure(&d->fastSurv, (size_t)survCap * sizeof(FastSurv));
@@ -1410,9 +1204,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   }
   CK(cudaEventRecord(d->ev[2], d->s1));
   if (nWork > 0) {
-    if (d->fbv1) {
-      k_fallbackT<<<d->nSM * 6, 32 * FB_WARPS, sm2 * FB_WARPS, d->s1>>>(t, B, maxq2, (int)sm2, fbl);
-    } else {
+    {
       /* persistent 8-lane groups; Bessel order bound of the instantiation: max(2 maxLBS, maxLBS + maxLECP - 1) */
       const int km = (2 * d->maxLBS > d->maxLBS + t.maxLECP - 1) ? 2 * d->maxLBS : d->maxLBS + t.maxLECP - 1;
       const int block = d->fbblock;

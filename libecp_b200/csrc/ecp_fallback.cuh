@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
         const int j = 8 * k + gl;
         const double *row = tile + (j < nq ? j : 0) * 9;
         const double A = row[0] + row[1], B = row[2] + row[3], Cq = row[4] + row[5], D = row[6] + row[7];
-        double res;
+        double hitI = 0.0;
+        int hitN = 0; /* points of the level at which the quadrature converged (0: not in this chunk) */
         if (c == 0) {
           /* slot 0 = centre, slots 2,3 = level 1, slots 4..7 = level 2 */
           I[k] = A;
@@ -236,15 +237,17 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
           Qv[k] = 2 * P[k];
           P[k] = 2 * I[k];
           I[k] += B;
-          if ((open >> k & 1) && ecp_psm92_update(3, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
-            Acc[k] += res; /* T += grid->I  (src/type2.c:513) */
+          if ((open >> k & 1) && ecp_psm92_test(3, t.tolerance, I[k], P[k], Qv[k])) {
+            hitI = I[k];
+            hitN = 3;
             open &= ~(1u << k);
           }
           Qv[k] = 2 * P[k];
           P[k] = 2 * I[k];
           I[k] += (Cq + D);
-          if ((open >> k & 1) && ecp_psm92_update(7, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
-            Acc[k] += res;
+          if ((open >> k & 1) && ecp_psm92_test(7, t.tolerance, I[k], P[k], Qv[k])) {
+            hitI = I[k];
+            hitN = 7;
             open &= ~(1u << k);
           }
         } else {
@@ -253,11 +256,14 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
             P[k] = 2 * I[k];
           }
           I[k] += ((A + B) + (Cq + D));
-          if (last && (open >> k & 1) && ecp_psm92_update(2 * n + 1, 1, t.tolerance, I[k], P[k], Qv[k], &res)) {
-            Acc[k] += res;
+          if (last && (open >> k & 1) && ecp_psm92_test(2 * n + 1, t.tolerance, I[k], P[k], Qv[k])) {
+            hitI = I[k];
+            hitN = 2 * n + 1;
             open &= ~(1u << k);
           }
         }
+        /* T += grid->I = 16 I / (3 N), N = points + 1  (src/gc_integrators.c:80, src/type2.c:513) */
+        if (hitN) Acc[k] += 16 * hitI / (3 * (hitN + 1.0));
       }
       if (c > 0 && last) {
         n = 2 * n + 1;

@@ -430,6 +430,13 @@ ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, int sa, const double *_
                                npts);
 }
 
+/* the PSM92 convergence test alone (kernels that keep the one division of the result out of the per-level code) */
+ECP_HD int ecp_psm92_test(int nNew, double tol, double I, double pv, double qv) {
+  const double N = nNew + 1.0;
+  const double e = I - pv;
+  return 16 * e * e <= 3 * N * fabs(I - qv) * tol;
+}
+
 /* FM06 linear map parameters of the large grid for a primitive pair (reference src/gc_integrators.c:316-331):
  * r = i1*x + i2, w' = w*i1 */
 ECP_HD void ecp_fm06_map(double zeta_p, double P, double *i1, double *i2) {

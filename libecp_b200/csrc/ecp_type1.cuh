@@ -7,8 +7,8 @@
  *   - k_t1prep writes one 80-byte record per primitive pair (exponent sum, |P|, prefactors, FM06 map, window, Q offset);
  *     a group fetches the next pair of its launch from an atomic work counter as soon as its current pair is finished.
  *     About 15 % of the pairs never converge on the small grid and walk all 48 chunks while the typical pair needs 2-4
- *     chunks: with a static assignment one such pair kept the other three groups of its warp idle (the round-1 kernels,
- *     ecp_type1_v1.cuh, spent ~2x the necessary warp-chunks that way).
+ *     chunks: with a static assignment one such pair kept the other three groups of its warp idle (the first kernels of
+ *     this round spent ~2x the necessary warp-chunks that way; 2.5 ms -> 1.3 ms on Au20, profiles/r1/ab_kernels.jsonl).
  *   - quadrature points are spread across the 8 lanes: every chunk each lane tabulates ONE grid point of the
  *     level-major slot layout (Bessel K_0..K_LAB, r^0..r^LAB, U_L, exp) in registers - only points a level of
  *     the adaptive rule really needs ("touched" points; the reference tabulates the whole window up front,

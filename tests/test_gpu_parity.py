@@ -161,3 +161,39 @@ def test_device_resident_matrix_matches_host_copy():
         rc, M = h.integrals_host()
     assert torch.cuda.is_available()
     assert_parity(M, load_matrix("au2"), "device-resident path")
+
+
+def _with_env(env, fn):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_launch_structure_does_not_change_results():
+    """the host pipeline (builder thread), the two-launch fast path (incl. the overflow of its survivor list) and
+    the block sizes of the persistent kernels are scheduling only: bit-identical matrices"""
+    s = synth.cfg3(4)
+    base = capi.get_integrals(s)
+    assert_parity(base, load_matrix("au4"), "au4")
+    for env in ({"LIBECP_B200_NO_PIPELINE": "1"}, {"LIBECP_B200_FASTLIM": "13"}, {"LIBECP_B200_FASTLIM": "7"},
+                {"LIBECP_B200_SURVCAP": "100"}, {"LIBECP_B200_T1BLOCK": "32", "LIBECP_B200_FBBLOCK": "128"},
+                {"LIBECP_B200_T1BLOCK": "128", "LIBECP_B200_FBBLOCK": "32", "LIBECP_B200_BATCH_TRIPLES": "500"}):
+        got = _with_env(env, lambda: capi.get_integrals(s))
+        # atomicAdd order into the matrix is not fixed: compare to the last ulps, not bitwise
+        assert np.allclose(got, base, rtol=1e-13, atol=1e-15), env
+
+
+def test_handles_in_sequence_reuse_parked_buffers():
+    """libECP_free parks the device scratch for the next handle: shapes of different size in sequence, then an
+    explicit release, still give the reference's matrices"""
+    for name in ("cfg2", "au4", "cfg4b", "cfg1", "au2", "cfg4a"):
+        assert_parity(capi.get_integrals(SMALL[name]()), load_matrix(name), name)
+    capi.lib().libecp_b200_release_cache()
+    assert_parity(capi.get_integrals(SMALL["au2"]()), load_matrix("au2"), "au2 after release")
