@@ -173,6 +173,7 @@ typedef struct {
   EcpBatchBuf *bb;
   int *centre;
   int keepCanon, took;
+  int flags, slot, prefetch; /* prefetch: start the H2D of the finished batch into input set `slot` */
   double ms;
 } BuildJob;
 static void build_job(BuildJob *j) {
@@ -181,6 +182,7 @@ static void build_job(BuildJob *j) {
   j->took = ecp_batch_build(j->h->tab, j->h->geometry, j->centre, j->h->maxTriples, j->h->rank, j->h->world, j->keepCanon,
                             j->bb);
   j->ms = now_ms() - t0;
+  if (j->prefetch && j->took > 0 && j->h->dev) ecpdev_prefetch_batch(j->h->dev, &j->bb->b, j->flags, j->slot);
 }
 struct BuildWorker {
   pthread_t th;
@@ -251,8 +253,9 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     fprintf(stderr, "libecp_b200: handle has no device context (tables-only); there is no CPU compute path\n");
     return -1;
   }
+  ecpdev_invalidate_prefetch(h->dev);
   EcpBatchBuf *bufs[2] = {h->bb, h->bb2};
-  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, 0.0};
+  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, flags, 0, 0, 0.0};
   build_job(&job); /* first batch: nothing to overlap with */
   if (getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] first batch built in %.1f ms\n", job.ms);
   if (!h->worker) h->worker = worker_new();
@@ -263,6 +266,8 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     const double t0 = now_ms();
     /* next batch on the helper thread (it advances the centre cursor; nobody else reads it meanwhile) */
     job.bb = bufs[(i + 1) & 1];
+    job.slot = (i + 1) & 1;
+    job.prefetch = threaded;
     if (threaded) worker_post(h->worker, &job);
     const EcpBatch *b = &cur->b;
     if ((flags & 2) && (size_t)b->outTotal > h->hostBlocksCap) {
@@ -271,7 +276,7 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
       h->hostBlocks = malloc(h->hostBlocksCap * sizeof(double));
     }
     EcpDevStats st;
-    const int rc = ecpdev_run_batch(h->dev, b, flags, (flags & 2) ? h->hostBlocks : NULL, &st);
+    const int rc = ecpdev_run_batch(h->dev, b, flags, i & 1, (flags & 2) ? h->hostBlocks : NULL, &st);
     if (threaded)
       worker_wait(h->worker);
     else

@@ -495,8 +495,16 @@ struct EcpDev {
   int nClasses, maxQPerL, nAO, maxLBS;
   Buf tab[64];
   int ntab;
-  Buf asAtom, asType, asR, asOmOff, ssShell, ssASlot, ssStart, ssEnd, ssFOff, trA, trB, trOut, trPair;
-  Buf prTriple, clsFirst, clsWork, clsElem, clsOutElem, clsPairBase, clsQBase;
+  /* batch inputs, two sets: the arrays of batch i+1 are copied on the copy stream s3 (from the builder thread, straight
+   * out of its page-locked output) while the kernels of batch i run */
+  struct UpSet {
+    Buf asAtom, asType, asR, asOmOff, ssShell, ssASlot, ssStart, ssEnd, ssFOff, trA, trB, trOut, trPair;
+    Buf prTriple, clsFirst, clsWork, clsElem, clsOutElem, clsPairBase, clsQBase;
+  } up[2];
+  cudaStream_t s3;
+  cudaEvent_t evUp[2];
+  const EcpBatch *upBatch[2]; /* batch whose arrays sit in the set (NULL: none) */
+  long long upBytes[2];
   Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
   double *matrix;
   size_t matrixBytes;
@@ -617,6 +625,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   cudaDeviceGetAttribute(&d->nSM, cudaDevAttrMultiProcessorCount, device);
   cudaStreamCreateWithFlags(&d->s1, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&d->s2real, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&d->s3, cudaStreamNonBlocking);
+  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&d->evUp[i], cudaEventDisableTiming);
   d->s2 = d->s2real;
   d->serial = getenv("LIBECP_B200_SERIAL") != NULL;
   {
@@ -750,7 +760,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
 /* scratch buffers (and the result matrix) of a destroyed handle are parked per device and adopted by the next handle
  * created there: a caller that goes through getIntegrals() creates a handle per call, and growing gigabytes of
  * scratch from the driver costs tens to hundreds of milliseconds each time.  libecp_b200_release_cache() frees them. */
-#define ECP_NBUF 48
+#define ECP_NBUF 72
 #define ECP_MAXDEV 16
 struct DevCache {
   int valid;
@@ -761,12 +771,15 @@ struct DevCache {
 static DevCache g_devCache[ECP_MAXDEV];
 static std::mutex g_devCacheMu;
 static int collect_bufs(EcpDev *d, Buf **bs) {
-  Buf *list[] = {&d->asAtom, &d->asType, &d->asR, &d->asOmOff, &d->ssShell, &d->ssASlot, &d->ssStart, &d->ssEnd,
-                 &d->ssFOff, &d->trA, &d->trB, &d->trOut, &d->trPair, &d->prTriple, &d->clsPairBase, &d->clsQBase,
-                 &d->clsFirst, &d->clsWork, &d->clsElem, &d->clsOutElem, &d->rshX, &d->uspX, &d->omX, &d->F, &d->T,
-                 &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks, &d->tfail, &d->tflags, &d->items,
-                 &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count, &d->t1work, &d->t1rec, &d->clsJ,
-                 &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR};
+  Buf *list[] = {&d->rshX, &d->uspX, &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks,
+                 &d->tfail, &d->tflags, &d->items, &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count,
+                 &d->t1work, &d->t1rec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR,
+#define UPSET(i) &d->up[i].asAtom, &d->up[i].asType, &d->up[i].asR, &d->up[i].asOmOff, &d->up[i].ssShell,            \
+                 &d->up[i].ssASlot, &d->up[i].ssStart, &d->up[i].ssEnd, &d->up[i].ssFOff, &d->up[i].trA, &d->up[i].trB, \
+                 &d->up[i].trOut, &d->up[i].trPair, &d->up[i].prTriple, &d->up[i].clsFirst, &d->up[i].clsWork,        \
+                 &d->up[i].clsElem, &d->up[i].clsOutElem, &d->up[i].clsPairBase, &d->up[i].clsQBase
+                 UPSET(0), UPSET(1)};
+#undef UPSET
   const int n = (int)(sizeof(list) / sizeof(list[0]));
   static_assert(sizeof(list) / sizeof(list[0]) <= ECP_NBUF, "ECP_NBUF too small");
   for (int i = 0; i < n; i++) bs[i] = list[i];
@@ -832,6 +845,8 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   for (int i = 0; i < 12; i++) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->s1);
   cudaStreamDestroy(d->s2real);
+  cudaStreamDestroy(d->s3);
+  for (int i = 0; i < 2; i++) cudaEventDestroy(d->evUp[i]);
   free(d);
 }
 
@@ -994,14 +1009,56 @@ extern "C" int ecpdev_sync(EcpDev *d) {
   return 0;
 }
 
-#define UP(buf, field, src, n, T)                                                                         \
+#define UP(buf, src, n, T)                                                                                \
   do {                                                                                                    \
-    int rc_ = ensure(&d->buf, ((n) ? (n) : 1) * sizeof(T));                                               \
+    int rc_ = ensure(&u.buf, ((n) ? (n) : 1) * sizeof(T));                                                \
     if (rc_) return rc_;                                                                                  \
-    if (n) CK(cudaMemcpyAsync(d->buf.p, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, d->s1));    \
-    d->batchH2D += (long long)((size_t)(n) * sizeof(T));                                                  \
-    B.field = (const T *)d->buf.p;                                                                        \
+    if (n) CK(cudaMemcpyAsync(u.buf.p, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, st));        \
+    d->upBytes[slot] += (long long)((size_t)(n) * sizeof(T));                                             \
   } while (0)
+/* copy the arrays of one batch into upload set `slot` on stream st */
+static int upload_set(EcpDev *d, const EcpBatch *h, int flags, int slot, cudaStream_t st) {
+  EcpDev::UpSet &u = d->up[slot];
+  const int nc = d->nClasses;
+  g_allocStream = st;
+  d->upBytes[slot] = 0;
+  UP(asAtom, h->asAtom, h->nASlots, int);
+  UP(asType, h->asType, h->nASlots, int);
+  UP(asR, h->asR, (size_t)h->nASlots * 4, double);
+  UP(asOmOff, (const long long *)h->asOmOff, h->nASlots, long long);
+  UP(ssShell, h->ssShell, h->nSSlots, int);
+  UP(ssASlot, h->ssASlot, h->nSSlots, int);
+  UP(ssStart, h->ssStart, h->nSSlots, int);
+  UP(ssEnd, h->ssEnd, h->nSSlots, int);
+  UP(ssFOff, (const long long *)h->ssFOff, h->nSSlots, long long);
+  UP(trA, h->trA, h->nTriples, int);
+  UP(trB, h->trB, h->nTriples, int);
+  if (flags & 2) UP(trOut, (const long long *)h->trOut, h->nTriples, long long);
+  UP(trPair, (const long long *)h->trPair, h->nTriples, long long);
+  UP(prTriple, h->prTriple, h->nPairs, int);
+  UP(clsFirst, h->clsFirst, nc + 1, int);
+  UP(clsWork, (const long long *)h->clsWork, nc + 1, long long);
+  UP(clsElem, (const long long *)h->clsElem, nc + 1, long long);
+  UP(clsOutElem, (const long long *)h->clsOutElem, nc + 1, long long);
+  UP(clsPairBase, (const long long *)h->clsPairBase, nc + 1, long long);
+  UP(clsQBase, (const long long *)h->clsQBase, nc + 1, long long);
+  CK(cudaEventRecord(d->evUp[slot], st));
+  d->upBatch[slot] = h;
+  return 0;
+}
+#undef UP
+/* forget prefetched inputs (start of a pass: a batch object of an aborted pass must not be mistaken for the new one) */
+extern "C" void ecpdev_invalidate_prefetch(EcpDev *d) {
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->s3);
+  d->upBatch[0] = d->upBatch[1] = NULL;
+}
+/* called from the builder thread as soon as batch i+1 is built: its H2D overlaps the kernels of batch i */
+extern "C" int ecpdev_prefetch_batch(EcpDev *d, const EcpBatch *h, int flags, int slot) {
+  CK(cudaSetDevice(d->device));
+  if (h->nTriples == 0) return 0;
+  return upload_set(d, h, flags, slot & 1, d->s3);
+}
 #define SCRATCH(buf, field, n, T)                                   \
   do {                                                              \
     int rc_ = ensure(&d->buf, ((n) ? (n) : 1) * sizeof(T));         \
@@ -1059,7 +1116,7 @@ static void launch_type1(EcpDev *d, int lab, const T1Segs &sg, long long listOff
 }
 
 
-extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double *hostBlocks, EcpDevStats *st) {
+extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slot, double *hostBlocks, EcpDevStats *st) {
   CK(cudaSetDevice(d->device));
   DevB &B = d->b;
   g_allocStream = d->s1;
@@ -1074,26 +1131,28 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, double 
   if (h->nTriples == 0) return 0;
   const bool trace = getenv("LIBECP_B200_TRACE") != NULL;
   const double tr0 = omp_get_wtime();
-  UP(asAtom, asAtom, h->asAtom, h->nASlots, int);
-  UP(asType, asType, h->asType, h->nASlots, int);
-  UP(asR, asR, h->asR, (size_t)h->nASlots * 4, double);
-  UP(asOmOff, asOmOff, (const long long *)h->asOmOff, h->nASlots, long long);
-  UP(ssShell, ssShell, h->ssShell, h->nSSlots, int);
-  UP(ssASlot, ssASlot, h->ssASlot, h->nSSlots, int);
-  UP(ssStart, ssStart, h->ssStart, h->nSSlots, int);
-  UP(ssEnd, ssEnd, h->ssEnd, h->nSSlots, int);
-  UP(ssFOff, ssFOff, (const long long *)h->ssFOff, h->nSSlots, long long);
-  UP(trA, trA, h->trA, h->nTriples, int);
-  UP(trB, trB, h->trB, h->nTriples, int);
-  if (flags & 2) UP(trOut, trOut, (const long long *)h->trOut, h->nTriples, long long);
-  UP(trPair, trPair, (const long long *)h->trPair, h->nTriples, long long);
-  UP(prTriple, prTriple, h->prTriple, h->nPairs, int);
-  UP(clsFirst, clsFirst, h->clsFirst, nc + 1, int);
-  UP(clsWork, clsWork, (const long long *)h->clsWork, nc + 1, long long);
-  UP(clsElem, clsElem, (const long long *)h->clsElem, nc + 1, long long);
-  UP(clsOutElem, clsOutElem, (const long long *)h->clsOutElem, nc + 1, long long);
-  UP(clsPairBase, clsPairBase, (const long long *)h->clsPairBase, nc + 1, long long);
-  UP(clsQBase, clsQBase, (const long long *)h->clsQBase, nc + 1, long long);
+  slot &= 1;
+  if (d->upBatch[slot] != h) { /* not prefetched (first batch, or no helper thread): copy now, on the compute stream */
+    int rc_ = upload_set(d, h, flags, slot, d->s1);
+    if (rc_) return rc_;
+  } else {
+    CK(cudaStreamWaitEvent(d->s1, d->evUp[slot], 0));
+  }
+  d->upBatch[slot] = NULL; /* consumed: the set may be refilled once this batch is through */
+  d->batchH2D = d->upBytes[slot];
+  g_allocStream = d->s1;
+  {
+    const EcpDev::UpSet &u = d->up[slot];
+    B.asAtom = (const int *)u.asAtom.p; B.asType = (const int *)u.asType.p; B.asR = (const double *)u.asR.p;
+    B.asOmOff = (const long long *)u.asOmOff.p; B.ssShell = (const int *)u.ssShell.p;
+    B.ssASlot = (const int *)u.ssASlot.p; B.ssStart = (const int *)u.ssStart.p; B.ssEnd = (const int *)u.ssEnd.p;
+    B.ssFOff = (const long long *)u.ssFOff.p; B.trA = (const int *)u.trA.p; B.trB = (const int *)u.trB.p;
+    B.trOut = (const long long *)u.trOut.p; B.trPair = (const long long *)u.trPair.p;
+    B.prTriple = (const int *)u.prTriple.p; B.clsFirst = (const int *)u.clsFirst.p;
+    B.clsWork = (const long long *)u.clsWork.p; B.clsElem = (const long long *)u.clsElem.p;
+    B.clsOutElem = (const long long *)u.clsOutElem.p; B.clsPairBase = (const long long *)u.clsPairBase.p;
+    B.clsQBase = (const long long *)u.clsQBase.p;
+  }
   SCRATCH(rshX, rshX, (size_t)h->nASlots * RSHX_STRIDE, double);
   SCRATCH(uspX, uspX, (size_t)h->nASlots * USPX_STRIDE, double);
   SCRATCH(omX, omX, (size_t)h->omTotal, double);

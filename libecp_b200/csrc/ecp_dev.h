@@ -135,8 +135,12 @@ int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigne
 void *ecpdev_matrix_ptr(EcpDev *d);
 void ecpdev_bind_thread(EcpDev *d);
 void ecpdev_release_cache(void);
-/* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks */
-int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, double *hostBlocks, EcpDevStats *stats);
+/* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks; slot = which of
+ * the two input sets to use (alternate between consecutive batches).  ecpdev_prefetch_batch copies the inputs of the
+ * NEXT batch into the other set on a copy stream while this one runs (any host thread). */
+int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, int slot, double *hostBlocks, EcpDevStats *stats);
+int ecpdev_prefetch_batch(EcpDev *d, const EcpBatch *b, int flags, int slot);
+void ecpdev_invalidate_prefetch(EcpDev *d);
 int ecpdev_sync(EcpDev *d);
 long long ecpdev_table_bytes(EcpDev *d);
 void ecpdev_set_serial(EcpDev *d, int on);
