@@ -51,6 +51,7 @@ struct DevT {
   const int *ijk, *ijkIndex;
   const double *small_r, *small_w, *large_x, *large_w;
   const int16_t *small_oidx;
+  const unsigned char *small_jL, *small_jR; /* first in-window pair per (level, start) / (level, end), ecp_math.h */
   const double *besselT, *besselC;
   const int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO, *atomMaxL;
   const double *primD, *primA;
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(128) k_fastT(DevT t, DevB b, long long nWork, 
     const FastQ f = fast_load(t, b, w);
     tri = f.tri;
     l = f.l;
-    rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, c_small_oidx, &t.sm, f.gs, f.ge,
+    rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, &t.sm, t.small_jL, t.small_jR, f.gs, f.ge,
                                t.tolerance, 0, lim, &st, &res, (int *)0);
   }
   /* unconverged after level lim-1: to the survivor list (one atomic per warp) */
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(128) k_fastT(DevT t, DevB b, long long nWork, 
         surv[pos].w = w;
       } else { /* list full: finish here */
         const FastQ f = fast_load(t, b, w);
-        rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, c_small_oidx, &t.sm, f.gs, f.ge,
+        rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, &t.sm, t.small_jL, t.small_jR, f.gs, f.ge,
                                    t.tolerance, lim, ECP_SMALL_LEVELS, &st, &res, (int *)0);
       }
     }
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
   const long long w = surv[i].w;
   const FastQ f = fast_load(t, b, w);
   double res = 0.0;
-  const int rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, c_small_oidx, &t.sm, f.gs,
+  const int rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, &t.sm, t.small_jL, t.small_jR, f.gs,
                                        f.ge, t.tolerance, lim, ECP_SMALL_LEVELS, &st, &res, (int *)0);
   fast_store(b, w, rc, res, f.tri, f.l);
 }
@@ -685,6 +686,19 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   t.small_r = upload_const(d, h->small_r, ECP_SMALL_SLOTS);
   t.small_w = upload_const(d, h->small_w, ECP_SMALL_SLOTS);
   t.small_oidx = upload_const(d, h->small_oidx, ECP_SMALL_SLOTS);
+  {
+    unsigned char *jl = (unsigned char *)malloc(2 * ECP_SMALL_LEVELS * ECP_SMALL_SLOTS), *jr = jl + ECP_SMALL_LEVELS * ECP_SMALL_SLOTS;
+    if (!ecp_small_suffix_tables(&t.sm, h->small_oidx, jl, jr)) {
+      snprintf(g_err, sizeof(g_err), "libecp_b200: small-grid slot table is not monotone per level");
+      free(jl);
+      ecpdev_destroy(d);
+      return NULL;
+    }
+    t.small_jL = upload_const(d, jl, (size_t)ECP_SMALL_LEVELS * ECP_SMALL_SLOTS);
+    t.small_jR = upload_const(d, jr, (size_t)ECP_SMALL_LEVELS * ECP_SMALL_SLOTS);
+    cudaStreamSynchronize(d->s1);
+    free(jl);
+  }
   t.large_x = upload_const(d, h->large_x, h->largeSlots);
   t.large_w = upload_const(d, h->large_w, h->largeSlots);
   t.besselT = upload_const(d, h->besselT, (size_t)1601 * h->besselStride);

@@ -322,6 +322,27 @@ ECP_HD void ecp_small_meta_bounds(EcpSmallMeta *m, const int16_t *oidx) {
   }
 }
 
+/* In-window pairs of a level form suffixes of its visiting order: the left indices ascend with the pair number j and
+ * a left point counts iff idx >= start; the right indices descend and a right point counts iff idx <= end
+ * (src/gc_integrators.c:186-199).  jL[v][start] / jR[v][end] = first pair of level v whose left / right point is inside
+ * ([ECP_SMALL_LEVELS][ECP_SMALL_SLOTS] bytes each; a level has at most 64 pairs).  With them the fast-path loop needs
+ * no per-point index test.  Returns 0 if the slot table is not monotone (never for the PS93 grid). */
+ECP_HD int ecp_small_suffix_tables(const EcpSmallMeta *m, const int16_t *oidx, unsigned char *jL, unsigned char *jR) {
+  for (int v = 0; v < ECP_SMALL_LEVELS; v++) {
+    const int s0 = m->levSlot[v], np = (m->levSlot[v + 1] - s0) / 2;
+    for (int j = 1; j < np; j++)
+      if (oidx[s0 + 2 * j] <= oidx[s0 + 2 * j - 2] || oidx[s0 + 2 * j + 1] >= oidx[s0 + 2 * j - 1]) return 0;
+    for (int w = 0; w < ECP_SMALL_SLOTS; w++) {
+      int a = 0, b = 0;
+      while (a < np && oidx[s0 + 2 * a] < w) a++;     /* first left index >= start = w */
+      while (b < np && oidx[s0 + 2 * b + 1] > w) b++; /* first right index <= end = w  */
+      jL[v * ECP_SMALL_SLOTS + w] = (unsigned char)a;
+      jR[v * ECP_SMALL_SLOTS + w] = (unsigned char)b;
+    }
+  }
+  return 1;
+}
+
 /* One PS93 level update after the level's points were added to I
  * (reference src/gc_integrators.c:201-214).  Returns 1 when converged (result in *res). */
 ECP_HD int ecp_ps93_update(int j, int n, int cnt, double tol, double I, double *p, double *q, double *res) {
@@ -373,8 +394,9 @@ typedef struct {
 } EcpPs93State;
 ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
                                  const double *__restrict__ U, int su, const double *__restrict__ w,
-                                 const int16_t *__restrict__ oidx, const EcpSmallMeta *meta, int start, int end,
-                                 double tol, int v0, int v1, EcpPs93State *st, double *result, int *npts) {
+                                 const EcpSmallMeta *meta, const unsigned char *__restrict__ jL,
+                                 const unsigned char *__restrict__ jR, int start, int end, double tol, int v0, int v1,
+                                 EcpPs93State *st, double *result, int *npts) {
   double p, q, I;
   int np = 0;
   if (v0 == 0) {
@@ -387,25 +409,36 @@ ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const do
     q = st->q;
     I = st->I;
   }
+  const int we = end < 0 ? 0 : (end >= ECP_SMALL_SLOTS ? ECP_SMALL_SLOTS - 1 : end);
+  const int ws = start < 0 ? 0 : (start >= ECP_SMALL_SLOTS ? ECP_SMALL_SLOTS - 1 : start);
   for (int v = v0; v < v1; v++) {
-    int cnt = 0;
-    const int s0 = meta->levSlot[v];
-    /* a level without any in-window point only moves the bookkeeping (cnt == 0, src/gc_integrators.c:203-208) */
-    const int s1 = (meta->levMaxL[v] < start && meta->levMinR[v] > end) ? s0 : meta->levSlot[v + 1];
-    int oa = s0 * sa, ob = s0 * sb, ou = s0 * su; /* running element offsets of slot s in the three strided rows */
+    const int s0 = meta->levSlot[v], npair = (meta->levSlot[v + 1] - s0) / 2;
+    /* pairs [ja, npair) have their left point inside the window, pairs [jb, npair) their right point; a level without
+     * any in-window point only moves the bookkeeping (cnt == 0, src/gc_integrators.c:203-208) */
+    const int ja = (start > ECP_SMALL_SLOTS - 1) ? npair : jL[v * ECP_SMALL_SLOTS + ws];
+    const int jb = (end < 0) ? npair : jR[v * ECP_SMALL_SLOTS + we];
+    const int cnt = (npair - ja) + (npair - jb);
+    const int j0 = ja < jb ? ja : jb, j1 = ja < jb ? jb : ja;
+    int s = s0 + 2 * j0;
+    int oa = s * sa, ob = s * sb, ou = s * su; /* running element offsets of slot s in the three strided rows */
+    if (ja < jb) { /* only the left point of these pairs counts: T = 0 + left */
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int s = s0; s < s1; s += 2, oa += 2 * sa, ob += 2 * sb, ou += 2 * su) {
-      double T = 0.0;
-      if (oidx[s] >= start) {
-        T += w[s] * (Fa[oa] * Fb[ob] * U[ou]);
-        cnt++;
-      }
-      if (oidx[s + 1] <= end) {
-        T += w[s + 1] * (Fa[oa + sa] * Fb[ob + sb] * U[ou + su]);
-        cnt++;
-      }
+      for (int j = j0; j < j1; j++, s += 2, oa += 2 * sa, ob += 2 * sb, ou += 2 * su) I += w[s] * (Fa[oa] * Fb[ob] * U[ou]);
+    } else { /* only the right point */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int j = j0; j < j1; j++, s += 2, oa += 2 * sa, ob += 2 * sb, ou += 2 * su)
+        I += w[s + 1] * (Fa[oa + sa] * Fb[ob + sb] * U[ou + su]);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = j1; j < npair; j++, s += 2, oa += 2 * sa, ob += 2 * sb, ou += 2 * su) {
+      double T = w[s] * (Fa[oa] * Fb[ob] * U[ou]);
+      T += w[s + 1] * (Fa[oa + sa] * Fb[ob + sb] * U[ou + su]);
       I += T;
     }
     np += cnt;
@@ -421,12 +454,12 @@ ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const do
   return (v1 >= ECP_SMALL_LEVELS) ? 1 : 2;
 }
 ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
-                          const double *__restrict__ U, int su, const double *__restrict__ w,
-                          const int16_t *__restrict__ oidx, const EcpSmallMeta *meta, int start, int end, double tol,
+                          const double *__restrict__ U, int su, const double *__restrict__ w, const EcpSmallMeta *meta,
+                          const unsigned char *jL, const unsigned char *jR, int start, int end, double tol,
                           double *result, int *npts) {
   EcpPs93State st;
   if (npts) *npts = 0;
-  return ecp_ps93_fastT_levels(Fa, sa, Fb, sb, U, su, w, oidx, meta, start, end, tol, 0, ECP_SMALL_LEVELS, &st, result,
+  return ecp_ps93_fastT_levels(Fa, sa, Fb, sb, U, su, w, meta, jL, jR, start, end, tol, 0, ECP_SMALL_LEVELS, &st, result,
                                npts);
 }
 

@@ -32,7 +32,9 @@ int hc_ps93_fastT(const double *Fa, const double *Fb, const double *U, const dou
   }
   for (int i = 0; i <= ECP_SMALL_LEVELS; i++) m.levSlot[i] = meta[39 + i];
   ecp_small_meta_bounds(&m, oidx);
-  return ecp_ps93_fastT(Fa, 1, Fb, 1, U, 1, w, oidx, &m, start, end, tol, res, npts);
+  static unsigned char jL[ECP_SMALL_LEVELS * ECP_SMALL_SLOTS], jR[ECP_SMALL_LEVELS * ECP_SMALL_SLOTS];
+  if (!ecp_small_suffix_tables(&m, oidx, jL, jR)) return -1;
+  return ecp_ps93_fastT(Fa, 1, Fb, 1, U, 1, w, &m, jL, jR, start, end, tol, res, npts);
 }
 double hc_pot_eval(const int *gl, const double *gn, const double *gd, const double *ga, int n, int l, double r) {
   return ecp_pot_eval(gl, gn, gd, ga, 0, n, l, r);
