@@ -62,6 +62,7 @@ struct DevT {
   int nAO;
 };
 struct T1Rec;
+struct TriRec;
 struct DevB {
   int nASlots, nSSlots, nTriples;
   long long nPairs;
@@ -80,6 +81,7 @@ struct DevB {
   unsigned char *tfail;
   int *tflags, *items;
   T1Rec *t1rec; /* per primitive pair, written by k_t1prep (ecp_type1.cuh) */
+  TriRec *trirec; /* per triple, written by k_triprep */
   int *counters; /* [0] nItems [1] work counter [2] err1 [3] err2 [4] nFastFail [5] nType1Fail [6] stale [7] work2 */
 };
 #define RSHX_STRIDE 121
@@ -304,6 +306,44 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
 
 #include "ecp_fallback.cuh"
 
+/* ---- per triple: everything the element-parallel kernels (link, chi, shift) would otherwise chase through
+ * trA/trB -> ssShell/ssASlot -> asAtom/asOmOff/shellK/... with up to five dependent loads PER ELEMENT.  Those kernels
+ * are bound by exactly that latency; one 64-byte record per triple (read as a warp broadcast) cuts the chain to one. */
+struct __align__(16) TriRec {
+  long long omA, omB; /* offsets of Omega_A / Omega_B in omX                               */
+  long long q0;       /* offset of Q / S_lm(P^) of the first primitive pair                */
+  int np;             /* primitive pairs Na * Nb                                           */
+  int asa, asb;       /* atom slots (unit-sphere monomial tables)                          */
+  int incA1, incB1;   /* C_DIM(lmax of atom A / B): stride of Omega_X over (l,m)           */
+  int dA, dB;         /* lmax + 1 of atom A / B                                            */
+  int rowAO, colAO;   /* first AO of shell a / b                                           */
+  int pad;
+};
+__global__ void k_triprep(DevT t, DevB b) {
+  const int tri = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tri >= b.nTriples) return;
+  const int c = find_class_i(b.clsFirst, t.nClasses, tri);
+  const int ssa = b.trA[tri], ssb = b.trB[tri];
+  const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
+  const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
+  const int lXa = t.atomMaxL[b.asAtom[asa]], lXb = t.atomMaxL[b.asAtom[asb]];
+  TriRec r;
+  r.omA = b.asOmOff[asa];
+  r.omB = b.asOmOff[asb];
+  r.q0 = pair_Q_off(t, b, c, b.trPair[tri]);
+  r.np = t.shellK[sha] * t.shellK[shb];
+  r.asa = asa;
+  r.asb = asb;
+  r.incA1 = ecp_cd(lXa);
+  r.incB1 = ecp_cd(lXb);
+  r.dA = lXa + 1;
+  r.dB = lXb + 1;
+  r.rowAO = t.shellAO[sha];
+  r.colAO = t.shellAO[shb];
+  r.pad = 0;
+  b.trirec[tri] = r;
+}
+
 /* ---- link: gamma[p][q], one thread per element ---- */
 __device__ __forceinline__ int deg_of_cindex(int p) {
   int l = 0;
@@ -328,12 +368,10 @@ __global__ void __launch_bounds__(128) k_link(DevT t, DevB b, int c) {
   const int tri = b.clsFirst[c] + (int)(idx / (cda * cdb));
   const int pq = (int)(idx % (cda * cdb)), p = pq / cdb, q = pq % cdb;
   const int alpha = deg_of_cindex(p), beta = deg_of_cindex(q);
-  const int ssa = b.trA[tri], ssb = b.trB[tri];
-  const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
-  const int lXa = t.atomMaxL[b.asAtom[asa]], lXb = t.atomMaxL[b.asAtom[asb]];
-  const int incA1 = ecp_cd(lXa), incA2 = L * L * incA1;
-  const int incB1 = ecp_cd(lXb), incB2 = L * L * incB1;
-  const double *oA = b.omX + b.asOmOff[asa] + p, *oB = b.omX + b.asOmOff[asb] + q;
+  const TriRec rec = b.trirec[tri];
+  const int incA1 = rec.incA1, incA2 = L * L * incA1;
+  const int incB1 = rec.incB1, incB2 = L * L * incB1;
+  const double *oA = b.omX + rec.omA + p, *oB = b.omX + rec.omB + q;
   const double *T = b.T + b.clsWork[c] + (long long)(tri - b.clsFirst[c]) * t.clsNq[c];
   const int16_t *qi = t.qidx + t.clsQidxOff[c];
   const int d2 = lb + L, d3 = la + lb + 1;
@@ -439,12 +477,12 @@ __global__ void k_chi(DevT t, DevB b, long long nElem) {
   const int D = t.ijkDim;
   const int p = t.ijkIndex[lx * D * D + ly * D + lz];
   const double *PM = t.poly2sph + (size_t)p * t.pcols;
-  const int ssa = b.trA[tri], ssb = b.trB[tri];
-  const int np = t.shellK[b.ssShell[ssa]] * t.shellK[b.ssShell[ssb]];
-  const long long pr0 = b.trPair[tri];
+  const int np = b.trirec[tri].np;
+  const long long q0 = b.trirec[tri].q0;
+  const int ld = (lab + 1) * (lab + 1);
   double chi = 0.0;
   for (int ip = 0; ip < np; ip++) {
-    const long long qo = pair_Q_off(t, b, c, pr0 + ip);
+    const long long qo = q0 + (long long)ip * ld;
     const double *rsh = b.rshP + qo;
     const double *Q = b.Q + qo + lmax * (lab + 1);
     for (int l = lmax; l >= 0; l -= 2) {
@@ -515,7 +553,7 @@ struct EcpDev {
   Buf fastSurv;
   int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
   long long survCapEnv; /* LIBECP_B200_SURVCAP: survivor-list capacity override (tests of the overflow path) */
-  Buf t1list, t1mask, t1count, t1work, t1rec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
+  Buf t1list, t1mask, t1count, t1work, t1rec, trirec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
   int fbblock, fbocc, fbminb; /* tuning knobs of the fallback kernel: LIBECP_B200_FBBLOCK threads, _FBOCC blocks per SM cap, _FBMINB */
   int t1block;                /* LIBECP_B200_T1BLOCK = 32/64/96/128 threads per block of the type-1 kernels */
@@ -787,7 +825,7 @@ static std::mutex g_devCacheMu;
 static int collect_bufs(EcpDev *d, Buf **bs) {
   Buf *list[] = {&d->rshX, &d->uspX, &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks,
                  &d->tfail, &d->tflags, &d->items, &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count,
-                 &d->t1work, &d->t1rec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR,
+                 &d->t1work, &d->t1rec, &d->trirec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR,
 #define UPSET(i) &d->up[i].asAtom, &d->up[i].asType, &d->up[i].asR, &d->up[i].asOmOff, &d->up[i].ssShell,            \
                  &d->up[i].ssASlot, &d->up[i].ssStart, &d->up[i].ssEnd, &d->up[i].ssFOff, &d->up[i].trA, &d->up[i].trB, \
                  &d->up[i].trOut, &d->up[i].trPair, &d->up[i].prTriple, &d->up[i].clsFirst, &d->up[i].clsWork,        \
@@ -1196,6 +1234,9 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     rc_ = ensure(&d->t1rec, ((size_t)h->nPairs + 1) * sizeof(T1Rec));
     if (rc_) return rc_;
     B.t1rec = (T1Rec *)d->t1rec.p;
+    rc_ = ensure(&d->trirec, ((size_t)h->nTriples + 1) * sizeof(TriRec));
+    if (rc_) return rc_;
+    B.trirec = (TriRec *)d->trirec.p;
     d->launchSeq = 0;
   }
   if ((flags & 1) && !d->matrix) {
@@ -1217,10 +1258,11 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   const double tr1 = omp_get_wtime();
   CK(cudaEventRecord(d->ev[0], d->s1));
   /* per-centre tables */
+  k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
   k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
   k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
   k_Ftab<<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
-  launches += 3;
+  launches += 4;
   CK(cudaEventRecord(d->ev[1], d->s1));
   /* type 1 on the second stream, after the uploads/tables */
   CK(cudaStreamWaitEvent(d->s2, d->ev[1], 0));

@@ -22,8 +22,8 @@ __global__ void k_shiftJ(DevT t, DevB b, const long long *__restrict__ clsJ, lon
   const long long idx = w - clsJ[c];
   const int tri = b.clsFirst[c] + (int)(idx / (na * cdb));
   const int rem = (int)(idx % (na * cdb)), c1 = rem / cdb, q = rem % cdb;
-  const int asa = b.ssASlot[b.trA[tri]];
-  const int dA = t.atomMaxL[b.asAtom[asa]] + 1;
+  const int asa = b.trirec[tri].asa;
+  const int dA = b.trirec[tri].dA;
   const double *uA = b.uspX + (size_t)asa * USPX_STRIDE;
   const long long gOff = tri_G_off(t, b, c, tri);
   const double *G1 = b.chi + gOff + q, *G2 = b.gamma + gOff + q;
@@ -52,9 +52,9 @@ __global__ void k_shiftI(DevT t, DevB b, const long long *__restrict__ clsJ, lon
   const long long idx = w - b.clsOutElem[c];
   const int tri = b.clsFirst[c] + (int)(idx / (na * nb));
   const int cc = (int)(idx % (na * nb)), c1 = cc / nb, c2 = cc % nb;
-  const int ssa = b.trA[tri], ssb = b.trB[tri];
-  const int asb = b.ssASlot[ssb];
-  const int dB = t.atomMaxL[b.asAtom[asb]] + 1;
+  const TriRec rec = b.trirec[tri];
+  const int asb = rec.asb;
+  const int dB = rec.dB;
   const double *uB = b.uspX + (size_t)asb * USPX_STRIDE;
   const double *J1 = Jbuf + 2 * (clsJ[c] + (long long)(tri - b.clsFirst[c]) * (na * cdb)) + c1 * cdb;
   const double *J2 = J1 + na * cdb;
@@ -75,7 +75,7 @@ __global__ void k_shiftI(DevT t, DevB b, const long long *__restrict__ clsJ, lon
     o[na * nb + cc] = I2;
   }
   if (flags & 1) {
-    const int row = t.shellAO[b.ssShell[ssa]] + c1, col = t.shellAO[b.ssShell[ssb]] + c2;
+    const int row = rec.rowAO + c1, col = rec.colAO + c2;
     if (row <= col) atomicAdd(&b.matrix[(size_t)row * t.nAO + col], I1 + I2); /* src/getIntegrals.c:38-40 */
   }
 }
