@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(128) k_link(DevT t, DevB b, int c) {
       for (int j = 0; j < NB; j++) f[i][j] = 0.0;
     const double *pa = oA + (size_t)ll1 * incA2 + (size_t)(l * l) * incA1;
     const double *pb = oB + (size_t)ll2 * incB2 + (size_t)(l * l) * incB1;
+#pragma unroll 2
     for (int m = 0; m < 2 * l + 1; m++) {
       double a[NA], bb[NB];
 #pragma unroll
