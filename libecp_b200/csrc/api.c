@@ -309,6 +309,17 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
 
 int calculateECPIntegrals(libECPHandle *h, ECPCallback cb, void *args) { return run_all(h, 2, cb, args); }
 
+/* AO rows of the shells whose shell-pair rows this rank owns (NULL for an unsharded handle); caller frees */
+static unsigned char *owned_rows(const libECPHandle *h) {
+  if (h->world <= 1) return NULL;
+  const EcpHostTables *v = &h->tab->v;
+  unsigned char *owned = calloc(v->nAO + 1, 1);
+  for (int s = 0; s < v->nrShells; s++)
+    if (ecp_pair_owner(s, s, h->world) == h->rank)
+      for (int k = 0; k < IJK_DIM(v->shellL[s]); k++) owned[v->shellAO[s] + k] = 1;
+  return owned;
+}
+
 int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
   if (nAO) *nAO = h->tab->v.nAO;
   if (h->empty) {
@@ -316,7 +327,9 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
     return 0;
   }
   if (!h->dev) return -1;
-  int rc = ecpdev_matrix_begin(h->dev);
+  unsigned char *owned = owned_rows(h);
+  int rc = ecpdev_matrix_begin(h->dev, owned, (long long)h->world * 1000003LL + h->rank);
+  free(owned);
   if (rc) return -rc;
   rc = run_all(h, 1, NULL, NULL);
   if (devMatrix) *devMatrix = ecpdev_matrix_ptr(h->dev);
@@ -330,14 +343,7 @@ int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   const int rc = libecp_b200_integrals_device(h, &dm, NULL);
   if (rc < 0 || h->empty) return rc;
   long long moved = 0;
-  unsigned char *owned = NULL;
-  if (h->world > 1) { /* only the AO rows of the shells this rank owns can be non-zero */
-    const EcpHostTables *v = &h->tab->v;
-    owned = calloc(n + 1, 1);
-    for (int s = 0; s < v->nrShells; s++)
-      if (ecp_pair_owner(s, s, h->world) == h->rank)
-        for (int k = 0; k < IJK_DIM(v->shellL[s]); k++) owned[v->shellAO[s] + k] = 1;
-  }
+  unsigned char *owned = owned_rows(h); /* only the AO rows of the shells this rank owns can be non-zero */
   const double tA = now_ms();
   const int rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, owned, &moved);
   if (getenv("LIBECP_B200_TRACE"))

@@ -548,6 +548,9 @@ struct EcpDev {
   Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
   double *matrix;
   size_t matrixBytes;
+  int matrixKnown, dirtyAll, nDirty; /* matrix is zero outside the upper-triangle parts of the dirty rows */
+  long long dirtySig;
+  Buf dirtyRows;
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
@@ -820,6 +823,9 @@ struct DevCache {
   Buf bufs[ECP_NBUF];
   double *matrix;
   size_t matrixBytes;
+  int matrixKnown, dirtyAll, nDirty; /* matrix is zero outside the upper-triangle parts of the dirty rows */
+  long long dirtySig;
+  Buf dirtyRows;
 };
 static DevCache g_devCache[ECP_MAXDEV];
 static std::mutex g_devCacheMu;
@@ -850,6 +856,7 @@ static void adopt_cached(EcpDev *d) {
   if (c.matrix && c.matrixBytes >= bytes && c.matrixBytes <= 2 * bytes + (1 << 20)) {
     d->matrix = c.matrix;
     d->matrixBytes = c.matrixBytes;
+    d->matrixKnown = 0; /* another handle's result */
   } else if (c.matrix) {
     cudaFreeAsync(c.matrix, d->s1);
   }
@@ -894,6 +901,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
     cudaStreamSynchronize(d->s1);
     if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
   }
+  if (d->dirtyRows.p) cudaFreeAsync(d->dirtyRows.p, d->s1);
   cudaStreamSynchronize(d->s1);
   for (int i = 0; i < 12; i++) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->s1);
@@ -903,14 +911,55 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   free(d);
 }
 
-extern "C" int ecpdev_matrix_begin(EcpDev *d) {
+/* zero M[i][i..n) of the listed rows (all rows when rows == NULL) */
+__global__ void k_zero_rows(double *__restrict__ M, int n, const int *__restrict__ rows) {
+  const int i = rows ? rows[blockIdx.x] : blockIdx.x;
+  double *r = M + (size_t)i * n;
+  for (int j = i + threadIdx.x; j < n; j += blockDim.x) r[j] = 0.0;
+}
+/* Result matrix, zeroed.  A pass only ever writes the upper-triangle part of the AO rows of the shells its rank owns
+ * (rowOwned, nAO bytes; NULL = all rows).  After the first full clear only those parts are cleared again - with the
+ * rows dealt to 8 ranks that is 1/16 of the 2.9 GB a full memset of the 500-atom matrix touches, a fixed cost that
+ * would otherwise not shrink with the number of GPUs.  `sig` identifies the ownership (rank, world). */
+extern "C" int ecpdev_matrix_begin(EcpDev *d, const unsigned char *rowOwned, long long sig) {
   CK(cudaSetDevice(d->device));
-  const size_t bytes = (size_t)d->nAO * d->nAO * sizeof(double);
+  const int n = d->nAO;
+  const size_t bytes = (size_t)n * n * sizeof(double);
   if (!d->matrix) {
     CK(cudaMallocAsync((void **)&d->matrix, bytes ? bytes : 8, d->s1));
     d->matrixBytes = bytes ? bytes : 8;
+    d->matrixKnown = 0;
   }
-  CK(cudaMemsetAsync(d->matrix, 0, bytes, d->s1));
+  if (!d->matrixKnown) {
+    CK(cudaMemsetAsync(d->matrix, 0, bytes, d->s1));
+  } else if (d->nDirty > 0) {
+    k_zero_rows<<<d->nDirty, 256, 0, d->s1>>>(d->matrix, n, d->dirtyAll ? NULL : (const int *)d->dirtyRows.p);
+  }
+  /* rows the coming pass may write */
+  if (!d->matrixKnown || sig != d->dirtySig) {
+    if (!rowOwned) {
+      d->dirtyAll = 1;
+      d->nDirty = n;
+    } else {
+      int *rows = (int *)malloc((size_t)(n + 1) * sizeof(int));
+      int nr = 0;
+      for (int i = 0; i < n; i++)
+        if (rowOwned[i]) rows[nr++] = i;
+      g_allocStream = d->s1;
+      int rc_ = ensure(&d->dirtyRows, (size_t)(nr + 1) * sizeof(int));
+      if (rc_) {
+        free(rows);
+        return rc_;
+      }
+      if (nr) CK(cudaMemcpyAsync(d->dirtyRows.p, rows, (size_t)nr * sizeof(int), cudaMemcpyHostToDevice, d->s1));
+      CK(cudaStreamSynchronize(d->s1)); /* rows is pageable */
+      free(rows);
+      d->dirtyAll = 0;
+      d->nDirty = nr;
+    }
+    d->dirtySig = sig;
+  }
+  d->matrixKnown = 1;
   return 0;
 }
 extern "C" int ecpdev_matrix_download(EcpDev *d, double *host) {
@@ -1241,7 +1290,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     d->launchSeq = 0;
   }
   if ((flags & 1) && !d->matrix) {
-    int rc = ecpdev_matrix_begin(d);
+    int rc = ecpdev_matrix_begin(d, NULL, -1);
     if (rc) return rc;
   }
   B.matrix = d->matrix;

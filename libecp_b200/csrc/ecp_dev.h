@@ -128,7 +128,7 @@ EcpDev *ecpdev_create(const EcpHostTables *t, int device);
 void ecpdev_destroy(EcpDev *d);
 const char *ecpdev_last_error(void);
 /* matrix accumulation target (device resident, nAO x nAO, zeroed) */
-int ecpdev_matrix_begin(EcpDev *d);
+int ecpdev_matrix_begin(EcpDev *d, const unsigned char *rowOwned /* [nAO] or NULL = all */, long long ownershipSig);
 int ecpdev_matrix_download(EcpDev *d, double *host /* nAO*nAO */);
 int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned /* [nAO] or NULL */,
                               long long *bytes);

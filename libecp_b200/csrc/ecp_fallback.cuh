@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
   extern __shared__ __align__(16) double fb_smem[];
   const int lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24;
   double *gsm = fb_smem + (size_t)(threadIdx.x >> 3) * Cfg::GROUP;
-  double *rows = gsm, *myrow = gsm + gl * RS;
+  double *myrow = gsm + gl * RS;
   double *tile = gsm + 8 * RS;
   int *qK = (int *)(tile + FB_TILE), *qQ = qK + FB_NQ; /* position in the class list / packed l | l1<<4 | l2<<8 | l3<<12 */
   const int nItems = b.counters[0];
