@@ -349,6 +349,14 @@ def run_b200(args):
             sagg = st if sagg is None else {k: sagg[k] + v for k, v in st.items()}
         serial_stats = {k: v / 2 for k, v in sagg.items()}
         h.set_serial_kernels(False)
+    per_rank = None
+    if dist:  # load balance of the shard partition: every rank's own figures
+        mine = torch.tensor([stats["ms_device_total"], stats["ms_build"], stats["executed_triples"], ev0.elapsed_time(ev1) / args.steps],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"device_ms": [round(float(x[0]), 2) for x in allr], "build_ms": [round(float(x[1]), 2) for x in allr],
+                    "executed_triples": [int(x[2]) for x in allr], "step_ms": [round(float(x[3]), 2) for x in allr]}
     executed_all = sum_over_ranks(stats["executed_triples"])
     launches = sum_over_ranks(agg["kernel_launches"])
     value = nominal * args.steps / (ms * 1e-3)
@@ -407,6 +415,8 @@ def run_b200(args):
         }
         if rl:
             line["roofline"] = rl
+        if per_rank:
+            line["per_rank"] = per_rank
     if world == 1 and rank == 0 and not args.no_secondary and args.workload != "cfg3":
         line["secondary"] = secondary_au20(capi, torch, peak_tf)
     h.close()

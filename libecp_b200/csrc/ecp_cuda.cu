@@ -463,36 +463,75 @@ __global__ void k_t1prep(DevT t, DevB b) {
   b.t1rec[pr] = rec;
 }
 
-/* ---- chi[i][j], one thread per element ---- */
-__global__ void k_chi(DevT t, DevB b, long long nElem) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nElem) return;
-  const int c = find_class(b.clsElem, t.nClasses, w);
-  const int la = t.clsLa[c], lb = t.clsLb[c], lab = la + lb;
-  const int cda = ecp_cd(la), cdb = ecp_cd(lb);
-  const long long idx = w - b.clsElem[c];
-  const int tri = b.clsFirst[c] + (int)(idx / (cda * cdb));
-  const int pq = (int)(idx % (cda * cdb)), i = pq / cdb, j = pq % cdb;
-  const int *ei = t.ijk + 3 * i, *ej = t.ijk + 3 * j;
-  const int lx = ei[0] + ej[0], ly = ei[1] + ej[1], lz = ei[2] + ej[2], lmax = lx + ly + lz;
-  const int D = t.ijkDim;
-  const int p = t.ijkIndex[lx * D * D + ly * D + lz];
-  const double *PM = t.poly2sph + (size_t)p * t.pcols;
-  const int np = b.trirec[tri].np;
-  const long long q0 = b.trirec[tri].q0;
+/* ---- chi[i][j]: eight lanes per triple, two phases ----
+ * The reference forms, per primitive pair, chi[i][j] += sum_{l = N, N-2, ...} (sum_m S_lm(P^) poly2sph[p][(l,m)]) Q[N][l]
+ * with N the degree and p the index of the product monomial x^i y^j z^k of the element (src/type1.c:266-295): the
+ * pair-dependent factors S_lm Q[N][l] do not depend on the element beyond N.  So the sum over the primitive pairs is
+ * taken first,
+ *     R[N][(l,m)] = sum_pairs S_lm(P^_pair) Q_pair[N][l]          (l = N, N-2, ...: C_DIM(la+lb) values per triple)
+ * by the 8 lanes of the triple into shared memory, and every element is one short dot product
+ *     chi[i][j] = sum_{l,m} poly2sph[p][(l,m)] R[N][(l,m)].
+ * The multiply-adds per triple drop from  pairs x elements x (N+1)(N+2)/2  to  (pairs + elements) x (N+1)(N+2)/2
+ * (p-p shells of the TZ sets have 16 pairs).  Same products as the reference, associated over the pairs first. */
+__device__ __forceinline__ int chi_roff(int N, int l) { /* position of (l, m = 0) of level N in the packed R */
+  return N * (N + 1) * (N + 2) / 6 + l * (l - 1) / 2;
+}
+__global__ void __launch_bounds__(128) k_chi(DevT t, DevB b, int rStride) {
+  extern __shared__ __align__(16) double chi_R[];
+  const int gl = threadIdx.x & 7;
+  double *R = chi_R + (size_t)(threadIdx.x >> 3) * rStride;
+  const int tri = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+  const bool valid = tri < b.nTriples;
+  int c = 0, la = 0, lb = 0, lab = 0, np = 0;
+  long long q0 = 0;
+  if (valid) {
+    c = find_class_i(b.clsFirst, t.nClasses, tri);
+    la = t.clsLa[c];
+    lb = t.clsLb[c];
+    lab = la + lb;
+    np = b.trirec[tri].np;
+    q0 = b.trirec[tri].q0;
+  }
   const int ld = (lab + 1) * (lab + 1);
-  double chi = 0.0;
-  for (int ip = 0; ip < np; ip++) {
-    const long long qo = q0 + (long long)ip * ld;
-    const double *rsh = b.rshP + qo;
-    const double *Q = b.Q + qo + lmax * (lab + 1);
-    for (int l = lmax; l >= 0; l -= 2) {
-      double factor = 0.0;
-      for (int m = 0; m < 2 * l + 1; m++) factor += rsh[l * l + m] * PM[l * l + m];
-      chi += factor * Q[l];
+  /* phase 1: R[N][(l,m)] */
+  if (valid) {
+    const int nR = ecp_cd(lab);
+    for (int e = gl; e < nR; e += 8) {
+      int N = 0;
+      while (ecp_cd(N) <= e) N++;
+      int rem = e - N * (N + 1) * (N + 2) / 6, l = N & 1;
+      while (rem >= 2 * l + 1) {
+        rem -= 2 * l + 1;
+        l += 2;
+      }
+      const double *rsh = b.rshP + q0 + l * l + rem;
+      const double *Q = b.Q + q0 + N * (lab + 1) + l;
+      double acc = 0.0;
+      for (int ip = 0; ip < np; ip++) acc += rsh[(size_t)ip * ld] * Q[(size_t)ip * ld];
+      R[e] = acc;
     }
   }
-  b.chi[w] = chi;
+  __syncwarp();
+  /* phase 2: the elements of the triple, 8 at a time */
+  if (valid) {
+    const int cdb = ecp_cd(lb), ne = ecp_cd(la) * cdb;
+    double *out = b.chi + b.clsElem[c] + (long long)(tri - b.clsFirst[c]) * ne;
+    const int D = t.ijkDim;
+    for (int pq = gl; pq < ne; pq += 8) {
+      const int i = pq / cdb, j = pq - i * cdb;
+      const int *ei = t.ijk + 3 * i, *ej = t.ijk + 3 * j;
+      const int lx = ei[0] + ej[0], ly = ei[1] + ej[1], lz = ei[2] + ej[2], N = lx + ly + lz;
+      const double *PM = t.poly2sph + (size_t)t.ijkIndex[lx * D * D + ly * D + lz] * t.pcols;
+      double chi = 0.0;
+      for (int l = N; l >= 0; l -= 2) {
+        const double *pm = PM + l * l, *r = R + chi_roff(N, l);
+        double f = 0.0;
+        for (int m = 0; m < 2 * l + 1; m++) f += pm[m] * r[m];
+        chi += f;
+      }
+      out[pq] = chi;
+    }
+  }
 }
 
 /* ---- shift to A/B-centred Cartesians, normalise, write blocks / accumulate matrix ---- */
@@ -1346,7 +1385,10 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     }
   }
   CK(cudaEventRecord(d->ev[7], d->s2));
-  k_chi<<<nblk(h->clsElem[nc], 128), 128, 0, d->s2>>>(t, B, h->clsElem[nc]);
+  { /* 8 lanes per triple; packed R[N][(l,m)] of the largest la+lb per group in shared memory */
+    const int labMax = 2 * d->maxLBS, rStride = (labMax + 1) * (labMax + 2) * (labMax + 3) / 6 + 1;
+    k_chi<<<nblk((long long)h->nTriples * 8, 128), 128, (size_t)16 * rStride * sizeof(double), d->s2>>>(t, B, rStride);
+  }
   CK(cudaEventRecord(d->ev[8], d->s2));
   launches += 2;
   /* type 2 */
