@@ -24,7 +24,7 @@ EXPORTS = [
     "libecp_b200_integrals_device", "libecp_b200_integrals_host", "libecp_b200_get_stats", "libecp_b200_screening",
     "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
     "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
-    "libecp_b200_set_serial_kernels", "libecp_b200_release_cache",
+    "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only",
 ]
 
 
@@ -205,6 +205,15 @@ class Handle:
         if rc:
             raise RuntimeError("not an ECP centre")
         return endl[:L], st, en, sk
+
+    def build_only(self):
+        """(ms, triples, batches) of the host batch builder alone"""
+        f = lib().libecp_b200_build_only
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+        n, nb = C.c_longlong(0), C.c_int(0)
+        ms = f(C.c_void_p(self.h), C.byref(n), C.byref(nb))
+        return float(ms), int(n.value), int(nb.value)
 
     def triple_list(self):
         n = lib().libecp_b200_triple_list(C.c_void_p(self.h), None, 0)

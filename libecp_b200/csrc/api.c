@@ -99,6 +99,7 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
   if (g_tables_only) { /* test hook: tables + builder without a device; every compute entry point fails */
     h->bb = ecp_batch_new(h->tab);
     h->bb2 = ecp_batch_new(h->tab);
+    ecp_batch_share_scratch(h->bb2, h->bb);
     return h;
   }
   int dev = g_device;
@@ -115,6 +116,7 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
   }
   h->bb = ecp_batch_new(h->tab);
   h->bb2 = ecp_batch_new(h->tab);
+  ecp_batch_share_scratch(h->bb2, h->bb);
   return h;
 }
 
@@ -180,7 +182,7 @@ static void build_job(BuildJob *j) {
   const double t0 = now_ms();
   if (j->h->dev) ecpdev_bind_thread(j->h->dev);
   j->took = ecp_batch_build(j->h->tab, j->h->geometry, j->centre, j->h->maxTriples, j->h->rank, j->h->world, j->keepCanon,
-                            j->bb);
+                            (j->flags & 2) != 0, j->bb);
   j->ms = now_ms() - t0;
   if (j->prefetch && j->took > 0 && j->h->dev) ecpdev_prefetch_batch(j->h->dev, &j->bb->b, j->flags, j->slot);
 }
@@ -458,7 +460,7 @@ long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap) {
   int centre = 0;
   if (h->empty) return 0;
   EcpBatchBuf *bb = ecp_batch_new(h->tab);
-  while (ecp_batch_build(h->tab, h->geometry, &centre, 1 << 20, h->rank, h->world, 1, bb) > 0)
+  while (ecp_batch_build(h->tab, h->geometry, &centre, 1 << 20, h->rank, h->world, 1, 1, bb) > 0)
     for (int k = 0; k < bb->nCanon; k++, n++)
       if (n < cap) {
         int *r = out + 7 * n;
@@ -467,6 +469,26 @@ long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap) {
       }
   ecp_batch_free(bb);
   return n;
+}
+
+/* host batch builder alone (no device work): wall ms of building every batch of one pass; for tuning / tests */
+double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches) {
+  long long n = 0;
+  int centre = 0, nb = 0;
+  if (triples) *triples = 0;
+  if (batches) *batches = 0;
+  if (h->empty) return 0.0;
+  EcpBatchBuf *bb = ecp_batch_new(h->tab);
+  const double t0 = now_ms();
+  while (ecp_batch_build(h->tab, h->geometry, &centre, h->maxTriples, h->rank, h->world, 0, 0, bb) > 0) {
+    n += bb->b.nTriples;
+    nb++;
+  }
+  const double ms = now_ms() - t0;
+  ecp_batch_free(bb);
+  if (triples) *triples = n;
+  if (batches) *batches = nb;
+  return ms;
 }
 
 int libecp_b200_debug_fetch(libECPHandle *h, const char *what, double *dst, long long n) {

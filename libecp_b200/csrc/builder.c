@@ -23,6 +23,7 @@ static int IJK(int l) { return (l + 1) * (l + 2) / 2; }
 typedef struct {
   int C, type, Lc, nSS, nAS;
   int *ssShell, *ssStart, *ssEnd, *ssAtom; /* ssAtom: local atom-slot index               */
+  unsigned char *ssL, *ssK, *ssOwn;        /* angular momentum, contraction depth, row owned by this rank */
   int *asAtom;
   double *asD;                             /* distance d_XC per local atom slot            */
   int *clsCount;                           /* executed triples per class                   */
@@ -34,6 +35,9 @@ typedef struct {
 struct BuilderScratch {
   CentreWork *cw;
   int ncw;
+  int refs;                 /* batch buffers sharing this scratch (ecp_batch_share_scratch)                    */
+  /* centres screened by the previous call that did not fit into its batch: cw[0..nleft) */
+  int nleft, leftCentre[1024], leftNext, leftRank, leftWorld;
 };
 
 EcpBatchBuf *ecp_batch_new(const EcpTables *t) {
@@ -50,13 +54,33 @@ EcpBatchBuf *ecp_batch_new(const EcpTables *t) {
 
 static void free_scratch(struct BuilderScratch *s) {
   if (!s) return;
+  if (--s->refs > 0) return;
   for (int i = 0; i < s->ncw; i++) {
     CentreWork *w = &s->cw[i];
     free(w->ssShell); free(w->ssStart); free(w->ssEnd); free(w->ssAtom); free(w->asAtom); free(w->asD);
+    free(w->ssL); free(w->ssK); free(w->ssOwn);
     free(w->clsCount); free(w->clsPairs);
   }
   free(s->cw);
   free(s);
+}
+
+static struct BuilderScratch *get_scratch(EcpBatchBuf *bb) {
+  if (!bb->scratch) {
+    struct BuilderScratch *S = calloc(1, sizeof(struct BuilderScratch));
+    S->refs = 1;
+    bb->scratch = S;
+  }
+  return (struct BuilderScratch *)bb->scratch;
+}
+/* the two batch buffers of a pipeline build alternately, never at the same time: with one scratch the centres the
+ * previous call screened beyond its batch are not screened again */
+void ecp_batch_share_scratch(EcpBatchBuf *dst, EcpBatchBuf *src) {
+  struct BuilderScratch *S = get_scratch(src);
+  if (dst->scratch == S) return;
+  free_scratch((struct BuilderScratch *)dst->scratch);
+  dst->scratch = S;
+  S->refs++;
 }
 
 void ecp_batch_free(EcpBatchBuf *bb) {
@@ -64,7 +88,7 @@ void ecp_batch_free(EcpBatchBuf *bb) {
   free(bb->asAtom); free(bb->asCentre); free(bb->asType); free(bb->asR); free(bb->asOmOff);
   free(bb->ssShell); free(bb->ssASlot); free(bb->ssStart); free(bb->ssEnd); free(bb->ssFOff);
   ecpdev_pinned_free(bb->trA); ecpdev_pinned_free(bb->trB); ecpdev_pinned_free(bb->trOut); ecpdev_pinned_free(bb->trPair);
-  ecpdev_pinned_free(bb->prTriple);
+ 
   free(bb->clsFirst); free(bb->clsWork); free(bb->clsElem); free(bb->clsOutElem); free(bb->clsPairBase); free(bb->clsQBase);
   free(bb->cnA); free(bb->cnS1); free(bb->cnB); free(bb->cnS2); free(bb->cnC); free(bb->cnLa); free(bb->cnLb);
   free(bb->cnOut);
@@ -123,17 +147,13 @@ static double dist3(const double *a, const double *b) { /* src/util.c:109-116 */
 static void centre_screen(const EcpTables *t, const double *geometry, int C, int rank, int world, CentreWork *w) {
   const EcpHostTables *v = &t->v;
   const int nat = v->nrAtoms, nc = v->nClasses, nsh = v->nrShells;
-  if (w->cap < nsh) {
-    w->ssShell = realloc(w->ssShell, nsh * sizeof(int));
-    w->ssStart = realloc(w->ssStart, nsh * sizeof(int));
-    w->ssEnd = realloc(w->ssEnd, nsh * sizeof(int));
-    w->ssAtom = realloc(w->ssAtom, nsh * sizeof(int));
+  if (!w->asAtom) { /* per-atom and per-class areas have fixed sizes; the per-slot ones grow with the slots found */
     w->asAtom = realloc(w->asAtom, (nat + 1) * sizeof(int));
     w->asD = realloc(w->asD, (nat + 1) * sizeof(double));
     w->clsCount = realloc(w->clsCount, (nc + 1) * sizeof(int));
     w->clsPairs = realloc(w->clsPairs, (nc + 1) * sizeof(long long));
-    w->cap = nsh;
   }
+  (void)nsh;
   w->C = C;
   w->type = t->atomType[C];
   const EcpType *T = &t->types[w->type];
@@ -160,10 +180,23 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
         w->asD[aslot] = d;
         omSize += (long long)(Lc + t->atomMaxL[X]) * Lc * Lc * CD(t->atomMaxL[X]);
       }
+      if (nSS == w->cap) {
+        w->cap = w->cap ? 2 * w->cap : 512;
+        w->ssShell = realloc(w->ssShell, w->cap * sizeof(int));
+        w->ssStart = realloc(w->ssStart, w->cap * sizeof(int));
+        w->ssEnd = realloc(w->ssEnd, w->cap * sizeof(int));
+        w->ssAtom = realloc(w->ssAtom, w->cap * sizeof(int));
+        w->ssL = realloc(w->ssL, w->cap);
+        w->ssK = realloc(w->ssK, w->cap);
+        w->ssOwn = realloc(w->ssOwn, w->cap);
+      }
       w->ssShell[nSS] = s;
       w->ssStart[nSS] = st;
       w->ssEnd[nSS] = en;
       w->ssAtom[nSS] = aslot;
+      w->ssL[nSS] = (unsigned char)v->shellL[s];
+      w->ssK[nSS] = (unsigned char)v->shellK[s];
+      w->ssOwn[nSS] = (unsigned char)(world <= 1 || ecp_pair_owner(s, s, world) == rank); /* row ownership */
       fRows += Lc + t->shellL[s];
       nSS++;
     }
@@ -176,22 +209,28 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
   memset(w->clsCount, 0, (nc + 1) * sizeof(int));
   memset(w->clsPairs, 0, (nc + 1) * sizeof(long long));
   long long nTri = 0, outSize = 0;
-  for (int a = 0; a < nSS; a++) {
-    const int sa = w->ssShell[a], la = v->shellL[sa], Ka = v->shellK[sa];
-    const int sta = w->ssStart[a], ena = w->ssEnd[a];
-    const int *lut = &t->clsLookup[la][0][0];
-    if (world > 1 && ecp_pair_owner(sa, sa, world) != rank) continue; /* row ownership */
-    for (int b = a; b < nSS; b++) {
-      const int gs = sta > w->ssStart[b] ? sta : w->ssStart[b];
-      const int ge = ena > w->ssEnd[b] ? ena : w->ssEnd[b];
-      if (!(gs < ge)) continue;
-      const int sb = w->ssShell[b];
-      const int lb = v->shellL[sb];
-      const int c = lut[lb * (ECP_MAX_LECP + 1) + Lc];
-      w->clsCount[c]++;
-      w->clsPairs[c] += Ka * v->shellK[sb];
-      outSize += 2 * IJK(la) * IJK(lb);
-      nTri++;
+  {
+    const int *st = w->ssStart, *en = w->ssEnd;
+    const unsigned char *sl = w->ssL, *sk = w->ssK;
+    for (int a = 0; a < nSS; a++) {
+      if (!w->ssOwn[a]) continue;
+      const int la = sl[a], Ka = sk[a], sta = st[a], ena = en[a];
+      int cnt[ECP_MAX_LBS + 1] = {0}, prs[ECP_MAX_LBS + 1] = {0};
+      for (int b = a; b < nSS; b++) {
+        const int gs = sta > st[b] ? sta : st[b];
+        const int ge = ena > en[b] ? ena : en[b];
+        const int ok = gs < ge; /* src/libecp.c:344 */
+        cnt[sl[b]] += ok;
+        prs[sl[b]] += ok ? sk[b] : 0;
+      }
+      for (int lb = 0; lb <= v->maxLBS; lb++) {
+        if (!cnt[lb]) continue;
+        const int c = t->clsLookup[la][lb][Lc];
+        w->clsCount[c] += cnt[lb];
+        w->clsPairs[c] += (long long)Ka * prs[lb];
+        outSize += 2LL * IJK(la) * IJK(lb) * cnt[lb];
+        nTri += cnt[lb];
+      }
     }
   }
   w->nTri = nTri;
@@ -214,33 +253,50 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
   } while (0)
 
 int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
-                    int keepCanon, EcpBatchBuf *bb) {
+                    int keepCanon, int wantOut, EcpBatchBuf *bb) {
+  const int needOut = wantOut || keepCanon; /* block offsets are only needed when the callback blocks are produced */
   const EcpHostTables *v = &t->v;
   const int nat = v->nrAtoms, nc = v->nClasses;
-  struct BuilderScratch *S = (struct BuilderScratch *)bb->scratch;
-  if (!S) bb->scratch = S = calloc(1, sizeof(struct BuilderScratch));
+  struct BuilderScratch *S = get_scratch(bb);
   int nthreads = 1;
 #ifdef _OPENMP
   nthreads = omp_get_max_threads();
 #endif
-  /* candidate window of centres: screened in parallel, then as many as fit into maxTriples are taken */
-  const int window = nthreads * 4 > 16 ? nthreads * 4 : 16;
+  /* candidate centres are screened in parallel, a round of a few per thread at a time, until the batch is full
+   * (a rank that owns 1/8 of the rows needs 8x the centres for the same batch size); then as many as fit into
+   * maxTriples are taken.  Screening results of centres that do not fit are recomputed by the next call. */
+  const int round = nthreads * 2 > 8 ? nthreads * 2 : 8;
   int cand[1024], ncand = 0, C = *centre;
-  for (; C < nat && ncand < window && ncand < 1024; C++)
-    if (t->atomType[C] >= 0) cand[ncand++] = C;
+  long long screened = 0;
+  CentreWork *cw = S->cw;
+  if (S->nleft > 0 && S->leftCentre[0] == *centre && S->leftRank == rank && S->leftWorld == world) {
+    for (int i = 0; i < S->nleft; i++) { /* screened by the previous call */
+      cand[ncand++] = S->leftCentre[i];
+      screened += cw[i].nTri;
+    }
+    C = S->leftNext;
+  }
+  S->nleft = 0;
+  while (C < nat && ncand < 1024 && screened < maxTriples) {
+    const int first = ncand;
+    for (; C < nat && ncand < first + round && ncand < 1024; C++)
+      if (t->atomType[C] >= 0) cand[ncand++] = C;
+    if (ncand == first) break;
+    if (S->ncw < ncand) {
+      S->cw = realloc(S->cw, ncand * sizeof(CentreWork));
+      memset(S->cw + S->ncw, 0, (ncand - S->ncw) * sizeof(CentreWork));
+      S->ncw = ncand;
+    }
+    cw = S->cw;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = first; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i]);
+    for (int i = first; i < ncand; i++) screened += cw[i].nTri;
+  }
   if (ncand == 0) {
     *centre = nat;
     bb->b.nTriples = 0;
     return 0;
   }
-  if (S->ncw < ncand) {
-    S->cw = realloc(S->cw, ncand * sizeof(CentreWork));
-    memset(S->cw + S->ncw, 0, (ncand - S->ncw) * sizeof(CentreWork));
-    S->ncw = ncand;
-  }
-  CentreWork *cw = S->cw;
-#pragma omp parallel for schedule(dynamic, 1)
-  for (int i = 0; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i]);
 
   /* ---- phase (b): how many centres, and where everything goes ---- */
   int ntake = 0;
@@ -307,10 +363,9 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   ENSURE(bb->ssFOff, bb->capSS, nSS, int64_t);
   if (nSS > bb->capSS) bb->capSS = (int)nSS + 16;
   ENSURE_PIN(bb->trA, bb->capTR, nTR, int); ENSURE_PIN(bb->trB, bb->capTR, nTR, int);
-  ENSURE_PIN(bb->trOut, bb->capTR, nTR, int64_t); ENSURE_PIN(bb->trPair, bb->capTR, nTR, int64_t);
+  ENSURE_PIN(bb->trOut, bb->capOut, needOut ? nTR : 0, int64_t); ENSURE_PIN(bb->trPair, bb->capTR, nTR, int64_t);
+  if (needOut && nTR > bb->capOut) bb->capOut = (int)(nTR + nTR / 4) + 16;
   if (nTR > bb->capTR) bb->capTR = (int)(nTR + nTR / 4) + 16;
-  ENSURE_PIN(bb->prTriple, bb->capPR, nPairs, int);
-  if (nPairs > bb->capPR) bb->capPR = (int)(nPairs + nPairs / 4) + 16;
   if (keepCanon) {
     ENSURE(bb->cnA, bb->capCanon, nTR, int); ENSURE(bb->cnS1, bb->capCanon, nTR, int);
     ENSURE(bb->cnB, bb->capCanon, nTR, int); ENSURE(bb->cnS2, bb->capCanon, nTR, int);
@@ -353,6 +408,13 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
     /* canonical enumeration: A, B>=A, s1, s2 (reference src/libecp.c:278-320); slots of one atom are contiguous */
     long long *lpos = calloc(2 * (nc + 1), sizeof(long long)), *lpair = lpos + nc + 1;
     long long out = outBase[i], cn = cnBase[i];
+    const int *st = w->ssStart, *en = w->ssEnd;
+    const unsigned char *sl = w->ssL, *sk = w->ssK;
+    const int sbase = (int)ssBase[i];
+    for (int c = 0; c < nc; c++) {
+      lpos[c] = posCC[(size_t)c * ntake + i];
+      lpair[c] = pairCC[(size_t)c * ntake + i];
+    }
     for (int ia = 0; ia < w->nSS;) {
       int ia1 = ia;
       while (ia1 < w->nSS && w->ssAtom[ia1] == w->ssAtom[ia]) ia1++;
@@ -360,37 +422,37 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
         int ib1 = ib;
         while (ib1 < w->nSS && w->ssAtom[ib1] == w->ssAtom[ib]) ib1++;
         for (int a = ia; a < ia1; a++) {
-          const int sa = w->ssShell[a], la = v->shellL[sa];
-          if (world > 1 && ecp_pair_owner(sa, sa, world) != rank) continue; /* row ownership */
+          if (!w->ssOwn[a]) continue; /* row ownership */
+          const int la = sl[a], Ka = sk[a], sta = st[a], ena = en[a];
+          const int *lut = &t->clsLookup[la][0][0] + Lc;
           for (int b = (ib == ia ? a : ib); b < ib1; b++) {
-            const int gs = w->ssStart[a] > w->ssStart[b] ? w->ssStart[a] : w->ssStart[b];
-            const int ge = w->ssEnd[a] > w->ssEnd[b] ? w->ssEnd[a] : w->ssEnd[b];
+            const int gs = sta > st[b] ? sta : st[b];
+            const int ge = ena > en[b] ? ena : en[b];
             if (!(gs < ge)) continue; /* src/libecp.c:344, identical for both types */
-            const int sb = w->ssShell[b];
-            const int lb = v->shellL[sb];
-            const int c = t->clsLookup[la][lb][Lc];
-            const long long p = posCC[(size_t)c * ntake + i] + lpos[c]++;
-            const long long pr = pairCC[(size_t)c * ntake + i] + lpair[c];
-            const int np = v->shellK[sa] * v->shellK[sb];
-            lpair[c] += np;
-            bb->trA[p] = (int)(ssBase[i] + a);
-            bb->trB[p] = (int)(ssBase[i] + b);
-            bb->trOut[p] = out;
-            bb->trPair[p] = pr;
-            for (int k = 0; k < np; k++) bb->prTriple[pr + k] = (int)p;
-            if (keepCanon) {
-              const int A = w->asAtom[w->ssAtom[a]], B = w->asAtom[w->ssAtom[b]];
-              bb->cnA[cn] = A;
-              bb->cnS1[cn] = sa - t->atomFirstShell[A];
-              bb->cnB[cn] = B;
-              bb->cnS2[cn] = sb - t->atomFirstShell[B];
-              bb->cnC[cn] = w->C;
-              bb->cnLa[cn] = la;
-              bb->cnLb[cn] = lb;
-              bb->cnOut[cn] = out;
-              cn++;
+            const int lb = sl[b];
+            const int c = lut[lb * (ECP_MAX_LECP + 1)];
+            const long long p = lpos[c]++;
+            bb->trA[p] = sbase + a;
+            bb->trB[p] = sbase + b;
+            bb->trPair[p] = lpair[c];
+            lpair[c] += Ka * sk[b];
+            if (needOut) {
+              bb->trOut[p] = out;
+              if (keepCanon) {
+                const int sa = w->ssShell[a], sb = w->ssShell[b];
+                const int A = w->asAtom[w->ssAtom[a]], B = w->asAtom[w->ssAtom[b]];
+                bb->cnA[cn] = A;
+                bb->cnS1[cn] = sa - t->atomFirstShell[A];
+                bb->cnB[cn] = B;
+                bb->cnS2[cn] = sb - t->atomFirstShell[B];
+                bb->cnC[cn] = w->C;
+                bb->cnLa[cn] = la;
+                bb->cnLb[cn] = lb;
+                bb->cnOut[cn] = out;
+                cn++;
+              }
+              out += 2 * (long long)IJK(la) * IJK(lb);
             }
-            out += 2 * (long long)IJK(la) * IJK(lb);
           }
         }
         ib = ib1;
@@ -401,6 +463,18 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   }
   free(asBase); free(ssBase); free(omBase); free(fBase); free(outBase); free(cnBase);
   free(posCC); free(pairCC); free(tBase); free(gBase); free(pairBase); free(qBase);
+
+  /* the screened centres that did not fit stay at the front of the scratch for the next call */
+  for (int i = ntake; i < ncand; i++) {
+    const CentreWork tmp = cw[i - ntake];
+    cw[i - ntake] = cw[i];
+    cw[i] = tmp;
+    S->leftCentre[i - ntake] = cand[i];
+  }
+  S->nleft = ncand - ntake;
+  S->leftNext = C;
+  S->leftRank = rank;
+  S->leftWorld = world;
 
   EcpBatch *b = &bb->b;
   b->nASlots = (int)nAS;
@@ -428,7 +502,6 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   b->nPairs = nPairs;
   b->qTotal = qTot;
   b->rshTotal = qTot;
-  b->prTriple = bb->prTriple;
   b->clsFirst = bb->clsFirst;
   b->clsWork = bb->clsWork;
   b->clsElem = bb->clsElem;

@@ -17,10 +17,9 @@ typedef struct {
   int64_t *ssFOff;
   int *trA, *trB;
   int64_t *trOut, *trPair;
-  int *prTriple;
   int *clsFirst;
   int64_t *clsWork, *clsElem, *clsOutElem, *clsPairBase, *clsQBase;
-  int capAS, capSS, capTR, capPR;
+  int capAS, capSS, capTR, capOut;
   /* canonical (reference loop order) list of the executed triples of this batch, for callback replay */
   int nCanon, capCanon;
   int *cnA, *cnS1, *cnB, *cnS2, *cnC, *cnLa, *cnLb;
@@ -32,13 +31,15 @@ typedef struct {
 
 EcpBatchBuf *ecp_batch_new(const EcpTables *t);
 void ecp_batch_free(EcpBatchBuf *bb);
+/* let dst use the per-centre work areas of src (two buffers that build alternately) */
+void ecp_batch_share_scratch(EcpBatchBuf *dst, EcpBatchBuf *src);
 
 /* Build one batch starting at atom index *centre (advanced past the centres consumed).  Stops adding centres
  * once the batch holds >= maxTriples triples (always takes at least one centre).  Only shell pairs owned by
- * (rank, world) are emitted (world = 1: everything).  keepCanon != 0 records the canonical list.
+ * (rank, world) are emitted (world = 1: everything).  keepCanon != 0 records the canonical list; wantOut != 0 fills the block offsets trOut.
  * Returns the number of centres consumed (0 = no ECP centre left). */
 int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
-                    int keepCanon, EcpBatchBuf *bb);
+                    int keepCanon, int wantOut, EcpBatchBuf *bb);
 
 /* exposed for tests: window of one (centre type, shell radius, distance) (reference src/type2.c:148-180) */
 void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip);

@@ -41,7 +41,7 @@ static char g_err[512] = "";
 /* device-side view of all tables of a handle + the current batch */
 struct DevT {
   int maxLECP, maxLBS, maxLambda, tmDim, ijkDim, besselStride, nU, pcols;
-  int largeSlots, largeLevels, nClasses, omD2, omD3;
+  int largeSlots, largeLevels, largeOrder, nClasses, omD2, omD3;
   double tolerance, accuracy, lnAcc1, lnAcc2;
   EcpSmallMeta sm;
   const double *fac, *dfac, *poly2sph, *omega, *binom;
@@ -49,7 +49,7 @@ struct DevT {
   const int *shTermOff, *shTermP, *shTermD;
   const double *shTermBin;
   const int *ijk, *ijkIndex;
-  const double *small_r, *small_w, *large_x, *large_w;
+  const double *small_r, *small_w, *large_x, *large_w, *large_xo;
   const int16_t *small_oidx;
   const unsigned char *small_jL, *small_jR; /* first in-window pair per (level, start) / (level, end), ecp_math.h */
   const double *besselT, *besselC;
@@ -82,8 +82,15 @@ struct DevB {
   int *tflags, *items;
   T1Rec *t1rec; /* per primitive pair, written by k_t1prep (ecp_type1.cuh) */
   TriRec *trirec; /* per triple, written by k_triprep */
+  unsigned long long *dbg; /* LIBECP_B200_TAILS: per-block (start, end) globaltimer of the persistent kernels, else NULL */
   int *counters; /* [0] nItems [1] work counter [2] err1 [3] err2 [4] nFastFail [5] nType1Fail [6] stale [7] work2 */
 };
+__device__ __forceinline__ unsigned long long ecp_gtimer() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+  return v;
+}
+#define DBG_STRIDE 8192 /* blocks per probed launch */
 #define RSHX_STRIDE 121
 #define USPX_STRIDE 216
 
@@ -174,36 +181,53 @@ __global__ void k_omegaX(DevT t, DevB b) {
   }
 }
 
-/* ---- F_lambda(r_n) per shell slot; one block of 384 threads per slot ---- */
+/* ---- F_lambda(r_n) per shell slot; one block of 384 threads per slot ----
+ * The Bessel order bound lmaxA = L - 1 + l_shell is uniform over the block: the body is instantiated per value, so the
+ * unrolled Taylor recurrence of ecp_bessel carries no masked-off orders (with the single KM = 10 instantiation an s
+ * shell under an L = 2 potential, lmaxA = 1, paid for 16 orders). */
+template <int LM>
+__device__ __forceinline__ void ftab_body(const DevT &t, const DevB &b, int ss, int k, int sh, double dAC) {
+  const int oi = t.small_oidx[k];
+  double acc[LM + 1];
+#pragma unroll
+  for (int i = 0; i <= LM; i++) acc[i] = 0.0;
+  if (oi >= b.ssStart[ss] && oi < b.ssEnd[ss]) { /* exclusive end: src/type2.c:292 */
+    const double r = t.small_r[k];
+    const int p0 = t.shellPrim[sh], np = t.shellK[sh];
+    for (int p = 0; p < np; p++) {
+      const double zeta = t.primA[p0 + p], da = t.primD[p0 + p];
+      double K[LM + 1];
+      ecp_bessel<LM>(t.besselT, t.besselStride, t.besselC, LM, 2.0 * zeta * dAC * r, K);
+      double e = dAC - r;
+      e = exp(-zeta * e * e);
+#pragma unroll
+      for (int i = 0; i <= LM; i++) acc[i] += da * K[i] * e;
+    }
+  }
+  /* slot-major: F[slot][lambda], lambda = 0..lmaxA (the rows a fast-path quadrature multiplies sit side by side) */
+  double *F = b.F + (size_t)b.ssFOff[ss] * ECP_SMALL_SLOTS + (size_t)k * (LM + 1);
+#pragma unroll
+  for (int i = 0; i <= LM; i++) F[i] = acc[i];
+}
 __global__ void __launch_bounds__(ECP_SMALL_SLOTS) k_Ftab(DevT t, DevB b) {
   const int ss = blockIdx.x, k = threadIdx.x;
   const int sh = b.ssShell[ss], as = b.ssASlot[ss];
   const int Lc = t.typeL[b.asType[as]];
   const int lmaxA = Lc - 1 + t.shellL[sh];
   const double dAC = b.asR[4 * as + 3];
-  const int oi = t.small_oidx[k];
-  double acc[KM + 1];
-#pragma unroll
-  for (int i = 0; i <= KM; i++) acc[i] = 0.0;
-  if (oi >= b.ssStart[ss] && oi < b.ssEnd[ss]) { /* exclusive end: src/type2.c:292 */
-    const double r = t.small_r[k];
-    const int p0 = t.shellPrim[sh], np = t.shellK[sh];
-    for (int p = 0; p < np; p++) {
-      const double zeta = t.primA[p0 + p], da = t.primD[p0 + p];
-      double K[KM + 1];
-      ecp_bessel<KM>(t.besselT, t.besselStride, t.besselC, lmaxA, 2.0 * zeta * dAC * r, K);
-      double e = dAC - r;
-      e = exp(-zeta * e * e);
-#pragma unroll
-      for (int i = 0; i <= KM; i++)
-        if (i <= lmaxA) acc[i] += da * K[i] * e;
-    }
+  switch (lmaxA) {
+    case 0: ftab_body<0>(t, b, ss, k, sh, dAC); break;
+    case 1: ftab_body<1>(t, b, ss, k, sh, dAC); break;
+    case 2: ftab_body<2>(t, b, ss, k, sh, dAC); break;
+    case 3: ftab_body<3>(t, b, ss, k, sh, dAC); break;
+    case 4: ftab_body<4>(t, b, ss, k, sh, dAC); break;
+    case 5: ftab_body<5>(t, b, ss, k, sh, dAC); break;
+    case 6: ftab_body<6>(t, b, ss, k, sh, dAC); break;
+    case 7: ftab_body<7>(t, b, ss, k, sh, dAC); break;
+    case 8: ftab_body<8>(t, b, ss, k, sh, dAC); break;
+    case 9: ftab_body<9>(t, b, ss, k, sh, dAC); break;
+    default: ftab_body<KM>(t, b, ss, k, sh, dAC); break;
   }
-  /* slot-major: F[slot][lambda], lambda = 0..lmaxA (the rows a fast-path quadrature multiplies sit side by side) */
-  double *F = b.F + (size_t)b.ssFOff[ss] * ECP_SMALL_SLOTS + (size_t)k * (lmaxA + 1);
-#pragma unroll
-  for (int i = 0; i <= KM; i++)
-    if (i <= lmaxA) F[i] = acc[i];
 }
 
 /* ---- type-2 fast path: one thread per used quadrature, two densely packed launches ----
@@ -304,6 +328,88 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
   fast_store(b, w, rc, res, f.tri, f.l);
 }
 
+/* ---- large grid (PSM92, level-major slots): which points of a level can pass the exponent gate ----
+ * Both large-grid integrands carry exp(e(r)) with e(r) = a r^2 + b r + c0, a < 0, and a point is tabulated only if
+ * e >= ln(acc) (src/type1.c:163, src/type2.c:479-490): the live points are those with r between the two roots of
+ * e(r) = ln(acc).  lg_live_range returns a range of ORIGINAL grid indices that contains all of them (roots widened,
+ * one index of slack on each side; every point still takes the exact gate).  Within level lev the left points are the
+ * original indices (2j+1) off - 1, ascending in j, and the right points their mirror images (src/gc_integrators.c:
+ * 58-66), so the candidates of a level are two runs of pairs, in closed form: the persistent groups visit 8 candidates
+ * per step instead of 8 consecutive slots (on the FM06-mapped grid [P-7s, P+9s] at most 73 % of the slots are live,
+ * typically far fewer). */
+struct LgRange {
+  int ilo, ihi; /* inclusive; ilo > ihi: no live point */
+};
+__device__ __forceinline__ LgRange lg_live_range(const DevT &t, double a, double b, double cmln, double i1, double i2) {
+  /* a r^2 + b r + cmln >= 0, cmln = c0 - ln(acc) */
+  LgRange R;
+  const double bb = b * b, ac4 = 4.0 * a * cmln;
+  double disc = bb - ac4;
+  if (!(disc >= -1e-9 * (bb + fabs(ac4)))) {
+    R.ilo = 1;
+    R.ihi = 0;
+    return R;
+  }
+  disc = disc > 0.0 ? disc : 0.0;
+  const double sq = sqrt(disc) * (1.0 + 1e-9) + 1e-9 * fabs(b);
+  const double r1 = (-b + sq) / (2.0 * a), r2 = (-b - sq) / (2.0 * a); /* a < 0: r1 <= r2 */
+  const double m = 1e-9 * (fabs(r1) + fabs(r2) + 1.0);
+  const double x1 = (r1 - m - i2) / i1, x2 = (r2 + m - i2) / i1;
+  const double *xo = t.large_xo;
+  const int n = t.largeOrder;
+  int lo = 0, hi = n; /* first index with xo >= x1 */
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (xo[mid] < x1)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  R.ilo = lo - 1;
+  lo = 0;
+  hi = n; /* first index with xo > x2 */
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (xo[mid] <= x2)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  R.ihi = lo;
+  if (R.ilo < 0) R.ilo = 0;
+  if (R.ihi > n - 1) R.ihi = n - 1;
+  return R;
+}
+struct LgLevel {
+  int jL, nL, jR, nLive; /* left points of the pairs [jL, jL + nL), right points of the pairs [jR, jR + nLive - nL) */
+};
+__device__ __forceinline__ void lg_pair_run(int ilo, int ihi, int off, int npair, int *j0, int *n) {
+  /* pairs j with ilo <= (2j+1) off - 1 <= ihi */
+  const int a = ilo + 1 - off, b = ihi + 1 - off, o2 = 2 * off;
+  int lo = a <= 0 ? 0 : (a + o2 - 1) / o2;
+  int hi = b < 0 ? -1 : b / o2;
+  if (hi > npair - 1) hi = npair - 1;
+  *j0 = lo;
+  *n = hi >= lo ? hi - lo + 1 : 0;
+}
+__device__ __forceinline__ LgLevel lg_level(const DevT &t, LgRange R, int lev) {
+  LgLevel L;
+  const int off = t.largeSlots >> (lev + 1), npair = 1 << (lev - 1);
+  int nR;
+  if (R.ilo > R.ihi) {
+    L.jL = L.jR = L.nL = L.nLive = 0;
+    return L;
+  }
+  lg_pair_run(R.ilo, R.ihi, off, npair, &L.jL, &L.nL);
+  lg_pair_run(t.largeOrder - 1 - R.ihi, t.largeOrder - 1 - R.ilo, off, npair, &L.jR, &nR);
+  L.nLive = L.nL + nR;
+  return L;
+}
+/* slot of candidate m of the level (1 = the pad slot: nothing to do) */
+__device__ __forceinline__ int lg_slot(const LgLevel &L, int lev, int m) {
+  return (m < L.nL) ? (1 << lev) + 2 * (L.jL + m) : ((m < L.nLive) ? (1 << lev) + 2 * (L.jR + m - L.nL) + 1 : 1);
+}
+
 #include "ecp_fallback.cuh"
 
 /* ---- per triple: everything the element-parallel kernels (link, chi, shift) would otherwise chase through
@@ -342,6 +448,8 @@ __global__ void k_triprep(DevT t, DevB b) {
   r.colAO = t.shellAO[shb];
   r.pad = 0;
   b.trirec[tri] = r;
+  int *pt = const_cast<int *>(b.prTriple) + b.trPair[tri]; /* owning triple of each primitive pair */
+  for (int k = 0; k < r.np; k++) pt[k] = tri;
 }
 
 /* ---- link: gamma[p][q], one thread per element ---- */
@@ -399,7 +507,7 @@ __global__ void __launch_bounds__(128) k_link(DevT t, DevB b, int c) {
 #pragma unroll
       for (int i = 0; i < NA; i++)
 #pragma unroll
-        for (int j = 0; j < NB; j++) f[i][j] += a[i] * bb[j]; /* rows/columns beyond n1/n2 are never read */
+        for (int j = 0; j < NB; j++) f[i][j] = fma(a[i], bb[j], f[i][j]); /* rows/columns beyond n1/n2 are never read */
       pa += incA1;
       pb += incB1;
     }
@@ -411,7 +519,7 @@ __global__ void __launch_bounds__(128) k_link(DevT t, DevB b, int c) {
       for (int j = 0; j < NB; j++)
         if (i < n1 && j < n2) {
           const int k = ql[(2 * i * d2 + 2 * j) * d3];
-          if (k >= 0) tmp += f[i][j] * T[k]; /* k < 0: angular factor identically zero */
+          if (k >= 0) tmp = fma(f[i][j], T[k], tmp); /* k < 0: angular factor identically zero */
         }
     g += tmp;
   }
@@ -507,7 +615,7 @@ __global__ void __launch_bounds__(128) k_chi(DevT t, DevB b, int rStride) {
       const double *rsh = b.rshP + q0 + l * l + rem;
       const double *Q = b.Q + q0 + N * (lab + 1) + l;
       double acc = 0.0;
-      for (int ip = 0; ip < np; ip++) acc += rsh[(size_t)ip * ld] * Q[(size_t)ip * ld];
+      for (int ip = 0; ip < np; ip++) acc = fma(rsh[(size_t)ip * ld], Q[(size_t)ip * ld], acc);
       R[e] = acc;
     }
   }
@@ -526,7 +634,7 @@ __global__ void __launch_bounds__(128) k_chi(DevT t, DevB b, int rStride) {
       for (int l = N; l >= 0; l -= 2) {
         const double *pm = PM + l * l, *r = R + chi_roff(N, l);
         double f = 0.0;
-        for (int m = 0; m < 2 * l + 1; m++) f += pm[m] * r[m];
+        for (int m = 0; m < 2 * l + 1; m++) f = fma(pm[m], r[m], f);
         chi += f;
       }
       out[pq] = chi;
@@ -598,6 +706,8 @@ struct EcpDev {
   long long survCapEnv; /* LIBECP_B200_SURVCAP: survivor-list capacity override (tests of the overflow path) */
   Buf t1list, t1mask, t1count, t1work, t1rec, trirec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
+  Buf dbgBuf;
+  int tails; /* LIBECP_B200_TAILS */
   int fbblock, fbocc, fbminb; /* tuning knobs of the fallback kernel: LIBECP_B200_FBBLOCK threads, _FBOCC blocks per SM cap, _FBMINB */
   int t1block;                /* LIBECP_B200_T1BLOCK = 32/64/96/128 threads per block of the type-1 kernels */
 };
@@ -711,6 +821,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&d->evUp[i], cudaEventDisableTiming);
   d->s2 = d->s2real;
   d->serial = getenv("LIBECP_B200_SERIAL") != NULL;
+  d->tails = getenv("LIBECP_B200_TAILS") != NULL;
   {
     const char *e = getenv("LIBECP_B200_FASTLIM");
     d->fastLim = e ? atoi(e) : 4;
@@ -739,7 +850,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   DevT &t = d->t;
   t.maxLECP = h->maxLECP; t.maxLBS = h->maxLBS; t.maxLambda = h->maxLambda; t.tmDim = h->tmDim; t.ijkDim = h->ijkDim;
   t.besselStride = h->besselStride; t.nU = h->nU; t.pcols = (h->tmDim + 1) * (h->tmDim + 1);
-  t.largeSlots = h->largeSlots; t.largeLevels = h->largeLevels; t.nClasses = h->nClasses;
+  t.largeSlots = h->largeSlots; t.largeLevels = h->largeLevels; t.largeOrder = h->largeOrder; t.nClasses = h->nClasses;
   t.omD2 = (h->maxLambda + 1) * (h->maxLambda + 1);
   t.omD3 = (h->maxAlpha + 1) * (h->maxAlpha + 2) * (h->maxAlpha + 3) / 6;
   t.tolerance = h->tolerance; t.accuracy = h->accuracy; t.lnAcc1 = h->lnAccuracy1; t.lnAcc2 = h->lnAccuracy2;
@@ -782,6 +893,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   }
   t.large_x = upload_const(d, h->large_x, h->largeSlots);
   t.large_w = upload_const(d, h->large_w, h->largeSlots);
+  t.large_xo = upload_const(d, h->large_xo, h->largeOrder);
   t.besselT = upload_const(d, h->besselT, (size_t)1601 * h->besselStride);
   t.besselC = upload_const(d, h->besselC, h->besselLMax + 1);
   t.shellL = upload_const(d, h->shellL, h->nrShells);
@@ -1176,7 +1288,10 @@ static int upload_set(EcpDev *d, const EcpBatch *h, int flags, int slot, cudaStr
   UP(trB, h->trB, h->nTriples, int);
   if (flags & 2) UP(trOut, (const long long *)h->trOut, h->nTriples, long long);
   UP(trPair, (const long long *)h->trPair, h->nTriples, long long);
-  UP(prTriple, h->prTriple, h->nPairs, int);
+  { /* pair -> triple map: filled on the device by k_triprep */
+    int rc_ = ensure(&u.prTriple, ((size_t)h->nPairs + 1) * sizeof(int));
+    if (rc_) return rc_;
+  }
   UP(clsFirst, h->clsFirst, nc + 1, int);
   UP(clsWork, (const long long *)h->clsWork, nc + 1, long long);
   UP(clsElem, (const long long *)h->clsElem, nc + 1, long long);
@@ -1328,6 +1443,13 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     B.trirec = (TriRec *)d->trirec.p;
     d->launchSeq = 0;
   }
+  B.dbg = NULL;
+  if (d->tails) {
+    int rc_ = ensure(&d->dbgBuf, (size_t)16 * DBG_STRIDE * 2 * sizeof(unsigned long long));
+    if (rc_) return rc_;
+    CK(cudaMemsetAsync(d->dbgBuf.p, 0, (size_t)16 * DBG_STRIDE * 2 * sizeof(unsigned long long), d->s1));
+    B.dbg = (unsigned long long *)d->dbgBuf.p;
+  }
   if ((flags & 1) && !d->matrix) {
     int rc = ecpdev_matrix_begin(d, NULL, -1);
     if (rc) return rc;
@@ -1475,6 +1597,29 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   const double tr2 = omp_get_wtime();
   CK(cudaStreamSynchronize(d->s1));
   CK(cudaStreamSynchronize(d->s2));
+  if (d->tails) { /* how long do the persistent kernels run with most of their blocks already gone? */
+    unsigned long long *hb = (unsigned long long *)malloc((size_t)16 * DBG_STRIDE * 2 * sizeof(unsigned long long));
+    cudaMemcpy(hb, d->dbgBuf.p, (size_t)16 * DBG_STRIDE * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    for (int k = 0; k < 16; k++) {
+      unsigned long long t0 = ~0ull, t1 = 0;
+      int nb = 0;
+      unsigned long long *e = hb + (size_t)k * DBG_STRIDE * 2;
+      static unsigned long long ends[DBG_STRIDE];
+      for (int i = 0; i < DBG_STRIDE; i++)
+        if (e[2 * i + 1]) {
+          if (e[2 * i] < t0) t0 = e[2 * i];
+          if (e[2 * i + 1] > t1) t1 = e[2 * i + 1];
+          ends[nb++] = e[2 * i + 1];
+        }
+      if (!nb) continue;
+      /* time-integrated fraction of blocks still running = mean(end - t0) / (t1 - t0) */
+      double sum = 0;
+      for (int i = 0; i < nb; i++) sum += (double)(ends[i] - t0);
+      fprintf(stderr, "[libecp_b200]   tails: kernel %2d blocks %5d span %8.1f us, mean block residency %.3f of the span\n", k, nb,
+              (t1 - t0) * 1e-3, sum / nb / (double)(t1 - t0));
+    }
+    free(hb);
+  }
   if (trace)
     fprintf(stderr, "[libecp_b200]   run_batch: alloc+H2D issue %.2f ms, launches %.2f ms, wait %.2f ms\n", 1e3 * (tr1 - tr0),
             1e3 * (tr2 - tr1), 1e3 * (omp_get_wtime() - tr2));

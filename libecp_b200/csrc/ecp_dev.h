@@ -55,6 +55,7 @@ typedef struct {
   int small_levSlot[ECP_SMALL_LEVELS + 1];
   /* large grid template on (-1,1), level-major padded layout */
   const double *large_x, *large_w;   /* [1024]                                     */
+  const double *large_xo;            /* abscissae in original (ascending) order [largeOrder] */
   const int16_t *large_oidx;         /* [1024]                                     */
   /* Bessel table transposed to [1601][besselStride], and C_j */
   const double *besselT, *besselC;
@@ -102,7 +103,6 @@ typedef struct {
   const int64_t *trOut;     /* offset of the (type1,type2) block pair in the block buffer */
   const int64_t *trPair;    /* first type-1 primitive pair                         */
   int64_t tTotal, gTotal, outTotal, nPairs, qTotal, rshTotal;
-  const int *prTriple;      /* [nPairs] owning triple                              */
   /* per class ranges (triples of class c are [clsFirst[c], clsFirst[c+1])) */
   const int *clsFirst;      /* [nClasses+1]                                        */
   const int64_t *clsWork;   /* [nClasses+1] prefix of ntriples*nq (fast-T threads) */

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
   double *myrow = gsm + gl * RS;
   double *tile = gsm + 8 * RS;
   int *qK = (int *)(tile + FB_TILE), *qQ = qK + FB_NQ; /* position in the class list / packed l | l1<<4 | l2<<8 | l3<<12 */
+  const unsigned long long dbgT0 = b.dbg ? ecp_gtimer() : 0;
   const int nItems = b.counters[0];
   const int nChunks = t.largeSlots / 8;
   /* item state */
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
     }
     /* ---- integrands of the pass's quadratures at my point -> tile[quadrature][lane] ---- */
     {
+      const double G = W * (CU * EX); /* common to all quadratures of the point */
       int nqMax = have ? nq : 0;
       nqMax = max(nqMax, __shfl_xor_sync(0xffffffffu, nqMax, 8));
       nqMax = max(nqMax, __shfl_xor_sync(0xffffffffu, nqMax, 16));
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
           const int qq = qQ[j];
           const int l1 = (qq >> 4) & 15, l2 = (qq >> 8) & 15, l3 = (qq >> 12) & 15;
           /* c_a c_b U r^N K_l1 K_l2 exp(e), times the mapped weight (src/type2.c:403-405) */
-          val = W * (CU * myrow[l3] * myrow[(KO + 1) + l1] * myrow[2 * (KO + 1) + l2] * EX);
+          val = G * (myrow[l3] * myrow[(KO + 1) + l1] * myrow[2 * (KO + 1) + l2]);
         }
         if (j < nq || !have) tile[j * 9 + gl] = val;
       }
@@ -296,6 +298,10 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
         open = 0;
       }
     }
+  }
+  if (b.dbg && threadIdx.x == 0 && blockIdx.x < DBG_STRIDE) {
+    b.dbg[2 * blockIdx.x] = dbgT0;
+    b.dbg[2 * blockIdx.x + 1] = ecp_gtimer();
   }
 }
 

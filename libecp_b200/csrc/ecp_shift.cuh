@@ -34,8 +34,8 @@ __global__ void k_shiftJ(DevT t, DevB b, const long long *__restrict__ clsJ, lon
     const double f = t.shTermBin[k] * uA[(dd & 15) * dA * dA + ((dd >> 4) & 15) * dA + (dd >> 8)];
     if (fabs(f) <= t.accuracy) continue; /* src/util.c:286 */
     const int p = t.shTermP[k] * cdb;
-    J1 += f * G1[p];
-    J2 += f * G2[p];
+    J1 = fma(f, G1[p], J1);
+    J2 = fma(f, G2[p], J2);
   }
   double *J = Jbuf + 2 * (clsJ[c] + (long long)(tri - b.clsFirst[c]) * (na * cdb));
   J[rem] = J1;
@@ -66,8 +66,8 @@ __global__ void k_shiftI(DevT t, DevB b, const long long *__restrict__ clsJ, lon
     const double f = t.shTermBin[k] * uB[(dd & 15) * dB * dB + ((dd >> 4) & 15) * dB + (dd >> 8)];
     if (fabs(f) <= t.accuracy) continue; /* src/util.c:318 */
     const int p = t.shTermP[k];
-    I1 += (f * n1) * J1[p]; /* factor *= N; I += factor * J  (src/util.c:321-324) */
-    I2 += (f * n2) * J2[p];
+    I1 = fma(f * n1, J1[p], I1); /* factor *= N; I += factor * J  (src/util.c:321-324) */
+    I2 = fma(f * n2, J2[p], I2);
   }
   if (flags & 2) {
     double *o = b.blocks + b.trOut[tri];

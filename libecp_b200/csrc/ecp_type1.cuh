@@ -76,15 +76,17 @@ static size_t t1_smem_bytes(int lab, int block) {
   return (size_t)(block / 32) * 4 * gs * sizeof(double);
 }
 
-/* w * C * r^N * U * K_lambda * exp(e)  (integrand order of src/type1.c:84) */
-template <int LAB>
-__device__ __forceinline__ double t1_wval(const T1Point<LAB> &p, double Cc, int N, int lam) {
-  return p.live ? p.w * (Cc * p.rn[N] * p.u * p.K[lam] * p.ex) : 0.0;
-}
+/* w * C * r^N * U * K_lambda * exp(e)  (integrand of src/type1.c:84).  The factors common to all quadratures of a point
+ * are multiplied once: G = w (C U exp(e)), H[N] = G r^N, value = H[N] K_lambda - 3 + (LAB+1) + NQ multiplications per
+ * point instead of 5 NQ (the same factors as the reference, associated differently). */
 template <int LAB, int... Q>
 __device__ __forceinline__ void t1_store_vals(const T1Point<LAB> &pt, double Cc, double *dst,
                                               std::integer_sequence<int, Q...>) {
-  ((dst[Q * T1Cfg<LAB>::ROW] = t1_wval<LAB>(pt, Cc, t1_qN(Q), t1_qLam(Q))), ...);
+  double H[LAB + 1];
+  const double G = pt.live ? pt.w * ((Cc * pt.u) * pt.ex) : 0.0;
+#pragma unroll
+  for (int i = 0; i <= LAB; i++) H[i] = pt.live ? G * pt.rn[i] : 0.0;
+  ((dst[Q * T1Cfg<LAB>::ROW] = pt.live ? H[t1_qN(Q)] * pt.K[t1_qLam(Q)] : 0.0), ...);
 }
 
 /* per primitive pair, written by k_t1prep */
@@ -111,6 +113,32 @@ __device__ __forceinline__ void t1_fill_point(const DevT &t, double r, double za
   }
 }
 
+/* Points of small-grid level v that the pair's window [gs, ge) tabulates (src/type1.c:121): the left indices of a level
+ * ascend with the pair number j and the right ones descend (src/gc_integrators.c:186-199), so they are the left points
+ * of the pairs [jLa, jLa + nLl) and the right points of the pairs [jRa, jRa + nLive - nLl) - read off the suffix tables
+ * of the fast path.  cnt = points the PS93 rule counts (left idx >= gs, right idx <= ge, :190-197). */
+struct T1Level {
+  int s0, jLa, nLl, jRa, nLive, cnt;
+};
+__device__ __forceinline__ T1Level t1_level(const DevT &t, int v, int gs, int ge) {
+  T1Level L;
+  L.s0 = t.sm.levSlot[v];
+  const int npair = (t.sm.levSlot[v + 1] - L.s0) >> 1;
+  const unsigned char *jl = t.small_jL + v * ECP_SMALL_SLOTS, *jr = t.small_jR + v * ECP_SMALL_SLOTS;
+  const int top = ECP_SMALL_SLOTS - 1;
+  const int lA = gs > top ? npair : jl[gs];               /* first left idx >= gs            */
+  const int lE = ge > top ? npair : jl[ge];               /* first left idx >= ge            */
+  const int rA = ge - 1 > top ? 0 : jr[ge - 1];           /* first right idx <= ge - 1       */
+  const int rE = gs < 1 ? npair : (gs - 1 > top ? 0 : jr[gs - 1]); /* first right idx <= gs - 1 */
+  const int rC = ge > top ? 0 : jr[ge];                   /* first right idx <= ge           */
+  L.jLa = lA;
+  L.nLl = lE > lA ? lE - lA : 0;
+  L.jRa = rA;
+  L.nLive = L.nLl + (rE > rA ? rE - rA : 0);
+  L.cnt = (npair - lA) + (npair - rC);
+  return L;
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 template <int LAB>
 __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_type1S(DevT t, DevB b, T1Segs segs, int *workCtr, int *failCount, int *failList,
@@ -120,6 +148,7 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
   extern __shared__ __align__(16) double t1_red[];
   const int lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24;
   double *red = t1_red + ((threadIdx.x >> 5) * 4 + (lane >> 3)) * Cfg::GS;
+  const unsigned long long dbgT0 = b.dbg ? ecp_gtimer() : 0;
   const int total = (int)segs.prefix[segs.nseg];
   bool have = false, drained = false;
   double z = 0.0, sS = 0.0, Cc = 0.0;
@@ -136,9 +165,10 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
     qo[k] = t1_qN(q) * (LAB + 1) + t1_qLam(q);
   }
   unsigned open = 0;
-  int c = 0;   /* chunk of 8 slots the group works on            */
-  int v = 4;   /* level being accumulated by chunks >= 2         */
-  int cnt = 0; /* in-window points of that level so far          */
+  int c = 0;   /* 0, 1: the two fixed chunks (slots 0..15 = first points and levels 0..3); 2: level-wise     */
+  int v = 4;   /* level being accumulated once c == 2                                                        */
+  int ks = 0;  /* 8-point step inside that level: only the points inside the window are visited              */
+  T1Level lv = {0, 0, 0, 0, 0, 0};
   for (;;) {
     /* ---- a group without a pair takes the next one of this launch ---- */
     const bool need = !have && !drained;
@@ -165,7 +195,8 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
             if (8 * k + gl < NQ) open |= 1u << k;
           c = 0;
           v = 4;
-          cnt = 0;
+          ks = 0;
+          lv = t1_level(t, 4, gs, ge);
           have = true;
         } else {
           drained = true;
@@ -173,8 +204,14 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
       }
     }
     if (!__any_sync(T1_FULL, have)) break;
-    /* ---- one chunk: every lane tabulates one slot ---- */
-    const int slot = 8 * c + gl;
+    /* ---- one chunk: every lane tabulates one slot; from level 4 on the 8 lanes take the next 8 points of the level
+     * that lie inside the window (about 30 % of a level on Au20: the pairs that never converge walked 48 chunks of
+     * mostly idle lanes) ---- */
+    int slot = 8 * c + gl;
+    if (c >= 2) {
+      const int m = 8 * ks + gl;
+      slot = (m < lv.nLl) ? lv.s0 + 2 * (lv.jLa + m) : ((m < lv.nLive) ? lv.s0 + 2 * (lv.jRa + m - lv.nLl) + 1 : 1);
+    }
     T1Point<LAB> pt;
     pt.live = false;
     pt.w = 0.0;
@@ -202,8 +239,8 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
     t1_store_vals<LAB>(pt, Cc, red + gl, std::make_integer_sequence<int, NQ>{});
     __syncwarp();
     if (have) {
-      const bool last = (c >= 2) && (8 * c + 8 == t.sm.levSlot[v + 1]);
-      if (c >= 2) cnt += __popc(bal);
+      const bool last = (c >= 2) && (8 * ks + 8 >= lv.nLive);
+      const int cnt = lv.cnt;
 #pragma unroll
       for (int k = 0; k < NQL; k++) {
         const int q = 8 * k + gl;
@@ -253,15 +290,19 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
           }
         }
       }
-      if (last) {
+      if (c < 2) {
+        c++;
+      } else if (last) {
         v++;
-        cnt = 0;
+        ks = 0;
+        if (v < ECP_SMALL_LEVELS) lv = t1_level(t, v, gs, ge);
+      } else {
+        ks++;
       }
-      c++;
     }
     /* ---- group finished: all its quadratures converged, or the grid is exhausted ---- */
     const unsigned ob = (__ballot_sync(T1_FULL, have && open != 0) >> gbase) & 0xffu;
-    const bool fin = have && (ob == 0 || c == ECP_SMALL_SLOTS / 8);
+    const bool fin = have && (ob == 0 || v == ECP_SMALL_LEVELS);
     if (__any_sync(T1_FULL, fin && ob != 0)) {
       /* quadratures that never converged on the small grid -> large grid (src/type1.c:149) */
       unsigned long long m = 0;
@@ -283,6 +324,11 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
       open = 0;
     }
   }
+  if (b.dbg && threadIdx.x == 0 && blockIdx.x < DBG_STRIDE) {
+    unsigned long long *e = b.dbg + (size_t)(1 + LAB) * DBG_STRIDE * 2;
+    e[2 * blockIdx.x] = dbgT0;
+    e[2 * blockIdx.x + 1] = ecp_gtimer();
+  }
 }
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -295,7 +341,6 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
   const int lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24;
   double *red = t1_red + ((threadIdx.x >> 5) * 4 + (lane >> 3)) * Cfg::GS;
   const int total = *failCount;
-  const int nChunks = t.largeSlots / 8;
   bool have = false, drained = false;
   double z = 0.0, sS = 0.0, zd2 = 0.0, Cc = 0.0, i1 = 0.0, i2 = 0.0;
   int Lc = 0, g0 = 0, g1 = 0;
@@ -309,8 +354,11 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
     qo[k] = t1_qN(q) * (LAB + 1) + t1_qLam(q);
   }
   unsigned open = 0;
-  int c = 0;
-  int lev = 3, n = 7; /* level accumulated by chunks >= 1: slots [2^lev, 2^(lev+1)); n = points before it */
+  int c = 0;          /* 0: the fixed first chunk (slots 0..7 = centre, levels 1 and 2); 1: level-wise            */
+  int lev = 3, n = 7; /* level accumulated once c == 1: slots [2^lev, 2^(lev+1)); n = points before it          */
+  int ks = 0;         /* 8-candidate step inside the level (lg_level: only points that can pass the gate)        */
+  LgRange lr = {1, 0};
+  LgLevel lv = {0, 0, 0, 0};
   for (;;) {
     const bool need = !have && !drained;
     if (__any_sync(T1_FULL, need)) {
@@ -339,6 +387,9 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
           c = 0;
           lev = 3;
           n = 7;
+          ks = 0;
+          lr = lg_live_range(t, z, sS, zd2 - t.lnAcc1, i1, i2);
+          lv = lg_level(t, lr, 3);
           have = true;
         } else {
           drained = true;
@@ -346,7 +397,7 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
       }
     }
     if (!__any_sync(T1_FULL, have)) break;
-    const int slot = 8 * c + gl;
+    const int slot = (c == 0) ? gl : lg_slot(lv, lev, 8 * ks + gl);
     T1Point<LAB> pt;
     pt.live = false;
     pt.w = 0.0;
@@ -365,8 +416,8 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
     t1_store_vals<LAB>(pt, Cc, red + gl, std::make_integer_sequence<int, NQ>{});
     __syncwarp();
     if (have) {
-      const bool first = (8 * c == (1 << lev));
-      const bool last = (8 * c + 8 == (2 << lev));
+      const bool first = (ks == 0);
+      const bool last = (8 * ks + 8 >= lv.nLive);
 #pragma unroll
       for (int k = 0; k < NQL; k++) {
         const int q = 8 * k + gl;
@@ -404,14 +455,19 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
           }
         }
       }
-      if (c > 0 && last) {
+      if (c == 0) {
+        c = 1;
+      } else if (last) {
         n = 2 * n + 1;
         lev++;
+        ks = 0;
+        if (lev <= t.largeLevels) lv = lg_level(t, lr, lev);
+      } else {
+        ks++;
       }
-      c++;
     }
     const unsigned ob = (__ballot_sync(T1_FULL, have && open != 0) >> gbase) & 0xffu;
-    const bool fin = have && (ob == 0 || c == nChunks);
+    const bool fin = have && (ob == 0 || (c == 1 && lev > t.largeLevels));
     if (fin) {
       if (ob != 0 && gl == 0) atomicExch(errFlag, 1); /* large grid failed: rc 1 (src/libecp.h:25) */
       have = false;

@@ -606,6 +606,7 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   v->small_oidx = t->small_oidx;
   v->large_x = t->large_xs;
   v->large_w = t->large_ws;
+  v->large_xo = t->large_x;
   v->large_oidx = t->large_oidx;
   v->besselT = t->besselT;
   v->besselC = t->besselC;
