@@ -395,6 +395,24 @@ def run_b200(args):
            "ms_init": 1e3 * parts[0] / e2e_steps, "ms_integrate_d2h": 1e3 * parts[1] / e2e_steps,
            "ms_free": 1e3 * parts[2] / e2e_steps}
 
+    # ---- device-resident consumer at N > 1: one NCCL all-gather of the packed shards (not part of `value`) ----
+    allgather = None
+    if dist:
+        from libecp_b200 import gather
+
+        h.integrals_device()
+        bufs, ts, nbytes = None, [], 0
+        for _ in range(3):
+            barrier()
+            dt, nbytes, bufs = gather.allgather_matrix(h, rank, world, buffers=bufs)
+            ts.append(max_over_ranks(dt))
+            h.integrals_device()  # a scatter dirties the matrix: the pass after it starts with a full clear
+        del bufs
+        allgather = {"ms": 1e3 * min(ts[1:]), "bytes_received_per_rank": int(nbytes),
+                     "GBps_per_rank": nbytes / min(ts[1:]) / 1e9,
+                     "note": "pack own rows + ncclAllGather (padded shards) + scatter of the other ranks' rows; "
+                             "leaves the full upper-triangular matrix on every GPU"}
+
     # ---- roofline, secondary (Au20) and CPU baseline on rank 0 / N=1 ----
     line = None
     if rank == 0:
@@ -417,6 +435,8 @@ def run_b200(args):
             line["roofline"] = rl
         if per_rank:
             line["per_rank"] = per_rank
+        if allgather:
+            line["allgather"] = allgather
     if world == 1 and rank == 0 and not args.no_secondary and args.workload != "cfg3":
         line["secondary"] = secondary_au20(capi, torch, peak_tf)
     h.close()

@@ -39,6 +39,20 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO);
 /* same, then copied into host memory I (row stride rowdim) with += on the upper triangle */
 int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I);
 
+/* Device-resident gather of a sharded run ("NCCL all-gather when the matrix stays on the device").
+ * A rank's matrix is non-zero only in the upper-triangle parts M[i][i..nAO) of the AO rows of the shells it owns.
+ *   libecp_b200_owned_rows : those rows (ascending) for any (rank, world) - every rank can list every other rank's rows;
+ *   libecp_b200_pack_rows  : packs the listed rows of the handle's device matrix back to back into a caller-provided
+ *                            DEVICE buffer of `cap` doubles (*elems = doubles used; devPacked NULL: only sizes it);
+ *   libecp_b200_unpack_rows: scatters such a packed buffer (another rank's shard after the collective) into the
+ *                            handle's device matrix.
+ * The collective itself (ncclAllGather / torch.distributed.all_gather_into_tensor over NVLink) belongs to the caller,
+ * which owns the communicator: libecp_b200/gather.py is the reference-side harness for it.  All three return 0 on
+ * success, -1 on error (libecp_b200_last_error). */
+long long libecp_b200_owned_rows(libECPHandle *h, int rank, int world, int *rows, long long cap);
+int libecp_b200_pack_rows(libECPHandle *h, const int *rows, long long nrows, void *devPacked, long long cap, long long *elems);
+int libecp_b200_unpack_rows(libECPHandle *h, const int *rows, long long nrows, const void *devPacked, long long cap);
+
 typedef struct {
   long long nominal_triples;   /* centres x nshells(nshells+1)/2 : the reference's loop domain (src/libecp.c:256-312) */
   long long executed_triples;  /* survive screening (src/libecp.c:304-320,344) */

@@ -24,7 +24,7 @@ EXPORTS = [
     "libecp_b200_integrals_device", "libecp_b200_integrals_host", "libecp_b200_get_stats", "libecp_b200_screening",
     "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
     "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
-    "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only",
+    "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only", "libecp_b200_owned_rows", "libecp_b200_pack_rows", "libecp_b200_unpack_rows",
 ]
 
 
@@ -205,6 +205,39 @@ class Handle:
         if rc:
             raise RuntimeError("not an ECP centre")
         return endl[:L], st, en, sk
+
+    def owned_rows(self, rank, world):
+        """AO rows (ascending) of the shells whose shell-pair rows `rank` of `world` owns"""
+        f = lib().libecp_b200_owned_rows
+        f.restype = C.c_longlong
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, _pi, C.c_longlong]
+        n = f(C.c_void_p(self.h), rank, world, None, 0)
+        out = np.zeros(max(int(n), 1), np.int32)
+        f(C.c_void_p(self.h), rank, world, _p(out, _pi), n)
+        return out[:n]
+
+    def packed_size(self, rows):
+        """doubles that the upper-triangle parts of `rows` take"""
+        n = int(self.s["dim"])
+        return int((n - np.asarray(rows, np.int64)).sum())
+
+    def pack_rows(self, rows, dev_ptr, cap):
+        f = lib().libecp_b200_pack_rows
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, _pi, C.c_longlong, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]
+        rows = np.ascontiguousarray(rows, np.int32)
+        e = C.c_longlong(0)
+        if f(C.c_void_p(self.h), _p(rows, _pi), len(rows), C.c_void_p(dev_ptr), cap, C.byref(e)):
+            raise RuntimeError("pack_rows: " + lib().libecp_b200_last_error().decode())
+        return int(e.value)
+
+    def unpack_rows(self, rows, dev_ptr, cap):
+        f = lib().libecp_b200_unpack_rows
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, _pi, C.c_longlong, C.c_void_p, C.c_longlong]
+        rows = np.ascontiguousarray(rows, np.int32)
+        if f(C.c_void_p(self.h), _p(rows, _pi), len(rows), C.c_void_p(dev_ptr), cap):
+            raise RuntimeError("unpack_rows: " + lib().libecp_b200_last_error().decode())
 
     def build_only(self):
         """(ms, triples, batches) of the host batch builder alone"""

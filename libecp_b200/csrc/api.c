@@ -176,12 +176,13 @@ typedef struct {
   int *centre;
   int keepCanon, took;
   int flags, slot, prefetch; /* prefetch: start the H2D of the finished batch into input set `slot` */
+  long long maxTriples;      /* size target of this batch */
   double ms;
 } BuildJob;
 static void build_job(BuildJob *j) {
   const double t0 = now_ms();
   if (j->h->dev) ecpdev_bind_thread(j->h->dev);
-  j->took = ecp_batch_build(j->h->tab, j->h->geometry, j->centre, j->h->maxTriples, j->h->rank, j->h->world, j->keepCanon,
+  j->took = ecp_batch_build(j->h->tab, j->h->geometry, j->centre, j->maxTriples, j->h->rank, j->h->world, j->keepCanon,
                             (j->flags & 2) != 0, j->bb);
   j->ms = now_ms() - t0;
   if (j->prefetch && j->took > 0 && j->h->dev) ecpdev_prefetch_batch(j->h->dev, &j->bb->b, j->flags, j->slot);
@@ -257,8 +258,17 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
   }
   ecpdev_invalidate_prefetch(h->dev);
   EcpBatchBuf *bufs[2] = {h->bb, h->bb2};
-  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, flags, 0, 0, 0.0};
+  /* Batch size: the builder works one batch ahead of the GPU, so the first batch of a pass is built with the GPU idle
+   * and is kept small; a rank of a sharded run owns 1/world of the triples and takes smaller batches so that its pass
+   * still has enough of them to pipeline (below ~0.5 M triples the per-batch launches and kernel tails start to show). */
+  long long full = h->maxTriples;
+  if (h->world > 1 && !getenv("LIBECP_B200_BATCH_TRIPLES")) {
+    full = 2 * h->maxTriples / h->world;
+    if (full < 500000) full = 500000;
+  }
+  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, flags, 0, 0, full / 6, 0.0};
   build_job(&job); /* first batch: nothing to overlap with */
+  job.maxTriples = full;
   if (getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] first batch built in %.1f ms\n", job.ms);
   if (!h->worker) h->worker = worker_new();
   const int threaded = h->worker->started && !getenv("LIBECP_B200_NO_PIPELINE");
@@ -336,6 +346,30 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
   rc = run_all(h, 1, NULL, NULL);
   if (devMatrix) *devMatrix = ecpdev_matrix_ptr(h->dev);
   return rc;
+}
+
+/* AO rows (ascending) whose shell-pair rows `rank` of `world` owns; returns the count (cap may be 0 to size) */
+long long libecp_b200_owned_rows(libECPHandle *h, int rank, int world, int *rows, long long cap) {
+  const EcpHostTables *v = &h->tab->v;
+  long long n = 0;
+  for (int s = 0; s < v->nrShells; s++)
+    if (ecp_pair_owner(s, s, world) == rank)
+      for (int k = 0; k < IJK_DIM(v->shellL[s]); k++, n++)
+        if (rows && n < cap) rows[n] = v->shellAO[s] + k;
+  return n;
+}
+int libecp_b200_pack_rows(libECPHandle *h, const int *rows, long long nrows, void *devPacked, long long cap, long long *elems) {
+  if (h->empty) {
+    if (elems) *elems = 0;
+    return 0;
+  }
+  if (!h->dev) return -1;
+  return ecpdev_matrix_rows(h->dev, 0, rows, nrows, devPacked, cap, elems) ? -1 : 0;
+}
+int libecp_b200_unpack_rows(libECPHandle *h, const int *rows, long long nrows, const void *devPacked, long long cap) {
+  if (h->empty) return 0;
+  if (!h->dev) return -1;
+  return ecpdev_matrix_rows(h->dev, 1, rows, nrows, (void *)devPacked, cap, NULL) ? -1 : 0;
 }
 
 int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {

@@ -209,7 +209,10 @@ __device__ __forceinline__ void ftab_body(const DevT &t, const DevB &b, int ss, 
 #pragma unroll
   for (int i = 0; i <= LM; i++) F[i] = acc[i];
 }
-__global__ void __launch_bounds__(ECP_SMALL_SLOTS) k_Ftab(DevT t, DevB b) {
+/* LMAX: highest order bound of the handle (L_max - 1 + l_max).  The usual shapes (s-f shells, L <= 4: LMAX = 6) fit two
+ * blocks per SM in registers; the deep-table stress shapes take the one-block variant. */
+template <int LMAX>
+__global__ void __launch_bounds__(ECP_SMALL_SLOTS, (LMAX <= 6 ? 2 : 1)) k_Ftab(DevT t, DevB b) {
   const int ss = blockIdx.x, k = threadIdx.x;
   const int sh = b.ssShell[ss], as = b.ssASlot[ss];
   const int Lc = t.typeL[b.asType[as]];
@@ -222,11 +225,18 @@ __global__ void __launch_bounds__(ECP_SMALL_SLOTS) k_Ftab(DevT t, DevB b) {
     case 3: ftab_body<3>(t, b, ss, k, sh, dAC); break;
     case 4: ftab_body<4>(t, b, ss, k, sh, dAC); break;
     case 5: ftab_body<5>(t, b, ss, k, sh, dAC); break;
-    case 6: ftab_body<6>(t, b, ss, k, sh, dAC); break;
-    case 7: ftab_body<7>(t, b, ss, k, sh, dAC); break;
-    case 8: ftab_body<8>(t, b, ss, k, sh, dAC); break;
-    case 9: ftab_body<9>(t, b, ss, k, sh, dAC); break;
-    default: ftab_body<KM>(t, b, ss, k, sh, dAC); break;
+    default:
+      if (LMAX <= 6 || lmaxA == 6) {
+        ftab_body<6>(t, b, ss, k, sh, dAC);
+      } else {
+        switch (lmaxA) {
+          case 7: ftab_body<(LMAX > 6 ? 7 : 6)>(t, b, ss, k, sh, dAC); break;
+          case 8: ftab_body<(LMAX > 6 ? 8 : 6)>(t, b, ss, k, sh, dAC); break;
+          case 9: ftab_body<(LMAX > 6 ? 9 : 6)>(t, b, ss, k, sh, dAC); break;
+          default: ftab_body<(LMAX > 6 ? KM : 6)>(t, b, ss, k, sh, dAC); break;
+        }
+      }
+      break;
   }
 }
 
@@ -654,6 +664,15 @@ __global__ void k_pack_rows(const double *__restrict__ M, int n, const int *__re
   for (int j = i + threadIdx.x; j < n; j += blockDim.x) o[j] = src[j];
 }
 
+/* inverse of k_pack_rows: packed upper-triangle rows (of another rank's shard) into the full matrix */
+__global__ void k_unpack_rows(double *__restrict__ M, int n, const int *__restrict__ rows, const long long *__restrict__ off,
+                              const double *__restrict__ in) {
+  const int i = rows[blockIdx.x];
+  const double *src = in + off[blockIdx.x] - i;
+  double *dst = M + (size_t)i * n;
+  for (int j = i + threadIdx.x; j < n; j += blockDim.x) dst[j] = src[j];
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* FP64 FMA peak probe (roofline denominator when no measured FP64 peak is published) */
 __global__ void k_fp64_probe(double *out, int iters) {
@@ -697,7 +716,7 @@ struct EcpDev {
   size_t matrixBytes;
   int matrixKnown, dirtyAll, nDirty; /* matrix is zero outside the upper-triangle parts of the dirty rows */
   long long dirtySig;
-  Buf dirtyRows;
+  Buf dirtyRows, gatherRows, gatherOff;
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
@@ -1053,6 +1072,8 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
     if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
   }
   if (d->dirtyRows.p) cudaFreeAsync(d->dirtyRows.p, d->s1);
+  if (d->gatherRows.p) cudaFreeAsync(d->gatherRows.p, d->s1);
+  if (d->gatherOff.p) cudaFreeAsync(d->gatherOff.p, d->s1);
   cudaStreamSynchronize(d->s1);
   for (int i = 0; i < 12; i++) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->s1);
@@ -1122,6 +1143,57 @@ extern "C" int ecpdev_matrix_download(EcpDev *d, double *host) {
 /* host I[i*rowdim + j] += M[i][j] for j >= i (what libECP_callback0 does block by block, reference
  * src/getIntegrals.c:36-42): upper-triangle row panels are copied D2H into two pinned staging buffers and
  * added by all host threads while the next panel is in flight. */
+/* Device-resident gather of a sharded result: pack the upper-triangle parts M[i][i..n) of the listed rows
+ * of the handle's matrix back to back into the caller's DEVICE buffer (dir = 0), or scatter such a packed buffer - e.g.
+ * another rank's shard after an NCCL all-gather - into the handle's matrix (dir = 1).  rows: ascending AO rows on the
+ * host.  Returns 0 and the number of doubles the rows take in *elems; with devBuf == NULL only counts. */
+extern "C" int ecpdev_matrix_rows(EcpDev *d, int dir, const int *rows, long long nrows, void *devBuf, long long cap,
+                                  long long *elems) {
+  CK(cudaSetDevice(d->device));
+  const int n = d->nAO;
+  long long *off = (long long *)malloc((size_t)(nrows + 2) * sizeof(long long));
+  long long tot = 0;
+  for (long long k = 0; k < nrows; k++) {
+    if (rows[k] < 0 || rows[k] >= n || (k && rows[k] <= rows[k - 1])) {
+      free(off);
+      snprintf(g_err, sizeof(g_err), "ecpdev_matrix_rows: row list must be ascending AO rows");
+      return -1;
+    }
+    off[k] = tot;
+    tot += n - rows[k];
+  }
+  if (elems) *elems = tot;
+  if (!devBuf || nrows == 0) {
+    free(off);
+    return 0;
+  }
+  if (tot > cap || !d->matrix) {
+    free(off);
+    snprintf(g_err, sizeof(g_err), "ecpdev_matrix_rows: %s", d->matrix ? "buffer too small" : "no result matrix yet");
+    return -1;
+  }
+  g_allocStream = d->s1;
+  int rc = ensure(&d->gatherRows, (size_t)(nrows + 1) * sizeof(int));
+  if (!rc) rc = ensure(&d->gatherOff, (size_t)(nrows + 2) * sizeof(long long));
+  if (rc) {
+    free(off);
+    return rc;
+  }
+  CK(cudaMemcpyAsync(d->gatherRows.p, rows, (size_t)nrows * sizeof(int), cudaMemcpyHostToDevice, d->s1));
+  CK(cudaMemcpyAsync(d->gatherOff.p, off, (size_t)nrows * sizeof(long long), cudaMemcpyHostToDevice, d->s1));
+  if (dir == 0)
+    k_pack_rows<<<(unsigned)nrows, 256, 0, d->s1>>>(d->matrix, n, (const int *)d->gatherRows.p,
+                                                  (const long long *)d->gatherOff.p, 0, (double *)devBuf);
+  else
+    k_unpack_rows<<<(unsigned)nrows, 256, 0, d->s1>>>(d->matrix, n, (const int *)d->gatherRows.p,
+                                                    (const long long *)d->gatherOff.p, (const double *)devBuf);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(d->s1)); /* off / rows are pageable; the caller's collective runs on its own stream */
+  free(off);
+  if (dir == 1) d->matrixKnown = 0; /* rows of other ranks are now non-zero: the next pass clears everything */
+  return 0;
+}
+
 extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned,
                                          long long *bytes) {
   CK(cudaSetDevice(d->device));
@@ -1472,7 +1544,10 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
   k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
   k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
-  k_Ftab<<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
+  if (t.maxLECP - 1 + d->maxLBS <= 6)
+    k_Ftab<6><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
+  else
+    k_Ftab<KM><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
   launches += 4;
   CK(cudaEventRecord(d->ev[1], d->s1));
   /* type 1 on the second stream, after the uploads/tables */

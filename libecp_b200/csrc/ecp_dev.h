@@ -130,6 +130,8 @@ const char *ecpdev_last_error(void);
 /* matrix accumulation target (device resident, nAO x nAO, zeroed) */
 int ecpdev_matrix_begin(EcpDev *d, const unsigned char *rowOwned /* [nAO] or NULL = all */, long long ownershipSig);
 int ecpdev_matrix_download(EcpDev *d, double *host /* nAO*nAO */);
+/* pack (dir 0) / scatter (dir 1) the upper-triangle parts of the listed rows between the matrix and a device buffer */
+int ecpdev_matrix_rows(EcpDev *d, int dir, const int *rows, long long nrows, void *devBuf, long long cap, long long *elems);
 int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned /* [nAO] or NULL */,
                               long long *bytes);
 void *ecpdev_matrix_ptr(EcpDev *d);

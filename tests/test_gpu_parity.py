@@ -197,3 +197,39 @@ def test_handles_in_sequence_reuse_parked_buffers():
         assert_parity(capi.get_integrals(SMALL[name]()), load_matrix(name), name)
     capi.lib().libecp_b200_release_cache()
     assert_parity(capi.get_integrals(SMALL["au2"]()), load_matrix("au2"), "au2 after release")
+
+
+def test_gather_pack_unpack_rebuilds_the_full_matrix():
+    """device-resident gather (libecp_b200_pack_rows / _unpack_rows): two handles play rank 0 and rank 1 of a 2-way
+    shard on one GPU; rank 1's packed rows scattered into rank 0's device matrix give the unsharded result, and the
+    next pass of that handle starts from a clean matrix again"""
+    import torch
+
+    from libecp_b200 import gather
+
+    s = synth.cfg3(4)
+    ref = load_matrix("au4")
+    n = int(s["dim"])
+    with capi.Handle(s) as h0, capi.Handle(s) as h1:
+        h0.set_shard(0, 2)
+        h1.set_shard(1, 2)
+        rows, sizes = gather.shard_layout(h0, 2)
+        assert sum(sizes) == n * (n + 1) // 2
+        assert h0.integrals_device()[0] == 0 and h1.integrals_device()[0] == 0
+        buf = torch.zeros(max(sizes), dtype=torch.float64, device="cuda")
+        assert h1.pack_rows(rows[1], buf.data_ptr(), buf.numel()) == sizes[1]
+        torch.cuda.synchronize()
+        h0.unpack_rows(rows[1], buf.data_ptr(), buf.numel())
+        full = np.zeros((n, n))
+        assert h0.pack_rows(np.arange(n, dtype=np.int32), 0, 0) == n * (n + 1) // 2  # sizing call only
+        allbuf = torch.zeros(n * (n + 1) // 2, dtype=torch.float64, device="cuda")
+        h0.pack_rows(np.arange(n, dtype=np.int32), allbuf.data_ptr(), allbuf.numel())
+        full[np.triu_indices(n)] = allbuf.cpu().numpy()
+        assert_parity(full, ref, "gathered au4")
+        # too small a buffer is refused, not overrun
+        with pytest.raises(RuntimeError):
+            h0.pack_rows(rows[0], buf.data_ptr(), 1)
+        # the scatter made other ranks' rows non-zero: the next pass must not accumulate onto them
+        rc, M = h0.integrals_host()
+        rc1, M1 = h1.integrals_host()
+        assert_parity(M + M1, ref, "shard union after a gather")

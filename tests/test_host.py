@@ -154,6 +154,33 @@ def test_shards_partition_the_triples():
         h.set_shard(0, 1)
 
 
+def test_gather_row_layout_partitions_the_matrix():
+    """rows of the device-resident gather (libecp_b200_owned_rows): every AO row belongs to exactly one rank, the
+    packed upper-triangle shards add up to n(n+1)/2 and follow the shell-pair ownership of the builder"""
+    from libecp_b200 import gather
+
+    s = synth.cfg5(30)
+    n = int(s["dim"])
+    with capi.Handle(s, tables_only=True) as h:
+        for world in (1, 2, 8):
+            rows, sizes = gather.shard_layout(h, world)
+            allr = np.concatenate(rows)
+            assert np.array_equal(np.sort(allr), np.arange(n))
+            assert all(np.all(np.diff(r) > 0) for r in rows if len(r) > 1)
+            assert sum(sizes) == n * (n + 1) // 2
+        # a rank's triples only ever write rows it owns: row shell of every triple = a shell whose AO rows are listed
+        world = 4
+        rows, _ = gather.shard_layout(h, world)
+        first = np.concatenate([[0], np.cumsum(s["shellsBS"])])
+        for rank in range(world):
+            h.set_shard(rank, world)
+            tl = h.triple_list()
+            shells = np.unique(first[tl[:, 0]] + tl[:, 1])
+            owners = {capi.lib().libecp_b200_pair_owner(int(x), int(x), world) for x in shells}
+            assert owners <= {rank}
+        h.set_shard(0, 1)
+
+
 @pytest.fixture(scope="module")
 def hc():
     L = C.CDLL(build.build_hostcheck())
