@@ -28,8 +28,9 @@ void libecp_b200_release_cache(void);
  * nest src/libecp.c:256-397); the union over ranks of what calculateECPIntegrals / the matrix
  * entry points produce equals the unsharded result block for block. */
 void libecp_b200_set_shard(libECPHandle *h, int rank, int world);
-/* owner rank of the shell pair (global shell indices) under that partition */
-int libecp_b200_pair_owner(int shellA, int shellB, int world);
+/* owner rank of the shell pair (global shell indices) under that partition: the rank that owns the row shell
+ * min(shellA, shellB); rows are dealt by a cost model over (l, contraction depth) (csrc/builder.c) */
+int libecp_b200_pair_owner(libECPHandle *h, int shellA, int shellB, int world);
 
 /* Upper-triangular ECP matrix accumulated on the device (what getIntegrals' callback
  * src/getIntegrals.c:22-43 builds on the host).  On return *devMatrix is a device pointer to

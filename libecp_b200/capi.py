@@ -58,7 +58,7 @@ def lib():
         L.getIntegrals.restype = C.c_int
         L.libecp_b200_set_device.argtypes = [C.c_int]
         L.libecp_b200_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
-        L.libecp_b200_pair_owner.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.libecp_b200_pair_owner.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.libecp_b200_integrals_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _pi]
         L.libecp_b200_integrals_host.argtypes = [C.c_void_p, C.c_int, _pd]
         L.libecp_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]

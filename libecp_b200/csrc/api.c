@@ -64,7 +64,7 @@ void libecp_b200_set_serial_kernels(libECPHandle *h, int on) {
   if (h && h->dev) ecpdev_set_serial(h->dev, on);
 }
 const char *libecp_b200_last_error(void) { return g_apierr[0] ? g_apierr : ecpdev_last_error(); }
-int libecp_b200_pair_owner(int a, int b, int world) { return ecp_pair_owner(a, b, world); }
+
 double libecp_b200_fp64_peak(int device, int iters) { return ecpdev_fp64_peak_probe(device, iters); }
 
 libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lECP, int *KECP, double *nECP,
@@ -327,7 +327,7 @@ static unsigned char *owned_rows(const libECPHandle *h) {
   const EcpHostTables *v = &h->tab->v;
   unsigned char *owned = calloc(v->nAO + 1, 1);
   for (int s = 0; s < v->nrShells; s++)
-    if (ecp_pair_owner(s, s, h->world) == h->rank)
+    if (ecp_pair_owner(h->tab, s, s, h->world) == h->rank)
       for (int k = 0; k < IJK_DIM(v->shellL[s]); k++) owned[v->shellAO[s] + k] = 1;
   return owned;
 }
@@ -348,12 +348,13 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
   return rc;
 }
 
+int libecp_b200_pair_owner(libECPHandle *h, int a, int b, int world) { return ecp_pair_owner(h->tab, a, b, world); }
 /* AO rows (ascending) whose shell-pair rows `rank` of `world` owns; returns the count (cap may be 0 to size) */
 long long libecp_b200_owned_rows(libECPHandle *h, int rank, int world, int *rows, long long cap) {
   const EcpHostTables *v = &h->tab->v;
   long long n = 0;
   for (int s = 0; s < v->nrShells; s++)
-    if (ecp_pair_owner(s, s, world) == rank)
+    if (ecp_pair_owner(h->tab, s, s, world) == rank)
       for (int k = 0; k < IJK_DIM(v->shellL[s]); k++, n++)
         if (rows && n < cap) rows[n] = v->shellAO[s] + k;
   return n;

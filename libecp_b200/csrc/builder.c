@@ -125,17 +125,15 @@ void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dis
 }
 
 /* Output ownership for the multi-GPU partition: the block of shell pair (a, b), a <= b in global shell order,
- * belongs to the rank that owns ROW shell a (rows are dealt to ranks by a hash of the shell index).  Owning whole
- * rows means that a rank's builder enumerates only its rows (work / world) and that its partial matrix has
- * non-zeros only in the AO rows of its shells (D2H / world). */
-int ecp_pair_owner(int a, int b, int world) {
+ * belongs to the rank that owns ROW shell a.  Owning whole rows means that a rank's builder enumerates only its rows
+ * (work / world) and that its partial matrix has non-zeros only in the AO rows of its shells (D2H / world).
+ * Cost-model deal: the cost of a triple is set by the kind of its shells (l, contraction depth, exponents).  The rows
+ * are dealt to the ranks one by one in the order "by kind, pseudo-random inside a kind" (t->rowDeal, tables.c): every
+ * rank receives the same number (+-1) of rows of every kind, from random places of the molecule. */
+int ecp_pair_owner(const EcpTables *t, int a, int b, int world) {
   if (world <= 1) return 0;
   const int row = a < b ? a : b;
-  uint64_t h = ((uint64_t)(uint32_t)row + 0x7F4A7C15ull) * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 29;
-  h *= 0xBF58476D1CE4E5B9ull;
-  h ^= h >> 32;
-  return (int)(h % (uint64_t)world);
+  return t->rowDeal[row] % world;
 }
 
 static double dist3(const double *a, const double *b) { /* src/util.c:109-116 */
@@ -196,7 +194,7 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
       w->ssAtom[nSS] = aslot;
       w->ssL[nSS] = (unsigned char)v->shellL[s];
       w->ssK[nSS] = (unsigned char)v->shellK[s];
-      w->ssOwn[nSS] = (unsigned char)(world <= 1 || ecp_pair_owner(s, s, world) == rank); /* row ownership */
+      w->ssOwn[nSS] = (unsigned char)(world <= 1 || ecp_pair_owner(t, s, s, world) == rank); /* row ownership */
       fRows += Lc + t->shellL[s];
       nSS++;
     }

@@ -44,6 +44,6 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
 /* exposed for tests: window of one (centre type, shell radius, distance) (reference src/type2.c:148-180) */
 void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip);
 /* owner rank of a shell pair under the multi-GPU partition */
-int ecp_pair_owner(int shellA, int shellB, int world);
+int ecp_pair_owner(const EcpTables *t, int shellA, int shellB, int world);
 
 #endif

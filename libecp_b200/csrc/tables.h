@@ -30,6 +30,7 @@ typedef struct {
   int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO;
   double *shellRadius;
   double *atomRmax;   /* largest shell radius per atom (atom-level screening prune) */
+  int *rowDeal;       /* position of every shell in the order rows are dealt to the ranks of a sharded run (builder.c) */
   int *atomMaxL, *atomFirstShell;
   /* ECP */
   int *atomType; /* per atom: type index or -1 */

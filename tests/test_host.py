@@ -176,7 +176,7 @@ def test_gather_row_layout_partitions_the_matrix():
             h.set_shard(rank, world)
             tl = h.triple_list()
             shells = np.unique(first[tl[:, 0]] + tl[:, 1])
-            owners = {capi.lib().libecp_b200_pair_owner(int(x), int(x), world) for x in shells}
+            owners = {capi.lib().libecp_b200_pair_owner(C.c_void_p(h.h), int(x), int(x), world) for x in shells}
             assert owners <= {rank}
         h.set_shard(0, 1)
 
