@@ -80,7 +80,7 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
   h->nrAtoms = nrAtoms;
   h->geometry = geometry;
   h->world = 1;
-  h->maxTriples = 1500000;
+  h->maxTriples = 3000000; /* ~0.9 ms of fixed device time per batch (57 launches, joins): fewer, larger batches */
   {
     const char *e = getenv("LIBECP_B200_BATCH_TRIPLES");
     if (e && atoll(e) > 0) h->maxTriples = atoll(e);
@@ -247,6 +247,16 @@ static void worker_wait(struct BuildWorker *w) {
   pthread_mutex_unlock(&w->mu);
 }
 
+/* batch size targets of a pass (see run_all): a small first batch, a half-size second one, then full size */
+static long long pass_batch_size(const libECPHandle *h, int i) {
+  long long full = h->maxTriples;
+  if (h->world > 1 && !getenv("LIBECP_B200_BATCH_TRIPLES")) {
+    full = 2 * h->maxTriples / h->world;
+    if (full < 500000) full = 500000;
+  }
+  return i == 0 ? full / 6 : (i == 1 ? full / 2 : full);
+}
+
 /* drive all batches; flags as ecpdev_run_batch; cb may be NULL */
 static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
   int result = 0, centre = 0;
@@ -261,14 +271,8 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
   /* Batch size: the builder works one batch ahead of the GPU, so the first batch of a pass is built with the GPU idle
    * and is kept small; a rank of a sharded run owns 1/world of the triples and takes smaller batches so that its pass
    * still has enough of them to pipeline (below ~0.5 M triples the per-batch launches and kernel tails start to show). */
-  long long full = h->maxTriples;
-  if (h->world > 1 && !getenv("LIBECP_B200_BATCH_TRIPLES")) {
-    full = 2 * h->maxTriples / h->world;
-    if (full < 500000) full = 500000;
-  }
-  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, flags, 0, 0, full / 6, 0.0};
+  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, flags, 0, 0, pass_batch_size(h, 0), 0.0};
   build_job(&job); /* first batch: nothing to overlap with */
-  job.maxTriples = full;
   if (getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] first batch built in %.1f ms\n", job.ms);
   if (!h->worker) h->worker = worker_new();
   const int threaded = h->worker->started && !getenv("LIBECP_B200_NO_PIPELINE");
@@ -279,6 +283,7 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     /* next batch on the helper thread (it advances the centre cursor; nobody else reads it meanwhile) */
     job.bb = bufs[(i + 1) & 1];
     job.slot = (i + 1) & 1;
+    job.maxTriples = pass_batch_size(h, i + 1); /* ramp: the GPU must not wait for a full-size build behind a small batch */
     job.prefetch = threaded;
     if (threaded) worker_post(h->worker, &job);
     const EcpBatch *b = &cur->b;
@@ -506,21 +511,21 @@ long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap) {
   return n;
 }
 
-/* host batch builder alone (no device work): wall ms of building every batch of one pass; for tuning / tests */
+/* host batch builder alone (no device work): wall ms of building every batch of one pass, with the batch sizes and
+ * the two alternating buffers of a real pass; for tuning / tests */
 double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches) {
   long long n = 0;
   int centre = 0, nb = 0;
   if (triples) *triples = 0;
   if (batches) *batches = 0;
   if (h->empty) return 0.0;
-  EcpBatchBuf *bb = ecp_batch_new(h->tab);
+  EcpBatchBuf *bufs[2] = {h->bb, h->bb2};
   const double t0 = now_ms();
-  while (ecp_batch_build(h->tab, h->geometry, &centre, h->maxTriples, h->rank, h->world, 0, 0, bb) > 0) {
-    n += bb->b.nTriples;
+  while (ecp_batch_build(h->tab, h->geometry, &centre, pass_batch_size(h, nb), h->rank, h->world, 0, 0, bufs[nb & 1]) > 0) {
+    n += bufs[nb & 1]->b.nTriples;
     nb++;
   }
   const double ms = now_ms() - t0;
-  ecp_batch_free(bb);
   if (triples) *triples = n;
   if (batches) *batches = nb;
   return ms;

@@ -304,6 +304,12 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
     ntake++;
     if (tri >= maxTriples) break;
   }
+  if (ntake < ncand && C >= nat) { /* every remaining centre is screened: a small rest joins this batch instead of
+                                    * paying a batch's launches for a few thousand triples */
+    long long rest = 0;
+    for (int i = ntake; i < ncand; i++) rest += cw[i].nTri;
+    if (4 * rest <= maxTriples) ntake = ncand;
+  }
   *centre = (ntake < ncand) ? cand[ntake] : C;
   long long nAS = 0, nSS = 0, omTotal = 0, fRows = 0, outTotal = 0, nTR = 0, nPairs = 0;
   long long *asBase = malloc((ntake + 1) * sizeof(long long)), *ssBase = malloc((ntake + 1) * sizeof(long long));
@@ -353,7 +359,8 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   }
   /* storage */
   ENSURE(bb->asAtom, bb->capAS, nAS, int); ENSURE(bb->asCentre, bb->capAS, nAS, int);
-  ENSURE(bb->asType, bb->capAS, nAS, int); ENSURE(bb->asR, bb->capAS * 4, nAS * 4, double);
+  ENSURE(bb->asType, bb->capAS, nAS, int);
+  if (nAS > bb->capAS) bb->asR = (double *)realloc(bb->asR, (size_t)(nAS + 16) * 4 * sizeof(double)); /* 4 per slot */
   ENSURE(bb->asOmOff, bb->capAS, nAS, int64_t);
   if (nAS > bb->capAS) bb->capAS = (int)nAS + 16;
   ENSURE(bb->ssShell, bb->capSS, nSS, int); ENSURE(bb->ssASlot, bb->capSS, nSS, int);

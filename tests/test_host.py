@@ -154,6 +154,38 @@ def test_shards_partition_the_triples():
         h.set_shard(0, 1)
 
 
+def test_builder_pass_dry_run_small_and_growing_batches():
+    """the batch sequence of a real pass (small first batch, half-size second, two alternating buffers that share the
+    screening scratch, leftover centres carried over) yields every executed triple exactly once for any batch size
+    and thread count - regression for a slot-array overrun that only growing batch sizes exposed"""
+    s = synth.cfg5(40)
+    old = os.environ.get("LIBECP_B200_BATCH_TRIPLES")
+    try:
+        counts = set()
+        for bt in ("300", "20000", "3000000"):
+            os.environ["LIBECP_B200_BATCH_TRIPLES"] = bt
+            for thr in (5, 2):
+                capi.set_host_threads(thr)
+                with capi.Handle(s, tables_only=True) as h:
+                    ms, n, nb = h.build_only()
+                    counts.add(n)
+                    assert nb >= 1 and (bt != "300" or nb > 20)
+                    tot = 0
+                    for r in range(3):
+                        h.set_shard(r, 3)
+                        tot += h.build_only()[1]
+                    assert tot == n
+                    h.set_shard(0, 1)
+                    assert len(h.triple_list()) == n
+        assert len(counts) == 1
+    finally:
+        capi.set_host_threads(0)
+        if old is None:
+            os.environ.pop("LIBECP_B200_BATCH_TRIPLES", None)
+        else:
+            os.environ["LIBECP_B200_BATCH_TRIPLES"] = old
+
+
 def test_gather_row_layout_partitions_the_matrix():
     """rows of the device-resident gather (libecp_b200_owned_rows): every AO row belongs to exactly one rank, the
     packed upper-triangle shards add up to n(n+1)/2 and follow the shell-pair ownership of the builder"""
