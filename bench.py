@@ -282,9 +282,9 @@ def run_b200(args):
     capi.set_device(local)
     # torchrun exports OMP_NUM_THREADS=1; every rank gets its share of the host cores for the batch builder
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # (one core per rank is left to the Python / CUDA-sync thread - OpenMP workers spin between parallel regions - and,
-    #  under torchrun, one more to the NCCL / launcher threads: an oversubscribed rank was measured 6 ms/step behind)
-    host_threads = max(1, ncores // max(1, world) - (1 if world == 1 else 2))
+    # (one core per rank is left to the Python thread / NCCL / launcher; the thread that drives the GPU sleeps on a
+    #  blocking-sync event while a batch runs, so it does not compete with the builder)
+    host_threads = max(1, ncores // max(1, world) - 1)
     capi.set_host_threads(host_threads)
     dist = None
     if world > 1:

@@ -11,6 +11,7 @@
 #include "builder.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -102,7 +103,21 @@ void ecp_batch_free(EcpBatchBuf *bb) {
 void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip) {
   const double rmin = dist - radius, rmax = dist + radius;
   const double *r = t->small_x;
-  int lo = -1, hi = endLast; /* largest j <= endLast with r[j] < rmin (or -1) */
+  /* winLut brackets both answers to the few points of one 1/16-bohr bin; the searches inside the bracket compare the
+   * same doubles as a search over the whole grid would */
+  int lo, hi; /* largest j <= endLast with r[j] < rmin (or -1) */
+  if (!(rmin > 0.0)) {
+    lo = hi = -1;
+  } else if (rmin * ECP_WIN_LUT_SCALE >= ECP_WIN_LUT_BINS) {
+    lo = -1;
+    hi = endLast;
+  } else {
+    const int k = (int)(rmin * ECP_WIN_LUT_SCALE);
+    lo = t->winLut[k] - 1;
+    hi = t->winLut[k + 1] - 1;
+    if (hi > endLast) hi = endLast;
+    if (lo > endLast) lo = endLast;
+  }
   while (lo < hi) {
     const int mid = (lo + hi + 1) / 2;
     if (r[mid] < rmin)
@@ -111,8 +126,19 @@ void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dis
       hi = mid - 1;
   }
   *start = lo + 1;
-  lo = -1;
-  hi = endLast; /* largest j <= endLast with r[j] <= rmax (or -1) */
+  /* largest j <= endLast with r[j] <= rmax (or -1) */
+  if (rmax < 0.0) {
+    lo = hi = -1;
+  } else if (rmax * ECP_WIN_LUT_SCALE >= ECP_WIN_LUT_BINS) {
+    lo = -1;
+    hi = endLast;
+  } else {
+    const int k = (int)(rmax * ECP_WIN_LUT_SCALE);
+    lo = t->winLut[k] - 1;
+    hi = t->winLut[k + 1] - 1;
+    if (hi > endLast) hi = endLast;
+    if (lo > endLast) lo = endLast;
+  }
   while (lo < hi) {
     const int mid = (lo + hi + 1) / 2;
     if (r[mid] <= rmax)
@@ -263,6 +289,8 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   /* candidate centres are screened in parallel, a round of a few per thread at a time, until the batch is full
    * (a rank that owns 1/8 of the rows needs 8x the centres for the same batch size); then as many as fit into
    * maxTriples are taken.  Screening results of centres that do not fit are recomputed by the next call. */
+  const int prof = getenv("LIBECP_B200_BUILD_PROFILE") != NULL;
+  const double tp0 = prof ? omp_get_wtime() : 0.0;
   const int round = nthreads * 2 > 8 ? nthreads * 2 : 8;
   int cand[1024], ncand = 0, C = *centre;
   long long screened = 0;
@@ -296,6 +324,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
     return 0;
   }
 
+  const double tp1 = prof ? omp_get_wtime() : 0.0;
   /* ---- phase (b): how many centres, and where everything goes ---- */
   int ntake = 0;
   long long tri = 0;
@@ -380,6 +409,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   }
   bb->nCanon = keepCanon ? (int)nTR : 0;
 
+  const double tp2 = prof ? omp_get_wtime() : 0.0;
   /* ---- phase (c): fill, parallel over centres ---- */
 #pragma omp parallel for schedule(dynamic, 1)
   for (int i = 0; i < ntake; i++) {
@@ -420,55 +450,78 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
       lpos[c] = posCC[(size_t)c * ntake + i];
       lpair[c] = pairCC[(size_t)c * ntake + i];
     }
-    for (int ia = 0; ia < w->nSS;) {
-      int ia1 = ia;
-      while (ia1 < w->nSS && w->ssAtom[ia1] == w->ssAtom[ia]) ia1++;
-      for (int ib = ia; ib < w->nSS;) {
-        int ib1 = ib;
-        while (ib1 < w->nSS && w->ssAtom[ib1] == w->ssAtom[ib]) ib1++;
+    /* atom blocks [bs[k], bs[k+1]) and, per slot, the end of its run of equal l inside the block (shells of an atom
+     * are l-ascending): a run of partners b shares the class, so its triples go to consecutive places */
+    const int nSSw = w->nSS;
+    int *bs = malloc((size_t)(w->nAS + 2) * sizeof(int)), *runEnd = malloc((size_t)(nSSw + 1) * sizeof(int));
+    int nblk = 0;
+    for (int s = 0; s < nSSw; s++)
+      if (s == 0 || w->ssAtom[s] != w->ssAtom[s - 1]) bs[nblk++] = s;
+    bs[nblk] = nSSw;
+    for (int k = 0; k < nblk; k++)
+      for (int s = bs[k + 1] - 1, e = bs[k + 1]; s >= bs[k]; s--) {
+        if (s + 1 < bs[k + 1] && sl[s + 1] != sl[s]) e = s + 1;
+        runEnd[s] = e;
+      }
+    for (int ka = 0; ka < nblk; ka++) {
+      const int ia = bs[ka], ia1 = bs[ka + 1];
+      int anyOwn = 0;
+      for (int a = ia; a < ia1; a++) anyOwn |= w->ssOwn[a];
+      if (!anyOwn) continue; /* row ownership: nothing of this atom belongs to the rank */
+      for (int kb = ka; kb < nblk; kb++) {
+        const int ib = bs[kb], ib1 = bs[kb + 1];
         for (int a = ia; a < ia1; a++) {
-          if (!w->ssOwn[a]) continue; /* row ownership */
+          if (!w->ssOwn[a]) continue;
           const int la = sl[a], Ka = sk[a], sta = st[a], ena = en[a];
           const int *lut = &t->clsLookup[la][0][0] + Lc;
-          for (int b = (ib == ia ? a : ib); b < ib1; b++) {
-            const int gs = sta > st[b] ? sta : st[b];
-            const int ge = ena > en[b] ? ena : en[b];
-            if (!(gs < ge)) continue; /* src/libecp.c:344, identical for both types */
-            const int lb = sl[b];
+          int b = (kb == ka ? a : ib);
+          while (b < ib1) {
+            const int e = runEnd[b], lb = sl[b];
             const int c = lut[lb * (ECP_MAX_LECP + 1)];
-            const long long p = lpos[c]++;
-            bb->trA[p] = sbase + a;
-            bb->trB[p] = sbase + b;
-            bb->trPair[p] = lpair[c];
-            lpair[c] += Ka * sk[b];
-            if (needOut) {
-              bb->trOut[p] = out;
-              if (keepCanon) {
-                const int sa = w->ssShell[a], sb = w->ssShell[b];
-                const int A = w->asAtom[w->ssAtom[a]], B = w->asAtom[w->ssAtom[b]];
-                bb->cnA[cn] = A;
-                bb->cnS1[cn] = sa - t->atomFirstShell[A];
-                bb->cnB[cn] = B;
-                bb->cnS2[cn] = sb - t->atomFirstShell[B];
-                bb->cnC[cn] = w->C;
-                bb->cnLa[cn] = la;
-                bb->cnLb[cn] = lb;
-                bb->cnOut[cn] = out;
-                cn++;
+            long long p = lpos[c], pr = lpair[c];
+            for (; b < e; b++) {
+              const int gs = sta > st[b] ? sta : st[b];
+              const int ge = ena > en[b] ? ena : en[b];
+              if (!(gs < ge)) continue; /* src/libecp.c:344, identical for both types */
+              bb->trA[p] = sbase + a;
+              bb->trB[p] = sbase + b;
+              bb->trPair[p] = pr;
+              pr += Ka * sk[b];
+              if (needOut) {
+                bb->trOut[p] = out;
+                if (keepCanon) {
+                  const int sa = w->ssShell[a], sb = w->ssShell[b];
+                  const int A = w->asAtom[w->ssAtom[a]], B = w->asAtom[w->ssAtom[b]];
+                  bb->cnA[cn] = A;
+                  bb->cnS1[cn] = sa - t->atomFirstShell[A];
+                  bb->cnB[cn] = B;
+                  bb->cnS2[cn] = sb - t->atomFirstShell[B];
+                  bb->cnC[cn] = w->C;
+                  bb->cnLa[cn] = la;
+                  bb->cnLb[cn] = lb;
+                  bb->cnOut[cn] = out;
+                  cn++;
+                }
+                out += 2 * (long long)IJK(la) * IJK(lb);
               }
-              out += 2 * (long long)IJK(la) * IJK(lb);
+              p++;
             }
+            lpos[c] = p;
+            lpair[c] = pr;
           }
         }
-        ib = ib1;
       }
-      ia = ia1;
     }
+    free(bs);
+    free(runEnd);
     free(lpos);
   }
   free(asBase); free(ssBase); free(omBase); free(fBase); free(outBase); free(cnBase);
   free(posCC); free(pairCC); free(tBase); free(gBase); free(pairBase); free(qBase);
 
+  if (prof)
+    fprintf(stderr, "[builder] centres %d/%d triples %lld: screen+count %.2f ms, layout %.2f ms, fill %.2f ms\n", ntake, ncand,
+            nTR, 1e3 * (tp1 - tp0), 1e3 * (tp2 - tp1), 1e3 * (omp_get_wtime() - tp2));
   /* the screened centres that did not fit stay at the front of the scratch for the next call */
   for (int i = ntake; i < ncand; i++) {
     const CentreWork tmp = cw[i - ntake];

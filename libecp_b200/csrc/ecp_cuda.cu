@@ -709,6 +709,7 @@ struct EcpDev {
   } up[2];
   cudaStream_t s3;
   cudaEvent_t evUp[2];
+  cudaEvent_t evDone; /* blocking-sync event: the driving thread sleeps while a batch runs (its core goes to the builder) */
   const EcpBatch *upBatch[2]; /* batch whose arrays sit in the set (NULL: none) */
   long long upBytes[2];
   Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
@@ -838,6 +839,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   cudaStreamCreateWithFlags(&d->s2real, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&d->s3, cudaStreamNonBlocking);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&d->evUp[i], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&d->evDone, cudaEventDisableTiming | cudaEventBlockingSync);
   d->s2 = d->s2real;
   d->serial = getenv("LIBECP_B200_SERIAL") != NULL;
   d->tails = getenv("LIBECP_B200_TAILS") != NULL;
@@ -1080,6 +1082,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   cudaStreamDestroy(d->s2real);
   cudaStreamDestroy(d->s3);
   for (int i = 0; i < 2; i++) cudaEventDestroy(d->evUp[i]);
+  cudaEventDestroy(d->evDone);
   free(d);
 }
 
@@ -1670,7 +1673,11 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   if ((flags & 2) && hostBlocks)
     CK(cudaMemcpyAsync(hostBlocks, B.blocks, (size_t)h->outTotal * sizeof(double), cudaMemcpyDeviceToHost, d->s1));
   const double tr2 = omp_get_wtime();
-  CK(cudaStreamSynchronize(d->s1));
+  /* s1 joined the type-1 stream before the shift kernels, so the end of s1 is the end of the batch.  Wait on a
+   * blocking-sync event instead of spinning in cudaStreamSynchronize: on a box with 4 host cores per GPU the spinning
+   * thread took a third of what the batch builder (one batch ahead, other thread) could use. */
+  CK(cudaEventRecord(d->evDone, d->s1));
+  CK(cudaEventSynchronize(d->evDone));
   CK(cudaStreamSynchronize(d->s2));
   if (d->tails) { /* how long do the persistent kernels run with most of their blocks already gone? */
     unsigned long long *hb = (unsigned long long *)malloc((size_t)16 * DBG_STRIDE * 2 * sizeof(unsigned long long));

@@ -199,6 +199,10 @@ static void build_small_grid(EcpTables *t) {
     w[i] = wi;
   }
   t->small_x = x;
+  for (int k = 0, j = 0; k <= ECP_WIN_LUT_BINS; k++) { /* abscissae ascend strictly */
+    while (j < order && x[j] < k / ECP_WIN_LUT_SCALE) j++;
+    t->winLut[k] = j;
+  }
   t->small_w = w;
 
   /* level-major padded slot layout: replay the visiting order of integrateGC_PS93

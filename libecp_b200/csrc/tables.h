@@ -21,6 +21,9 @@ typedef struct {
   double *shTermBin;
   int *ijk, *ijkIndex;
   double *small_x, *small_w;   /* original order [383] (screening uses these)   */
+#define ECP_WIN_LUT_SCALE 16.0 /* bins of 1/16 bohr */
+#define ECP_WIN_LUT_BINS 640
+  int winLut[ECP_WIN_LUT_BINS + 1]; /* winLut[k] = number of small-grid points with r < k/16 (builder.c: ecp_shell_window) */
   double *small_rs, *small_ws; /* slot layout [384]                              */
   int16_t *small_oidx;
   double *large_x, *large_w;   /* original order [1023]                          */
