@@ -338,88 +338,6 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
   fast_store(b, w, rc, res, f.tri, f.l);
 }
 
-/* ---- large grid (PSM92, level-major slots): which points of a level can pass the exponent gate ----
- * Both large-grid integrands carry exp(e(r)) with e(r) = a r^2 + b r + c0, a < 0, and a point is tabulated only if
- * e >= ln(acc) (src/type1.c:163, src/type2.c:479-490): the live points are those with r between the two roots of
- * e(r) = ln(acc).  lg_live_range returns a range of ORIGINAL grid indices that contains all of them (roots widened,
- * one index of slack on each side; every point still takes the exact gate).  Within level lev the left points are the
- * original indices (2j+1) off - 1, ascending in j, and the right points their mirror images (src/gc_integrators.c:
- * 58-66), so the candidates of a level are two runs of pairs, in closed form: the persistent groups visit 8 candidates
- * per step instead of 8 consecutive slots (on the FM06-mapped grid [P-7s, P+9s] at most 73 % of the slots are live,
- * typically far fewer). */
-struct LgRange {
-  int ilo, ihi; /* inclusive; ilo > ihi: no live point */
-};
-__device__ __forceinline__ LgRange lg_live_range(const DevT &t, double a, double b, double cmln, double i1, double i2) {
-  /* a r^2 + b r + cmln >= 0, cmln = c0 - ln(acc) */
-  LgRange R;
-  const double bb = b * b, ac4 = 4.0 * a * cmln;
-  double disc = bb - ac4;
-  if (!(disc >= -1e-9 * (bb + fabs(ac4)))) {
-    R.ilo = 1;
-    R.ihi = 0;
-    return R;
-  }
-  disc = disc > 0.0 ? disc : 0.0;
-  const double sq = sqrt(disc) * (1.0 + 1e-9) + 1e-9 * fabs(b);
-  const double r1 = (-b + sq) / (2.0 * a), r2 = (-b - sq) / (2.0 * a); /* a < 0: r1 <= r2 */
-  const double m = 1e-9 * (fabs(r1) + fabs(r2) + 1.0);
-  const double x1 = (r1 - m - i2) / i1, x2 = (r2 + m - i2) / i1;
-  const double *xo = t.large_xo;
-  const int n = t.largeOrder;
-  int lo = 0, hi = n; /* first index with xo >= x1 */
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (xo[mid] < x1)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  R.ilo = lo - 1;
-  lo = 0;
-  hi = n; /* first index with xo > x2 */
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (xo[mid] <= x2)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  R.ihi = lo;
-  if (R.ilo < 0) R.ilo = 0;
-  if (R.ihi > n - 1) R.ihi = n - 1;
-  return R;
-}
-struct LgLevel {
-  int jL, nL, jR, nLive; /* left points of the pairs [jL, jL + nL), right points of the pairs [jR, jR + nLive - nL) */
-};
-__device__ __forceinline__ void lg_pair_run(int ilo, int ihi, int off, int npair, int *j0, int *n) {
-  /* pairs j with ilo <= (2j+1) off - 1 <= ihi */
-  const int a = ilo + 1 - off, b = ihi + 1 - off, o2 = 2 * off;
-  int lo = a <= 0 ? 0 : (a + o2 - 1) / o2;
-  int hi = b < 0 ? -1 : b / o2;
-  if (hi > npair - 1) hi = npair - 1;
-  *j0 = lo;
-  *n = hi >= lo ? hi - lo + 1 : 0;
-}
-__device__ __forceinline__ LgLevel lg_level(const DevT &t, LgRange R, int lev) {
-  LgLevel L;
-  const int off = t.largeSlots >> (lev + 1), npair = 1 << (lev - 1);
-  int nR;
-  if (R.ilo > R.ihi) {
-    L.jL = L.jR = L.nL = L.nLive = 0;
-    return L;
-  }
-  lg_pair_run(R.ilo, R.ihi, off, npair, &L.jL, &L.nL);
-  lg_pair_run(t.largeOrder - 1 - R.ihi, t.largeOrder - 1 - R.ilo, off, npair, &L.jR, &nR);
-  L.nLive = L.nL + nR;
-  return L;
-}
-/* slot of candidate m of the level (1 = the pad slot: nothing to do) */
-__device__ __forceinline__ int lg_slot(const LgLevel &L, int lev, int m) {
-  return (m < L.nL) ? (1 << lev) + 2 * (L.jL + m) : ((m < L.nLive) ? (1 << lev) + 2 * (L.jR + m - L.nL) + 1 : 1);
-}
-
 #include "ecp_fallback.cuh"
 
 /* ---- per triple: everything the element-parallel kernels (link, chi, shift) would otherwise chase through

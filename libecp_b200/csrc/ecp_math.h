@@ -463,6 +463,118 @@ ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, int sa, const double *_
                                npts);
 }
 
+/* Points of small-grid level v that the pair's window [gs, ge) tabulates (src/type1.c:121): the left indices of a level
+ * ascend with the pair number j and the right ones descend (src/gc_integrators.c:186-199), so they are the left points
+ * of the pairs [jLa, jLa + nLl) and the right points of the pairs [jRa, jRa + nLive - nLl) - read off the suffix tables
+ * of the fast path.  cnt = points the PS93 rule counts (left idx >= gs, right idx <= ge, :190-197). */
+struct T1Level {
+  int s0, jLa, nLl, jRa, nLive, cnt;
+};
+ECP_HD T1Level t1_level(const EcpSmallMeta *sm, const unsigned char *__restrict__ jL, const unsigned char *__restrict__ jR,
+                        int v, int gs, int ge) {
+  T1Level L;
+  L.s0 = sm->levSlot[v];
+  const int npair = (sm->levSlot[v + 1] - L.s0) >> 1;
+  const unsigned char *jl = jL + v * ECP_SMALL_SLOTS, *jr = jR + v * ECP_SMALL_SLOTS;
+  const int top = ECP_SMALL_SLOTS - 1;
+  const int lA = gs > top ? npair : jl[gs];               /* first left idx >= gs            */
+  const int lE = ge > top ? npair : jl[ge];               /* first left idx >= ge            */
+  const int rA = ge - 1 > top ? 0 : jr[ge - 1];           /* first right idx <= ge - 1       */
+  const int rE = gs < 1 ? npair : (gs - 1 > top ? 0 : jr[gs - 1]); /* first right idx <= gs - 1 */
+  const int rC = ge > top ? 0 : jr[ge];                   /* first right idx <= ge           */
+  L.jLa = lA;
+  L.nLl = lE > lA ? lE - lA : 0;
+  L.jRa = rA;
+  L.nLive = L.nLl + (rE > rA ? rE - rA : 0);
+  L.cnt = (npair - lA) + (npair - rC);
+  return L;
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Large grid (PSM92, level-major slots): which points of a level can pass the exponent gate
+ * Both large-grid integrands carry exp(e(r)) with e(r) = a r^2 + b r + c0, a < 0, and a point is tabulated only if
+ * e >= ln(acc) (src/type1.c:163, src/type2.c:479-490): the live points are those with r between the two roots of
+ * e(r) = ln(acc).  lg_live_range returns a range of ORIGINAL grid indices that contains all of them (roots widened,
+ * one index of slack on each side; every point still takes the exact gate).  Within level lev the left points are the
+ * original indices (2j+1) off - 1, ascending in j, and the right points their mirror images (src/gc_integrators.c:
+ * 58-66), so the candidates of a level are two runs of pairs, in closed form: the persistent groups visit 8 candidates
+ * per step instead of 8 consecutive slots (on the FM06-mapped grid [P-7s, P+9s] at most 73 % of the slots are live,
+ * typically far fewer).
+ * ---------------------------------------------------------------------------------------------- */
+struct LgRange {
+  int ilo, ihi; /* inclusive; ilo > ihi: no live point */
+};
+ECP_HD LgRange lg_live_range(const double *__restrict__ xo /* abscissae, original order */, int n, double a, double b,
+                             double cmln, double i1, double i2) {
+  /* a r^2 + b r + cmln >= 0, cmln = c0 - ln(acc) */
+  LgRange R;
+  const double bb = b * b, ac4 = 4.0 * a * cmln;
+  double disc = bb - ac4;
+  if (!(disc >= -1e-9 * (bb + fabs(ac4)))) {
+    R.ilo = 1;
+    R.ihi = 0;
+    return R;
+  }
+  disc = disc > 0.0 ? disc : 0.0;
+  const double sq = sqrt(disc) * (1.0 + 1e-9) + 1e-9 * fabs(b);
+  const double r1 = (-b + sq) / (2.0 * a), r2 = (-b - sq) / (2.0 * a); /* a < 0: r1 <= r2 */
+  const double m = 1e-9 * (fabs(r1) + fabs(r2) + 1.0);
+  const double x1 = (r1 - m - i2) / i1, x2 = (r2 + m - i2) / i1;
+  int lo = 0, hi = n; /* first index with xo >= x1 */
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (xo[mid] < x1)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  R.ilo = lo - 1;
+  lo = 0;
+  hi = n; /* first index with xo > x2 */
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (xo[mid] <= x2)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  R.ihi = lo;
+  if (R.ilo < 0) R.ilo = 0;
+  if (R.ihi > n - 1) R.ihi = n - 1;
+  return R;
+}
+struct LgLevel {
+  int jL, nL, jR, nLive; /* left points of the pairs [jL, jL + nL), right points of the pairs [jR, jR + nLive - nL) */
+};
+ECP_HD void lg_pair_run(int ilo, int ihi, int off, int npair, int *j0, int *n) {
+  /* pairs j with ilo <= (2j+1) off - 1 <= ihi */
+  const int a = ilo + 1 - off, b = ihi + 1 - off, o2 = 2 * off;
+  int lo = a <= 0 ? 0 : (a + o2 - 1) / o2;
+  int hi = b < 0 ? -1 : b / o2;
+  if (hi > npair - 1) hi = npair - 1;
+  *j0 = lo;
+  *n = hi >= lo ? hi - lo + 1 : 0;
+}
+ECP_HD LgLevel lg_level(int largeSlots, int largeOrder, LgRange R, int lev) {
+  LgLevel L;
+  const int off = largeSlots >> (lev + 1), npair = 1 << (lev - 1);
+  int nR;
+  if (R.ilo > R.ihi) {
+    L.jL = L.jR = L.nL = L.nLive = 0;
+    return L;
+  }
+  lg_pair_run(R.ilo, R.ihi, off, npair, &L.jL, &L.nL);
+  lg_pair_run(largeOrder - 1 - R.ihi, largeOrder - 1 - R.ilo, off, npair, &L.jR, &nR);
+  L.nLive = L.nL + nR;
+  return L;
+}
+/* slot of candidate m of the level (1 = the pad slot: nothing to do) */
+ECP_HD int lg_slot(const LgLevel &L, int lev, int m) {
+  return (m < L.nL) ? (1 << lev) + 2 * (L.jL + m) : ((m < L.nLive) ? (1 << lev) + 2 * (L.jR + m - L.nL) + 1 : 1);
+}
+
+
 /* the PSM92 convergence test alone (kernels that keep the one division of the result out of the per-level code) */
 ECP_HD int ecp_psm92_test(int nNew, double tol, double I, double pv, double qv) {
   const double N = nNew + 1.0;

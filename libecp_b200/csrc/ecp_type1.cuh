@@ -113,32 +113,6 @@ __device__ __forceinline__ void t1_fill_point(const DevT &t, double r, double za
   }
 }
 
-/* Points of small-grid level v that the pair's window [gs, ge) tabulates (src/type1.c:121): the left indices of a level
- * ascend with the pair number j and the right ones descend (src/gc_integrators.c:186-199), so they are the left points
- * of the pairs [jLa, jLa + nLl) and the right points of the pairs [jRa, jRa + nLive - nLl) - read off the suffix tables
- * of the fast path.  cnt = points the PS93 rule counts (left idx >= gs, right idx <= ge, :190-197). */
-struct T1Level {
-  int s0, jLa, nLl, jRa, nLive, cnt;
-};
-__device__ __forceinline__ T1Level t1_level(const DevT &t, int v, int gs, int ge) {
-  T1Level L;
-  L.s0 = t.sm.levSlot[v];
-  const int npair = (t.sm.levSlot[v + 1] - L.s0) >> 1;
-  const unsigned char *jl = t.small_jL + v * ECP_SMALL_SLOTS, *jr = t.small_jR + v * ECP_SMALL_SLOTS;
-  const int top = ECP_SMALL_SLOTS - 1;
-  const int lA = gs > top ? npair : jl[gs];               /* first left idx >= gs            */
-  const int lE = ge > top ? npair : jl[ge];               /* first left idx >= ge            */
-  const int rA = ge - 1 > top ? 0 : jr[ge - 1];           /* first right idx <= ge - 1       */
-  const int rE = gs < 1 ? npair : (gs - 1 > top ? 0 : jr[gs - 1]); /* first right idx <= gs - 1 */
-  const int rC = ge > top ? 0 : jr[ge];                   /* first right idx <= ge           */
-  L.jLa = lA;
-  L.nLl = lE > lA ? lE - lA : 0;
-  L.jRa = rA;
-  L.nLive = L.nLl + (rE > rA ? rE - rA : 0);
-  L.cnt = (npair - lA) + (npair - rC);
-  return L;
-}
-
 /* ---------------------------------------------------------------------------------------------- */
 template <int LAB>
 __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_type1S(DevT t, DevB b, T1Segs segs, int *workCtr, int *failCount, int *failList,
@@ -196,7 +170,7 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
           c = 0;
           v = 4;
           ks = 0;
-          lv = t1_level(t, 4, gs, ge);
+          lv = t1_level(&t.sm, t.small_jL, t.small_jR, 4, gs, ge);
           have = true;
         } else {
           drained = true;
@@ -295,7 +269,7 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
       } else if (last) {
         v++;
         ks = 0;
-        if (v < ECP_SMALL_LEVELS) lv = t1_level(t, v, gs, ge);
+        if (v < ECP_SMALL_LEVELS) lv = t1_level(&t.sm, t.small_jL, t.small_jR, v, gs, ge);
       } else {
         ks++;
       }
@@ -388,8 +362,8 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
           lev = 3;
           n = 7;
           ks = 0;
-          lr = lg_live_range(t, z, sS, zd2 - t.lnAcc1, i1, i2);
-          lv = lg_level(t, lr, 3);
+          lr = lg_live_range(t.large_xo, t.largeOrder, z, sS, zd2 - t.lnAcc1, i1, i2);
+          lv = lg_level(t.largeSlots, t.largeOrder, lr, 3);
           have = true;
         } else {
           drained = true;
@@ -461,7 +435,7 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
         n = 2 * n + 1;
         lev++;
         ks = 0;
-        if (lev <= t.largeLevels) lv = lg_level(t, lr, lev);
+        if (lev <= t.largeLevels) lv = lg_level(t.largeSlots, t.largeOrder, lr, lev);
       } else {
         ks++;
       }

@@ -303,3 +303,74 @@ def test_device_math_ps93_windowed_bitwise(hc):
                 assert r1[0] == r2[0]
         assert 0 < nfail < 200
     o.close()
+
+
+def _small_layout(h):
+    oidx = h.host_itable("small_oidx").astype(np.int32)
+    meta = h.host_itable("small_meta").astype(np.int32)
+    return oidx, meta
+
+
+def test_type1_small_grid_levelwise_points_are_exactly_the_window(hc):
+    """k_type1S visits, per level, the points t1_level lists instead of all slots: they must be exactly the slots of the
+    level whose original index lies in the tabulated window [gs, ge) (reference src/type1.c:121), and cnt the number of
+    points PS93 counts (left idx >= gs, right idx <= ge; src/gc_integrators.c:190-197)"""
+    hc.hc_t1_level_slots.argtypes = [_pi, _pi, C.c_int, C.c_int, C.c_int, _pi, C.POINTER(C.c_int)]
+    with capi.Handle(synth.cfg2(), tables_only=True) as h:
+        oidx, meta = _small_layout(h)
+    lev_slot = meta[39:53]
+    rng = np.random.default_rng(5)
+    windows = [(0, 383), (0, 1), (382, 383), (100, 101), (0, 200), (191, 192)]
+    windows += [tuple(sorted(rng.integers(0, 384, 2))) for _ in range(300)]
+    out = np.zeros(400, np.int32)
+    for gs, ge in windows:
+        if not gs < ge:
+            continue
+        for v in range(4, 13):
+            cnt = C.c_int(0)
+            n = hc.hc_t1_level_slots(_p(oidx, _pi), _p(meta, _pi), v, int(gs), int(ge), _p(out, _pi), C.byref(cnt))
+            s0, s1 = int(lev_slot[v]), int(lev_slot[v + 1])
+            sl = np.arange(s0, s1)
+            oi = oidx[sl]
+            want = sl[(oi >= gs) & (oi < ge)]
+            assert n >= 0 and sorted(out[:n].tolist()) == want.tolist(), (gs, ge, v)
+            left, right = sl[0::2], sl[1::2]
+            assert cnt.value == int((oidx[left] >= gs).sum() + (oidx[right] <= ge).sum()), (gs, ge, v)
+
+
+def test_large_grid_levelwise_candidates_cover_every_live_point(hc):
+    """k_type1L / the gate bracket: the candidates of a level (lg_live_range + lg_level) contain every slot whose
+    exponent passes the gate e(r) >= ln(acc) (reference src/type2.c:479-490, src/type1.c:163), and far fewer slots than
+    the level has"""
+    hc.hc_lg_level_slots.argtypes = [_pd, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_int, _pi]
+    hc.hc_fm06_map.argtypes = [C.c_double, C.c_double, _pd, _pd]
+    with capi.Handle(synth.cfg2(), tables_only=True) as h:
+        xo = h.host_table("large_x")
+        xs = h.host_table("large_xs")
+    order, slots = len(xo), len(xs)
+    ln_acc = np.log(1e-14) - 2.0
+    rng = np.random.default_rng(11)
+    out = np.zeros(slots, np.int32)
+    tot = cand = live_n = 0
+    for it in range(400):
+        zA = 60.0 * 2.6 ** (-float(rng.integers(0, 9)))
+        zB = 24.0 * 2.6 ** (-float(rng.integers(0, 9)))
+        dAC, dBC = float(rng.choice([0.0, 1e-3, 4.5, 5.45, 9.44, 10.9, 31.0])), float(rng.choice([0.0, 5.45, 9.44, 22.0]))
+        zp = zA + zB
+        i1, i2 = np.zeros(1), np.zeros(1)
+        hc.hc_fm06_map(zp, (zA * dAC + zB * dBC) / zp, _p(i1, _pd), _p(i2, _pd))
+        r = i1[0] * xs + i2[0]
+        e = -zA * (dAC - r) ** 2 - zB * (dBC - r) ** 2
+        live = e >= ln_acc
+        a, b, c0 = -zp, 2.0 * (zA * dAC + zB * dBC), -(zA * dAC * dAC + zB * dBC * dBC)
+        for lev in range(3, 10):
+            n = hc.hc_lg_level_slots(_p(xo, _pd), order, slots, a, b, c0 - ln_acc, float(i1[0]), float(i2[0]), lev, _p(out, _pi))
+            got = set(out[:n].tolist())
+            lo, hi = 1 << lev, 2 << lev
+            assert all(lo <= s < hi for s in got) and len(got) == n
+            need = set((np.nonzero(live[lo:hi])[0] + lo).tolist())
+            assert need <= got, (zA, zB, dAC, dBC, lev)
+            tot += hi - lo
+            cand += n
+            live_n += len(need)
+    assert cand < 0.6 * tot and cand <= live_n + 4 * 7 * 400  # at most a point or two of slack per run and level
