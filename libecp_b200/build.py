@@ -54,7 +54,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     headers += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     objs = []
     log = []
-    for name in ("tables.c", "builder.c", "api.c"):
+    for name in ("tables.c", "builder.c", "api.c", "loaders.c"):
         src = os.path.join(CSRC, name)
         obj = os.path.join(objdir, name[:-2] + ".o")
         if force or _stale(obj, [src] + headers):

@@ -50,12 +50,12 @@ def test_cabi_exports_every_declared_symbol():
     """the shared library loads without a GPU and exports every function include/*.h declares"""
     L = capi.lib()
     declared = set()
-    for hdr in ("libecp.h", "getIntegrals.h", "dimensions.h", "libecp_b200.h"):
+    for hdr in ("libecp.h", "getIntegrals.h", "dimensions.h", "libecp_b200.h", "libecp_b200_io.h"):
         txt = open(os.path.join(ROOT, "include", hdr)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", txt):
             name = m.group(1)
-            if name.startswith(("libECP_", "libecp_b200_", "cartesianShellOrder")) or name in (
+            if name.startswith(("libECP_", "libecp_b200_", "libecp_io_", "cartesianShellOrder")) or name in (
                     "calculateECPIntegrals", "getIntegrals"):
                 declared.add(name)
     assert {"libECP_init", "calculateECPIntegrals", "libECP_free", "getIntegrals"} <= declared
@@ -374,3 +374,99 @@ def test_large_grid_levelwise_candidates_cover_every_live_point(hc):
             cand += n
             live_n += len(need)
     assert cand < 0.6 * tot and cand <= live_n + 4 * 7 * 400  # at most a point or two of slack per run and level
+
+
+_ECP_SHIPPED_FORMAT = """6 2 4
+  0 1
+          37.4565000               6.8446000  2
+  1 1
+          -2.6739000               7.9317000  2
+  2 1
+          -0.5945000               6.0209000  2
+  3 1
+           0.0000000               1.0000000  2
+"""
+
+
+def _write_bs(path, s):
+    """a basis-set file in the layout of the reference's example input, written from the arrays"""
+    with open(path, "w") as f:
+        sh = p = 0
+        for a in range(int(s["nat"])):
+            f.write(f"6 {int(s['shellsBS'][a])}\n")
+            for _ in range(int(s["shellsBS"][a])):
+                f.write(f" {int(s['lBS'][sh])} {int(s['KBS'][sh])}\n")
+                for k in range(int(s["KBS"][sh])):
+                    f.write(f"  {k + 1}  {float(s['aBS'][p])!r}   {float(s['dBS'][p])!r}\n")
+                    p += 1
+                sh += 1
+
+
+def test_loaders_reproduce_config1_and_the_corrected_reading(tmp_path):
+    """include/libecp_b200_io.h: the text loaders give configuration 1 ("as shipped": the reference's loader applied to
+    the shipped ECP format) array for array; the corrected reading keeps signs and columns; broken
+    files are reported, not read past"""
+    from libecp_b200 import io as ecpio
+
+    ref = synth.cfg1()
+    (tmp_path / "c.xyz").write_text("1\ncarbon atom\nC 0.0 0.0 0.0\n")
+    (tmp_path / "c.ecp").write_text(_ECP_SHIPPED_FORMAT * 2)  # the shipped file holds two carbon blocks
+    _write_bs(tmp_path / "c.bs", ref)
+    got = ecpio.load(tmp_path / "c.xyz", tmp_path / "c.ecp", tmp_path / "c.bs")
+    for k in ("nat", "dim", "nshells"):
+        assert got[k] == ref[k], k
+    for k in ("geometry", "shellsECP", "lECP", "KECP", "nECP", "dECP", "aECP", "shellsBS", "lBS", "KBS", "dBS", "aBS"):
+        assert np.array_equal(np.asarray(got[k]), np.asarray(ref[k])), k
+    fixed = ecpio.load(tmp_path / "c.xyz", tmp_path / "c.ecp", tmp_path / "c.bs", ecp_format=ecpio.SHIPPED)
+    assert np.array_equal(fixed["dECP"], [37.4565, -2.6739, -0.5945, 0.0])
+    assert np.array_equal(fixed["aECP"], [6.8446, 7.9317, 6.0209, 1.0])
+    assert np.array_equal(fixed["nECP"], [2.0, 2.0, 2.0, 2.0]) and np.array_equal(fixed["lECP"], [0, 1, 2, 3])
+    # two atoms: second block of the same files
+    (tmp_path / "c2.xyz").write_text("2\n\nC 0 0 0\nC 0.0 0.0 2.5e0\n")
+    two = dict(ref)
+    two.update(nat=2, shellsBS=np.concatenate([ref["shellsBS"]] * 2), lBS=np.concatenate([ref["lBS"]] * 2),
+               KBS=np.concatenate([ref["KBS"]] * 2), aBS=np.concatenate([ref["aBS"]] * 2), dBS=np.concatenate([ref["dBS"]] * 2))
+    _write_bs(tmp_path / "c2.bs", two)
+    g2 = ecpio.load(tmp_path / "c2.xyz", tmp_path / "c.ecp", tmp_path / "c2.bs")
+    assert g2["nat"] == 2 and g2["dim"] == 10 and np.array_equal(g2["geometry"], [0, 0, 0, 0, 0, 2.5])
+    assert np.array_equal(g2["aECP"], np.concatenate([ref["aECP"]] * 2)) and np.array_equal(g2["shellsECP"], [4, 4])
+    # errors: missing file, truncated file, three atoms but two blocks
+    with pytest.raises(OSError):
+        ecpio.load(tmp_path / "nope.xyz", tmp_path / "c.ecp", tmp_path / "c.bs")
+    (tmp_path / "short.ecp").write_text(_ECP_SHIPPED_FORMAT[:60])
+    with pytest.raises(OSError):
+        ecpio.load(tmp_path / "c.xyz", tmp_path / "short.ecp", tmp_path / "c.bs")
+    (tmp_path / "c3.xyz").write_text("3\n\nC 0 0 0\nC 0 0 2\nC 0 0 4\n")
+    with pytest.raises(OSError):
+        ecpio.load(tmp_path / "c3.xyz", tmp_path / "c.ecp", tmp_path / "c2.bs")
+
+
+def test_loaders_on_the_shipped_example_files():
+    """the reference's own example inputs (read only where the reference tree is present: this container)"""
+    from libecp_b200 import io as ecpio
+
+    d = "/root/reference/example"
+    if not os.path.exists(os.path.join(d, "test_c.ecp")):
+        pytest.skip("reference tree not present")
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        xyz = os.path.join(tmp, "c.xyz")
+        open(xyz, "w").write("1\nC\nC 0 0 0\n")
+        got = ecpio.load(xyz, os.path.join(d, "test_c.ecp"), os.path.join(d, "test_c.bs"))
+    ref = synth.cfg1()
+    for k in ("shellsECP", "lECP", "KECP", "nECP", "dECP", "aECP", "shellsBS", "lBS", "KBS", "dBS", "aBS"):
+        assert np.array_equal(np.asarray(got[k]), np.asarray(ref[k])), k
+
+
+def test_example_program_compiles_against_the_public_headers(tmp_path):
+    """examples/ex1.c (the reference's example program on this library) builds with nothing but include/ and the .so"""
+    import subprocess
+
+    exe = tmp_path / "ex1"
+    cmd = ["gcc", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "ex1.c"),
+           "-L", os.path.dirname(capi.SO_PATH), "-lecp_b200", "-Wl,-rpath," + os.path.dirname(capi.SO_PATH), "-o", str(exe)]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout
+    p = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 2 and "usage" in p.stdout
