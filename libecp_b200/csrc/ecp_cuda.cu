@@ -458,6 +458,105 @@ typedef void (*LinkKernel)(DevT, DevB, int);
 static const LinkKernel g_linkKernels[ECP_MAX_LBS + 1][ECP_MAX_LBS + 1] = {LINK_ROW(1), LINK_ROW(2), LINK_ROW(3),
                                                                            LINK_ROW(4), LINK_ROW(5), LINK_ROW(6)};
 
+/* ---- link, experimental variant (OFF by default; LIBECP_B200_LINK=smem): Omega slices and T staged in shared memory ----
+ * Why: k_link is bound by the L2 latency of its Omega loads (ncu, profiles/r1: ~9 warps stalled on the long scoreboard
+ * per issue, L1 hit rate 78 %): every thread of a triple walks the same two small slices - Omega_A rows
+ * [lambda < la+L][(l,m) < L^2][p < C_DIM(la)] and the same for B - each value being read by C_DIM(lb) resp. C_DIM(la)
+ * threads, one dependent global load at a time.  Here a block takes `tpb` consecutive triples of the class, copies
+ * their slices (rows of Omega_X truncated to the shell's C_DIM: d-d, L = 4: 2 x 960 doubles) and their T values into
+ * shared memory with coalesced, independent loads, and then runs exactly the loop nest of k_link on shared memory
+ * (same operations in the same order: gamma must come out bit-identical to k_link's).
+ * Only for classes with at least LINK2_MIN_ELEMS gamma elements per triple (the staged values are reused by that many
+ * threads) and slices that fit; everything else keeps k_link.
+ * STATUS: written at the end of round 1 after the GPU budget was spent - compiles, never run.  To try it:
+ *   LIBECP_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_parity.py -k link_smem      (parity with k_link)
+ *   python tools/ab_kernels.py cfg3 LIBECP_B200_LINK=-,smem                                (A/B timing) */
+#define LINK2_MIN_ELEMS 40
+#define LINK2_MAX_SMEM (46 * 1024)
+template <int NA, int NB>
+__global__ void __launch_bounds__(128) k_link2(DevT t, DevB b, int c, int tpb, int slotStride) {
+  constexpr int la = NA - 1, lb = NB - 1;
+  constexpr int cda = (la + 1) * (la + 2) * (la + 3) / 6, cdb = (lb + 1) * (lb + 2) * (lb + 3) / 6, E = cda * cdb;
+  extern __shared__ __align__(16) double lk_sm[];
+  const int L = t.clsL[c], L2 = L * L, nq = t.clsNq[c];
+  const int SA = (la + L) * L2 * cda, SB = (lb + L) * L2 * cdb;
+  const int nTri = b.clsFirst[c + 1] - b.clsFirst[c];
+  const int lt0 = blockIdx.x * tpb; /* first triple of the block, class-local */
+  /* ---- stage: every thread of the block copies, triple after triple ---- */
+  for (int s = 0; s < tpb && lt0 + s < nTri; s++) {
+    const TriRec rec = b.trirec[b.clsFirst[c] + lt0 + s];
+    double *A = lk_sm + (size_t)s * slotStride, *Bm = A + SA, *Ts = Bm + SB;
+    const double *gA = b.omX + rec.omA, *gB = b.omX + rec.omB;
+    for (int i = threadIdx.x; i < SA; i += blockDim.x) {
+      const int row = i / cda; /* row = lambda * L^2 + (l,m): rows of Omega_X are incA1 apart */
+      A[i] = gA[(size_t)row * rec.incA1 + (i - row * cda)];
+    }
+    for (int i = threadIdx.x; i < SB; i += blockDim.x) {
+      const int row = i / cdb;
+      Bm[i] = gB[(size_t)row * rec.incB1 + (i - row * cdb)];
+    }
+    const double *gT = b.T + b.clsWork[c] + (long long)(lt0 + s) * nq;
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) Ts[i] = gT[i];
+  }
+  __syncthreads();
+  /* ---- compute: thread -> (triple slot, element); triples with more than 128 elements loop ---- */
+  const int16_t *qi = t.qidx + t.clsQidxOff[c];
+  const int d2 = lb + L, d3 = la + lb + 1;
+  const int incA1 = cda, incA2 = L2 * cda, incB1 = cdb, incB2 = L2 * cdb; /* strides inside the staged slices */
+  for (int e = threadIdx.x; e < tpb * E; e += blockDim.x) {
+    const int s = e / E, pq = e - s * E;
+    if (lt0 + s >= nTri) break;
+    const int p = pq / cdb, q = pq - p * cdb;
+    const int alpha = deg_of_cindex(p), beta = deg_of_cindex(q);
+    const double *oA = lk_sm + (size_t)s * slotStride + p, *oB = lk_sm + (size_t)s * slotStride + SA + q;
+    const double *T = lk_sm + (size_t)s * slotStride + SA + SB;
+    double g = 0.0;
+    for (int l = 0; l < L; l++) {
+      int ll1 = l - alpha, ll2 = l - beta;
+      const int par1 = (alpha + l) % 2, par2 = (beta + l) % 2;
+      ll1 = (par1 > ll1) ? par1 : ll1;
+      ll2 = (par2 > ll2) ? par2 : ll2;
+      const int n1 = (la + l - ll1) / 2 + 1, n2 = (lb + l - ll2) / 2 + 1;
+      double f[NA][NB];
+#pragma unroll
+      for (int i = 0; i < NA; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) f[i][j] = 0.0;
+      const double *pa = oA + ll1 * incA2 + (l * l) * incA1;
+      const double *pb = oB + ll2 * incB2 + (l * l) * incB1;
+      for (int m = 0; m < 2 * l + 1; m++) {
+        double a[NA], bb[NB];
+#pragma unroll
+        for (int i = 0; i < NA; i++) a[i] = (i < n1) ? pa[(2 * i) * incA2] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NB; j++) bb[j] = (j < n2) ? pb[(2 * j) * incB2] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NA; i++)
+#pragma unroll
+          for (int j = 0; j < NB; j++) f[i][j] = fma(a[i], bb[j], f[i][j]);
+        pa += incA1;
+        pb += incB1;
+      }
+      double tmp = 0.0;
+      const int16_t *ql = qi + ((l * (la + L) + ll1) * d2 + ll2) * d3 + alpha + beta;
+#pragma unroll
+      for (int i = 0; i < NA; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++)
+          if (i < n1 && j < n2) {
+            const int k = ql[(2 * i * d2 + 2 * j) * d3];
+            if (k >= 0) tmp = fma(f[i][j], T[k], tmp);
+          }
+      g += tmp;
+    }
+    b.gamma[b.clsElem[c] + (long long)(lt0 + s) * E + pq] = g;
+  }
+}
+typedef void (*Link2Kernel)(DevT, DevB, int, int, int);
+#define LINK2_ROW(A) {k_link2<A, 1>, k_link2<A, 2>, k_link2<A, 3>, k_link2<A, 4>, k_link2<A, 5>, k_link2<A, 6>}
+static const Link2Kernel g_link2Kernels[ECP_MAX_LBS + 1][ECP_MAX_LBS + 1] = {LINK2_ROW(1), LINK2_ROW(2), LINK2_ROW(3),
+                                                                             LINK2_ROW(4), LINK2_ROW(5), LINK2_ROW(6)};
+
 #include "ecp_type1.cuh"
 
 /* ---- type 1, per primitive pair: P = 2(za r_AC + zb r_BC), |P|, S_lm(P^), and the pair record of the radial kernels ---- */
@@ -638,8 +737,9 @@ struct EcpDev {
   Buf dirtyRows, gatherRows, gatherOff;
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
-  int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES];
+  int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES], hClsL[ECP_MAX_CLASSES], hClsNq[ECP_MAX_CLASSES];
   Buf fastSurv;
+  int linkSmem; /* LIBECP_B200_LINK=smem: experimental shared-memory link kernel for the large classes (k_link2) */
   int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
   long long survCapEnv; /* LIBECP_B200_SURVCAP: survivor-list capacity override (tests of the overflow path) */
   Buf t1list, t1mask, t1count, t1work, t1rec, trirec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
@@ -764,6 +864,10 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   {
     const char *e = getenv("LIBECP_B200_FASTLIM");
     d->fastLim = e ? atoi(e) : 4;
+    {
+      const char *lk = getenv("LIBECP_B200_LINK");
+      d->linkSmem = lk && !strcmp(lk, "smem");
+    }
     if (d->fastLim < 1) d->fastLim = 1;
     e = getenv("LIBECP_B200_SURVCAP");
     d->survCapEnv = e ? atoll(e) : 0;
@@ -885,6 +989,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   for (int c = 0; c < h->nClasses; c++) {
     d->hClsLa[c] = h->clsLa[c];
     d->hClsLb[c] = h->clsLb[c];
+    d->hClsL[c] = h->clsL[c];
+    d->hClsNq[c] = h->clsNq[c];
   }
   d->maxQPerL = h->maxQPerL;
   d->nAO = h->nAO;
@@ -1560,7 +1666,22 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   for (int c = 0; c < nc; c++) { /* one launch per class: the (lambda1, lambda2) tile is sized by (la, lb) */
     const long long ne = h->clsElem[c + 1] - h->clsElem[c];
     if (ne <= 0) continue;
-    g_linkKernels[d->hClsLa[c]][d->hClsLb[c]]<<<nblk(ne, 128), 128, 0, d->s1>>>(t, B, c);
+    const int la_ = d->hClsLa[c], lb_ = d->hClsLb[c], Lc_ = d->hClsL[c];
+    const int E_ = ((la_ + 1) * (la_ + 2) * (la_ + 3) / 6) * ((lb_ + 1) * (lb_ + 2) * (lb_ + 3) / 6);
+    if (d->linkSmem && E_ >= LINK2_MIN_ELEMS) { /* experimental, off by default (see k_link2) */
+      const int SA = (la_ + Lc_) * Lc_ * Lc_ * ((la_ + 1) * (la_ + 2) * (la_ + 3) / 6);
+      const int SB = (lb_ + Lc_) * Lc_ * Lc_ * ((lb_ + 1) * (lb_ + 2) * (lb_ + 3) / 6);
+      const int slotStride = SA + SB + d->hClsNq[c] + 1;
+      const int tpb = E_ >= 128 ? 1 : 128 / E_;
+      const size_t smem = (size_t)tpb * slotStride * sizeof(double);
+      if (smem <= LINK2_MAX_SMEM) {
+        const long long ntri = h->clsFirst[c + 1] - h->clsFirst[c];
+        g_link2Kernels[la_][lb_]<<<nblk(ntri, tpb), 128, smem, d->s1>>>(t, B, c, tpb, slotStride);
+        launches++;
+        continue;
+      }
+    }
+    g_linkKernels[la_][lb_]<<<nblk(ne, 128), 128, 0, d->s1>>>(t, B, c);
     launches++;
   }
   CK(cudaEventRecord(d->ev[4], d->s1));

@@ -233,3 +233,21 @@ def test_gather_pack_unpack_rebuilds_the_full_matrix():
         rc, M = h0.integrals_host()
         rc1, M1 = h1.integrals_host()
         assert_parity(M + M1, ref, "shard union after a gather")
+
+
+@pytest.mark.skipif(not os.environ.get("LIBECP_B200_EXPERIMENTAL"),
+                    reason="experimental kernels are opt-in: set LIBECP_B200_EXPERIMENTAL=1")
+def test_link_smem_variant_matches_default():
+    """k_link2 (LIBECP_B200_LINK=smem, off by default: Omega slices and T staged in shared memory) performs the
+    operations of k_link in the same order: gamma must be bit-identical and the matrices equal to the last ulps"""
+    for s, name in ((synth.cfg3(4), "au4"), (synth.cfg4("a"), "cfg4a")):
+        def run():
+            with capi.Handle(s) as h:
+                rc, M = h.integrals_host()
+                n = 200000
+                return M, h.debug_fetch("gamma", n)
+        base, g0 = run()
+        assert_parity(base, load_matrix(name), name)
+        got, g1 = _with_env({"LIBECP_B200_LINK": "smem"}, run)
+        assert np.array_equal(g0, g1), name
+        assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
