@@ -5,16 +5,19 @@
  *  the same doubles as the reference takes them; see ecp_math.h).
  *
  * Kernel map (reference code each one replaces, paths relative to /root/reference):
+ *   k_triprep    one record per triple + the pair -> triple map                 (indices only)
  *   k_atomslot   S_lm(r_XC) and (-x)^i(-y)^j(-z)^k per (C, atom)          src/util.c:214-243, spherical_harmonics.c
  *   k_omegaX     Omega_X = sum_mu S_lam,mu Omega per (C, atom)            src/angular_integrals.c:104-142
  *   k_Ftab       contracted radial table F_lambda(r_n) per (C, shell)     src/type2.c:284-303
  *   k_fastT(2)   type-2 fast path, PS93 on Fa*Fb*r^N U_l, two launches    src/type2.c:336-381
  *   k_fallbackG  type-2 large-grid fallback, PSM92 per primitive pair     src/type2.c:417-528   (ecp_fallback.cuh)
  *   k_link       gamma = sum Omega_A Omega_B T, one launch per class      src/type2.c:583-623
+ *   k_link2      the same on shared-memory slices (experimental, off by default)
  *   k_t1prep     P, |P|, S_lm(P^), pair record per primitive pair         src/type1.c:235-252
  *   k_type1S/L   radial Q(N,lambda): PS93 small grid, PSM92 fallback      src/type1.c:94-208    (ecp_type1.cuh)
- *   k_chi        chi = sum (S.poly2sph) Q                                 src/type1.c:266-295
+ *   k_chi        chi = sum poly2sph (sum_pairs S Q), 8 lanes per triple   src/type1.c:266-295
  *   k_shift      binomial shift to A/B, x4pi / x16pi^2, block + matrix    src/util.c:246-334, getIntegrals.c:22-43
+ *   k_zero_rows, k_pack_rows, k_unpack_rows   result matrix: partial clear, packed rows for D2H / the all-gather
  */
 #include <cuda_runtime.h>
 #include <omp.h>
@@ -1227,10 +1230,6 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   CK(cudaStreamSynchronize(d->s1));
   const int n = d->nAO;
   const size_t panelBytes = (size_t)24 << 20;
-  int rowsPer = (int)(panelBytes / ((size_t)n * sizeof(double)));
-  if (rowsPer < 1) rowsPer = 1;
-  if (rowsPer > n) rowsPer = n;
-  (void)rowsPer;
   /* rows this rank owns (all rows when rowOwned == NULL): a sharded rank's partial matrix is zero outside the AO
    * rows of its shells, so other rows are never transferred.  The upper-triangle parts M[i][i..n) of the owned
    * rows are packed back to back on the device (k_pack_rows), moved in panels of ~24 MB with one contiguous copy

@@ -19,27 +19,60 @@ def shard_layout(h, world):
     return rows, [h.packed_size(x) for x in rows]
 
 
+def allgather_shards(pack, unpack, rows, sizes, rank, world, device, group=None, buffers=None):
+    """The collective step alone: `pack(rows, tensor)` fills the send buffer with this rank's packed rows,
+    `unpack(rows, tensor)` scatters another rank's shard.  One all-gather of shards padded to the largest one.
+    (The CUDA path passes the C-ABI kernels; the CPU tier runs the same code over gloo with numpy callables.)"""
+    import torch
+    import torch.distributed as dist
+
+    cap = max(max(sizes), 1)  # all_gather wants equal shards: pad to the largest
+    if buffers is None or buffers[0].numel() < cap:
+        buffers = (torch.zeros(cap, dtype=torch.float64, device=device),
+                   torch.empty(world * cap, dtype=torch.float64, device=device))
+    send, recv = buffers
+    pack(rows[rank], send[:cap])
+    dist.all_gather_into_tensor(recv[: world * cap], send[:cap], group=group)
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    for r in range(world):
+        if r != rank:
+            unpack(rows[r], recv[r * cap:(r + 1) * cap])
+    return buffers
+
+
 def allgather_matrix(h, rank, world, group=None, buffers=None):
     """Call after h.integrals_device() on every rank.  On return the handle's device matrix holds the full
     upper-triangular ECP matrix on every rank.  Returns (seconds, bytes received per rank, buffers); pass `buffers`
     back in to reuse the staging tensors."""
     import torch
-    import torch.distributed as dist
 
     rows, sizes = shard_layout(h, world)
-    cap = max(sizes)  # all_gather wants equal shards: pad to the largest
-    if buffers is None or buffers[0].numel() < cap:
-        buffers = (torch.zeros(cap, dtype=torch.float64, device="cuda"),
-                   torch.empty(world * cap, dtype=torch.float64, device="cuda"))
-    send, recv = buffers
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    h.pack_rows(rows[rank], send.data_ptr(), cap)
-    dist.all_gather_into_tensor(recv[: world * cap], send[:cap], group=group)
-    torch.cuda.current_stream().synchronize()
-    for r in range(world):
-        if r != rank:
-            h.unpack_rows(rows[r], recv[r * cap:].data_ptr(), cap)
+    buffers = allgather_shards(lambda r, t: h.pack_rows(r, t.data_ptr(), t.numel()),
+                               lambda r, t: h.unpack_rows(r, t.data_ptr(), t.numel()),
+                               rows, sizes, rank, world, "cuda", group=group, buffers=buffers)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return dt, 8 * (sum(sizes) - sizes[rank]), buffers
+
+
+def numpy_pack(M, rows, out):
+    """host mirror of k_pack_rows: the upper-triangle parts M[i][i:] of `rows`, back to back (tests, CPU tier)"""
+    o = 0
+    n = M.shape[0]
+    for i in rows:
+        out[o:o + n - i] = M[i, i:]
+        o += n - i
+    return o
+
+
+def numpy_unpack(M, rows, packed):
+    """host mirror of k_unpack_rows"""
+    o = 0
+    n = M.shape[0]
+    for i in rows:
+        M[i, i:] = packed[o:o + n - i]
+        o += n - i
+    return o

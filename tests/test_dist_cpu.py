@@ -51,8 +51,29 @@ def _worker(rank, world, port, out):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     share = torch.tensor([len(mine) / max(len(full), 1)], dtype=torch.float64)
     dist.all_reduce(share, op=dist.ReduceOp.MAX)
+    # device-resident gather, host logic over gloo: every rank fills the rows it owns of a known matrix, one
+    # all-gather of the padded packed shards, scatter of the other ranks' rows -> the full upper triangle everywhere
+    from libecp_b200 import gather
+
+    n = int(s["dim"])
+    with capi.Handle(s, tables_only=True) as h:
+        rows, sizes = gather.shard_layout(h, world)
+        first = np.concatenate([[0], np.cumsum([(l + 1) * (l + 2) // 2 for l in s["lBS"]])])
+        shell_first = np.concatenate([[0], np.cumsum(s["shellsBS"])])
+        # AO rows of the row shells of my triples must be among the rows the layout gives me
+        my_row_shells = np.unique(shell_first[mine[:, 0]] + mine[:, 1])
+        mine_ok = all(set(range(first[x], first[x + 1])) <= set(rows[rank].tolist()) for x in my_row_shells)
+    want = np.triu(np.arange(n * n, dtype=np.float64).reshape(n, n) + 0.5)
+    M = np.zeros((n, n))
+    for i in rows[rank]:
+        M[i, i:] = want[i, i:]
+    gather.allgather_shards(lambda r, t: gather.numpy_pack(M, r, t.numpy()), lambda r, t: gather.numpy_unpack(M, r, t.numpy()),
+                            rows, sizes, rank, world, "cpu")
+    gflag = torch.tensor([1 if (mine_ok and np.array_equal(M, want) and sum(sizes) == n * (n + 1) // 2) else 0],
+                         dtype=torch.int64)
+    dist.all_reduce(gflag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        out.put((int(flag), float(share), total, len(full), len(pairs_mine)))
+        out.put((int(flag) * int(gflag), float(share), total, len(full), len(pairs_mine)))
     dist.barrier()
     dist.destroy_process_group()
 
