@@ -470,3 +470,37 @@ def test_example_program_compiles_against_the_public_headers(tmp_path):
     assert p.returncode == 0, p.stdout
     p = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert p.returncode == 2 and "usage" in p.stdout
+
+
+def test_screening_windows_identical_over_many_distances():
+    """the lookup-bracketed window searches of the builder give the reference's integers (src/type2.c:148-180) for
+    shells at distances from 1e-3 to 60 bohr of centres with different potential cut-offs (two ECP kinds), including
+    shells that are skipped and windows clipped by the potential"""
+    rng = np.random.default_rng(3)
+    dists = np.concatenate([[1e-3, 0.05, 0.0625, 0.125, 1.0, 36.9, 37.3, 40.0, 60.0], rng.uniform(0.0, 45.0, 60)])
+    coords = [(0.0, 0.0, 0.0)]
+    for k, d in enumerate(dists):
+        v = rng.normal(size=3)
+        v *= d / np.linalg.norm(v)
+        coords.append(tuple(v))
+    n = len(coords)
+    ecps = [synth.ecp_set(4)] + [synth.ecp_set(2, 1.5) if k % 7 == 0 else None for k in range(1, n)]
+    s = synth.assemble("window_stress", coords, [synth.tz_basis(3)] * n, ecps)
+    o = Oracle(s)
+    ns = int(s["nshells"])
+    checked = skipped = 0
+    with capi.Handle(s, tables_only=True) as h:
+        for c in range(n):
+            if s["shellsECP"][c] == 0:
+                continue
+            endl = np.zeros(8, np.int32)
+            st, en, sk = (np.zeros(ns, np.int32) for _ in range(3))
+            o.L.oracle_screening(C.c_void_p(o.h), c, _p(endl, _pi), _p(st, _pi), _p(en, _pi), _p(sk, _pi))
+            _, st2, en2, sk2 = h.screening(c, 8)
+            assert np.array_equal(sk, sk2), c
+            live = sk == 0
+            assert np.array_equal(st[live], st2[live]) and np.array_equal(en[live], en2[live]), c
+            checked += int(live.sum())
+            skipped += int((~live).sum())
+    o.close()
+    assert checked > 500 and skipped > 500
