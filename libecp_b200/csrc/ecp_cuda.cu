@@ -742,6 +742,7 @@ struct EcpDev {
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES], hClsL[ECP_MAX_CLASSES], hClsNq[ECP_MAX_CLASSES];
   Buf fastSurv;
+  int shiftFused; /* LIBECP_B200_SHIFT=fused: experimental single shift of 4 pi chi + 16 pi^2 gamma in matrix-only runs */
   int linkSmem; /* LIBECP_B200_LINK=smem: experimental shared-memory link kernel for the large classes (k_link2) */
   int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
   long long survCapEnv; /* LIBECP_B200_SURVCAP: survivor-list capacity override (tests of the overflow path) */
@@ -870,6 +871,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     {
       const char *lk = getenv("LIBECP_B200_LINK");
       d->linkSmem = lk && !strcmp(lk, "smem");
+      lk = getenv("LIBECP_B200_SHIFT");
+      d->shiftFused = lk && !strcmp(lk, "fused");
     }
     if (d->fastLim < 1) d->fastLim = 1;
     e = getenv("LIBECP_B200_SURVCAP");
@@ -1698,9 +1701,10 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     rc_ = ensure(&d->Jbuf, (size_t)(2 * clsJ[nc] + 1) * sizeof(double));
     if (rc_) return rc_;
     CK(cudaMemcpyAsync(d->clsJ.p, clsJ, (nc + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->s1));
-    k_shiftJ<<<nblk(clsJ[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, clsJ[nc], (double *)d->Jbuf.p);
+    const int fuse = d->shiftFused && !(flags & 2); /* experimental, off by default; never when blocks are wanted */
+    k_shiftJ<<<nblk(clsJ[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, clsJ[nc], (double *)d->Jbuf.p, fuse);
     k_shiftI<<<nblk(h->clsOutElem[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, h->clsOutElem[nc],
-                                                              (const double *)d->Jbuf.p, flags);
+                                                              (const double *)d->Jbuf.p, flags, fuse);
   }
   launches += 2;
   CK(cudaEventRecord(d->ev[5], d->s1));

@@ -13,7 +13,8 @@
 #ifndef ECP_SHIFT_CUH
 #define ECP_SHIFT_CUH
 
-__global__ void k_shiftJ(DevT t, DevB b, const long long *__restrict__ clsJ, long long nElem, double *__restrict__ Jbuf) {
+__global__ void k_shiftJ(DevT t, DevB b, const long long *__restrict__ clsJ, long long nElem, double *__restrict__ Jbuf,
+                         int fuse) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nElem) return;
   const int c = find_class(clsJ, t.nClasses, w);
@@ -34,16 +35,22 @@ __global__ void k_shiftJ(DevT t, DevB b, const long long *__restrict__ clsJ, lon
     const double f = t.shTermBin[k] * uA[(dd & 15) * dA * dA + ((dd >> 4) & 15) * dA + (dd >> 8)];
     if (fabs(f) <= t.accuracy) continue; /* src/util.c:286 */
     const int p = t.shTermP[k] * cdb;
-    J1 = fma(f, G1[p], J1);
-    J2 = fma(f, G2[p], J2);
+    if (fuse) { /* experimental (LIBECP_B200_SHIFT=fused, matrix-only runs): the shift is linear, so 4 pi chi + 16 pi^2 gamma
+                 * is shifted once instead of chi and gamma separately */
+      const double n1 = 4.0 * M_PI;
+      J1 = fma(f, fma(n1 * n1, G2[p], n1 * G1[p]), J1);
+    } else {
+      J1 = fma(f, G1[p], J1);
+      J2 = fma(f, G2[p], J2);
+    }
   }
   double *J = Jbuf + 2 * (clsJ[c] + (long long)(tri - b.clsFirst[c]) * (na * cdb));
   J[rem] = J1;
-  J[na * cdb + rem] = J2;
+  if (!fuse) J[na * cdb + rem] = J2;
 }
 
 __global__ void k_shiftI(DevT t, DevB b, const long long *__restrict__ clsJ, long long nElem,
-                         const double *__restrict__ Jbuf, int flags) {
+                         const double *__restrict__ Jbuf, int flags, int fuse) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nElem) return;
   const int c = find_class(b.clsOutElem, t.nClasses, w);
@@ -66,8 +73,12 @@ __global__ void k_shiftI(DevT t, DevB b, const long long *__restrict__ clsJ, lon
     const double f = t.shTermBin[k] * uB[(dd & 15) * dB * dB + ((dd >> 4) & 15) * dB + (dd >> 8)];
     if (fabs(f) <= t.accuracy) continue; /* src/util.c:318 */
     const int p = t.shTermP[k];
-    I1 = fma(f * n1, J1[p], I1); /* factor *= N; I += factor * J  (src/util.c:321-324) */
-    I2 = fma(f * n2, J2[p], I2);
+    if (fuse) {
+      I1 = fma(f, J1[p], I1); /* the factors 4 pi / 16 pi^2 went into J (k_shiftJ) */
+    } else {
+      I1 = fma(f * n1, J1[p], I1); /* factor *= N; I += factor * J  (src/util.c:321-324) */
+      I2 = fma(f * n2, J2[p], I2);
+    }
   }
   if (flags & 2) {
     double *o = b.blocks + b.trOut[tri];

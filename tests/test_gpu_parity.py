@@ -251,3 +251,13 @@ def test_link_smem_variant_matches_default():
         got, g1 = _with_env({"LIBECP_B200_LINK": "smem"}, run)
         assert np.array_equal(g0, g1), name
         assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
+
+
+@pytest.mark.skipif(not os.environ.get("LIBECP_B200_EXPERIMENTAL"),
+                    reason="experimental kernels are opt-in: set LIBECP_B200_EXPERIMENTAL=1")
+def test_fused_shift_variant_within_tolerance():
+    """LIBECP_B200_SHIFT=fused (off by default): 4 pi chi + 16 pi^2 gamma shifted once in matrix-only runs - same
+    terms, associated differently, so parity with the reference within the tolerance and callbacks untouched"""
+    for fn, name in ((lambda: synth.cfg3(4), "au4"), (lambda: synth.cfg4("a"), "cfg4a"), (synth.cfg2, "cfg2")):
+        got = _with_env({"LIBECP_B200_SHIFT": "fused"}, lambda: capi.get_integrals(fn()))
+        assert_parity(got, load_matrix(name), name + " fused shift")
