@@ -135,6 +135,11 @@ def cfg3(natoms: int = 20):
     return assemble(f"cfg3_au{natoms}", c, [tz_basis(3)] * len(c), [ecp_set(4)] * len(c))
 
 
+def deriv_pair(lbs: int = 2, L: int = 4):
+    """two atoms off-axis, TZ(lbs) + ECP(L): shape of the derivative fixtures (tests/golden/deriv1_*; needs lbs + n <= L - 1)"""
+    return assemble(f"deriv_tz{lbs}_L{L}", [(0.0, 0.0, 0.0), (0.3, -0.4, 4.1)], [tz_basis(lbs)] * 2, [ecp_set(L)] * 2)
+
+
 def cfg4(variant: str = "a"):
     """high-angular-momentum stress: (a) TZ(4)+ECP(5), (b) TZ(5)+ECP(6); 2 atoms on the z axis."""
     lbs, L = (4, 5) if variant == "a" else (5, 6)

@@ -59,11 +59,12 @@ class RefLib:
             raise RuntimeError(f"getIntegrals rc={rc}")
         return I
 
-    def callbacks(self, s, tol=1e-12, acc=1e-14, large=1024, keep_blocks=True):
+    def callbacks(self, s, tol=1e-12, acc=1e-14, large=1024, keep_blocks=True, n=0):
         """Run init/calculate/free with a recording callback.
 
         Returns (rc, records) with records = list of (A,s1,la,shifta,B,s2,lb,shiftb,C,block ndarray|None)
-        in the call order of src/libecp.c:372.
+        in the call order of src/libecp.c:372.  n = derivative order (only the compiled reference, kind "ref",
+        implements n > 0: shifted-momentum blocks, src/libecp.c:246-250,322-369).
         """
         recs = []
 
@@ -78,7 +79,7 @@ class RefLib:
                         _p(s["nECP"], _pd), _p(s["dECP"], _pd), _p(s["aECP"], _pd),
                         _p(s["shellsBS"], _pi), _p(s["lBS"], _pi), _p(s["KBS"], _pi),
                         _p(s["dBS"], _pd), _p(s["aBS"], _pd),
-                        C.c_int(0), C.c_int(-1), None, C.c_int(large), C.c_double(tol), C.c_double(acc))
+                        C.c_int(n), C.c_int(-1), None, C.c_int(large), C.c_double(tol), C.c_double(acc))
         if not h:
             raise RuntimeError("libECP_init returned NULL")
         rc = self.f_calc(C.c_void_p(h), cbf, None)

@@ -2,13 +2,17 @@
 oracle/Makefile from /root/reference/src).  Run in the build container only (the GPU box has no
 /root/reference); the resulting .npz files are committed.
 
-    python tests/golden/make_golden.py [--big]
+    python tests/golden/make_golden.py [--big | --deriv]
 
 Fixtures (float64, exact bytes of the reference's output):
   <cfg>_matrix.npz   : getIntegrals matrix (upper triangle incl. diagonal as a flat vector `triu`,
                        dimension `dim`), Σ and Σ|.| checksums, callback count
   cfg2_blocks.npz    : every callback block of config 2 in call order (keys, block offsets, values)
   au2_blocks.npz     : same for the first two atoms of the Au20 tetrahedron (two-centre cases, fallback)
+  deriv1_*_blocks.npz: callback blocks of derivative order n = 1 (shifted-momentum blocks, src/libecp.c:246-250,322-369)
+                       for two-atom systems - fixtures for the NEXT scope row; the product rejects n > 0
+                       today.  n = 2 is not recorded: the reference returns NaN in a few (1,0)/(0,1)-shift blocks on
+                       every shape tried (TZ(1..2) x ECP(4..6)), i.e. its own output is not defined there.
 """
 import os
 import sys
@@ -50,8 +54,8 @@ def save_digest(ref, name, s):
     print(f"{name}: dim {s['dim']} sum {M.sum():.15e} sumabs {np.abs(M).sum():.15e} nnz {len(nz)}  {dt:.1f}s")
 
 
-def save_blocks(ref, name, s):
-    rc, recs = ref.callbacks(s)
+def save_blocks(ref, name, s, n=0):
+    rc, recs = ref.callbacks(s, n=n)
     assert rc == 0
     keys = np.array([r[:9] for r in recs], np.int32)
     off = np.cumsum([0] + [len(r[9]) for r in recs])
@@ -62,6 +66,10 @@ def save_blocks(ref, name, s):
 
 def main():
     ref = RefLib("ref")
+    if "--deriv" in sys.argv:  # next scope row (f1): first derivatives, two shapes; nothing else is regenerated
+        save_blocks(ref, "deriv1_tz2_L4", synth.deriv_pair(2, 4), n=1)
+        save_blocks(ref, "deriv1_tz3_L5", synth.deriv_pair(3, 5), n=1)
+        return
     save_matrix(ref, "cfg1", synth.cfg1())
     save_matrix(ref, "cfg2", synth.cfg2())
     save_matrix(ref, "cfg2_L5", synth.cfg2(5))

@@ -1,9 +1,11 @@
 """CPU tier: the oracle restatement (oracle/oracle_ecp.c) against the golden fixtures generated from the
 unmodified reference, against the reference itself when oracle/_ref is present, and against the
 known-answer vectors of SURVEY.md App. D."""
+import os
+
 import numpy as np
 import pytest
-from conftest import load_blocks, load_matrix
+from conftest import GOLDEN, load_blocks, load_matrix
 
 from libecp_b200 import synth
 from oracle.refbind import RefLib, have, port_counters
@@ -101,3 +103,25 @@ def test_port_equals_compiled_reference(port, name):
     for x, y in zip(a, b):
         assert x[:9] == y[:9]
         assert np.array_equal(x[9], y[9])
+
+
+def test_first_derivative_fixtures_are_the_compiled_references_output():
+    """tests/golden/deriv1_*: callback blocks of derivative order n = 1 (the next scope row; the product
+    rejects n > 0 today).  Where the compiled reference is available they must be its output bit for bit; everywhere the
+    fixtures must be well formed: finite, 4 shift patterns, shifted block sizes."""
+    from libecp_b200 import synth
+
+    for name, lbs, L in (("deriv1_tz2_L4", 2, 4), ("deriv1_tz3_L5", 3, 5)):
+        d = np.load(os.path.join(GOLDEN, name + "_blocks.npz"))
+        keys, off, vals = d["keys"], d["off"], d["vals"]
+        assert np.isfinite(vals).all() and len(off) == len(keys) + 1 and off[-1] == len(vals)
+        shifts = {(int(k[3]), int(k[7])) for k in keys}
+        assert shifts == {(1, 0), (-1, 0), (0, 1), (0, -1)}
+        for k, a, b in zip(keys, off[:-1], off[1:]):
+            la, lb = k[2] + k[3], k[6] + k[7]
+            assert b - a == ((la + 1) * (la + 2) // 2) * ((lb + 1) * (lb + 2) // 2)
+        if have("ref"):
+            rc, recs = RefLib("ref").callbacks(synth.deriv_pair(lbs, L), n=1)
+            assert rc == 0 and len(recs) == len(keys)
+            assert np.array_equal(np.array([r[:9] for r in recs], np.int32), keys)
+            assert np.array_equal(np.concatenate([r[9] for r in recs]), vals)
