@@ -251,9 +251,9 @@ static void worker_wait(struct BuildWorker *w) {
 static long long pass_batch_size(const libECPHandle *h, int i) {
   long long full = h->maxTriples;
   if (h->world > 1 && !getenv("LIBECP_B200_BATCH_TRIPLES")) {
-    /* every batch costs ~0.9 ms of device time that does not shrink with its size (the longest fallback item and
-     * type-1 pair of a batch are serial chains of a few hundred microseconds, plus ~57 launches): at 8 ranks six
-     * 0.5 M batches were 4.5 of 19.9 ms.  A rank's pass is cut into about three batches (ramp 1/6, 1/2, 1). */
+    /* a nearly empty batch was measured at ~0.9 ms of device time (the longest fallback item and type-1 pair of a
+     * batch are serial chains of a few hundred microseconds, plus ~57 launches); large batches hide most of it, six
+     * 0.5 M batches per rank at 8 GPUs less so.  A rank's pass is cut into about three batches (ramp 1/6, 1/2, 1). */
     full = 4 * h->maxTriples / h->world;
     if (full > h->maxTriples) full = h->maxTriples;
     if (full < 500000) full = 500000;
