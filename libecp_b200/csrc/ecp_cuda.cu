@@ -54,6 +54,7 @@ struct DevT {
   const int *ijk, *ijkIndex;
   const double *small_r, *small_w, *large_x, *large_w, *large_xo;
   const int16_t *small_oidx;
+  const int16_t *small_slotOf; /* original index -> slot (inverse of small_oidx) */
   const unsigned char *small_jL, *small_jR; /* first in-window pair per (level, start) / (level, end), ecp_math.h */
   const double *besselT, *besselC;
   const int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO, *atomMaxL;
@@ -240,6 +241,45 @@ __global__ void __launch_bounds__(ECP_SMALL_SLOTS, (LMAX <= 6 ? 2 : 1)) k_Ftab(D
         }
       }
       break;
+  }
+}
+
+/* Experimental variant (OFF by default; LIBECP_B200_FTAB=compact): a shell's window covers ~30 % of the grid, so 70 % of
+ * k_Ftab's threads only write zeros and every warp (32 consecutive level-major slots span the whole radial range) keeps
+ * a few live lanes.  Here the F rows are cleared by one memset and a block of 128 threads walks the ORIGINAL indices
+ * of the window [start, end) only, writing each point to its slot: the same arithmetic per point (F is bit-identical),
+ * about a third of the warps.  STATUS: written after the round-1 GPU budget was spent - compiles, never run; opt-in
+ * test -k ftab_compact, A/B with tools/ab_kernels.py cfg3 LIBECP_B200_FTAB=-,compact. */
+template <int LMAX>
+__global__ void __launch_bounds__(128) k_Ftab2(DevT t, DevB b) {
+  const int ss = blockIdx.x;
+  const int sh = b.ssShell[ss], as = b.ssASlot[ss];
+  const int Lc = t.typeL[b.asType[as]];
+  const int lmaxA = Lc - 1 + t.shellL[sh];
+  const double dAC = b.asR[4 * as + 3];
+  const int gs = b.ssStart[ss], ge = min(b.ssEnd[ss], ECP_SMALL_ORDER);
+  for (int oi = gs + threadIdx.x; oi < ge; oi += blockDim.x) {
+    const int k = t.small_slotOf[oi];
+    switch (lmaxA) {
+      case 0: ftab_body<0>(t, b, ss, k, sh, dAC); break;
+      case 1: ftab_body<1>(t, b, ss, k, sh, dAC); break;
+      case 2: ftab_body<2>(t, b, ss, k, sh, dAC); break;
+      case 3: ftab_body<3>(t, b, ss, k, sh, dAC); break;
+      case 4: ftab_body<4>(t, b, ss, k, sh, dAC); break;
+      case 5: ftab_body<5>(t, b, ss, k, sh, dAC); break;
+      default:
+        if (LMAX <= 6 || lmaxA == 6) {
+          ftab_body<6>(t, b, ss, k, sh, dAC);
+        } else {
+          switch (lmaxA) {
+            case 7: ftab_body<(LMAX > 6 ? 7 : 6)>(t, b, ss, k, sh, dAC); break;
+            case 8: ftab_body<(LMAX > 6 ? 8 : 6)>(t, b, ss, k, sh, dAC); break;
+            case 9: ftab_body<(LMAX > 6 ? 9 : 6)>(t, b, ss, k, sh, dAC); break;
+            default: ftab_body<(LMAX > 6 ? KM : 6)>(t, b, ss, k, sh, dAC); break;
+          }
+        }
+        break;
+    }
   }
 }
 
@@ -742,6 +782,7 @@ struct EcpDev {
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES], hClsL[ECP_MAX_CLASSES], hClsNq[ECP_MAX_CLASSES];
   Buf fastSurv;
+  int ftabCompact; /* LIBECP_B200_FTAB=compact: experimental window-only F tabulation (k_Ftab2) */
   int shiftFused; /* LIBECP_B200_SHIFT=fused: experimental single shift of 4 pi chi + 16 pi^2 gamma in matrix-only runs */
   int linkSmem; /* LIBECP_B200_LINK=smem: experimental shared-memory link kernel for the large classes (k_link2) */
   int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
@@ -873,6 +914,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
       d->linkSmem = lk && !strcmp(lk, "smem");
       lk = getenv("LIBECP_B200_SHIFT");
       d->shiftFused = lk && !strcmp(lk, "fused");
+      lk = getenv("LIBECP_B200_FTAB");
+      d->ftabCompact = lk && !strcmp(lk, "compact");
     }
     if (d->fastLim < 1) d->fastLim = 1;
     e = getenv("LIBECP_B200_SURVCAP");
@@ -927,6 +970,13 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   t.small_r = upload_const(d, h->small_r, ECP_SMALL_SLOTS);
   t.small_w = upload_const(d, h->small_w, ECP_SMALL_SLOTS);
   t.small_oidx = upload_const(d, h->small_oidx, ECP_SMALL_SLOTS);
+  {
+    static int16_t slotOf[ECP_SMALL_SLOTS]; /* the small grid is the same for every handle */
+    for (int i = 0; i < ECP_SMALL_SLOTS; i++) slotOf[i] = 1; /* pad slot */
+    for (int k = 0; k < ECP_SMALL_SLOTS; k++)
+      if (h->small_oidx[k] >= 0) slotOf[h->small_oidx[k]] = (int16_t)k;
+    t.small_slotOf = upload_const(d, slotOf, ECP_SMALL_SLOTS);
+  }
   {
     unsigned char *jl = (unsigned char *)malloc(2 * ECP_SMALL_LEVELS * ECP_SMALL_SLOTS), *jr = jl + ECP_SMALL_LEVELS * ECP_SMALL_SLOTS;
     if (!ecp_small_suffix_tables(&t.sm, h->small_oidx, jl, jr)) {
@@ -1573,7 +1623,13 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
   k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
   k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
-  if (t.maxLECP - 1 + d->maxLBS <= 6)
+  if (d->ftabCompact) { /* experimental, off by default (see k_Ftab2) */
+    CK(cudaMemsetAsync(B.F, 0, (size_t)h->fRows * ECP_SMALL_SLOTS * sizeof(double), d->s1));
+    if (t.maxLECP - 1 + d->maxLBS <= 6)
+      k_Ftab2<6><<<h->nSSlots, 128, 0, d->s1>>>(t, B);
+    else
+      k_Ftab2<KM><<<h->nSSlots, 128, 0, d->s1>>>(t, B);
+  } else if (t.maxLECP - 1 + d->maxLBS <= 6)
     k_Ftab<6><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
   else
     k_Ftab<KM><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);

@@ -261,3 +261,20 @@ def test_fused_shift_variant_within_tolerance():
     for fn, name in ((lambda: synth.cfg3(4), "au4"), (lambda: synth.cfg4("a"), "cfg4a"), (synth.cfg2, "cfg2")):
         got = _with_env({"LIBECP_B200_SHIFT": "fused"}, lambda: capi.get_integrals(fn()))
         assert_parity(got, load_matrix(name), name + " fused shift")
+
+
+@pytest.mark.skipif(not os.environ.get("LIBECP_B200_EXPERIMENTAL"),
+                    reason="experimental kernels are opt-in: set LIBECP_B200_EXPERIMENTAL=1")
+def test_ftab_compact_variant_is_bit_identical():
+    """k_Ftab2 (LIBECP_B200_FTAB=compact, off by default) tabulates only the window of every shell slot into a cleared
+    table: same arithmetic per point, so the F table and the matrices are bit-identical to k_Ftab's"""
+    for s, name in ((synth.cfg3(4), "au4"), (synth.cfg4("b"), "cfg4b")):
+        def run():
+            with capi.Handle(s) as h:
+                rc, M = h.integrals_host()
+                return M, h.debug_fetch("F", 400000)
+        base, f0 = run()
+        got, f1 = _with_env({"LIBECP_B200_FTAB": "compact"}, run)
+        assert np.array_equal(f0, f1), name
+        assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
+        assert_parity(got, load_matrix(name), name + " compact F")
