@@ -159,7 +159,8 @@ void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dis
 int ecp_pair_owner(const EcpTables *t, int a, int b, int world) {
   if (world <= 1) return 0;
   const int row = a < b ? a : b;
-  return t->rowDeal[row] % world;
+  const int *deal = t->rowDeal ? t->rowDeal : ecp_tables_row_deal((EcpTables *)t);
+  return deal[row] % world;
 }
 
 static double dist3(const double *a, const double *b) { /* src/util.c:109-116 */
@@ -281,6 +282,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   const int needOut = wantOut || keepCanon; /* block offsets are only needed when the callback blocks are produced */
   const EcpHostTables *v = &t->v;
   const int nat = v->nrAtoms, nc = v->nClasses;
+  if (world > 1) ecp_tables_row_deal((EcpTables *)t); /* before the parallel regions */
   struct BuilderScratch *S = get_scratch(bb);
   int nthreads = 1;
 #ifdef _OPENMP

@@ -10,6 +10,7 @@
 #include "tables.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -51,6 +52,52 @@ static void cartesian_order(int am, int **ijk_, int **inv_) {
 }
 
 /* packed (l, m, c) offsets of the Cartesian->spherical matrix (reference src/transformations.h:13-14) */
+/* ---- process-wide cache of the tables that do not depend on the molecule ----
+ * cart2sph / poly2sph (key tmDim), Omega (key maxLECP, maxLambda, maxAlpha, tmDim) and the Bessel table (key lMax,
+ * accuracy) are pure functions of a few integers.  A caller of getIntegrals creates a handle per call (reference
+ * src/getIntegrals.c:78-89): the first handle computes them as before, later ones copy the stored doubles
+ * (bit-identical by construction; 2.6 of 4.6 ms of the host part of libECP_init on the 500-atom config). */
+typedef struct {
+  int used, key[4];
+  double acc;
+  size_t n;
+  double *data;
+} ConstEntry;
+enum { CC_C2S, CC_P2S, CC_OMEGA, CC_BESSELK, CC_KINDS };
+#define CC_SLOTS 6
+static ConstEntry g_cc[CC_KINDS][CC_SLOTS];
+static pthread_mutex_t g_ccMu = PTHREAD_MUTEX_INITIALIZER;
+static double *cc_get(int kind, int k0, int k1, int k2, int k3, double acc, size_t *n) {
+  double *out = NULL;
+  pthread_mutex_lock(&g_ccMu);
+  for (int i = 0; i < CC_SLOTS; i++) {
+    const ConstEntry *e = &g_cc[kind][i];
+    if (e->used && e->key[0] == k0 && e->key[1] == k1 && e->key[2] == k2 && e->key[3] == k3 && e->acc == acc) {
+      out = malloc((e->n ? e->n : 1) * sizeof(double));
+      memcpy(out, e->data, e->n * sizeof(double));
+      if (n) *n = e->n;
+      break;
+    }
+  }
+  pthread_mutex_unlock(&g_ccMu);
+  return out;
+}
+static void cc_put(int kind, int k0, int k1, int k2, int k3, double acc, const double *data, size_t n) {
+  pthread_mutex_lock(&g_ccMu);
+  for (int i = 0; i < CC_SLOTS; i++) {
+    ConstEntry *e = &g_cc[kind][i];
+    if (e->used) continue; /* a full cache simply stops learning */
+    e->data = malloc((n ? n : 1) * sizeof(double));
+    memcpy(e->data, data, n * sizeof(double));
+    e->n = n;
+    e->key[0] = k0; e->key[1] = k1; e->key[2] = k2; e->key[3] = k3;
+    e->acc = acc;
+    e->used = 1;
+    break;
+  }
+  pthread_mutex_unlock(&g_ccMu);
+}
+
 static int c2s_size(int l, const double *fac) { return (int)((3 * l + 2) * fac[l + 3] / (12 * fac[l])); }
 static int c2s_index(int l, int m, int c, const double *fac) { return l == 0 ? 0 : c2s_size(l - 1, fac) + m * IJK(l) + c; }
 
@@ -319,10 +366,14 @@ static void build_large_grid(EcpTables *t, int maxPoints) {
 static int build_bessel(EcpTables *t, int lMax, double accuracy) {
   const int N = 16 * 100, cutoff = 200, dim = N + 1;
   double *F = malloc((cutoff + 1) * sizeof(double)), *G = malloc((cutoff + lMax + 2) * sizeof(double));
-  double *K = calloc((size_t)(lMax + 1) * dim, sizeof(double));
   int rc = 0;
-  K[0] = 1.0;
-  for (int i = 1; i <= N && !rc; i++) {
+  double *K = cc_get(CC_BESSELK, lMax, 0, 0, 0, accuracy, NULL);
+  const int cached = K != NULL;
+  if (!cached) {
+    K = calloc((size_t)(lMax + 1) * dim, sizeof(double));
+    K[0] = 1.0;
+  }
+  for (int i = 1; i <= N && !rc && !cached; i++) {
     const double z = i / (N / 16.0);
     int j = 0;
     double f = z * z / 2.0, s;
@@ -354,6 +405,7 @@ static int build_bessel(EcpTables *t, int lMax, double accuracy) {
   free(G);
   t->besselK = K;
   if (rc) return rc;
+  if (!cached) cc_put(CC_BESSELK, lMax, 0, 0, 0, accuracy, K, (size_t)(lMax + 1) * dim);
   t->besselC = calloc(lMax + 1, sizeof(double));
   for (int i = 1; i <= lMax; i++) t->besselC[i] = i / (2.0 * i + 1.0);
   const int stride = (lMax + 1 + 3) & ~3; /* rows padded to 32 bytes */
@@ -447,6 +499,32 @@ static int deal_cmp(const void *pa, const void *pb) {
   const uint64_t ha = deal_mix((uint64_t)a), hb = deal_mix((uint64_t)b);
   if (ha != hb) return ha < hb ? -1 : 1;
   return a < b ? -1 : (a > b);
+}
+
+/* Deal of the rows of a sharded run (builder.c: ecp_pair_owner = rowDeal % world).  Shells are grouped by kind -
+     * (l, contraction depth, exponents), i.e. "the same shell on another atom": the kind sets the cost of a triple.
+     * The shells of a kind are dealt out one by one in a fixed pseudo-random order (atom indices of a lattice are
+     * periodic in space: dealing 8 ranks down a column of 8 sites hands one rank the whole surface layer - measured;
+     * pairing early with late rows, which have many / few partners b >= a, was measured too and is worse because it
+     * halves the number of independent units).  Every rank receives the same number (+-1) of rows of every kind.
+     * Executed triples per rank on the 500-atom config, max / mean: 1.001, 1.009, 1.040 at 2, 4, 8 ranks
+     * (hash of the row index alone: 1.001, 1.034, -). */
+const int *ecp_tables_row_deal(EcpTables *t) {
+  static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  pthread_mutex_lock(&mu); /* the comparator reads file-scope pointers */
+  if (!t->rowDeal) {
+    const int nsh = t->v.nrShells;
+    int *deal = malloc((nsh + 1) * sizeof(int));
+    int *ord = malloc((nsh + 1) * sizeof(int));
+    for (int s = 0; s < nsh; s++) ord[s] = s;
+    g_dealL = t->dealL; g_dealK = t->dealK; g_dealA = t->dealA; g_dealP = t->shellPrim;
+    qsort(ord, nsh, sizeof(int), deal_cmp);
+    for (int k = 0; k < nsh; k++) deal[ord[k]] = k;
+    free(ord);
+    t->rowDeal = deal;
+  }
+  pthread_mutex_unlock(&mu);
+  return t->rowDeal;
 }
 
 EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shellsECP, const int *lECP,
@@ -575,9 +653,23 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   t->fac = factorial_table(2 * v->tmDim + 1, 1);
   t->dfac = factorial_table(2 * v->tmDim + 1, 2);
   cartesian_order(v->tmDim, &t->ijk, &t->ijkIndex);
-  t->cart2sph = build_cart2sph(v->tmDim, t->ijk, t->fac);
-  t->poly2sph = build_poly2sph(t->cart2sph, v->tmDim, t->ijk, t->dfac);
-  t->omega = build_omega(t, &v->nomega);
+  if (!(t->cart2sph = cc_get(CC_C2S, v->tmDim, 0, 0, 0, 0.0, NULL))) {
+    t->cart2sph = build_cart2sph(v->tmDim, t->ijk, t->fac);
+    cc_put(CC_C2S, v->tmDim, 0, 0, 0, 0.0, t->cart2sph, (size_t)c2s_size(v->tmDim, t->fac));
+  }
+  if (!(t->poly2sph = cc_get(CC_P2S, v->tmDim, 0, 0, 0, 0.0, NULL))) {
+    t->poly2sph = build_poly2sph(t->cart2sph, v->tmDim, t->ijk, t->dfac);
+    cc_put(CC_P2S, v->tmDim, 0, 0, 0, 0.0, t->poly2sph, (size_t)CD(v->tmDim) * LD(v->tmDim));
+  }
+  {
+    size_t nom = 0;
+    if ((t->omega = cc_get(CC_OMEGA, v->maxLECP, v->maxLambda, v->maxAlpha, v->tmDim, 0.0, &nom))) {
+      v->nomega = (int)nom;
+    } else {
+      t->omega = build_omega(t, &v->nomega);
+      cc_put(CC_OMEGA, v->maxLECP, v->maxLambda, v->maxAlpha, v->tmDim, 0.0, t->omega, (size_t)v->nomega);
+    }
+  }
   t->binom = calloc((v->maxLBS + 1) * (v->maxLBS + 1), sizeof(double));
   for (int n = 0; n <= v->maxLBS; n++)
     for (int k = 0; k <= n; k++) t->binom[n * (v->maxLBS + 1) + k] = nk(n, k, t->fac);
@@ -647,22 +739,8 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   t->shellRadius = malloc((nsh + 1) * sizeof(double));
   for (int s = 0; s < nsh; s++)
     t->shellRadius[s] = shell_radius(KBS[s], lBS[s], dBS + t->shellPrim[s], aBS + t->shellPrim[s], 1.0E-14);
-  { /* Deal of the rows of a sharded run (builder.c: ecp_pair_owner = rowDeal % world).  Shells are grouped by kind -
-     * (l, contraction depth, exponents), i.e. "the same shell on another atom": the kind sets the cost of a triple.
-     * The shells of a kind are dealt out one by one in a fixed pseudo-random order (atom indices of a lattice are
-     * periodic in space: dealing 8 ranks down a column of 8 sites hands one rank the whole surface layer - measured;
-     * pairing early with late rows, which have many / few partners b >= a, was measured too and is worse because it
-     * halves the number of independent units).  Every rank receives the same number (+-1) of rows of every kind.
-     * Executed triples per rank on the 500-atom config, max / mean: 1.001, 1.009, 1.040 at 2, 4, 8 ranks
-     * (hash of the row index alone: 1.001, 1.034, -). */
-    t->rowDeal = malloc((nsh + 1) * sizeof(int));
-    int *ord = malloc((nsh + 1) * sizeof(int));
-    for (int s = 0; s < nsh; s++) ord[s] = s;
-    g_dealL = lBS; g_dealK = KBS; g_dealA = aBS; g_dealP = t->shellPrim;
-    qsort(ord, nsh, sizeof(int), deal_cmp);
-    for (int k = 0; k < nsh; k++) t->rowDeal[ord[k]] = k;
-    free(ord);
-  }
+  t->rowDeal = NULL; /* dealt on the first sharded use: ecp_tables_row_deal */
+  t->dealL = lBS; t->dealK = KBS; t->dealA = aBS;
   t->atomRmax = calloc(nrAtoms + 1, sizeof(double));
   for (int s = 0; s < nsh; s++)
     if (t->shellRadius[s] > t->atomRmax[t->shellAtom[s]]) t->atomRmax[t->shellAtom[s]] = t->shellRadius[s];

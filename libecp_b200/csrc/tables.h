@@ -33,7 +33,10 @@ typedef struct {
   int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO;
   double *shellRadius;
   double *atomRmax;   /* largest shell radius per atom (atom-level screening prune) */
-  int *rowDeal;       /* position of every shell in the order rows are dealt to the ranks of a sharded run (builder.c) */
+  int *rowDeal;       /* position of every shell in the order rows are dealt to the ranks of a sharded run; NULL until
+                         ecp_tables_row_deal() is called (unsharded handles never need it) */
+  const int *dealL, *dealK; /* borrowed basis arrays the deal is computed from (the handle borrows them anyway) */
+  const double *dealA;
   int *atomMaxL, *atomFirstShell;
   /* ECP */
   int *atomType; /* per atom: type index or -1 */
@@ -52,6 +55,8 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
                             const int *shellsBS, const int *lBS, const int *KBS, const double *dBS, const double *aBS,
                             int largeGridOrder, double tolerance, double accuracy);
 void ecp_tables_free(EcpTables *t);
+/* row deal of a sharded run (see rowDeal); computed on first use, thread-safe */
+const int *ecp_tables_row_deal(EcpTables *t);
 
 /* helpers shared with builder.c */
 double ecp_host_pot_eval(const EcpTables *t, int type, int l, double r);
