@@ -92,6 +92,11 @@ def test_unsupported_arguments_rejected():
 def test_host_tables_bitwise(name):
     s = SHAPES[name]()
     o = Oracle(s)
+    # twice: the first handle of a process computes the molecule-independent tables, later ones copy them from the
+    # process-wide cache (tables.c) - both must be the reference's doubles
+    with capi.Handle(s, tables_only=True) as h0:
+        for t in ["fac", "dfac", "poly2sph", "omega", "small_x", "small_w", "large_x", "large_w", "bessel", "besselC"]:
+            assert np.array_equal(o.table(t), h0.host_table(t)), t
     with capi.Handle(s, tables_only=True) as h:
         for t in ["fac", "dfac", "poly2sph", "omega", "small_x", "small_w", "large_x", "large_w", "bessel", "besselC"]:
             assert np.array_equal(o.table(t), h.host_table(t)), t
