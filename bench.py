@@ -408,11 +408,39 @@ def run_b200(args):
             dt, nbytes, bufs = gather.allgather_matrix(h, rank, world, buffers=bufs)
             ts.append(max_over_ranks(dt))
             h.integrals_device()  # a scatter dirties the matrix: the pass after it starts with a full clear
-        del bufs
         allgather = {"ms": 1e3 * min(ts[1:]), "bytes_received_per_rank": int(nbytes),
                      "GBps_per_rank": nbytes / min(ts[1:]) / 1e9,
                      "note": "pack own rows + ncclAllGather (padded shards) + scatter of the other ranks' rows; "
                              "leaves the full upper-triangular matrix on every GPU"}
+        # result check below: the matrix of the last pass, gathered
+        barrier()
+        gather.allgather_matrix(h, rank, world, buffers=bufs)
+        del bufs
+
+    # ---- parity of what was just timed: the matrix resident in HBM (after the all-gather at N > 1) against the
+    #      reference (cfg5: digest of a full 500-centre run of the unmodified reference; small configs: full matrix) ----
+    parity_res = None
+    if rank == 0 and not args.no_parity:
+        from libecp_b200 import parity
+
+        rc_, ptr_, n_ = (0, None, 0)
+        if not dist:
+            rc_, ptr_, n_ = h.integrals_device()
+        else:
+            ptr_, n_ = h.matrix_ptr(), dim
+        Mdev = parity.device_view(ptr_, n_)
+        golden = {"cfg3": "cfg3", "cfg2": "cfg2", "cfg4b": "cfg4b"}
+        if args.workload == "cfg5":
+            parity_res = parity.check_digest(Mdev, s)
+        elif args.workload in golden:
+            parity_res = parity.check_matrix(Mdev, golden[args.workload])
+        if parity_res is not None:
+            parity_res["checked"] = ("device-resident matrix of a pass identical to the timed ones"
+                                     + (f", after the NCCL all-gather of the {world} shards" if dist else ""))
+            parity_res["tolerance"] = "|x-ref| <= 1e-12 + 1e-10 |ref|"
+        del Mdev
+    if dist:
+        barrier()
 
     # ---- roofline, secondary (Au20) and CPU baseline on rank 0 / N=1 ----
     line = None
@@ -428,7 +456,7 @@ def run_b200(args):
                        "host_threads_per_rank": host_threads,
                        "l2": "per-step working set (F/T/gamma/chi intermediates, GBs) exceeds the 126 MB L2; no flush needed",
                        "timed_region": "host batch build + H2D of batch arrays + all kernels; matrix stays in HBM"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity_res,
             "host_ms_build_per_step": stats["ms_build"], "device_ms_per_step": stats["ms_device_total"],
             "wall_ms_per_step": 1e3 * wall / args.steps,
         }
@@ -514,6 +542,7 @@ def main():
     ap.add_argument("--workload", default="cfg5")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the Au20 secondary measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the result check against the reference digest")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

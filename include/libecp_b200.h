@@ -37,6 +37,9 @@ int libecp_b200_pair_owner(libECPHandle *h, int shellA, int shellB, int world);
  * nAO*nAO doubles owned by the handle (valid until the next call or libECP_free), *nAO its dimension.
  * Same return codes as calculateECPIntegrals. */
 int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO);
+/* device pointer of the handle's resident result matrix (NULL before the first pass); after a gather of a sharded run
+ * (libecp_b200_unpack_rows) it holds the full upper-triangular matrix */
+void *libecp_b200_matrix_ptr(libECPHandle *h);
 /* same, then copied into host memory I (row stride rowdim) with += on the upper triangle */
 int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I);
 

@@ -25,6 +25,7 @@ EXPORTS = [
     "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
     "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
     "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only", "libecp_b200_owned_rows", "libecp_b200_pack_rows", "libecp_b200_unpack_rows",
+    "libecp_b200_matrix_ptr",
 ]
 
 
@@ -174,6 +175,13 @@ class Handle:
         if rc < 0:
             raise RuntimeError("device failure: " + (lib().libecp_b200_last_error() or b"").decode())
         return rc, ptr.value, n.value
+
+    def matrix_ptr(self):
+        """device pointer of the handle's resident result matrix (0 before the first pass)"""
+        f = lib().libecp_b200_matrix_ptr
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p]
+        return f(C.c_void_p(self.h)) or 0
 
     def set_serial_kernels(self, on=True):
         L = lib()

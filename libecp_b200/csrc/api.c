@@ -70,13 +70,21 @@ double libecp_b200_fp64_peak(int device, int iters) { return ecpdev_fp64_peak_pr
 libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lECP, int *KECP, double *nECP,
                           double *dECP, double *aECP, int *shellsBS, int *lBS, int *KBS, double *dBS, double *aBS,
                           int n, int lmax, int *shellOrdering, int largeGridOrder, double tolerance, double accuracy) {
-  (void)lmax;
+  (void)lmax; /* only read together with shellOrdering (reference src/libecp.c:152-166) */
   g_apierr[0] = 0;
-  if (n != 0 || shellOrdering != NULL) {
-    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d / custom shell ordering not supported", n);
+  if (n != 0) {
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d not supported (only n=0)", n);
+    return NULL;
+  }
+  if (shellOrdering != NULL) {
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: custom shell ordering (lmax=%d) not supported; pass -1, NULL", lmax);
     return NULL;
   }
   libECPHandle *h = calloc(1, sizeof(*h));
+  if (!h) {
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: out of memory");
+    return NULL;
+  }
   h->nrAtoms = nrAtoms;
   h->geometry = geometry;
   h->world = 1;
@@ -88,7 +96,7 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
   h->tab = ecp_tables_build(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, shellsBS, lBS, KBS, dBS, aBS,
                             largeGridOrder, tolerance, accuracy);
   if (!h->tab) {
-    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: unsupported shape or Bessel tabulation failed");
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: %s", ecp_tables_last_error());
     free(h);
     return NULL;
   }
@@ -356,6 +364,8 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
   if (devMatrix) *devMatrix = ecpdev_matrix_ptr(h->dev);
   return rc;
 }
+
+void *libecp_b200_matrix_ptr(libECPHandle *h) { return (h && h->dev) ? ecpdev_matrix_ptr(h->dev) : NULL; }
 
 int libecp_b200_pair_owner(libECPHandle *h, int a, int b, int world) { return ecp_pair_owner(h->tab, a, b, world); }
 /* AO rows (ascending) whose shell-pair rows `rank` of `world` owns; returns the count (cap may be 0 to size) */

@@ -29,6 +29,7 @@
 #include "ecp_math.h"
 
 #define KM ECP_KMAX
+#define ECP_MAXDEV 16 /* devices with per-device caches (parked scratch, occupancy figures) */
 
 
 static char g_err[512] = "";
@@ -1069,7 +1070,6 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
  * created there: a caller that goes through getIntegrals() creates a handle per call, and growing gigabytes of
  * scratch from the driver costs tens to hundreds of milliseconds each time.  libecp_b200_release_cache() frees them. */
 #define ECP_NBUF 72
-#define ECP_MAXDEV 16
 struct DevCache {
   int valid;
   Buf bufs[ECP_NBUF];
@@ -1307,24 +1307,20 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   if (!rc) rc = ensure(&dStage[0], (size_t)panelElems * sizeof(double));
   if (!rc) rc = ensure(&dStage[1], (size_t)panelElems * sizeof(double));
   if (rc) return rc;
-  /* pinned staging buffers are kept for the life of the process: cudaMallocHost of tens of MB costs far more
-   * than the transfer itself */
-  static double *s_pin[2] = {NULL, NULL};
-  static size_t s_pinCap = 0;
-  if (s_pinCap < (size_t)panelElems * sizeof(double)) {
-    for (int k = 0; k < 2; k++) {
-      if (s_pin[k]) cudaFreeHost(s_pin[k]);
-      s_pin[k] = NULL;
-      CK(cudaMallocHost((void **)&s_pin[k], (size_t)panelElems * sizeof(double)));
-    }
-    s_pinCap = (size_t)panelElems * sizeof(double);
-  }
-  double *pin[2] = {s_pin[0], s_pin[1]};
-  cudaEvent_t done[2];
+  /* pinned staging buffers come from the process-wide page-locked cache (mutex-protected, blocks marked in use: two
+   * handles driven from different host threads never share one; cudaMallocHost of tens of MB costs far more than the
+   * transfer itself, so the blocks stay cached after the call) */
+  double *pin[2];
   for (int k = 0; k < 2; k++) {
-
-    CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    pin[k] = (double *)ecpdev_pinned_alloc((size_t)panelElems * sizeof(double));
+    if (!pin[k]) {
+      if (k) ecpdev_pinned_free(pin[0]);
+      snprintf(g_err, sizeof(g_err), "ecpdev_matrix_add_to_host: no staging memory");
+      return -1;
+    }
   }
+  cudaEvent_t done[2];
+  for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
   if (nR) {
     CK(cudaMemcpyAsync(dRows.p, rows, (size_t)nR * sizeof(int), cudaMemcpyHostToDevice, d->s1));
     CK(cudaMemcpyAsync(dOff.p, off, (size_t)(nR + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->s1));
@@ -1386,9 +1382,9 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
             nR, nPanels, moved / 1e6, 0.0, 1e3 * tWait, 1e3 * tAdd, omp_get_max_threads());
   (void)tStart;
   for (int k = 0; k < 2; k++) {
-
     cudaEventDestroy(done[k]);
     cudaFreeAsync(dStage[k].p, d->s1);
+    ecpdev_pinned_free(pin[k]);
   }
   cudaFreeAsync(dRows.p, d->s1);
   cudaFreeAsync(dOff.p, d->s1);
@@ -1486,9 +1482,11 @@ static void launch_type1_t(EcpDev *d, const T1Segs &sg, long long listOff, int s
   unsigned long long *mask = (unsigned long long *)d->t1mask.p;
   const int block = d->t1block;
   const size_t smem = t1_smem_bytes(LAB, block);
-  static int occS[5] = {0}, occL[5] = {0}; /* resident blocks per SM, per block size 32/64/96/128 */
+  /* resident blocks per SM, per device (the shared-memory attribute is per device too) and block size 32/64/96/128 */
+  static int occS_[ECP_MAXDEV][5] = {{0}}, occL_[ECP_MAXDEV][5] = {{0}};
+  int *occS = occS_[d->device < ECP_MAXDEV ? d->device : 0], *occL = occL_[d->device < ECP_MAXDEV ? d->device : 0];
   const int bi = block / 32;
-  if (!occS[bi]) {
+  if (!occS[bi] || d->device >= ECP_MAXDEV) {
     cudaFuncSetAttribute(k_type1S<LAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_type1L<LAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS[bi], k_type1S<LAB>, block, smem);
@@ -1708,9 +1706,10 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
         kern = k_fallbackG<10, 2>;
         slot = 2;
       }
-      static int occ[3][5] = {{0}};
+      static int occ_[ECP_MAXDEV][3][5] = {{{0}}};
+      int (*occ)[5] = occ_[d->device < ECP_MAXDEV ? d->device : 0];
       const int bi = block / 32;
-      if (!occ[slot][bi]) {
+      if (!occ[slot][bi] || d->device >= ECP_MAXDEV) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(km <= 6 ? fb_smem_bytes<6>(128) : fb_smem_bytes<10>(128)));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[slot][bi], kern, block, smem);
         if (occ[slot][bi] < 1) occ[slot][bi] = 1;

@@ -527,6 +527,15 @@ const int *ecp_tables_row_deal(EcpTables *t) {
   return t->rowDeal;
 }
 
+static _Thread_local char g_taberr[200] = "";
+const char *ecp_tables_last_error(void) { return g_taberr; }
+#define TAB_FAIL(...)                                     \
+  do {                                                    \
+    snprintf(g_taberr, sizeof(g_taberr), __VA_ARGS__);    \
+    ecp_tables_free(t);                                   \
+    return NULL;                                          \
+  } while (0)
+
 EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shellsECP, const int *lECP,
                             const int *KECP, const double *nECP, const double *dECP, const double *aECP,
                             const int *shellsBS, const int *lBS, const int *KBS, const double *dBS, const double *aBS,
@@ -555,10 +564,8 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
     t->atomFirstShell[i] = s;
     for (int j = 0; j < shellsBS[i]; j++, s++) {
       const int l = lBS[s];
-      if (l < 0 || l > ECP_MAX_LBS || KBS[s] < 1) {
-        ecp_tables_free(t);
-        return NULL;
-      }
+      if (l < 0 || l > ECP_MAX_LBS || KBS[s] < 1)
+        TAB_FAIL("basis shell %d: angular momentum %d outside 0..%d (s-h) or contraction depth %d < 1", s, l, ECP_MAX_LBS, KBS[s]);
       t->shellL[s] = l;
       t->shellK[s] = KBS[s];
       t->shellPrim[s] = nprim;
@@ -608,10 +615,7 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
         t->gaussA[ng] = aECP[pi];
       }
     }
-    if (L > ECP_MAX_LECP) {
-      ecp_tables_free(t);
-      return NULL;
-    }
+    if (L > ECP_MAX_LECP) TAB_FAIL("ECP on atom %d: L = %d exceeds the supported maximum %d", i, L, ECP_MAX_LECP);
     const int N = ng - g0;
     int found = -1;
     for (int k = 0; k < v->nTypes && found < 0; k++) {
@@ -637,6 +641,10 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
       if (L > v->maxLECP) v->maxLECP = L;
     }
   }
+  /* the row deal of a sharded run only needs the basis bookkeeping: valid on a handle without ECP centres too
+   * (libecp_b200_owned_rows / _pair_owner are legal there and every rank of a gather asks for them) */
+  t->rowDeal = NULL; /* dealt on the first sharded use: ecp_tables_row_deal */
+  t->dealL = lBS; t->dealK = KBS; t->dealA = aBS;
   if (v->nTypes == 0) return t; /* no ECP centre: nothing to integrate */
 
   /* ---- dimensions (reference src/libecp.c:143-171) ---- */
@@ -645,10 +653,9 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   v->tmDim = v->maxLambda + v->maxAlpha;
   v->ijkDim = v->tmDim + 1;
   /* shapes the kernels are built for; maxLBS <= maxLECP+1 keeps every Bessel request inside the table */
-  if (v->maxLECP < 1 || v->maxLambda > ECP_KMAX || 2 * v->maxLBS > ECP_KMAX || v->maxLBS > v->maxLECP + 1) {
-    ecp_tables_free(t);
-    return NULL;
-  }
+  if (v->maxLECP < 1 || v->maxLambda > ECP_KMAX || 2 * v->maxLBS > ECP_KMAX || v->maxLBS > v->maxLECP + 1)
+    TAB_FAIL("unsupported shape: max l of the basis %d, max L of the ECPs %d (need L >= 1, L - 1 + l <= %d, l <= L + 1)",
+             v->maxLBS, v->maxLECP, ECP_KMAX);
   v->nfac = 2 * v->tmDim + 2;
   t->fac = factorial_table(2 * v->tmDim + 1, 1);
   t->dfac = factorial_table(2 * v->tmDim + 1, 2);
@@ -714,10 +721,8 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   }
   build_small_grid(t);
   build_large_grid(t, largeGridOrder);
-  if (build_bessel(t, v->maxLECP + v->maxAlpha + 6, accuracy)) {
-    ecp_tables_free(t);
-    return NULL;
-  }
+  if (build_bessel(t, v->maxLECP + v->maxAlpha + 6, accuracy))
+    TAB_FAIL("Bessel tabulation did not converge (reference src/libecp.c:181-185)");
   v->fac = t->fac;
   v->dfac = t->dfac;
   v->ijk = t->ijk;
@@ -739,8 +744,6 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   t->shellRadius = malloc((nsh + 1) * sizeof(double));
   for (int s = 0; s < nsh; s++)
     t->shellRadius[s] = shell_radius(KBS[s], lBS[s], dBS + t->shellPrim[s], aBS + t->shellPrim[s], 1.0E-14);
-  t->rowDeal = NULL; /* dealt on the first sharded use: ecp_tables_row_deal */
-  t->dealL = lBS; t->dealK = KBS; t->dealA = aBS;
   t->atomRmax = calloc(nrAtoms + 1, sizeof(double));
   for (int s = 0; s < nsh; s++)
     if (t->shellRadius[s] > t->atomRmax[t->shellAtom[s]]) t->atomRmax[t->shellAtom[s]] = t->shellRadius[s];
@@ -846,10 +849,7 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
       }
     }
     if (!pass) {
-      if (nc > ECP_MAX_CLASSES) {
-        ecp_tables_free(t);
-        return NULL;
-      }
+      if (nc > ECP_MAX_CLASSES) TAB_FAIL("more than %d (la, lb, L) classes", ECP_MAX_CLASSES);
       t->clsLa = malloc((nc + 1) * sizeof(int));
       t->clsLb = malloc((nc + 1) * sizeof(int));
       t->clsL = malloc((nc + 1) * sizeof(int));

@@ -55,6 +55,8 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
                             const int *shellsBS, const int *lBS, const int *KBS, const double *dBS, const double *aBS,
                             int largeGridOrder, double tolerance, double accuracy);
 void ecp_tables_free(EcpTables *t);
+/* why the last ecp_tables_build of this thread returned NULL */
+const char *ecp_tables_last_error(void);
 /* row deal of a sharded run (see rowDeal); computed on first use, thread-safe */
 const int *ecp_tables_row_deal(EcpTables *t);
 

@@ -28,7 +28,9 @@ def allgather_shards(pack, unpack, rows, sizes, rank, world, device, group=None,
 
     cap = max(max(sizes), 1)  # all_gather wants equal shards: pad to the largest
     if buffers is None or buffers[0].numel() < cap:
-        buffers = (torch.zeros(cap, dtype=torch.float64, device=device),
+        # torch.empty, not zeros: a fill kernel on torch's stream would not be ordered against the pack kernel, which
+        # runs on the library's own non-blocking stream (unpack only reads the packed prefix of every shard)
+        buffers = (torch.empty(cap, dtype=torch.float64, device=device),
                    torch.empty(world * cap, dtype=torch.float64, device=device))
     send, recv = buffers
     pack(rows[rank], send[:cap])

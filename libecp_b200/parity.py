@@ -1,0 +1,137 @@
+"""Result check of a 19 000 x 19 000 ECP matrix against the reference's digest (harness code: tests and bench.py).
+
+The digest (tests/golden/cfg5_full_digest.npz, generator tests/golden/make_cfg5_full.py) comes from a full
+500-centre run of the UNMODIFIED reference: row / column sums, sum and sum|.| of every (atom, atom) block, and 200 000
+fixed non-zero elements.  `check_digest` evaluates the same quantities of a result that is resident on the GPU (a torch
+view of the handle's device pointer, no 2.9 GB download) or of a numpy matrix, and compares them with the tolerance of
+the parity tests, |x - ref| <= 1e-12 + 1e-10 |ref| element-wise (sums: the same bound on the sum of |.| they run over).
+
+Nothing here computes integrals; the product path never imports this module.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def atom_ao_offsets(s):
+    """first AO of every atom (+ total) for a synth system"""
+    nao = np.array([(l + 1) * (l + 2) // 2 for l in s["lBS"]], np.int64)
+    first = np.zeros(int(s["nat"]) + 1, np.int64)
+    first[1:] = np.cumsum(s["shellsBS"])
+    ao = np.zeros(len(nao) + 1, np.int64)
+    ao[1:] = np.cumsum(nao)
+    return ao[first]
+
+
+class _DevPtr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n, n), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+def device_view(ptr, n):
+    """torch tensor aliasing the handle's device-resident nAO x nAO matrix (no copy)"""
+    import torch
+
+    return torch.as_tensor(_DevPtr(ptr, n), device="cuda")
+
+
+def _block_sums(M, off):
+    """[nat, nat] sums of M over the (atom, atom) AO blocks; numpy or torch"""
+    if isinstance(M, np.ndarray):
+        rows = np.add.reduceat(M, off[:-1], axis=0)
+        return np.add.reduceat(rows, off[:-1], axis=1)
+    import torch
+
+    nat = len(off) - 1
+    ids = torch.repeat_interleave(torch.arange(nat, device=M.device),
+                                  torch.as_tensor(np.diff(off), device=M.device))
+    rows = torch.zeros((nat, M.shape[1]), dtype=M.dtype, device=M.device).index_add_(0, ids, M)
+    return torch.zeros((nat, nat), dtype=M.dtype, device=M.device).index_add_(1, ids, rows)
+
+
+def make_digest(M, s, path, nsample=200000, seed=20261018, **extra):
+    """write the digest of a reference matrix M (numpy) of system `s` (used by tests/golden/make_cfg5_full.py)"""
+    off = atom_ao_offsets(s)
+    A = np.abs(M)
+    flat = M.ravel()
+    nz = np.flatnonzero(flat)
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(nz, size=min(nsample, len(nz)), replace=False))
+    out = dict(dim=int(s["dim"]), nat=int(s["nat"]), rowsum=M.sum(1), colsum=M.sum(0), rowabs=A.sum(1),
+               ablk_sum=_block_sums(M, off), ablk_abs=_block_sums(A, off), sum=M.sum(), sumabs=A.sum(), nnz=len(nz),
+               sample_idx=pick, sample_val=flat[pick], **extra)
+    np.savez_compressed(path, **out)
+    return out
+
+
+def check_digest(M, s, digest="cfg5_full_digest.npz"):
+    """Compare matrix M (numpy array or CUDA torch tensor, upper triangle incl. diagonal) of system `s` with a
+    reference digest.  Returns a dict with max_abs / max_rel over the sampled elements, the worst sum deviations in
+    units of their tolerance, and ok."""
+    z = np.load(digest if os.path.isabs(digest) else os.path.join(GOLDEN, digest))
+    n = int(z["dim"])
+    assert tuple(M.shape) == (n, n)
+    off = atom_ao_offsets(s)
+    is_np = isinstance(M, np.ndarray)
+    if is_np:
+        to_np = lambda x: np.asarray(x)  # noqa: E731
+        A = np.abs(M)
+        sample = M.ravel()[z["sample_idx"]]
+        lower = float(np.abs(np.tril(M, -1)).max()) if n else 0.0
+    else:
+        import torch
+
+        to_np = lambda x: x.detach().cpu().numpy()  # noqa: E731
+        A = M.abs()
+        sample = to_np(M.reshape(-1)[torch.as_tensor(z["sample_idx"], device=M.device)])
+        lower = float(torch.tril(A, -1).max().item()) if n else 0.0
+    ref = z["sample_val"]
+    err = np.abs(sample - ref)
+    tol = 1e-12 + 1e-10 * np.abs(ref)
+    big = np.abs(ref) > 1e-8
+    res = {
+        "reference": "full 500-centre run of the unmodified reference (tests/golden/cfg5_full_digest.npz)",
+        "samples": int(len(ref)), "max_abs": float(err.max()), "max_rel": float((err[big] / np.abs(ref[big])).max()),
+        "sample_violations": int((err > tol).sum()),
+    }
+    rowabs = to_np(A.sum(1))
+    rowsum, colsum = to_np(M.sum(1)), to_np(M.sum(0))
+    colabs = to_np(A.sum(0))
+    res["rowsum_worst"] = float((np.abs(rowsum - z["rowsum"]) / (1e-11 + 1e-10 * z["rowabs"])).max())
+    res["colsum_worst"] = float((np.abs(colsum - z["colsum"]) / (1e-11 + 1e-10 * colabs)).max())
+    res["rowabs_worst"] = float((np.abs(rowabs - z["rowabs"]) / (1e-11 + 1e-10 * z["rowabs"])).max())
+    bs, ba = to_np(_block_sums(M, off)), to_np(_block_sums(A, off))
+    res["atom_blocks"] = int((z["ablk_abs"] > 0).sum())
+    res["ablk_sum_worst"] = float((np.abs(bs - z["ablk_sum"]) / (1e-11 + 1e-10 * z["ablk_abs"])).max())
+    res["ablk_abs_worst"] = float((np.abs(ba - z["ablk_abs"]) / (1e-11 + 1e-10 * z["ablk_abs"])).max())
+    # identical screening and indexing: the same (atom, atom) blocks are touched, nothing below the diagonal
+    res["block_support_equal"] = bool(np.array_equal(ba > 0, z["ablk_abs"] > 0))
+    res["lower_triangle_max"] = lower
+    tot, totabs = float(to_np(M.sum())), float(to_np(A.sum()))
+    res["sum_rel_dev"] = abs(tot - float(z["sum"])) / float(z["sumabs"])
+    res["sumabs_rel_dev"] = abs(totabs - float(z["sumabs"])) / float(z["sumabs"])
+    res["ok"] = bool(res["sample_violations"] == 0 and res["rowsum_worst"] <= 1.0 and res["colsum_worst"] <= 1.0
+                     and res["rowabs_worst"] <= 1.0 and res["ablk_sum_worst"] <= 1.0 and res["ablk_abs_worst"] <= 1.0
+                     and res["block_support_equal"] and lower == 0.0 and res["sum_rel_dev"] <= 1e-10)
+    return res
+
+
+def check_matrix(M, name):
+    """small configurations: element-wise against the committed full reference matrix tests/golden/<name>_matrix.npz"""
+    z = np.load(os.path.join(GOLDEN, f"{name}_matrix.npz"))
+    dim = int(z["dim"])
+    ref = np.zeros((dim, dim))
+    ref[np.triu_indices(dim)] = z["triu"]
+    if not isinstance(M, np.ndarray):
+        M = M.detach().cpu().numpy()
+    err = np.abs(M - ref)
+    tol = 1e-12 + 1e-10 * np.abs(ref)
+    big = np.abs(ref) > 1e-8
+    return {"reference": f"unmodified reference, full matrix (tests/golden/{name}_matrix.npz)", "samples": int(ref.size),
+            "max_abs": float(err.max()), "max_rel": float((err[big] / np.abs(ref[big])).max()) if big.any() else 0.0,
+            "sample_violations": int((err > tol).sum()), "ok": bool(np.all(err <= tol))}

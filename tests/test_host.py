@@ -8,6 +8,7 @@ import re
 import numpy as np
 import pytest
 
+from conftest import GOLDEN
 from libecp_b200 import build, capi, synth
 from oracle.refbind import RefLib, _p, _pd, _pi
 
@@ -509,3 +510,63 @@ def test_screening_windows_identical_over_many_distances():
             skipped += int((~live).sum())
     o.close()
     assert checked > 500 and skipped > 500
+
+
+def test_sharding_queries_on_a_handle_without_ecp_centres():
+    """owned_rows / pair_owner need only the basis bookkeeping: legal on a handle with no ECP centre (every rank of a
+    gather lists every rank's rows)"""
+    s = synth.mask_centres(synth.cfg3(4), [])
+    h = capi.Handle(s, tables_only=True)
+    rows = [h.owned_rows(r, 2) for r in range(2)]
+    assert sorted(np.concatenate(rows).tolist()) == list(range(int(s["dim"])))
+    assert capi.lib().libecp_b200_pair_owner(h.h, 0, 5, 2) in (0, 1)
+    h.close()
+
+
+def test_init_rejections_carry_their_own_message():
+    s = synth.cfg2()
+    with pytest.raises(RuntimeError, match="derivative order n=1"):
+        capi.Handle(s, n=1, tables_only=True)
+    # g shells under an L = 2 potential: outside the compiled-in shape domain, rejected with the shape in the message
+    bad = synth.assemble("bad", [(0.0, 0.0, 0.0)], [synth.tz_basis(4)], [synth.ecp_set(2)])
+    with pytest.raises(RuntimeError, match="unsupported shape: max l of the basis 4, max L of the ECPs 2"):
+        capi.Handle(bad, tables_only=True)
+
+
+def test_digest_checker_accepts_the_reference_and_rejects_a_perturbation(tmp_path):
+    """libecp_b200/parity.py (the result check of bench.py and of the full config-5 GPU test) on a small system:
+    the reference's own matrix passes, a 1e-6 relative change of one element or a value below the diagonal does not"""
+    from libecp_b200 import parity
+    from oracle.refbind import RefLib, have
+
+    s = synth.cfg3(3)
+    M = RefLib("ref" if have("ref") else "port").get_integrals(s)
+    f = str(tmp_path / "d.npz")
+    parity.make_digest(M, s, f, nsample=4000)
+    assert parity.check_digest(M, s, f)["ok"]
+    i, j = np.unravel_index(np.argmax(np.abs(M)), M.shape)
+    bad = M.copy()
+    bad[i, j] *= 1.0 + 1e-6
+    assert not parity.check_digest(bad, s, f)["ok"]
+    bad = M.copy()
+    bad[5, 2] = 1e-9
+    assert not parity.check_digest(bad, s, f)["ok"]
+    bad = M.copy()
+    off = parity.atom_ao_offsets(s)
+    bad[off[0]:off[1], off[2]:off[3]] = 0.0  # a whole (atom, atom) block missing: screening / indexing error
+    r = parity.check_digest(bad, s, f)
+    assert not r["ok"] and not r["block_support_equal"]
+
+
+def test_committed_config5_digest_is_self_consistent():
+    z = np.load(os.path.join(GOLDEN, "cfg5_full_digest.npz"))
+    assert int(z["dim"]) == 19000 and int(z["nat"]) == 500 and int(z["nominal"]) == 9767187500
+    assert abs(z["rowsum"].sum() - float(z["sum"])) <= 1e-12 * float(z["sumabs"])
+    assert abs(z["ablk_sum"].sum() - float(z["sum"])) <= 1e-12 * float(z["sumabs"])
+    assert abs(z["ablk_abs"].sum() - float(z["sumabs"])) <= 1e-12 * float(z["sumabs"])
+    assert np.all(np.tril(z["ablk_abs"], -1) == 0.0)
+    # the four single-centre digests of round 1 are partial sums of it: every element they sample that is also sampled
+    # here cannot exceed it in a way additivity forbids - checked loosely through the support of the rows
+    for c in (0, 1, 288, 289):
+        zc = np.load(os.path.join(GOLDEN, f"cfg5_c{c}_digest.npz"))
+        assert np.all((zc["rowabs"] > 0) <= (z["rowabs"] > 0))
