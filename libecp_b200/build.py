@@ -17,8 +17,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libecp_b200.so")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp", "-Xptxas", "-v"]
+if os.environ.get("LIBECP_B200_NOFMAD"):  # A/B builds of the round-1 flag
+    NVCC_FLAGS.insert(4, "-fmad=false")
 CC_FLAGS = ["-O2", "-fPIC", "-Wall", "-Wno-comment", "-ffp-contract=off", "-std=gnu11", "-fopenmp"]
 
 

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "lib", "libecp_b200.so")
+# LIBECP_B200_SO: another build of the same library (A/B of compiler flags, tools/); never a different code path
+SO_PATH = os.environ.get("LIBECP_B200_SO") or os.path.join(HERE, "lib", "libecp_b200.so")
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int)

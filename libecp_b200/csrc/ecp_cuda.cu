@@ -1,8 +1,7 @@
 /* ecp_cuda.cu - hand-written FP64 sm_100a kernels for the ECP hot path + the thin C-ABI device layer.
  *
- * Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
- * (-fmad=false: decisions such as Bessel node index, exponent gates and convergence tests are taken on
- *  the same doubles as the reference takes them; see ecp_math.h).
+ * Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo
+ * (FMA contraction on; values an integer decision reads are pinned with __dmul_rn / __dadd_rn, see ecp_math.h).
  *
  * Kernel map (reference code each one replaces, paths relative to /root/reference):
  *   k_triprep    one record per triple + the pair -> triple map                 (indices only)
@@ -12,7 +11,7 @@
  *   k_fastT(2)   type-2 fast path, PS93 on Fa*Fb*r^N U_l, two launches    src/type2.c:336-381
  *   k_fallbackG  type-2 large-grid fallback, PSM92 per primitive pair     src/type2.c:417-528   (ecp_fallback.cuh)
  *   k_link       gamma = sum Omega_A Omega_B T, one launch per class      src/type2.c:583-623
- *   k_link2      the same on shared-memory slices (experimental, off by default)
+ *   k_link4      the same for the large classes: slices in shared memory, compile-time strides, runs of triples
  *   k_t1prep     P, |P|, S_lm(P^), pair record per primitive pair         src/type1.c:235-252
  *   k_type1S/L   radial Q(N,lambda): PS93 small grid, PSM92 fallback      src/type1.c:94-208    (ecp_type1.cuh)
  *   k_chi        chi = sum poly2sph (sum_pairs S Q), 8 lanes per triple   src/type1.c:266-295
@@ -369,6 +368,7 @@ __global__ void __launch_bounds__(128) k_fastT(DevT t, DevB b, long long nWork, 
   }
   if (valid && rc != 2) fast_store(b, w, rc, res, tri, l);
 }
+template <int UNR>
 __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const FastSurv *surv, int survCap) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(b.counters[8], survCap);
@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
   const long long w = surv[i].w;
   const FastQ f = fast_load(t, b, w);
   double res = 0.0;
-  const int rc = ecp_ps93_fastT_levels(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, &t.sm, t.small_jL, t.small_jR, f.gs,
-                                       f.ge, t.tolerance, lim, ECP_SMALL_LEVELS, &st, &res, (int *)0);
+  const int rc = ecp_ps93_fastT_levels_u<UNR>(f.Fa, f.strA, f.Fb, f.strB, f.U, f.strU, c_small_w, &t.sm, t.small_jL, t.small_jR,
+                                              f.gs, f.ge, t.tolerance, lim, ECP_SMALL_LEVELS, &st, &res, (int *)0);
   fast_store(b, w, rc, res, f.tri, f.l);
 }
 
@@ -502,104 +502,166 @@ typedef void (*LinkKernel)(DevT, DevB, int);
 static const LinkKernel g_linkKernels[ECP_MAX_LBS + 1][ECP_MAX_LBS + 1] = {LINK_ROW(1), LINK_ROW(2), LINK_ROW(3),
                                                                            LINK_ROW(4), LINK_ROW(5), LINK_ROW(6)};
 
-/* ---- link, experimental variant (OFF by default; LIBECP_B200_LINK=smem): Omega slices and T staged in shared memory ----
- * Why: k_link is bound by the L2 latency of its Omega loads (ncu, profiles/r1: ~9 warps stalled on the long scoreboard
- * per issue, L1 hit rate 78 %): every thread of a triple walks the same two small slices - Omega_A rows
- * [lambda < la+L][(l,m) < L^2][p < C_DIM(la)] and the same for B - each value being read by C_DIM(lb) resp. C_DIM(la)
- * threads, one dependent global load at a time.  Here a block takes `tpb` consecutive triples of the class, copies
- * their slices (rows of Omega_X truncated to the shell's C_DIM: d-d, L = 4: 2 x 960 doubles) and their T values into
- * shared memory with coalesced, independent loads, and then runs exactly the loop nest of k_link on shared memory
- * (same operations in the same order: gamma must come out bit-identical to k_link's).
- * Only for classes with at least LINK2_MIN_ELEMS gamma elements per triple (the staged values are reused by that many
- * threads) and slices that fit; everything else keeps k_link.
- * STATUS: written at the end of round 1 after the GPU budget was spent - compiles, never run.  To try it:
- *   LIBECP_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_parity.py -k link_smem      (parity with k_link)
- *   python tools/ab_kernels.py cfg3 LIBECP_B200_LINK=-,smem                                (A/B timing) */
-#define LINK2_MIN_ELEMS 40
-#define LINK2_MAX_SMEM (46 * 1024)
-template <int NA, int NB>
-__global__ void __launch_bounds__(128) k_link2(DevT t, DevB b, int c, int tpb, int slotStride) {
-  constexpr int la = NA - 1, lb = NB - 1;
-  constexpr int cda = (la + 1) * (la + 2) * (la + 3) / 6, cdb = (lb + 1) * (lb + 2) * (lb + 3) / 6, E = cda * cdb;
-  extern __shared__ __align__(16) double lk_sm[];
-  const int L = t.clsL[c], L2 = L * L, nq = t.clsNq[c];
-  const int SA = (la + L) * L2 * cda, SB = (lb + L) * L2 * cdb;
-  const int nTri = b.clsFirst[c + 1] - b.clsFirst[c];
-  const int lt0 = blockIdx.x * tpb; /* first triple of the block, class-local */
-  /* ---- stage: every thread of the block copies, triple after triple ---- */
-  for (int s = 0; s < tpb && lt0 + s < nTri; s++) {
-    const TriRec rec = b.trirec[b.clsFirst[c] + lt0 + s];
-    double *A = lk_sm + (size_t)s * slotStride, *Bm = A + SA, *Ts = Bm + SB;
-    const double *gA = b.omX + rec.omA, *gB = b.omX + rec.omB;
-    for (int i = threadIdx.x; i < SA; i += blockDim.x) {
-      const int row = i / cda; /* row = lambda * L^2 + (l,m): rows of Omega_X are incA1 apart */
-      A[i] = gA[(size_t)row * rec.incA1 + (i - row * cda)];
-    }
-    for (int i = threadIdx.x; i < SB; i += blockDim.x) {
-      const int row = i / cdb;
-      Bm[i] = gB[(size_t)row * rec.incB1 + (i - row * cdb)];
-    }
-    const double *gT = b.T + b.clsWork[c] + (long long)(lt0 + s) * nq;
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) Ts[i] = gT[i];
+/* ---- link, specialised shared-memory kernel for the large classes (default; LIBECP_B200_LINK=global keeps k_link) ----
+ * ncu on k_link and on two shared-memory rewrites of it (profiles/r2: k_link2 of round 1, staging per triple, and
+ * k_link3, staging per run of triples) showed the same picture: 66-71 % of the issue slots busy, 10 % of the executed
+ * instructions DFMA - integer multiply-adds for strides that are only known at run time, predicates and zeroing of the
+ * (lambda1, lambda2) tile, a division per staged element.  The link is instruction-issue bound.  k_link4 removes the
+ * instructions instead of hiding their latency:
+ *   - templated on (la+1, lb+1, L): every stride inside the staged slices is a compile-time constant, the l and m
+ *     loops are fully unrolled, so the tile update is  NA + NB  LDS with immediate offsets and  NA * NB  DFMA;
+ *   - no predication: rows beyond the admissible lambda are simply read (they lie inside the shared-memory slab; a
+ *     tile entry they feed is never used because its qidx entry is < 0);
+ *   - a thread owns one gamma element for the whole block; its per-l slice offsets and the NA * NB * L positions of
+ *     its T values are computed once per block and kept in registers;
+ *   - runs: the angular factors depend on the two atoms only, so they are formed once for the consecutive triples of
+ *     the class that share both (k_link3's idea, kept), and only the slice that changed is staged again.
+ * Per element the multiply-adds and their order are those of k_link (src/type2.c:583-623): gamma is bit-identical
+ * (up to the sign of exact zeros: the first m term is a product instead of fma(a, b, +0)). */
+#define LINK4_RMAX 4
+#define LINK4_MAXL 5
+/* one l of the link for one gamma element: the tile is as large as the admissible lambda counts of this l can get,
+ * min(la, (la + l) / 2) + 1 by min(lb, (lb + l) / 2) + 1 (compile time) */
+template <int NA, int NB, int L, int l>
+__device__ __forceinline__ void link4_level(const double *__restrict__ pa, const double *__restrict__ pb,
+                                            const double *__restrict__ Ts, const int (&kk)[NA][NB], int rl,
+                                            double (&g)[LINK4_RMAX]) {
+  constexpr int la = NA - 1, lb = NB - 1, L2 = L * L;
+  constexpr int cda = (la + 1) * (la + 2) * (la + 3) / 6, cdb = (lb + 1) * (lb + 2) * (lb + 3) / 6;
+  constexpr int incA1 = cda, incA2 = L2 * cda, incB1 = cdb, incB2 = L2 * cdb;
+  constexpr int NAl = ((la + l) / 2 + 1 < NA) ? (la + l) / 2 + 1 : NA, NBl = ((lb + l) / 2 + 1 < NB) ? (lb + l) / 2 + 1 : NB;
+  double f[NAl][NBl];
+#pragma unroll
+  for (int m = 0; m < 2 * l + 1; m++) {
+    double a[NAl], bb[NBl];
+#pragma unroll
+    for (int i = 0; i < NAl; i++) a[i] = pa[(2 * i) * incA2 + m * incA1];
+#pragma unroll
+    for (int j = 0; j < NBl; j++) bb[j] = pb[(2 * j) * incB2 + m * incB1];
+#pragma unroll
+    for (int i = 0; i < NAl; i++)
+#pragma unroll
+      for (int j = 0; j < NBl; j++) f[i][j] = (m == 0) ? a[i] * bb[j] : fma(a[i], bb[j], f[i][j]);
   }
-  __syncthreads();
-  /* ---- compute: thread -> (triple slot, element); triples with more than 128 elements loop ---- */
-  const int16_t *qi = t.qidx + t.clsQidxOff[c];
-  const int d2 = lb + L, d3 = la + lb + 1;
-  const int incA1 = cda, incA2 = L2 * cda, incB1 = cdb, incB2 = L2 * cdb; /* strides inside the staged slices */
-  for (int e = threadIdx.x; e < tpb * E; e += blockDim.x) {
-    const int s = e / E, pq = e - s * E;
-    if (lt0 + s >= nTri) break;
-    const int p = pq / cdb, q = pq - p * cdb;
-    const int alpha = deg_of_cindex(p), beta = deg_of_cindex(q);
-    const double *oA = lk_sm + (size_t)s * slotStride + p, *oB = lk_sm + (size_t)s * slotStride + SA + q;
-    const double *T = lk_sm + (size_t)s * slotStride + SA + SB;
-    double g = 0.0;
+#pragma unroll
+  for (int r = 0; r < LINK4_RMAX; r++)
+    if (r < rl) {
+      double tmp = 0.0;
+#pragma unroll
+      for (int i = 0; i < NAl; i++)
+#pragma unroll
+        for (int j = 0; j < NBl; j++) tmp = fma(f[i][j], Ts[kk[i][j] + r], tmp);
+      g[r] += tmp;
+    }
+}
+template <int NA, int NB, int L, int... Ls>
+__device__ __forceinline__ void link4_levels(const double *A, const double *Bm, const double *Ts, const int (&offA)[L],
+                                             const int (&offB)[L], const int (&kk)[L][NA][NB], int rl,
+                                             double (&g)[LINK4_RMAX], std::integer_sequence<int, Ls...>) {
+  (link4_level<NA, NB, L, Ls>(A + offA[Ls], Bm + offB[Ls], Ts, kk[Ls], rl, g), ...);
+}
+#define LINK4_BD(NA, NB) ((((NA) * ((NA) + 1) * ((NA) + 2) / 6) * ((NB) * ((NB) + 1) * ((NB) + 2) / 6) + 31) / 32 * 32)
+template <int NA, int NB, int L>
+__global__ void __launch_bounds__(LINK4_BD(NA, NB), (512 / LINK4_BD(NA, NB) > 0 ? 512 / LINK4_BD(NA, NB) : 1))
+    k_link4(DevT t, DevB b, int c, int tpb, int smTotal) {
+  constexpr int la = NA - 1, lb = NB - 1, L2 = L * L;
+  constexpr int cda = (la + 1) * (la + 2) * (la + 3) / 6, cdb = (lb + 1) * (lb + 2) * (lb + 3) / 6, E = cda * cdb;
+  constexpr int SA = (la + L) * L2 * cda, SB = (lb + L) * L2 * cdb;
+  constexpr int incA1 = cda, incA2 = L2 * cda, incB1 = cdb, incB2 = L2 * cdb;
+  constexpr int d2 = lb + L, d3 = la + lb + 1, BD = LINK4_BD(NA, NB); /* = blockDim.x */
+  extern __shared__ __align__(16) double lk_sm[];
+  /* A | B | T of the run, [quadrature][triple of the run] + one row of zeros | slack.  Rows beyond the admissible
+   * lambda are read without a predicate: from A they fall into B, from B into T and the slack, which hold finite
+   * numbers (the slack and the zero row are cleared once); the tile entries they feed meet the zero row of T. */
+  double *A = lk_sm, *Bm = A + SA, *Ts = Bm + SB;
+  const int nq = t.clsNq[c];
+  const int first = b.clsFirst[c], nTri = b.clsFirst[c + 1] - first;
+  const int lt0 = blockIdx.x * tpb, lt1 = min(lt0 + tpb, nTri);
+  const int e = threadIdx.x;
+  const bool active = e < E;
+  const int p = active ? e / cdb : 0, q = active ? e - p * cdb : 0;
+  const int alpha = deg_of_cindex(p), beta = deg_of_cindex(q);
+  int offA[L], offB[L], kk[L][NA][NB]; /* kk: offset of the quadrature's T row (the zero row if the factor vanishes) */
+  {
+    const int16_t *qi = t.qidx + t.clsQidxOff[c];
+#pragma unroll
     for (int l = 0; l < L; l++) {
       int ll1 = l - alpha, ll2 = l - beta;
       const int par1 = (alpha + l) % 2, par2 = (beta + l) % 2;
       ll1 = (par1 > ll1) ? par1 : ll1;
       ll2 = (par2 > ll2) ? par2 : ll2;
-      const int n1 = (la + l - ll1) / 2 + 1, n2 = (lb + l - ll2) / 2 + 1;
-      double f[NA][NB];
-#pragma unroll
-      for (int i = 0; i < NA; i++)
-#pragma unroll
-        for (int j = 0; j < NB; j++) f[i][j] = 0.0;
-      const double *pa = oA + ll1 * incA2 + (l * l) * incA1;
-      const double *pb = oB + ll2 * incB2 + (l * l) * incB1;
-      for (int m = 0; m < 2 * l + 1; m++) {
-        double a[NA], bb[NB];
-#pragma unroll
-        for (int i = 0; i < NA; i++) a[i] = (i < n1) ? pa[(2 * i) * incA2] : 0.0;
-#pragma unroll
-        for (int j = 0; j < NB; j++) bb[j] = (j < n2) ? pb[(2 * j) * incB2] : 0.0;
-#pragma unroll
-        for (int i = 0; i < NA; i++)
-#pragma unroll
-          for (int j = 0; j < NB; j++) f[i][j] = fma(a[i], bb[j], f[i][j]);
-        pa += incA1;
-        pb += incB1;
-      }
-      double tmp = 0.0;
+      const int n1 = (la + l - ll1) / 2 + 1, n2 = (lb + l - ll2) / 2 + 1; /* lambda1 = ll1 + 2i, lambda2 = ll2 + 2j */
+      offA[l] = p + ll1 * incA2 + (l * l) * incA1;
+      offB[l] = q + ll2 * incB2 + (l * l) * incB1;
       const int16_t *ql = qi + ((l * (la + L) + ll1) * d2 + ll2) * d3 + alpha + beta;
 #pragma unroll
       for (int i = 0; i < NA; i++)
 #pragma unroll
-        for (int j = 0; j < NB; j++)
-          if (i < n1 && j < n2) {
-            const int k = ql[(2 * i * d2 + 2 * j) * d3];
-            if (k >= 0) tmp = fma(f[i][j], T[k], tmp);
-          }
-      g += tmp;
+        for (int j = 0; j < NB; j++) {
+          int k = (i < n1 && j < n2) ? (int)ql[(2 * i * d2 + 2 * j) * d3] : -1;
+          kk[l][i][j] = (k >= 0 ? k : nq) * LINK4_RMAX;
+        }
     }
-    b.gamma[b.clsElem[c] + (long long)(lt0 + s) * E + pq] = g;
+  }
+  for (int i = SA + SB + threadIdx.x; i < smTotal; i += BD) lk_sm[i] = 0.0;
+  constexpr int RPA = BD / cda, RPB = BD / cdb; /* rows of a slice one sweep of the block copies */
+  const int rowA = threadIdx.x / cda, colA = threadIdx.x - rowA * cda, rowB = threadIdx.x / cdb, colB = threadIdx.x - rowB * cdb;
+  long long curA = -1, curB = -1;
+  for (int lt = lt0; lt < lt1;) {
+    const TriRec rec = b.trirec[first + lt];
+    int rl = 1; /* run: triples with the same two atom slots */
+    while (rl < LINK4_RMAX && lt + rl < lt1) {
+      const TriRec *r2 = &b.trirec[first + lt + rl];
+      if (r2->omA != rec.omA || r2->omB != rec.omB) break;
+      rl++;
+    }
+    __syncthreads(); /* the previous run's readers are through */
+    if (rec.omA != curA) { /* rows (lambda, (l,m)) of Omega_A, cut to the cda columns of the shell: RPA rows per sweep */
+      const double *gA = b.omX + rec.omA + rowA * rec.incA1 + colA;
+      const int stepG = RPA * rec.incA1;
+      if (rowA < RPA) {
+#pragma unroll 4
+        for (int r = rowA, o = 0; r < (la + L) * L2; r += RPA, o += stepG) A[r * cda + colA] = gA[o];
+      }
+      curA = rec.omA;
+    }
+    if (rec.omB != curB) {
+      const double *gB = b.omX + rec.omB + rowB * rec.incB1 + colB;
+      const int stepG = RPB * rec.incB1;
+      if (rowB < RPB) {
+#pragma unroll 4
+        for (int r = rowB, o = 0; r < (lb + L) * L2; r += RPB, o += stepG) Bm[r * cdb + colB] = gB[o];
+      }
+      curB = rec.omB;
+    }
+    {
+      const double *gT = b.T + b.clsWork[c] + (long long)lt * nq; /* T of consecutive triples is contiguous */
+      for (int r = 0; r < rl; r++)
+        for (int i = threadIdx.x; i < nq; i += BD) Ts[i * LINK4_RMAX + r] = gT[r * nq + i];
+    }
+    __syncthreads();
+    if (active) {
+      double g[LINK4_RMAX];
+#pragma unroll
+      for (int r = 0; r < LINK4_RMAX; r++) g[r] = 0.0;
+      link4_levels<NA, NB, L>(A, Bm, Ts, offA, offB, kk, rl, g, std::make_integer_sequence<int, L>{});
+      double *out = b.gamma + b.clsElem[c] + (long long)lt * E + e;
+#pragma unroll
+      for (int r = 0; r < LINK4_RMAX; r++)
+        if (r < rl) out[(size_t)r * E] = g[r];
+    }
+    lt += rl;
   }
 }
-typedef void (*Link2Kernel)(DevT, DevB, int, int, int);
-#define LINK2_ROW(A) {k_link2<A, 1>, k_link2<A, 2>, k_link2<A, 3>, k_link2<A, 4>, k_link2<A, 5>, k_link2<A, 6>}
-static const Link2Kernel g_link2Kernels[ECP_MAX_LBS + 1][ECP_MAX_LBS + 1] = {LINK2_ROW(1), LINK2_ROW(2), LINK2_ROW(3),
-                                                                             LINK2_ROW(4), LINK2_ROW(5), LINK2_ROW(6)};
+typedef void (*Link4Kernel)(DevT, DevB, int, int, int);
+/* classes with at least 36 gamma elements per triple among the s-f shells, L = 1..5; everything else keeps k_link */
+#define LINK4_L(A, B) {NULL, k_link4<A, B, 1>, k_link4<A, B, 2>, k_link4<A, B, 3>, k_link4<A, B, 4>, k_link4<A, B, 5>}
+#define LINK4_NONE {NULL, NULL, NULL, NULL, NULL, NULL}
+static const Link4Kernel g_link4Kernels[4][4][LINK4_MAXL + 1] = {
+    {LINK4_NONE, LINK4_NONE, LINK4_NONE, LINK4_NONE},
+    {LINK4_NONE, LINK4_NONE, LINK4_L(2, 3), LINK4_L(2, 4)},
+    {LINK4_NONE, LINK4_L(3, 2), LINK4_L(3, 3), LINK4_L(3, 4)},
+    {LINK4_NONE, LINK4_L(4, 2), LINK4_L(4, 3), LINK4_L(4, 4)}};
 
 #include "ecp_type1.cuh"
 
@@ -785,8 +847,11 @@ struct EcpDev {
   Buf fastSurv;
   int ftabCompact; /* LIBECP_B200_FTAB=compact: experimental window-only F tabulation (k_Ftab2) */
   int shiftFused; /* LIBECP_B200_SHIFT=fused: experimental single shift of 4 pi chi + 16 pi^2 gamma in matrix-only runs */
-  int linkSmem; /* LIBECP_B200_LINK=smem: experimental shared-memory link kernel for the large classes (k_link2) */
+  int linkMode; /* LIBECP_B200_LINK: 4 (default) specialised shared-memory kernel k_link4 for the large classes; global = k_link
+                 * everywhere */
+  int linkTpb;  /* LIBECP_B200_LINKTPB: consecutive triples per block of k_link4 (0 = sized to the class) */
   int fastLim; /* levels of the first fast-path launch (LIBECP_B200_FASTLIM, default 4 = 15 points) */
+  int fastUnroll; /* LIBECP_B200_FASTUNROLL: point pairs of the survivors' loop whose loads are in flight together (1, 2, 4) */
   long long survCapEnv; /* LIBECP_B200_SURVCAP: survivor-list capacity override (tests of the overflow path) */
   Buf t1list, t1mask, t1count, t1work, t1rec, trirec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
   int launchSeq;
@@ -912,13 +977,19 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     d->fastLim = e ? atoi(e) : 4;
     {
       const char *lk = getenv("LIBECP_B200_LINK");
-      d->linkSmem = lk && !strcmp(lk, "smem");
+      d->linkMode = (lk && !strcmp(lk, "global")) ? 1 : 4;
+      {
+        const char *tp = getenv("LIBECP_B200_LINKTPB");
+        d->linkTpb = tp ? atoi(tp) : 0;
+      }
       lk = getenv("LIBECP_B200_SHIFT");
       d->shiftFused = lk && !strcmp(lk, "fused");
       lk = getenv("LIBECP_B200_FTAB");
       d->ftabCompact = lk && !strcmp(lk, "compact");
     }
     if (d->fastLim < 1) d->fastLim = 1;
+    e = getenv("LIBECP_B200_FASTUNROLL");
+    d->fastUnroll = e ? atoi(e) : 1;
     e = getenv("LIBECP_B200_SURVCAP");
     d->survCapEnv = e ? atoll(e) : 0;
     e = getenv("LIBECP_B200_FBBLOCK");
@@ -1685,7 +1756,12 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     launches++;
     if (lim < ECP_SMALL_LEVELS) {
       /* the survivor count lives on the device: the grid covers the list capacity, surplus blocks leave at once */
-      k_fastT2<<<nblk(survCap, 128), 128, 0, d->s1>>>(t, B, lim, (const FastSurv *)d->fastSurv.p, survCap);
+      if (d->fastUnroll == 4)
+        k_fastT2<4><<<nblk(survCap, 128), 128, 0, d->s1>>>(t, B, lim, (const FastSurv *)d->fastSurv.p, survCap);
+      else if (d->fastUnroll == 2)
+        k_fastT2<2><<<nblk(survCap, 128), 128, 0, d->s1>>>(t, B, lim, (const FastSurv *)d->fastSurv.p, survCap);
+      else
+        k_fastT2<1><<<nblk(survCap, 128), 128, 0, d->s1>>>(t, B, lim, (const FastSurv *)d->fastSurv.p, survCap);
       launches++;
     }
   }
@@ -1724,16 +1800,28 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     const long long ne = h->clsElem[c + 1] - h->clsElem[c];
     if (ne <= 0) continue;
     const int la_ = d->hClsLa[c], lb_ = d->hClsLb[c], Lc_ = d->hClsL[c];
-    const int E_ = ((la_ + 1) * (la_ + 2) * (la_ + 3) / 6) * ((lb_ + 1) * (lb_ + 2) * (lb_ + 3) / 6);
-    if (d->linkSmem && E_ >= LINK2_MIN_ELEMS) { /* experimental, off by default (see k_link2) */
-      const int SA = (la_ + Lc_) * Lc_ * Lc_ * ((la_ + 1) * (la_ + 2) * (la_ + 3) / 6);
-      const int SB = (lb_ + Lc_) * Lc_ * Lc_ * ((lb_ + 1) * (lb_ + 2) * (lb_ + 3) / 6);
-      const int slotStride = SA + SB + d->hClsNq[c] + 1;
-      const int tpb = E_ >= 128 ? 1 : 128 / E_;
-      const size_t smem = (size_t)tpb * slotStride * sizeof(double);
-      if (smem <= LINK2_MAX_SMEM) {
-        const long long ntri = h->clsFirst[c + 1] - h->clsFirst[c];
-        g_link2Kernels[la_][lb_]<<<nblk(ntri, tpb), 128, smem, d->s1>>>(t, B, c, tpb, slotStride);
+    const int cda_ = (la_ + 1) * (la_ + 2) * (la_ + 3) / 6, cdb_ = (lb_ + 1) * (lb_ + 2) * (lb_ + 3) / 6;
+    const int E_ = cda_ * cdb_;
+    const int SA = (la_ + Lc_) * Lc_ * Lc_ * cda_, SB = (lb_ + Lc_) * Lc_ * Lc_ * cdb_;
+    const long long ntri = h->clsFirst[c + 1] - h->clsFirst[c];
+    const Link4Kernel k4 = (d->linkMode == 4 && la_ < 4 && lb_ < 4 && Lc_ <= LINK4_MAXL) ? g_link4Kernels[la_][lb_][Lc_] : NULL;
+    if (k4) { /* specialised shared-memory kernel for the large classes */
+      const int slack = (la_ * Lc_ * Lc_ * cda_ > lb_ * Lc_ * Lc_ * cdb_) ? la_ * Lc_ * Lc_ * cda_ : lb_ * Lc_ * Lc_ * cdb_;
+      const int smTotal = SA + SB + LINK4_RMAX * (d->hClsNq[c] + 1) + slack; /* doubles: slices, T rows + zero row, slack */
+      const size_t smem = (size_t)smTotal * sizeof(double);
+      if (smem <= 200 * 1024) {
+        static unsigned char attr_[ECP_MAXDEV][4][4][LINK4_MAXL + 1];
+        unsigned char *at = &attr_[d->device < ECP_MAXDEV ? d->device : 0][la_][lb_][Lc_];
+        if (!*at || d->device >= ECP_MAXDEV) {
+          cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          *at = 1;
+        }
+        /* triples per block: long enough to reuse a staged Omega_A over the runs that share atom A and to pay for the
+         * per-block set-up, short enough that a small class still fills the device */
+        long long tpb = d->linkTpb > 0 ? d->linkTpb : ntri / (4LL * d->nSM);
+        if (tpb < 1) tpb = 1;
+        if (d->linkTpb <= 0 && tpb > 16) tpb = 16;
+        k4<<<nblk(ntri, (int)tpb), ((E_ + 31) / 32) * 32, smem, d->s1>>>(t, B, c, (int)tpb, smTotal);
         launches++;
         continue;
       }

@@ -4,10 +4,9 @@
  * compiled by g++ into a test-only harness (tests/hostcheck) and compared with the oracle on the CPU
  * before GPU time is spent.  The product never runs these on the host.
  *
- * The arithmetic follows the reference's operation order (file:line cited per function); the CUDA
- * translation unit is compiled with -fmad=false so that no product-sum is contracted and decisions
- * (Bessel branch / node index, exponent gates, window cuts, convergence tests) are taken on the same
- * doubles as the reference takes them.
+ * The arithmetic follows the reference's operation order (file:line cited per function).  The host harness compiles
+ * this header with -ffp-contract=off (bit-identity tests against the oracle); the CUDA translation unit allows FMA
+ * contraction except where ECP_MUL_RN / ECP_ADD_RN pin a value an integer decision reads (see below).
  */
 #ifndef ECP_MATH_H
 #define ECP_MATH_H
@@ -25,6 +24,20 @@
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
+#endif
+
+/* The CUDA translation unit is compiled with FMA contraction enabled (round 2; round 1 used -fmad=false).  Products and
+ * sums whose value an INTEGER decision reads are formed with these, so that no contraction can move them off the
+ * reference's doubles: the Bessel node index (src/bessel.c:141).  Everything the host decides (screening, windows,
+ * triple list) never passes through device arithmetic.  Floating-point gates and convergence tests compare values that
+ * already differ from the reference's in the last ulp (device exp / sin, summation order); a contraction there adds
+ * nothing new in kind ("stop-level flips"). */
+#if defined(__CUDA_ARCH__)
+#define ECP_MUL_RN(a, b) __dmul_rn((a), (b))
+#define ECP_ADD_RN(a, b) __dadd_rn((a), (b))
+#else
+#define ECP_MUL_RN(a, b) ((a) * (b))
+#define ECP_ADD_RN(a, b) ((a) + (b))
 #endif
 
 /* index helpers (reference src/dimensions.h:18-29) */
@@ -61,7 +74,7 @@ ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double 
   } else if (z < 16.0) {
     double d[KM + 6];
     const int maxL = lmax + 5;
-    const int index = (int)floor(z * 100.0 + 0.5);
+    const int index = (int)floor(ECP_ADD_RN(ECP_MUL_RN(z, 100.0), 0.5));
     const double dz = z - index / 100.0;
     const double *row = tabT + (size_t)index * stride;
     double scale = 1.0;
@@ -131,7 +144,7 @@ ECP_HD int ecp_bessel_mem(const double *__restrict__ tabT, int stride, const dou
     return 0;
   } else if (z < 16.0) {
     const int maxL = lmax + 5;
-    const int index = (int)floor(z * 100.0 + 0.5);
+    const int index = (int)floor(ECP_ADD_RN(ECP_MUL_RN(z, 100.0), 0.5));
     const double dz = z - index / 100.0;
     const double *row = tabT + (size_t)index * stride;
     double scale = 1.0;
@@ -392,7 +405,8 @@ ECP_HD int ecp_psm92_update(int nNew, int cnt, double tol, double I, double pv, 
 typedef struct {
   double I, p, q;
 } EcpPs93State;
-ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
+template <int UNR>
+ECP_HD int ecp_ps93_fastT_levels_u(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
                                  const double *__restrict__ U, int su, const double *__restrict__ w,
                                  const EcpSmallMeta *meta, const unsigned char *__restrict__ jL,
                                  const unsigned char *__restrict__ jR, int start, int end, double tol, int v0, int v1,
@@ -434,7 +448,7 @@ ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const do
         I += w[s + 1] * (Fa[oa + sa] * Fb[ob + sb] * U[ou + su]);
     }
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+#pragma unroll UNR
 #endif
     for (int j = j1; j < npair; j++, s += 2, oa += 2 * sa, ob += 2 * sb, ou += 2 * su) {
       double T = w[s] * (Fa[oa] * Fb[ob] * U[ou]);
@@ -452,6 +466,13 @@ ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const do
   st->p = p;
   st->q = q;
   return (v1 >= ECP_SMALL_LEVELS) ? 1 : 2;
+}
+ECP_HD int ecp_ps93_fastT_levels(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
+                                 const double *__restrict__ U, int su, const double *__restrict__ w,
+                                 const EcpSmallMeta *meta, const unsigned char *__restrict__ jL,
+                                 const unsigned char *__restrict__ jR, int start, int end, double tol, int v0, int v1,
+                                 EcpPs93State *st, double *result, int *npts) {
+  return ecp_ps93_fastT_levels_u<1>(Fa, sa, Fb, sb, U, su, w, meta, jL, jR, start, end, tol, v0, v1, st, result, npts);
 }
 ECP_HD int ecp_ps93_fastT(const double *__restrict__ Fa, int sa, const double *__restrict__ Fb, int sb,
                           const double *__restrict__ U, int su, const double *__restrict__ w, const EcpSmallMeta *meta,

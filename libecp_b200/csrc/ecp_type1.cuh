@@ -19,6 +19,10 @@
  *     3 double shuffles per quadrature per lane by one store + one load per owned quadrature and makes the level
  *     update (PS93 / PSM92 state I,p,q of quadrature q lives in lane q mod 8) run on all lanes at once;
  *   - convergence is a ballot over the group.
+ *   Measured and rejected in round 2 (profiles/r2/README.md): a "dense" variant that strings the live points of a pair
+ *   (inside the window and below the exponent gate) into one sequence across the levels and lets a chunk span levels
+ *   halves the chunks of a typical pair, but its per-pair set-up (gate search, level table) and the point-by-point
+ *   owner loop cost more than the chunks saved: 1.17 -> 1.30 ms on Au20, 30.9 -> 38.5 ms per config-5 pass.
  *   k_type1S<LAB>: small 383-point grid, PS93; writes converged Q, records a mask of failed quadratures
  *   k_type1L<LAB>: failed quadratures on the per-pair FM06-mapped 1023-point grid, PSM92
  */

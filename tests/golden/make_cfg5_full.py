@@ -12,7 +12,9 @@ The 2.9 GB matrix cannot be committed; the digest keeps
   sample_idx, sample_val   : 200 000 fixed non-zero elements (flat index, value)
   sum, sumabs, nnz
 
-    python tests/golden/make_cfg5_full.py [nproc]          (about 5 minutes on 8 cores, 25 GB of RAM)
+    python tests/golden/make_cfg5_full.py [nproc]          (about 6 minutes on 8 cores, 25 GB of RAM)
+    python tests/golden/make_cfg5_full.py --variant fma     (same run with oracle/_ref/libecp_ref_fma.so, `make -C oracle
+                                                             ref_fma`: the reference against itself, see oracle/Makefile)
 
 Run in the build container only (needs oracle/_ref built from /root/reference by oracle/Makefile).
 """
@@ -33,8 +35,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 TMP = os.environ.get("CFG5_TMP", "/tmp")
 
 
+VARIANT = None  # None: the -O2 build of oracle/Makefile (the oracle); "fma": the same sources, -mfma -ffp-contract=fast
+
+
 def worker(p, queue, done):
     ref = RefLib("ref")
+    if VARIANT == "fma":  # same binding, other build of the same unmodified sources
+        ref.lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libecp_ref_fma.so"))
+        ref.f_get = ref.lib.getIntegrals
+        ref.f_get.restype = C.c_int
     full = synth.cfg5(500)
     dim = int(full["dim"])
     M = np.zeros((dim, dim))
@@ -63,7 +72,26 @@ def digest(M, s, seconds, nproc):
           f"lower-triangle zero: {bool(np.all(np.tril(M, -1) == 0.0))}  {seconds:.0f}s on {nproc} procs")
 
 
+def variant_digest(M, seconds, nproc):
+    """the reference against ITSELF: values of the other build at the sample positions of the committed digest"""
+    z = np.load(os.path.join(HERE, "cfg5_full_digest.npz"))
+    val = M.ravel()[z["sample_idx"]]
+    ref = z["sample_val"]
+    err = np.abs(val - ref)
+    bad = err > 1e-12 + 1e-10 * np.abs(ref)
+    np.savez_compressed(os.path.join(HERE, f"cfg5_full_variant_{VARIANT}.npz"), sample_val=val, rowsum=M.sum(1),
+                        sum=M.sum(), sumabs=np.abs(M).sum(), ref_seconds=seconds, ref_procs=nproc,
+                        build="gcc -O2 -fPIC -mfma -ffp-contract=fast (oracle/Makefile target ref_fma)")
+    print(f"variant {VARIANT}: {int(bad.sum())} of {len(ref)} sampled elements outside 1e-12 + 1e-10|ref| of the -O2 build, "
+          f"max |d| {err.max():.3e}, max rel {np.max(err / np.maximum(np.abs(ref), 1e-300)):.3e}")
+
+
 def main():
+    global VARIANT
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        VARIANT = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
     nproc = int(sys.argv[1]) if len(sys.argv) > 1 else (os.cpu_count() or 8)
     s = synth.cfg5(500)
     centres = [i for i in range(int(s["nat"])) if s["shellsECP"][i] > 0]
@@ -91,7 +119,10 @@ def main():
         part = np.load(f)
         M = part if M is None else M.__iadd__(part)
         os.remove(f)
-    digest(M, s, seconds, nproc)
+    if VARIANT:
+        variant_digest(M, seconds, nproc)
+    else:
+        digest(M, s, seconds, nproc)
 
 
 if __name__ == "__main__":

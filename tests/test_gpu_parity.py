@@ -288,22 +288,22 @@ def test_gather_pack_unpack_rebuilds_the_full_matrix():
         assert_parity(M + M1, ref, "shard union after a gather")
 
 
-@pytest.mark.skipif(not os.environ.get("LIBECP_B200_EXPERIMENTAL"),
-                    reason="experimental kernels are opt-in: set LIBECP_B200_EXPERIMENTAL=1")
-def test_link_smem_variant_matches_default():
-    """k_link2 (LIBECP_B200_LINK=smem, off by default: Omega slices and T staged in shared memory) performs the
-    operations of k_link in the same order: gamma must be bit-identical and the matrices equal to the last ulps"""
-    for s, name in ((synth.cfg3(4), "au4"), (synth.cfg4("a"), "cfg4a")):
+def test_link_variants_are_bit_identical():
+    """k_link4 (default for the large classes: Omega slices staged per run of triples that share both atoms, strides
+    and loops fixed at compile time) performs the per-element operations of k_link (LIBECP_B200_LINK=global) in the same
+    order: gamma must be bit-identical, for any triples-per-block setting; L = 2, 4 (config 5), 4 (Au), 5 (g stress)"""
+    for s, name in ((synth.cfg3(4), "au4"), (synth.cfg4("a"), "cfg4a"), (synth.cfg5(24), None)):
         def run():
             with capi.Handle(s) as h:
                 rc, M = h.integrals_host()
-                n = 200000
-                return M, h.debug_fetch("gamma", n)
-        base, g0 = run()
-        assert_parity(base, load_matrix(name), name)
-        got, g1 = _with_env({"LIBECP_B200_LINK": "smem"}, run)
-        assert np.array_equal(g0, g1), name
-        assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
+                return M, h.debug_fetch("gamma", 400000)
+        base, g0 = _with_env({"LIBECP_B200_LINK": "global"}, run)
+        if name:
+            assert_parity(base, load_matrix(name), name)
+        for env in ({}, {"LIBECP_B200_LINKTPB": "1"}, {"LIBECP_B200_LINKTPB": "5"}, {"LIBECP_B200_LINKTPB": "64"}):
+            got, g1 = _with_env(env, run)
+            assert np.array_equal(g0, g1), (name, env)
+            assert np.allclose(got, base, rtol=1e-13, atol=1e-15), (name, env)
 
 
 @pytest.mark.skipif(not os.environ.get("LIBECP_B200_EXPERIMENTAL"),

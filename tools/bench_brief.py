@@ -20,4 +20,11 @@ for line in sys.stdin:
         s = d["secondary"]
         msg += "\n  Au20 %.2f ms/step device %.2f %s whole-step frac %.4f" % (
             s["ms_per_step"], s["device_ms_per_step"], s["roofline"]["kernel_ms_per_step"], s["roofline"]["whole_step_frac"])
+    if d.get("parity"):
+        p = d["parity"]
+        msg += "\n  parity ok=%s max_abs %.2e max_rel %.2e %s" % (p.get("ok"), p.get("max_abs", -1), p.get("max_rel", -1), {k: (round(v, 4) if isinstance(v, float) else v) for k, v in p.items() if k.endswith("_worst") or k in ("block_support_equal", "sample_violations")})
+    if d.get("allgather"):
+        msg += "\n  allgather %s" % d["allgather"]
+    if d.get("per_rank"):
+        msg += "\n  per_rank %s" % d["per_rank"]
     print(msg)
