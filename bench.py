@@ -396,26 +396,40 @@ def run_b200(args):
            "ms_init": 1e3 * parts[0] / e2e_steps, "ms_integrate_d2h": 1e3 * parts[1] / e2e_steps,
            "ms_free": 1e3 * parts[2] / e2e_steps}
 
-    # ---- device-resident consumer at N > 1: one NCCL all-gather of the packed shards (not part of `value`) ----
-    allgather = None
+    # ---- device-resident consumer at N > 1: the C-ABI collective (libecp_b200_allgather: pack + one in-place
+    #      ncclAllGather over NVLink + scatter), timed alone and as part of the step (`gathered`) ----
+    allgather = gathered = None
     if dist:
-        from libecp_b200 import gather
-
-        h.integrals_device()
-        bufs, ts, nbytes = None, [], 0
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(rank, world, uid[0])
+        nbytes = 0
+        for _ in range(2):  # warm-up: NCCL channel set-up, staging buffers
+            h.integrals_device()
+            nbytes = h.allgather()
+            h.device_sync()
+        ts = []
         for _ in range(3):
+            h.integrals_device()
             barrier()
-            dt, nbytes, bufs = gather.allgather_matrix(h, rank, world, buffers=bufs)
-            ts.append(max_over_ranks(dt))
-            h.integrals_device()  # a scatter dirties the matrix: the pass after it starts with a full clear
-        allgather = {"ms": 1e3 * min(ts[1:]), "bytes_received_per_rank": int(nbytes),
-                     "GBps_per_rank": nbytes / min(ts[1:]) / 1e9,
-                     "note": "pack own rows + ncclAllGather (padded shards) + scatter of the other ranks' rows; "
-                             "leaves the full upper-triangular matrix on every GPU"}
-        # result check below: the matrix of the last pass, gathered
+            t0_ = time.perf_counter()
+            h.allgather()
+            h.device_sync()
+            ts.append(max_over_ranks(time.perf_counter() - t0_))
+        allgather = {"ms": 1e3 * min(ts), "bytes_received_per_rank": int(nbytes), "GBps_per_rank": nbytes / min(ts) / 1e9,
+                     "note": "libecp_b200_allgather: pack own rows + one in-place ncclAllGather (padded shards) + scatter of "
+                             "the other ranks' rows; leaves the full upper-triangular matrix on every GPU"}
         barrier()
-        gather.allgather_matrix(h, rank, world, buffers=bufs)
-        del bufs
+        t0_ = time.perf_counter()
+        for _ in range(args.steps):
+            h.integrals_device()
+            h.allgather()
+            h.device_sync()
+        barrier()
+        ms_g = max_over_ranks(1e3 * (time.perf_counter() - t0_))
+        gathered = {"value": nominal * args.steps / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / args.steps,
+                    "note": "same step followed by the all-gather: end state = the full matrix in every GPU's HBM, as at N=1"}
+        # the result check below reads the gathered matrix of the last of these steps
 
     # ---- parity of what was just timed: the matrix resident in HBM (after the all-gather at N > 1) against the
     #      reference (cfg5: digest of a full 500-centre run of the unmodified reference; small configs: full matrix) ----
@@ -466,6 +480,7 @@ def run_b200(args):
             line["per_rank"] = per_rank
         if allgather:
             line["allgather"] = allgather
+            line["gathered"] = gathered
     if world == 1 and rank == 0 and not args.no_secondary and args.workload != "cfg3":
         line["secondary"] = secondary_au20(capi, torch, peak_tf)
     h.close()

@@ -50,12 +50,28 @@ int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I);
  *                            DEVICE buffer of `cap` doubles (*elems = doubles used; devPacked NULL: only sizes it);
  *   libecp_b200_unpack_rows: scatters such a packed buffer (another rank's shard after the collective) into the
  *                            handle's device matrix.
- * The collective itself (ncclAllGather / torch.distributed.all_gather_into_tensor over NVLink) belongs to the caller,
- * which owns the communicator: libecp_b200/gather.py is the reference-side harness for it.  All three return 0 on
- * success, -1 on error (libecp_b200_last_error). */
+ * These three are the building blocks for a caller that brings its own collective (libecp_b200/gather.py does it with
+ * torch.distributed); libecp_b200_allgather below is the complete collective.  All three return 0 on success, -1 on
+ * error (libecp_b200_last_error). */
 long long libecp_b200_owned_rows(libECPHandle *h, int rank, int world, int *rows, long long cap);
 int libecp_b200_pack_rows(libECPHandle *h, const int *rows, long long nrows, void *devPacked, long long cap, long long *elems);
 int libecp_b200_unpack_rows(libECPHandle *h, const int *rows, long long nrows, const void *devPacked, long long cap);
+
+/* The collective itself, behind the C ABI (a C / Fortran caller needs no Python and no NCCL code of its own).  NCCL is
+ * bound with dlopen at first use.  Either the library creates the communicator -
+ *     rank 0:    libecp_b200_comm_unique_id(id);  ... the caller distributes the 128 bytes (MPI_Bcast, a file, ...) ...
+ *     all ranks: libecp_b200_comm_init(h, rank, world, id);          (collective; also does libecp_b200_set_shard)
+ * - or it adopts the caller's:  libecp_b200_comm_attach(h, (void *)ncclComm, rank, world).
+ * After libecp_b200_integrals_device() on every rank, libecp_b200_allgather(h, &bytes) packs the rank's rows, runs one
+ * in-place ncclAllGather over NVLink and scatters the other shards: the handle's device matrix then holds the full
+ * upper-triangular result on every GPU.  Stream-ordered on the handle's compute stream (libecp_b200_device_sync waits
+ * for it).  All return 0 on success, -1 on error (libecp_b200_last_error). */
+int libecp_b200_comm_unique_id(void *id128);
+int libecp_b200_comm_init(libECPHandle *h, int rank, int world, const void *id128);
+int libecp_b200_comm_attach(libECPHandle *h, void *ncclComm, int rank, int world);
+int libecp_b200_allgather(libECPHandle *h, long long *bytesReceived);
+int libecp_b200_device_sync(libECPHandle *h);
+void libecp_b200_comm_free(libECPHandle *h);
 
 typedef struct {
   long long nominal_triples;   /* centres x nshells(nshells+1)/2 : the reference's loop domain (src/libecp.c:256-312) */

@@ -26,7 +26,8 @@ EXPORTS = [
     "libecp_b200_host_table", "libecp_b200_host_itable", "libecp_b200_triple_list", "libecp_b200_set_tables_only",
     "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
     "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only", "libecp_b200_owned_rows", "libecp_b200_pack_rows", "libecp_b200_unpack_rows",
-    "libecp_b200_matrix_ptr",
+    "libecp_b200_matrix_ptr", "libecp_b200_comm_unique_id", "libecp_b200_comm_init", "libecp_b200_comm_attach",
+    "libecp_b200_allgather", "libecp_b200_device_sync", "libecp_b200_comm_free",
 ]
 
 
@@ -94,6 +95,14 @@ def set_host_threads(n: int) -> None:
 
 def fp64_peak(dev: int = 0, iters: int = 200000) -> float:
     return float(lib().libecp_b200_fp64_peak(int(dev), int(iters)))
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it, the caller distributes it to all ranks)"""
+    buf = C.create_string_buffer(128)
+    if lib().libecp_b200_comm_unique_id(buf):
+        raise RuntimeError("comm_unique_id: " + (lib().libecp_b200_last_error() or b"").decode())
+    return buf.raw
 
 
 def get_integrals(s, tol=1e-12, acc=1e-14, large=1024):
@@ -183,6 +192,27 @@ class Handle:
         f.restype = C.c_void_p
         f.argtypes = [C.c_void_p]
         return f(C.c_void_p(self.h)) or 0
+
+    def comm_init(self, rank, world, unique_id: bytes):
+        """collective: communicator inside the library from the 128-byte NCCL unique id (see comm_unique_id)"""
+        f = lib().libecp_b200_comm_init
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        if f(C.c_void_p(self.h), rank, world, unique_id):
+            raise RuntimeError("comm_init: " + (lib().libecp_b200_last_error() or b"").decode())
+
+    def allgather(self):
+        """after integrals_device() on every rank: NCCL all-gather of the shards; returns bytes received"""
+        f = lib().libecp_b200_allgather
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        n = C.c_longlong(0)
+        if f(C.c_void_p(self.h), C.byref(n)):
+            raise RuntimeError("allgather: " + (lib().libecp_b200_last_error() or b"").decode())
+        return int(n.value)
+
+    def device_sync(self):
+        f = lib().libecp_b200_device_sync
+        f.argtypes = [C.c_void_p]
+        return f(C.c_void_p(self.h))
 
     def set_serial_kernels(self, on=True):
         L = lib()

@@ -392,6 +392,43 @@ int libecp_b200_unpack_rows(libECPHandle *h, const int *rows, long long nrows, c
   return ecpdev_matrix_rows(h->dev, 1, rows, nrows, (void *)devPacked, cap, NULL) ? -1 : 0;
 }
 
+/* ---- C-ABI collective (include/libecp_b200.h): NCCL all-gather of the shards of a device-resident result ---- */
+int libecp_b200_comm_unique_id(void *id128) { return ecpdev_comm_unique_id(id128) ? -1 : 0; }
+static int comm_layout(libECPHandle *h, int world) {
+  int **rows = calloc(world, sizeof(int *));
+  long long *nrows = calloc(world, sizeof(long long));
+  for (int r = 0; r < world; r++) {
+    nrows[r] = libecp_b200_owned_rows(h, r, world, NULL, 0);
+    rows[r] = malloc((size_t)(nrows[r] + 1) * sizeof(int));
+    libecp_b200_owned_rows(h, r, world, rows[r], nrows[r]);
+  }
+  const int rc = ecpdev_allgather_layout(h->dev, (const int *const *)rows, nrows);
+  for (int r = 0; r < world; r++) free(rows[r]);
+  free(rows);
+  free(nrows);
+  return rc ? -1 : 0;
+}
+int libecp_b200_comm_init(libECPHandle *h, int rank, int world, const void *id128) {
+  if (!h || h->empty || !h->dev || world < 1 || rank < 0 || rank >= world) return -1;
+  if (ecpdev_comm_init(h->dev, rank, world, id128, NULL)) return -1;
+  libecp_b200_set_shard(h, rank, world);
+  return comm_layout(h, world);
+}
+int libecp_b200_comm_attach(libECPHandle *h, void *ncclComm, int rank, int world) {
+  if (!h || h->empty || !h->dev || !ncclComm || world < 1 || rank < 0 || rank >= world) return -1;
+  if (ecpdev_comm_init(h->dev, rank, world, NULL, ncclComm)) return -1;
+  libecp_b200_set_shard(h, rank, world);
+  return comm_layout(h, world);
+}
+int libecp_b200_allgather(libECPHandle *h, long long *bytesReceived) {
+  if (!h || h->empty || !h->dev) return -1;
+  return ecpdev_allgather(h->dev, bytesReceived) ? -1 : 0;
+}
+int libecp_b200_device_sync(libECPHandle *h) { return (h && h->dev) ? (ecpdev_sync(h->dev) ? -1 : 0) : 0; }
+void libecp_b200_comm_free(libECPHandle *h) {
+  if (h && h->dev) ecpdev_comm_destroy(h->dev);
+}
+
 int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   const int n = h->tab->v.nAO;
   const double tCall = now_ms();

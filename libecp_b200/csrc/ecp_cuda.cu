@@ -561,22 +561,39 @@ __device__ __forceinline__ void link4_levels(const double *A, const double *Bm, 
   (link4_level<NA, NB, L, Ls>(A + offA[Ls], Bm + offB[Ls], Ts, kk[Ls], rl, g), ...);
 }
 #define LINK4_BD(NA, NB) ((((NA) * ((NA) + 1) * ((NA) + 2) / 6) * ((NB) * ((NB) + 1) * ((NB) + 2) / 6) + 31) / 32 * 32)
+/* 8-byte asynchronous global -> shared copy (LDGSTS): the slices of the NEXT run arrive while this run is computed */
+__device__ __forceinline__ void cp_async8(double *smemDst, const double *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#define LINK4_TPB_MAX 32
 template <int NA, int NB, int L>
 __global__ void __launch_bounds__(LINK4_BD(NA, NB), (512 / LINK4_BD(NA, NB) > 0 ? 512 / LINK4_BD(NA, NB) : 1))
-    k_link4(DevT t, DevB b, int c, int tpb, int smTotal) {
+    k_link4(DevT t, DevB b, int c, int tpb, int tsz, int smTotal) {
   constexpr int la = NA - 1, lb = NB - 1, L2 = L * L;
   constexpr int cda = (la + 1) * (la + 2) * (la + 3) / 6, cdb = (lb + 1) * (lb + 2) * (lb + 3) / 6, E = cda * cdb;
   constexpr int SA = (la + L) * L2 * cda, SB = (lb + L) * L2 * cdb;
-  constexpr int incA1 = cda, incA2 = L2 * cda, incB1 = cdb, incB2 = L2 * cdb;
+  constexpr int incA2 = L2 * cda, incB2 = L2 * cdb;
   constexpr int d2 = lb + L, d3 = la + lb + 1, BD = LINK4_BD(NA, NB); /* = blockDim.x */
   extern __shared__ __align__(16) double lk_sm[];
-  /* A | B | T of the run, [quadrature][triple of the run] + one row of zeros | slack.  Rows beyond the admissible
-   * lambda are read without a predicate: from A they fall into B, from B into T and the slack, which hold finite
-   * numbers (the slack and the zero row are cleared once); the tile entries they feed meet the zero row of T. */
-  double *A = lk_sm, *Bm = A + SA, *Ts = Bm + SB;
+  /* A0 A1 | B0 B1 | T0 T1 ([quadrature][triple of the run] + one row of zeros each) | slack.  Two copies of each: the
+   * slices of run k+1 are fetched with cp.async while run k is computed.  Rows beyond the admissible lambda are read
+   * without a predicate: from A they fall into the next slice, from B into T and the slack, which hold finite numbers
+   * (everything is cleared once); the tile entries they feed meet the zero row of T. */
+  double *Abuf = lk_sm, *Bbuf = Abuf + 2 * SA, *Tbuf = Bbuf + 2 * SB;
+  __shared__ long long mOmA[LINK4_TPB_MAX], mOmB[LINK4_TPB_MAX];
+  __shared__ int mIncA[LINK4_TPB_MAX], mIncB[LINK4_TPB_MAX];
   const int nq = t.clsNq[c];
   const int first = b.clsFirst[c], nTri = b.clsFirst[c + 1] - first;
-  const int lt0 = blockIdx.x * tpb, lt1 = min(lt0 + tpb, nTri);
+  const int lt0 = blockIdx.x * tpb, nT = min(tpb, nTri - lt0); /* triples of this block */
+  if ((int)threadIdx.x < nT) {
+    const TriRec *r = &b.trirec[first + lt0 + threadIdx.x];
+    mOmA[threadIdx.x] = r->omA;
+    mOmB[threadIdx.x] = r->omB;
+    mIncA[threadIdx.x] = r->incA1;
+    mIncB[threadIdx.x] = r->incB1;
+  }
   const int e = threadIdx.x;
   const bool active = e < E;
   const int p = active ? e / cdb : 0, q = active ? e - p * cdb : 0;
@@ -591,8 +608,8 @@ __global__ void __launch_bounds__(LINK4_BD(NA, NB), (512 / LINK4_BD(NA, NB) > 0 
       ll1 = (par1 > ll1) ? par1 : ll1;
       ll2 = (par2 > ll2) ? par2 : ll2;
       const int n1 = (la + l - ll1) / 2 + 1, n2 = (lb + l - ll2) / 2 + 1; /* lambda1 = ll1 + 2i, lambda2 = ll2 + 2j */
-      offA[l] = p + ll1 * incA2 + (l * l) * incA1;
-      offB[l] = q + ll2 * incB2 + (l * l) * incB1;
+      offA[l] = p + ll1 * incA2 + (l * l) * cda;
+      offB[l] = q + ll2 * incB2 + (l * l) * cdb;
       const int16_t *ql = qi + ((l * (la + L) + ll1) * d2 + ll2) * d3 + alpha + beta;
 #pragma unroll
       for (int i = 0; i < NA; i++)
@@ -603,57 +620,70 @@ __global__ void __launch_bounds__(LINK4_BD(NA, NB), (512 / LINK4_BD(NA, NB) > 0 
         }
     }
   }
-  for (int i = SA + SB + threadIdx.x; i < smTotal; i += BD) lk_sm[i] = 0.0;
+  for (int i = threadIdx.x; i < smTotal; i += BD) lk_sm[i] = 0.0; /* unpredicated reads only ever see finite numbers */
   constexpr int RPA = BD / cda, RPB = BD / cdb; /* rows of a slice one sweep of the block copies */
   const int rowA = threadIdx.x / cda, colA = threadIdx.x - rowA * cda, rowB = threadIdx.x / cdb, colB = threadIdx.x - rowB * cdb;
+  __syncthreads();
+  /* issue the copies of the run that starts at block-local triple `s`; returns its length.  ia / ib: slice copies in use */
+  int ia = 0, ib = 0;
   long long curA = -1, curB = -1;
-  for (int lt = lt0; lt < lt1;) {
-    const TriRec rec = b.trirec[first + lt];
-    int rl = 1; /* run: triples with the same two atom slots */
-    while (rl < LINK4_RMAX && lt + rl < lt1) {
-      const TriRec *r2 = &b.trirec[first + lt + rl];
-      if (r2->omA != rec.omA || r2->omB != rec.omB) break;
-      rl++;
-    }
-    __syncthreads(); /* the previous run's readers are through */
-    if (rec.omA != curA) { /* rows (lambda, (l,m)) of Omega_A, cut to the cda columns of the shell: RPA rows per sweep */
-      const double *gA = b.omX + rec.omA + rowA * rec.incA1 + colA;
-      const int stepG = RPA * rec.incA1;
+  auto fetch = [&](int s, int tb, int &ja, int &jb, long long &nA, long long &nB) -> int {
+    const long long oA = mOmA[s], oB = mOmB[s];
+    int rl = 1;
+    while (rl < LINK4_RMAX && s + rl < nT && mOmA[s + rl] == oA && mOmB[s + rl] == oB) rl++;
+    if (oA != nA) { /* rows (lambda, (l,m)) of Omega_A, cut to the cda columns of the shell: RPA rows per sweep */
+      ja ^= 1;
+      nA = oA;
       if (rowA < RPA) {
+        const double *g = b.omX + oA + rowA * mIncA[s] + colA;
+        double *dst = Abuf + ja * SA + rowA * cda + colA;
+        const int stepG = RPA * mIncA[s];
 #pragma unroll 4
-        for (int r = rowA, o = 0; r < (la + L) * L2; r += RPA, o += stepG) A[r * cda + colA] = gA[o];
+        for (int r = rowA; r < (la + L) * L2; r += RPA, g += stepG, dst += RPA * cda) cp_async8(dst, g);
       }
-      curA = rec.omA;
     }
-    if (rec.omB != curB) {
-      const double *gB = b.omX + rec.omB + rowB * rec.incB1 + colB;
-      const int stepG = RPB * rec.incB1;
+    if (oB != nB) {
+      jb ^= 1;
+      nB = oB;
       if (rowB < RPB) {
+        const double *g = b.omX + oB + rowB * mIncB[s] + colB;
+        double *dst = Bbuf + jb * SB + rowB * cdb + colB;
+        const int stepG = RPB * mIncB[s];
 #pragma unroll 4
-        for (int r = rowB, o = 0; r < (lb + L) * L2; r += RPB, o += stepG) Bm[r * cdb + colB] = gB[o];
+        for (int r = rowB; r < (lb + L) * L2; r += RPB, g += stepG, dst += RPB * cdb) cp_async8(dst, g);
       }
-      curB = rec.omB;
     }
-    {
-      const double *gT = b.T + b.clsWork[c] + (long long)lt * nq; /* T of consecutive triples is contiguous */
-      for (int r = 0; r < rl; r++)
-        for (int i = threadIdx.x; i < nq; i += BD) Ts[i * LINK4_RMAX + r] = gT[r * nq + i];
-    }
-    __syncthreads();
+    const double *gT = b.T + b.clsWork[c] + (long long)(lt0 + s) * nq; /* T of consecutive triples is contiguous */
+    double *Ts = Tbuf + tb * tsz;
+    for (int r = 0; r < rl; r++)
+      for (int i = threadIdx.x; i < nq; i += BD) cp_async8(Ts + i * LINK4_RMAX + r, gT + r * nq + i);
+    return rl;
+  };
+  int s = 0, tb = 0;
+  int rl = nT > 0 ? fetch(0, 0, ia, ib, curA, curB) : 0;
+  while (s < nT) {
+    cp_async_wait_all();
+    __syncthreads(); /* run s has arrived; every thread is through with the run before it (its slices may be overwritten) */
+    const double *A = Abuf + ia * SA, *Bm = Bbuf + ib * SB, *Ts = Tbuf + tb * tsz;
+    const int sNext = s + rl;
+    int rlNext = 0;
+    if (sNext < nT) rlNext = fetch(sNext, tb ^ 1, ia, ib, curA, curB); /* ia / ib now name the NEXT run's slices */
     if (active) {
       double g[LINK4_RMAX];
 #pragma unroll
       for (int r = 0; r < LINK4_RMAX; r++) g[r] = 0.0;
       link4_levels<NA, NB, L>(A, Bm, Ts, offA, offB, kk, rl, g, std::make_integer_sequence<int, L>{});
-      double *out = b.gamma + b.clsElem[c] + (long long)lt * E + e;
+      double *out = b.gamma + b.clsElem[c] + (long long)(lt0 + s) * E + e;
 #pragma unroll
       for (int r = 0; r < LINK4_RMAX; r++)
         if (r < rl) out[(size_t)r * E] = g[r];
     }
-    lt += rl;
+    s = sNext;
+    rl = rlNext;
+    tb ^= 1;
   }
 }
-typedef void (*Link4Kernel)(DevT, DevB, int, int, int);
+typedef void (*Link4Kernel)(DevT, DevB, int, int, int, int);
 /* classes with at least 36 gamma elements per triple among the s-f shells, L = 1..5; everything else keeps k_link */
 #define LINK4_L(A, B) {NULL, k_link4<A, B, 1>, k_link4<A, B, 2>, k_link4<A, B, 3>, k_link4<A, B, 4>, k_link4<A, B, 5>}
 #define LINK4_NONE {NULL, NULL, NULL, NULL, NULL, NULL}
@@ -841,6 +871,11 @@ struct EcpDev {
   int matrixKnown, dirtyAll, nDirty; /* matrix is zero outside the upper-triangle parts of the dirty rows */
   long long dirtySig;
   Buf dirtyRows, gatherRows, gatherOff;
+  /* C-ABI collective (ecpdev_comm_*, ecpdev_allgather): NCCL communicator, shard layout of all ranks, staging */
+  void *comm;
+  int commOwned, commRank, commWorld;
+  Buf agRows, agOff, agBuf;
+  long long agCap, *agCount, *agFirst; /* per rank: packed doubles, first entry of its rows in agRows/agOff */
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES], hClsL[ECP_MAX_CLASSES], hClsNq[ECP_MAX_CLASSES];
@@ -857,6 +892,7 @@ struct EcpDev {
   int launchSeq;
   Buf dbgBuf;
   int tails; /* LIBECP_B200_TAILS */
+  int fbWarp; /* 1 (default): k_fallbackW, one warp per item; LIBECP_B200_FB=group: k_fallbackG, 8-lane groups */
   int fbblock, fbocc, fbminb; /* tuning knobs of the fallback kernel: LIBECP_B200_FBBLOCK threads, _FBOCC blocks per SM cap, _FBMINB */
   int t1block;                /* LIBECP_B200_T1BLOCK = 32/64/96/128 threads per block of the type-1 kernels */
 };
@@ -950,6 +986,7 @@ extern "C" void ecpdev_pinned_free(void *p) {
 extern "C" const char *ecpdev_last_error(void) { return g_err; }
 
 static void adopt_cached(EcpDev *d);
+static void comm_release(EcpDev *d);
 
 extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   int ndev = 0;
@@ -995,6 +1032,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     e = getenv("LIBECP_B200_FBBLOCK");
     d->fbblock = e ? atoi(e) : 64;
     if (d->fbblock != 32 && d->fbblock != 64 && d->fbblock != 128) d->fbblock = 64;
+    e = getenv("LIBECP_B200_FB");
+    d->fbWarp = !(e && !strcmp(e, "group"));
     e = getenv("LIBECP_B200_FBMINB");
     d->fbminb = e ? atoi(e) : 3;
     e = getenv("LIBECP_B200_FBOCC");
@@ -1224,6 +1263,10 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
     cudaStreamSynchronize(d->s1);
     if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
   }
+  comm_release(d);
+  if (d->agRows.p) cudaFreeAsync(d->agRows.p, d->s1);
+  if (d->agOff.p) cudaFreeAsync(d->agOff.p, d->s1);
+  if (d->agBuf.p) cudaFreeAsync(d->agBuf.p, d->s1);
   if (d->dirtyRows.p) cudaFreeAsync(d->dirtyRows.p, d->s1);
   if (d->gatherRows.p) cudaFreeAsync(d->gatherRows.p, d->s1);
   if (d->gatherOff.p) cudaFreeAsync(d->gatherOff.p, d->s1);
@@ -1768,25 +1811,32 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   CK(cudaEventRecord(d->ev[2], d->s1));
   if (nWork > 0) {
     {
-      /* persistent 8-lane groups; Bessel order bound of the instantiation: max(2 maxLBS, maxLBS + maxLECP - 1) */
+      /* persistent warps (k_fallbackW, one item per warp) or 8-lane groups (k_fallbackG, LIBECP_B200_FB=group); Bessel
+       * order bound of the instantiation: max(2 maxLBS, maxLBS + maxLECP - 1) */
       const int km = (2 * d->maxLBS > d->maxLBS + t.maxLECP - 1) ? 2 * d->maxLBS : d->maxLBS + t.maxLECP - 1;
-      const int block = d->fbblock;
+      const int block = d->fbWarp ? 128 : d->fbblock;
       void (*kern)(DevT, DevB);
-      size_t smem;
+      size_t smem, smemMax;
       int slot;
-      if (km <= 6) {
+      if (d->fbWarp) {
+        if (km <= 6 && d->fbminb == 4) { kern = k_fallbackW<6, 4>; smem = smemMax = fbw_smem_bytes<6>(block); slot = 0; }
+        else if (km <= 6) { kern = k_fallbackW<6, 3>; smem = smemMax = fbw_smem_bytes<6>(block); slot = 3; }
+        else { kern = k_fallbackW<10, 2>; smem = smemMax = fbw_smem_bytes<10>(block); slot = 4; }
+      } else if (km <= 6) {
         smem = fb_smem_bytes<6>(block);
+        smemMax = fb_smem_bytes<6>(128);
         if (d->fbminb == 4) { kern = k_fallbackG<6, 4>; slot = 0; } else { kern = k_fallbackG<6, 3>; slot = 1; }
       } else {
         smem = fb_smem_bytes<10>(block);
+        smemMax = fb_smem_bytes<10>(128);
         kern = k_fallbackG<10, 2>;
         slot = 2;
       }
-      static int occ_[ECP_MAXDEV][3][5] = {{{0}}};
-      int (*occ)[5] = occ_[d->device < ECP_MAXDEV ? d->device : 0];
+      static int occ_[ECP_MAXDEV][2][5][5] = {{{{0}}}};
+      int (*occ)[5] = occ_[d->device < ECP_MAXDEV ? d->device : 0][d->fbWarp];
       const int bi = block / 32;
       if (!occ[slot][bi] || d->device >= ECP_MAXDEV) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(km <= 6 ? fb_smem_bytes<6>(128) : fb_smem_bytes<10>(128)));
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[slot][bi], kern, block, smem);
         if (occ[slot][bi] < 1) occ[slot][bi] = 1;
       }
@@ -1807,7 +1857,8 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     const Link4Kernel k4 = (d->linkMode == 4 && la_ < 4 && lb_ < 4 && Lc_ <= LINK4_MAXL) ? g_link4Kernels[la_][lb_][Lc_] : NULL;
     if (k4) { /* specialised shared-memory kernel for the large classes */
       const int slack = (la_ * Lc_ * Lc_ * cda_ > lb_ * Lc_ * Lc_ * cdb_) ? la_ * Lc_ * Lc_ * cda_ : lb_ * Lc_ * Lc_ * cdb_;
-      const int smTotal = SA + SB + LINK4_RMAX * (d->hClsNq[c] + 1) + slack; /* doubles: slices, T rows + zero row, slack */
+      const int tsz = LINK4_RMAX * (d->hClsNq[c] + 1); /* T rows of a run + the zero row */
+      const int smTotal = 2 * (SA + SB + tsz) + slack; /* doubles: two copies of the slices and of T, slack */
       const size_t smem = (size_t)smTotal * sizeof(double);
       if (smem <= 200 * 1024) {
         static unsigned char attr_[ECP_MAXDEV][4][4][LINK4_MAXL + 1];
@@ -1821,7 +1872,8 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
         long long tpb = d->linkTpb > 0 ? d->linkTpb : ntri / (4LL * d->nSM);
         if (tpb < 1) tpb = 1;
         if (d->linkTpb <= 0 && tpb > 16) tpb = 16;
-        k4<<<nblk(ntri, (int)tpb), ((E_ + 31) / 32) * 32, smem, d->s1>>>(t, B, c, (int)tpb, smTotal);
+        if (tpb > LINK4_TPB_MAX) tpb = LINK4_TPB_MAX;
+        k4<<<nblk(ntri, (int)tpb), ((E_ + 31) / 32) * 32, smem, d->s1>>>(t, B, c, (int)tpb, tsz, smTotal);
         launches++;
         continue;
       }
@@ -1911,6 +1963,183 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     st->err1 = hc[2];
     st->err2 = hc[3];
   }
+  return 0;
+}
+
+/* ================================================================================================
+ * C-ABI collective for a sharded, device-resident result ("NCCL all-gather over NVLink when the matrix stays
+ * on the device").  Every rank holds the upper-triangle parts of its own AO rows; ecpdev_allgather packs them into the
+ * rank's slot of one receive buffer, runs ONE in-place ncclAllGather (shards padded to the largest) and scatters the
+ * other ranks' rows into the resident matrix - all on the handle's compute stream, no host synchronisation.
+ * NCCL is bound with dlopen at first use (a single-GPU caller needs no NCCL at all): libnccl.so.2 is whatever the
+ * process already loaded (e.g. the copy bundled with PyTorch) or the system library. */
+#include <dlfcn.h>
+struct EcpNcclId {
+  char internal[128];
+};
+typedef int (*PfnGetUniqueId)(EcpNcclId *);
+typedef int (*PfnCommInitRank)(void **, int, EcpNcclId, int);
+typedef int (*PfnAllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*PfnCommDestroy)(void *);
+typedef const char *(*PfnGetErrorString)(int);
+static struct {
+  void *lib;
+  PfnGetUniqueId getUniqueId;
+  PfnCommInitRank commInitRank;
+  PfnAllGather allGather;
+  PfnCommDestroy commDestroy;
+  PfnGetErrorString errorString;
+} g_nccl;
+static std::mutex g_ncclMu;
+static int nccl_bind() {
+  std::lock_guard<std::mutex> lk(g_ncclMu);
+  if (g_nccl.lib) return 0;
+  const char *names[] = {getenv("LIBECP_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+  void *lib = NULL;
+  for (int i = 0; i < 3 && !lib; i++)
+    if (names[i]) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    snprintf(g_err, sizeof(g_err), "libecp_b200: cannot load NCCL (libnccl.so.2): %s", dlerror());
+    return -1;
+  }
+  g_nccl.getUniqueId = (PfnGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+  g_nccl.commInitRank = (PfnCommInitRank)dlsym(lib, "ncclCommInitRank");
+  g_nccl.allGather = (PfnAllGather)dlsym(lib, "ncclAllGather");
+  g_nccl.commDestroy = (PfnCommDestroy)dlsym(lib, "ncclCommDestroy");
+  g_nccl.errorString = (PfnGetErrorString)dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.getUniqueId || !g_nccl.commInitRank || !g_nccl.allGather || !g_nccl.commDestroy) {
+    snprintf(g_err, sizeof(g_err), "libecp_b200: NCCL library lacks the expected entry points");
+    return -1;
+  }
+  g_nccl.lib = lib;
+  return 0;
+}
+#define NCCLCK(call)                                                                                   \
+  do {                                                                                                 \
+    const int r_ = (call);                                                                             \
+    if (r_ != 0) {                                                                                     \
+      snprintf(g_err, sizeof(g_err), "%s:%d: %s: %s", __FILE__, __LINE__, #call,                       \
+               g_nccl.errorString ? g_nccl.errorString(r_) : "NCCL error");                           \
+      return -1;                                                                                       \
+    }                                                                                                  \
+  } while (0)
+
+extern "C" int ecpdev_comm_unique_id(void *id128) {
+  if (nccl_bind()) return -1;
+  NCCLCK(g_nccl.getUniqueId((EcpNcclId *)id128));
+  return 0;
+}
+static void comm_release(EcpDev *d) {
+  if (d->comm && d->commOwned && g_nccl.commDestroy) g_nccl.commDestroy(d->comm);
+  d->comm = NULL;
+  d->commOwned = 0;
+  free(d->agCount);
+  d->agCount = NULL;
+  d->agFirst = NULL;
+}
+/* comm == NULL: create a communicator from the unique id (collective call: every rank of `world`); else adopt the
+ * caller's ncclComm_t (it stays the caller's) */
+extern "C" int ecpdev_comm_init(EcpDev *d, int rank, int world, const void *id128, void *comm) {
+  CK(cudaSetDevice(d->device));
+  if (nccl_bind()) return -1;
+  comm_release(d);
+  if (comm) {
+    d->comm = comm;
+    d->commOwned = 0;
+  } else {
+    EcpNcclId id;
+    memcpy(&id, id128, sizeof(id));
+    NCCLCK(g_nccl.commInitRank(&d->comm, world, id, rank));
+    d->commOwned = 1;
+  }
+  d->commRank = rank;
+  d->commWorld = world;
+  return 0;
+}
+extern "C" void ecpdev_comm_destroy(EcpDev *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->s1);
+  comm_release(d);
+}
+/* shard layout of all ranks: rows[r] = ascending AO rows of rank r (nrows[r] of them); uploaded once per communicator */
+extern "C" int ecpdev_allgather_layout(EcpDev *d, const int *const *rows, const long long *nrows) {
+  CK(cudaSetDevice(d->device));
+  const int world = d->commWorld, n = d->nAO;
+  if (!d->comm || world < 1) {
+    snprintf(g_err, sizeof(g_err), "ecpdev_allgather_layout: no communicator");
+    return -1;
+  }
+  long long tot = 0;
+  for (int r = 0; r < world; r++) tot += nrows[r];
+  int *hr = (int *)malloc((size_t)(tot + 1) * sizeof(int));
+  long long *ho = (long long *)malloc((size_t)(tot + 1) * sizeof(long long));
+  free(d->agCount);
+  d->agCount = (long long *)calloc(2 * (size_t)world + 2, sizeof(long long));
+  d->agFirst = d->agCount + world + 1;
+  long long k = 0, cap = 1;
+  for (int r = 0; r < world; r++) {
+    d->agFirst[r] = k;
+    long long off = 0;
+    for (long long i = 0; i < nrows[r]; i++, k++) {
+      const int row = rows[r][i];
+      if (row < 0 || row >= n || (i && row <= rows[r][i - 1])) {
+        free(hr);
+        free(ho);
+        snprintf(g_err, sizeof(g_err), "ecpdev_allgather_layout: rows of rank %d are not ascending AO rows", r);
+        return -1;
+      }
+      hr[k] = row;
+      ho[k] = off; /* offset inside the rank's packed shard */
+      off += n - row;
+    }
+    d->agCount[r] = off;
+    if (off > cap) cap = off;
+  }
+  d->agFirst[world] = k;
+  d->agCap = cap;
+  g_allocStream = d->s1;
+  int rc = ensure(&d->agRows, (size_t)(tot + 1) * sizeof(int));
+  if (!rc) rc = ensure(&d->agOff, (size_t)(tot + 1) * sizeof(long long));
+  if (!rc) rc = ensure(&d->agBuf, (size_t)cap * world * sizeof(double));
+  if (!rc && tot) {
+    rc = (int)cudaMemcpyAsync(d->agRows.p, hr, (size_t)tot * sizeof(int), cudaMemcpyHostToDevice, d->s1);
+    if (!rc) rc = (int)cudaMemcpyAsync(d->agOff.p, ho, (size_t)tot * sizeof(long long), cudaMemcpyHostToDevice, d->s1);
+    if (!rc) rc = (int)cudaStreamSynchronize(d->s1); /* hr / ho are pageable */
+  }
+  free(hr);
+  free(ho);
+  if (rc) snprintf(g_err, sizeof(g_err), "ecpdev_allgather_layout: device allocation / copy failed (%d)", rc);
+  return rc ? -1 : 0;
+}
+/* pack own rows -> in-place ncclAllGather -> scatter the other ranks' rows; stream-ordered behind the last batch.
+ * bytesRecv: bytes this rank received (shards of the others, unpadded). */
+extern "C" int ecpdev_allgather(EcpDev *d, long long *bytesRecv) {
+  CK(cudaSetDevice(d->device));
+  if (!d->comm || !d->agCount || !d->matrix) {
+    snprintf(g_err, sizeof(g_err), "ecpdev_allgather: %s", !d->comm ? "no communicator" : (!d->agCount ? "no shard layout" : "no result matrix yet"));
+    return -1;
+  }
+  const int world = d->commWorld, me = d->commRank, n = d->nAO;
+  double *buf = (double *)d->agBuf.p;
+  const int *rows = (const int *)d->agRows.p;
+  const long long *off = (const long long *)d->agOff.p;
+  const long long cap = d->agCap;
+  const long long nMine = d->agFirst[me + 1] - d->agFirst[me];
+  if (nMine)
+    k_pack_rows<<<(unsigned)nMine, 256, 0, d->s1>>>(d->matrix, n, rows + d->agFirst[me], off + d->agFirst[me], 0, buf + (size_t)me * cap);
+  NCCLCK(g_nccl.allGather(buf + (size_t)me * cap, buf, (size_t)cap, 8 /* ncclFloat64 */, d->comm, d->s1));
+  long long recv = 0;
+  for (int r = 0; r < world; r++) {
+    if (r == me) continue;
+    const long long nr = d->agFirst[r + 1] - d->agFirst[r];
+    if (nr)
+      k_unpack_rows<<<(unsigned)nr, 256, 0, d->s1>>>(d->matrix, n, rows + d->agFirst[r], off + d->agFirst[r], buf + (size_t)r * cap);
+    recv += d->agCount[r] * (long long)sizeof(double);
+  }
+  CK(cudaGetLastError());
+  if (bytesRecv) *bytesRecv = recv;
+  d->matrixKnown = 0; /* rows of other ranks are now non-zero: the next pass clears everything */
   return 0;
 }
 

@@ -135,6 +135,13 @@ int ecpdev_matrix_rows(EcpDev *d, int dir, const int *rows, long long nrows, voi
 int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned /* [nAO] or NULL */,
                               long long *bytes);
 void *ecpdev_matrix_ptr(EcpDev *d);
+/* C-ABI collective of a sharded device-resident result (NCCL bound with dlopen): unique id for the caller to distribute,
+ * communicator from that id (comm == NULL) or adopted from the caller, shard layout of all ranks, the all-gather itself */
+int ecpdev_comm_unique_id(void *id128);
+int ecpdev_comm_init(EcpDev *d, int rank, int world, const void *id128, void *comm);
+void ecpdev_comm_destroy(EcpDev *d);
+int ecpdev_allgather_layout(EcpDev *d, const int *const *rows, const long long *nrows);
+int ecpdev_allgather(EcpDev *d, long long *bytesRecv);
 void ecpdev_bind_thread(EcpDev *d);
 void ecpdev_release_cache(void);
 /* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks; slot = which of

@@ -288,6 +288,24 @@ def test_gather_pack_unpack_rebuilds_the_full_matrix():
         assert_parity(M + M1, ref, "shard union after a gather")
 
 
+def test_fallback_kernels_agree():
+    """k_fallbackW (default: one warp per (triple, l) item, Bessel code per order) and k_fallbackG (LIBECP_B200_FB=group,
+    8-lane groups) evaluate the same integrand values and differ only in the association of the sums inside a level:
+    T equal to ~1e-15 relative, matrices within the parity tolerance of the reference"""
+    for fn, name in ((lambda: synth.cfg3(4), "au4"), (lambda: synth.cfg4("a"), "cfg4a"), (lambda: synth.cfg4("b"), "cfg4b")):
+        def run():
+            with capi.Handle(fn()) as h:
+                rc, M = h.integrals_host()
+                st = h.stats()
+                return rc, M, h.debug_fetch("T", 300000), st["fallback_items"]
+        rc0, base, t0, n0 = _with_env({"LIBECP_B200_FB": "group"}, run)
+        for env in ({}, {"LIBECP_B200_FBMINB": "4"}):
+            rc1, got, t1, n1 = _with_env(env, run)
+            assert rc0 == rc1 == 0 and n0 == n1 and n0 > 0
+            assert_parity(got, load_matrix(name), name)
+            assert np.allclose(t1, t0, rtol=1e-11, atol=1e-14), (name, np.abs(t1 - t0).max())
+
+
 def test_link_variants_are_bit_identical():
     """k_link4 (default for the large classes: Omega slices staged per run of triples that share both atoms, strides
     and loops fixed at compile time) performs the per-element operations of k_link (LIBECP_B200_LINK=global) in the same

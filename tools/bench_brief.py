@@ -24,7 +24,8 @@ for line in sys.stdin:
         p = d["parity"]
         msg += "\n  parity ok=%s max_abs %.2e max_rel %.2e %s" % (p.get("ok"), p.get("max_abs", -1), p.get("max_rel", -1), {k: (round(v, 4) if isinstance(v, float) else v) for k, v in p.items() if k.endswith("_worst") or k in ("block_support_equal", "sample_violations")})
     if d.get("allgather"):
-        msg += "\n  allgather %s" % d["allgather"]
+        msg += "\n  allgather %.2f ms %.0f GB/s per rank; gathered step %.2f ms value %.3e" % (
+            d["allgather"]["ms"], d["allgather"]["GBps_per_rank"], d["gathered"]["ms_per_step"], d["gathered"]["value"])
     if d.get("per_rank"):
         msg += "\n  per_rank %s" % d["per_rank"]
     print(msg)
