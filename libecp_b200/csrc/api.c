@@ -429,24 +429,120 @@ void libecp_b200_comm_free(libECPHandle *h) {
   if (h && h->dev) ecpdev_comm_destroy(h->dev);
 }
 
-int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
-  const int n = h->tab->v.nAO;
-  const double tCall = now_ms();
-  void *dm = NULL;
-  const int rc = libecp_b200_integrals_device(h, &dm, NULL);
-  if (rc < 0 || h->empty) return rc;
-  long long moved = 0;
-  unsigned char *owned = owned_rows(h); /* only the AO rows of the shells this rank owns can be non-zero */
-  const double tA = now_ms();
-  const int rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, owned, &moved);
-  if (getenv("LIBECP_B200_TRACE"))
-    fprintf(stderr, "[libecp_b200] rank %d/%d integrals_host: add_to_host %.1f ms (whole call so far %.1f ms)\n", h->rank, h->world,
-            now_ms() - tA, now_ms() - tCall);
+/* Host consumer (getIntegrals): the pass is cut into `panels` row panels - the rows this rank owns are dealt once more
+ * (libecp_b200_set_shard machinery: panel p of P inside rank r of W owns what rank p * W + r of W * P would) - and run
+ * one after the other; as soon as a panel's pass has returned its rows are final, and a helper thread packs them,
+ * moves them over PCIe on the download stream and adds them into the caller's matrix (src/getIntegrals.c:36-42) while
+ * the next panel computes.  Only the last panel's transfer (1 / panels of the 1.44 GB of config 5) is left as a tail.
+ * Every panel screens all centres again and recomputes their tables (~3 ms per config-5 pass), so few panels. */
+typedef struct {
+  libECPHandle *h;
+  double *I;
+  int rowdim, rank, world, rc;
+  long long moved;
+  pthread_t th;
+} PanelJob;
+static void *panel_download(void *p) {
+  PanelJob *j = p;
+  unsigned char *owned = NULL;
+  if (j->world > 1) {
+    const EcpHostTables *v = &j->h->tab->v;
+    owned = calloc(v->nAO + 1, 1);
+    for (int s = 0; s < v->nrShells; s++)
+      if (ecp_pair_owner(j->h->tab, s, s, j->world) == j->rank)
+        for (int k = 0; k < IJK_DIM(v->shellL[s]); k++) owned[v->shellAO[s] + k] = 1;
+  }
+#ifdef _OPENMP
+  if (g_host_threads > 0) omp_set_num_threads(g_host_threads);
+#endif
+  j->rc = ecpdev_matrix_add_to_host(j->h->dev, j->I, j->rowdim, owned, &j->moved, 1);
   free(owned);
-  h->stats.d2h_bytes += moved;
-  if (rc2) return -rc2;
-  (void)n;
-  return rc;
+  return NULL;
+}
+static int host_panels(const libECPHandle *h) {
+  const char *e = getenv("LIBECP_B200_HOST_PANELS");
+  if (e && atoi(e) > 0) return atoi(e) > 16 ? 16 : atoi(e);
+  /* worth it when the transfer is long compared with a panel's fixed costs: upper triangle above ~256 MB */
+  const double bytes = 4.0 * (double)h->tab->v.nAO * h->tab->v.nAO / h->world;
+  return bytes > 256e6 ? 3 : 1;
+}
+int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
+  const double tCall = now_ms();
+  const int P = (h->empty || !h->dev) ? 1 : host_panels(h);
+  if (P <= 1) {
+    void *dm = NULL;
+    const int rc = libecp_b200_integrals_device(h, &dm, NULL);
+    if (rc < 0 || h->empty) return rc;
+    long long moved = 0;
+    unsigned char *owned = owned_rows(h); /* only the AO rows of the shells this rank owns can be non-zero */
+    const double tA = now_ms();
+    const int rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, owned, &moved, 0);
+    if (getenv("LIBECP_B200_TRACE"))
+      fprintf(stderr, "[libecp_b200] rank %d/%d integrals_host: add_to_host %.1f ms (whole call so far %.1f ms)\n", h->rank, h->world,
+              now_ms() - tA, now_ms() - tCall);
+    free(owned);
+    h->stats.d2h_bytes += moved;
+    if (rc2) return -rc2;
+    return rc;
+  }
+  /* clear the rows of the whole rank once; the panels then accumulate without clearing */
+  unsigned char *owned = owned_rows(h);
+  int rc = ecpdev_matrix_begin(h->dev, owned, (long long)h->world * 1000003LL + h->rank);
+  free(owned);
+  if (rc) return -rc;
+  const int rank0 = h->rank, world0 = h->world;
+  libecp_b200_stats_t tot;
+  memset(&tot, 0, sizeof(tot));
+  PanelJob jobs[16];
+  int result = 0, started = 0;
+  for (int p = 0; p < P; p++) {
+    h->rank = p * world0 + rank0; /* deal % (world0 P) = p world0 + rank0  =>  deal % world0 = rank0: a subset of the rank's rows */
+    h->world = world0 * P;
+    const int r = run_all(h, 1, NULL, NULL);
+    { /* statistics of the call = sum over the panels */
+      const libecp_b200_stats_t *s = &h->stats;
+      long long *a = (long long *)&tot;
+      const long long *c = (const long long *)s;
+      const int nll = (int)((const char *)&s->ms_build - (const char *)s) / (int)sizeof(long long);
+      for (int k = 0; k < nll; k++) a[k] += c[k];
+      tot.tables_h2d_bytes = s->tables_h2d_bytes;
+      tot.nominal_triples = s->nominal_triples; /* every panel walks the same loop domain */
+      double *ad = &tot.ms_build;
+      const double *cd = &s->ms_build;
+      for (int k = 0; k < 9; k++) ad[k] += cd[k];
+    }
+    if (r < 0) {
+      result = r;
+      break;
+    }
+    if (r && !result) result = r;
+    PanelJob *j = &jobs[p];
+    j->h = h;
+    j->I = I;
+    j->rowdim = rowdim;
+    j->rank = h->rank;
+    j->world = h->world;
+    j->rc = 0;
+    j->moved = 0;
+    if (p > 0) pthread_join(jobs[p - 1].th, NULL); /* one download at a time: they share the PCIe link and the host cores */
+    if (pthread_create(&j->th, NULL, panel_download, j)) {
+      panel_download(j);
+      j->th = 0;
+    }
+    started = p + 1;
+  }
+  h->rank = rank0;
+  h->world = world0;
+  for (int p = (started > 1 ? started - 1 : 0); p < started; p++)
+    if (jobs[p].th) pthread_join(jobs[p].th, NULL);
+  h->stats = tot;
+  for (int p = 0; p < started; p++) {
+    h->stats.d2h_bytes += jobs[p].moved;
+    if (jobs[p].rc && result >= 0) result = -jobs[p].rc;
+  }
+  if (getenv("LIBECP_B200_TRACE"))
+    fprintf(stderr, "[libecp_b200] rank %d/%d integrals_host: %d panels, whole call %.1f ms\n", h->rank, h->world, P, now_ms() - tCall);
+  return result;
 }
 
 int getIntegrals(int nrAtoms, double *geometry, int *shellsECP, int *KECP, int *lECP, double *nECP, double *dECP,

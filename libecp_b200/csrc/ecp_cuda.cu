@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
 }
 
 #include "ecp_fallback.cuh"
+#include "ecp_waves.cuh"
 
 /* ---- per triple: everything the element-parallel kernels (link, chi, shift) would otherwise chase through
  * trA/trB -> ssShell/ssASlot -> asAtom/asOmOff/shellK/... with up to five dependent loads PER ELEMENT.  Those kernels
@@ -861,6 +862,7 @@ struct EcpDev {
     Buf prTriple, clsFirst, clsWork, clsElem, clsOutElem, clsPairBase, clsQBase;
   } up[2];
   cudaStream_t s3;
+  cudaStream_t s4; /* D2H of finished row panels while the next panel computes (ecpdev_matrix_add_to_host, async = 1) */
   cudaEvent_t evUp[2];
   cudaEvent_t evDone; /* blocking-sync event: the driving thread sleeps while a batch runs (its core goes to the builder) */
   const EcpBatch *upBatch[2]; /* batch whose arrays sit in the set (NULL: none) */
@@ -892,7 +894,8 @@ struct EcpDev {
   int launchSeq;
   Buf dbgBuf;
   int tails; /* LIBECP_B200_TAILS */
-  int fbWarp; /* 1 (default): k_fallbackW, one warp per item; LIBECP_B200_FB=group: k_fallbackG, 8-lane groups */
+  int fbWaves; /* 1 (default): level waves (ecp_waves.cuh); LIBECP_B200_FB=group: k_fallbackG, persistent 8-lane groups */
+  Buf fbwItems, fbwUnits, fbwQd, fbwSI, fbwSP, fbwSQ, fbwRes, fbwOpenFlag, fbwVals, fbwListA, fbwListB, fbwCtr;
   int fbblock, fbocc, fbminb; /* tuning knobs of the fallback kernel: LIBECP_B200_FBBLOCK threads, _FBOCC blocks per SM cap, _FBMINB */
   int t1block;                /* LIBECP_B200_T1BLOCK = 32/64/96/128 threads per block of the type-1 kernels */
 };
@@ -1004,6 +1007,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   cudaStreamCreateWithFlags(&d->s1, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&d->s2real, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&d->s3, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&d->s4, cudaStreamNonBlocking);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&d->evUp[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&d->evDone, cudaEventDisableTiming | cudaEventBlockingSync);
   d->s2 = d->s2real;
@@ -1033,7 +1037,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     d->fbblock = e ? atoi(e) : 64;
     if (d->fbblock != 32 && d->fbblock != 64 && d->fbblock != 128) d->fbblock = 64;
     e = getenv("LIBECP_B200_FB");
-    d->fbWarp = !(e && !strcmp(e, "group"));
+    d->fbWaves = !(e && !strcmp(e, "group"));
     e = getenv("LIBECP_B200_FBMINB");
     d->fbminb = e ? atoi(e) : 3;
     e = getenv("LIBECP_B200_FBOCC");
@@ -1179,7 +1183,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
 /* scratch buffers (and the result matrix) of a destroyed handle are parked per device and adopted by the next handle
  * created there: a caller that goes through getIntegrals() creates a handle per call, and growing gigabytes of
  * scratch from the driver costs tens to hundreds of milliseconds each time.  libecp_b200_release_cache() frees them. */
-#define ECP_NBUF 72
+#define ECP_NBUF 96
 struct DevCache {
   int valid;
   Buf bufs[ECP_NBUF];
@@ -1195,6 +1199,8 @@ static int collect_bufs(EcpDev *d, Buf **bs) {
   Buf *list[] = {&d->rshX, &d->uspX, &d->omX, &d->F, &d->T, &d->gamma, &d->chi, &d->Q, &d->rshP, &d->sP, &d->blocks,
                  &d->tfail, &d->tflags, &d->items, &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count,
                  &d->t1work, &d->t1rec, &d->trirec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR,
+                 &d->fbwItems, &d->fbwUnits, &d->fbwQd, &d->fbwSI, &d->fbwSP, &d->fbwSQ, &d->fbwRes, &d->fbwOpenFlag, &d->fbwVals,
+                 &d->fbwListA, &d->fbwListB, &d->fbwCtr,
 #define UPSET(i) &d->up[i].asAtom, &d->up[i].asType, &d->up[i].asR, &d->up[i].asOmOff, &d->up[i].ssShell,            \
                  &d->up[i].ssASlot, &d->up[i].ssStart, &d->up[i].ssEnd, &d->up[i].ssFOff, &d->up[i].trA, &d->up[i].trB, \
                  &d->up[i].trOut, &d->up[i].trPair, &d->up[i].prTriple, &d->up[i].clsFirst, &d->up[i].clsWork,        \
@@ -1275,6 +1281,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   cudaStreamDestroy(d->s1);
   cudaStreamDestroy(d->s2real);
   cudaStreamDestroy(d->s3);
+  cudaStreamDestroy(d->s4);
   for (int i = 0; i < 2; i++) cudaEventDestroy(d->evUp[i]);
   cudaEventDestroy(d->evDone);
   free(d);
@@ -1392,9 +1399,12 @@ extern "C" int ecpdev_matrix_rows(EcpDev *d, int dir, const int *rows, long long
 }
 
 extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned,
-                                         long long *bytes) {
+                                         long long *bytes, int async) {
+  /* async = 1: the listed rows are final (their pass has returned) while another pass may be running on the compute
+   * stream - use the download stream and never touch the compute stream (called from a helper host thread) */
   CK(cudaSetDevice(d->device));
-  CK(cudaStreamSynchronize(d->s1));
+  cudaStream_t st = async ? d->s4 : d->s1;
+  if (!async) CK(cudaStreamSynchronize(d->s1));
   const int n = d->nAO;
   const size_t panelBytes = (size_t)24 << 20;
   /* rows this rank owns (all rows when rowOwned == NULL): a sharded rank's partial matrix is zero outside the AO
@@ -1415,7 +1425,7 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   off[nR] = tot;
   const long long panelElems = (long long)(panelBytes / sizeof(double)) > n ? (long long)(panelBytes / sizeof(double)) : n;
   Buf dRows = {NULL, 0}, dOff = {NULL, 0}, dStage[2] = {{NULL, 0}, {NULL, 0}};
-  g_allocStream = d->s1;
+  g_allocStream = st;
   int rc = ensure(&dRows, (size_t)(nR + 1) * sizeof(int));
   if (!rc) rc = ensure(&dOff, (size_t)(nR + 2) * sizeof(long long));
   if (!rc) rc = ensure(&dStage[0], (size_t)panelElems * sizeof(double));
@@ -1436,8 +1446,8 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   cudaEvent_t done[2];
   for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
   if (nR) {
-    CK(cudaMemcpyAsync(dRows.p, rows, (size_t)nR * sizeof(int), cudaMemcpyHostToDevice, d->s1));
-    CK(cudaMemcpyAsync(dOff.p, off, (size_t)(nR + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->s1));
+    CK(cudaMemcpyAsync(dRows.p, rows, (size_t)nR * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dOff.p, off, (size_t)(nR + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   }
   /* panel boundaries in row-list positions */
   int *pb = (int *)malloc((size_t)(nR + 2) * sizeof(int));
@@ -1453,12 +1463,12 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   auto issue = [&](int p) -> cudaError_t {
     const int k0 = pb[p], k1 = pb[p + 1];
     const long long elems = off[k1] - off[k0];
-    k_pack_rows<<<k1 - k0, 256, 0, d->s1>>>(d->matrix, n, (const int *)dRows.p + k0, (const long long *)dOff.p + k0,
+    k_pack_rows<<<k1 - k0, 256, 0, st>>>(d->matrix, n, (const int *)dRows.p + k0, (const long long *)dOff.p + k0,
                                            off[k0], (double *)dStage[p & 1].p);
     moved += elems * (long long)sizeof(double);
-    cudaError_t e = cudaMemcpyAsync(pin[p & 1], dStage[p & 1].p, (size_t)elems * sizeof(double), cudaMemcpyDeviceToHost, d->s1);
+    cudaError_t e = cudaMemcpyAsync(pin[p & 1], dStage[p & 1].p, (size_t)elems * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return e;
-    return cudaEventRecord(done[p & 1], d->s1);
+    return cudaEventRecord(done[p & 1], st);
   };
   const bool trace = getenv("LIBECP_B200_TRACE") != NULL;
   double tWait = 0, tAdd = 0, tStart = omp_get_wtime();
@@ -1497,11 +1507,11 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   (void)tStart;
   for (int k = 0; k < 2; k++) {
     cudaEventDestroy(done[k]);
-    cudaFreeAsync(dStage[k].p, d->s1);
+    cudaFreeAsync(dStage[k].p, st);
     ecpdev_pinned_free(pin[k]);
   }
-  cudaFreeAsync(dRows.p, d->s1);
-  cudaFreeAsync(dOff.p, d->s1);
+  cudaFreeAsync(dRows.p, st);
+  cudaFreeAsync(dOff.p, st);
   free(rows);
   free(off);
   free(pb);
@@ -1634,6 +1644,83 @@ static void launch_type1(EcpDev *d, int lab, const T1Segs &sg, long long listOff
   }
 }
 
+
+/* type-2 large-grid fallback as level waves (ecp_waves.cuh) on stream s1.  The host reads three counters back per wave
+ * (items -> units / states, then open units and value space of the next wave) to size the next launches; the type-1
+ * kernels of the batch are already queued on the other stream and keep the GPU busy meanwhile. */
+static int run_fallback_waves(EcpDev *d, int km, long long *launches) {
+  const DevT &t = d->t;
+  DevB &B = d->b;
+  cudaStream_t s = d->s1;
+  int hc[4];
+  CK(cudaMemcpyAsync(hc, B.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int nItems = hc[0];
+  if (nItems <= 0) return 0;
+  g_allocStream = s;
+  int rc = ensure(&d->fbwItems, (size_t)nItems * sizeof(FbwItem));
+  if (!rc) rc = ensure(&d->fbwCtr, 8 * sizeof(unsigned long long));
+  if (rc) return rc;
+  unsigned long long *ctr = (unsigned long long *)d->fbwCtr.p;
+  CK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s));
+  k_fbw_count<<<nblk(nItems, 128), 128, 0, s>>>(t, B, (FbwItem *)d->fbwItems.p, ctr);
+  unsigned long long hctr[8];
+  CK(cudaMemcpyAsync(hctr, ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const long long nUnits = (long long)hctr[0], nStates = (long long)hctr[1], nQd = (long long)hctr[2];
+  if (nUnits <= 0 || nStates <= 0) return 0;
+  if (nUnits > 0x7fffffffLL) {
+    snprintf(g_err, sizeof(g_err), "fallback: too many units in one batch");
+    return -1;
+  }
+  rc = ensure(&d->fbwUnits, (size_t)nUnits * sizeof(FbwUnit));
+  if (!rc) rc = ensure(&d->fbwQd, (size_t)(nQd + 1) * sizeof(FbwQ));
+  if (!rc) rc = ensure(&d->fbwSI, (size_t)nStates * sizeof(double));
+  if (!rc) rc = ensure(&d->fbwSP, (size_t)nStates * sizeof(double));
+  if (!rc) rc = ensure(&d->fbwSQ, (size_t)nStates * sizeof(double));
+  if (!rc) rc = ensure(&d->fbwRes, (size_t)nStates * sizeof(double));
+  if (!rc) rc = ensure(&d->fbwOpenFlag, (size_t)nStates);
+  if (!rc) rc = ensure(&d->fbwVals, (size_t)nStates * 32 * sizeof(double));
+  if (!rc) rc = ensure(&d->fbwListA, (size_t)nUnits * sizeof(FbwOpen));
+  if (!rc) rc = ensure(&d->fbwListB, (size_t)nUnits * sizeof(FbwOpen));
+  if (rc) return rc;
+  const FbwUnit *units = (const FbwUnit *)d->fbwUnits.p;
+  const FbwQ *qd = (const FbwQ *)d->fbwQd.p;
+  double *sI = (double *)d->fbwSI.p, *sP = (double *)d->fbwSP.p, *sQ = (double *)d->fbwSQ.p, *sRes = (double *)d->fbwRes.p;
+  unsigned char *sOpen = (unsigned char *)d->fbwOpenFlag.p;
+  k_fbw_units<<<nblk(nItems, 128), 128, 0, s>>>(t, B, (const FbwItem *)d->fbwItems.p, (FbwUnit *)d->fbwUnits.p, (FbwQ *)d->fbwQd.p);
+  *launches += 2;
+  FbwOpen *cur = NULL, *nxt = (FbwOpen *)d->fbwListA.p, *other = (FbwOpen *)d->fbwListB.p;
+  long long nOpen = nUnits;
+  for (int lev = 4; lev <= t.largeLevels && nOpen > 0; lev++) {
+    const int S = lev == 4 ? 32 : (1 << lev), slot0 = lev == 4 ? 0 : (1 << lev);
+    const long long nWarps = nOpen * (S >> 5);
+    if (km <= 6)
+      k_fbw_eval<6><<<nblk(nWarps, 4), 128, 0, s>>>(t, B, units, qd, cur, nWarps, S, slot0, (double *)d->fbwVals.p);
+    else
+      k_fbw_eval<10><<<nblk(nWarps, 4), 128, 0, s>>>(t, B, units, qd, cur, nWarps, S, slot0, (double *)d->fbwVals.p);
+    CK(cudaMemsetAsync(ctr + 3, 0, 2 * sizeof(unsigned long long), s));
+    k_fbw_book<<<nblk(nOpen * 8, 128), 128, 0, s>>>(t, units, cur, (int)nOpen, lev, (const double *)d->fbwVals.p, sI, sP, sQ, sRes, sOpen,
+                                                   nxt, ctr, B.counters + 3);
+    *launches += 2;
+    CK(cudaGetLastError());
+    if (lev == t.largeLevels) break;
+    CK(cudaMemcpyAsync(hctr, ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    nOpen = (long long)hctr[3];
+    if (nOpen > 0) {
+      rc = ensure(&d->fbwVals, (size_t)hctr[4] * sizeof(double)); /* the values of the wave just booked are no longer needed */
+      if (rc) return rc;
+    }
+    cur = nxt;
+    FbwOpen *tmp = nxt == (FbwOpen *)d->fbwListA.p ? other : (FbwOpen *)d->fbwListA.p;
+    nxt = tmp;
+  }
+  k_fbw_final<<<nblk(nItems, 4), 128, 0, s>>>(B, (const FbwItem *)d->fbwItems.p, qd, sRes);
+  *launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slot, double *hostBlocks, EcpDevStats *st) {
   CK(cudaSetDevice(d->device));
@@ -1811,37 +1898,35 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   CK(cudaEventRecord(d->ev[2], d->s1));
   if (nWork > 0) {
     {
-      /* persistent warps (k_fallbackW, one item per warp) or 8-lane groups (k_fallbackG, LIBECP_B200_FB=group); Bessel
-       * order bound of the instantiation: max(2 maxLBS, maxLBS + maxLECP - 1) */
+      /* Bessel order bound of the instantiation: max(2 maxLBS, maxLBS + maxLECP - 1) */
       const int km = (2 * d->maxLBS > d->maxLBS + t.maxLECP - 1) ? 2 * d->maxLBS : d->maxLBS + t.maxLECP - 1;
-      const int block = d->fbWarp ? 128 : d->fbblock;
-      void (*kern)(DevT, DevB);
-      size_t smem, smemMax;
-      int slot;
-      if (d->fbWarp) {
-        if (km <= 6 && d->fbminb == 4) { kern = k_fallbackW<6, 4>; smem = smemMax = fbw_smem_bytes<6>(block); slot = 0; }
-        else if (km <= 6) { kern = k_fallbackW<6, 3>; smem = smemMax = fbw_smem_bytes<6>(block); slot = 3; }
-        else { kern = k_fallbackW<10, 2>; smem = smemMax = fbw_smem_bytes<10>(block); slot = 4; }
-      } else if (km <= 6) {
-        smem = fb_smem_bytes<6>(block);
-        smemMax = fb_smem_bytes<6>(128);
-        if (d->fbminb == 4) { kern = k_fallbackG<6, 4>; slot = 0; } else { kern = k_fallbackG<6, 3>; slot = 1; }
-      } else {
-        smem = fb_smem_bytes<10>(block);
-        smemMax = fb_smem_bytes<10>(128);
-        kern = k_fallbackG<10, 2>;
-        slot = 2;
+      if (d->fbWaves) {
+        int rc_ = run_fallback_waves(d, km, &launches);
+        if (rc_) return rc_;
+      } else { /* persistent 8-lane groups */
+        const int block = d->fbblock;
+        void (*kern)(DevT, DevB);
+        size_t smem;
+        int slot;
+        if (km <= 6) {
+          smem = fb_smem_bytes<6>(block);
+          if (d->fbminb == 4) { kern = k_fallbackG<6, 4>; slot = 0; } else { kern = k_fallbackG<6, 3>; slot = 1; }
+        } else {
+          smem = fb_smem_bytes<10>(block);
+          kern = k_fallbackG<10, 2>;
+          slot = 2;
+        }
+        static int occ_[ECP_MAXDEV][3][5] = {{{0}}};
+        int (*occ)[5] = occ_[d->device < ECP_MAXDEV ? d->device : 0];
+        const int bi = block / 32;
+        if (!occ[slot][bi] || d->device >= ECP_MAXDEV) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(km <= 6 ? fb_smem_bytes<6>(128) : fb_smem_bytes<10>(128)));
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[slot][bi], kern, block, smem);
+          if (occ[slot][bi] < 1) occ[slot][bi] = 1;
+        }
+        const int per = (d->fbocc > 0 && d->fbocc < occ[slot][bi]) ? d->fbocc : occ[slot][bi];
+        kern<<<d->nSM * per, block, smem, d->s1>>>(t, B);
       }
-      static int occ_[ECP_MAXDEV][2][5][5] = {{{{0}}}};
-      int (*occ)[5] = occ_[d->device < ECP_MAXDEV ? d->device : 0][d->fbWarp];
-      const int bi = block / 32;
-      if (!occ[slot][bi] || d->device >= ECP_MAXDEV) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[slot][bi], kern, block, smem);
-        if (occ[slot][bi] < 1) occ[slot][bi] = 1;
-      }
-      const int per = (d->fbocc > 0 && d->fbocc < occ[slot][bi]) ? d->fbocc : occ[slot][bi];
-      kern<<<d->nSM * per, block, smem, d->s1>>>(t, B);
     }
     launches++;
   }

@@ -133,7 +133,7 @@ int ecpdev_matrix_download(EcpDev *d, double *host /* nAO*nAO */);
 /* pack (dir 0) / scatter (dir 1) the upper-triangle parts of the listed rows between the matrix and a device buffer */
 int ecpdev_matrix_rows(EcpDev *d, int dir, const int *rows, long long nrows, void *devBuf, long long cap, long long *elems);
 int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned /* [nAO] or NULL */,
-                              long long *bytes);
+                              long long *bytes, int async /* 1: download stream only, rows are final */);
 void *ecpdev_matrix_ptr(EcpDev *d);
 /* C-ABI collective of a sharded device-resident result (NCCL bound with dlopen): unique id for the caller to distribute,
  * communicator from that id (comm == NULL) or adopted from the caller, shard layout of all ranks, the all-gather itself */

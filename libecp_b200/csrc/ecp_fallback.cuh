@@ -306,238 +306,4 @@ __global__ void __launch_bounds__(128, MINB) k_fallbackG(DevT t, DevB b) {
 }
 
 
-/* ------------------------------------------------------------------------------------------------
- * k_fallbackW: ONE WARP PER (triple, l) ITEM (default; LIBECP_B200_FB=group keeps k_fallbackG).
- *
- * ncu on k_fallbackG (profiles/r2): 11-17 of 32 lanes active in the Bessel code, 23 % of the executed instructions
- * FP64, 17 % of the stall samples waiting for instructions (50 KB of code walked by four unrelated state machines per
- * warp).  A large-grid quadrature needs ~130 points per primitive pair, so the whole warp can work on one item:
- *   - slots 0..31 of the level-major grid are exactly the centre and the levels 1..4 (1 + 2 + 4 + 8 + 16 points): the first
- *     chunk evaluates them all, the owner lanes run the four PSM92 tests on the per-level sums;
- *   - from level 5 on a chunk takes the next 32 points of the level that can pass the exponent gate (closed-form
- *     candidate runs, lg_level) - no lane waits for a point outside the live range;
- *   - all lanes share (la + l, lb + l): the Bessel code is instantiated per order and selected by a warp-uniform switch
- *     (k_fallbackG ran every item at the highest order of the handle, with the surplus orders predicated off);
- *   - the integrands of the item's failed quadratures go through a [quadrature][lane] tile in shared memory; lane j
- *     owns quadrature j (up to 32 per pass) and adds its 32 values pair by pair in slot order - within the first five
- *     levels that is the reference's own association (T = left + right, I += T; src/gc_integrators.c:58-72).
- * Integrand values are those of k_fallbackG (same factors, same association); primitive pairs in reference order.
- */
-#define FBW_NQ 32
-template <int KO>
-struct FbwCfg {
-  static constexpr int RS = 3 * (KO + 1);                 /* row: r^0..r^KO, Ka[0..KO], Kb[0..KO]; odd for KO even */
-  static constexpr int WARP = 32 * RS + 32 * 33 + FBW_NQ; /* doubles per warp: rows, tile, 2 x 32 ints */
-};
-template <int KO>
-static size_t fbw_smem_bytes(int block) {
-  return (size_t)(block / 32) * FbwCfg<KO>::WARP * sizeof(double);
-}
-template <int K>
-__device__ __noinline__ void fbw_bessel(const double *__restrict__ tabT, int stride, const double *__restrict__ Cj, double z,
-                                        double *dst) {
-  double Kv[K + 1];
-  ecp_bessel<K>(tabT, stride, Cj, K, z, Kv);
-#pragma unroll
-  for (int i = 0; i <= K; i++) dst[i] = Kv[i];
-}
-template <int KO>
-__device__ __forceinline__ void fbw_bessel_sel(const DevT &t, int lmax, double z, double *dst) {
-  switch (lmax) { /* warp-uniform */
-    case 0: fbw_bessel<0>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-    case 1: fbw_bessel<1>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-    case 2: fbw_bessel<2>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-    case 3: fbw_bessel<3>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-    case 4: fbw_bessel<4>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-    case 5: fbw_bessel<5>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-    case 6: fbw_bessel<6>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-    default:
-      if (KO > 6) {
-        switch (lmax) {
-          case 7: fbw_bessel<(KO > 6 ? 7 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-          case 8: fbw_bessel<(KO > 6 ? 8 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-          case 9: fbw_bessel<(KO > 6 ? 9 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-          default: fbw_bessel<(KO > 6 ? 10 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
-        }
-      }
-      break;
-  }
-}
-
-template <int KO, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_fallbackW(DevT t, DevB b) {
-  using Cfg = FbwCfg<KO>;
-  constexpr int RS = Cfg::RS;
-  constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) double fb_smem[];
-  const int lane = threadIdx.x & 31;
-  double *wsm = fb_smem + (size_t)(threadIdx.x >> 5) * Cfg::WARP;
-  double *myrow = wsm + lane * RS;
-  double *tile = wsm + 32 * RS; /* [quadrature][33] */
-  int *qK = (int *)(tile + 32 * 33), *qQ = qK + FBW_NQ;
-  const int nItems = b.counters[0];
-  for (;;) {
-    int it = 0;
-    if (lane == 0) it = atomicAdd(&b.counters[1], 1);
-    it = __shfl_sync(FULL, it, 0);
-    if (it >= nItems) break;
-    /* ---- item (warp-uniform) ---- */
-    const int item = b.items[it], tri = item >> 3, l = item & 7;
-    const int cl = find_class_i(b.clsFirst, t.nClasses, tri);
-    const int la = t.clsLa[cl], lb = t.clsLb[cl], laC = la + l, lbC = lb + l, lab = la + lb;
-    const int k0 = t.clsQlOff[cl * (ECP_MAX_LECP + 1) + l], k1 = t.clsQlOff[cl * (ECP_MAX_LECP + 1) + l + 1];
-    const long long tOff = tri_T_off(t, b, cl, tri);
-    const int *ql = t.qlist + t.clsQOff[cl];
-    const int ssa = b.trA[tri], ssb = b.trB[tri];
-    const int sha = b.ssShell[ssa], shb = b.ssShell[ssb];
-    const int asa = b.ssASlot[ssa], asb = b.ssASlot[ssb];
-    const double dAC = b.asR[4 * asa + 3], dBC = b.asR[4 * asb + 3];
-    const int type = b.asType[asa];
-    int g0 = t.typeGaussOff[type], g1 = t.typeGaussOff[type + 1];
-    /* Gaussians of channel l form one run of the type's list (src/ecp.c:47-57 tests and skips the others) */
-    while (g0 < g1 && t.gaussL[g0] != l) g0++;
-    while (g1 > g0 && t.gaussL[g1 - 1] != l) g1--;
-    const int Na = t.shellK[sha], Nb = t.shellK[shb];
-    const double *za = t.primA + t.shellPrim[sha], *ca = t.primD + t.shellPrim[sha];
-    const double *zb = t.primA + t.shellPrim[shb], *cb = t.primD + t.shellPrim[shb];
-    int nf = 0; /* failed quadratures of the item */
-    for (int base = k0; base < k1; base += 32) {
-      const int k = base + lane;
-      nf += __popc(__ballot_sync(FULL, k < k1 && b.tfail[tOff + k]));
-    }
-    bool itemFailed = false;
-    for (int pass = 0; FBW_NQ * pass < nf; pass++) {
-      /* the failed quadratures with rank [32 pass, 32 pass + 32) go to qK / qQ */
-      const int lo = FBW_NQ * pass;
-      int seen = 0;
-      __syncwarp();
-      for (int base = k0; base < k1; base += 32) {
-        const int k = base + lane;
-        const bool f = k < k1 && b.tfail[tOff + k];
-        const unsigned m = __ballot_sync(FULL, f);
-        if (f) {
-          const int rank = seen + __popc(m & ((1u << lane) - 1)) - lo;
-          if (rank >= 0 && rank < FBW_NQ) {
-            qK[rank] = k;
-            qQ[rank] = ql[k];
-          }
-        }
-        seen += __popc(m);
-      }
-      __syncwarp();
-      const int nq = nf - lo < FBW_NQ ? nf - lo : FBW_NQ;
-      const bool owner = lane < nq;
-      double Acc = 0.0;
-      for (int pa = 0; pa < Na; pa++)
-        for (int pb = 0; pb < Nb; pb++) { /* primitive pairs in the reference's order (src/type2.c:452-468) */
-          const double zA = za[pa], zB = zb[pb];
-          const double s1 = 2.0 * zA * dAC, s2 = 2.0 * zB * dBC, Cc = ca[pa] * cb[pb];
-          const double zp = zA + zB;
-          double i1, i2;
-          ecp_fm06_map(zp, (zA * dAC + zB * dBC) / zp, &i1, &i2);
-          /* exponent -zA (dAC - r)^2 - zB (dBC - r)^2 = a r^2 + bq r + c0: original indices that can pass the gate */
-          const LgRange lr = lg_live_range(t.large_xo, t.largeOrder, -zp, 2.0 * (zA * dAC + zB * dBC),
-                                           -(zA * dAC * dAC + zB * dBC * dBC) - t.lnAcc2, i1, i2);
-          double I = 0.0, P = 0.0, Qv = 0.0;
-          bool open = owner;
-          int lev = 4, n = 31; /* level of the chunk being accumulated (4: the first chunk, levels 0..4); points before the next */
-          LgLevel lv = {0, 0, 0, 0};
-          int ks = 0;
-          for (;;) {
-            /* ---- one chunk: every lane tabulates one slot (src/type2.c:471-495) ---- */
-            const int slot = (lev == 4) ? lane : lg_slot(lv, lev, 32 * ks + lane);
-            double G = 0.0;
-            bool live = false;
-            const double r = i1 * t.large_x[slot] + i2; /* src/gc_integrators.c:326-329 */
-            if (slot != 1) {
-              const double d1 = dAC - r, d2 = dBC - r;
-              const double e = -zA * d1 * d1 - zB * d2 * d2;
-              live = e >= t.lnAcc2;
-              if (slot == 0 && r > dAC && r > dBC && e < t.lnAcc2) atomicAdd(&b.counters[6], 1);
-              if (live) {
-                const double U = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, g0, g1, l, r);
-                G = (t.large_w[slot] * i1) * ((Cc * U) * exp(e));
-                double rn = 1.0;
-                for (int i = 0; i <= lab; i++) {
-                  myrow[i] = rn;
-                  rn = r * rn;
-                }
-              }
-            }
-            if (__any_sync(FULL, live)) { /* warp-uniform order selection; dead lanes stay out */
-              if (live) {
-                fbw_bessel_sel<KO>(t, laC, s1 * r, myrow + (KO + 1));
-                fbw_bessel_sel<KO>(t, lbC, s2 * r, myrow + 2 * (KO + 1));
-              }
-            }
-            /* ---- integrands of the pass's quadratures at my point -> tile[quadrature][lane] ---- */
-            __syncwarp();
-            for (int j = 0; j < nq; j++) {
-              const int qq = qQ[j];
-              const int l1 = (qq >> 4) & 15, l2 = (qq >> 8) & 15, l3 = (qq >> 12) & 15;
-              /* c_a c_b U r^N K_l1 K_l2 exp(e), times the mapped weight (src/type2.c:403-405) */
-              tile[j * 33 + lane] = live ? G * (myrow[l3] * myrow[(KO + 1) + l1] * myrow[2 * (KO + 1) + l2]) : 0.0;
-            }
-            __syncwarp();
-            /* ---- owner lanes: PSM92 bookkeeping (src/gc_integrators.c:49-83) ---- */
-            bool levelDone = true;
-            if (lev == 4) {
-              if (owner) {
-                const double *v = tile + lane * 33;
-                double hitI = 0.0;
-                int hitN = 0;
-                I = v[0]; /* centre (slot 1 is the pad) */
-                P = I;
-                int off = 2, np = 1;
-#pragma unroll
-                for (int lvl = 1; lvl <= 4; lvl++) { /* q = 2p; p = 2I; I += level; test  (:56-57, :73-83) */
-                  Qv = 2 * P;
-                  P = 2 * I;
-                  for (int i = 0; i < (1 << lvl); i += 2) I += v[off + i] + v[off + i + 1];
-                  off += 1 << lvl;
-                  np = 2 * np + 1;
-                  if (open && ecp_psm92_test(np, t.tolerance, I, P, Qv)) {
-                    hitI = I;
-                    hitN = np;
-                    open = false;
-                  }
-                }
-                if (hitN) Acc += 16 * hitI / (3 * (hitN + 1.0));
-              }
-            } else {
-              if (owner) {
-                const double *v = tile + lane * 33;
-                if (ks == 0) {
-                  Qv = 2 * P;
-                  P = 2 * I;
-                }
-                for (int i = 0; i < 32; i += 2) I += v[i] + v[i + 1];
-              }
-              levelDone = 32 * ks + 32 >= lv.nLive;
-              if (levelDone && owner && open && ecp_psm92_test(2 * n + 1, t.tolerance, I, P, Qv)) {
-                Acc += 16 * I / (3 * (2 * n + 2.0));
-                open = false;
-              }
-            }
-            if (levelDone) {
-              if (lev > 4) n = 2 * n + 1;
-              if (!__any_sync(FULL, open)) break; /* every quadrature of the pass converged for this pair */
-              lev++;
-              ks = 0;
-              if (lev > t.largeLevels) {
-                itemFailed = true; /* large grid did not converge: rc 2 (src/libecp.h:26) */
-                break;
-              }
-              lv = lg_level(t.largeSlots, t.largeOrder, lr, lev);
-            } else {
-              ks++;
-            }
-          }
-        }
-      if (owner) b.T[tOff + qK[lane]] = Acc; /* T += grid->I over the pairs (src/type2.c:513) */
-    }
-    if (itemFailed && lane == 0) atomicExch(&b.counters[3], 2);
-  }
-}
-
 #endif

@@ -243,6 +243,34 @@ def test_launch_structure_does_not_change_results():
         assert np.allclose(got, base, rtol=1e-13, atol=1e-15), env
 
 
+def test_host_consumer_in_row_panels():
+    """libecp_b200_integrals_host cuts its pass into row panels whose download and host += overlap the next panel's
+    compute (LIBECP_B200_HOST_PANELS; default 3 for large matrices, 1 here): same matrix, also for a sharded handle,
+    and += semantics into a pre-filled caller matrix"""
+    for s, name in ((synth.cfg3(4), "au4"), (synth.cfg5(40), None)):
+        base = _with_env({"LIBECP_B200_HOST_PANELS": "1"}, lambda: capi.get_integrals(s))
+        if name:
+            assert_parity(base, load_matrix(name), name)
+        for P in ("2", "3", "5"):
+            got = _with_env({"LIBECP_B200_HOST_PANELS": P}, lambda: capi.get_integrals(s))
+            assert np.allclose(got, base, rtol=1e-13, atol=1e-15), (name, P)
+            assert np.all(np.tril(got, -1) == 0.0)
+
+        def sharded():
+            acc = np.zeros_like(base)
+            with capi.Handle(s) as h:
+                for rank in range(2):
+                    h.set_shard(rank, 2)
+                    rc, part = h.integrals_host()
+                    assert rc == 0 and not np.any((part != 0) & (acc != 0))
+                    acc += part
+                st = h.stats()
+            return acc, st
+        got, st = _with_env({"LIBECP_B200_HOST_PANELS": "3"}, sharded)
+        assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
+        assert st["batches"] >= 3
+
+
 def test_handles_in_sequence_reuse_parked_buffers():
     """libECP_free parks the device scratch for the next handle: shapes of different size in sequence, then an
     explicit release, still give the reference's matrices"""
@@ -289,21 +317,23 @@ def test_gather_pack_unpack_rebuilds_the_full_matrix():
 
 
 def test_fallback_kernels_agree():
-    """k_fallbackW (default: one warp per (triple, l) item, Bessel code per order) and k_fallbackG (LIBECP_B200_FB=group,
-    8-lane groups) evaluate the same integrand values and differ only in the association of the sums inside a level:
-    T equal to ~1e-15 relative, matrices within the parity tolerance of the reference"""
-    for fn, name in ((lambda: synth.cfg3(4), "au4"), (lambda: synth.cfg4("a"), "cfg4a"), (lambda: synth.cfg4("b"), "cfg4b")):
+    """the level-wave fallback (default, ecp_waves.cuh) and the persistent 8-lane kernel k_fallbackG (LIBECP_B200_FB=group)
+    evaluate the same integrand values and differ only in the association of the sums inside a level: T equal to
+    ~1e-15 relative, matrices within the parity tolerance of the reference, same items, same return code"""
+    for fn, name in ((lambda: synth.cfg3(4), "au4"), (lambda: synth.cfg4("a"), "cfg4a"), (lambda: synth.cfg4("b"), "cfg4b"),
+                     (lambda: synth.cfg5(24), None)):
         def run():
             with capi.Handle(fn()) as h:
                 rc, M = h.integrals_host()
                 st = h.stats()
                 return rc, M, h.debug_fetch("T", 300000), st["fallback_items"]
         rc0, base, t0, n0 = _with_env({"LIBECP_B200_FB": "group"}, run)
-        for env in ({}, {"LIBECP_B200_FBMINB": "4"}):
-            rc1, got, t1, n1 = _with_env(env, run)
-            assert rc0 == rc1 == 0 and n0 == n1 and n0 > 0
+        rc1, got, t1, n1 = run()
+        assert rc0 == rc1 == 0 and n0 == n1 and n0 > 0
+        if name:
             assert_parity(got, load_matrix(name), name)
-            assert np.allclose(t1, t0, rtol=1e-11, atol=1e-14), (name, np.abs(t1 - t0).max())
+        assert np.allclose(got, base, rtol=1e-12, atol=1e-14), name
+        assert np.allclose(t1, t0, rtol=1e-11, atol=1e-14), (name, np.abs(t1 - t0).max())
 
 
 def test_link_variants_are_bit_identical():
