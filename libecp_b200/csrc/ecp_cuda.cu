@@ -244,12 +244,11 @@ __global__ void __launch_bounds__(ECP_SMALL_SLOTS, (LMAX <= 6 ? 2 : 1)) k_Ftab(D
   }
 }
 
-/* Experimental variant (OFF by default; LIBECP_B200_FTAB=compact): a shell's window covers ~30 % of the grid, so 70 % of
- * k_Ftab's threads only write zeros and every warp (32 consecutive level-major slots span the whole radial range) keeps
- * a few live lanes.  Here the F rows are cleared by one memset and a block of 128 threads walks the ORIGINAL indices
- * of the window [start, end) only, writing each point to its slot: the same arithmetic per point (F is bit-identical),
- * about a third of the warps.  STATUS: written after the round-1 GPU budget was spent - compiles, never run; opt-in
- * test -k ftab_compact, A/B with tools/ab_kernels.py cfg3 LIBECP_B200_FTAB=-,compact. */
+/* Window-only variant (default since round 2; LIBECP_B200_FTAB=full keeps k_Ftab): a shell's window covers ~30 % of the
+ * grid, so 70 % of k_Ftab's threads only write zeros and every warp (32 consecutive level-major slots span the whole
+ * radial range) keeps a few live lanes.  Here the F rows are cleared by one memset and a block of 128 threads walks the
+ * ORIGINAL indices of the window [start, end) only, writing each point to its slot: the same arithmetic per point (F is
+ * bit-identical, test_ftab_variants_are_bit_identical), about a third of the warps; 3.03 -> 2.64 ms per config-5 pass. */
 template <int LMAX>
 __global__ void __launch_bounds__(128) k_Ftab2(DevT t, DevB b) {
   const int ss = blockIdx.x;
@@ -303,8 +302,15 @@ __device__ __forceinline__ FastQ fast_load(const DevT &t, const DevB &b, long lo
   const int c = find_class(b.clsWork, t.nClasses, w);
   const int nq = t.clsNq[c];
   const long long idx = w - b.clsWork[c];
-  f.tri = b.clsFirst[c] + (int)(idx / nq);
-  const int k = (int)(idx % nq);
+  int k;
+  if (idx < 0x7fffffffLL) { /* (almost always) a 32-bit division instead of two 64-bit ones */
+    const unsigned u = (unsigned)idx, tl = u / (unsigned)nq;
+    f.tri = b.clsFirst[c] + (int)tl;
+    k = (int)(u - tl * (unsigned)nq);
+  } else {
+    f.tri = b.clsFirst[c] + (int)(idx / nq);
+    k = (int)(idx % nq);
+  }
   const int q = t.qlist[t.clsQOff[c] + k];
   const int l1 = (q >> 4) & 15, l2 = (q >> 8) & 15, l3 = (q >> 12) & 15;
   f.l = q & 15;
@@ -716,7 +722,16 @@ __global__ void k_t1prep(DevT t, DevB b) {
   ecp_sphcoord(Px, Py, Pz, &r, &th, &ph);
   const int lab = t.shellL[sha] + t.shellL[shb];
   const long long qoff = pair_Q_off(t, b, find_class(b.clsPairBase, t.nClasses, pr), pr);
-  ecp_rsh(lab, th, ph, t.fac, t.dfac, b.rshP + qoff);
+  switch (lab) { /* pairs are class-sorted: (almost) uniform over a warp */
+    case 0: ecp_rsh_t<0>(th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+    case 1: ecp_rsh_t<1>(th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+    case 2: ecp_rsh_t<2>(th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+    case 3: ecp_rsh_t<3>(th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+    case 4: ecp_rsh_t<4>(th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+    case 5: ecp_rsh_t<5>(th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+    case 6: ecp_rsh_t<6>(th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+    default: ecp_rsh(lab, th, ph, t.fac, t.dfac, b.rshP + qoff); break;
+  }
   b.sP[pr] = r;
   const double dAC = rA[3], dBC = rB[3];
   T1Rec rec;
@@ -744,7 +759,10 @@ __global__ void k_t1prep(DevT t, DevB b) {
  * by the 8 lanes of the triple into shared memory, and every element is one short dot product
  *     chi[i][j] = sum_{l,m} poly2sph[p][(l,m)] R[N][(l,m)].
  * The multiply-adds per triple drop from  pairs x elements x (N+1)(N+2)/2  to  (pairs + elements) x (N+1)(N+2)/2
- * (p-p shells of the TZ sets have 16 pairs).  Same products as the reference, associated over the pairs first. */
+ * (p-p shells of the TZ sets have 16 pairs).  Same products as the reference, associated over the pairs first.
+ * Measured and rejected in round 2 (profiles/r2/README.md): a class-uniform block version with the index maps and the
+ * poly2sph rows staged in shared memory - its per-block tables cost more than the index decoding they replace
+ * (0.19 -> 0.26 / 0.65 ms on Au20 with 8 / 128 triples per block, 8.2 -> 19.0 / 15.5 ms per config-5 pass). */
 __device__ __forceinline__ int chi_roff(int N, int l) { /* position of (l, m = 0) of level N in the packed R */
   return N * (N + 1) * (N + 2) / 6 + l * (l - 1) / 2;
 }
@@ -882,8 +900,9 @@ struct EcpDev {
   long long tableBytes, batchH2D;
   int hClsLa[ECP_MAX_CLASSES], hClsLb[ECP_MAX_CLASSES], hClsL[ECP_MAX_CLASSES], hClsNq[ECP_MAX_CLASSES];
   Buf fastSurv;
-  int ftabCompact; /* LIBECP_B200_FTAB=compact: experimental window-only F tabulation (k_Ftab2) */
-  int shiftFused; /* LIBECP_B200_SHIFT=fused: experimental single shift of 4 pi chi + 16 pi^2 gamma in matrix-only runs */
+  int ftabCompact; /* 1 (default): k_Ftab2, only the window of a shell slot is tabulated; LIBECP_B200_FTAB=full: k_Ftab */
+  int shift2, shift2Attr; /* 1 (default): k_shift2, both passes in one kernel; LIBECP_B200_SHIFT=two: k_shiftJ + k_shiftI */
+  int hShTerms[ECP_MAX_LBS + 1]; /* binomial-shift terms per shell angular momentum */
   int linkMode; /* LIBECP_B200_LINK: 4 (default) specialised shared-memory kernel k_link4 for the large classes; global = k_link
                  * everywhere */
   int linkTpb;  /* LIBECP_B200_LINKTPB: consecutive triples per block of k_link4 (0 = sized to the class) */
@@ -1024,9 +1043,9 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
         d->linkTpb = tp ? atoi(tp) : 0;
       }
       lk = getenv("LIBECP_B200_SHIFT");
-      d->shiftFused = lk && !strcmp(lk, "fused");
+      d->shift2 = !(lk && !strcmp(lk, "two"));
       lk = getenv("LIBECP_B200_FTAB");
-      d->ftabCompact = lk && !strcmp(lk, "compact");
+      d->ftabCompact = !(lk && !strcmp(lk, "full"));
     }
     if (d->fastLim < 1) d->fastLim = 1;
     e = getenv("LIBECP_B200_FASTUNROLL");
@@ -1166,6 +1185,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   d->maxQPerL = h->maxQPerL;
   d->nAO = h->nAO;
   d->maxLBS = h->maxLBS;
+  for (int l = 0; l <= h->maxLBS; l++)
+    d->hShTerms[l] = h->shTermOff[l * h->shOffStride + (l + 1) * (l + 2) / 2] - h->shTermOff[l * h->shOffStride];
   adopt_cached(d);
   for (int i = 0; i < d->ntab; i++)
     if (!d->tab[i].p) {
@@ -1659,14 +1680,24 @@ static int run_fallback_waves(EcpDev *d, int km, long long *launches) {
   if (nItems <= 0) return 0;
   g_allocStream = s;
   int rc = ensure(&d->fbwItems, (size_t)nItems * sizeof(FbwItem));
-  if (!rc) rc = ensure(&d->fbwCtr, 8 * sizeof(unsigned long long));
+  if (!rc) rc = ensure(&d->fbwCtr, (FBW_CTR + FBW_NBUCKET) * (sizeof(unsigned long long) + sizeof(int)));
   if (rc) return rc;
   unsigned long long *ctr = (unsigned long long *)d->fbwCtr.p;
-  CK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s));
+  int *bucketOff = (int *)(ctr + FBW_CTR + FBW_NBUCKET);
+  CK(cudaMemsetAsync(ctr, 0, (FBW_CTR + FBW_NBUCKET) * sizeof(unsigned long long), s));
   k_fbw_count<<<nblk(nItems, 128), 128, 0, s>>>(t, B, (FbwItem *)d->fbwItems.p, ctr);
-  unsigned long long hctr[8];
+  unsigned long long hctr[FBW_CTR + FBW_NBUCKET];
   CK(cudaMemcpyAsync(hctr, ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  {
+    int hoff[FBW_NBUCKET], acc = 0;
+    for (int k = 0; k < FBW_NBUCKET; k++) {
+      hoff[k] = acc;
+      acc += (int)hctr[FBW_CTR + k];
+    }
+    CK(cudaMemcpyAsync(bucketOff, hoff, sizeof(hoff), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s)); /* hoff is on the stack */
+  }
   const long long nUnits = (long long)hctr[0], nStates = (long long)hctr[1], nQd = (long long)hctr[2];
   if (nUnits <= 0 || nStates <= 0) return 0;
   if (nUnits > 0x7fffffffLL) {
@@ -1688,7 +1719,7 @@ static int run_fallback_waves(EcpDev *d, int km, long long *launches) {
   const FbwQ *qd = (const FbwQ *)d->fbwQd.p;
   double *sI = (double *)d->fbwSI.p, *sP = (double *)d->fbwSP.p, *sQ = (double *)d->fbwSQ.p, *sRes = (double *)d->fbwRes.p;
   unsigned char *sOpen = (unsigned char *)d->fbwOpenFlag.p;
-  k_fbw_units<<<nblk(nItems, 128), 128, 0, s>>>(t, B, (const FbwItem *)d->fbwItems.p, (FbwUnit *)d->fbwUnits.p, (FbwQ *)d->fbwQd.p);
+  k_fbw_units<<<nblk(nItems, 128), 128, 0, s>>>(t, B, (const FbwItem *)d->fbwItems.p, bucketOff, (FbwUnit *)d->fbwUnits.p, (FbwQ *)d->fbwQd.p);
   *launches += 2;
   FbwOpen *cur = NULL, *nxt = (FbwOpen *)d->fbwListA.p, *other = (FbwOpen *)d->fbwListB.p;
   long long nOpen = nUnits;
@@ -1705,7 +1736,7 @@ static int run_fallback_waves(EcpDev *d, int km, long long *launches) {
     *launches += 2;
     CK(cudaGetLastError());
     if (lev == t.largeLevels) break;
-    CK(cudaMemcpyAsync(hctr, ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hctr, ctr, FBW_CTR * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     nOpen = (long long)hctr[3];
     if (nOpen > 0) {
@@ -1822,7 +1853,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
   k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
   k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
-  if (d->ftabCompact) { /* experimental, off by default (see k_Ftab2) */
+  if (d->ftabCompact) { /* window-only tabulation into a cleared table (k_Ftab2) */
     CK(cudaMemsetAsync(B.F, 0, (size_t)h->fRows * ECP_SMALL_SLOTS * sizeof(double), d->s1));
     if (t.maxLECP - 1 + d->maxLBS <= 6)
       k_Ftab2<6><<<h->nSSlots, 128, 0, d->s1>>>(t, B);
@@ -1968,6 +1999,34 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   }
   CK(cudaEventRecord(d->ev[4], d->s1));
   CK(cudaStreamWaitEvent(d->s1, d->ev[8], 0));
+  if (d->shift2) { /* both shift passes in one kernel, blocks of consecutive triples of one class (k_shift2) */
+    int clsBlk[2 * ECP_MAX_CLASSES + 2]; /* first block of every class, then its chunks per block */
+    size_t smemMax = 0;
+    clsBlk[0] = 0;
+    for (int c = 0; c < nc; c++) {
+      const int la = d->hClsLa[c], lb = d->hClsLb[c];
+      const int ntri = h->clsFirst[c + 1] - h->clsFirst[c];
+      const int tpb = shift2_tpb(la, lb);
+      /* chunks per block: the per-block tables are paid once per block, but a small class must still fill the device */
+      long long ch = ntri / ((long long)tpb * d->nSM * 4);
+      ch = ch < 1 ? 1 : (ch > SHIFT2_CH ? SHIFT2_CH : ch);
+      clsBlk[nc + 1 + c] = (int)ch;
+      clsBlk[c + 1] = clsBlk[c] + (int)((ntri + tpb * ch - 1) / (tpb * ch));
+      if (ntri > 0) {
+        Shift2Layout L;
+        const size_t sm = shift2_smem(la, lb, d->hShTerms[la], d->hShTerms[lb], tpb, &L);
+        if (sm > smemMax) smemMax = sm;
+      }
+    }
+    int rc_ = ensure(&d->clsJ, (2 * nc + 2) * sizeof(int));
+    if (rc_) return rc_;
+    CK(cudaMemcpyAsync(d->clsJ.p, clsBlk, (2 * nc + 1) * sizeof(int), cudaMemcpyHostToDevice, d->s1));
+    if (smemMax > 48 * 1024 && !d->shift2Attr) {
+      CK(cudaFuncSetAttribute(k_shift2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      d->shift2Attr = 1;
+    }
+    if (clsBlk[nc] > 0) k_shift2<<<clsBlk[nc], 128, smemMax, d->s1>>>(t, B, (const int *)d->clsJ.p, flags);
+  } else
   { /* binomial shift in two passes (ecp_shift.cuh); J[type][c1][q] per triple goes through a scratch buffer */
     long long clsJ[ECP_MAX_CLASSES + 1];
     clsJ[0] = 0;
@@ -1981,10 +2040,9 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
     rc_ = ensure(&d->Jbuf, (size_t)(2 * clsJ[nc] + 1) * sizeof(double));
     if (rc_) return rc_;
     CK(cudaMemcpyAsync(d->clsJ.p, clsJ, (nc + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->s1));
-    const int fuse = d->shiftFused && !(flags & 2); /* experimental, off by default; never when blocks are wanted */
-    k_shiftJ<<<nblk(clsJ[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, clsJ[nc], (double *)d->Jbuf.p, fuse);
+    k_shiftJ<<<nblk(clsJ[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, clsJ[nc], (double *)d->Jbuf.p);
     k_shiftI<<<nblk(h->clsOutElem[nc], 128), 128, 0, d->s1>>>(t, B, (const long long *)d->clsJ.p, h->clsOutElem[nc],
-                                                              (const double *)d->Jbuf.p, flags, fuse);
+                                                              (const double *)d->Jbuf.p, flags);
   }
   launches += 2;
   CK(cudaEventRecord(d->ev[5], d->s1));

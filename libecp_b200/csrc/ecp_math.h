@@ -299,6 +299,85 @@ ECP_HD void ecp_rsh(int lmax, double theta, double phi, const double *__restrict
 #undef ECP_RS
 }
 
+/* The same with the order bound fixed at compile time: every loop unrolls and the work arrays stay in registers (the
+ * run-time version indexes them dynamically, which puts them into local memory on the device - ncu on k_t1prep showed
+ * 2.5 warps per issue throttled by local-memory traffic).  Identical operations in identical order: identical values. */
+template <int LM>
+ECP_HD void ecp_rsh_t(double theta, double phi, const double *__restrict__ fac, const double *__restrict__ dfac,
+                      double *__restrict__ out) {
+  double P[(LM + 1) * (LM + 1)];
+  double s[LM + 2], c[LM + 2];
+#define ECP_RS(l, m) ((l) * (l) + (l) + (m))
+#pragma unroll
+  for (int i = 0; i < (LM + 1) * (LM + 1); i++) P[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < LM + 2; i++) s[i] = c[i] = 0.0;
+  const double x = cos(theta);
+  if (1.0 == x) {
+#pragma unroll
+    for (int l = 0; l <= LM; l++) P[ECP_RS(l, 0)] = 1.0;
+  } else if (-1.0 == x) {
+    P[ECP_RS(0, 0)] = 1.0;
+#pragma unroll
+    for (int l = 1; l <= LM; l++) P[ECP_RS(l, 0)] = -P[ECP_RS(l - 1, 0)];
+  } else {
+    if (LM >= 1) s[1] = sqrt(1.0 - x * x);
+#pragma unroll
+    for (int l = 2; l <= LM; l++) s[l] = s[l - 1] * s[1];
+#pragma unroll
+    for (int l = 0; l <= LM; l++) {
+      if (0 == l)
+        P[ECP_RS(l, 0)] = 1.0;
+      else {
+        P[ECP_RS(l, l)] = s[l] * dfac[2 * l - 1];
+        P[ECP_RS(l, l - 1)] = x * (2 * (l - 1) + 1) * P[ECP_RS(l - 1, l - 1)];
+        if (l > 1) {
+#pragma unroll
+          for (int m = 0; m <= l - 2; m++)
+            P[ECP_RS(l, m)] = (x * (2 * l - 1) * P[ECP_RS(l - 1, m)] - (l + m - 1) * P[ECP_RS(l - 2, m)]) / (l - m);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l <= LM; l++) {
+    const double norm0 = sqrt((2.0 * l + 1.0) / (2.0 * M_PI));
+    P[ECP_RS(l, 0)] = norm0 * P[ECP_RS(l, 0)];
+#pragma unroll
+    for (int m = 1; m <= l; m++) {
+      const double norm = sqrt(fac[l - m] / fac[l + m]) * norm0;
+      P[ECP_RS(l, m)] = norm * P[ECP_RS(l, m)];
+    }
+  }
+  if (LM > 0) {
+    if (0.0 == phi) {
+#pragma unroll
+      for (int m = 0; m <= LM; m++) {
+        s[m] = 0.0;
+        c[m] = 1.0;
+      }
+    } else {
+      s[1] = sin(phi);
+      c[1] = cos(phi);
+#pragma unroll
+      for (int m = 2; m <= LM; m++) {
+        s[m] = s[1] * c[m - 1] + c[1] * s[m - 1];
+        c[m] = c[1] * c[m - 1] - s[1] * s[m - 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l <= LM; l++) {
+    out[ECP_RS(l, 0)] = P[ECP_RS(l, 0)] / sqrt(2.0);
+#pragma unroll
+    for (int m = 1; m <= l; m++) {
+      out[ECP_RS(l, -m)] = P[ECP_RS(l, m)] * s[m];
+      out[ECP_RS(l, +m)] = P[ECP_RS(l, m)] * c[m];
+    }
+  }
+#undef ECP_RS
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Small-grid level structure (PS93), level-major padded slot layout:
  *   slot 0 = centre point, slot 1 = pad, slots 2,3 = first pair, then level `v` occupies slots

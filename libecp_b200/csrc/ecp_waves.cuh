@@ -29,8 +29,14 @@
 struct __align__(16) FbwItem {
   long long sBase; /* first state of the item: states [sBase + ip * nf + j], ip = pair, j = failed quadrature */
   long long tOff;  /* T of the triple */
-  int uBase, qBase, nf, npair;
+  int uRank, qBase, nf, npair; /* uRank: first unit of the item inside its bucket */
+  int bucket, pad0, pad1, pad2;
 };
+/* units are laid out bucket by bucket, a bucket = the Bessel orders (la + l, lb + l) of the item: the warps that run side
+ * by side on an SM then execute the same instantiation of the Bessel code (ncu on the unsorted form: 5.8 warps per issue
+ * stalled on instruction fetch) */
+#define FBW_NBUCKET 128
+#define FBW_CTR 8 /* counters before the per-bucket unit counts */
 struct __align__(16) FbwUnit {
   double dAC, dBC, zA, zB, Cc, i1, i2;
   long long sBase; /* first state of the unit */
@@ -45,7 +51,8 @@ struct FbwQ { /* one failed quadrature of an item */
   int lll; /* l1 | l2 << 4 | l3 << 8 */
   int k;   /* position in the class list = index into the triple's T */
 };
-/* counters: [0] units [1] states [2] quadrature descriptors [3] open units of the next wave [4..5] value space (64 bit) */
+/* counters: [0] units [1] states [2] quadrature descriptors [3] open units of the next wave [4] value space of the next
+ * wave; [FBW_CTR + bucket] units per bucket */
 
 /* warp-aggregated reservation: every lane asks for n (may be 0) entries of counter c; returns the lane's first entry */
 __device__ __forceinline__ long long fbw_reserve(unsigned long long *ctr, long long n) {
@@ -67,33 +74,54 @@ __device__ __forceinline__ long long fbw_reserve(unsigned long long *ctr, long l
 __global__ void k_fbw_count(DevT t, DevB b, FbwItem *items, unsigned long long *ctr) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   const int nItems = b.counters[0];
-  int nf = 0, npair = 0;
+  int nf = 0, npair = 0, bucket = -1;
   long long tOff = 0;
   if (it < nItems) {
     const int item = b.items[it], tri = item >> 3, l = item & 7;
     const int cl = find_class_i(b.clsFirst, t.nClasses, tri);
+    bucket = (t.clsLa[cl] + l) * 11 + (t.clsLb[cl] + l); /* orders <= ECP_KMAX = 10 */
     const int k0 = t.clsQlOff[cl * (ECP_MAX_LECP + 1) + l], k1 = t.clsQlOff[cl * (ECP_MAX_LECP + 1) + l + 1];
     tOff = tri_T_off(t, b, cl, tri);
     for (int k = k0; k < k1; k++) nf += b.tfail[tOff + k] ? 1 : 0;
     npair = t.shellK[b.ssShell[b.trA[tri]]] * t.shellK[b.ssShell[b.trB[tri]]];
   }
-  const long long u = fbw_reserve(ctr + 0, npair);
+  /* rank of the item's units inside its bucket: one atomic per distinct bucket of the warp */
+  long long u = 0;
+  {
+    const unsigned peers = __match_any_sync(0xffffffffu, bucket);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    /* exclusive prefix of npair over the peers, in lane order */
+    int before = 0, total = 0;
+    for (unsigned m = peers; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      const int v = __shfl_sync(peers, npair, src);
+      if (src < lane) before += v;
+      total += v;
+    }
+    unsigned long long base = 0;
+    if (lane == leader && bucket >= 0 && total > 0) base = atomicAdd(ctr + FBW_CTR + bucket, (unsigned long long)total);
+    base = __shfl_sync(peers, base, leader);
+    u = (long long)base + before;
+  }
+  fbw_reserve(ctr + 0, npair);
   const long long s = fbw_reserve(ctr + 1, (long long)npair * nf);
   const long long q = fbw_reserve(ctr + 2, nf);
   if (it < nItems) {
     FbwItem r;
     r.sBase = s;
     r.tOff = tOff;
-    r.uBase = (int)u;
+    r.uRank = (int)u;
     r.qBase = (int)q;
     r.nf = nf;
     r.npair = npair;
+    r.bucket = bucket;
+    r.pad0 = r.pad1 = r.pad2 = 0;
     items[it] = r;
   }
 }
 
 /* ---- per item: quadrature descriptors and one record per primitive pair (src/type2.c:452-468) ---- */
-__global__ void k_fbw_units(DevT t, DevB b, const FbwItem *items, FbwUnit *units, FbwQ *qd) {
+__global__ void k_fbw_units(DevT t, DevB b, const FbwItem *items, const int *bucketOff, FbwUnit *units, FbwQ *qd) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= b.counters[0]) return;
   const FbwItem I = items[it];
@@ -142,19 +170,23 @@ __global__ void k_fbw_units(DevT t, DevB b, const FbwItem *items, FbwUnit *units
       u.g1 = g1;
       u.lpack = (la + l) | ((lb + l) << 4) | ((la + lb) << 8) | (l << 12);
       u.pad = 0;
-      units[I.uBase + ip] = u;
+      units[bucketOff[I.bucket] + I.uRank + ip] = u;
     }
 }
 
-/* Bessel vector of exactly the order the unit needs (warp-uniform switch) */
+/* Bessel vector of exactly the order the unit needs (warp-uniform switch); one out-of-line copy per order */
+template <int K>
+__device__ __noinline__ void fbw_bessel(const double *__restrict__ tabT, int stride, const double *__restrict__ Cj, double z,
+                                        double *dst) {
+  double Kv[K + 1];
+  ecp_bessel<K>(tabT, stride, Cj, K, z, Kv);
+#pragma unroll
+  for (int i = 0; i <= K; i++) dst[i] = Kv[i];
+}
 template <int KO>
 __device__ __forceinline__ void fbw_bessel_sel(const DevT &t, int lmax, double z, double *dst) {
-#define FBW_CASE(K)                                                     \
-  case K: {                                                             \
-    double Kv[K + 1];                                                   \
-    ecp_bessel<K>(t.besselT, t.besselStride, t.besselC, K, z, Kv);      \
-    _Pragma("unroll") for (int i = 0; i <= K; i++) dst[i] = Kv[i];      \
-  } break;
+#define FBW_CASE(K) \
+  case K: fbw_bessel<K>(t.besselT, t.besselStride, t.besselC, z, dst); break;
   switch (lmax) {
     FBW_CASE(0)
     FBW_CASE(1)
@@ -166,15 +198,10 @@ __device__ __forceinline__ void fbw_bessel_sel(const DevT &t, int lmax, double z
     default:
       if (KO > 6) {
         switch (lmax) {
-          FBW_CASE(7)
-          FBW_CASE(8)
-          FBW_CASE(9)
-          default: {
-            double Kv[11];
-            ecp_bessel<10>(t.besselT, t.besselStride, t.besselC, 10, z, Kv);
-#pragma unroll
-            for (int i = 0; i <= 10; i++) dst[i] = Kv[i];
-          } break;
+          case 7: fbw_bessel<(KO > 6 ? 7 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
+          case 8: fbw_bessel<(KO > 6 ? 8 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
+          case 9: fbw_bessel<(KO > 6 ? 9 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
+          default: fbw_bessel<(KO > 6 ? 10 : 6)>(t.besselT, t.besselStride, t.besselC, z, dst); break;
         }
       }
       break;
@@ -254,14 +281,18 @@ __global__ void __launch_bounds__(128) k_fbw_book(DevT t, const FbwUnit *units, 
       const long long si = u.sBase + j;
       const double *v = vb + (size_t)j * S;
       if (lev == 4) {
-        double I = v[0], P = I, Qv = 0.0, res = 0.0; /* centre (slot 1 is the pad) */
+        double2 vv[16]; /* the 32 values of the wave, all loads in flight together */
+#pragma unroll
+        for (int i = 0; i < 16; i++) vv[i] = __ldcs(reinterpret_cast<const double2 *>(v) + i);
+        double I = vv[0].x, P = I, Qv = 0.0, res = 0.0; /* centre (slot 1 is the pad) */
         bool op = true;
         int off = 2, np = 1;
 #pragma unroll
         for (int lvl = 1; lvl <= 4; lvl++) { /* q = 2p; p = 2I; I += level; test  (src/gc_integrators.c:56-57, 73-83) */
           Qv = 2 * P;
           P = 2 * I;
-          for (int i = 0; i < (1 << lvl); i += 2) I += v[off + i] + v[off + i + 1];
+#pragma unroll
+          for (int i = 0; i < (1 << lvl); i += 2) I += vv[(off + i) >> 1].x + vv[(off + i) >> 1].y;
           off += 1 << lvl;
           np = 2 * np + 1;
           if (op && ecp_psm92_test(np, t.tolerance, I, P, Qv)) {
@@ -281,7 +312,13 @@ __global__ void __launch_bounds__(128) k_fbw_book(DevT t, const FbwUnit *units, 
         double I = sI[si], P = sP[si], Qv;
         Qv = 2 * P;
         P = 2 * I;
-        for (int i = 0; i < S; i += 2) I += v[i] + v[i + 1];
+        for (int i0 = 0; i0 < S; i0 += 32) {
+          double2 vv[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) vv[i] = __ldcs(reinterpret_cast<const double2 *>(v + i0) + i);
+#pragma unroll
+          for (int i = 0; i < 16; i++) I += vv[i].x + vv[i].y;
+        }
         const int np = 2 * S - 1; /* points including this level */
         if (ecp_psm92_test(np, t.tolerance, I, P, Qv)) {
           sRes[si] = 16 * I / (3 * (np + 1.0));

@@ -354,28 +354,36 @@ def test_link_variants_are_bit_identical():
             assert np.allclose(got, base, rtol=1e-13, atol=1e-15), (name, env)
 
 
-@pytest.mark.skipif(not os.environ.get("LIBECP_B200_EXPERIMENTAL"),
-                    reason="experimental kernels are opt-in: set LIBECP_B200_EXPERIMENTAL=1")
-def test_fused_shift_variant_within_tolerance():
-    """LIBECP_B200_SHIFT=fused (off by default): 4 pi chi + 16 pi^2 gamma shifted once in matrix-only runs - same
-    terms, associated differently, so parity with the reference within the tolerance and callbacks untouched"""
-    for fn, name in ((lambda: synth.cfg3(4), "au4"), (lambda: synth.cfg4("a"), "cfg4a"), (synth.cfg2, "cfg2")):
-        got = _with_env({"LIBECP_B200_SHIFT": "fused"}, lambda: capi.get_integrals(fn()))
-        assert_parity(got, load_matrix(name), name + " fused shift")
+def test_shift_kernels_are_bit_identical():
+    """k_shift2 (default: both binomial-shift passes in one kernel, J in shared memory, factors per (triple, term)) runs
+    the terms of k_shiftJ / k_shiftI (LIBECP_B200_SHIFT=two) in the same order with the same fma's: callback blocks
+    bit-identical, matrices equal to the last ulps (atomicAdd order)"""
+    for s, name in ((synth.cfg3(3), None), (synth.cfg4("a"), "cfg4a"), (synth.cfg4("b"), "cfg4b"), (synth.cfg5(16), None)):
+        def run():
+            with capi.Handle(s) as h:
+                rc, recs = h.callbacks()
+                rc2, M = h.integrals_host()
+                return rc, rc2, np.concatenate([r[9] for r in recs]), M
+        rc0, rc0b, blk0, M0 = _with_env({"LIBECP_B200_SHIFT": "two"}, run)
+        rc1, rc1b, blk1, M1 = run()
+        assert rc0 == rc1 == rc0b == rc1b == 0
+        assert np.array_equal(blk0, blk1), name
+        assert np.allclose(M0, M1, rtol=1e-13, atol=1e-15), name
+        if name:
+            assert_parity(M1, load_matrix(name), name)
 
 
-@pytest.mark.skipif(not os.environ.get("LIBECP_B200_EXPERIMENTAL"),
-                    reason="experimental kernels are opt-in: set LIBECP_B200_EXPERIMENTAL=1")
-def test_ftab_compact_variant_is_bit_identical():
-    """k_Ftab2 (LIBECP_B200_FTAB=compact, off by default) tabulates only the window of every shell slot into a cleared
-    table: same arithmetic per point, so the F table and the matrices are bit-identical to k_Ftab's"""
+def test_ftab_variants_are_bit_identical():
+    """k_Ftab2 (default) tabulates only the window of every shell slot into a cleared table, k_Ftab (LIBECP_B200_FTAB=full)
+    the whole grid with zeros outside the window: same arithmetic per point, so the F table and the matrices are
+    bit-identical"""
     for s, name in ((synth.cfg3(4), "au4"), (synth.cfg4("b"), "cfg4b")):
         def run():
             with capi.Handle(s) as h:
                 rc, M = h.integrals_host()
                 return M, h.debug_fetch("F", 400000)
-        base, f0 = run()
-        got, f1 = _with_env({"LIBECP_B200_FTAB": "compact"}, run)
+        base, f0 = _with_env({"LIBECP_B200_FTAB": "full"}, run)
+        got, f1 = run()
         assert np.array_equal(f0, f1), name
         assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
         assert_parity(got, load_matrix(name), name + " compact F")
