@@ -123,9 +123,12 @@ def get_integrals(s, tol=1e-12, acc=1e-14, large=1024):
 class Handle:
     """libECP_init / calculateECPIntegrals / libECP_free (reference src/libecp.h:15-29) + device extensions."""
 
-    def __init__(self, s, tol=1e-12, acc=1e-14, large=1024, n=0, tables_only=False):
+    def __init__(self, s, tol=1e-12, acc=1e-14, large=1024, n=0, tables_only=False, ordering=None, lmax=-1):
+        """ordering: int32 array in the layout of cartesianShellOrder(lmax) - the caller's Cartesian component order
+        (reference src/libecp.c:152-166); n: derivative order (0 or 1)"""
         L = lib()
         self.s = s  # keeps the borrowed arrays alive (the handle borrows them, reference src/libecp.c:68-74)
+        self.ordering = None if ordering is None else np.ascontiguousarray(ordering, np.int32)
         if tables_only:
             L.libecp_b200_set_tables_only(1)
         try:
@@ -134,7 +137,8 @@ class Handle:
                                    _p(s["nECP"], _pd), _p(s["dECP"], _pd), _p(s["aECP"], _pd),
                                    _p(s["shellsBS"], _pi), _p(s["lBS"], _pi), _p(s["KBS"], _pi),
                                    _p(s["dBS"], _pd), _p(s["aBS"], _pd),
-                                   C.c_int(n), C.c_int(-1), None, C.c_int(large), C.c_double(tol), C.c_double(acc))
+                                   C.c_int(n), C.c_int(lmax), None if self.ordering is None else _p(self.ordering, _pi),
+                                   C.c_int(large), C.c_double(tol), C.c_double(acc))
         finally:
             if tables_only:
                 L.libecp_b200_set_tables_only(0)
@@ -162,7 +166,7 @@ class Handle:
         recs = []
 
         def cb(A, s1, la, sha, B, s2, lb, shb, Cc, I, args):
-            n = ((la + 1) * (la + 2) // 2) * ((lb + 1) * (lb + 2) // 2)
+            n = ((la + sha + 1) * (la + sha + 2) // 2) * ((lb + shb + 1) * (lb + shb + 2) // 2)
             blk = np.ctypeslib.as_array(I, shape=(n,)).copy() if keep_blocks else None
             recs.append((A, s1, la, sha, B, s2, lb, shb, Cc, blk))
 

@@ -70,14 +70,9 @@ double libecp_b200_fp64_peak(int device, int iters) { return ecpdev_fp64_peak_pr
 libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lECP, int *KECP, double *nECP,
                           double *dECP, double *aECP, int *shellsBS, int *lBS, int *KBS, double *dBS, double *aBS,
                           int n, int lmax, int *shellOrdering, int largeGridOrder, double tolerance, double accuracy) {
-  (void)lmax; /* only read together with shellOrdering (reference src/libecp.c:152-166) */
-  g_apierr[0] = 0;
+  g_apierr[0] = 0; /* lmax is only read together with shellOrdering (reference src/libecp.c:152-166) */
   if (n != 0) {
     snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d not supported (only n=0)", n);
-    return NULL;
-  }
-  if (shellOrdering != NULL) {
-    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: custom shell ordering (lmax=%d) not supported; pass -1, NULL", lmax);
     return NULL;
   }
   libECPHandle *h = calloc(1, sizeof(*h));
@@ -93,8 +88,9 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
     const char *e = getenv("LIBECP_B200_BATCH_TRIPLES");
     if (e && atoll(e) > 0) h->maxTriples = atoll(e);
   }
+  EcpBuildOpts opts = {shellOrdering, lmax, NULL};
   h->tab = ecp_tables_build(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, shellsBS, lBS, KBS, dBS, aBS,
-                            largeGridOrder, tolerance, accuracy);
+                            largeGridOrder, tolerance, accuracy, &opts);
   if (!h->tab) {
     snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: %s", ecp_tables_last_error());
     free(h);

@@ -51,6 +51,37 @@ static void cartesian_order(int am, int **ijk_, int **inv_) {
   *inv_ = inv;
 }
 
+/* a caller-supplied order (layout of cartesianShellOrder(lmaxOrd)): the shells l <= am are copied, the inverse cube has
+ * the caller's edge lmaxOrd + 1 (reference src/libecp.c:163-165, src/dimensions.c:42-57).  Returns 1 if a shell's
+ * components are not a permutation of its monomials. */
+static int custom_order(const int *ord, int lmaxOrd, int am, int **ijk_, int **inv_) {
+  const int dim = lmaxOrd + 1;
+  int *ijk = calloc(3 * CD(am), sizeof(int)), *inv = calloc((size_t)dim * dim * dim, sizeof(int));
+  int bad = 0;
+  for (int i = 0; i < dim * dim * dim; i++) inv[i] = -1;
+  for (int l = 0; l <= am && !bad; l++)
+    for (int c = 0; c < IJK(l); c++) {
+      const int *s = ord + 3 * CIDX(l, c);
+      int *e = ijk + 3 * CIDX(l, c);
+      if (s[0] < 0 || s[1] < 0 || s[2] < 0 || s[0] + s[1] + s[2] != l || inv[s[0] * dim * dim + s[1] * dim + s[2]] >= 0) {
+        bad = 1;
+        break;
+      }
+      e[0] = s[0]; e[1] = s[1]; e[2] = s[2];
+      inv[e[0] * dim * dim + e[1] * dim + e[2]] = CIDX(l, c);
+    }
+  for (int i = 0; i < dim * dim * dim; i++)
+    if (inv[i] < 0) inv[i] = 0; /* the reference's calloc'ed cube */
+  if (bad) {
+    free(ijk);
+    free(inv);
+    return 1;
+  }
+  *ijk_ = ijk;
+  *inv_ = inv;
+  return 0;
+}
+
 /* packed (l, m, c) offsets of the Cartesian->spherical matrix (reference src/transformations.h:13-14) */
 /* ---- process-wide cache of the tables that do not depend on the molecule ----
  * cart2sph / poly2sph (key tmDim), Omega (key maxLECP, maxLambda, maxAlpha, tmDim) and the Bessel table (key lMax,
@@ -539,8 +570,9 @@ const char *ecp_tables_last_error(void) { return g_taberr; }
 EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shellsECP, const int *lECP,
                             const int *KECP, const double *nECP, const double *dECP, const double *aECP,
                             const int *shellsBS, const int *lBS, const int *KBS, const double *dBS, const double *aBS,
-                            int largeGridOrder, double tolerance, double accuracy) {
+                            int largeGridOrder, double tolerance, double accuracy, const EcpBuildOpts *opts) {
   EcpTables *t = calloc(1, sizeof(EcpTables));
+  const int *customOrder = opts ? opts->shellOrdering : NULL;
   EcpHostTables *v = &t->v;
   (void)geometry;
   v->nrAtoms = nrAtoms;
@@ -659,16 +691,30 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   v->nfac = 2 * v->tmDim + 2;
   t->fac = factorial_table(2 * v->tmDim + 1, 1);
   t->dfac = factorial_table(2 * v->tmDim + 1, 2);
-  cartesian_order(v->tmDim, &t->ijk, &t->ijkIndex);
-  if (!(t->cart2sph = cc_get(CC_C2S, v->tmDim, 0, 0, 0, 0.0, NULL))) {
+  if (customOrder) {
+    /* the caller's component order (reference src/libecp.c:158-166): it must reach one shell beyond tmDim, the index
+     * cube has the caller's edge lmax + 1, and the order-dependent tables are built for this handle (no cache) */
+    const int lm = opts->lmaxOrd;
+    if (lm < v->tmDim + 1)
+      TAB_FAIL("shell ordering given up to lmax = %d, needed up to %d (reference src/libecp.c:159-162)", lm, v->tmDim + 1);
+    v->ijkDim = lm + 1;
+    if (custom_order(customOrder, lm, v->tmDim, &t->ijk, &t->ijkIndex))
+      TAB_FAIL("shell ordering: the components of a shell l <= %d are not a permutation of its %s", v->tmDim, "monomials");
     t->cart2sph = build_cart2sph(v->tmDim, t->ijk, t->fac);
-    cc_put(CC_C2S, v->tmDim, 0, 0, 0, 0.0, t->cart2sph, (size_t)c2s_size(v->tmDim, t->fac));
-  }
-  if (!(t->poly2sph = cc_get(CC_P2S, v->tmDim, 0, 0, 0, 0.0, NULL))) {
     t->poly2sph = build_poly2sph(t->cart2sph, v->tmDim, t->ijk, t->dfac);
-    cc_put(CC_P2S, v->tmDim, 0, 0, 0, 0.0, t->poly2sph, (size_t)CD(v->tmDim) * LD(v->tmDim));
+    t->omega = build_omega(t, &v->nomega);
+  } else {
+    cartesian_order(v->tmDim, &t->ijk, &t->ijkIndex);
+    if (!(t->cart2sph = cc_get(CC_C2S, v->tmDim, 0, 0, 0, 0.0, NULL))) {
+      t->cart2sph = build_cart2sph(v->tmDim, t->ijk, t->fac);
+      cc_put(CC_C2S, v->tmDim, 0, 0, 0, 0.0, t->cart2sph, (size_t)c2s_size(v->tmDim, t->fac));
+    }
+    if (!(t->poly2sph = cc_get(CC_P2S, v->tmDim, 0, 0, 0, 0.0, NULL))) {
+      t->poly2sph = build_poly2sph(t->cart2sph, v->tmDim, t->ijk, t->dfac);
+      cc_put(CC_P2S, v->tmDim, 0, 0, 0, 0.0, t->poly2sph, (size_t)CD(v->tmDim) * LD(v->tmDim));
+    }
   }
-  {
+  if (!customOrder) {
     size_t nom = 0;
     if ((t->omega = cc_get(CC_OMEGA, v->maxLECP, v->maxLambda, v->maxAlpha, v->tmDim, 0.0, &nom))) {
       v->nomega = (int)nom;
@@ -742,8 +788,10 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
 
   /* ---- shell radii (reference src/type2.c:251 recomputes them per centre; they do not depend on it) ---- */
   t->shellRadius = malloc((nsh + 1) * sizeof(double));
-  for (int s = 0; s < nsh; s++)
-    t->shellRadius[s] = shell_radius(KBS[s], lBS[s], dBS + t->shellPrim[s], aBS + t->shellPrim[s], 1.0E-14);
+  for (int s = 0; s < nsh; s++) {
+    const int ps = (opts && opts->screenParent) ? opts->screenParent[s] : s; /* a shifted shell is screened as its parent */
+    t->shellRadius[s] = shell_radius(KBS[ps], lBS[ps], dBS + t->shellPrim[ps], aBS + t->shellPrim[ps], 1.0E-14);
+  }
   t->atomRmax = calloc(nrAtoms + 1, sizeof(double));
   for (int s = 0; s < nsh; s++)
     if (t->shellRadius[s] > t->atomRmax[t->shellAtom[s]]) t->atomRmax[t->shellAtom[s]] = t->shellRadius[s];

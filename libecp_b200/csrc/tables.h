@@ -49,11 +49,22 @@ typedef struct {
   int clsLookup[ECP_MAX_LBS + 1][ECP_MAX_LBS + 1][ECP_MAX_LECP + 1];
 } EcpTables;
 
+/* optional inputs of ecp_tables_build (NULL = none) */
+typedef struct {
+  /* caller's Cartesian component order (reference src/libecp.c:152-166): exponent triples of every component of the
+   * shells l = 0..lmaxOrd in the layout of cartesianShellOrder(lmaxOrd); NULL = libint order */
+  const int *shellOrdering;
+  int lmaxOrd;
+  /* derivative runs (api.c): the basis handed in is the expanded list of shifted shells; screenParent[s] = the shell
+   * whose radius screens shell s (the unshifted one, reference src/type2.c:251); NULL = every shell screens itself */
+  const int *screenParent;
+} EcpBuildOpts;
+
 /* returns NULL on unsupported shape / Bessel series failure (reference: src/libecp.c:159-162,181-185) */
 EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shellsECP, const int *lECP,
                             const int *KECP, const double *nECP, const double *dECP, const double *aECP,
                             const int *shellsBS, const int *lBS, const int *KBS, const double *dBS, const double *aBS,
-                            int largeGridOrder, double tolerance, double accuracy);
+                            int largeGridOrder, double tolerance, double accuracy, const EcpBuildOpts *opts);
 void ecp_tables_free(EcpTables *t);
 /* why the last ecp_tables_build of this thread returned NULL */
 const char *ecp_tables_last_error(void);

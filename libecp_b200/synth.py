@@ -140,6 +140,24 @@ def deriv_pair(lbs: int = 2, L: int = 4):
     return assemble(f"deriv_tz{lbs}_L{L}", [(0.0, 0.0, 0.0), (0.3, -0.4, 4.1)], [tz_basis(lbs)] * 2, [ecp_set(L)] * 2)
 
 
+def shell_order(lmax: int, kind: str = "libint"):
+    """Cartesian component order of the shells l = 0..lmax in the layout of cartesianShellOrder(lmax)
+    (reference src/dimensions.c:17-37): int32 [3 * C_DIM(lmax)], exponent triples (nx, ny, nz).
+    kind "libint": the library's default; "reversed": every shell back to front (z^l first);
+    "zfirst": components sorted by (nz, ny) descending - neither order is a relabelling of the axes of the default."""
+    out = []
+    for l in range(lmax + 1):
+        comp = [(l - i, i - j, j) for i in range(l + 1) for j in range(i + 1)]
+        if kind == "reversed":
+            comp = comp[::-1]
+        elif kind == "zfirst":
+            comp = sorted(comp, key=lambda e: (-e[2], -e[1]))
+        elif kind != "libint":
+            raise ValueError(kind)
+        out += [x for e in comp for x in e]
+    return np.array(out, np.int32)
+
+
 def cfg4(variant: str = "a"):
     """high-angular-momentum stress: (a) TZ(4)+ECP(5), (b) TZ(5)+ECP(6); 2 atoms on the z axis."""
     lbs, L = (4, 5) if variant == "a" else (5, 6)

@@ -59,7 +59,7 @@ class RefLib:
             raise RuntimeError(f"getIntegrals rc={rc}")
         return I
 
-    def callbacks(self, s, tol=1e-12, acc=1e-14, large=1024, keep_blocks=True, n=0):
+    def callbacks(self, s, tol=1e-12, acc=1e-14, large=1024, keep_blocks=True, n=0, ordering=None, lmax=-1):
         """Run init/calculate/free with a recording callback.
 
         Returns (rc, records) with records = list of (A,s1,la,shifta,B,s2,lb,shiftb,C,block ndarray|None)
@@ -67,6 +67,8 @@ class RefLib:
         implements n > 0: shifted-momentum blocks, src/libecp.c:246-250,322-369).
         """
         recs = []
+        if ordering is not None:  # ordering: int32 array laid out like cartesianShellOrder(lmax) (src/libecp.c:152-166)
+            ordering = np.ascontiguousarray(ordering, np.int32)
 
         def cb(A, s1, la, sha, B, s2, lb, shb, Cc, I, args):
             n = ((la + sha + 1) * (la + sha + 2) // 2) * ((lb + shb + 1) * (lb + shb + 2) // 2)
@@ -79,7 +81,8 @@ class RefLib:
                         _p(s["nECP"], _pd), _p(s["dECP"], _pd), _p(s["aECP"], _pd),
                         _p(s["shellsBS"], _pi), _p(s["lBS"], _pi), _p(s["KBS"], _pi),
                         _p(s["dBS"], _pd), _p(s["aBS"], _pd),
-                        C.c_int(n), C.c_int(-1), None, C.c_int(large), C.c_double(tol), C.c_double(acc))
+                        C.c_int(n), C.c_int(lmax), None if ordering is None else _p(ordering, _pi),
+                        C.c_int(large), C.c_double(tol), C.c_double(acc))
         if not h:
             raise RuntimeError("libECP_init returned NULL")
         rc = self.f_calc(C.c_void_p(h), cbf, None)

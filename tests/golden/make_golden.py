@@ -2,13 +2,14 @@
 oracle/Makefile from /root/reference/src).  Run in the build container only (the GPU box has no
 /root/reference); the resulting .npz files are committed.
 
-    python tests/golden/make_golden.py [--big | --deriv]
+    python tests/golden/make_golden.py [--big | --deriv | --order]
 
 Fixtures (float64, exact bytes of the reference's output):
   <cfg>_matrix.npz   : getIntegrals matrix (upper triangle incl. diagonal as a flat vector `triu`,
                        dimension `dim`), Σ and Σ|.| checksums, callback count
   cfg2_blocks.npz    : every callback block of config 2 in call order (keys, block offsets, values)
   au2_blocks.npz     : same for the first two atoms of the Au20 tetrahedron (two-centre cases, fallback)
+  order_*_blocks.npz : callback blocks with a caller-supplied Cartesian component order (synth.shell_order)
   deriv1_*_blocks.npz: callback blocks of derivative order n = 1 (shifted-momentum blocks, src/libecp.c:246-250,322-369)
                        for two-atom systems - fixtures for the NEXT scope row; the product rejects n > 0
                        today.  n = 2 is not recorded: the reference returns NaN in a few (1,0)/(0,1)-shift blocks on
@@ -54,8 +55,8 @@ def save_digest(ref, name, s):
     print(f"{name}: dim {s['dim']} sum {M.sum():.15e} sumabs {np.abs(M).sum():.15e} nnz {len(nz)}  {dt:.1f}s")
 
 
-def save_blocks(ref, name, s, n=0):
-    rc, recs = ref.callbacks(s, n=n)
+def save_blocks(ref, name, s, n=0, ordering=None, lmax=-1):
+    rc, recs = ref.callbacks(s, n=n, ordering=ordering, lmax=lmax)
     assert rc == 0
     keys = np.array([r[:9] for r in recs], np.int32)
     off = np.cumsum([0] + [len(r[9]) for r in recs])
@@ -69,6 +70,10 @@ def main():
     if "--deriv" in sys.argv:  # next scope row (f1): first derivatives, two shapes; nothing else is regenerated
         save_blocks(ref, "deriv1_tz2_L4", synth.deriv_pair(2, 4), n=1)
         save_blocks(ref, "deriv1_tz3_L5", synth.deriv_pair(3, 5), n=1)
+        return
+    if "--order" in sys.argv:  # scope row f4: caller-supplied Cartesian component order (src/libecp.c:152-166)
+        save_blocks(ref, "order_rev_cfg2", synth.cfg2(), ordering=synth.shell_order(10, "reversed"), lmax=10)
+        save_blocks(ref, "order_zfirst_au2", synth.cfg3(2), ordering=synth.shell_order(11, "zfirst"), lmax=11)
         return
     save_matrix(ref, "cfg1", synth.cfg1())
     save_matrix(ref, "cfg2", synth.cfg2())

@@ -387,3 +387,43 @@ def test_ftab_variants_are_bit_identical():
         assert np.array_equal(f0, f1), name
         assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
         assert_parity(got, load_matrix(name), name + " compact F")
+
+
+ORDER_CASES = {"order_rev_cfg2": (synth.cfg2, "reversed", 10), "order_zfirst_au2": (lambda: synth.cfg3(2), "zfirst", 11)}
+
+
+@pytest.mark.parametrize("name", list(ORDER_CASES))
+def test_custom_shell_ordering_matches_golden(name):
+    """scope row f4: caller-supplied Cartesian component order (libECP_init(..., lmax, shellOrdering, ...), reference
+    src/libecp.c:152-166) vs blocks of the compiled reference run with the same order; and the blocks are the
+    default-order blocks with rows / columns permuted"""
+    mk, kind, lmax = ORDER_CASES[name]
+    keys, off, vals = load_blocks(name)
+    s = mk()
+    order = synth.shell_order(lmax, kind)
+    with capi.Handle(s, ordering=order, lmax=lmax) as h:
+        rc, recs = h.callbacks()
+    assert rc == 0 and len(recs) == len(keys)
+    for k, r in enumerate(recs):
+        assert tuple(keys[k]) == r[:9]
+    assert_parity(np.concatenate([r[9] for r in recs]), vals, name)
+    with capi.Handle(s) as h:
+        rc, std = h.callbacks()
+    libint = synth.shell_order(lmax, "libint").reshape(-1, 3)
+    mine = order.reshape(-1, 3)
+
+    def perm(l):  # position in the default order of every component of the custom order
+        lo, n = l * (l + 1) * (l + 2) // 6, (l + 1) * (l + 2) // 2
+        where = {tuple(e): i for i, e in enumerate(libint[lo:lo + n])}
+        return np.array([where[tuple(e)] for e in mine[lo:lo + n]])
+
+    for a, b in zip(recs, std):
+        la, lb = a[2], a[6]
+        want = b[9].reshape(len(perm(la)), len(perm(lb)))[np.ix_(perm(la), perm(lb))].ravel()
+        assert np.all(np.abs(a[9] - want) <= 1e-12 + 1e-10 * np.abs(want))
+
+
+def test_custom_shell_ordering_too_short_is_rejected():
+    """reference src/libecp.c:159-162: lmax < maxLambda + maxAlpha + 1 -> NULL"""
+    with pytest.raises(RuntimeError):
+        capi.Handle(synth.cfg2(), ordering=synth.shell_order(9, "reversed"), lmax=9)

@@ -570,3 +570,32 @@ def test_committed_config5_digest_is_self_consistent():
     for c in (0, 1, 288, 289):
         zc = np.load(os.path.join(GOLDEN, f"cfg5_c{c}_digest.npz"))
         assert np.all((zc["rowabs"] > 0) <= (z["rowabs"] > 0))
+
+
+def test_custom_shell_ordering_tables():
+    """scope row f4 (reference src/libecp.c:152-166): with a caller-supplied component order the order-dependent
+    host tables are the default ones with their monomial index permuted; a too short ordering is rejected"""
+    s = synth.cfg2()
+    with capi.Handle(s, tables_only=True) as h0:
+        tm = int(h0.host_itable("dims")[4])
+        p0, ijk0 = h0.host_table("poly2sph"), h0.host_itable("ijk").reshape(-1, 3)
+    lmax = tm + 1
+    for kind in ("reversed", "zfirst"):
+        order = synth.shell_order(lmax, kind)
+        with capi.Handle(s, tables_only=True, ordering=order, lmax=lmax) as h:
+            p1, ijk1 = h.host_table("poly2sph"), h.host_itable("ijk").reshape(-1, 3)
+            idx = h.host_itable("ijkIndex").reshape(lmax + 1, lmax + 1, lmax + 1)
+        assert np.array_equal(ijk1, order.reshape(-1, 3)[:len(ijk1)])
+        cols = len(p0) // len(ijk0)
+        where = {tuple(e): i for i, e in enumerate(ijk0)}
+        perm = np.array([where[tuple(e)] for e in ijk1])
+        # same numbers up to the order of the sums over a shell's components (src/transformations.c:146-207)
+        assert np.allclose(p1.reshape(-1, cols), p0.reshape(-1, cols)[perm], rtol=1e-13, atol=1e-15)
+        for i, e in enumerate(ijk1):
+            assert idx[tuple(e)] == i
+    with pytest.raises(RuntimeError):
+        capi.Handle(s, tables_only=True, ordering=synth.shell_order(tm, "reversed"), lmax=tm)
+    with pytest.raises(RuntimeError):  # not a permutation of the monomials of a shell
+        bad = synth.shell_order(lmax, "libint").copy()
+        bad[3:6] = bad[6:9]
+        capi.Handle(s, tables_only=True, ordering=bad, lmax=lmax)
