@@ -99,6 +99,9 @@ int libecp_b200_host_table(libECPHandle *h, const char *name, const double **ptr
 int libecp_b200_host_itable(libECPHandle *h, const char *name, int *out, int cap);
 /* executed triples of the whole job in the reference's loop order, rows (A,s1,la,B,s2,lb,C); host only */
 long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap);
+/* callback keys of the whole job in call order, rows (A,s1,la,shifta,B,s2,lb,shiftb,C), one row per executed (shifted)
+ * triple = one type-1 and one type-2 callback (reference src/libecp.c:372); host only */
+long long libecp_b200_callback_keys(libECPHandle *h, int *out, long long cap);
 /* Wall time (ms) of the host batch builder alone over one pass (no device work); optional totals. */
 double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches);
 /* test hook: handles created afterwards build tables + batches only (no device); compute entry points

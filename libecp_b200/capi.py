@@ -27,7 +27,7 @@ EXPORTS = [
     "libecp_b200_debug_fetch", "libecp_b200_fp64_peak", "libecp_b200_last_error", "libecp_b200_set_host_threads",
     "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only", "libecp_b200_owned_rows", "libecp_b200_pack_rows", "libecp_b200_unpack_rows",
     "libecp_b200_matrix_ptr", "libecp_b200_comm_unique_id", "libecp_b200_comm_init", "libecp_b200_comm_attach",
-    "libecp_b200_allgather", "libecp_b200_device_sync", "libecp_b200_comm_free",
+    "libecp_b200_allgather", "libecp_b200_device_sync", "libecp_b200_comm_free", "libecp_b200_callback_keys",
 ]
 
 
@@ -248,6 +248,16 @@ class Handle:
         if rc:
             raise RuntimeError("not an ECP centre")
         return endl[:L], st, en, sk
+
+    def callback_keys(self):
+        """(A,s1,la,shifta,B,s2,lb,shiftb,C) of every executed (shifted) triple in call order (host only)"""
+        f = lib().libecp_b200_callback_keys
+        f.restype = C.c_longlong
+        f.argtypes = [C.c_void_p, _pi, C.c_longlong]
+        n = int(f(C.c_void_p(self.h), None, 0))
+        out = np.zeros((max(n, 1), 9), np.int32)
+        f(C.c_void_p(self.h), _p(out, _pi), n)
+        return out[:n]
 
     def owned_rows(self, rank, world):
         """AO rows (ascending) of the shells whose shell-pair rows `rank` of `world` owns"""

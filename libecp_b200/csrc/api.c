@@ -32,6 +32,9 @@ struct _libECPHandle {
   long long maxTriples;
   double *hostBlocks;
   size_t hostBlocksCap;
+  /* derivative runs: the expanded shell list the tables borrow (libECP_init) */
+  int *xShells, *xL, *xK;
+  double *xD, *xA;
   libecp_b200_stats_t stats;
 };
 
@@ -46,6 +49,10 @@ static double now_ms(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+static void free_expanded(libECPHandle *h) {
+  free(h->xShells); free(h->xL); free(h->xK); free(h->xD); free(h->xA);
 }
 
 void libecp_b200_set_device(int device) { g_device = device; }
@@ -71,8 +78,9 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
                           double *dECP, double *aECP, int *shellsBS, int *lBS, int *KBS, double *dBS, double *aBS,
                           int n, int lmax, int *shellOrdering, int largeGridOrder, double tolerance, double accuracy) {
   g_apierr[0] = 0; /* lmax is only read together with shellOrdering (reference src/libecp.c:152-166) */
-  if (n != 0) {
-    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d not supported (only n=0)", n);
+  if (n != 0 && n != 1) {
+    /* n = 2: the reference's own output contains NaN blocks on every shape tried (tests/golden/make_golden.py) */
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d not supported (n = 0 or 1)", n);
     return NULL;
   }
   libECPHandle *h = calloc(1, sizeof(*h));
@@ -88,11 +96,59 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
     const char *e = getenv("LIBECP_B200_BATCH_TRIPLES");
     if (e && atoll(e) > 0) h->maxTriples = atoll(e);
   }
-  EcpBuildOpts opts = {shellOrdering, lmax, NULL};
-  h->tab = ecp_tables_build(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, shellsBS, lBS, KBS, dBS, aBS,
-                            largeGridOrder, tolerance, accuracy, &opts);
+  EcpBuildOpts opts = {shellOrdering, lmax, NULL, 0, NULL, NULL};
+  if (n == 1) {
+    /* First derivatives (scope row f1; reference src/libecp.c:203-210,246-250,322-330): a derivative block is an
+     * ordinary block between shells shifted in angular momentum - l + 1 with the coefficients d zeta (src/type1.c:239-246,
+     * src/type2.c:263-269,459-462) or l - 1 with d - screened as the unshifted shell (src/type2.c:251).  The handle
+     * therefore runs on an expanded shell list: every shell is followed by its two shifted copies; the builder pairs
+     * them as the reference's shift table prescribes.  All sizes (tables, Bessel depth, classes) follow from the
+     * expanded list exactly as the reference derives them from maxLBS + n. */
+    int nsh = 0, nprim = 0;
+    for (int i = 0; i < nrAtoms; i++)
+      for (int j = 0; j < shellsBS[i]; j++) nprim += KBS[nsh++];
+    h->xShells = malloc((nrAtoms + 1) * sizeof(int));
+    h->xL = malloc((3 * nsh + 1) * sizeof(int));
+    h->xK = malloc((3 * nsh + 1) * sizeof(int));
+    h->xD = malloc((3 * nprim + 1) * sizeof(double));
+    h->xA = malloc((3 * nprim + 1) * sizeof(double));
+    int *par = malloc((3 * nsh + 1) * sizeof(int)), *vsh = malloc((3 * nsh + 1) * sizeof(int));
+    int *vloc = malloc((3 * nsh + 1) * sizeof(int));
+    int s = 0, p = 0, xs = 0, xp = 0;
+    for (int i = 0; i < nrAtoms; i++) {
+      int cnt = 0;
+      for (int j = 0; j < shellsBS[i]; j++, s++) {
+        const int l = lBS[s], K = KBS[s], x0 = xs;
+        for (int c = 0; c < (l >= 1 ? 3 : 2); c++, xs++, cnt++) {
+          h->xL[xs] = c == 0 ? l : (c == 1 ? l + 1 : l - 1);
+          h->xK[xs] = K;
+          par[xs] = x0;
+          vsh[xs] = c == 0 ? 0 : (c == 1 ? +1 : -1);
+          vloc[xs] = j;
+          for (int k = 0; k < K; k++, xp++) {
+            h->xA[xp] = aBS[p + k];
+            h->xD[xp] = c == 1 ? dBS[p + k] * aBS[p + k] : dBS[p + k]; /* da *= zeta  (src/type2.c:267-269) */
+          }
+        }
+        p += K;
+      }
+      h->xShells[i] = cnt;
+    }
+    opts.screenParent = par;
+    opts.deriv = 1;
+    opts.virtShift = vsh;
+    opts.virtLocal = vloc;
+    h->tab = ecp_tables_build(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, h->xShells, h->xL, h->xK, h->xD,
+                              h->xA, largeGridOrder, tolerance, accuracy, &opts);
+    free(par);
+    free(vsh);
+    free(vloc);
+  } else
+    h->tab = ecp_tables_build(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, shellsBS, lBS, KBS, dBS, aBS,
+                              largeGridOrder, tolerance, accuracy, &opts);
   if (!h->tab) {
     snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: %s", ecp_tables_last_error());
+    free_expanded(h);
     free(h);
     return NULL;
   }
@@ -115,6 +171,7 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
   if (!h->dev) { /* no CPU fallback: fail loudly */
     fprintf(stderr, "libecp_b200: cannot create device context: %s\n", ecpdev_last_error());
     ecp_tables_free(h->tab);
+    free_expanded(h);
     free(h);
     return NULL;
   }
@@ -132,6 +189,7 @@ void libECP_free(libECPHandle *h) {
   if (h->bb2) ecp_batch_free(h->bb2);
   if (h->tab) ecp_tables_free(h->tab);
   free(h->hostBlocks);
+  free_expanded(h);
   free(h);
 }
 
@@ -322,10 +380,11 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
       CallSite call = (CallSite)cb;
       const EcpBatchBuf *bb = cur;
       for (int k = 0; k < bb->nCanon; k++) {
-        const int nb = IJK_DIM(bb->cnLa[k]) * IJK_DIM(bb->cnLb[k]);
+        const int sa = bb->cnShA[k], sb = bb->cnShB[k]; /* blocks of a derivative run have the shifted sizes */
+        const int nb = IJK_DIM(bb->cnLa[k] + sa) * IJK_DIM(bb->cnLb[k] + sb);
         double *blk = h->hostBlocks + bb->cnOut[k];
-        call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], 0, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], 0, bb->cnC[k], blk, args);
-        call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], 0, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], 0, bb->cnC[k], blk + nb, args);
+        call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], sa, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], sb, bb->cnC[k], blk, args);
+        call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], sa, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], sb, bb->cnC[k], blk + nb, args);
       }
     }
   }
@@ -352,6 +411,10 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
     return 0;
   }
   if (!h->dev) return -1;
+  if (h->tab->deriv) { /* the matrix consumer is the n = 0 one-call interface (reference src/getIntegrals.c:78-82) */
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative handles deliver callback blocks only (calculateECPIntegrals)");
+    return -1;
+  }
   unsigned char *owned = owned_rows(h);
   int rc = ecpdev_matrix_begin(h->dev, owned, (long long)h->world * 1000003LL + h->rank);
   free(owned);
@@ -464,7 +527,7 @@ static int host_panels(const libECPHandle *h) {
 }
 int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   const double tCall = now_ms();
-  const int P = (h->empty || !h->dev) ? 1 : host_panels(h);
+  const int P = (h->empty || !h->dev || h->tab->deriv) ? 1 : host_panels(h);
   if (P <= 1) {
     void *dm = NULL;
     const int rc = libecp_b200_integrals_device(h, &dm, NULL);
@@ -649,6 +712,24 @@ long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap) {
         int *r = out + 7 * n;
         r[0] = bb->cnA[k]; r[1] = bb->cnS1[k]; r[2] = bb->cnLa[k]; r[3] = bb->cnB[k];
         r[4] = bb->cnS2[k]; r[5] = bb->cnLb[k]; r[6] = bb->cnC[k];
+      }
+  ecp_batch_free(bb);
+  return n;
+}
+
+/* callback keys of the whole job in call order, one row of 9 ints per executed (shifted) triple - every row stands for
+ * the type-1 and the type-2 callback (A, s1, la, shifta, B, s2, lb, shiftb, C); host only; tests */
+long long libecp_b200_callback_keys(libECPHandle *h, int *out, long long cap) {
+  long long n = 0;
+  int centre = 0;
+  if (h->empty) return 0;
+  EcpBatchBuf *bb = ecp_batch_new(h->tab);
+  while (ecp_batch_build(h->tab, h->geometry, &centre, 1 << 20, h->rank, h->world, 1, 1, bb) > 0)
+    for (int k = 0; k < bb->nCanon; k++, n++)
+      if (n < cap) {
+        int *r = out + 9 * n;
+        r[0] = bb->cnA[k]; r[1] = bb->cnS1[k]; r[2] = bb->cnLa[k]; r[3] = bb->cnShA[k]; r[4] = bb->cnB[k];
+        r[5] = bb->cnS2[k]; r[6] = bb->cnLb[k]; r[7] = bb->cnShB[k]; r[8] = bb->cnC[k];
       }
   ecp_batch_free(bb);
   return n;

@@ -92,7 +92,7 @@ void ecp_batch_free(EcpBatchBuf *bb) {
  
   free(bb->clsFirst); free(bb->clsWork); free(bb->clsElem); free(bb->clsOutElem); free(bb->clsPairBase); free(bb->clsQBase);
   free(bb->cnA); free(bb->cnS1); free(bb->cnB); free(bb->cnS2); free(bb->cnC); free(bb->cnLa); free(bb->cnLb);
-  free(bb->cnOut);
+  free(bb->cnOut); free(bb->cnShA); free(bb->cnShB);
   free_scratch((struct BuilderScratch *)bb->scratch);
   free(bb);
 }
@@ -168,6 +168,19 @@ static double dist3(const double *a, const double *b) { /* src/util.c:109-116 */
   return sqrt(x * x + y * y + z * z);
 }
 
+/* Shift s = 0..3 of a first-derivative run: (+1,0), (-1,0), (0,+1), (0,-1) on (la, lb) (reference src/libecp.c:246-247).
+ * Returns 0 when the reference skips it (:325-330): momentum below zero, or the shifted function sits on the ECP centre
+ * (translational invariance).  *a2 / *b2 = slot offset of the shifted copy behind its unshifted shell: 0, +1 (l + 1),
+ * +2 (l - 1). */
+int ecp_deriv_shift(int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2) {
+  static const int sa[4] = {+1, -1, 0, 0}, sb[4] = {0, 0, +1, -1};
+  const int shifta = sa[s], shiftb = sb[s];
+  if (la < -shifta || lb < -shiftb || (aOnC && shifta) || (bOnC && shiftb)) return 0;
+  *a2 = shifta > 0 ? 1 : (shifta < 0 ? 2 : 0);
+  *b2 = shiftb > 0 ? 1 : (shiftb < 0 ? 2 : 0);
+  return 1;
+}
+
 /* phase (a) for one centre */
 static void centre_screen(const EcpTables *t, const double *geometry, int C, int rank, int world, CentreWork *w) {
   const EcpHostTables *v = &t->v;
@@ -234,7 +247,32 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
   memset(w->clsCount, 0, (nc + 1) * sizeof(int));
   memset(w->clsPairs, 0, (nc + 1) * sizeof(long long));
   long long nTri = 0, outSize = 0;
-  {
+  if (t->deriv) { /* first derivatives: up to four shifted triples per executed shell pair (src/libecp.c:246-250,322-330) */
+    const int *st = w->ssStart, *en = w->ssEnd;
+    const unsigned char *sl = w->ssL, *sk = w->ssK;
+    for (int a = 0; a < nSS; a++) {
+      if (t->virtShift[w->ssShell[a]]) continue;
+      const int A = w->asAtom[w->ssAtom[a]];
+      for (int b = a; b < nSS; b++) {
+        if (t->virtShift[w->ssShell[b]]) continue;
+        const int B = w->asAtom[w->ssAtom[b]];
+        if (A == C && B == C) continue; /* src/libecp.c:305 */
+        const int gs = st[a] > st[b] ? st[a] : st[b];
+        const int ge = en[a] > en[b] ? en[a] : en[b];
+        if (!(gs < ge)) continue;
+        for (int sh = 0; sh < 4; sh++) {
+          int a2, b2;
+          if (!ecp_deriv_shift(sh, sl[a], sl[b], A == C, B == C, &a2, &b2)) continue;
+          const int la = sl[a + a2], lb = sl[b + b2];
+          const int c = t->clsLookup[la][lb][Lc];
+          w->clsCount[c] += 1;
+          w->clsPairs[c] += (long long)sk[a] * sk[b];
+          outSize += 2LL * IJK(la) * IJK(lb);
+          nTri++;
+        }
+      }
+    }
+  } else {
     const int *st = w->ssStart, *en = w->ssEnd;
     const unsigned char *sl = w->ssL, *sk = w->ssK;
     for (int a = 0; a < nSS; a++) {
@@ -407,6 +445,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
     ENSURE(bb->cnB, bb->capCanon, nTR, int); ENSURE(bb->cnS2, bb->capCanon, nTR, int);
     ENSURE(bb->cnC, bb->capCanon, nTR, int); ENSURE(bb->cnLa, bb->capCanon, nTR, int);
     ENSURE(bb->cnLb, bb->capCanon, nTR, int); ENSURE(bb->cnOut, bb->capCanon, nTR, int64_t);
+    ENSURE(bb->cnShA, bb->capCanon, nTR, int); ENSURE(bb->cnShB, bb->capCanon, nTR, int);
     if (nTR > bb->capCanon) bb->capCanon = (int)nTR + 16;
   }
   bb->nCanon = keepCanon ? (int)nTR : 0;
@@ -465,6 +504,51 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
         if (s + 1 < bs[k + 1] && sl[s + 1] != sl[s]) e = s + 1;
         runEnd[s] = e;
       }
+    if (t->deriv) { /* shifted triples in the reference's order: A, B, s1, s2, shift (src/libecp.c:278-330) */
+      static const int sha[4] = {+1, -1, 0, 0}, shb[4] = {0, 0, +1, -1};
+      for (int ka = 0; ka < nblk; ka++)
+      for (int kb = ka; kb < nblk; kb++)
+      for (int a = bs[ka]; a < bs[ka + 1]; a++) {
+        if (t->virtShift[w->ssShell[a]]) continue;
+        const int A = w->asAtom[w->ssAtom[a]];
+        for (int b = (kb == ka ? a : bs[kb]); b < bs[kb + 1]; b++) {
+          if (t->virtShift[w->ssShell[b]]) continue;
+          const int B = w->asAtom[w->ssAtom[b]];
+          if (A == w->C && B == w->C) continue;
+          const int gs = st[a] > st[b] ? st[a] : st[b];
+          const int ge = en[a] > en[b] ? en[a] : en[b];
+          if (!(gs < ge)) continue;
+          for (int sh = 0; sh < 4; sh++) {
+            int a2, b2;
+            if (!ecp_deriv_shift(sh, sl[a], sl[b], A == w->C, B == w->C, &a2, &b2)) continue;
+            const int la = sl[a + a2], lb = sl[b + b2];
+            const int c = t->clsLookup[la][lb][Lc];
+            const long long p = lpos[c]++;
+            bb->trA[p] = sbase + a + a2;
+            bb->trB[p] = sbase + b + b2;
+            bb->trPair[p] = lpair[c];
+            lpair[c] += sk[a] * sk[b];
+            if (needOut) {
+              bb->trOut[p] = out;
+              if (keepCanon) {
+                bb->cnA[cn] = A;
+                bb->cnS1[cn] = t->virtLocal[w->ssShell[a]];
+                bb->cnB[cn] = B;
+                bb->cnS2[cn] = t->virtLocal[w->ssShell[b]];
+                bb->cnC[cn] = w->C;
+                bb->cnLa[cn] = sl[a];
+                bb->cnLb[cn] = sl[b];
+                bb->cnShA[cn] = sha[sh];
+                bb->cnShB[cn] = shb[sh];
+                bb->cnOut[cn] = out;
+                cn++;
+              }
+              out += 2 * (long long)IJK(la) * IJK(lb);
+            }
+          }
+        }
+      }
+    } else
     for (int ka = 0; ka < nblk; ka++) {
       const int ia = bs[ka], ia1 = bs[ka + 1];
       int anyOwn = 0;
@@ -501,6 +585,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
                   bb->cnC[cn] = w->C;
                   bb->cnLa[cn] = la;
                   bb->cnLb[cn] = lb;
+                  bb->cnShA[cn] = bb->cnShB[cn] = 0;
                   bb->cnOut[cn] = out;
                   cn++;
                 }

@@ -22,7 +22,8 @@ typedef struct {
   int capAS, capSS, capTR, capOut;
   /* canonical (reference loop order) list of the executed triples of this batch, for callback replay */
   int nCanon, capCanon;
-  int *cnA, *cnS1, *cnB, *cnS2, *cnC, *cnLa, *cnLb;
+  int *cnA, *cnS1, *cnB, *cnS2, *cnC, *cnLa, *cnLb; /* cnLa / cnLb: the UNSHIFTED momenta (callback arguments)        */
+  int *cnShA, *cnShB;                               /* momentum shifts of a derivative run (0 otherwise)                */
   int64_t *cnOut;
   /* statistics */
   long long nominal, screenedShells;
@@ -41,6 +42,8 @@ void ecp_batch_share_scratch(EcpBatchBuf *dst, EcpBatchBuf *src);
 int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
                     int keepCanon, int wantOut, EcpBatchBuf *bb);
 
+/* shift s = 0..3 of a first-derivative run and whether the reference evaluates it (builder.c) */
+int ecp_deriv_shift(int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2);
 /* exposed for tests: window of one (centre type, shell radius, distance) (reference src/type2.c:148-180) */
 void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip);
 /* owner rank of a shell pair under the multi-GPU partition */

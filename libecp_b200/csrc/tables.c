@@ -675,6 +675,13 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   }
   /* the row deal of a sharded run only needs the basis bookkeeping: valid on a handle without ECP centres too
    * (libecp_b200_owned_rows / _pair_owner are legal there and every rank of a gather asks for them) */
+  if (opts && opts->deriv) {
+    t->deriv = opts->deriv;
+    t->virtShift = malloc((nsh + 1) * sizeof(int));
+    t->virtLocal = malloc((nsh + 1) * sizeof(int));
+    memcpy(t->virtShift, opts->virtShift, nsh * sizeof(int));
+    memcpy(t->virtLocal, opts->virtLocal, nsh * sizeof(int));
+  }
   t->rowDeal = NULL; /* dealt on the first sharded use: ecp_tables_row_deal */
   t->dealL = lBS; t->dealK = KBS; t->dealA = aBS;
   if (v->nTypes == 0) return t; /* no ECP centre: nothing to integrate */
@@ -931,6 +938,7 @@ void ecp_tables_free(EcpTables *t) {
   free(t->fac); free(t->dfac); free(t->cart2sph); free(t->poly2sph); free(t->omega); free(t->binom);
   free(t->shTermOff); free(t->shTermP); free(t->shTermD); free(t->shTermBin);
   free(t->ijk); free(t->ijkIndex);
+  free(t->virtShift); free(t->virtLocal);
   free(t->small_x); free(t->small_w); free(t->small_rs); free(t->small_ws); free(t->small_oidx);
   free(t->large_x); free(t->large_w); free(t->large_xs); free(t->large_ws); free(t->large_oidx);
   free(t->besselK); free(t->besselT); free(t->besselC);

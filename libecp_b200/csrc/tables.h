@@ -38,6 +38,11 @@ typedef struct {
   const int *dealL, *dealK; /* borrowed basis arrays the deal is computed from (the handle borrows them anyway) */
   const double *dealA;
   int *atomMaxL, *atomFirstShell;
+  /* derivative runs (scope row f1): the shell list is the expanded one - every shell of the caller's basis is followed
+   * by its copies at l + 1 (coefficients d zeta, reference src/type1.c:239-246, src/type2.c:263-269,459-462) and, for
+   * l >= 1, at l - 1 (src/libecp.c:246-250) */
+  int deriv;
+  int *virtShift, *virtLocal;
   /* ECP */
   int *atomType; /* per atom: type index or -1 */
   EcpType *types;
@@ -58,6 +63,10 @@ typedef struct {
   /* derivative runs (api.c): the basis handed in is the expanded list of shifted shells; screenParent[s] = the shell
    * whose radius screens shell s (the unshifted one, reference src/type2.c:251); NULL = every shell screens itself */
   const int *screenParent;
+  /* derivative order of the run (0 or 1) and, per shell of the expanded list, its momentum shift (0, +1, -1) and the
+   * position of its unshifted shell among the shells of the atom in the caller's basis (callback argument s1 / s2) */
+  int deriv;
+  const int *virtShift, *virtLocal;
 } EcpBuildOpts;
 
 /* returns NULL on unsupported shape / Bessel series failure (reference: src/libecp.c:159-162,181-185) */

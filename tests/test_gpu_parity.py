@@ -427,3 +427,53 @@ def test_custom_shell_ordering_too_short_is_rejected():
     """reference src/libecp.c:159-162: lmax < maxLambda + maxAlpha + 1 -> NULL"""
     with pytest.raises(RuntimeError):
         capi.Handle(synth.cfg2(), ordering=synth.shell_order(9, "reversed"), lmax=9)
+
+
+@pytest.mark.parametrize("name,lbs,L", [("deriv1_tz2_L4", 2, 4), ("deriv1_tz3_L5", 3, 5)])
+def test_first_derivative_blocks_match_golden(name, lbs, L):
+    """scope row f1: derivative order n = 1 - the shifted-momentum blocks handed to the callback
+    (reference src/libecp.c:246-250,322-373; zeta factors src/type1.c:239-246, src/type2.c:263-269,459-462) vs the
+    blocks of the compiled reference, same key sequence, same tolerance"""
+    keys, off, vals = load_blocks(name)
+    with capi.Handle(synth.deriv_pair(lbs, L), n=1) as h:
+        rc, recs = h.callbacks()
+        with pytest.raises(RuntimeError):
+            h.integrals_host()  # the matrix consumer is the n = 0 one-call interface
+    assert rc == 0 and len(recs) == len(keys)
+    for k, r in enumerate(recs):
+        assert tuple(keys[k]) == r[:9]
+        assert len(r[9]) == off[k + 1] - off[k]
+    assert_parity(np.concatenate([r[9] for r in recs]), vals, name)
+
+
+def test_first_derivative_is_the_gradient_of_the_integrals():
+    """size-independent property of row f1: d/dA <a|U_C|b> assembled from the shifted blocks,
+    2 zeta <a+1|U|b> - a <a-1|U|b> per Cartesian direction, equals the central finite difference of the n = 0 blocks
+    when atom A moves (one s-p pair of a two-atom system, h = 1e-4 bohr)"""
+    base = synth.deriv_pair(2, 4)
+
+    def blocks(s, n):
+        with capi.Handle(s, n=n) as h:
+            rc, recs = h.callbacks()
+        assert rc == 0
+        return recs
+
+    recs = blocks(base, 1)
+    # shell 0 of atom 0 (s, K = 2) with shell 6 of atom 1 (first p shell), centre C = 1: d/dA_x of the s function
+    # = 2 zeta * (p_x function with the same exponents): the +1 block holds coefficients d zeta, so grad = 2 * block
+    tgt = [r for r in recs if r[:9] == (0, 0, 0, 1, 1, 6, 1, 0, 1)]
+    assert len(tgt) == 2
+    grad = 2.0 * (tgt[0][9] + tgt[1][9]).reshape(3, 3)  # rows: direction x, y, z of the shifted p function
+    h = 1e-4
+    fd = np.zeros((3, 3))
+    for d in range(3):
+        vals = []
+        for sgn in (+1, -1):
+            s = dict(base)
+            g = base["geometry"].copy()
+            g[d] += sgn * h
+            s["geometry"] = g
+            r0 = [r for r in blocks(s, 0) if r[:9] == (0, 0, 0, 0, 1, 6, 1, 0, 1)]
+            vals.append((r0[0][9] + r0[1][9]).reshape(1, 3)[0])
+        fd[d] = (vals[0] - vals[1]) / (2 * h)
+    assert np.allclose(grad, fd, rtol=1e-6, atol=1e-9)

@@ -83,7 +83,7 @@ def test_no_cpu_fallback_without_device():
 def test_unsupported_arguments_rejected():
     s = synth.cfg2()
     with pytest.raises(RuntimeError):
-        capi.Handle(s, n=1, tables_only=True)  # derivatives: SURVEY §8f, not built yet
+        capi.Handle(s, n=2, tables_only=True)  # second derivatives: the reference's own output is NaN (make_golden.py)
     bad = synth.assemble("bad", [(0, 0, 0)], [synth.tz_basis(5)], [synth.ecp_set(3)])  # maxLBS > L+1
     with pytest.raises(RuntimeError):
         capi.Handle(bad, tables_only=True)
@@ -525,8 +525,8 @@ def test_sharding_queries_on_a_handle_without_ecp_centres():
 
 def test_init_rejections_carry_their_own_message():
     s = synth.cfg2()
-    with pytest.raises(RuntimeError, match="derivative order n=1"):
-        capi.Handle(s, n=1, tables_only=True)
+    with pytest.raises(RuntimeError, match="derivative order n=2"):
+        capi.Handle(s, n=2, tables_only=True)
     # g shells under an L = 2 potential: outside the compiled-in shape domain, rejected with the shape in the message
     bad = synth.assemble("bad", [(0.0, 0.0, 0.0)], [synth.tz_basis(4)], [synth.ecp_set(2)])
     with pytest.raises(RuntimeError, match="unsupported shape: max l of the basis 4, max L of the ECPs 2"):
@@ -599,3 +599,20 @@ def test_custom_shell_ordering_tables():
         bad = synth.shell_order(lmax, "libint").copy()
         bad[3:6] = bad[6:9]
         capi.Handle(s, tables_only=True, ordering=bad, lmax=lmax)
+
+
+DERIV = {"deriv1_tz2_L4": (2, 4), "deriv1_tz3_L5": (3, 5)}
+
+
+@pytest.mark.parametrize("name", list(DERIV))
+def test_derivative_callback_keys_match_reference(name):
+    """scope row f1, host part: the (shifted) triples of a first-derivative run and their call order
+    (A,s1,la,shifta,B,s2,lb,shiftb,C) are the reference's (src/libecp.c:246-250,297-330); the tables have the sizes the
+    reference derives from maxLBS + n (src/libecp.c:143-147)"""
+    d = np.load(os.path.join(GOLDEN, f"{name}_blocks.npz"))
+    lbs, L = DERIV[name]
+    with capi.Handle(synth.deriv_pair(lbs, L), n=1, tables_only=True) as h:
+        keys = h.callback_keys()
+        dims = h.host_itable("dims")
+    assert np.array_equal(keys, d["keys"][0::2]) and np.array_equal(keys, d["keys"][1::2])
+    assert dims[1] == lbs + 1 and dims[2] == lbs + 1 and dims[3] == L - 1 + lbs + 1
