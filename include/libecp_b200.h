@@ -109,6 +109,12 @@ double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches)
 void libecp_b200_set_tables_only(int on);
 /* last batch's device intermediates, tests only: "F" "omegaX" "T" "gamma" "chi" "Q" */
 int libecp_b200_debug_fetch(libECPHandle *h, const char *what, double *dst, long long n);
+/* tests only: the per-point device functions of the kernels run on the GPU on caller-supplied arguments -
+ * "bessel" (weightedBesselFunction, src/bessel.c:101-199), "rsh" (realSphericalHarmonics, src/spherical_harmonics.c:15-114),
+ * "ps93" (integrateGC_PS93 on slot-ordered tables, src/gc_integrators.c:156-217), "pot" (evalECP, src/ecp.c:46-60);
+ * argument layout in csrc/ecp_cuda.cu (k_unit) */
+int libecp_b200_debug_unit(libECPHandle *h, const char *what, int n, const double *in, long long nin, const int *ipar, int npar,
+                           double *out, long long nout);
 
 /* measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator for bench.py) */
 double libecp_b200_fp64_peak(int device, int iters);

@@ -28,6 +28,7 @@ EXPORTS = [
     "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only", "libecp_b200_owned_rows", "libecp_b200_pack_rows", "libecp_b200_unpack_rows",
     "libecp_b200_matrix_ptr", "libecp_b200_comm_unique_id", "libecp_b200_comm_init", "libecp_b200_comm_attach",
     "libecp_b200_allgather", "libecp_b200_device_sync", "libecp_b200_comm_free", "libecp_b200_callback_keys",
+    "libecp_b200_debug_unit",
 ]
 
 
@@ -248,6 +249,17 @@ class Handle:
         if rc:
             raise RuntimeError("not an ECP centre")
         return endl[:L], st, en, sk
+
+    def unit(self, what, n, inp, ipar, nout):
+        """tests: run a per-point device function on the GPU (include/libecp_b200.h: libecp_b200_debug_unit)"""
+        f = lib().libecp_b200_debug_unit
+        f.argtypes = [C.c_void_p, C.c_char_p, C.c_int, _pd, C.c_longlong, _pi, C.c_int, _pd, C.c_longlong]
+        inp = np.ascontiguousarray(inp, np.float64)
+        ipar = np.ascontiguousarray(ipar, np.int32)
+        out = np.zeros(nout)
+        if f(C.c_void_p(self.h), what.encode(), int(n), _p(inp, _pd), inp.size, _p(ipar, _pi), ipar.size, _p(out, _pd), nout):
+            raise RuntimeError("debug_unit failed: " + (lib().libecp_b200_last_error() or b"").decode())
+        return out
 
     def callback_keys(self):
         """(A,s1,la,shifta,B,s2,lb,shiftb,C) of every executed (shifted) triple in call order (host only)"""

@@ -755,6 +755,11 @@ double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches)
   return ms;
 }
 
+int libecp_b200_debug_unit(libECPHandle *h, const char *what, int n, const double *in, long long nin, const int *ipar, int npar,
+                           double *out, long long nout) {
+  if (!h || h->empty || !h->dev) return -1;
+  return ecpdev_unit(h->dev, what, n, in, nin, ipar, npar, out, nout) ? -1 : 0;
+}
 int libecp_b200_debug_fetch(libECPHandle *h, const char *what, double *dst, long long n) {
   if (h->empty || !h->dev) return -1;
   return ecpdev_debug_fetch(h->dev, what, dst, n);

@@ -2302,6 +2302,66 @@ extern "C" int ecpdev_debug_fetch(EcpDev *d, const char *what, double *dst, int6
   return 0;
 }
 
+/* ---- device-side unit entry points (tests only): the per-point math of the kernels run on the GPU on caller-supplied
+ * arguments, so that the GPU tier can compare primitives - not only end results - with the oracle:
+ *   "bessel": in = n x z, ipar[0] = lmax                          -> out = n x (lmax + 1)   weighted Bessel functions
+ *   "rsh"   : in = n x (theta, phi), ipar[0] = lmax               -> out = n x (lmax + 1)^2 real spherical harmonics
+ *   "ps93"  : in = n x 3 rows of 384 slot-ordered doubles (Fa, Fb, U), ipar = n x (start, end)
+ *                                                                  -> out = n x (result, rc, points)
+ *   "pot"   : in = n x r, ipar[0] = ECP type, ipar[1] = l         -> out = n x U_l(r)
+ * One thread per item; the same device functions the kernels call (ecp_math.h). */
+__global__ void k_unit(DevT t, int what, int n, const double *in, const int *ipar, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (what == 0) {
+    const int lmax = ipar[0];
+    double K[ECP_KMAX + 1];
+#pragma unroll
+    for (int l = 0; l <= ECP_KMAX; l++) K[l] = 0.0;
+    ecp_bessel<ECP_KMAX>(t.besselT, t.besselStride, t.besselC, lmax, in[i], K);
+#pragma unroll
+    for (int l = 0; l <= ECP_KMAX; l++)
+      if (l <= lmax) out[(size_t)i * (lmax + 1) + l] = K[l];
+  } else if (what == 1) {
+    const int lmax = ipar[0];
+    ecp_rsh(lmax, in[2 * i], in[2 * i + 1], t.fac, t.dfac, out + (size_t)i * (lmax + 1) * (lmax + 1));
+  } else if (what == 2) {
+    const double *Fa = in + (size_t)i * 3 * ECP_SMALL_SLOTS, *Fb = Fa + ECP_SMALL_SLOTS, *U = Fb + ECP_SMALL_SLOTS;
+    double res = 0.0;
+    int np = 0;
+    const int rc = ecp_ps93_fastT(Fa, 1, Fb, 1, U, 1, c_small_w, &t.sm, t.small_jL, t.small_jR, ipar[2 * i], ipar[2 * i + 1],
+                                  t.tolerance, &res, &np);
+    out[3 * i] = res;
+    out[3 * i + 1] = rc;
+    out[3 * i + 2] = np;
+  } else if (what == 3) {
+    const int type = ipar[0], l = ipar[1];
+    out[i] = ecp_pot_eval(t.gaussL, t.gaussN, t.gaussD, t.gaussA, t.typeGaussOff[type], t.typeGaussOff[type + 1], l, in[i]);
+  }
+}
+extern "C" int ecpdev_unit(EcpDev *d, const char *what, int n, const double *in, int64_t nin, const int *ipar, int npar,
+                           double *out, int64_t nout) {
+  CK(cudaSetDevice(d->device));
+  const int w = !strcmp(what, "bessel") ? 0 : (!strcmp(what, "rsh") ? 1 : (!strcmp(what, "ps93") ? 2 : (!strcmp(what, "pot") ? 3 : -1)));
+  if (w < 0 || n <= 0) return -1;
+  double *din = NULL, *dout = NULL;
+  int *dpar = NULL;
+  CK(cudaMalloc(&din, (size_t)nin * sizeof(double)));
+  CK(cudaMalloc(&dout, (size_t)nout * sizeof(double)));
+  CK(cudaMalloc(&dpar, (size_t)(npar > 0 ? npar : 1) * sizeof(int)));
+  CK(cudaMemcpy(din, in, (size_t)nin * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dpar, ipar, (size_t)npar * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0, (size_t)nout * sizeof(double)));
+  k_unit<<<(n + 63) / 64, 64, 0, d->s1>>>(d->t, w, n, din, dpar, dout);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(d->s1));
+  CK(cudaMemcpy(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(din);
+  cudaFree(dout);
+  cudaFree(dpar);
+  return 0;
+}
+
 extern "C" double ecpdev_fp64_peak_probe(int device, int iters) {
   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
   int nsm = 0;

@@ -155,6 +155,9 @@ long long ecpdev_table_bytes(EcpDev *d);
 void ecpdev_set_serial(EcpDev *d, int on);
 /* debug access to the intermediates of the last batch (tests only): "F" "omegaX" "T" "gamma" "chi" "Q" "tfail" */
 int ecpdev_debug_fetch(EcpDev *d, const char *what, double *dst, int64_t n);
+/* tests only: run a per-point device function on the GPU ("bessel" "rsh" "ps93" "pot"; ecp_cuda.cu: k_unit) */
+int ecpdev_unit(EcpDev *d, const char *what, int n, const double *in, int64_t nin, const int *ipar, int npar, double *out,
+                int64_t nout);
 /* FP64 FMA peak probe used by bench.py for the roofline denominator: returns TFLOP/s */
 double ecpdev_fp64_peak_probe(int device, int iters);
 

@@ -56,6 +56,21 @@ ECP_HD int ecp_cidx(int l, int c) { return ecp_cd(l - 1) + c; }
  * per step).  The correction terms carry factors dz^i / i! <= 5e-3, so this moves K by far less than one ulp of K
  * (the result is the reference's double in all but rare rounding-boundary cases, where it differs by one ulp).
  * ---------------------------------------------------------------------------------------------- */
+/* a / B for a small integer constant B, correctly rounded, in three instructions instead of the division routine
+ * (Markstein: y = RN(1/B), q = RN(a y) is within one ulp of a / B, r = a - B q is exact in an fma, RN(q + r y) = RN(a / B)
+ * for every a whose quotient is a normal number; B = 3, 5, 100 have no all-ones significand).  The node abscissa
+ * index / 100 (src/bessel.c:143) and the series factors dz^i / i! (:170) keep the reference's doubles
+ * (tests/test_host.py::test_device_math_bessel_rsh_bitwise sweeps all three branches).  Together with the recurrence
+ * factors C_j = j / (2j + 1) as immediates instead of 35 loads per evaluation: type-1 1.13 -> 0.99 ms, fallback 0.94 ->
+ * 0.83 ms on Au20, results unchanged bit for bit (profiles/r2/README.md). */
+template <int B>
+ECP_HD double ecp_div_const(double a) {
+  const double y = 1.0 / B;
+  const double q = a * y;
+  const double r = fma(-(double)B, q, a);
+  return fma(r, y, q);
+}
+
 template <int KM>
 ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double *__restrict__ Cj, int lmax, double z,
                       double (&K)[KM + 1]) {
@@ -75,7 +90,7 @@ ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double 
     double d[KM + 6];
     const int maxL = lmax + 5;
     const int index = (int)floor(ECP_ADD_RN(ECP_MUL_RN(z, 100.0), 0.5));
-    const double dz = z - index / 100.0;
+    const double dz = z - ecp_div_const<100>((double)index);
     const double *row = tabT + (size_t)index * stride;
     double scale = 1.0;
 #pragma unroll
@@ -91,11 +106,11 @@ ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double 
       for (int j = 1; j <= KM + 5 - i; j++) {
         if (j <= top) {
           const double cur = d[j];
-          d[j] = fma(Cj[j], prev - d[j + 1], d[j + 1] - cur);
+          d[j] = fma((double)j / (2.0 * j + 1.0), prev - d[j + 1], d[j + 1] - cur); /* C_j as an immediate */
           prev = cur;
         }
       }
-      scale = scale * dz / i;
+      scale = (i == 1) ? scale * dz : ((i == 2) ? scale * dz * 0.5 : ((i == 4) ? scale * dz * 0.25 : (i == 3 ? ecp_div_const<3>(scale * dz) : ecp_div_const<5>(scale * dz))));
 #pragma unroll
       for (int j = 0; j <= KM; j++)
         if (j <= lmax) K[j] = fma(scale, d[j], K[j]);
@@ -145,7 +160,7 @@ ECP_HD int ecp_bessel_mem(const double *__restrict__ tabT, int stride, const dou
   } else if (z < 16.0) {
     const int maxL = lmax + 5;
     const int index = (int)floor(ECP_ADD_RN(ECP_MUL_RN(z, 100.0), 0.5));
-    const double dz = z - index / 100.0;
+    const double dz = z - ecp_div_const<100>((double)index);
     const double *row = tabT + (size_t)index * stride;
     double scale = 1.0;
     for (int l = 0; l <= maxL; l++) {
@@ -158,7 +173,7 @@ ECP_HD int ecp_bessel_mem(const double *__restrict__ tabT, int stride, const dou
       double prev = d[0], next = d[1];
       const double d0 = next - prev;
       d[0] = d0;
-      scale = scale * dz / i;
+      scale = (i == 1) ? scale * dz : ((i == 2) ? scale * dz * 0.5 : ((i == 4) ? scale * dz * 0.25 : (i == 3 ? ecp_div_const<3>(scale * dz) : ecp_div_const<5>(scale * dz))));
       K[0] = fma(scale, d0, K[0]);
       for (int j = 1; j <= top; j++) {
         const double cur = next;

@@ -459,9 +459,9 @@ def test_first_derivative_is_the_gradient_of_the_integrals():
         return recs
 
     recs = blocks(base, 1)
-    # shell 0 of atom 0 (s, K = 2) with shell 6 of atom 1 (first p shell), centre C = 1: d/dA_x of the s function
+    # shell 5 of atom 0 (the most diffuse s) with shell 6 of atom 1 (first p shell), centre C = 1: d/dA_x of the s function
     # = 2 zeta * (p_x function with the same exponents): the +1 block holds coefficients d zeta, so grad = 2 * block
-    tgt = [r for r in recs if r[:9] == (0, 0, 0, 1, 1, 6, 1, 0, 1)]
+    tgt = [r for r in recs if r[:9] == (0, 5, 0, 1, 1, 6, 1, 0, 1)]
     assert len(tgt) == 2
     grad = 2.0 * (tgt[0][9] + tgt[1][9]).reshape(3, 3)  # rows: direction x, y, z of the shifted p function
     h = 1e-4
@@ -473,7 +473,7 @@ def test_first_derivative_is_the_gradient_of_the_integrals():
             g = base["geometry"].copy()
             g[d] += sgn * h
             s["geometry"] = g
-            r0 = [r for r in blocks(s, 0) if r[:9] == (0, 0, 0, 0, 1, 6, 1, 0, 1)]
+            r0 = [r for r in blocks(s, 0) if r[:9] == (0, 5, 0, 0, 1, 6, 1, 0, 1)]
             vals.append((r0[0][9] + r0[1][9]).reshape(1, 3)[0])
         fd[d] = (vals[0] - vals[1]) / (2 * h)
     assert np.allclose(grad, fd, rtol=1e-6, atol=1e-9)
