@@ -57,6 +57,11 @@ struct DevT {
   const int16_t *small_slotOf; /* original index -> slot (inverse of small_oidx) */
   const unsigned char *small_jL, *small_jR; /* first in-window pair per (level, start) / (level, end), ecp_math.h */
   const double *besselT, *besselC;
+  /* non-zero entries of poly2sph per monomial, in the order k_chi adds them (l = N, N-2, ...; m ascending): position
+   * in the packed R of the monomial's degree, bit 15 set on the last entry of an l group; ~25 % of the dense rows */
+  const int *p2sOff;
+  const unsigned short *p2sIdx;
+  const double *p2sVal;
   const int *shellL, *shellK, *shellPrim, *shellAtom, *shellAO, *atomMaxL;
   const double *primD, *primA;
   const int *typeL, *typeGaussOff, *gaussL;
@@ -811,13 +816,19 @@ __global__ void __launch_bounds__(128) k_chi(DevT t, DevB b, int rStride) {
       const int i = pq / cdb, j = pq - i * cdb;
       const int *ei = t.ijk + 3 * i, *ej = t.ijk + 3 * j;
       const int lx = ei[0] + ej[0], ly = ei[1] + ej[1], lz = ei[2] + ej[2], N = lx + ly + lz;
-      const double *PM = t.poly2sph + (size_t)t.ijkIndex[lx * D * D + ly * D + lz] * t.pcols;
-      double chi = 0.0;
-      for (int l = N; l >= 0; l -= 2) {
-        const double *pm = PM + l * l, *r = R + chi_roff(N, l);
-        double f = 0.0;
-        for (int m = 0; m < 2 * l + 1; m++) f = fma(pm[m], r[m], f);
-        chi += f;
+      (void)N;
+      /* only the non-zero poly2sph entries of the monomial (a zero entry adds an exact zero: same value); the sums over
+       * m of one l are closed into chi at the flagged entry, as the dense loop nest did (src/type1.c:283-291) */
+      const int mono = t.ijkIndex[lx * D * D + ly * D + lz];
+      const int k1 = t.p2sOff[mono + 1];
+      double chi = 0.0, f = 0.0;
+      for (int k = t.p2sOff[mono]; k < k1; k++) {
+        const unsigned ix = t.p2sIdx[k];
+        f = fma(t.p2sVal[k], R[ix & 0x7fffu], f);
+        if (ix & 0x8000u) {
+          chi += f;
+          f = 0.0;
+        }
       }
       out[pq] = chi;
     }
@@ -1099,6 +1110,37 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   t.shTermP = upload_const(d, h->shTermP, h->nShTerms);
   t.shTermD = upload_const(d, h->shTermD, h->nShTerms);
   t.shTermBin = upload_const(d, h->shTermBin, h->nShTerms);
+  { /* sparse form of poly2sph for k_chi: a monomial x^a y^b z^c only has components of matching parities */
+    const int pc = t.pcols;
+    int *off = (int *)malloc((size_t)(cdT + 1) * sizeof(int));
+    unsigned short *idx = (unsigned short *)malloc((size_t)cdT * pc * sizeof(unsigned short));
+    double *val = (double *)malloc((size_t)cdT * pc * sizeof(double));
+    int n = 0;
+    for (int p = 0; p < cdT; p++) {
+      const int N = h->ijk[3 * p] + h->ijk[3 * p + 1] + h->ijk[3 * p + 2];
+      off[p] = n;
+      for (int l = N; l >= 0; l -= 2) {
+        int last = -1;
+        for (int m = 0; m < 2 * l + 1; m++) {
+          const double v = h->poly2sph[(size_t)p * pc + l * l + m];
+          if (v != 0.0) {
+            idx[n] = (unsigned short)(N * (N + 1) * (N + 2) / 6 + l * (l - 1) / 2 + m); /* chi_roff(N, l) + m */
+            val[n] = v;
+            last = n++;
+          }
+        }
+        if (last >= 0) idx[last] |= 0x8000u;
+      }
+    }
+    off[cdT] = n;
+    t.p2sOff = upload_const(d, off, (size_t)cdT + 1);
+    t.p2sIdx = upload_const(d, idx, (size_t)(n > 0 ? n : 1));
+    t.p2sVal = upload_const(d, val, (size_t)(n > 0 ? n : 1));
+    cudaStreamSynchronize(d->s1);
+    free(off);
+    free(idx);
+    free(val);
+  }
   t.ijk = upload_const(d, h->ijk, (size_t)3 * cdT);
   t.ijkIndex = upload_const(d, h->ijkIndex, (size_t)h->ijkDim * h->ijkDim * h->ijkDim);
   t.small_r = upload_const(d, h->small_r, ECP_SMALL_SLOTS);
@@ -2000,9 +2042,16 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   CK(cudaEventRecord(d->ev[4], d->s1));
   CK(cudaStreamWaitEvent(d->s1, d->ev[8], 0));
   if (d->shift2) { /* both shift passes in one kernel, blocks of consecutive triples of one class (k_shift2) */
-    int clsBlk[2 * ECP_MAX_CLASSES + 2]; /* first block of every class, then its chunks per block */
-    size_t smemMax = 0;
-    clsBlk[0] = 0;
+    /* One launch per shared-memory bucket: the dynamic shared memory of a launch is that of its largest class, and with
+     * a single launch the f-f classes (tens of KB per block) held every block - also those of the s and p classes that
+     * make up most triples - at 4 resident blocks per SM (ncu: 24 % of the warp slots in use, profiles/r2).  Per bucket:
+     * first block of every class (classes of other buckets are empty), then the chunks per block of every class. */
+    enum { NBK = 3 };
+    const size_t bucketCap[NBK] = {14 * 1024, 40 * 1024, 200 * 1024};
+    const int stride = 2 * nc + 2;
+    int clsBlk[NBK][2 * ECP_MAX_CLASSES + 2];
+    size_t smemMax[NBK] = {0, 0, 0};
+    for (int k = 0; k < NBK; k++) clsBlk[k][0] = 0;
     for (int c = 0; c < nc; c++) {
       const int la = d->hClsLa[c], lb = d->hClsLb[c];
       const int ntri = h->clsFirst[c + 1] - h->clsFirst[c];
@@ -2010,22 +2059,30 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
       /* chunks per block: the per-block tables are paid once per block, but a small class must still fill the device */
       long long ch = ntri / ((long long)tpb * d->nSM * 4);
       ch = ch < 1 ? 1 : (ch > SHIFT2_CH ? SHIFT2_CH : ch);
-      clsBlk[nc + 1 + c] = (int)ch;
-      clsBlk[c + 1] = clsBlk[c] + (int)((ntri + tpb * ch - 1) / (tpb * ch));
-      if (ntri > 0) {
-        Shift2Layout L;
-        const size_t sm = shift2_smem(la, lb, d->hShTerms[la], d->hShTerms[lb], tpb, &L);
-        if (sm > smemMax) smemMax = sm;
+      Shift2Layout L;
+      const size_t sm = shift2_smem(la, lb, d->hShTerms[la], d->hShTerms[lb], tpb, &L);
+      int bk = 0;
+      while (bk < NBK - 1 && sm > bucketCap[bk]) bk++;
+      for (int k = 0; k < NBK; k++) {
+        clsBlk[k][nc + 1 + c] = (int)ch;
+        clsBlk[k][c + 1] = clsBlk[k][c] + ((k == bk) ? (int)((ntri + tpb * ch - 1) / (tpb * ch)) : 0);
       }
+      if (ntri > 0 && sm > smemMax[bk]) smemMax[bk] = sm;
     }
-    int rc_ = ensure(&d->clsJ, (2 * nc + 2) * sizeof(int));
+    int rc_ = ensure(&d->clsJ, (size_t)NBK * stride * sizeof(int));
     if (rc_) return rc_;
-    CK(cudaMemcpyAsync(d->clsJ.p, clsBlk, (2 * nc + 1) * sizeof(int), cudaMemcpyHostToDevice, d->s1));
-    if (smemMax > 48 * 1024 && !d->shift2Attr) {
+    for (int k = 0; k < NBK; k++)
+      CK(cudaMemcpyAsync((int *)d->clsJ.p + k * stride, clsBlk[k], (2 * nc + 1) * sizeof(int), cudaMemcpyHostToDevice, d->s1));
+    if (smemMax[NBK - 1] > 48 * 1024 && !d->shift2Attr) {
       CK(cudaFuncSetAttribute(k_shift2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       d->shift2Attr = 1;
     }
-    if (clsBlk[nc] > 0) k_shift2<<<clsBlk[nc], 128, smemMax, d->s1>>>(t, B, (const int *)d->clsJ.p, flags);
+    for (int k = 0; k < NBK; k++)
+      if (clsBlk[k][nc] > 0) {
+        k_shift2<<<clsBlk[k][nc], 128, smemMax[k], d->s1>>>(t, B, (const int *)d->clsJ.p + k * stride, flags);
+        launches++;
+      }
+    launches -= 2; /* counted below */
   } else
   { /* binomial shift in two passes (ecp_shift.cuh); J[type][c1][q] per triple goes through a scratch buffer */
     long long clsJ[ECP_MAX_CLASSES + 1];

@@ -28,10 +28,13 @@ def test_device_bessel_matches_oracle_on_all_branches():
             for i, z in enumerate(zs):
                 o.L.oracle_bessel(C.c_void_p(o.h), lmax, float(z), _p(ref[i], _pd))
             taylor = (zs >= 1e-7) & (zs < 16.0)
-            # small-z and asymptotic branches: plain arithmetic in the reference's order, no library call -> bit-identical;
-            # Taylor branch: fma in the derivative recurrence (ecp_math.h): a few ulp, or < 1e-24 absolute for the tiny
-            # high orders at small z
-            assert np.array_equal(got[~taylor], ref[~taylor]), lmax
+            # small-z branch: products and exact small-integer divisions only -> within an ulp or two; asymptotic branch
+            # (z >= 16): the alternating sum R_l(-z) cancels (sum of |terms| / |result| up to ~1e3 at l = 10, z = 16)
+            # and the device contracts K += f A[i] into an fma -> relative 1e-12; Taylor branch: fma in the derivative
+            # recurrence (ecp_math.h): a few ulp, or < 1e-24 absolute for the tiny high orders at small z
+            small, asym = zs < 1e-7, zs >= 16.0
+            assert np.all(np.abs(got[small] - ref[small]) <= 2 * np.spacing(np.abs(ref[small]))), lmax
+            assert np.all(np.abs(got[asym] - ref[asym]) <= 2e-12 * np.abs(ref[asym])), lmax
             assert np.all(np.abs(got[taylor] - ref[taylor]) <= 8 * np.spacing(np.abs(ref[taylor])) + 1e-24), lmax
             exact = np.all(np.abs(got[taylor] - ref[taylor]) <= np.spacing(np.abs(ref[taylor])), axis=1)
             assert exact.mean() > 0.9
