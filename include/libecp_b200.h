@@ -102,7 +102,9 @@ long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap);
 /* callback keys of the whole job in call order, rows (A,s1,la,shifta,B,s2,lb,shiftb,C), one row per executed (shifted)
  * triple = one type-1 and one type-2 callback (reference src/libecp.c:372); host only */
 long long libecp_b200_callback_keys(libECPHandle *h, int *out, long long cap);
-/* Wall time (ms) of the host batch builder alone over one pass (no device work); optional totals. */
+/* Wall time (ms) of the host batch builder alone over one pass (no device work); optional totals.  By default this is
+ * what a matrix run leaves to the host - screening and slot layout; *triples then counts the shell pairs (owned a, b >= a)
+ * handed to the device enumeration.  With LIBECP_B200_ENUM=host: the full host enumeration and the executed triples. */
 double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches);
 /* test hook: handles created afterwards build tables + batches only (no device); compute entry points
  * then fail with -1.  Used by the CPU-only test tier; never a compute fallback. */

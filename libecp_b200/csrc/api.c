@@ -32,6 +32,7 @@ struct _libECPHandle {
   long long maxTriples;
   double *hostBlocks;
   size_t hostBlocksCap;
+  double triPerPair; /* executed triples per tested shell pair, measured on the batches run so far (device enumeration) */
   /* derivative runs: the expanded shell list the tables borrow (libECP_init) */
   int *xShells, *xL, *xK;
   double *xD, *xA;
@@ -238,14 +239,21 @@ typedef struct {
   int *centre;
   int keepCanon, took;
   int flags, slot, prefetch; /* prefetch: start the H2D of the finished batch into input set `slot` */
+  int devEnum;               /* screening only; the device enumerates the triples */
   long long maxTriples;      /* size target of this batch */
   double ms;
 } BuildJob;
 static void build_job(BuildJob *j) {
   const double t0 = now_ms();
   if (j->h->dev) ecpdev_bind_thread(j->h->dev);
-  j->took = ecp_batch_build(j->h->tab, j->h->geometry, j->centre, j->maxTriples, j->h->rank, j->h->world, j->keepCanon,
-                            (j->flags & 2) != 0, j->bb);
+  /* matrix runs: the host only screens, the device enumerates the triples (ecp_enum.cuh); runs that deliver callback
+   * blocks keep the host enumeration (the replay needs the canonical list) */
+  if (j->devEnum) {
+    j->bb->triPerPair = j->h->triPerPair;
+    j->took = ecp_batch_build_slots(j->h->tab, j->h->geometry, j->centre, j->maxTriples, j->h->rank, j->h->world, j->bb);
+  } else
+    j->took = ecp_batch_build(j->h->tab, j->h->geometry, j->centre, j->maxTriples, j->h->rank, j->h->world, j->keepCanon,
+                              (j->flags & 2) != 0, j->bb);
   j->ms = now_ms() - t0;
   if (j->prefetch && j->took > 0 && j->h->dev) ecpdev_prefetch_batch(j->h->dev, &j->bb->b, j->flags, j->slot);
 }
@@ -337,7 +345,11 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
   /* Batch size: the builder works one batch ahead of the GPU, so the first batch of a pass is built with the GPU idle
    * and is kept small; a rank of a sharded run owns 1/world of the triples and takes smaller batches so that its pass
    * still has enough of them to pipeline (below ~0.5 M triples the per-batch launches and kernel tails start to show). */
-  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, flags, 0, 0, pass_batch_size(h, 0), 0.0};
+  BuildJob job = {h, bufs[0], &centre, cb != NULL, 0, flags, 0, 0, 0, pass_batch_size(h, 0), 0.0};
+  {
+    const char *e = getenv("LIBECP_B200_ENUM"); /* =host: the host builder enumerates the triples of matrix runs too */
+    job.devEnum = (flags == 1) && !h->tab->deriv && !(e && !strcmp(e, "host"));
+  }
   build_job(&job); /* first batch: nothing to overlap with */
   if (getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] first batch built in %.1f ms\n", job.ms);
   if (!h->worker) h->worker = worker_new();
@@ -352,7 +364,7 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     job.maxTriples = pass_batch_size(h, i + 1); /* ramp: the GPU must not wait for a full-size build behind a small batch */
     job.prefetch = threaded;
     if (threaded) worker_post(h->worker, &job);
-    const EcpBatch *b = &cur->b;
+    EcpBatch *b = &cur->b;
     if ((flags & 2) && (size_t)b->outTotal > h->hostBlocksCap) {
       free(h->hostBlocks);
       h->hostBlocksCap = (size_t)b->outTotal * 5 / 4 + 1024;
@@ -368,6 +380,8 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
       fprintf(stderr, "libecp_b200: device failure: %s\n", ecpdev_last_error());
       return -rc;
     }
+    if (b->devEnum && b->pairCand > 0 && b->nTriples > 0) /* feedback for the size estimate of the next batches */
+      h->triPerPair = (double)b->nTriples / (double)b->pairCand;
     add_stats(h, cur, &st, msBuild);
     if (getenv("LIBECP_B200_TRACE"))
       fprintf(stderr, "[libecp_b200] rank %d batch: %d triples build %.1f ms (overlapped) run_batch+join wall %.1f ms device %.1f ms\n",
@@ -745,10 +759,17 @@ double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches)
   if (h->empty) return 0.0;
   EcpBatchBuf *bufs[2] = {h->bb, h->bb2};
   const double t0 = now_ms();
-  while (ecp_batch_build(h->tab, h->geometry, &centre, pass_batch_size(h, nb), h->rank, h->world, 0, 0, bufs[nb & 1]) > 0) {
-    n += bufs[nb & 1]->b.nTriples;
-    nb++;
-  }
+  const char *e = getenv("LIBECP_B200_ENUM");
+  if (!h->tab->deriv && !(e && !strcmp(e, "host"))) { /* what a matrix run leaves to the host: screening and slot layout */
+    while (ecp_batch_build_slots(h->tab, h->geometry, &centre, pass_batch_size(h, nb), h->rank, h->world, bufs[nb & 1]) > 0) {
+      n += bufs[nb & 1]->b.pairCand; /* shell pairs the device will test (it counts the triples itself) */
+      nb++;
+    }
+  } else
+    while (ecp_batch_build(h->tab, h->geometry, &centre, pass_batch_size(h, nb), h->rank, h->world, 0, 0, bufs[nb & 1]) > 0) {
+      n += bufs[nb & 1]->b.nTriples;
+      nb++;
+    }
   const double ms = now_ms() - t0;
   if (triples) *triples = n;
   if (batches) *batches = nb;

@@ -93,6 +93,7 @@ void ecp_batch_free(EcpBatchBuf *bb) {
   free(bb->clsFirst); free(bb->clsWork); free(bb->clsElem); free(bb->clsOutElem); free(bb->clsPairBase); free(bb->clsQBase);
   free(bb->cnA); free(bb->cnS1); free(bb->cnB); free(bb->cnS2); free(bb->cnC); free(bb->cnLa); free(bb->cnLb);
   free(bb->cnOut); free(bb->cnShA); free(bb->cnShB);
+  free(bb->ceAS0); free(bb->cePair0); free(bb->asSS0); free(bb->ssOwn);
   free_scratch((struct BuilderScratch *)bb->scratch);
   free(bb);
 }
@@ -182,7 +183,7 @@ int ecp_deriv_shift(int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2)
 }
 
 /* phase (a) for one centre */
-static void centre_screen(const EcpTables *t, const double *geometry, int C, int rank, int world, CentreWork *w) {
+static void centre_screen(const EcpTables *t, const double *geometry, int C, int rank, int world, CentreWork *w, int doCount) {
   const EcpHostTables *v = &t->v;
   const int nat = v->nrAtoms, nc = v->nClasses, nsh = v->nrShells;
   if (!w->asAtom) { /* per-atom and per-class areas have fixed sizes; the per-slot ones grow with the slots found */
@@ -243,6 +244,14 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
   w->nAS = nAS;
   w->fRows = fRows;
   w->omSize = omSize;
+  if (!doCount) { /* device enumeration: only the number of shell pairs (owned a, b >= a) the device will test */
+    long long cand = 0;
+    for (int a = 0; a < nSS; a++)
+      if (w->ssOwn[a]) cand += nSS - a;
+    w->nTri = cand;
+    w->outSize = 0;
+    return;
+  }
   /* count executed triples per class (canonical enumeration, src/libecp.c:297-320,344) */
   memset(w->clsCount, 0, (nc + 1) * sizeof(int));
   memset(w->clsPairs, 0, (nc + 1) * sizeof(long long));
@@ -355,7 +364,7 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
     }
     cw = S->cw;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int i = first; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i]);
+    for (int i = first; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i], 1);
     for (int i = first; i < ncand; i++) screened += cw[i].nTri;
   }
   if (ncand == 0) {
@@ -647,6 +656,172 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
   b->nPairs = nPairs;
   b->qTotal = qTot;
   b->rshTotal = qTot;
+  b->clsFirst = bb->clsFirst;
+  b->clsWork = bb->clsWork;
+  b->clsElem = bb->clsElem;
+  b->clsOutElem = bb->clsOutElem;
+  b->clsPairBase = bb->clsPairBase;
+  b->clsQBase = bb->clsQBase;
+  return ntake;
+}
+
+
+/* ---- device-enumerated batch: screening + slot layout (builder.h) ---- */
+int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
+                          EcpBatchBuf *bb) {
+  const EcpHostTables *v = &t->v;
+  const int nat = v->nrAtoms;
+  if (world > 1) ecp_tables_row_deal((EcpTables *)t);
+  struct BuilderScratch *S = get_scratch(bb);
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  const double ratio = bb->triPerPair > 0.0 ? bb->triPerPair : 0.5;
+  const int round = nthreads * 2 > 8 ? nthreads * 2 : 8;
+  int cand[1024], ncand = 0, C = *centre;
+  double screened = 0.0; /* estimated triples of the screened centres */
+  CentreWork *cw = S->cw;
+  if (S->nleft > 0 && S->leftCentre[0] == *centre && S->leftRank == rank && S->leftWorld == world) {
+    for (int i = 0; i < S->nleft; i++) {
+      cand[ncand++] = S->leftCentre[i];
+      screened += ratio * (double)cw[i].nTri;
+    }
+    C = S->leftNext;
+  }
+  S->nleft = 0;
+  while (C < nat && ncand < 1024 && screened < (double)maxTriples) {
+    const int first = ncand;
+    for (; C < nat && ncand < first + round && ncand < 1024; C++)
+      if (t->atomType[C] >= 0) cand[ncand++] = C;
+    if (ncand == first) break;
+    if (S->ncw < ncand) {
+      S->cw = realloc(S->cw, ncand * sizeof(CentreWork));
+      memset(S->cw + S->ncw, 0, (ncand - S->ncw) * sizeof(CentreWork));
+      S->ncw = ncand;
+    }
+    cw = S->cw;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = first; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i], 0);
+    for (int i = first; i < ncand; i++) screened += ratio * (double)cw[i].nTri;
+  }
+  EcpBatch *b = &bb->b;
+  memset(b, 0, sizeof(*b));
+  b->devEnum = 1;
+  if (ncand == 0) {
+    *centre = nat;
+    return 0;
+  }
+  int ntake = 0;
+  double est = 0.0;
+  while (ntake < ncand) {
+    est += ratio * (double)cw[ntake].nTri;
+    ntake++;
+    if (est >= (double)maxTriples) break;
+  }
+  if (ntake < ncand && C >= nat) {
+    double rest = 0.0;
+    for (int i = ntake; i < ncand; i++) rest += ratio * (double)cw[i].nTri;
+    if (4.0 * rest <= (double)maxTriples) ntake = ncand;
+  }
+  *centre = (ntake < ncand) ? cand[ntake] : C;
+  long long nAS = 0, nSS = 0, omTotal = 0, fRows = 0, nPairAS = 0, pairCand = 0;
+  long long *asBase = malloc((ntake + 1) * sizeof(long long)), *ssBase = malloc((ntake + 1) * sizeof(long long));
+  long long *omBase = malloc((ntake + 1) * sizeof(long long)), *fBase = malloc((ntake + 1) * sizeof(long long));
+  ENSURE(bb->ceAS0, bb->capCE, ntake + 1, int);
+  ENSURE(bb->cePair0, bb->capCE, ntake + 1, int64_t);
+  if (ntake + 1 > bb->capCE) bb->capCE = ntake + 1 + 16;
+  bb->nominal = 0;
+  for (int i = 0; i < ntake; i++) {
+    asBase[i] = nAS; ssBase[i] = nSS; omBase[i] = omTotal; fBase[i] = fRows;
+    bb->ceAS0[i] = (int)nAS;
+    bb->cePair0[i] = nPairAS;
+    nAS += cw[i].nAS; nSS += cw[i].nSS; omTotal += cw[i].omSize; fRows += cw[i].fRows;
+    nPairAS += (long long)cw[i].nAS * (cw[i].nAS + 1) / 2;
+    pairCand += cw[i].nTri;
+    bb->nominal += (long long)v->nrShells * (v->nrShells + 1) / 2;
+  }
+  bb->ceAS0[ntake] = (int)nAS;
+  bb->cePair0[ntake] = nPairAS;
+  bb->screenedShells = nSS;
+  ENSURE(bb->asAtom, bb->capAS, nAS + 1, int); ENSURE(bb->asCentre, bb->capAS, nAS + 1, int);
+  ENSURE(bb->asType, bb->capAS, nAS + 1, int);
+  ENSURE(bb->asSS0, bb->capAS0, nAS + 1, int);
+  if (nAS + 1 > bb->capAS0) bb->capAS0 = (int)nAS + 17;
+  if (nAS + 1 > bb->capAS) bb->asR = (double *)realloc(bb->asR, (size_t)(nAS + 17) * 4 * sizeof(double));
+  ENSURE(bb->asOmOff, bb->capAS, nAS + 1, int64_t);
+  if (nAS + 1 > bb->capAS) bb->capAS = (int)nAS + 17;
+  ENSURE(bb->ssShell, bb->capSS, nSS, int); ENSURE(bb->ssASlot, bb->capSS, nSS, int);
+  ENSURE(bb->ssStart, bb->capSS, nSS, int); ENSURE(bb->ssEnd, bb->capSS, nSS, int);
+  ENSURE(bb->ssFOff, bb->capSS, nSS, int64_t);
+  ENSURE(bb->ssOwn, bb->capOwn, nSS, unsigned char);
+  if (nSS > bb->capOwn) bb->capOwn = (int)nSS + 16;
+  if (nSS > bb->capSS) bb->capSS = (int)nSS + 16;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int i = 0; i < ntake; i++) {
+    const CentreWork *w = &cw[i];
+    const double *rC = geometry + 3 * w->C;
+    const int Lc = w->Lc;
+    long long om = omBase[i], fr = fBase[i];
+    for (int a = 0; a < w->nAS; a++) {
+      const long long g = asBase[i] + a;
+      const int X = w->asAtom[a];
+      bb->asAtom[g] = X;
+      bb->asCentre[g] = w->C;
+      bb->asType[g] = w->type;
+      bb->asR[4 * g + 0] = geometry[3 * X + 0] - rC[0];
+      bb->asR[4 * g + 1] = geometry[3 * X + 1] - rC[1];
+      bb->asR[4 * g + 2] = geometry[3 * X + 2] - rC[2];
+      bb->asR[4 * g + 3] = w->asD[a];
+      bb->asOmOff[g] = om;
+      om += (long long)(Lc + t->atomMaxL[X]) * Lc * Lc * CD(t->atomMaxL[X]);
+    }
+    for (int s = 0; s < w->nSS; s++) {
+      const long long g = ssBase[i] + s;
+      bb->ssShell[g] = w->ssShell[s];
+      bb->ssASlot[g] = (int)(asBase[i] + w->ssAtom[s]);
+      bb->ssStart[g] = w->ssStart[s];
+      bb->ssEnd[g] = w->ssEnd[s];
+      bb->ssOwn[g] = w->ssOwn[s];
+      bb->ssFOff[g] = fr;
+      fr += Lc + v->shellL[w->ssShell[s]];
+      if (s == 0 || w->ssAtom[s] != w->ssAtom[s - 1]) bb->asSS0[asBase[i] + w->ssAtom[s]] = (int)g; /* slots of an atom are contiguous */
+    }
+  }
+  bb->asSS0[nAS] = (int)nSS;
+  free(asBase); free(ssBase); free(omBase); free(fBase);
+  for (int i = ntake; i < ncand; i++) {
+    const CentreWork tmp = cw[i - ntake];
+    cw[i - ntake] = cw[i];
+    cw[i] = tmp;
+    S->leftCentre[i - ntake] = cand[i];
+  }
+  S->nleft = ncand - ntake;
+  S->leftNext = C;
+  S->leftRank = rank;
+  S->leftWorld = world;
+  bb->nCanon = 0;
+  b->nASlots = (int)nAS;
+  b->asAtom = bb->asAtom;
+  b->asCentre = bb->asCentre;
+  b->asType = bb->asType;
+  b->asR = bb->asR;
+  b->asOmOff = bb->asOmOff;
+  b->omTotal = omTotal;
+  b->nSSlots = (int)nSS;
+  b->ssShell = bb->ssShell;
+  b->ssASlot = bb->ssASlot;
+  b->ssStart = bb->ssStart;
+  b->ssEnd = bb->ssEnd;
+  b->ssFOff = bb->ssFOff;
+  b->fRows = fRows;
+  b->nCentres = ntake;
+  b->ceAS0 = bb->ceAS0;
+  b->cePair0 = bb->cePair0;
+  b->asSS0 = bb->asSS0;
+  b->ssOwn = bb->ssOwn;
+  b->pairCand = pairCand;
+  /* filled by the device layer (ecpdev_run_batch): the triple count, the totals and the class prefixes */
   b->clsFirst = bb->clsFirst;
   b->clsWork = bb->clsWork;
   b->clsElem = bb->clsElem;

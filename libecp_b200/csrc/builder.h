@@ -20,6 +20,12 @@ typedef struct {
   int *clsFirst;
   int64_t *clsWork, *clsElem, *clsOutElem, *clsPairBase, *clsQBase;
   int capAS, capSS, capTR, capOut;
+  /* device enumeration (EcpBatch.devEnum) */
+  int *ceAS0, *asSS0;
+  int64_t *cePair0;
+  unsigned char *ssOwn;
+  int capCE, capAS0, capOwn;
+  double triPerPair; /* executed triples per tested shell pair of the batches run so far (batch sizing; api.c feeds it back) */
   /* canonical (reference loop order) list of the executed triples of this batch, for callback replay */
   int nCanon, capCanon;
   int *cnA, *cnS1, *cnB, *cnS2, *cnC, *cnLa, *cnLb; /* cnLa / cnLb: the UNSHIFTED momenta (callback arguments)        */
@@ -41,6 +47,10 @@ void ecp_batch_share_scratch(EcpBatchBuf *dst, EcpBatchBuf *src);
  * Returns the number of centres consumed (0 = no ECP centre left). */
 int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
                     int keepCanon, int wantOut, EcpBatchBuf *bb);
+/* The same for a device-enumerated batch: screening and slot layout only (O(centres x shells) instead of O(triples));
+ * the batch is cut by an estimate of the triples (tested shell pairs x bb->triPerPair). */
+int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
+                          EcpBatchBuf *bb);
 
 /* shift s = 0..3 of a first-derivative run and whether the reference evaluates it (builder.c) */
 int ecp_deriv_shift(int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2);

@@ -68,6 +68,7 @@ struct DevT {
   const double *gaussN, *gaussD, *gaussA, *typeUtabT, *typeUL; /* typeUtabT: [type][slot][l][N] */
   const int *clsLa, *clsLb, *clsL, *clsNq, *clsQOff, *clsQlOff, *qlist, *clsQidxOff;
   const int16_t *qidx;
+  const int *clsLookup; /* [(la (ECP_MAX_LBS+1) + lb) (ECP_MAX_LECP+1) + L] -> class or -1 */
   int nAO;
 };
 struct T1Rec;
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(128) k_fastT2(DevT t, DevB b, int lim, const F
 
 #include "ecp_fallback.cuh"
 #include "ecp_waves.cuh"
+#include "ecp_enum.cuh"
 
 /* ---- per triple: everything the element-parallel kernels (link, chi, shift) would otherwise chase through
  * trA/trB -> ssShell/ssASlot -> asAtom/asOmOff/shellK/... with up to five dependent loads PER ELEMENT.  Those kernels
@@ -889,7 +891,14 @@ struct EcpDev {
   struct UpSet {
     Buf asAtom, asType, asR, asOmOff, ssShell, ssASlot, ssStart, ssEnd, ssFOff, trA, trB, trOut, trPair;
     Buf prTriple, clsFirst, clsWork, clsElem, clsOutElem, clsPairBase, clsQBase;
+    /* device enumeration (ecp_enum.cuh): per-centre layout, counters, and the totals / class prefixes read back */
+    Buf ceAS0, cePair0, asSS0, ssOwn, ccTri, ccPair, pairCnt, meta;
+    EnumIn ein;
+    size_t enumSmem;
   } up[2];
+  void *enumHost[2]; /* page-locked: EnumMeta, clsFirst (as long long), clsWork, clsElem, clsOutElem, clsPairBase, clsQBase */
+  int enumHost_nc;
+  int enumOff; /* LIBECP_B200_ENUM=host: triples from the host builder also in matrix runs */
   cudaStream_t s3;
   cudaStream_t s4; /* D2H of finished row panels while the next panel computes (ecpdev_matrix_add_to_host, async = 1) */
   cudaEvent_t evUp[2];
@@ -1036,7 +1045,12 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   cudaDeviceGetAttribute(&d->nSM, cudaDevAttrMultiProcessorCount, device);
   cudaStreamCreateWithFlags(&d->s1, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&d->s2real, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&d->s3, cudaStreamNonBlocking);
+  { /* the upload stream also counts / scans the next batch's triples (ecp_enum.cuh): highest priority, so that those small
+     * kernels run between the blocks of the current batch instead of behind them */
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&d->s3, cudaStreamNonBlocking, hi) != cudaSuccess) cudaStreamCreateWithFlags(&d->s3, cudaStreamNonBlocking);
+  }
   cudaStreamCreateWithFlags(&d->s4, cudaStreamNonBlocking);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&d->evUp[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&d->evDone, cudaEventDisableTiming | cudaEventBlockingSync);
@@ -1059,6 +1073,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
       d->ftabCompact = !(lk && !strcmp(lk, "full"));
     }
     if (d->fastLim < 1) d->fastLim = 1;
+    e = getenv("LIBECP_B200_ENUM");
+    d->enumOff = e && !strcmp(e, "host");
     e = getenv("LIBECP_B200_FASTUNROLL");
     d->fastUnroll = e ? atoi(e) : 1;
     e = getenv("LIBECP_B200_SURVCAP");
@@ -1207,6 +1223,16 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   cudaMemcpyToSymbolAsync(c_small_r, h->small_r, ECP_SMALL_SLOTS * sizeof(double), 0, cudaMemcpyHostToDevice, d->s1);
   cudaMemcpyToSymbolAsync(c_small_oidx, h->small_oidx, ECP_SMALL_SLOTS * sizeof(int16_t), 0, cudaMemcpyHostToDevice, d->s1);
   t.typeUL = upload_const(d, h->typeUL, (size_t)h->nTypes * ECP_SMALL_SLOTS);
+  {
+    const int nl = (ECP_MAX_LBS + 1) * (ECP_MAX_LBS + 1) * (ECP_MAX_LECP + 1);
+    int *lut = (int *)malloc(nl * sizeof(int));
+    for (int k = 0; k < nl; k++) lut[k] = -1;
+    for (int c = 0; c < h->nClasses; c++)
+      lut[(h->clsLa[c] * (ECP_MAX_LBS + 1) + h->clsLb[c]) * (ECP_MAX_LECP + 1) + h->clsL[c]] = c;
+    t.clsLookup = upload_const(d, lut, (size_t)nl);
+    cudaStreamSynchronize(d->s1);
+    free(lut);
+  }
   t.clsLa = upload_const(d, h->clsLa, h->nClasses);
   t.clsLb = upload_const(d, h->clsLb, h->nClasses);
   t.clsL = upload_const(d, h->clsL, h->nClasses);
@@ -1246,7 +1272,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
 /* scratch buffers (and the result matrix) of a destroyed handle are parked per device and adopted by the next handle
  * created there: a caller that goes through getIntegrals() creates a handle per call, and growing gigabytes of
  * scratch from the driver costs tens to hundreds of milliseconds each time.  libecp_b200_release_cache() frees them. */
-#define ECP_NBUF 96
+#define ECP_NBUF 128
 struct DevCache {
   int valid;
   Buf bufs[ECP_NBUF];
@@ -1267,7 +1293,9 @@ static int collect_bufs(EcpDev *d, Buf **bs) {
 #define UPSET(i) &d->up[i].asAtom, &d->up[i].asType, &d->up[i].asR, &d->up[i].asOmOff, &d->up[i].ssShell,            \
                  &d->up[i].ssASlot, &d->up[i].ssStart, &d->up[i].ssEnd, &d->up[i].ssFOff, &d->up[i].trA, &d->up[i].trB, \
                  &d->up[i].trOut, &d->up[i].trPair, &d->up[i].prTriple, &d->up[i].clsFirst, &d->up[i].clsWork,        \
-                 &d->up[i].clsElem, &d->up[i].clsOutElem, &d->up[i].clsPairBase, &d->up[i].clsQBase
+                 &d->up[i].clsElem, &d->up[i].clsOutElem, &d->up[i].clsPairBase, &d->up[i].clsQBase,                 \
+                 &d->up[i].ceAS0, &d->up[i].cePair0, &d->up[i].asSS0, &d->up[i].ssOwn, &d->up[i].ccTri, &d->up[i].ccPair, \
+                 &d->up[i].pairCnt, &d->up[i].meta
                  UPSET(0), UPSET(1)};
 #undef UPSET
   const int n = (int)(sizeof(list) / sizeof(list[0]));
@@ -1333,6 +1361,8 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
     if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
   }
   comm_release(d);
+  for (int k = 0; k < 2; k++)
+    if (d->enumHost[k]) ecpdev_pinned_free(d->enumHost[k]);
   if (d->agRows.p) cudaFreeAsync(d->agRows.p, d->s1);
   if (d->agOff.p) cudaFreeAsync(d->agOff.p, d->s1);
   if (d->agBuf.p) cudaFreeAsync(d->agBuf.p, d->s1);
@@ -1618,6 +1648,67 @@ static int upload_set(EcpDev *d, const EcpBatch *h, int flags, int slot, cudaStr
   UP(ssStart, h->ssStart, h->nSSlots, int);
   UP(ssEnd, h->ssEnd, h->nSSlots, int);
   UP(ssFOff, (const long long *)h->ssFOff, h->nSSlots, long long);
+  if (h->devEnum) { /* triples are enumerated on the device: count + scan here, fill once the sizes are known */
+    UP(ceAS0, h->ceAS0, h->nCentres + 1, int);
+    UP(cePair0, (const long long *)h->cePair0, h->nCentres + 1, long long);
+    UP(asSS0, h->asSS0, h->nASlots + 1, int);
+    UP(ssOwn, h->ssOwn, h->nSSlots, unsigned char);
+    const int lb1 = d->maxLBS + 1, nK = lb1 * lb1;
+    int rc_ = ensure(&u.ccTri, (size_t)nc * h->nCentres * sizeof(int));
+    if (!rc_) rc_ = ensure(&u.ccPair, (size_t)nc * h->nCentres * sizeof(int));
+    if (!rc_) rc_ = ensure(&u.pairCnt, ((size_t)h->cePair0[h->nCentres] * nK + 1) * sizeof(int2));
+    if (!rc_) rc_ = ensure(&u.meta, sizeof(EnumMeta));
+    if (!rc_) rc_ = ensure(&u.clsFirst, (size_t)(nc + 1) * sizeof(int));
+    if (!rc_) rc_ = ensure(&u.clsWork, (size_t)(nc + 1) * sizeof(long long));
+    if (!rc_) rc_ = ensure(&u.clsElem, (size_t)(nc + 1) * sizeof(long long));
+    if (!rc_) rc_ = ensure(&u.clsOutElem, (size_t)(nc + 1) * sizeof(long long));
+    if (!rc_) rc_ = ensure(&u.clsPairBase, (size_t)(nc + 1) * sizeof(long long));
+    if (!rc_) rc_ = ensure(&u.clsQBase, (size_t)(nc + 1) * sizeof(long long));
+    if (rc_) return rc_;
+    EnumIn &in = u.ein;
+    in.nCentres = h->nCentres; in.nc = nc; in.lb1 = lb1;
+    in.ceAS0 = (const int *)u.ceAS0.p; in.cePair0 = (const long long *)u.cePair0.p; in.asSS0 = (const int *)u.asSS0.p;
+    in.asType = (const int *)u.asType.p; in.ssShell = (const int *)u.ssShell.p; in.ssStart = (const int *)u.ssStart.p;
+    in.ssEnd = (const int *)u.ssEnd.p; in.ssOwn = (const unsigned char *)u.ssOwn.p;
+    in.ccTri = (int *)u.ccTri.p; in.ccPair = (int *)u.ccPair.p; in.pairCnt = (int2 *)u.pairCnt.p;
+    int maxS = 0; /* most shell slots of one centre: shared memory of the enumeration kernels */
+    for (int i = 0; i < h->nCentres; i++) {
+      const int n = h->asSS0[h->ceAS0[i + 1]] - h->asSS0[h->ceAS0[i]];
+      if (n > maxS) maxS = n;
+    }
+    u.enumSmem = (size_t)2 * maxS * sizeof(unsigned);
+    if (u.enumSmem > 48 * 1024) {
+      snprintf(g_err, sizeof(g_err), "libecp_b200: %d shell slots around one centre exceed the enumeration kernels' shared memory", maxS);
+      return -1;
+    }
+    k_enum_count<<<h->nCentres, 256, u.enumSmem, st>>>(d->t, in);
+    k_enum_scan<<<1, 128, 0, st>>>(d->t, in, (int *)u.clsFirst.p, (long long *)u.clsWork.p, (long long *)u.clsElem.p,
+                                  (long long *)u.clsOutElem.p, (long long *)u.clsPairBase.p, (long long *)u.clsQBase.p,
+                                  (EnumMeta *)u.meta.p);
+    CK(cudaGetLastError());
+    /* read back: EnumMeta | clsFirst (int) | five long long prefix arrays */
+    if (!d->enumHost[slot] || d->enumHost_nc < nc) {
+      for (int k = 0; k < 2; k++) { /* page-locked blocks from the process-wide cache (pinning costs ~0.3 ms) */
+        if (d->enumHost[k]) ecpdev_pinned_free(d->enumHost[k]);
+        d->enumHost[k] = ecpdev_pinned_alloc(sizeof(EnumMeta) + (size_t)(nc + 2) * 6 * sizeof(long long));
+        if (!d->enumHost[k]) return -1;
+      }
+      d->enumHost_nc = nc;
+    }
+    char *hp = (char *)d->enumHost[slot];
+    const size_t stride = (size_t)(nc + 2) * sizeof(long long);
+    CK(cudaMemcpyAsync(hp, u.meta.p, sizeof(EnumMeta), cudaMemcpyDeviceToHost, st));
+    hp += sizeof(EnumMeta);
+    CK(cudaMemcpyAsync(hp, u.clsFirst.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + stride, u.clsWork.p, (nc + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + 2 * stride, u.clsElem.p, (nc + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + 3 * stride, u.clsOutElem.p, (nc + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + 4 * stride, u.clsPairBase.p, (nc + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + 5 * stride, u.clsQBase.p, (nc + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(d->evUp[slot], st));
+    d->upBatch[slot] = h;
+    return 0;
+  }
   UP(trA, h->trA, h->nTriples, int);
   UP(trB, h->trB, h->nTriples, int);
   if (flags & 2) UP(trOut, (const long long *)h->trOut, h->nTriples, long long);
@@ -1646,7 +1737,7 @@ extern "C" void ecpdev_invalidate_prefetch(EcpDev *d) {
 /* called from the builder thread as soon as batch i+1 is built: its H2D overlaps the kernels of batch i */
 extern "C" int ecpdev_prefetch_batch(EcpDev *d, const EcpBatch *h, int flags, int slot) {
   CK(cudaSetDevice(d->device));
-  if (h->nTriples == 0) return 0;
+  if (h->nTriples == 0 && !h->devEnum) return 0;
   return upload_set(d, h, flags, slot & 1, d->s3);
 }
 #define SCRATCH(buf, field, n, T)                                   \
@@ -1795,19 +1886,15 @@ static int run_fallback_waves(EcpDev *d, int km, long long *launches) {
   return 0;
 }
 
-extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slot, double *hostBlocks, EcpDevStats *st) {
+extern "C" int ecpdev_run_batch(EcpDev *d, EcpBatch *h, int flags, int slot, double *hostBlocks, EcpDevStats *st) {
   CK(cudaSetDevice(d->device));
   DevB &B = d->b;
   g_allocStream = d->s1;
   d->s2 = d->serial ? d->s1 : d->s2real;
   const int nc = d->nClasses;
-  B.nASlots = h->nASlots;
-  B.nSSlots = h->nSSlots;
-  B.nTriples = h->nTriples;
-  B.nPairs = h->nPairs;
   if (st) memset(st, 0, sizeof(*st));
   d->batchH2D = 0;
-  if (h->nTriples == 0) return 0;
+  if (h->nTriples == 0 && !h->devEnum) return 0;
   const bool trace = getenv("LIBECP_B200_TRACE") != NULL;
   const double tr0 = omp_get_wtime();
   slot &= 1;
@@ -1820,6 +1907,51 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   d->upBatch[slot] = NULL; /* consumed: the set may be refilled once this batch is through */
   d->batchH2D = d->upBytes[slot];
   g_allocStream = d->s1;
+  if (h->devEnum) {
+    /* sizes and class prefixes of the device-enumerated batch (counted and scanned behind the upload, ecp_enum.cuh);
+     * they land in the host arrays the batch view points at, and everything below sizes itself from them as before */
+    CK(cudaEventSynchronize(d->evUp[slot]));
+    const char *hp = (const char *)d->enumHost[slot];
+    const EnumMeta *m = (const EnumMeta *)hp;
+    hp += sizeof(EnumMeta);
+    const size_t stride = (size_t)(nc + 2) * sizeof(long long);
+    if (m->nTriples > 0x7fffffffLL || m->nPairs > 0x7fffffffLL) {
+      snprintf(g_err, sizeof(g_err), "libecp_b200: batch of %lld triples / %lld primitive pairs exceeds 2^31", m->nTriples, m->nPairs);
+      return -1;
+    }
+    h->nTriples = (int)m->nTriples;
+    h->nPairs = m->nPairs;
+    h->tTotal = m->tTotal;
+    h->gTotal = m->gTotal;
+    h->qTotal = m->qTotal;
+    h->rshTotal = m->qTotal;
+    h->outTotal = m->outTotal;
+    memcpy((void *)h->clsFirst, hp, (nc + 1) * sizeof(int));
+    memcpy((void *)h->clsWork, hp + stride, (nc + 1) * sizeof(long long));
+    memcpy((void *)h->clsElem, hp + 2 * stride, (nc + 1) * sizeof(long long));
+    memcpy((void *)h->clsOutElem, hp + 3 * stride, (nc + 1) * sizeof(long long));
+    memcpy((void *)h->clsPairBase, hp + 4 * stride, (nc + 1) * sizeof(long long));
+    memcpy((void *)h->clsQBase, hp + 5 * stride, (nc + 1) * sizeof(long long));
+    if (h->nTriples == 0) return 0;
+    EcpDev::UpSet &u = d->up[slot];
+    int rc_ = ensure(&u.trA, (size_t)h->nTriples * sizeof(int));
+    if (!rc_) rc_ = ensure(&u.trB, (size_t)h->nTriples * sizeof(int));
+    if (!rc_) rc_ = ensure(&u.trPair, (size_t)h->nTriples * sizeof(long long));
+    if (!rc_) rc_ = ensure(&u.prTriple, ((size_t)h->nPairs + 1) * sizeof(int));
+    if (rc_) return rc_;
+    CK(cudaEventRecord(d->ev[0], d->s1)); /* the batch's device time includes the fill (count / scan ran behind the previous batch) */
+    /* fill + k_triprep on the second stream: the per-centre tables (k_atomslot, k_omegaX, k_Ftab) only need the slots and
+     * run beside them on the first */
+    cudaStream_t sE = d->serial ? d->s1 : d->s2real;
+    if (sE != d->s1) CK(cudaStreamWaitEvent(sE, d->ev[0], 0));
+    k_enum_fill<<<h->nCentres, 256, u.enumSmem, sE>>>(d->t, u.ein, (const int *)u.clsFirst.p, (const long long *)u.clsPairBase.p,
+                                               (int *)u.trA.p, (int *)u.trB.p, (long long *)u.trPair.p);
+    CK(cudaGetLastError());
+  }
+  B.nASlots = h->nASlots;
+  B.nSSlots = h->nSSlots;
+  B.nTriples = h->nTriples;
+  B.nPairs = h->nPairs;
   {
     const EcpDev::UpSet &u = d->up[slot];
     B.asAtom = (const int *)u.asAtom.p; B.asType = (const int *)u.asType.p; B.asR = (const double *)u.asR.p;
@@ -1890,9 +2022,15 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   const DevT &t = d->t;
   long long launches = 0;
   const double tr1 = omp_get_wtime();
-  CK(cudaEventRecord(d->ev[0], d->s1));
+  if (!h->devEnum) CK(cudaEventRecord(d->ev[0], d->s1)); /* device-enumerated batch: recorded before k_enum_fill */
   /* per-centre tables */
-  k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
+  if (h->devEnum && !d->serial) {
+    CK(cudaEventRecord(d->ev[11], d->s1)); /* the scratch k_triprep writes was (re)allocated in s1's order */
+    CK(cudaStreamWaitEvent(d->s2real, d->ev[11], 0));
+    k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s2real>>>(t, B);
+    CK(cudaEventRecord(d->ev[10], d->s2real));
+  } else
+    k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
   k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
   k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
   if (d->ftabCompact) { /* window-only tabulation into a cleared table (k_Ftab2) */
@@ -1906,6 +2044,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
   else
     k_Ftab<KM><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
   launches += 4;
+  if (h->devEnum && !d->serial) CK(cudaStreamWaitEvent(d->s1, d->ev[10], 0)); /* triples and their records are in place */
   CK(cudaEventRecord(d->ev[1], d->s1));
   /* type 1 on the second stream, after the uploads/tables */
   CK(cudaStreamWaitEvent(d->s2, d->ev[1], 0));
@@ -1919,8 +2058,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, const EcpBatch *h, int flags, int slo
       sg.prefix[0] = 0;
       for (int c = 0; c < nc; c++) {
         if (d->hClsLa[c] + d->hClsLb[c] != lab || h->clsFirst[c + 1] == h->clsFirst[c]) continue;
-        const long long p0 = h->trPair[h->clsFirst[c]];
-        const long long p1 = (h->clsFirst[c + 1] < h->nTriples) ? h->trPair[h->clsFirst[c + 1]] : h->nPairs;
+        const long long p0 = h->clsPairBase[c], p1 = h->clsPairBase[c + 1]; /* primitive pairs of the class */
         if (sg.nseg == T1_MAXSEG) {
           launch_type1(d, lab, sg, listOff);
           launches += 2;

@@ -110,6 +110,17 @@ typedef struct {
   const int64_t *clsOutElem;/* [nClasses+1] prefix of ntriples*IJK(la)*IJK(lb)     */
   const int64_t *clsPairBase; /* [nClasses+1] prefix of primitive pairs per class  */
   const int64_t *clsQBase;    /* [nClasses+1] prefix of pairs*(la+lb+1)^2 (offsets into Q / rsh) */
+  /* Device enumeration (matrix runs): the host only screens - per centre the atom slots and shell slots above - and the
+   * triples, their class order and every per-class prefix are produced on the device (ecp_enum.cuh).  ecpdev_run_batch
+   * fills nTriples, nPairs, the totals and the cls* arrays (which then point at writable host storage) before the
+   * kernels of the batch are sized. */
+  int devEnum;
+  int nCentres;
+  const int *ceAS0;           /* [nCentres+1] first atom slot of every centre                     */
+  const int64_t *cePair0;     /* [nCentres+1] first atom-slot pair (ka <= kb) of every centre     */
+  const int *asSS0;           /* [nASlots+1] first shell slot of every atom slot                  */
+  const unsigned char *ssOwn; /* [nSSlots] the row of this shell belongs to the rank              */
+  int64_t pairCand;           /* shell pairs (owned a, b >= a) the device tests: for the next batch's size estimate */
 } EcpBatch;
 
 typedef struct {
@@ -147,7 +158,7 @@ void ecpdev_release_cache(void);
 /* run one batch: flags bit0 = accumulate into matrix, bit1 = keep blocks and copy them to hostBlocks; slot = which of
  * the two input sets to use (alternate between consecutive batches).  ecpdev_prefetch_batch copies the inputs of the
  * NEXT batch into the other set on a copy stream while this one runs (any host thread). */
-int ecpdev_run_batch(EcpDev *d, const EcpBatch *b, int flags, int slot, double *hostBlocks, EcpDevStats *stats);
+int ecpdev_run_batch(EcpDev *d, EcpBatch *b, int flags, int slot, double *hostBlocks, EcpDevStats *stats);
 int ecpdev_prefetch_batch(EcpDev *d, const EcpBatch *b, int flags, int slot);
 void ecpdev_invalidate_prefetch(EcpDev *d);
 int ecpdev_sync(EcpDev *d);

@@ -477,3 +477,32 @@ def test_first_derivative_is_the_gradient_of_the_integrals():
             vals.append((r0[0][9] + r0[1][9]).reshape(1, 3)[0])
         fd[d] = (vals[0] - vals[1]) / (2 * h)
     assert np.allclose(grad, fd, rtol=1e-6, atol=1e-9)
+
+
+def test_device_enumeration_matches_host_builder():
+    """matrix runs enumerate the triples on the device (ecp_enum.cuh) from the host's screening; LIBECP_B200_ENUM=host
+    keeps the host builder.  Same triples in the same class order: every intermediate (T, gamma, chi, Q) is identical
+    element for element, the statistics agree, also for a shard and for several small batches"""
+    for mk, name, shard, batch in ((lambda: synth.cfg3(4), "au4", None, None), (lambda: synth.cfg4("b"), "cfg4b", None, None),
+                                   (lambda: synth.cfg5(40), None, None, "20000"), (lambda: synth.cfg5(40), None, (1, 4), "7000"),
+                                   (lambda: synth.cfg1(), "cfg1", None, None)):
+        def run():
+            with capi.Handle(mk()) as h:
+                if shard:
+                    h.set_shard(*shard)
+                rc, M = h.integrals_host()
+                st = h.stats()
+                return rc, M, {k: h.debug_fetch(k, 200000) for k in ("T", "gamma", "chi", "Q")}, st
+        env = {"LIBECP_B200_BATCH_TRIPLES": batch} if batch else {}
+        rc0, M0, f0, st0 = _with_env(dict(env, LIBECP_B200_ENUM="host"), run)
+        rc1, M1, f1, st1 = _with_env(env, run)
+        assert rc0 == rc1 == 0
+        for k in ("executed_triples", "prim_pairs", "fast_quadratures", "fast_failed", "fallback_items", "shell_slots"):
+            assert st0[k] == st1[k], (name, k, st0[k], st1[k])
+        assert st1["h2d_bytes"] < st0["h2d_bytes"] or st0["executed_triples"] < 1000
+        if batch is None:  # one batch: the intermediates of the last batch are those of the whole run
+            for k in f0:
+                assert np.array_equal(f0[k], f1[k]), (name, k)
+        assert np.allclose(M0, M1, rtol=1e-13, atol=1e-15), name
+        if name:
+            assert_parity(M1, load_matrix(name), name)

@@ -166,7 +166,26 @@ def test_builder_pass_dry_run_small_and_growing_batches():
     and thread count - regression for a slot-array overrun that only growing batch sizes exposed"""
     s = synth.cfg5(40)
     old = os.environ.get("LIBECP_B200_BATCH_TRIPLES")
+    old_enum = os.environ.get("LIBECP_B200_ENUM")
     try:
+        # what a matrix run leaves to the host (screening + slot layout for the device enumeration): the shell pairs
+        # handed to the device are the same for any batch size / thread count, and the shards partition them
+        cands = set()
+        os.environ.pop("LIBECP_B200_ENUM", None)
+        for bt in ("300", "20000", "3000000"):
+            os.environ["LIBECP_B200_BATCH_TRIPLES"] = bt
+            for thr in (5, 2):
+                capi.set_host_threads(thr)
+                with capi.Handle(s, tables_only=True) as h:
+                    ms, n, nb = h.build_only()
+                    cands.add(n)
+                    tot = 0
+                    for r in range(3):
+                        h.set_shard(r, 3)
+                        tot += h.build_only()[1]
+                    assert tot == n and nb >= 1
+        assert len(cands) == 1
+        os.environ["LIBECP_B200_ENUM"] = "host"
         counts = set()
         for bt in ("300", "20000", "3000000"):
             os.environ["LIBECP_B200_BATCH_TRIPLES"] = bt
@@ -190,6 +209,10 @@ def test_builder_pass_dry_run_small_and_growing_batches():
             os.environ.pop("LIBECP_B200_BATCH_TRIPLES", None)
         else:
             os.environ["LIBECP_B200_BATCH_TRIPLES"] = old
+        if old_enum is None:
+            os.environ.pop("LIBECP_B200_ENUM", None)
+        else:
+            os.environ["LIBECP_B200_ENUM"] = old_enum
 
 
 def test_gather_row_layout_partitions_the_matrix():
