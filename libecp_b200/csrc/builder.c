@@ -678,6 +678,10 @@ int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centr
   nthreads = omp_get_max_threads();
 #endif
   const double ratio = bb->triPerPair > 0.0 ? bb->triPerPair : 0.5;
+  /* the screening of a batch is a few hundred microseconds of work per thread: a small team, so that one thread losing
+   * its core to another process (NCCL proxy, a sampler) cannot hold a large team at the loop's barrier for a scheduler
+   * quantum - measured at 2 and 8 ranks: builds of 3 ms that took 10-30 ms now and then */
+  if (nthreads > 4) nthreads = 4;
   const int round = nthreads * 2 > 8 ? nthreads * 2 : 8;
   int cand[1024], ncand = 0, C = *centre;
   double screened = 0.0; /* estimated triples of the screened centres */
@@ -701,7 +705,7 @@ int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centr
       S->ncw = ncand;
     }
     cw = S->cw;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
     for (int i = first; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i], 0);
     for (int i = first; i < ncand; i++) screened += ratio * (double)cw[i].nTri;
   }
@@ -757,7 +761,7 @@ int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centr
   ENSURE(bb->ssOwn, bb->capOwn, nSS, unsigned char);
   if (nSS > bb->capOwn) bb->capOwn = (int)nSS + 16;
   if (nSS > bb->capSS) bb->capSS = (int)nSS + 16;
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
   for (int i = 0; i < ntake; i++) {
     const CentreWork *w = &cw[i];
     const double *rC = geometry + 3 * w->C;

@@ -2032,6 +2032,10 @@ extern "C" int ecpdev_run_batch(EcpDev *d, EcpBatch *h, int flags, int slot, dou
   } else
     k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
   k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
+  /* the type-1 chain (second stream) needs the triples and the atom slots, not Omega_X or F: it starts here and runs
+   * beside the two table kernels, which are latency bound (k_Ftab2: 21 % of the issue slots) - at 8 GPUs the tables of a
+   * rank (every rank tabulates F for nearly all shells) were 19 % of its pass */
+  if (!d->serial) CK(cudaEventRecord(d->ev[11], d->s1));
   k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
   if (d->ftabCompact) { /* window-only tabulation into a cleared table (k_Ftab2) */
     CK(cudaMemsetAsync(B.F, 0, (size_t)h->fRows * ECP_SMALL_SLOTS * sizeof(double), d->s1));
@@ -2046,8 +2050,8 @@ extern "C" int ecpdev_run_batch(EcpDev *d, EcpBatch *h, int flags, int slot, dou
   launches += 4;
   if (h->devEnum && !d->serial) CK(cudaStreamWaitEvent(d->s1, d->ev[10], 0)); /* triples and their records are in place */
   CK(cudaEventRecord(d->ev[1], d->s1));
-  /* type 1 on the second stream, after the uploads/tables */
-  CK(cudaStreamWaitEvent(d->s2, d->ev[1], 0));
+  /* type 1 on the second stream, after the uploads / triples / atom slots (serial mode: after the tables, same stream) */
+  CK(cudaStreamWaitEvent(d->s2, d->serial ? d->ev[1] : d->ev[11], 0));
   CK(cudaEventRecord(d->ev[6], d->s2));
   k_t1prep<<<nblk(h->nPairs, 128), 128, 0, d->s2>>>(t, B);
   { /* type-1 radial integrals: per LAB = la+lb, one thread per primitive pair (ecp_type1.cuh) */
