@@ -502,9 +502,17 @@ int libecp_b200_comm_attach(libECPHandle *h, void *ncclComm, int rank, int world
 }
 int libecp_b200_allgather(libECPHandle *h, long long *bytesReceived) {
   if (!h || h->empty || !h->dev) return -1;
-  return ecpdev_allgather(h->dev, bytesReceived) ? -1 : 0;
+  const double t0 = now_ms();
+  const int rc = ecpdev_allgather(h->dev, bytesReceived) ? -1 : 0;
+  if (getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] rank %d allgather issued in %.2f ms\n", h->rank, now_ms() - t0);
+  return rc;
 }
-int libecp_b200_device_sync(libECPHandle *h) { return (h && h->dev) ? (ecpdev_sync(h->dev) ? -1 : 0) : 0; }
+int libecp_b200_device_sync(libECPHandle *h) {
+  const double t0 = now_ms();
+  const int rc = (h && h->dev) ? (ecpdev_sync(h->dev) ? -1 : 0) : 0;
+  if (h && getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] rank %d device_sync %.2f ms\n", h->rank, now_ms() - t0);
+  return rc;
+}
 void libecp_b200_comm_free(libECPHandle *h) {
   if (h && h->dev) ecpdev_comm_destroy(h->dev);
 }

@@ -677,6 +677,8 @@ int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centr
 #ifdef _OPENMP
   nthreads = omp_get_max_threads();
 #endif
+  const int prof = getenv("LIBECP_B200_BUILD_PROFILE") != NULL;
+  const double tp0 = prof ? omp_get_wtime() : 0.0;
   const double ratio = bb->triPerPair > 0.0 ? bb->triPerPair : 0.5;
   /* the screening of a batch is a few hundred microseconds of work per thread: a small team, so that one thread losing
    * its core to another process (NCCL proxy, a sampler) cannot hold a large team at the loop's barrier for a scheduler
@@ -709,6 +711,7 @@ int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centr
     for (int i = first; i < ncand; i++) centre_screen(t, geometry, cand[i], rank, world, &cw[i], 0);
     for (int i = first; i < ncand; i++) screened += ratio * (double)cw[i].nTri;
   }
+  const double tp1 = prof ? omp_get_wtime() : 0.0;
   EcpBatch *b = &bb->b;
   memset(b, 0, sizeof(*b));
   b->devEnum = 1;
@@ -794,6 +797,9 @@ int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centr
   }
   bb->asSS0[nAS] = (int)nSS;
   free(asBase); free(ssBase); free(omBase); free(fBase);
+  if (prof)
+    fprintf(stderr, "[builder] rank %d slots: centres %d/%d, %lld shell slots, threads %d: screen %.2f ms, layout %.2f ms\n", rank,
+            ntake, ncand, nSS, nthreads, 1e3 * (tp1 - tp0), 1e3 * (omp_get_wtime() - tp1));
   for (int i = ntake; i < ncand; i++) {
     const CentreWork tmp = cw[i - ntake];
     cw[i - ntake] = cw[i];

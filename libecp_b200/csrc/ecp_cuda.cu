@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(ECP_SMALL_SLOTS, (LMAX <= 6 ? 2 : 1)) k_Ftab(D
  * ORIGINAL indices of the window [start, end) only, writing each point to its slot: the same arithmetic per point (F is
  * bit-identical, test_ftab_variants_are_bit_identical), about a third of the warps; 3.03 -> 2.64 ms per config-5 pass. */
 template <int LMAX>
-__global__ void __launch_bounds__(128) k_Ftab2(DevT t, DevB b) {
+__global__ void __launch_bounds__(128, (LMAX <= 6 ? 7 : 5)) k_Ftab2(DevT t, DevB b) {
   const int ss = blockIdx.x;
   const int sh = b.ssShell[ss], as = b.ssASlot[ss];
   const int Lc = t.typeL[b.asType[as]];
@@ -895,13 +895,18 @@ struct EcpDev {
     Buf ceAS0, cePair0, asSS0, ssOwn, ccTri, ccPair, pairCnt, meta;
     EnumIn ein;
     size_t enumSmem;
+    /* per-centre tables of the batch in the set (rsh / monomials per atom slot, Omega_X, F): they only need the slot arrays,
+     * so the set that is prefetched behind the running batch also computes them there (tablesDone) */
+    Buf rshX, uspX, omX, F;
+    int tablesDone;
   } up[2];
   void *enumHost[2]; /* page-locked: EnumMeta, clsFirst (as long long), clsWork, clsElem, clsOutElem, clsPairBase, clsQBase */
   int enumHost_nc;
   int enumOff; /* LIBECP_B200_ENUM=host: triples from the host builder also in matrix runs */
   cudaStream_t s3;
   cudaStream_t s4; /* D2H of finished row panels while the next panel computes (ecpdev_matrix_add_to_host, async = 1) */
-  cudaEvent_t evUp[2];
+  cudaEvent_t evUp[2], evTab[2];
+  int tabPrefetch; /* LIBECP_B200_TABPREFETCH=1: tables of the prefetched batch on the upload stream (default: with the batch) */
   cudaEvent_t evDone; /* blocking-sync event: the driving thread sleeps while a batch runs (its core goes to the builder) */
   const EcpBatch *upBatch[2]; /* batch whose arrays sit in the set (NULL: none) */
   long long upBytes[2];
@@ -1053,6 +1058,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
   }
   cudaStreamCreateWithFlags(&d->s4, cudaStreamNonBlocking);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&d->evUp[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&d->evTab[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&d->evDone, cudaEventDisableTiming | cudaEventBlockingSync);
   d->s2 = d->s2real;
   d->serial = getenv("LIBECP_B200_SERIAL") != NULL;
@@ -1073,6 +1079,9 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
       d->ftabCompact = !(lk && !strcmp(lk, "full"));
     }
     if (d->fastLim < 1) d->fastLim = 1;
+    e = getenv("LIBECP_B200_TABPREFETCH");
+    d->tabPrefetch = e && !strcmp(e, "1"); /* measured: no gain at 1 or 8 GPUs (the table kernels take the same share of
+                                             * the device beside the running batch) - off unless asked for */
     e = getenv("LIBECP_B200_ENUM");
     d->enumOff = e && !strcmp(e, "host");
     e = getenv("LIBECP_B200_FASTUNROLL");
@@ -1295,7 +1304,7 @@ static int collect_bufs(EcpDev *d, Buf **bs) {
                  &d->up[i].trOut, &d->up[i].trPair, &d->up[i].prTriple, &d->up[i].clsFirst, &d->up[i].clsWork,        \
                  &d->up[i].clsElem, &d->up[i].clsOutElem, &d->up[i].clsPairBase, &d->up[i].clsQBase,                 \
                  &d->up[i].ceAS0, &d->up[i].cePair0, &d->up[i].asSS0, &d->up[i].ssOwn, &d->up[i].ccTri, &d->up[i].ccPair, \
-                 &d->up[i].pairCnt, &d->up[i].meta
+                 &d->up[i].pairCnt, &d->up[i].meta, &d->up[i].rshX, &d->up[i].uspX, &d->up[i].omX, &d->up[i].F
                  UPSET(0), UPSET(1)};
 #undef UPSET
   const int n = (int)(sizeof(list) / sizeof(list[0]));
@@ -1376,6 +1385,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   cudaStreamDestroy(d->s3);
   cudaStreamDestroy(d->s4);
   for (int i = 0; i < 2; i++) cudaEventDestroy(d->evUp[i]);
+  for (int i = 0; i < 2; i++) cudaEventDestroy(d->evTab[i]);
   cudaEventDestroy(d->evDone);
   free(d);
 }
@@ -1626,6 +1636,41 @@ extern "C" int ecpdev_sync(EcpDev *d) {
   return 0;
 }
 
+/* per-centre tables of one batch into the buffers of upload set `slot` on stream st (reference: evalAngularIntegrals,
+ * unitarySpherePolynomials, calcF_FM06 per centre, src/libecp.c:262-292) */
+static int launch_tables(EcpDev *d, const EcpBatch *h, int slot, cudaStream_t st) {
+  EcpDev::UpSet &u = d->up[slot];
+  const DevT &t = d->t;
+  g_allocStream = st;
+  int rc_ = ensure(&u.rshX, ((size_t)h->nASlots * RSHX_STRIDE + 1) * sizeof(double));
+  if (!rc_) rc_ = ensure(&u.uspX, ((size_t)h->nASlots * USPX_STRIDE + 1) * sizeof(double));
+  if (!rc_) rc_ = ensure(&u.omX, ((size_t)h->omTotal + 1) * sizeof(double));
+  if (!rc_) rc_ = ensure(&u.F, ((size_t)h->fRows * ECP_SMALL_SLOTS + 1) * sizeof(double));
+  if (rc_) return rc_;
+  DevB B;
+  memset(&B, 0, sizeof(B));
+  B.nASlots = h->nASlots;
+  B.nSSlots = h->nSSlots;
+  B.asAtom = (const int *)u.asAtom.p; B.asType = (const int *)u.asType.p; B.asR = (const double *)u.asR.p;
+  B.asOmOff = (const long long *)u.asOmOff.p; B.ssShell = (const int *)u.ssShell.p; B.ssASlot = (const int *)u.ssASlot.p;
+  B.ssStart = (const int *)u.ssStart.p; B.ssEnd = (const int *)u.ssEnd.p; B.ssFOff = (const long long *)u.ssFOff.p;
+  B.rshX = (double *)u.rshX.p; B.uspX = (double *)u.uspX.p; B.omX = (double *)u.omX.p; B.F = (double *)u.F.p;
+  k_atomslot<<<(unsigned)((h->nASlots + 127) / 128), 128, 0, st>>>(t, B);
+  k_omegaX<<<h->nASlots, 256, 0, st>>>(t, B);
+  if (d->ftabCompact) { /* window-only tabulation into a cleared table (k_Ftab2) */
+    CK(cudaMemsetAsync(B.F, 0, (size_t)h->fRows * ECP_SMALL_SLOTS * sizeof(double), st));
+    if (t.maxLECP - 1 + d->maxLBS <= 6)
+      k_Ftab2<6><<<h->nSSlots, 128, 0, st>>>(t, B);
+    else
+      k_Ftab2<KM><<<h->nSSlots, 128, 0, st>>>(t, B);
+  } else if (t.maxLECP - 1 + d->maxLBS <= 6)
+    k_Ftab<6><<<h->nSSlots, ECP_SMALL_SLOTS, 0, st>>>(t, B);
+  else
+    k_Ftab<KM><<<h->nSSlots, ECP_SMALL_SLOTS, 0, st>>>(t, B);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 #define UP(buf, src, n, T)                                                                                \
   do {                                                                                                    \
     int rc_ = ensure(&u.buf, ((n) ? (n) : 1) * sizeof(T));                                                \
@@ -1738,7 +1783,19 @@ extern "C" void ecpdev_invalidate_prefetch(EcpDev *d) {
 extern "C" int ecpdev_prefetch_batch(EcpDev *d, const EcpBatch *h, int flags, int slot) {
   CK(cudaSetDevice(d->device));
   if (h->nTriples == 0 && !h->devEnum) return 0;
-  return upload_set(d, h, flags, slot & 1, d->s3);
+  slot &= 1;
+  d->up[slot].tablesDone = 0;
+  int rc = upload_set(d, h, flags, slot, d->s3);
+  if (rc) return rc;
+  if (d->tabPrefetch && h->nSSlots > 0) {
+    /* the next batch's tables beside the running batch: the table kernels are latency bound (k_Ftab2: 21 % of the issue
+     * slots) and at 8 GPUs - where every rank tabulates F for nearly all shells - they were 19 % of a rank's pass */
+    rc = launch_tables(d, h, slot, d->s3);
+    if (rc) return rc;
+    d->up[slot].tablesDone = 1;
+    CK(cudaEventRecord(d->evTab[slot], d->s3));
+  }
+  return 0;
 }
 #define SCRATCH(buf, field, n, T)                                   \
   do {                                                              \
@@ -1899,6 +1956,7 @@ extern "C" int ecpdev_run_batch(EcpDev *d, EcpBatch *h, int flags, int slot, dou
   const double tr0 = omp_get_wtime();
   slot &= 1;
   if (d->upBatch[slot] != h) { /* not prefetched (first batch, or no helper thread): copy now, on the compute stream */
+    d->up[slot].tablesDone = 0;
     int rc_ = upload_set(d, h, flags, slot, d->s1);
     if (rc_) return rc_;
   } else {
@@ -1964,10 +2022,22 @@ extern "C" int ecpdev_run_batch(EcpDev *d, EcpBatch *h, int flags, int slot, dou
     B.clsOutElem = (const long long *)u.clsOutElem.p; B.clsPairBase = (const long long *)u.clsPairBase.p;
     B.clsQBase = (const long long *)u.clsQBase.p;
   }
-  SCRATCH(rshX, rshX, (size_t)h->nASlots * RSHX_STRIDE, double);
-  SCRATCH(uspX, uspX, (size_t)h->nASlots * USPX_STRIDE, double);
-  SCRATCH(omX, omX, (size_t)h->omTotal, double);
-  SCRATCH(F, F, (size_t)h->fRows * ECP_SMALL_SLOTS, double);
+  const bool tablesDone = d->up[slot].tablesDone != 0; /* computed behind the previous batch (ecpdev_prefetch_batch) */
+  d->up[slot].tablesDone = 0;
+  if (!tablesDone) { /* buffers of the set; the kernels are launched below */
+    EcpDev::UpSet &u = d->up[slot];
+    int rc_ = ensure(&u.rshX, ((size_t)h->nASlots * RSHX_STRIDE + 1) * sizeof(double));
+    if (!rc_) rc_ = ensure(&u.uspX, ((size_t)h->nASlots * USPX_STRIDE + 1) * sizeof(double));
+    if (!rc_) rc_ = ensure(&u.omX, ((size_t)h->omTotal + 1) * sizeof(double));
+    if (!rc_) rc_ = ensure(&u.F, ((size_t)h->fRows * ECP_SMALL_SLOTS + 1) * sizeof(double));
+    if (rc_) return rc_;
+  } else {
+    CK(cudaStreamWaitEvent(d->s1, d->evTab[slot], 0));
+  }
+  B.rshX = (double *)d->up[slot].rshX.p;
+  B.uspX = (double *)d->up[slot].uspX.p;
+  B.omX = (double *)d->up[slot].omX.p;
+  B.F = (double *)d->up[slot].F.p;
   SCRATCH(T, T, (size_t)h->tTotal, double);
   SCRATCH(gamma, gamma, (size_t)h->gTotal, double);
   SCRATCH(chi, chi, (size_t)h->gTotal, double);
@@ -2031,22 +2101,24 @@ extern "C" int ecpdev_run_batch(EcpDev *d, EcpBatch *h, int flags, int slot, dou
     CK(cudaEventRecord(d->ev[10], d->s2real));
   } else
     k_triprep<<<nblk(h->nTriples, 128), 128, 0, d->s1>>>(t, B);
-  k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
+  if (!tablesDone) k_atomslot<<<nblk(h->nASlots, 128), 128, 0, d->s1>>>(t, B);
   /* the type-1 chain (second stream) needs the triples and the atom slots, not Omega_X or F: it starts here and runs
    * beside the two table kernels, which are latency bound (k_Ftab2: 21 % of the issue slots) - at 8 GPUs the tables of a
    * rank (every rank tabulates F for nearly all shells) were 19 % of its pass */
   if (!d->serial) CK(cudaEventRecord(d->ev[11], d->s1));
-  k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
-  if (d->ftabCompact) { /* window-only tabulation into a cleared table (k_Ftab2) */
-    CK(cudaMemsetAsync(B.F, 0, (size_t)h->fRows * ECP_SMALL_SLOTS * sizeof(double), d->s1));
-    if (t.maxLECP - 1 + d->maxLBS <= 6)
-      k_Ftab2<6><<<h->nSSlots, 128, 0, d->s1>>>(t, B);
+  if (!tablesDone) {
+    k_omegaX<<<h->nASlots, 256, 0, d->s1>>>(t, B);
+    if (d->ftabCompact) { /* window-only tabulation into a cleared table (k_Ftab2) */
+      CK(cudaMemsetAsync(B.F, 0, (size_t)h->fRows * ECP_SMALL_SLOTS * sizeof(double), d->s1));
+      if (t.maxLECP - 1 + d->maxLBS <= 6)
+        k_Ftab2<6><<<h->nSSlots, 128, 0, d->s1>>>(t, B);
+      else
+        k_Ftab2<KM><<<h->nSSlots, 128, 0, d->s1>>>(t, B);
+    } else if (t.maxLECP - 1 + d->maxLBS <= 6)
+      k_Ftab<6><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
     else
-      k_Ftab2<KM><<<h->nSSlots, 128, 0, d->s1>>>(t, B);
-  } else if (t.maxLECP - 1 + d->maxLBS <= 6)
-    k_Ftab<6><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
-  else
-    k_Ftab<KM><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
+      k_Ftab<KM><<<h->nSSlots, ECP_SMALL_SLOTS, 0, d->s1>>>(t, B);
+  }
   launches += 4;
   if (h->devEnum && !d->serial) CK(cudaStreamWaitEvent(d->s1, d->ev[10], 0)); /* triples and their records are in place */
   CK(cudaEventRecord(d->ev[1], d->s1));
