@@ -199,29 +199,51 @@ def falg_per_kernel(workload, executed):
 
 KERNEL_OF = {"tables": "ms_tables", "fastT": "ms_fastT", "fallback": "ms_fallback", "link": "ms_link",
              "type1": "ms_type1", "chi": "ms_chi", "shift": "ms_shift"}
-KERNEL_NAME = {"tables": "k_atomslot+k_omegaX+k_Ftab", "fastT": "k_fastT+k_fastT2", "fallback": "k_fallbackG<KO>",
-               "link": "k_link<la+1,lb+1>", "type1": "k_t1prep+k_type1S<LAB>+k_type1L<LAB>", "chi": "k_chi",
-               "shift": "k_shiftJ+k_shiftI"}
-# ncu --set full captures of one launch on Au20 kept under profiles/ (DRAM traffic of the dominant kernel, per launch)
-NCU_FILE = {"fastT": "k_fastT2", "fallback": "k_fallbackG", "link": "k_link", "type1": "k_type1S", "chi": "k_chi",
-            "shift": "k_shiftI", "tables": "k_Ftab"}
+KERNEL_NAME = {"tables": "k_enum_fill+k_triprep+k_atomslot+k_omegaX+k_Ftab2", "fastT": "k_fastT+k_fastT2",
+               "fallback": "k_fbw_count+k_fbw_units+k_fbw_eval<KO>+k_fbw_book+k_fbw_final",
+               "link": "k_link4<la+1,lb+1,L>+k_link<la+1,lb+1>", "type1": "k_t1prep+k_type1S<LAB>+k_type1L<LAB>", "chi": "k_chi",
+               "shift": "k_shift2"}
+# ncu --set full captures kept under profiles/ (DRAM traffic of the dominant kernel family):
+#   Au20 (cfg3): one launch of the family's main kernel, profiles/r*/ncu_full_<kernel>.raw.csv
+#   cfg5: every launch of the family in ONE full-size batch, profiles/r*/ncu_full_cfg5_<family>_family.raw.csv, with the
+#         batch's executed triples in the .json beside it
+NCU_FILE = {"fastT": "k_fastT2", "fallback": "k_fbw_eval", "link": "k_link4", "type1": "k_type1S", "chi": "k_chi",
+            "shift": "k_shift2", "tables": "k_Ftab2"}
 
 
-def ncu_traffic(kernel_key):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the committed Au20 capture of that kernel (bytes), or None"""
+def _dram_bytes(path):
     import csv
+
+    rows = list(csv.reader(open(path)))
+    names, units = rows[0], rows[1]
+    tot = 0.0
+    for vals in rows[2:]:
+        if len(vals) != len(names):
+            continue
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = names.index(key)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1.0)
+            tot += float(vals[i].replace(",", "")) * scale
+    return tot
+
+
+def ncu_traffic(kernel_key, workload="cfg3", executed=None):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures, or None.
+    cfg3: one launch of the family's main kernel on Au20.  cfg5: the launches of the family in one full-size batch,
+    scaled to a step by executed triples (step) / executed triples (that batch)."""
     import glob
 
+    if workload == "cfg5":
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", f"ncu_full_cfg5_{kernel_key}_family.raw.csv")))[::-1]:
+            try:
+                meta = json.load(open(path.replace(".raw.csv", ".json")))
+                return _dram_bytes(path) * (float(executed) / float(meta["batch_triples"]) if executed else 1.0)
+            except Exception:
+                continue
+        return None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", f"ncu_full_{NCU_FILE.get(kernel_key, '')}.raw.csv")))[::-1]:
         try:
-            rows = list(csv.reader(open(path)))
-            names, units, vals = rows[0], rows[1], rows[2]
-            tot = 0.0
-            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                i = names.index(key)
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1.0)
-                tot += float(vals[i].replace(",", "")) * scale
-            return tot
+            return _dram_bytes(path)
         except Exception:
             continue
     return None
@@ -256,9 +278,11 @@ def roofline(workload, stats, nsteps, peak_tf, serial_stats=None):
         **extra,
         "bound": "fp64", "kernel": KERNEL_NAME[dom], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": ach / peak_tf if peak_tf else None,
-        "traffic": ncu_traffic(dom) if workload == "cfg3" else None,
-        "traffic_note": "DRAM bytes of one launch of the kernel family's main kernel on Au20 from the committed ncu --set full "
-                        "capture (profiles/); null for cfg5, which was not captured under ncu --set full",
+        "traffic": ncu_traffic(dom, "cfg5" if workload.startswith("cfg5") else workload, stats["executed_triples"])
+        if (workload == "cfg3" or workload == "cfg5") else None,
+        "traffic_note": "DRAM bytes from the committed ncu --set full captures (profiles/): cfg3 = one launch of the kernel "
+                        "family's main kernel on Au20; cfg5 = all launches of the dominant family in one full-size batch, "
+                        "scaled to the step by executed triples",
         "peak_source": "FP64 FMA probe kernel run by bench.py on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
                        "vendor figure ~37-40 TFLOP/s)",
         "algorithmic_flops_per_step": flops["total"], "algorithmic_flops_kernel": flops[dom], "flops_count": how,

@@ -7,8 +7,10 @@
  * Differences a caller can observe:
  *   - the work runs on a CUDA device (sm_100a); libECP_init returns NULL when none is usable - there is
  *     no CPU path;
- *   - derivative order n must be 0 and shellOrdering must be NULL;
- *     libECP_init returns NULL otherwise;
+ *   - derivative order n = 0 or 1 (n = 1: the callback receives the shifted-momentum blocks of the reference,
+ *     src/libecp.c:246-250,322-373; n = 2 returns NULL - the reference's own n = 2 output contains NaN blocks);
+ *     shellOrdering / lmax as in the reference (src/libecp.c:152-166): NULL = libint order, else the caller's
+ *     Cartesian component order for l = 0..lmax, lmax >= maxLambda + maxAlpha + 1;
  *   - shapes must satisfy maxLBS <= 5, L_ECP <= 6, L_ECP-1+maxLBS <= 10, maxLBS <= L_ECP+1.
  */
 #ifndef LIBECP_H
@@ -22,8 +24,8 @@ typedef struct _libECPHandle libECPHandle;
 
 /* Positional meaning is the reference call site's (src/libecp.c:372):
  *   cb(A, s1, la, shifta, B, s2, lb, shiftb, C, I, args)
- * s1/s2 are shell indices within atom A/B; I is row-major IJK_DIM(la) x IJK_DIM(lb), valid only during
- * the call.  Invoked on the caller's thread, in the reference's loop order (C, A, B>=A, s1, s2), type 1
+ * s1/s2 are shell indices within atom A/B; I is row-major IJK_DIM(la + shifta) x IJK_DIM(lb + shiftb) (the shifts are 0
+ * in an n = 0 run), valid only during the call.  Invoked on the caller's thread, in the reference's loop order (C, A, B>=A, s1, s2), type 1
  * then type 2 for every executed triple.  (The parameter names below are the reference typedef's.) */
 typedef void (*ECPCallback)(int A, int B, int C,
 			    int sa, int sb,

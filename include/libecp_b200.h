@@ -99,6 +99,17 @@ int libecp_b200_host_table(libECPHandle *h, const char *name, const double **ptr
 int libecp_b200_host_itable(libECPHandle *h, const char *name, int *out, int cap);
 /* executed triples of the whole job in the reference's loop order, rows (A,s1,la,B,s2,lb,C); host only */
 long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap);
+/* Spherical-harmonic output ("output to spherical AOs"; the reference carries TM_cart2sph / TM_sph2cart,
+ * src/transformations.c:28-141, but returns Cartesian blocks only).  The pure function (l, m) of a shell is
+ * sum_c cart2sph[l][m][c] * (Cartesian component c), with the reference's table and m = 0 .. 2l in its order;
+ * S = C^T M C is formed on the device from the resident Cartesian matrix of an n = 0 run.
+ *   _spherical_dim    : sum over shells of 2l + 1
+ *   _spherical_device : run the integrals, leave S (upper triangle, nSph x nSph, row-major) in device memory owned by the handle
+ *   _spherical_host   : the same, then S += into the caller's matrix (upper triangle, leading dimension rowdim)
+ * return values as libecp_b200_integrals_device. */
+int libecp_b200_spherical_dim(libECPHandle *h);
+int libecp_b200_spherical_device(libECPHandle *h, void **devS, int *nSph);
+int libecp_b200_spherical_host(libECPHandle *h, int rowdim, double *S);
 /* callback keys of the whole job in call order, rows (A,s1,la,shifta,B,s2,lb,shiftb,C), one row per executed (shifted)
  * triple = one type-1 and one type-2 callback (reference src/libecp.c:372); host only */
 long long libecp_b200_callback_keys(libECPHandle *h, int *out, long long cap);

@@ -28,7 +28,7 @@ EXPORTS = [
     "libecp_b200_set_serial_kernels", "libecp_b200_release_cache", "libecp_b200_build_only", "libecp_b200_owned_rows", "libecp_b200_pack_rows", "libecp_b200_unpack_rows",
     "libecp_b200_matrix_ptr", "libecp_b200_comm_unique_id", "libecp_b200_comm_init", "libecp_b200_comm_attach",
     "libecp_b200_allgather", "libecp_b200_device_sync", "libecp_b200_comm_free", "libecp_b200_callback_keys",
-    "libecp_b200_debug_unit",
+    "libecp_b200_debug_unit", "libecp_b200_spherical_dim", "libecp_b200_spherical_device", "libecp_b200_spherical_host",
 ]
 
 
@@ -260,6 +260,18 @@ class Handle:
         if f(C.c_void_p(self.h), what.encode(), int(n), _p(inp, _pd), inp.size, _p(ipar, _pi), ipar.size, _p(out, _pd), nout):
             raise RuntimeError("debug_unit failed: " + (lib().libecp_b200_last_error() or b"").decode())
         return out
+
+    def spherical_host(self):
+        """S = C^T M C of an n = 0 run in pure spherical-harmonic functions (upper triangle), on host memory"""
+        L = lib()
+        L.libecp_b200_spherical_dim.argtypes = [C.c_void_p]
+        n = int(L.libecp_b200_spherical_dim(C.c_void_p(self.h)))
+        S = np.zeros((n, n))
+        L.libecp_b200_spherical_host.argtypes = [C.c_void_p, C.c_int, _pd]
+        rc = L.libecp_b200_spherical_host(C.c_void_p(self.h), n, _p(S, _pd))
+        if rc < 0:
+            raise RuntimeError("spherical_host: " + (L.libecp_b200_last_error() or b"").decode())
+        return rc, S
 
     def callback_keys(self):
         """(A,s1,la,shifta,B,s2,lb,shiftb,C) of every executed (shifted) triple in call order (host only)"""

@@ -445,6 +445,33 @@ int libecp_b200_integrals_device(libECPHandle *h, void **devMatrix, int *nAO) {
   return rc;
 }
 
+/* spherical-harmonic (pure 5d / 7f ...) form of the result: dimension, device-resident matrix, host accumulation */
+int libecp_b200_spherical_dim(libECPHandle *h) {
+  int n = 0;
+  for (int s = 0; s < h->tab->v.nrShells; s++) n += 2 * h->tab->v.shellL[s] + 1;
+  return n;
+}
+int libecp_b200_spherical_device(libECPHandle *h, void **devS, int *nSph) {
+  if (nSph) *nSph = libecp_b200_spherical_dim(h);
+  if (h->empty) {
+    if (devS) *devS = NULL;
+    return 0;
+  }
+  void *dm = NULL;
+  const int rc = libecp_b200_integrals_device(h, &dm, NULL);
+  if (rc < 0) return rc;
+  if (ecpdev_spherical(h->dev, devS, nSph)) return -1;
+  return rc;
+}
+int libecp_b200_spherical_host(libECPHandle *h, int rowdim, double *S) {
+  if (h->empty) return 0;
+  void *dm = NULL;
+  const int rc = libecp_b200_integrals_device(h, &dm, NULL);
+  if (rc < 0) return rc;
+  if (ecpdev_spherical_add_to_host(h->dev, S, rowdim)) return -1;
+  return rc;
+}
+
 void *libecp_b200_matrix_ptr(libECPHandle *h) { return (h && h->dev) ? ecpdev_matrix_ptr(h->dev) : NULL; }
 
 int libecp_b200_pair_owner(libECPHandle *h, int a, int b, int world) { return ecp_pair_owner(h->tab, a, b, world); }
@@ -690,6 +717,7 @@ int libecp_b200_host_table(libECPHandle *h, const char *name, const double **ptr
   if (!strcmp(name, "large_ws")) RET(t->large_ws, v->largeSlots);
   if (!strcmp(name, "typeUtab")) RET(t->typeUtab, v->nTypes * v->maxLECP * v->nU * ECP_SMALL_SLOTS);
   if (!strcmp(name, "typeUL")) RET(t->typeUL, v->nTypes * ECP_SMALL_SLOTS);
+  if (!strcmp(name, "cart2sph")) RET(t->cart2sph, v->ncart2sph);
 #undef RET
   *ptr = NULL;
   return 0;

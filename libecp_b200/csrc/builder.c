@@ -679,7 +679,9 @@ int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centr
 #endif
   const int prof = getenv("LIBECP_B200_BUILD_PROFILE") != NULL;
   const double tp0 = prof ? omp_get_wtime() : 0.0;
-  const double ratio = bb->triPerPair > 0.0 ? bb->triPerPair : 0.5;
+  /* executed triples per tested shell pair: measured on the batches run so far; before the first one the upper bound 1
+   * (a batch can then only come out smaller than asked for) */
+  const double ratio = bb->triPerPair > 0.0 ? bb->triPerPair : 1.0;
   /* the screening of a batch is a few hundred microseconds of work per thread: a small team, so that one thread losing
    * its core to another process (NCCL proxy, a sampler) cannot hold a large team at the loop's barrier for a scheduler
    * quantum - measured at 2 and 8 ranks: builds of 3 ms that took 10-30 ms now and then */

@@ -911,6 +911,11 @@ struct EcpDev {
   const EcpBatch *upBatch[2]; /* batch whose arrays sit in the set (NULL: none) */
   long long upBytes[2];
   Buf rshX, uspX, omX, F, T, gamma, chi, Q, rshP, sP, blocks, tfail, tflags, items, counters;
+  /* spherical-harmonic output (ecpdev_spherical) */
+  Buf sphMatrix;
+  int nSph;
+  const int *sphShell, *shellSph, *c2sOff;
+  const double *c2s;
   double *matrix;
   size_t matrixBytes;
   int matrixKnown, dirtyAll, nDirty; /* matrix is zero outside the upper-triangle parts of the dirty rows */
@@ -1242,6 +1247,29 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     cudaStreamSynchronize(d->s1);
     free(lut);
   }
+  { /* spherical output: cart2sph of the shells' momenta, spherical row <-> shell maps */
+    int off[ECP_MAX_LBS + 2], acc = 0;
+    for (int l = 0; l <= ECP_MAX_LBS; l++) {
+      off[l] = acc;
+      acc += (2 * l + 1) * ((l + 1) * (l + 2) / 2);
+    }
+    int nSph = 0;
+    for (int s2 = 0; s2 < h->nrShells; s2++) nSph += 2 * h->shellL[s2] + 1;
+    int *ssph = (int *)malloc(((size_t)h->nrShells + 1) * sizeof(int)), *sof = (int *)malloc(((size_t)nSph + 1) * sizeof(int));
+    for (int s2 = 0, k = 0; s2 < h->nrShells; s2++) {
+      ssph[s2] = k;
+      for (int m = 0; m < 2 * h->shellL[s2] + 1; m++) sof[k++] = s2;
+    }
+    d->nSph = nSph;
+    d->shellSph = upload_const(d, ssph, (size_t)h->nrShells);
+    d->sphShell = upload_const(d, sof, (size_t)(nSph > 0 ? nSph : 1));
+    d->c2sOff = upload_const(d, off, (size_t)ECP_MAX_LBS + 1);
+    const int need = off[h->maxLBS] + (2 * h->maxLBS + 1) * ((h->maxLBS + 1) * (h->maxLBS + 2) / 2);
+    d->c2s = upload_const(d, h->cart2sph, (size_t)(need < h->ncart2sph ? need : h->ncart2sph));
+    cudaStreamSynchronize(d->s1);
+    free(ssph);
+    free(sof);
+  }
   t.clsLa = upload_const(d, h->clsLa, h->nClasses);
   t.clsLb = upload_const(d, h->clsLb, h->nClasses);
   t.clsL = upload_const(d, h->clsL, h->nClasses);
@@ -1352,7 +1380,10 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
   Buf *bs[ECP_NBUF];
   const int n = collect_bufs(d, bs);
   bool parked = false;
-  if (d->device >= 0 && d->device < ECP_MAXDEV) {
+  /* LIBECP_B200_NO_PARK=1: give the scratch and the result buffer back to the driver with the handle (a caller that
+   * shares the GPU with other allocators); default: parked for the next handle on this device, libecp_b200_release_cache
+   * frees them */
+  if (d->device >= 0 && d->device < ECP_MAXDEV && !getenv("LIBECP_B200_NO_PARK")) {
     std::lock_guard<std::mutex> lk(g_devCacheMu);
     DevCache &c = g_devCache[d->device];
     if (!c.valid) {
@@ -1370,6 +1401,7 @@ extern "C" void ecpdev_destroy(EcpDev *d) {
     if (d->matrix) cudaFreeAsync(d->matrix, d->s1);
   }
   comm_release(d);
+  if (d->sphMatrix.p) cudaFreeAsync(d->sphMatrix.p, d->s1);
   for (int k = 0; k < 2; k++)
     if (d->enumHost[k]) ecpdev_pinned_free(d->enumHost[k]);
   if (d->agRows.p) cudaFreeAsync(d->agRows.p, d->s1);
@@ -1622,6 +1654,76 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   return 0;
 }
 extern "C" void *ecpdev_matrix_ptr(EcpDev *d) { return d->matrix; }
+
+/* ---- spherical-harmonic output (scope row f4, second half: "output to spherical AOs") ----
+ * The reference carries the Cartesian -> real-spherical-harmonic matrix (TM_cart2sph, src/transformations.c:28-87; its
+ * inverse TM_sph2cart :91-141 is unused) but offers no spherical output; callers with pure (5d / 7f) functions transform
+ * the Cartesian matrix themselves.  Here the resident matrix is transformed on the device, per shell pair
+ *     S[(a,m)][(b,m')] = sum_{c,c'} cart2sph[la][m][c] cart2sph[lb][m'][c'] M[(a,c)][(b,c')],
+ * with the same table (bit-identical to the reference's) and the handle's component order.  A thread per element of the
+ * upper triangle of S; the diagonal shell blocks of M hold their upper triangle only (src/getIntegrals.c:36-41) and are
+ * read symmetrically. */
+__global__ void k_cart2sph_matrix(const double *__restrict__ M, int nAO, double *__restrict__ S, int nSph,
+                                  const int *__restrict__ sphShell, const int *__restrict__ shellSph,
+                                  const int *__restrict__ shellAO, const int *__restrict__ shellL,
+                                  const double *__restrict__ c2s, const int *__restrict__ c2sOff) {
+  const int i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nSph || j < i) return;
+  const int a = sphShell[i], b = sphShell[j];
+  const int la = shellL[a], lb = shellL[b], na = (la + 1) * (la + 2) / 2, nb = (lb + 1) * (lb + 2) / 2;
+  const double *ca = c2s + c2sOff[la] + (i - shellSph[a]) * na, *cb = c2s + c2sOff[lb] + (j - shellSph[b]) * nb;
+  const int r0 = shellAO[a], c0 = shellAO[b];
+  double acc = 0.0;
+  for (int c = 0; c < na; c++) {
+    double row = 0.0;
+    for (int cc = 0; cc < nb; cc++) {
+      int r = r0 + c, q = c0 + cc;
+      if (r > q) { /* diagonal shell block: mirror */
+        const int tsw = r;
+        r = q;
+        q = tsw;
+      }
+      row = fma(cb[cc], M[(size_t)r * nAO + q], row);
+    }
+    acc = fma(ca[c], row, acc);
+  }
+  S[(size_t)i * nSph + j] = acc;
+}
+extern "C" int ecpdev_spherical(EcpDev *d, void **devS, int *nSphOut) {
+  CK(cudaSetDevice(d->device));
+  if (!d->matrix) {
+    snprintf(g_err, sizeof(g_err), "ecpdev_spherical: no result matrix yet");
+    return -1;
+  }
+  g_allocStream = d->s1;
+  const int nSph = d->nSph;
+  int rc = ensure(&d->sphMatrix, (size_t)nSph * nSph * sizeof(double));
+  if (rc) return rc;
+  CK(cudaMemsetAsync(d->sphMatrix.p, 0, (size_t)nSph * nSph * sizeof(double), d->s1));
+  dim3 grid((nSph + 127) / 128, nSph);
+  k_cart2sph_matrix<<<grid, 128, 0, d->s1>>>(d->matrix, d->nAO, (double *)d->sphMatrix.p, nSph, d->sphShell, d->shellSph,
+                                            d->t.shellAO, d->t.shellL, d->c2s, d->c2sOff);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(d->s1));
+  if (devS) *devS = d->sphMatrix.p;
+  if (nSphOut) *nSphOut = nSph;
+  return 0;
+}
+extern "C" int ecpdev_spherical_add_to_host(EcpDev *d, double *host, int rowdim) {
+  void *dS = NULL;
+  int n = 0;
+  int rc = ecpdev_spherical(d, &dS, &n);
+  if (rc) return rc;
+  double *tmp = (double *)malloc((size_t)n * n * sizeof(double));
+  if (!tmp) return -1;
+  CK(cudaMemcpy(tmp, dS, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++)
+    for (int j = i; j < n; j++) host[(size_t)i * rowdim + j] += tmp[(size_t)i * n + j];
+  free(tmp);
+  return 0;
+}
 /* make the handle's device current on the calling host thread (the builder thread allocates page-locked memory) */
 extern "C" void ecpdev_bind_thread(EcpDev *d) {
   if (d) cudaSetDevice(d->device);

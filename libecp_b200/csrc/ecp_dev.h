@@ -38,6 +38,8 @@ typedef struct {
   const double *fac, *dfac;       int nfac;
   const int *ijk, *ijkIndex;      /* [3*C_DIM(tmDim)], [ijkDim^3]                  */
   const double *poly2sph;         /* [C_DIM(tmDim)][L_DIM(tmDim)]                  */
+  const double *cart2sph;         /* packed [l][m][c] (reference src/transformations.h:13-14), l <= tmDim */
+  int ncart2sph;
   const double *omega;            /* [L_DIM(maxLECP)][L_DIM(maxLambda)][C_DIM(maxAlpha)] */
   int nomega;
   const double *binom;            /* [(maxLBS+1)^2] n over k                       */
@@ -146,6 +148,10 @@ int ecpdev_matrix_rows(EcpDev *d, int dir, const int *rows, long long nrows, voi
 int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned /* [nAO] or NULL */,
                               long long *bytes, int async /* 1: download stream only, rows are final */);
 void *ecpdev_matrix_ptr(EcpDev *d);
+/* spherical-harmonic form of the resident matrix: S = C^T M C per shell pair with the handle's cart2sph table, upper
+ * triangle, nSph = sum over shells of 2l+1; the buffer belongs to the handle */
+int ecpdev_spherical(EcpDev *d, void **devS, int *nSph);
+int ecpdev_spherical_add_to_host(EcpDev *d, double *host, int rowdim);
 /* C-ABI collective of a sharded device-resident result (NCCL bound with dlopen): unique id for the caller to distribute,
  * communicator from that id (comm == NULL) or adopted from the caller, shard layout of all ranks, the all-gather itself */
 int ecpdev_comm_unique_id(void *id128);

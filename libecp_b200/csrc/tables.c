@@ -781,6 +781,8 @@ EcpTables *ecp_tables_build(int nrAtoms, const double *geometry, const int *shel
   v->ijk = t->ijk;
   v->ijkIndex = t->ijkIndex;
   v->poly2sph = t->poly2sph;
+  v->cart2sph = t->cart2sph;
+  v->ncart2sph = c2s_size(v->tmDim, t->fac);
   v->omega = t->omega;
   v->binom = t->binom;
   v->small_r = t->small_rs;

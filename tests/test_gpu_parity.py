@@ -506,3 +506,31 @@ def test_device_enumeration_matches_host_builder():
         assert np.allclose(M0, M1, rtol=1e-13, atol=1e-15), name
         if name:
             assert_parity(M1, load_matrix(name), name)
+
+
+@pytest.mark.parametrize("name", ["cfg2", "au4", "cfg4b"])
+def test_spherical_output_is_the_transformed_cartesian_matrix(name):
+    """scope row f4, "output to spherical AOs": libecp_b200_spherical_host returns S = C^T M C per shell pair with the
+    reference's Cartesian -> real-spherical-harmonic table (TM_cart2sph, src/transformations.c:28-87) - checked against
+    the same transformation of the reference's Cartesian matrix in numpy; the trace-like invariant: an s shell is
+    unchanged up to the constant cart2sph[0][0][0]"""
+    s = SMALL[name]()
+    ref = load_matrix(name)
+    full = ref + np.triu(ref, 1).T  # the Cartesian matrix is symmetric; the reference stores its upper triangle
+    with capi.Handle(s) as h:
+        c2s = h.host_table("cart2sph")
+        rc, S = h.spherical_host()
+    assert rc == 0
+    ls = np.asarray(s["lBS"])
+    nc = [(l + 1) * (l + 2) // 2 for l in ls]
+    aoff = np.concatenate([[0], np.cumsum(nc)])
+    soff = np.concatenate([[0], np.cumsum(2 * ls + 1)])
+    toff = np.concatenate([[0], np.cumsum([(2 * l + 1) * (l + 1) * (l + 2) // 2 for l in range(ls.max() + 1)])])
+    C = np.zeros((aoff[-1], soff[-1]))
+    for k, l in enumerate(ls):
+        blk = c2s[toff[l]:toff[l + 1]].reshape(2 * l + 1, nc[k])  # [m][c]
+        C[aoff[k]:aoff[k + 1], soff[k]:soff[k + 1]] = blk.T
+    want = np.triu(C.T @ full @ C)
+    assert S.shape == want.shape and np.all(np.tril(S, -1) == 0.0)
+    assert np.all(np.abs(S - want) <= 1e-12 + 1e-10 * np.abs(want)), np.abs(S - want).max()
+    assert np.count_nonzero(S) > 0
