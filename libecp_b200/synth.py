@@ -158,6 +158,32 @@ def shell_order(lmax: int, kind: str = "libint"):
     return np.array(out, np.int32)
 
 
+def deriv_triangle():
+    """three atoms in general position with three different shapes - TZ(2) + ECP(4), TZ(1) + ECP(5, scaled exponents) and
+    TZ(2) without an ECP: first-derivative triples with A != B != C, mixed L and an atom that is no ECP centre
+    (needs lbs + n <= L - 1 on every centre)"""
+    return assemble("deriv_triangle", [(0.0, 0.0, 0.0), (2.9, 0.4, -0.6), (-0.7, 3.1, 1.2)],
+                    [tz_basis(2), tz_basis(1), tz_basis(2)], [ecp_set(4), ecp_set(5, 0.8), None])
+
+
+def random_system(seed: int):
+    """small random molecule for randomized parity runs: 2-4 atoms at random positions (>= 1.5 bohr apart), every atom a
+    TZ(0..3) basis, ECP(L) with L >= lbs + 1 on a random non-empty subset of the atoms, random exponent scale"""
+    rng = np.random.default_rng(seed)
+    nat = int(rng.integers(2, 5))
+    pts = []
+    while len(pts) < nat:
+        p = rng.uniform(-3.5, 3.5, 3)
+        if all(np.linalg.norm(p - q) >= 1.5 for q in pts):
+            pts.append(p)
+    lbs = [int(rng.integers(0, 4)) for _ in range(nat)]
+    lmax = max(lbs)
+    has = rng.random(nat) < 0.6
+    has[int(rng.integers(0, nat))] = True
+    ecps = [ecp_set(int(rng.integers(lmax + 1, 6)), float(rng.uniform(0.6, 1.6))) if has[i] else None for i in range(nat)]
+    return assemble(f"random_{seed}", [tuple(p) for p in pts], [tz_basis(l) for l in lbs], ecps)
+
+
 def cfg4(variant: str = "a"):
     """high-angular-momentum stress: (a) TZ(4)+ECP(5), (b) TZ(5)+ECP(6); 2 atoms on the z axis."""
     lbs, L = (4, 5) if variant == "a" else (5, 6)

@@ -70,6 +70,7 @@ def main():
     if "--deriv" in sys.argv:  # next scope row (f1): first derivatives, two shapes; nothing else is regenerated
         save_blocks(ref, "deriv1_tz2_L4", synth.deriv_pair(2, 4), n=1)
         save_blocks(ref, "deriv1_tz3_L5", synth.deriv_pair(3, 5), n=1)
+        save_blocks(ref, "deriv1_triangle", synth.deriv_triangle(), n=1)
         return
     if "--order" in sys.argv:  # scope row f4: caller-supplied Cartesian component order (src/libecp.c:152-166)
         save_blocks(ref, "order_rev_cfg2", synth.cfg2(), ordering=synth.shell_order(10, "reversed"), lmax=10)

@@ -429,6 +429,32 @@ def test_custom_shell_ordering_too_short_is_rejected():
         capi.Handle(synth.cfg2(), ordering=synth.shell_order(9, "reversed"), lmax=9)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_small_systems_match_oracle(oracle, seed):
+    """randomized parity: 2-4 atoms at random positions, TZ(0..3) bases, ECP(L <= 5) on a random subset of the atoms with
+    random exponent scales (synth.random_system) - matrix and callback sequence against the oracle run live"""
+    s = synth.random_system(seed)
+    ref = oracle.get_integrals(s)
+    got = capi.get_integrals(s)
+    assert_parity(got, ref, s["name"])
+    assert np.all(np.tril(got, -1) == 0.0)
+    rc_o, ro = oracle.callbacks(s, keep_blocks=False)
+    with capi.Handle(s) as h:
+        rc, rg = h.callbacks(keep_blocks=False)
+    assert rc == rc_o == 0 and [r[:9] for r in rg] == [r[:9] for r in ro]
+
+
+def test_first_derivative_blocks_triangle():
+    """row f1 on three atoms in general position with mixed shapes and one atom without ECP (synth.deriv_triangle):
+    triples with A != B != C, both ECP types, every skip rule of src/libecp.c:303-330"""
+    keys, off, vals = load_blocks("deriv1_triangle")
+    with capi.Handle(synth.deriv_triangle(), n=1) as h:
+        rc, recs = h.callbacks()
+    assert rc == 0 and len(recs) == len(keys)
+    assert all(tuple(keys[k]) == r[:9] for k, r in enumerate(recs))
+    assert_parity(np.concatenate([r[9] for r in recs]), vals, "deriv1_triangle")
+
+
 @pytest.mark.parametrize("name,lbs,L", [("deriv1_tz2_L4", 2, 4), ("deriv1_tz3_L5", 3, 5)])
 def test_first_derivative_blocks_match_golden(name, lbs, L):
     """scope row f1: derivative order n = 1 - the shifted-momentum blocks handed to the callback

@@ -627,6 +627,14 @@ def test_custom_shell_ordering_tables():
 DERIV = {"deriv1_tz2_L4": (2, 4), "deriv1_tz3_L5": (3, 5)}
 
 
+def test_derivative_callback_keys_triangle():
+    """three atoms, mixed shapes, one atom without ECP: the key sequence of the n = 1 run is the reference's"""
+    d = np.load(os.path.join(GOLDEN, "deriv1_triangle_blocks.npz"))
+    with capi.Handle(synth.deriv_triangle(), n=1, tables_only=True) as h:
+        keys = h.callback_keys()
+    assert np.array_equal(keys, d["keys"][0::2]) and np.array_equal(keys, d["keys"][1::2])
+
+
 @pytest.mark.parametrize("name", list(DERIV))
 def test_derivative_callback_keys_match_reference(name):
     """scope row f1, host part: the (shifted) triples of a first-derivative run and their call order
