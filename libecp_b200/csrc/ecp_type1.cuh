@@ -32,6 +32,13 @@
 #include <utility>
 
 #define T1_MAXSEG 24
+/* resident blocks of 128 threads per SM the type-1 kernels are compiled for (registers <= 65536 / (128 MINB)) */
+#ifndef T1_MINB_LO
+#define T1_MINB_LO 5
+#endif
+#ifndef T1_MINB_MID
+#define T1_MINB_MID 4
+#endif
 struct T1Segs {
   int nseg;
   long long start[T1_MAXSEG];      /* first pair of the segment                      */
@@ -119,7 +126,7 @@ __device__ __forceinline__ void t1_fill_point(const DevT &t, double r, double za
 
 /* ---------------------------------------------------------------------------------------------- */
 template <int LAB>
-__global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_type1S(DevT t, DevB b, T1Segs segs, int *workCtr, int *failCount, int *failList,
+__global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_MINB_MID : 3))) k_type1S(DevT t, DevB b, T1Segs segs, int *workCtr, int *failCount, int *failList,
                                                 unsigned long long *failMask) {
   using Cfg = T1Cfg<LAB>;
   constexpr int NQ = Cfg::NQ, NQL = Cfg::NQL;
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_ty
 
 /* ---------------------------------------------------------------------------------------------- */
 template <int LAB>
-__global__ void __launch_bounds__(128, (LAB <= 3 ? 5 : (LAB <= 6 ? 4 : 3))) k_type1L(DevT t, DevB b, int *workCtr, const int *failCount, const int *failList,
+__global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_MINB_MID : 3))) k_type1L(DevT t, DevB b, int *workCtr, const int *failCount, const int *failList,
                                                 const unsigned long long *failMask, int *errFlag) {
   using Cfg = T1Cfg<LAB>;
   constexpr int NQ = Cfg::NQ, NQL = Cfg::NQL;

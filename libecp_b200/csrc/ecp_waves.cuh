@@ -211,8 +211,11 @@ __device__ __forceinline__ void fbw_bessel_sel(const DevT &t, int lmax, double z
 
 /* ---- one thread per (open unit, point of the wave); a warp = 32 consecutive slots of one unit ----
  * S = points of the wave per unit (32 for levels 0..4, 2^lev for a later level), slot0 = first slot of the wave */
+#ifndef FBW_MINB
+#define FBW_MINB 8 /* 64 registers, 132 bytes of spills: 0.82 -> 0.77 ms on Au20 against the unbounded 80-register build */
+#endif
 template <int KO>
-__global__ void __launch_bounds__(128) k_fbw_eval(DevT t, DevB b, const FbwUnit *units, const FbwQ *qd, const FbwOpen *open,
+__global__ void __launch_bounds__(128, FBW_MINB) k_fbw_eval(DevT t, DevB b, const FbwUnit *units, const FbwQ *qd, const FbwOpen *open,
                                                  long long nWarps, int S, int slot0, double *vals) {
   constexpr int RS = 3 * (KO + 1); /* odd for even KO: conflict-free rows */
   __shared__ double rows[128 * RS];
