@@ -7,11 +7,11 @@
  * Differences a caller can observe:
  *   - the work runs on a CUDA device (sm_100a); libECP_init returns NULL when none is usable - there is
  *     no CPU path;
- *   - derivative order n = 0 or 1 (n = 1: the callback receives the shifted-momentum blocks of the reference,
- *     src/libecp.c:246-250,322-373; n = 2 returns NULL - the reference's own n = 2 output contains NaN blocks);
+ *   - derivative order n = 0, 1 or 2 (n >= 1: the callback receives the shifted-momentum blocks of the reference,
+ *     src/libecp.c:246-250,322-373; n = 2, shifts (+1,0) / (0,+1): IJK_DIM(la) x IJK_DIM(lb) elements, :362-369);
  *     shellOrdering / lmax as in the reference (src/libecp.c:152-166): NULL = libint order, else the caller's
  *     Cartesian component order for l = 0..lmax, lmax >= maxLambda + maxAlpha + 1;
- *   - shapes must satisfy maxLBS <= 5, L_ECP <= 6, L_ECP-1+maxLBS <= 10, maxLBS <= L_ECP+1.
+ *   - shapes must satisfy (with maxLBS + n for maxLBS in a derivative run) maxLBS <= 5, L_ECP <= 6, L_ECP-1+maxLBS <= 10, maxLBS <= L_ECP+1.
  */
 #ifndef LIBECP_H
 #define LIBECP_H 1

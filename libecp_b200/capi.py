@@ -126,8 +126,9 @@ class Handle:
 
     def __init__(self, s, tol=1e-12, acc=1e-14, large=1024, n=0, tables_only=False, ordering=None, lmax=-1):
         """ordering: int32 array in the layout of cartesianShellOrder(lmax) - the caller's Cartesian component order
-        (reference src/libecp.c:152-166); n: derivative order (0 or 1)"""
+        (reference src/libecp.c:152-166); n: derivative order (0, 1 or 2)"""
         L = lib()
+        self.n = n
         self.s = s  # keeps the borrowed arrays alive (the handle borrows them, reference src/libecp.c:68-74)
         self.ordering = None if ordering is None else np.ascontiguousarray(ordering, np.int32)
         if tables_only:
@@ -166,8 +167,12 @@ class Handle:
     def callbacks(self, keep_blocks=True):
         recs = []
 
+        order = self.n
+
         def cb(A, s1, la, sha, B, s2, lb, shb, Cc, I, args):
-            n = ((la + sha + 1) * (la + sha + 2) // 2) * ((lb + shb + 1) * (lb + shb + 2) // 2)
+            # second derivatives, shifts (+1,0) / (0,+1): blocks at the unshifted momenta (reference src/libecp.c:362-369)
+            ea, eb = (0, 0) if order == 2 and (sha, shb) in ((1, 0), (0, 1)) else (sha, shb)
+            n = ((la + ea + 1) * (la + ea + 2) // 2) * ((lb + eb + 1) * (lb + eb + 2) // 2)
             blk = np.ctypeslib.as_array(I, shape=(n,)).copy() if keep_blocks else None
             recs.append((A, s1, la, sha, B, s2, lb, shb, Cc, blk))
 

@@ -79,9 +79,8 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
                           double *dECP, double *aECP, int *shellsBS, int *lBS, int *KBS, double *dBS, double *aBS,
                           int n, int lmax, int *shellOrdering, int largeGridOrder, double tolerance, double accuracy) {
   g_apierr[0] = 0; /* lmax is only read together with shellOrdering (reference src/libecp.c:152-166) */
-  if (n != 0 && n != 1) {
-    /* n = 2: the reference's own output contains NaN blocks on every shape tried (tests/golden/make_golden.py) */
-    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d not supported (n = 0 or 1)", n);
+  if (n < 0 || n > 2) {
+    snprintf(g_apierr, sizeof(g_apierr), "libecp_b200: derivative order n=%d not supported (n = 0, 1 or 2)", n);
     return NULL;
   }
   libECPHandle *h = calloc(1, sizeof(*h));
@@ -98,45 +97,58 @@ libECPHandle *libECP_init(int nrAtoms, double *geometry, int *shellsECP, int *lE
     if (e && atoll(e) > 0) h->maxTriples = atoll(e);
   }
   EcpBuildOpts opts = {shellOrdering, lmax, NULL, 0, NULL, NULL};
-  if (n == 1) {
-    /* First derivatives (scope row f1; reference src/libecp.c:203-210,246-250,322-330): a derivative block is an
-     * ordinary block between shells shifted in angular momentum - l + 1 with the coefficients d zeta (src/type1.c:239-246,
-     * src/type2.c:263-269,459-462) or l - 1 with d - screened as the unshifted shell (src/type2.c:251).  The handle
-     * therefore runs on an expanded shell list: every shell is followed by its two shifted copies; the builder pairs
-     * them as the reference's shift table prescribes.  All sizes (tables, Bessel depth, classes) follow from the
-     * expanded list exactly as the reference derives them from maxLBS + n. */
+  if (n >= 1) {
+    /* Derivatives (scope row f1; reference src/libecp.c:203-210,246-250,322-330): a derivative block is an ordinary
+     * block between shells shifted in angular momentum - l + k with the coefficients d zeta^k (src/type1.c:239-246,
+     * src/type2.c:263-269,459-462) or l - k with d - screened as the unshifted shell (src/type2.c:251).  The handle
+     * therefore runs on an expanded shell list: every shell is followed by its shifted copies (ecp_deriv_copy: n = 1:
+     * l+1, l-1; n = 2: l+1, l+2, l with d zeta, l-1, l-2; copies below l = 0 are left out, they come last); the builder
+     * pairs them as the reference's shift table prescribes.  All sizes (tables, Bessel depth, classes) follow from the
+     * expanded list exactly as the reference derives them from maxLBS + n.
+     * n = 2, shifts (+1,0) and (0,+1) (src/libecp.c:362-369): the terms of a second derivative that raise one Cartesian
+     * exponent and lower another - momentum l, coefficients d zeta.  The reference evaluates chi / gamma at l + 1 and
+     * shifts only their lower-degree part (the arrays are cumulative over the momenta); here the copy "l with d zeta"
+     * gives the same block directly. */
+    const int ncopy = ecp_deriv_ncopies(n);
     int nsh = 0, nprim = 0;
     for (int i = 0; i < nrAtoms; i++)
       for (int j = 0; j < shellsBS[i]; j++) nprim += KBS[nsh++];
     h->xShells = malloc((nrAtoms + 1) * sizeof(int));
-    h->xL = malloc((3 * nsh + 1) * sizeof(int));
-    h->xK = malloc((3 * nsh + 1) * sizeof(int));
-    h->xD = malloc((3 * nprim + 1) * sizeof(double));
-    h->xA = malloc((3 * nprim + 1) * sizeof(double));
-    int *par = malloc((3 * nsh + 1) * sizeof(int)), *vsh = malloc((3 * nsh + 1) * sizeof(int));
-    int *vloc = malloc((3 * nsh + 1) * sizeof(int));
+    h->xL = malloc((ncopy * nsh + 1) * sizeof(int));
+    h->xK = malloc((ncopy * nsh + 1) * sizeof(int));
+    h->xD = malloc((ncopy * nprim + 1) * sizeof(double));
+    h->xA = malloc((ncopy * nprim + 1) * sizeof(double));
+    int *par = malloc((ncopy * nsh + 1) * sizeof(int)), *vsh = malloc((ncopy * nsh + 1) * sizeof(int));
+    int *vloc = malloc((ncopy * nsh + 1) * sizeof(int));
     int s = 0, p = 0, xs = 0, xp = 0;
     for (int i = 0; i < nrAtoms; i++) {
       int cnt = 0;
       for (int j = 0; j < shellsBS[i]; j++, s++) {
         const int l = lBS[s], K = KBS[s], x0 = xs;
-        for (int c = 0; c < (l >= 1 ? 3 : 2); c++, xs++, cnt++) {
-          h->xL[xs] = c == 0 ? l : (c == 1 ? l + 1 : l - 1);
+        for (int c = 0; c < ncopy; c++) {
+          int dl, zp;
+          ecp_deriv_copy(n, c, &dl, &zp);
+          if (l + dl < 0) break; /* the lowered copies come last */
+          h->xL[xs] = l + dl;
           h->xK[xs] = K;
           par[xs] = x0;
-          vsh[xs] = c == 0 ? 0 : (c == 1 ? +1 : -1);
+          vsh[xs] = c; /* 0 = the caller's shell, > 0 = a copy */
           vloc[xs] = j;
           for (int k = 0; k < K; k++, xp++) {
+            double dd = dBS[p + k];
+            for (int q = 0; q < zp; q++) dd *= aBS[p + k]; /* da *= zeta  (src/type2.c:267-269) */
             h->xA[xp] = aBS[p + k];
-            h->xD[xp] = c == 1 ? dBS[p + k] * aBS[p + k] : dBS[p + k]; /* da *= zeta  (src/type2.c:267-269) */
+            h->xD[xp] = dd;
           }
+          xs++;
+          cnt++;
         }
         p += K;
       }
       h->xShells[i] = cnt;
     }
     opts.screenParent = par;
-    opts.deriv = 1;
+    opts.deriv = n;
     opts.virtShift = vsh;
     opts.virtLocal = vloc;
     h->tab = ecp_tables_build(nrAtoms, geometry, shellsECP, lECP, KECP, nECP, dECP, aECP, h->xShells, h->xL, h->xK, h->xD,
@@ -405,7 +417,8 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
       const EcpBatchBuf *bb = cur;
       for (int k = 0; k < bb->nCanon; k++) {
         const int sa = bb->cnShA[k], sb = bb->cnShB[k]; /* blocks of a derivative run have the shifted sizes */
-        const int nb = IJK_DIM(bb->cnLa[k] + sa) * IJK_DIM(bb->cnLb[k] + sb);
+        const int mixed = h->tab->deriv == 2 && sa + sb == 1 && sa >= 0 && sb >= 0; /* momentum unchanged (src/libecp.c:362-369) */
+        const int nb = mixed ? IJK_DIM(bb->cnLa[k]) * IJK_DIM(bb->cnLb[k]) : IJK_DIM(bb->cnLa[k] + sa) * IJK_DIM(bb->cnLb[k] + sb);
         double *blk = h->hostBlocks + bb->cnOut[k];
         call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], sa, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], sb, bb->cnC[k], blk, args);
         call(bb->cnA[k], bb->cnS1[k], bb->cnLa[k], sa, bb->cnB[k], bb->cnS2[k], bb->cnLb[k], sb, bb->cnC[k], blk + nb, args);

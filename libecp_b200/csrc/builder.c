@@ -169,14 +169,43 @@ static double dist3(const double *a, const double *b) { /* src/util.c:109-116 */
   return sqrt(x * x + y * y + z * z);
 }
 
-/* Shift s = 0..3 of a first-derivative run: (+1,0), (-1,0), (0,+1), (0,-1) on (la, lb) (reference src/libecp.c:246-247).
- * Returns 0 when the reference skips it (:325-330): momentum below zero, or the shifted function sits on the ECP centre
- * (translational invariance).  *a2 / *b2 = slot offset of the shifted copy behind its unshifted shell: 0, +1 (l + 1),
- * +2 (l - 1). */
-int ecp_deriv_shift(int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2) {
-  static const int sa[4] = {+1, -1, 0, 0}, sb[4] = {0, 0, +1, -1};
-  const int shifta = sa[s], shiftb = sb[s];
-  if (la < -shifta || lb < -shiftb || (aOnC && shifta) || (bOnC && shiftb)) return 0;
+/* Copies of a shell in the expanded list of a derivative run (api.c), behind the caller's shell (copy 0): momentum change
+ * and power of zeta in the contraction coefficients (reference src/type1.c:239-246, src/type2.c:263-269).  The lowered
+ * copies come last: a shell with l < 1 / l < 2 simply has fewer copies. */
+int ecp_deriv_ncopies(int n) { return n == 2 ? 6 : (n == 1 ? 3 : 1); }
+void ecp_deriv_copy(int n, int c, int *dl, int *zpow) {
+  static const int dl1[3] = {0, +1, -1}, zp1[3] = {0, 1, 0};
+  static const int dl2[6] = {0, +1, +2, 0, -1, -2}, zp2[6] = {0, 1, 2, 1, 0, 0};
+  if (n == 2) {
+    *dl = dl2[c];
+    *zpow = zp2[c];
+  } else {
+    *dl = dl1[c];
+    *zpow = zp1[c];
+  }
+}
+int ecp_deriv_nshifts(int n) { return n == 2 ? 10 : (n == 1 ? 4 : 1); }
+/* Shift s of a derivative run of order n on (la, lb): the reference's table src/libecp.c:246-250.  Returns 0 when the
+ * reference skips it (:325-330): momentum below zero, or - first derivatives only - the shifted function sits on the ECP
+ * centre (translational invariance).  *a2 / *b2 = slot offset of the shifted copy behind its unshifted shell
+ * (ecp_deriv_copy), *sa / *sb = the shifts handed to the callback.  Second derivatives, shifts (+1,0) and (0,+1)
+ * (:362-369): the copy with unchanged momentum and coefficients d zeta. */
+int ecp_deriv_shift(int n, int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2, int *sa, int *sb) {
+  static const int sa1[4] = {+1, -1, 0, 0}, sb1[4] = {0, 0, +1, -1};
+  static const int sa2[10] = {+2, -2, +1, +1, -1, -1, 0, 0, +1, 0}, sb2[10] = {0, 0, +1, -1, +1, -1, +2, -2, 0, +1};
+  const int shifta = n == 2 ? sa2[s] : sa1[s], shiftb = n == 2 ? sb2[s] : sb1[s];
+  if (la < -shifta || lb < -shiftb) return 0;
+  *sa = shifta;
+  *sb = shiftb;
+  if (n == 2) {
+    static const int slot[5] = {5, 4, 0, 1, 2}; /* shift -2 .. +2 */
+    *a2 = slot[shifta + 2];
+    *b2 = slot[shiftb + 2];
+    if (s == 8) *a2 = 3;
+    if (s == 9) *b2 = 3;
+    return 1;
+  }
+  if ((aOnC && shifta) || (bOnC && shiftb)) return 0;
   *a2 = shifta > 0 ? 1 : (shifta < 0 ? 2 : 0);
   *b2 = shiftb > 0 ? 1 : (shiftb < 0 ? 2 : 0);
   return 1;
@@ -269,9 +298,9 @@ static void centre_screen(const EcpTables *t, const double *geometry, int C, int
         const int gs = st[a] > st[b] ? st[a] : st[b];
         const int ge = en[a] > en[b] ? en[a] : en[b];
         if (!(gs < ge)) continue;
-        for (int sh = 0; sh < 4; sh++) {
-          int a2, b2;
-          if (!ecp_deriv_shift(sh, sl[a], sl[b], A == C, B == C, &a2, &b2)) continue;
+        for (int sh = 0; sh < ecp_deriv_nshifts(t->deriv); sh++) {
+          int a2, b2, sha, shb;
+          if (!ecp_deriv_shift(t->deriv, sh, sl[a], sl[b], A == C, B == C, &a2, &b2, &sha, &shb)) continue;
           const int la = sl[a + a2], lb = sl[b + b2];
           const int c = t->clsLookup[la][lb][Lc];
           w->clsCount[c] += 1;
@@ -514,7 +543,6 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
         runEnd[s] = e;
       }
     if (t->deriv) { /* shifted triples in the reference's order: A, B, s1, s2, shift (src/libecp.c:278-330) */
-      static const int sha[4] = {+1, -1, 0, 0}, shb[4] = {0, 0, +1, -1};
       for (int ka = 0; ka < nblk; ka++)
       for (int kb = ka; kb < nblk; kb++)
       for (int a = bs[ka]; a < bs[ka + 1]; a++) {
@@ -527,9 +555,9 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
           const int gs = st[a] > st[b] ? st[a] : st[b];
           const int ge = en[a] > en[b] ? en[a] : en[b];
           if (!(gs < ge)) continue;
-          for (int sh = 0; sh < 4; sh++) {
-            int a2, b2;
-            if (!ecp_deriv_shift(sh, sl[a], sl[b], A == w->C, B == w->C, &a2, &b2)) continue;
+          for (int sh = 0; sh < ecp_deriv_nshifts(t->deriv); sh++) {
+            int a2, b2, sha, shb;
+            if (!ecp_deriv_shift(t->deriv, sh, sl[a], sl[b], A == w->C, B == w->C, &a2, &b2, &sha, &shb)) continue;
             const int la = sl[a + a2], lb = sl[b + b2];
             const int c = t->clsLookup[la][lb][Lc];
             const long long p = lpos[c]++;
@@ -547,8 +575,8 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
                 bb->cnC[cn] = w->C;
                 bb->cnLa[cn] = sl[a];
                 bb->cnLb[cn] = sl[b];
-                bb->cnShA[cn] = sha[sh];
-                bb->cnShB[cn] = shb[sh];
+                bb->cnShA[cn] = sha;
+                bb->cnShB[cn] = shb;
                 bb->cnOut[cn] = out;
                 cn++;
               }

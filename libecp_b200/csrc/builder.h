@@ -52,8 +52,12 @@ int ecp_batch_build(const EcpTables *t, const double *geometry, int *centre, lon
 int ecp_batch_build_slots(const EcpTables *t, const double *geometry, int *centre, long long maxTriples, int rank, int world,
                           EcpBatchBuf *bb);
 
-/* shift s = 0..3 of a first-derivative run and whether the reference evaluates it (builder.c) */
-int ecp_deriv_shift(int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2);
+/* derivative runs (builder.c): copies of a shell in the expanded list, and shift s of the reference's table - whether the
+ * reference evaluates it, which copies it pairs and the shifts the callback receives */
+int ecp_deriv_ncopies(int n);
+void ecp_deriv_copy(int n, int c, int *dl, int *zpow);
+int ecp_deriv_nshifts(int n);
+int ecp_deriv_shift(int n, int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2, int *sa, int *sb);
 /* exposed for tests: window of one (centre type, shell radius, distance) (reference src/type2.c:148-180) */
 void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip);
 /* owner rank of a shell pair under the multi-GPU partition */

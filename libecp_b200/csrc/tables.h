@@ -39,8 +39,8 @@ typedef struct {
   const double *dealA;
   int *atomMaxL, *atomFirstShell;
   /* derivative runs (scope row f1): the shell list is the expanded one - every shell of the caller's basis is followed
-   * by its copies at l + 1 (coefficients d zeta, reference src/type1.c:239-246, src/type2.c:263-269,459-462) and, for
-   * l >= 1, at l - 1 (src/libecp.c:246-250) */
+   * by its shifted copies - l + k with coefficients d zeta^k (reference src/type1.c:239-246, src/type2.c:263-269,459-462),
+   * l - k with d, second derivatives also l with d zeta (src/libecp.c:246-250,362-369); virtShift = copy number */
   int deriv;
   int *virtShift, *virtLocal;
   /* ECP */
@@ -63,7 +63,8 @@ typedef struct {
   /* derivative runs (api.c): the basis handed in is the expanded list of shifted shells; screenParent[s] = the shell
    * whose radius screens shell s (the unshifted one, reference src/type2.c:251); NULL = every shell screens itself */
   const int *screenParent;
-  /* derivative order of the run (0 or 1) and, per shell of the expanded list, its momentum shift (0, +1, -1) and the
+  /* derivative order of the run (0, 1 or 2) and, per shell of the expanded list, its copy number (0 = the caller's shell,
+   * > 0 = a shifted copy, builder.c: ecp_deriv_copy) and the
    * position of its unshifted shell among the shells of the atom in the caller's basis (callback argument s1 / s2) */
   int deriv;
   const int *virtShift, *virtLocal;

@@ -166,6 +166,13 @@ def deriv_triangle():
                     [tz_basis(2), tz_basis(1), tz_basis(2)], [ecp_set(4), ecp_set(5, 0.8), None])
 
 
+def deriv2_triangle():
+    """second-derivative companion of deriv_triangle: TZ(1) + ECP(4), TZ(1) + ECP(5, scaled exponents), TZ(0) without an ECP
+    (lbs + 2 <= L - 1 on every centre)"""
+    return assemble("deriv2_triangle", [(0.0, 0.0, 0.0), (2.9, 0.4, -0.6), (-0.7, 3.1, 1.2)],
+                    [tz_basis(1), tz_basis(1), tz_basis(0)], [ecp_set(4), ecp_set(5, 0.8), None])
+
+
 def random_system(seed: int):
     """small random molecule for randomized parity runs: 2-4 atoms at random positions (>= 1.5 bohr apart), every atom a
     TZ(0..3) basis, ECP(L) with L >= lbs + 1 on a random non-empty subset of the atoms, random exponent scale"""

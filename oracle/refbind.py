@@ -70,8 +70,12 @@ class RefLib:
         if ordering is not None:  # ordering: int32 array laid out like cartesianShellOrder(lmax) (src/libecp.c:152-166)
             ordering = np.ascontiguousarray(ordering, np.int32)
 
+        order = n
+
         def cb(A, s1, la, sha, B, s2, lb, shb, Cc, I, args):
-            n = ((la + sha + 1) * (la + sha + 2) // 2) * ((lb + shb + 1) * (lb + shb + 2) // 2)
+            # second derivatives, shifts (+1,0) / (0,+1): momentum reset before calcPolynomials (src/libecp.c:362-369)
+            ea, eb = (0, 0) if order == 2 and (sha, shb) in ((1, 0), (0, 1)) else (sha, shb)
+            n = ((la + ea + 1) * (la + ea + 2) // 2) * ((lb + eb + 1) * (lb + eb + 2) // 2)
             blk = np.ctypeslib.as_array(I, shape=(n,)).copy() if keep_blocks else None
             recs.append((A, s1, la, sha, B, s2, lb, shb, Cc, blk))
 

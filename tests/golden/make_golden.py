@@ -2,7 +2,7 @@
 oracle/Makefile from /root/reference/src).  Run in the build container only (the GPU box has no
 /root/reference); the resulting .npz files are committed.
 
-    python tests/golden/make_golden.py [--big | --deriv | --order]
+    python tests/golden/make_golden.py [--big | --deriv | --deriv2 | --order]
 
 Fixtures (float64, exact bytes of the reference's output):
   <cfg>_matrix.npz   : getIntegrals matrix (upper triangle incl. diagonal as a flat vector `triu`,
@@ -11,9 +11,10 @@ Fixtures (float64, exact bytes of the reference's output):
   au2_blocks.npz     : same for the first two atoms of the Au20 tetrahedron (two-centre cases, fallback)
   order_*_blocks.npz : callback blocks with a caller-supplied Cartesian component order (synth.shell_order)
   deriv1_*_blocks.npz: callback blocks of derivative order n = 1 (shifted-momentum blocks, src/libecp.c:246-250,322-369)
-                       for two-atom systems - fixtures for the NEXT scope row; the product rejects n > 0
-                       today.  n = 2 is not recorded: the reference returns NaN in a few (1,0)/(0,1)-shift blocks on
-                       every shape tried (TZ(1..2) x ECP(4..6)), i.e. its own output is not defined there.
+                       (scope row f1)
+  deriv2_*_blocks.npz: derivative order n = 2: every callback block.  The (+1,0) / (0,+1) blocks (`mixed`) are computed at
+                       l + 1 and shifted with the dimensions of l (src/libecp.c:362-369): the momentum-l block with
+                       coefficients d zeta, IJK(la) x IJK(lb) elements.
 """
 import os
 import sys
@@ -61,7 +62,20 @@ def save_blocks(ref, name, s, n=0, ordering=None, lmax=-1):
     keys = np.array([r[:9] for r in recs], np.int32)
     off = np.cumsum([0] + [len(r[9]) for r in recs])
     vals = np.concatenate([r[9] for r in recs])
-    np.savez_compressed(os.path.join(HERE, f"{name}_blocks.npz"), keys=keys, off=off, vals=vals)
+    extra = {}
+    if n == 2:
+        # (+1,0) / (0,+1) blocks: the reference evaluates chi / gamma at l + 1 and shifts with the dimensions of l
+        # (src/libecp.c:362-369) - the lower-degree part of the larger array, i.e. the momentum-l block with coefficients
+        # d zeta; the block handed to the callback has IJK(la) x IJK(lb) elements (refbind sizes it so; reading it with
+        # the shifted size runs past the block - the "NaN" an earlier version of this script reported).  `mixed` marks them.
+        mixed = np.zeros(len(vals), bool)
+        for k, r in enumerate(recs):
+            if (r[3], r[7]) in ((1, 0), (0, 1)):
+                mixed[off[k]:off[k + 1]] = True
+        extra["mixed"] = mixed
+        print(f"{name}: {int(mixed.sum())} values in (+1,0)/(0,+1) blocks, {int(np.isnan(vals).sum())} NaN, "
+              f"{int(np.isnan(vals[~mixed]).sum())} NaN elsewhere")
+    np.savez_compressed(os.path.join(HERE, f"{name}_blocks.npz"), keys=keys, off=off, vals=vals, **extra)
     print(f"{name}: {len(recs)} callbacks, {len(vals)} values")
 
 
@@ -71,6 +85,11 @@ def main():
         save_blocks(ref, "deriv1_tz2_L4", synth.deriv_pair(2, 4), n=1)
         save_blocks(ref, "deriv1_tz3_L5", synth.deriv_pair(3, 5), n=1)
         save_blocks(ref, "deriv1_triangle", synth.deriv_triangle(), n=1)
+        return
+    if "--deriv2" in sys.argv:  # second derivatives
+        save_blocks(ref, "deriv2_tz1_L4", synth.deriv_pair(1, 4), n=2)
+        save_blocks(ref, "deriv2_tz2_L5", synth.deriv_pair(2, 5), n=2)
+        save_blocks(ref, "deriv2_triangle", synth.deriv2_triangle(), n=2)
         return
     if "--order" in sys.argv:  # scope row f4: caller-supplied Cartesian component order (src/libecp.c:152-166)
         save_blocks(ref, "order_rev_cfg2", synth.cfg2(), ordering=synth.shell_order(10, "reversed"), lmax=10)

@@ -505,33 +505,122 @@ def test_first_derivative_is_the_gradient_of_the_integrals():
     assert np.allclose(grad, fd, rtol=1e-6, atol=1e-9)
 
 
-def test_device_enumeration_matches_host_builder():
-    """matrix runs enumerate the triples on the device (ecp_enum.cuh) from the host's screening; LIBECP_B200_ENUM=host
-    keeps the host builder.  Same triples in the same class order: every intermediate (T, gamma, chi, Q) is identical
-    element for element, the statistics agree, also for a shard and for several small batches"""
-    for mk, name, shard, batch in ((lambda: synth.cfg3(4), "au4", None, None), (lambda: synth.cfg4("b"), "cfg4b", None, None),
-                                   (lambda: synth.cfg5(40), None, None, "20000"), (lambda: synth.cfg5(40), None, (1, 4), "7000"),
-                                   (lambda: synth.cfg1(), "cfg1", None, None)):
-        def run():
-            with capi.Handle(mk()) as h:
-                if shard:
-                    h.set_shard(*shard)
-                rc, M = h.integrals_host()
-                st = h.stats()
-                return rc, M, {k: h.debug_fetch(k, 200000) for k in ("T", "gamma", "chi", "Q")}, st
-        env = {"LIBECP_B200_BATCH_TRIPLES": batch} if batch else {}
-        rc0, M0, f0, st0 = _with_env(dict(env, LIBECP_B200_ENUM="host"), run)
-        rc1, M1, f1, st1 = _with_env(env, run)
-        assert rc0 == rc1 == 0
-        for k in ("executed_triples", "prim_pairs", "fast_quadratures", "fast_failed", "fallback_items", "shell_slots"):
-            assert st0[k] == st1[k], (name, k, st0[k], st1[k])
-        assert st1["h2d_bytes"] < st0["h2d_bytes"] or st0["executed_triples"] < 1000
-        if batch is None:  # one batch: the intermediates of the last batch are those of the whole run
-            for k in f0:
-                assert np.array_equal(f0[k], f1[k]), (name, k)
-        assert np.allclose(M0, M1, rtol=1e-13, atol=1e-15), name
-        if name:
-            assert_parity(M1, load_matrix(name), name)
+@pytest.mark.parametrize("name,mk", [("deriv2_tz1_L4", lambda: synth.deriv_pair(1, 4)), ("deriv2_tz2_L5", lambda: synth.deriv_pair(2, 5)),
+                                     ("deriv2_triangle", synth.deriv2_triangle)])
+def test_second_derivative_blocks_match_golden(name, mk):
+    """scope row f1, n = 2: the ten shifted blocks per executed shell pair (reference src/libecp.c:246-250) - same key
+    sequence, block sizes and values as the compiled reference at the usual tolerance, including the (+1,0) / (0,+1)
+    blocks (momentum unchanged, coefficients d zeta: the reference evaluates them at l + 1 and shifts the lower-degree
+    part, src/libecp.c:362-369; here they are ordinary blocks of a copy of the shell)."""
+    keys, off, vals = load_blocks(name)
+    with capi.Handle(mk(), n=2) as h:
+        rc, recs = h.callbacks()
+    assert rc == 0 and len(recs) == len(keys)
+    for k, r in enumerate(recs):
+        assert tuple(keys[k]) == r[:9]
+        assert len(r[9]) == off[k + 1] - off[k]
+    assert np.isfinite(vals).all()
+    assert_parity(np.concatenate([r[9] for r in recs]), vals, name)
+
+
+def _comp_index(l):
+    """component (nx, ny, nz) -> position in the shell, default (libint) order"""
+    o = synth.shell_order(l, "libint").reshape(-1, 3)
+    first = sum((k + 1) * (k + 2) // 2 for k in range(l))
+    return {tuple(int(x) for x in o[first + c]): c for c in range((l + 1) * (l + 2) // 2)}
+
+
+def test_second_derivative_is_the_gradient_of_the_first():
+    """size-independent property of row f1, n = 2, and the definition of its (+1,0) / (0,+1) blocks: the Hessian blocks
+    d2/dA_i dA_j, d2/dA_i dB_j of <a|U_C|b> assembled from the n = 2 callbacks,
+        D_i D_j g(a) = 4 z^2 g(a+1i+1j) - 2 z (a_i + d_ij) g(a+1j-1i) - 2 z a_j g(a-1j+1i) + a_j (a_i - d_ij) g(a-1j-1i)
+    (the two middle terms are the momentum-l blocks with coefficients d zeta), equal central finite differences of the
+    gradients assembled from n = 1 callbacks when atom A moves (three atoms, A != B != C, a p shell against a p shell)."""
+    base = synth.deriv2_triangle()
+    A, B, Cc = 0, 2, 1
+    ls = list(base["lBS"])
+    first = np.concatenate([[0], np.cumsum(base["shellsBS"])])
+    s1 = [j for j in range(int(base["shellsBS"][A])) if ls[first[A] + j] == 1][-1]  # most diffuse p shell of atom A
+    s2 = [j for j in range(int(base["shellsBS"][B])) if ls[first[B] + j] == 0][-1]  # most diffuse s shell of atom B
+    la, lb = 1, 0
+
+    def blocks(s, n):
+        with capi.Handle(s, n=n) as h:
+            rc, recs = h.callbacks()
+        assert rc == 0
+        out = {}
+        for r in recs:
+            if (r[0], r[1], r[4], r[5], r[8]) == (A, s1, B, s2, Cc):
+                ea, eb = (0, 0) if n == 2 and (r[3], r[7]) in ((1, 0), (0, 1)) else (r[3], r[7])
+                shp = ((la + ea + 1) * (la + ea + 2) // 2, (lb + eb + 1) * (lb + eb + 2) // 2)
+                out[(r[3], r[7])] = out.get((r[3], r[7]), 0.0) + r[9].reshape(shp)  # type 1 + type 2
+        return out
+
+    ia = {l: _comp_index(l) for l in range(0, 4)}
+    e = np.eye(3, dtype=int)
+
+    def get(blk, key, l1, c1, l2, c2):
+        """element of a block, 0 when a lowered exponent would be negative (its coefficient vanishes)"""
+        if min(c1) < 0 or min(c2) < 0 or key not in blk:
+            return 0.0
+        return blk[key][ia[l1][tuple(c1)], ia[l2][tuple(c2)]]
+
+    comps_a = [np.array(c) for c in ia[la]]
+    comps_b = [np.array(c) for c in ia[lb]]
+
+    def gradients(s):
+        """G_A[j], G_B[j] [ca, cb] from the n = 1 blocks: 2 z g(+1j) - a_j g(-1j)"""
+        blk = blocks(s, 1)
+        GA = np.zeros((3, len(comps_a), len(comps_b)))
+        GB = np.zeros_like(GA)
+        for j in range(3):
+            for x, ca in enumerate(comps_a):
+                for y, cb in enumerate(comps_b):
+                    GA[j, x, y] = 2 * get(blk, (1, 0), la + 1, ca + e[j], lb, cb) - ca[j] * get(blk, (-1, 0), la - 1, ca - e[j], lb, cb)
+                    GB[j, x, y] = 2 * get(blk, (0, 1), la, ca, lb + 1, cb + e[j]) - cb[j] * get(blk, (0, -1), la, ca, lb - 1, cb - e[j])
+        return GA, GB
+
+    blk2 = blocks(base, 2)
+    assert set(blk2) >= {(2, 0), (1, 0), (1, 1), (-1, 1), (0, 2), (0, 1)}
+    HAA = np.zeros((3, 3, len(comps_a), len(comps_b)))
+    HAB = np.zeros_like(HAA)
+    for i in range(3):
+        for j in range(3):
+            dij = int(i == j)
+            for x, ca in enumerate(comps_a):
+                for y, cb in enumerate(comps_b):
+                    HAA[i, j, x, y] = (4 * get(blk2, (2, 0), la + 2, ca + e[i] + e[j], lb, cb)
+                                       - 2 * (ca[i] + dij) * get(blk2, (1, 0), la, ca + e[j] - e[i], lb, cb)
+                                       - 2 * ca[j] * get(blk2, (1, 0), la, ca - e[j] + e[i], lb, cb)
+                                       + ca[j] * (ca[i] - dij) * get(blk2, (-2, 0), la - 2, ca - e[j] - e[i], lb, cb))
+                    HAB[i, j, x, y] = (4 * get(blk2, (1, 1), la + 1, ca + e[i], lb + 1, cb + e[j])
+                                       - 2 * cb[j] * get(blk2, (1, -1), la + 1, ca + e[i], lb - 1, cb - e[j])
+                                       - 2 * ca[i] * get(blk2, (-1, 1), la - 1, ca - e[i], lb + 1, cb + e[j])
+                                       + ca[i] * cb[j] * get(blk2, (-1, -1), la - 1, ca - e[i], lb - 1, cb - e[j]))
+    # central differences at h and 2h, Richardson-extrapolated (error O(h^4)).  The two sides agree to 1.1e-6 absolute on a
+    # scale of 0.11 - and to the same 1.1e-6 when both are assembled from the compiled reference's own blocks on the CPU
+    # (the integrals themselves are only that consistent under a displacement), independent of h: tolerance 2e-5 of the
+    # scale; a wrong coefficient or a wrong block shows up at order one.
+    h = 4e-3
+
+    def central(i, step):
+        g = []
+        for sgn in (+1, -1):
+            s = dict(base)
+            geo = base["geometry"].copy()
+            geo[3 * A + i] += sgn * step
+            s["geometry"] = geo
+            g.append(gradients(s))
+        return (g[0][0] - g[1][0]) / (2 * step), (g[0][1] - g[1][1]) / (2 * step)
+
+    for i in range(3):
+        a1, b1 = central(i, h)
+        a2, b2 = central(i, 2 * h)
+        fdA, fdB = (4 * a1 - a2) / 3, (4 * b1 - b2) / 3
+        scale = max(np.abs(fdA).max(), np.abs(fdB).max(), 1e-6)
+        print("n=2 vs FD, direction", i, "max |d| AA", np.abs(HAA[i] - fdA).max(), "AB", np.abs(HAB[i] - fdB).max(), "scale", scale)
+        assert np.allclose(HAA[i], fdA, rtol=0, atol=2e-5 * scale), (i, np.abs(HAA[i] - fdA).max(), scale)
+        assert np.allclose(HAB[i], fdB, rtol=0, atol=2e-5 * scale), (i, np.abs(HAB[i] - fdB).max(), scale)
 
 
 @pytest.mark.parametrize("name", ["cfg2", "au4", "cfg4b"])

@@ -83,7 +83,7 @@ def test_no_cpu_fallback_without_device():
 def test_unsupported_arguments_rejected():
     s = synth.cfg2()
     with pytest.raises(RuntimeError):
-        capi.Handle(s, n=2, tables_only=True)  # second derivatives: the reference's own output is NaN (make_golden.py)
+        capi.Handle(s, n=3, tables_only=True)  # the reference's shift table ends at second derivatives (src/libecp.c:246-250)
     bad = synth.assemble("bad", [(0, 0, 0)], [synth.tz_basis(5)], [synth.ecp_set(3)])  # maxLBS > L+1
     with pytest.raises(RuntimeError):
         capi.Handle(bad, tables_only=True)
@@ -548,8 +548,8 @@ def test_sharding_queries_on_a_handle_without_ecp_centres():
 
 def test_init_rejections_carry_their_own_message():
     s = synth.cfg2()
-    with pytest.raises(RuntimeError, match="derivative order n=2"):
-        capi.Handle(s, n=2, tables_only=True)
+    with pytest.raises(RuntimeError, match="derivative order n=3"):
+        capi.Handle(s, n=3, tables_only=True)
     # g shells under an L = 2 potential: outside the compiled-in shape domain, rejected with the shape in the message
     bad = synth.assemble("bad", [(0.0, 0.0, 0.0)], [synth.tz_basis(4)], [synth.ecp_set(2)])
     with pytest.raises(RuntimeError, match="unsupported shape: max l of the basis 4, max L of the ECPs 2"):
@@ -625,6 +625,27 @@ def test_custom_shell_ordering_tables():
 
 
 DERIV = {"deriv1_tz2_L4": (2, 4), "deriv1_tz3_L5": (3, 5)}
+DERIV2 = {"deriv2_tz1_L4": lambda: synth.deriv_pair(1, 4), "deriv2_tz2_L5": lambda: synth.deriv_pair(2, 5),
+          "deriv2_triangle": synth.deriv2_triangle}
+
+
+@pytest.mark.parametrize("name", list(DERIV2))
+def test_second_derivative_callback_keys_match_reference(name):
+    """scope row f1, n = 2, host part: ten shifts per executed shell pair (src/libecp.c:246-250), no translational-invariance
+    skip (:325-330 only for n = 1), call order and keys of the compiled reference; tables sized from maxLBS + 2"""
+    d = np.load(os.path.join(GOLDEN, f"{name}_blocks.npz"))
+    s = DERIV2[name]()
+    with capi.Handle(s, n=2, tables_only=True) as h:
+        keys = h.callback_keys()
+        dims = h.host_itable("dims")
+    assert np.array_equal(keys, d["keys"][0::2]) and np.array_equal(keys, d["keys"][1::2])
+    assert dims[1] == max(s["lBS"]) + 2
+    # block sizes of the fixture: shifted momenta, except the (+1,0) / (0,+1) blocks (momentum unchanged)
+    ijk = lambda l: (l + 1) * (l + 2) // 2
+    for k in (0, len(keys) // 2, len(keys) - 1):
+        A, s1, la, sa, B, s2, lb, sb, C = d["keys"][2 * k]
+        ea, eb = (0, 0) if (sa, sb) in ((1, 0), (0, 1)) else (sa, sb)
+        assert d["off"][2 * k + 1] - d["off"][2 * k] == ijk(la + ea) * ijk(lb + eb)
 
 
 def test_derivative_callback_keys_triangle():
