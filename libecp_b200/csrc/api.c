@@ -593,7 +593,13 @@ static void *panel_download(void *p) {
 static int host_panels(const libECPHandle *h) {
   const char *e = getenv("LIBECP_B200_HOST_PANELS");
   if (e && atoi(e) > 0) return atoi(e) > 16 ? 16 : atoi(e);
-  /* worth it when the transfer is long compared with a panel's fixed costs: upper triangle above ~256 MB */
+  /* Dense download (LIBECP_B200_D2H=dense): worth it when the transfer is long compared with a panel's fixed costs -
+   * upper triangle above ~256 MB.  The default sparse download moves a third of the bytes and is bound by the host +=
+   * (configuration 5: 14 ms after an 81 ms pass); an extra panel costs 5-8 ms (per-centre tables, screening, smaller
+   * batches, the download competing with the builder for host cores) and saves half of that tail at best: one panel
+   * (measured 95.2 / 96.3 / 100.6 ms for 1 / 2 / 3 panels, profiles/r2/README.md). */
+  const char *m = getenv("LIBECP_B200_D2H");
+  if (!(m && !strcmp(m, "dense"))) return 1;
   const double bytes = 4.0 * (double)h->tab->v.nAO * h->tab->v.nAO / h->world;
   return bytes > 256e6 ? 3 : 1;
 }

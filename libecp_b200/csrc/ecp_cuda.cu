@@ -859,6 +859,70 @@ __global__ void k_unpack_rows(double *__restrict__ M, int n, const int *__restri
   for (int j = i + threadIdx.x; j < n; j += blockDim.x) dst[j] = src[j];
 }
 
+/* ---- sparse download of the result matrix (host consumer, src/getIntegrals.c:36-42) ----
+ * The ECP matrix is block sparse: a block is non-zero only if both shells reach a common ECP centre (configuration 5:
+ * 15 % of the upper triangle, 24 % of its 128-byte lines).  Instead of the dense upper triangle the host consumer moves
+ * only the RUNS of SPR_RUN consecutive elements of a row M[i][i..n) that hold a non-zero, plus one bit per run.
+ * k_rows_flag: bitmap and number of such runs per listed row; the host turns the counts into row offsets;
+ * k_rows_pack_sparse: the flagged runs of every row back to back (a short last run of a row is padded with zeros). */
+#define SPR_RUN 16
+__global__ void k_rows_flag(const double *__restrict__ M, int n, const int *__restrict__ rows, int words,
+                            unsigned *__restrict__ bitmap, int *__restrict__ count) {
+  extern __shared__ unsigned spr_bm[];
+  __shared__ int total;
+  const int i = rows[blockIdx.x];
+  const double *src = M + (size_t)i * n + i;
+  const int len = n - i, nruns = (len + SPR_RUN - 1) / SPR_RUN;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) spr_bm[w] = 0;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const int hw = threadIdx.x >> 4, nhw = blockDim.x >> 4, l16 = threadIdx.x & 15;
+  for (int r0 = 0; r0 < nruns; r0 += nhw) { /* half a warp per run; every thread makes the same number of trips */
+    const int r = r0 + hw, j = r * SPR_RUN + l16;
+    const bool nz = (r < nruns && j < len) ? (src[j] != 0.0) : false;
+    const unsigned b = __ballot_sync(0xffffffffu, nz);
+    const unsigned half = (threadIdx.x & 16) ? (b >> 16) : (b & 0xffffu);
+    if (l16 == 0 && half) atomicOr(&spr_bm[r >> 5], 1u << (r & 31));
+  }
+  __syncthreads();
+  int c = 0;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) {
+    const unsigned v = spr_bm[w];
+    bitmap[(size_t)blockIdx.x * words + w] = v;
+    c += __popc(v);
+  }
+  if (c) atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) count[blockIdx.x] = total;
+}
+__global__ void k_rows_pack_sparse(const double *__restrict__ M, int n, const int *__restrict__ rows, int words,
+                                   const unsigned *__restrict__ bitmap, const long long *__restrict__ rowBase,
+                                   double *__restrict__ out) {
+  extern __shared__ unsigned spr_bm[]; /* [words] bitmap, [words] runs before each word */
+  unsigned *pre = spr_bm + words;
+  const int i = rows[blockIdx.x];
+  const double *src = M + (size_t)i * n + i;
+  const int len = n - i, nruns = (len + SPR_RUN - 1) / SPR_RUN;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) spr_bm[w] = bitmap[(size_t)blockIdx.x * words + w];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (int w = 0; w < words; w++) {
+      pre[w] = acc;
+      acc += __popc(spr_bm[w]);
+    }
+  }
+  __syncthreads();
+  double *o = out + rowBase[blockIdx.x] * SPR_RUN;
+  const int hw = threadIdx.x >> 4, nhw = blockDim.x >> 4, l16 = threadIdx.x & 15;
+  for (int r = hw; r < nruns; r += nhw) {
+    const unsigned word = spr_bm[r >> 5], bit = 1u << (r & 31);
+    if (!(word & bit)) continue;
+    const int pos = pre[r >> 5] + __popc(word & (bit - 1)), j = r * SPR_RUN + l16;
+    o[(size_t)pos * SPR_RUN + l16] = (j < len) ? src[j] : 0.0;
+  }
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* FP64 FMA peak probe (roofline denominator when no measured FP64 peak is published) */
 __global__ void k_fp64_probe(double *out, int iters) {
@@ -1534,6 +1598,150 @@ extern "C" int ecpdev_matrix_rows(EcpDev *d, int dir, const int *rows, long long
   return 0;
 }
 
+/* Sparse variant of the host consumer (default; LIBECP_B200_D2H=dense keeps the dense panels): flag the non-zero
+ * 16-element runs of the listed rows, read the per-row counts and bitmaps back (a few MB), pack the flagged runs on the
+ * device in row order, move them in chunks of ~24 MB through two page-locked buffers and add them into the caller's matrix
+ * by all host threads while the next chunk is in flight.  The caller's matrix is touched exactly where the dense variant
+ * touches it with a non-zero: same result bit for bit. */
+static int matrix_add_to_host_sparse(EcpDev *d, double *host, int rowdim, const int *rows, int nR, cudaStream_t st,
+                                     long long *bytes) {
+  const int n = d->nAO;
+  const int maxRuns = (n + SPR_RUN - 1) / SPR_RUN, words = (maxRuns + 31) / 32;
+  const size_t chunkRuns = ((size_t)24 << 20) / (SPR_RUN * sizeof(double));
+  const bool trace = getenv("LIBECP_B200_TRACE") != NULL;
+  const double t0 = omp_get_wtime();
+  Buf dRows = {NULL, 0}, dBits = {NULL, 0}, dCount = {NULL, 0}, dBase = {NULL, 0}, dPay = {NULL, 0};
+  g_allocStream = st;
+  int rc = ensure(&dRows, (size_t)nR * sizeof(int));
+  if (!rc) rc = ensure(&dBits, (size_t)nR * words * sizeof(unsigned));
+  if (!rc) rc = ensure(&dCount, (size_t)nR * sizeof(int));
+  if (!rc) rc = ensure(&dBase, (size_t)nR * sizeof(long long));
+  if (rc) return rc;
+  const size_t metaBytes = (size_t)nR * words * sizeof(unsigned) + (size_t)nR * sizeof(int);
+  unsigned *hBits = (unsigned *)ecpdev_pinned_alloc(metaBytes);
+  double *pin[2] = {(double *)ecpdev_pinned_alloc(chunkRuns * SPR_RUN * sizeof(double) + (size_t)n * sizeof(double)),
+                    (double *)ecpdev_pinned_alloc(chunkRuns * SPR_RUN * sizeof(double) + (size_t)n * sizeof(double))};
+  long long *base = (long long *)malloc((size_t)(nR + 1) * sizeof(long long));
+  int *cb = (int *)malloc((size_t)(nR + 2) * sizeof(int));
+  cudaEvent_t done[2] = {NULL, NULL};
+  long long moved = 0;
+  int nChunks = 0;
+  double tWait = 0, tAdd = 0, tMeta = 0;
+  int *hCount = NULL;
+#define SPR_CK(call)                                                                                       \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess) {                                                                               \
+      snprintf(g_err, sizeof(g_err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+      rc = (int)e_;                                                                                        \
+      goto spr_out;                                                                                        \
+    }                                                                                                      \
+  } while (0)
+  if (!hBits || !pin[0] || !pin[1] || !base || !cb) {
+    snprintf(g_err, sizeof(g_err), "ecpdev_matrix_add_to_host: no staging memory");
+    rc = -1;
+    goto spr_out;
+  }
+  hCount = (int *)(hBits + (size_t)nR * words);
+  for (int k = 0; k < 2; k++) SPR_CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+  SPR_CK(cudaMemcpyAsync(dRows.p, rows, (size_t)nR * sizeof(int), cudaMemcpyHostToDevice, st));
+  k_rows_flag<<<nR, 256, words * sizeof(unsigned), st>>>(d->matrix, n, (const int *)dRows.p, words, (unsigned *)dBits.p,
+                                                        (int *)dCount.p);
+  SPR_CK(cudaGetLastError());
+  SPR_CK(cudaMemcpyAsync(hBits, dBits.p, (size_t)nR * words * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  SPR_CK(cudaMemcpyAsync(hCount, dCount.p, (size_t)nR * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SPR_CK(cudaStreamSynchronize(st));
+  moved += (long long)metaBytes;
+  /* row offsets (in runs) and chunk boundaries at row boundaries */
+  base[0] = 0;
+  for (int k = 0; k < nR; k++) base[k + 1] = base[k] + hCount[k];
+  for (int k = 0; k < nR;) {
+    int e = k + 1;
+    while (e < nR && (size_t)(base[e + 1] - base[k]) <= chunkRuns) e++;
+    cb[nChunks++] = k;
+    k = e;
+  }
+  cb[nChunks] = nR;
+  if (base[nR] > 0) {
+    rc = ensure(&dPay, (size_t)base[nR] * SPR_RUN * sizeof(double));
+    if (rc) goto spr_out;
+    SPR_CK(cudaMemcpyAsync(dBase.p, base, (size_t)nR * sizeof(long long), cudaMemcpyHostToDevice, st));
+    k_rows_pack_sparse<<<nR, 256, 2 * words * sizeof(unsigned), st>>>(d->matrix, n, (const int *)dRows.p, words,
+                                                                     (const unsigned *)dBits.p, (const long long *)dBase.p,
+                                                                     (double *)dPay.p);
+    SPR_CK(cudaGetLastError());
+  }
+  tMeta = omp_get_wtime() - t0;
+  {
+    auto issue = [&](int p) -> cudaError_t {
+      const long long r0 = base[cb[p]], r1 = base[cb[p + 1]];
+      moved += (r1 - r0) * SPR_RUN * (long long)sizeof(double);
+      if (r1 > r0) {
+        cudaError_t e = cudaMemcpyAsync(pin[p & 1], (const double *)dPay.p + r0 * SPR_RUN,
+                                        (size_t)(r1 - r0) * SPR_RUN * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+      }
+      return cudaEventRecord(done[p & 1], st);
+    };
+    if (nChunks) SPR_CK(issue(0));
+    for (int p = 0; p < nChunks; p++) {
+      if (p + 1 < nChunks) SPR_CK(issue(p + 1));
+      const double tw0 = omp_get_wtime();
+      SPR_CK(cudaEventSynchronize(done[p & 1]));
+      const double tw1 = omp_get_wtime();
+      tWait += tw1 - tw0;
+      const int k0 = cb[p], k1 = cb[p + 1];
+      const double *src = pin[p & 1];
+      const long long b0 = base[k0];
+#pragma omp parallel for schedule(dynamic, 8)
+      for (int k = k0; k < k1; k++) {
+        if (!hCount[k]) continue;
+        const int i = rows[k];
+        const double *pr = src + (base[k] - b0) * SPR_RUN;
+        double *dr = host + (size_t)i * rowdim + i;
+        const unsigned *bm = hBits + (size_t)k * words;
+        const int len = n - i;
+        for (int w = 0; w < words; w++) {
+          unsigned bits = bm[w];
+          while (bits) {
+            const int r = w * 32 + __builtin_ctz(bits), j = r * SPR_RUN;
+            bits &= bits - 1;
+            double *dj = dr + j;
+            if (j + SPR_RUN <= len)
+              for (int q = 0; q < SPR_RUN; q++) dj[q] += pr[q];
+            else
+              for (int q = 0; j + q < len; q++) dj[q] += pr[q];
+            pr += SPR_RUN;
+          }
+        }
+      }
+      tAdd += omp_get_wtime() - tw1;
+    }
+  }
+  if (trace) {
+    long long allRuns = 0;
+    for (int k = 0; k < nR; k++) allRuns += (n - rows[k] + SPR_RUN - 1) / SPR_RUN;
+    fprintf(stderr, "[libecp_b200] sparse d2h+add: rows %d runs %lld of %lld chunks %d bytes %.1f MB flag+meta+pack %.1f ms wait %.1f ms add %.1f ms threads %d\n",
+            nR, base[nR], allRuns, nChunks, moved / 1e6, 1e3 * tMeta, 1e3 * tWait, 1e3 * tAdd, omp_get_max_threads());
+  }
+spr_out:
+#undef SPR_CK
+  for (int k = 0; k < 2; k++) {
+    if (done[k]) cudaEventDestroy(done[k]);
+    if (pin[k]) ecpdev_pinned_free(pin[k]);
+  }
+  if (hBits) ecpdev_pinned_free(hBits);
+  if (dRows.p) cudaFreeAsync(dRows.p, st);
+  if (dBits.p) cudaFreeAsync(dBits.p, st);
+  if (dCount.p) cudaFreeAsync(dCount.p, st);
+  if (dBase.p) cudaFreeAsync(dBase.p, st);
+  if (dPay.p) cudaFreeAsync(dPay.p, st);
+  free(base);
+  free(cb);
+  if (bytes) *bytes = moved;
+  return rc;
+}
+
 extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, const unsigned char *rowOwned,
                                          long long *bytes, int async) {
   /* async = 1: the listed rows are final (their pass has returned) while another pass may be running on the compute
@@ -1560,6 +1768,15 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
     }
   off[nR] = tot;
   const long long panelElems = (long long)(panelBytes / sizeof(double)) > n ? (long long)(panelBytes / sizeof(double)) : n;
+  {
+    const char *e = getenv("LIBECP_B200_D2H");
+    if (!(e && !strcmp(e, "dense")) && nR) {
+      const int rc = matrix_add_to_host_sparse(d, host, rowdim, rows, nR, st, bytes);
+      free(rows);
+      free(off);
+      return rc;
+    }
+  }
   Buf dRows = {NULL, 0}, dOff = {NULL, 0}, dStage[2] = {{NULL, 0}, {NULL, 0}};
   g_allocStream = st;
   int rc = ensure(&dRows, (size_t)(nR + 1) * sizeof(int));

@@ -3,6 +3,7 @@ getIntegrals.h, libecp_b200.h), with the oracle and the golden fixtures of the c
 
 Tolerance (north_star): |x - ref| <= 1e-12 + 1e-10 |ref| element-wise, identical screening decisions
 and integral indexing (the callback key sequence must be identical)."""
+import ctypes
 import os
 
 import numpy as np
@@ -269,6 +270,37 @@ def test_host_consumer_in_row_panels():
         got, st = _with_env({"LIBECP_B200_HOST_PANELS": "3"}, sharded)
         assert np.allclose(got, base, rtol=1e-13, atol=1e-15), name
         assert st["batches"] >= 3
+
+
+def test_sparse_download_equals_dense_download():
+    """the host consumer moves only the non-zero 16-element runs of the result rows plus one bit per run
+    (ecp_cuda.cu: matrix_add_to_host_sparse; LIBECP_B200_D2H=dense keeps the dense upper-triangle panels): the caller's
+    matrix is the same (bit for bit on a single centre) - small matrices (rows shorter than a run), a sparse one (distant atoms), row panels,
+    a sharded handle, and += into a pre-filled matrix; fewer bytes cross PCIe"""
+    far = synth.assemble("far", [(0.0, 0.0, 0.0), (0.0, 0.0, 40.0), (3.0, 0.5, 0.2)], [synth.tz_basis(2)] * 3,
+                         [synth.ecp_set(3), synth.ecp_set(3), None])
+    for s in (synth.cfg1(), synth.cfg3(4), far, synth.cfg5(40)):
+        def run(shard=None):
+            dim = int(s["dim"])
+            acc = np.full((dim, dim), 0.25)
+            with capi.Handle(s) as h:
+                if shard:
+                    h.set_shard(*shard)
+                rc = capi.lib().libecp_b200_integrals_host(ctypes.c_void_p(h.h), dim, acc.ctypes.data_as(capi._pd))
+                st = h.stats()
+            assert rc == 0
+            return acc, st["d2h_bytes"]
+        for P in ("1", "3"):
+            for shard in (None, (1, 2)):
+                dense, bd = _with_env({"LIBECP_B200_D2H": "dense", "LIBECP_B200_HOST_PANELS": P}, lambda: run(shard))
+                sparse, bs = _with_env({"LIBECP_B200_HOST_PANELS": P}, lambda: run(shard))
+                # two runs differ in the last bit where several centres add into an element (atomicAdd order); the
+                # set of touched elements is the same and nothing else may differ
+                assert np.array_equal(dense != 0.25, sparse != 0.25), (s.get("name"), P, shard)
+                assert np.allclose(dense, sparse, rtol=1e-13, atol=1e-15), (s.get("name"), P, shard)
+                assert np.any(dense != 0.25)
+        if s is far:
+            assert bs < 0.8 * bd
 
 
 def test_handles_in_sequence_reuse_parked_buffers():
