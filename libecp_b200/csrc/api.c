@@ -32,6 +32,7 @@ struct _libECPHandle {
   long long maxTriples;
   double *hostBlocks;
   size_t hostBlocksCap;
+  struct StreamState *stream; /* host consumer: rows that are final are downloaded while the pass goes on (below) */
   double triPerPair; /* executed triples per tested shell pair, measured on the batches run so far (device enumeration) */
   /* derivative runs: the expanded shell list the tables borrow (libECP_init) */
   int *xShells, *xL, *xK;
@@ -330,13 +331,16 @@ static void worker_wait(struct BuildWorker *w) {
 }
 
 /* batch size targets of a pass (see run_all): a small first batch, a half-size second one, then full size */
-static long long pass_batch_size_enum(const libECPHandle *h, int i) {
+static long long pass_batch_size_enum(const libECPHandle *h, int i, int centre) {
   /* device-enumerated batches: the host part of a batch is the screening of its centres (a fraction of a millisecond
    * per 100 centres), so only the very first batch is kept small; everything after it is full size at any world size -
    * a rank of 8 then runs its pass in two batches instead of three or four (about 0.9 ms of fixed device time each) */
   const char *e = getenv("LIBECP_B200_BATCH_TRIPLES");
   const long long full = (e && atoll(e) > 0) ? h->maxTriples : 2 * h->maxTriples; /* 6 M: 83.3 -> 81.0 ms per config-5 pass */
   const long long first = full / 6 < 500000 ? full / 6 : 500000;
+  /* streamed host consumer: rows leave the device batch by batch, the rows the LAST batch finishes are the tail of the
+   * call - third-size batches over the last 45 % of the centres (about 0.7 ms of fixed cost each) */
+  if (h->stream && i > 0 && h->world == 1 && centre > (h->nrAtoms * 11) / 20 && !getenv("LIBECP_B200_STREAM_EVEN")) return full / 3;
   return i == 0 ? first : full;
 }
 static long long pass_batch_size(const libECPHandle *h, int i) {
@@ -350,6 +354,92 @@ static long long pass_batch_size(const libECPHandle *h, int i) {
     if (full < 500000) full = 500000;
   }
   return i == 0 ? full / 6 : (i == 1 ? full / 2 : full);
+}
+
+/* ---- streamed download of the host consumer ----
+ * The AO rows of an atom are final as soon as the pass is beyond the last centre that can reach the atom
+ * (ecp_atom_last_centre: the builder's atom-level prune).  After every batch the rows that have become final are handed
+ * to a helper thread, which packs their non-zero runs, moves them on the download stream and adds them into the caller's
+ * matrix (src/getIntegrals.c:36-42) while the next batches compute; only the rows the last batch finishes are left as a
+ * tail.  How early rows become final depends on the spatial order of the atoms (a lattice-ordered nanocrystal: 60 % of
+ * the upper triangle before the last batch); in the worst case everything is downloaded after the pass, as without
+ * streaming.  One download at a time: a batch that ends while the previous download is still running keeps its rows
+ * for the next one. */
+typedef struct StreamState {
+  libECPHandle *h;
+  double *I;
+  int rowdim;
+  int *lastC;               /* per atom */
+  unsigned char *sent;      /* per atom */
+  unsigned char *ownedRows; /* per AO row, NULL = all (unsharded) */
+  unsigned char *mask;      /* rows of the running download */
+  pthread_t th;
+  int running, done, rc, jobs;
+  long long moved;
+} StreamState;
+static void *stream_thread(void *p) {
+  StreamState *s = p;
+#ifdef _OPENMP
+  if (g_host_threads > 0) omp_set_num_threads(g_host_threads > 5 ? g_host_threads - 3 : g_host_threads); /* the builder's team works beside it */
+#endif
+  long long moved = 0;
+  const int rc = ecpdev_matrix_add_to_host(s->h->dev, s->I, s->rowdim, s->mask, &moved, 1);
+  s->moved += moved;
+  if (rc && !s->rc) s->rc = rc;
+  __atomic_store_n(&s->done, 1, __ATOMIC_RELEASE);
+  return NULL;
+}
+static void stream_join(StreamState *s) {
+  if (!s->running) return;
+  pthread_join(s->th, NULL);
+  s->running = 0;
+}
+/* rows of the atoms that are final once every centre < centreEnd is done and that have not been sent: into s->mask;
+ * returns the number of upper-triangle elements they hold */
+static long long stream_collect(StreamState *s, int centreEnd) {
+  const EcpTables *t = s->h->tab;
+  const EcpHostTables *v = &t->v;
+  const int n = v->nAO;
+  long long elems = 0;
+  memset(s->mask, 0, (size_t)n + 1);
+  for (int X = 0; X < v->nrAtoms; X++) {
+    if (s->sent[X] || s->lastC[X] < 0 || s->lastC[X] >= centreEnd) continue;
+    const int s0 = t->atomFirstShell[X], s1 = t->atomFirstShell[X + 1];
+    if (s0 == s1) continue;
+    const int r0 = v->shellAO[s0], r1 = (s1 < v->nrShells) ? v->shellAO[s1] : n;
+    for (int r = r0; r < r1; r++)
+      if (!s->ownedRows || s->ownedRows[r]) {
+        s->mask[r] = 1;
+        elems += n - r;
+      }
+  }
+  return elems;
+}
+static void stream_mark_sent(StreamState *s, int centreEnd) {
+  for (int X = 0; X < s->h->tab->v.nrAtoms; X++)
+    if (s->lastC[X] >= 0 && s->lastC[X] < centreEnd) s->sent[X] = 1;
+}
+/* after a batch (not the last one of the pass): centres < centreEnd are done */
+static void stream_after_batch(StreamState *s, int centreEnd) {
+  if (s->running) {
+    if (!__atomic_load_n(&s->done, __ATOMIC_ACQUIRE)) return; /* still busy: these rows go with the next download */
+    stream_join(s);
+  }
+  if (s->rc) return;
+  const long long elems = stream_collect(s, centreEnd);
+  {
+    const char *e = getenv("LIBECP_B200_STREAM_MIN_BYTES"); /* tests stream small matrices */
+    const long long minBytes = e ? atoll(e) : (16LL << 20);
+    if (elems == 0 || elems * 8 < minBytes) return; /* not worth a download of its own yet */
+  }
+  stream_mark_sent(s, centreEnd);
+  s->done = 0;
+  if (pthread_create(&s->th, NULL, stream_thread, s) == 0) {
+    s->running = 1;
+    s->jobs++;
+  } else {
+    stream_thread(s);
+  }
 }
 
 /* drive all batches; flags as ecpdev_run_batch; cb may be NULL */
@@ -370,7 +460,7 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
   {
     const char *e = getenv("LIBECP_B200_ENUM"); /* =host: the host builder enumerates the triples of matrix runs too */
     job.devEnum = (flags == 1) && !h->tab->deriv && !(e && !strcmp(e, "host"));
-    if (job.devEnum) job.maxTriples = pass_batch_size_enum(h, 0);
+    if (job.devEnum) job.maxTriples = pass_batch_size_enum(h, 0, 0);
   }
   build_job(&job); /* first batch: nothing to overlap with */
   if (getenv("LIBECP_B200_TRACE")) fprintf(stderr, "[libecp_b200] first batch built in %.1f ms\n", job.ms);
@@ -380,10 +470,11 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     EcpBatchBuf *cur = bufs[i & 1];
     const double msBuild = job.ms;
     const double t0 = now_ms();
+    const int centreEnd = centre; /* centres < centreEnd are done when this batch is (the helper thread moves the cursor on) */
     /* next batch on the helper thread (it advances the centre cursor; nobody else reads it meanwhile) */
     job.bb = bufs[(i + 1) & 1];
     job.slot = (i + 1) & 1;
-    job.maxTriples = job.devEnum ? pass_batch_size_enum(h, i + 1) : pass_batch_size(h, i + 1); /* ramp: the GPU must not wait for a full-size build behind a small batch */
+    job.maxTriples = job.devEnum ? pass_batch_size_enum(h, i + 1, centre) : pass_batch_size(h, i + 1); /* ramp: the GPU must not wait for a full-size build behind a small batch */
     job.prefetch = threaded;
     if (threaded) worker_post(h->worker, &job);
     EcpBatch *b = &cur->b;
@@ -411,6 +502,7 @@ static int run_all(libECPHandle *h, int flags, ECPCallback cb, void *args) {
     if (st.err1 && result == 0) result = 1; /* src/libecp.h:23-27 */
     if (st.err2 && result == 0) result = 2;
     if (result) break;
+    if (h->stream && job.took > 0) stream_after_batch(h->stream, centreEnd);
     if (cb) { /* replay in the reference's loop order, type 1 then type 2 (src/libecp.c:332-373) */
       typedef void (*CallSite)(int, int, int, int, int, int, int, int, int, double *, void *);
       CallSite call = (CallSite)cb;
@@ -608,7 +700,50 @@ int libecp_b200_integrals_host(libECPHandle *h, int rowdim, double *I) {
   const int P = (h->empty || !h->dev || h->tab->deriv) ? 1 : host_panels(h);
   if (P <= 1) {
     void *dm = NULL;
+    StreamState st;
+    memset(&st, 0, sizeof(st));
+    {
+      const char *e = getenv("LIBECP_B200_STREAM_D2H");
+      if (!h->empty && h->dev && !h->tab->deriv && !(e && !strcmp(e, "0"))) {
+        const int nat = h->tab->v.nrAtoms, n = h->tab->v.nAO;
+        st.h = h;
+        st.I = I;
+        st.rowdim = rowdim;
+        st.lastC = malloc((size_t)(nat + 1) * sizeof(int));
+        st.sent = calloc((size_t)nat + 1, 1);
+        st.mask = calloc((size_t)n + 1, 1);
+        st.ownedRows = owned_rows(h);
+        ecp_atom_last_centre(h->tab, h->geometry, st.lastC);
+        h->stream = &st;
+      }
+    }
     const int rc = libecp_b200_integrals_device(h, &dm, NULL);
+    h->stream = NULL;
+    if (st.h) {
+      stream_join(&st);
+      long long rest = 0;
+      int rc2 = st.rc;
+      if (rc >= 0 && !rc2) {
+        const double tA = now_ms();
+        rest = stream_collect(&st, h->nrAtoms + 1); /* everything that has not been sent (atoms no centre reaches stay zero) */
+        if (rest) {
+          long long moved = 0;
+          rc2 = ecpdev_matrix_add_to_host(h->dev, I, rowdim, st.mask, &moved, 0);
+          st.moved += moved;
+        }
+        if (getenv("LIBECP_B200_TRACE"))
+          fprintf(stderr, "[libecp_b200] rank %d/%d integrals_host: %d streamed downloads, tail %.1f MB dense-equivalent in %.1f ms (whole call %.1f ms)\n",
+                  h->rank, h->world, st.jobs, rest * 8 / 1e6, now_ms() - tA, now_ms() - tCall);
+      }
+      free(st.lastC);
+      free(st.sent);
+      free(st.mask);
+      free(st.ownedRows);
+      if (rc < 0) return rc;
+      h->stats.d2h_bytes += st.moved;
+      if (rc2) return -rc2;
+      return rc;
+    }
     if (rc < 0 || h->empty) return rc;
     long long moved = 0;
     unsigned char *owned = owned_rows(h); /* only the AO rows of the shells this rank owns can be non-zero */
@@ -826,7 +961,7 @@ double libecp_b200_build_only(libECPHandle *h, long long *triples, int *batches)
   const double t0 = now_ms();
   const char *e = getenv("LIBECP_B200_ENUM");
   if (!h->tab->deriv && !(e && !strcmp(e, "host"))) { /* what a matrix run leaves to the host: screening and slot layout */
-    while (ecp_batch_build_slots(h->tab, h->geometry, &centre, pass_batch_size_enum(h, nb), h->rank, h->world, bufs[nb & 1]) > 0) {
+    while (ecp_batch_build_slots(h->tab, h->geometry, &centre, pass_batch_size_enum(h, nb, centre), h->rank, h->world, bufs[nb & 1]) > 0) {
       n += bufs[nb & 1]->b.pairCand; /* shell pairs the device will test (it counts the triples itself) */
       nb++;
     }

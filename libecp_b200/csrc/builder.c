@@ -211,6 +211,26 @@ int ecp_deriv_shift(int n, int s, int la, int lb, int aOnC, int bOnC, int *a2, i
   return 1;
 }
 
+/* Last ECP centre (in processing order = atom order) that can touch the rows of each atom: the atom-level prune of
+ * centre_screen below, evaluated for every (atom, centre).  lastC[X] = -1: no centre reaches the atom (its rows stay
+ * zero).  Once the pass is beyond lastC[X] the AO rows of X are final - the host consumer streams them out while later
+ * centres are still being integrated (api.c). */
+void ecp_atom_last_centre(const EcpTables *t, const double *geometry, int *lastC) {
+  const int nat = t->v.nrAtoms;
+  for (int X = 0; X < nat; X++) lastC[X] = -1;
+  for (int C = 0; C < nat; C++) {
+    if (t->atomType[C] < 0) continue;
+    const int endLast = t->types[t->atomType[C]].endLast;
+    if (endLast < 0) continue;
+    const double rcap = t->small_x[endLast];
+    for (int X = 0; X < nat; X++) {
+      if (t->atomFirstShell[X] == t->atomFirstShell[X + 1]) continue;
+      if (dist3(geometry + 3 * C, geometry + 3 * X) - t->atomRmax[X] > rcap) continue;
+      lastC[X] = C;
+    }
+  }
+}
+
 /* phase (a) for one centre */
 static void centre_screen(const EcpTables *t, const double *geometry, int C, int rank, int world, CentreWork *w, int doCount) {
   const EcpHostTables *v = &t->v;

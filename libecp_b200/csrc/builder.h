@@ -58,6 +58,8 @@ int ecp_deriv_ncopies(int n);
 void ecp_deriv_copy(int n, int c, int *dl, int *zpow);
 int ecp_deriv_nshifts(int n);
 int ecp_deriv_shift(int n, int s, int la, int lb, int aOnC, int bOnC, int *a2, int *b2, int *sa, int *sb);
+/* last centre (atom order) whose screening can keep a shell of each atom; -1 = none (builder.c) */
+void ecp_atom_last_centre(const EcpTables *t, const double *geometry, int *lastC);
 /* exposed for tests: window of one (centre type, shell radius, distance) (reference src/type2.c:148-180) */
 void ecp_shell_window(const EcpTables *t, int endLast, double radius, double dist, int *start, int *end, int *skip);
 /* owner rank of a shell pair under the multi-GPU partition */

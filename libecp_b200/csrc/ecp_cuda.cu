@@ -990,6 +990,7 @@ struct EcpDev {
   void *comm;
   int commOwned, commRank, commWorld;
   Buf agRows, agOff, agBuf;
+  Buf dlRows, dlBits, dlCount, dlBase, dlPay; /* sparse download of the host consumer (matrix_add_to_host_sparse); parked with the scratch */
   long long agCap, *agCount, *agFirst; /* per rank: packed doubles, first entry of its rows in agRows/agOff */
   size_t lastSizes[8];
   long long tableBytes, batchH2D;
@@ -1391,7 +1392,7 @@ static int collect_bufs(EcpDev *d, Buf **bs) {
                  &d->tfail, &d->tflags, &d->items, &d->counters, &d->fastSurv, &d->t1list, &d->t1mask, &d->t1count,
                  &d->t1work, &d->t1rec, &d->trirec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR,
                  &d->fbwItems, &d->fbwUnits, &d->fbwQd, &d->fbwSI, &d->fbwSP, &d->fbwSQ, &d->fbwRes, &d->fbwOpenFlag, &d->fbwVals,
-                 &d->fbwListA, &d->fbwListB, &d->fbwCtr,
+                 &d->fbwListA, &d->fbwListB, &d->fbwCtr, &d->dlRows, &d->dlBits, &d->dlCount, &d->dlBase, &d->dlPay,
 #define UPSET(i) &d->up[i].asAtom, &d->up[i].asType, &d->up[i].asR, &d->up[i].asOmOff, &d->up[i].ssShell,            \
                  &d->up[i].ssASlot, &d->up[i].ssStart, &d->up[i].ssEnd, &d->up[i].ssFOff, &d->up[i].trA, &d->up[i].trB, \
                  &d->up[i].trOut, &d->up[i].trPair, &d->up[i].prTriple, &d->up[i].clsFirst, &d->up[i].clsWork,        \
@@ -1610,13 +1611,18 @@ static int matrix_add_to_host_sparse(EcpDev *d, double *host, int rowdim, const 
   const size_t chunkRuns = ((size_t)24 << 20) / (SPR_RUN * sizeof(double));
   const bool trace = getenv("LIBECP_B200_TRACE") != NULL;
   const double t0 = omp_get_wtime();
-  Buf dRows = {NULL, 0}, dBits = {NULL, 0}, dCount = {NULL, 0}, dBase = {NULL, 0}, dPay = {NULL, 0};
+  /* device buffers of the download live in the handle and are parked with its scratch (one download at a time, see
+   * api.c): cudaMallocAsync beside a running batch was measured at up to 0.7 s when the pool had to grow - and the batch
+   * stalled with it (profiles/r2/session3/e2e_outliers_*.txt).  Sized for all rows once, so that no download of a pass
+   * allocates. */
+  Buf &dRows = d->dlRows, &dBits = d->dlBits, &dCount = d->dlCount, &dBase = d->dlBase, &dPay = d->dlPay;
   g_allocStream = st;
-  int rc = ensure(&dRows, (size_t)nR * sizeof(int));
-  if (!rc) rc = ensure(&dBits, (size_t)nR * words * sizeof(unsigned));
-  if (!rc) rc = ensure(&dCount, (size_t)nR * sizeof(int));
-  if (!rc) rc = ensure(&dBase, (size_t)nR * sizeof(long long));
+  int rc = ensure(&dRows, (size_t)n * sizeof(int));
+  if (!rc) rc = ensure(&dBits, (size_t)n * words * sizeof(unsigned));
+  if (!rc) rc = ensure(&dCount, (size_t)n * sizeof(int));
+  if (!rc) rc = ensure(&dBase, (size_t)n * sizeof(long long));
   if (rc) return rc;
+  const double tP1 = omp_get_wtime();
   const size_t metaBytes = (size_t)nR * words * sizeof(unsigned) + (size_t)nR * sizeof(int);
   unsigned *hBits = (unsigned *)ecpdev_pinned_alloc(metaBytes);
   double *pin[2] = {(double *)ecpdev_pinned_alloc(chunkRuns * SPR_RUN * sizeof(double) + (size_t)n * sizeof(double)),
@@ -1628,6 +1634,8 @@ static int matrix_add_to_host_sparse(EcpDev *d, double *host, int rowdim, const 
   int nChunks = 0;
   double tWait = 0, tAdd = 0, tMeta = 0;
   int *hCount = NULL;
+  const double tP2 = omp_get_wtime();
+  double tP3 = 0, tP4 = 0, tP5 = 0;
 #define SPR_CK(call)                                                                                       \
   do {                                                                                                     \
     cudaError_t e_ = (call);                                                                               \
@@ -1650,7 +1658,9 @@ static int matrix_add_to_host_sparse(EcpDev *d, double *host, int rowdim, const 
   SPR_CK(cudaGetLastError());
   SPR_CK(cudaMemcpyAsync(hBits, dBits.p, (size_t)nR * words * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   SPR_CK(cudaMemcpyAsync(hCount, dCount.p, (size_t)nR * sizeof(int), cudaMemcpyDeviceToHost, st));
+  tP3 = omp_get_wtime();
   SPR_CK(cudaStreamSynchronize(st));
+  tP4 = omp_get_wtime();
   moved += (long long)metaBytes;
   /* row offsets (in runs) and chunk boundaries at row boundaries */
   base[0] = 0;
@@ -1663,7 +1673,12 @@ static int matrix_add_to_host_sparse(EcpDev *d, double *host, int rowdim, const 
   }
   cb[nChunks] = nR;
   if (base[nR] > 0) {
-    rc = ensure(&dPay, (size_t)base[nR] * SPR_RUN * sizeof(double));
+    { /* grow in large steps: the payload of the whole matrix is a few hundred MB */
+      size_t need = (size_t)base[nR] * SPR_RUN * sizeof(double);
+      if (need > dPay.cap && need < ((size_t)256 << 20)) need = (size_t)256 << 20;
+      rc = ensure(&dPay, need);
+    }
+    tP5 = omp_get_wtime();
     if (rc) goto spr_out;
     SPR_CK(cudaMemcpyAsync(dBase.p, base, (size_t)nR * sizeof(long long), cudaMemcpyHostToDevice, st));
     k_rows_pack_sparse<<<nR, 256, 2 * words * sizeof(unsigned), st>>>(d->matrix, n, (const int *)dRows.p, words,
@@ -1721,8 +1736,9 @@ static int matrix_add_to_host_sparse(EcpDev *d, double *host, int rowdim, const 
   if (trace) {
     long long allRuns = 0;
     for (int k = 0; k < nR; k++) allRuns += (n - rows[k] + SPR_RUN - 1) / SPR_RUN;
-    fprintf(stderr, "[libecp_b200] sparse d2h+add: rows %d runs %lld of %lld chunks %d bytes %.1f MB flag+meta+pack %.1f ms wait %.1f ms add %.1f ms threads %d\n",
-            nR, base[nR], allRuns, nChunks, moved / 1e6, 1e3 * tMeta, 1e3 * tWait, 1e3 * tAdd, omp_get_max_threads());
+    fprintf(stderr, "[libecp_b200] sparse d2h+add: rows %d runs %lld of %lld chunks %d bytes %.1f MB flag+meta+pack %.1f ms (dev alloc %.1f, pinned %.1f, issue %.1f, sync %.1f, payload alloc %.1f) wait %.1f ms add %.1f ms threads %d\n",
+            nR, base[nR], allRuns, nChunks, moved / 1e6, 1e3 * tMeta, 1e3 * (tP1 - t0), 1e3 * (tP2 - tP1), 1e3 * (tP3 - tP2),
+            1e3 * (tP4 - tP3), 1e3 * (tP5 - tP4), 1e3 * tWait, 1e3 * tAdd, omp_get_max_threads());
   }
 spr_out:
 #undef SPR_CK
@@ -1731,11 +1747,6 @@ spr_out:
     if (pin[k]) ecpdev_pinned_free(pin[k]);
   }
   if (hBits) ecpdev_pinned_free(hBits);
-  if (dRows.p) cudaFreeAsync(dRows.p, st);
-  if (dBits.p) cudaFreeAsync(dBits.p, st);
-  if (dCount.p) cudaFreeAsync(dCount.p, st);
-  if (dBase.p) cudaFreeAsync(dBase.p, st);
-  if (dPay.p) cudaFreeAsync(dPay.p, st);
   free(base);
   free(cb);
   if (bytes) *bytes = moved;

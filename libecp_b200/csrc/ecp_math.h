@@ -106,7 +106,12 @@ ECP_HD int ecp_bessel(const double *__restrict__ tabT, int stride, const double 
       for (int j = 1; j <= KM + 5 - i; j++) {
         if (j <= top) {
           const double cur = d[j];
+#if defined(ECP_BESSEL_3OP)
           d[j] = fma((double)j / (2.0 * j + 1.0), prev - d[j + 1], d[j + 1] - cur); /* C_j as an immediate */
+#else
+          /* C_j (prev - next) + (next - cur) = C_j prev + (1 - C_j) next - cur: two fused operations instead of three */
+          d[j] = fma((double)j / (2.0 * j + 1.0), prev, fma((double)(j + 1) / (2.0 * j + 1.0), d[j + 1], -cur));
+#endif
           prev = cur;
         }
       }

@@ -303,6 +303,31 @@ def test_sparse_download_equals_dense_download():
             assert bs < 0.8 * bd
 
 
+def test_streamed_download_equals_download_after_the_pass():
+    """the host consumer hands the rows of atoms no later centre can reach to a download thread while the pass goes on
+    (api.c: stream_after_batch; LIBECP_B200_STREAM_D2H=0 downloads everything after the pass): same matrix, also sharded,
+    with many small batches so that several downloads really overlap the pass"""
+    for s in (synth.cfg5(60), synth.cfg3(4)):
+        def run(shard=None):
+            dim = int(s["dim"])
+            acc = np.full((dim, dim), -0.5)
+            with capi.Handle(s) as h:
+                if shard:
+                    h.set_shard(*shard)
+                rc = capi.lib().libecp_b200_integrals_host(ctypes.c_void_p(h.h), dim, acc.ctypes.data_as(capi._pd))
+                st = h.stats()
+            assert rc == 0
+            return acc, st
+        env = {"LIBECP_B200_BATCH_TRIPLES": "20000" if s["nat"] > 4 else "300", "LIBECP_B200_STREAM_MIN_BYTES": "1"}
+        for shard in (None, (0, 2)):
+            ref, st0 = _with_env(dict(env, LIBECP_B200_STREAM_D2H="0"), lambda: run(shard))
+            got, st1 = _with_env(env, lambda: run(shard))
+            assert st1["batches"] >= 3
+            assert np.array_equal(ref != -0.5, got != -0.5), (s.get("name"), shard)
+            assert np.allclose(ref, got, rtol=1e-13, atol=1e-15), (s.get("name"), shard)
+            assert np.all(got[np.tril_indices(got.shape[0], -1)] == -0.5)
+
+
 def test_handles_in_sequence_reuse_parked_buffers():
     """libECP_free parks the device scratch for the next handle: shapes of different size in sequence, then an
     explicit release, still give the reference's matrices"""
