@@ -1006,6 +1006,8 @@ struct EcpDev {
   int fastUnroll; /* LIBECP_B200_FASTUNROLL: point pairs of the survivors' loop whose loads are in flight together (1, 2, 4) */
   long long survCapEnv; /* LIBECP_B200_SURVCAP: survivor-list capacity override (tests of the overflow path) */
   Buf t1list, t1mask, t1count, t1work, t1rec, trirec, clsJ, Jbuf, fbItems, fbList, fbUnits, fbTotals, fbR;
+  Buf t1surv, t1smask, t1scount, t1state; /* k_type1A -> k_type1S: survivor list, open masks, per-launch count, (I, p, q) */
+  int t1legacy;                           /* LIBECP_B200_T1=legacy: k_type1S alone, from the first point */
   int launchSeq;
   Buf dbgBuf;
   int tails; /* LIBECP_B200_TAILS */
@@ -1168,6 +1170,8 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     d->fbminb = e ? atoi(e) : 3;
     e = getenv("LIBECP_B200_FBOCC");
     d->fbocc = e ? atoi(e) : 0;
+    e = getenv("LIBECP_B200_T1");
+    d->t1legacy = (e && !strcmp(e, "legacy"));
     e = getenv("LIBECP_B200_T1BLOCK");
     d->t1block = e ? atoi(e) : 64;
     if (d->t1block != 32 && d->t1block != 64 && d->t1block != 96 && d->t1block != 128) d->t1block = 64;
@@ -1393,6 +1397,7 @@ static int collect_bufs(EcpDev *d, Buf **bs) {
                  &d->t1work, &d->t1rec, &d->trirec, &d->clsJ, &d->Jbuf, &d->fbItems, &d->fbList, &d->fbUnits, &d->fbTotals, &d->fbR,
                  &d->fbwItems, &d->fbwUnits, &d->fbwQd, &d->fbwSI, &d->fbwSP, &d->fbwSQ, &d->fbwRes, &d->fbwOpenFlag, &d->fbwVals,
                  &d->fbwListA, &d->fbwListB, &d->fbwCtr, &d->dlRows, &d->dlBits, &d->dlCount, &d->dlBase, &d->dlPay,
+                 &d->t1surv, &d->t1smask, &d->t1scount, &d->t1state,
 #define UPSET(i) &d->up[i].asAtom, &d->up[i].asType, &d->up[i].asR, &d->up[i].asOmOff, &d->up[i].ssShell,            \
                  &d->up[i].ssASlot, &d->up[i].ssStart, &d->up[i].ssEnd, &d->up[i].ssFOff, &d->up[i].trA, &d->up[i].trB, \
                  &d->up[i].trOut, &d->up[i].trPair, &d->up[i].prTriple, &d->up[i].clsFirst, &d->up[i].clsWork,        \
@@ -1882,6 +1887,18 @@ extern "C" int ecpdev_matrix_add_to_host(EcpDev *d, double *host, int rowdim, co
   if (bytes) *bytes = moved;
   return 0;
 }
+/* diagnostic builds (-DT1_STATS): read and clear the lane / chunk statistics of k_type1S; 0 = not compiled in */
+extern "C" int ecpdev_t1stats(unsigned long long *out) {
+#ifdef T1_STATS
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out, g_t1stats, sizeof(z)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_t1stats, z, sizeof(z));
+  return 1;
+#else
+  (void)out;
+  return 0;
+#endif
+}
 extern "C" void *ecpdev_matrix_ptr(EcpDev *d) { return d->matrix; }
 
 /* ---- spherical-harmonic output (scope row f4, second half: "output to spherical AOs") ----
@@ -2163,7 +2180,25 @@ static void launch_type1_t(EcpDev *d, const T1Segs &sg, long long listOff, int s
   const long long groupsPerBlock = block / 8;
   const long long wantS = (n + groupsPerBlock - 1) / groupsPerBlock;
   const long long capS = (long long)d->nSM * occS[bi], capL = (long long)d->nSM * occL[bi];
-  k_type1S<LAB><<<(unsigned)(wantS < capS ? wantS : capS), block, smem, d->s2>>>(d->t, d->b, sg, work, cnt, list, mask);
+  if (d->t1legacy) {
+    k_type1S<LAB><<<(unsigned)(wantS < capS ? wantS : capS), block, smem, d->s2>>>(d->t, d->b, sg, work, cnt, list, mask, NULL,
+                                                                               NULL, NULL, NULL);
+  } else {
+    /* first 16 slots of every pair as a block-wide wave, then the open pairs level-wise (ecp_type1.cuh) */
+    static int attrA_[ECP_MAXDEV] = {0};
+    const size_t smemA = t1a_smem_bytes(LAB);
+    if (d->device >= ECP_MAXDEV || !attrA_[d->device]) {
+      cudaFuncSetAttribute(k_type1A<LAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
+      if (d->device < ECP_MAXDEV) attrA_[d->device] = 1;
+    }
+    int *scnt = (int *)d->t1scount.p + slot;
+    int *slist = (int *)d->t1surv.p + listOff;
+    unsigned long long *smask = (unsigned long long *)d->t1smask.p;
+    const int PB = T1ACfg<LAB>::PB;
+    k_type1A<LAB><<<(unsigned)((n + PB - 1) / PB), 256, smemA, d->s2>>>(d->t, d->b, sg, scnt, slist, smask, (double *)d->t1state.p);
+    k_type1S<LAB><<<(unsigned)(wantS < capS ? wantS : capS), block, smem, d->s2>>>(d->t, d->b, sg, work, cnt, list, mask, scnt,
+                                                                               slist, smask, (const double *)d->t1state.p);
+  }
   /* the number of failed pairs is only known on the device: at most one resident wave, blocks without work leave */
   const long long wantL = (wantS + 3) / 4 > 1 ? (wantS + 3) / 4 : 1;
   k_type1L<LAB><<<(unsigned)(wantL < capL ? wantL : capL), block, smem, d->s2>>>(d->t, d->b, work + 1, cnt, list, mask,
@@ -2388,6 +2423,26 @@ extern "C" int ecpdev_run_batch(EcpDev *d, EcpBatch *h, int flags, int slot, dou
     rc_ = ensure(&d->t1count, 256 * sizeof(int));
     if (rc_) return rc_;
     CK(cudaMemsetAsync(d->t1count.p, 0, 256 * sizeof(int), d->s1));
+    if (!d->t1legacy) {
+      rc_ = ensure(&d->t1surv, ((size_t)h->nPairs + 1) * sizeof(int));
+      if (rc_) return rc_;
+      rc_ = ensure(&d->t1smask, ((size_t)h->nPairs + 1) * sizeof(unsigned long long));
+      if (rc_) return rc_;
+      rc_ = ensure(&d->t1scount, 256 * sizeof(int));
+      if (rc_) return rc_;
+      CK(cudaMemsetAsync(d->t1scount.p, 0, 256 * sizeof(int), d->s1));
+      /* (I, p, q) of every quadrature of the pairs of ONE launch (launches of a batch follow each other on one stream) */
+      size_t need = 0;
+      for (int lab = 0; lab <= 2 * d->maxLBS; lab++) {
+        long long np = 0;
+        for (int c = 0; c < nc; c++)
+          if (d->hClsLa[c] + d->hClsLb[c] == lab) np += h->clsPairBase[c + 1] - h->clsPairBase[c];
+        const size_t bytes = (size_t)np * T1_NQ(lab) * 3 * sizeof(double);
+        if (bytes > need) need = bytes;
+      }
+      rc_ = ensure(&d->t1state, need + 64);
+      if (rc_) return rc_;
+    }
     rc_ = ensure(&d->t1work, 512 * sizeof(int));
     if (rc_) return rc_;
     CK(cudaMemsetAsync(d->t1work.p, 0, 512 * sizeof(int), d->s1));

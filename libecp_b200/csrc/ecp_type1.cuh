@@ -23,6 +23,12 @@
  *   (inside the window and below the exponent gate) into one sequence across the levels and lets a chunk span levels
  *   halves the chunks of a typical pair, but its per-pair set-up (gate search, level table) and the point-by-point
  *   owner loop cost more than the chunks saved: 1.17 -> 1.30 ms on Au20, 30.9 -> 38.5 ms per config-5 pass.
+ *   Round-2 session 3, tools/t1_stats.py (-DT1_STATS build): on configuration 5 half of all 8-slot chunks are the two fixed
+ *   ones of a pair (slots 0..15) with 2.1 live lanes of 8, the level-wise chunks hold 6.6 of 8; 3.6 % of the pairs fail on
+ *   the small grid and take 40 % of the chunks.  Evaluating the first 16 slots in ONE chunk when at most 8 are live (pre-test
+ *   of window and gate, lane i takes the i-th live slot, owners pick the values out by slot number; Q bit-identical) removes
+ *   a quarter of the chunks but costs ~250 instructions in every warp iteration in which any of the four groups starts a
+ *   pair (three out of four): type-1 23.4 -> 24.8 ms per configuration-5 pass.  Removed (profiles/r2/session3).
  *   k_type1S<LAB>: small 383-point grid, PS93; writes converged Q, records a mask of failed quadratures
  *   k_type1L<LAB>: failed quadratures on the per-pair FM06-mapped 1023-point grid, PSM92
  */
@@ -32,6 +38,13 @@
 #include <utility>
 
 #define T1_MAXSEG 24
+/* -DT1_STATS: lane / chunk statistics of k_type1S (diagnostic builds only, tools/t1_stats.py) */
+#ifdef T1_STATS
+__device__ unsigned long long g_t1stats[16];
+#define T1_STAT(i, v) atomicAdd(&g_t1stats[i], (unsigned long long)(v))
+#else
+#define T1_STAT(i, v) ((void)0)
+#endif
 /* resident blocks of 128 threads per SM the type-1 kernels are compiled for (registers <= 65536 / (128 MINB)) */
 #ifndef T1_MINB_LO
 #define T1_MINB_LO 5
@@ -125,16 +138,185 @@ __device__ __forceinline__ void t1_fill_point(const DevT &t, double r, double za
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+/* k_type1A<LAB>: the first 16 slots of every primitive pair (the three unconditional points and levels 0..3 of the PS93
+ * rule, src/gc_integrators.c:175-199) as a block-wide wave.  tools/t1_stats.py: in the 8-lanes-per-pair kernel these two
+ * fixed chunks are half of all chunks of a configuration-5 pass and hold 2.1 live lanes of 8 (window and exponent gate).
+ * Here a block takes PB pairs: (1) a thread per (pair, slot) tests window and gate and appends the live ones to a list in
+ * shared memory; (2) a thread per LIVE point evaluates it - potential, exponential, Bessel vector, powers - and stores the
+ * products of all NQ quadratures into a zeroed shared-memory table [pair][slot][quadrature] (full warps instead of a third
+ * of the lanes); (3) a thread per (pair, quadrature) runs the bookkeeping of levels 0..3 on its 16 values with exactly
+ * the sums of k_type1S (pairs first, absent points are exact zeros) and either writes the converged Q or leaves
+ * (I, p, q) in `state`; (4) pairs with an open quadrature go to the survivor list, which k_type1S continues level-wise
+ * from level 4.  Q is bit-identical to the one-kernel path (LIBECP_B200_T1=legacy; test). */
+template <int LAB>
+struct T1ACfg {
+  static constexpr int NQ = T1_NQ(LAB);
+  static constexpr int NQP = NQ | 1;                                 /* odd row: conflict-free stores of a point's products */
+  static constexpr int PB = LAB <= 4 ? 64 : (LAB <= 6 ? 32 : 16);    /* pairs per block: 72 / 68 / 74 KB of values at most */
+};
+struct T1ARec {
+  double z, sS, Cc;
+  const double *UL;
+  double *Qo;
+  long long pr;
+  int gs, ge;
+  unsigned wm, lm; /* in-window / live masks of the 16 slots */
+  unsigned open0, open1;
+};
+static size_t t1a_smem_bytes(int lab) {
+  const int nq = T1_NQ(lab), nqp = nq | 1, pb = lab <= 4 ? 64 : (lab <= 6 ? 32 : 16);
+  return (size_t)pb * 16 * nqp * sizeof(double) + (size_t)pb * sizeof(T1ARec) + (size_t)pb * 16 * sizeof(unsigned short);
+}
+template <int LAB, int... Q>
+__device__ __forceinline__ void t1a_store_vals(const T1Point<LAB> &pt, double Cc, double *dst, std::integer_sequence<int, Q...>) {
+  double H[LAB + 1];
+  const double G = pt.w * ((Cc * pt.u) * pt.ex);
+#pragma unroll
+  for (int i = 0; i <= LAB; i++) H[i] = G * pt.rn[i];
+  ((dst[Q] = H[t1_qN(Q)] * pt.K[t1_qLam(Q)]), ...);
+}
+template <int LAB>
+__global__ void __launch_bounds__(256, 2) k_type1A(DevT t, DevB b, T1Segs segs, int *survCount, int *survList,
+                                                   unsigned long long *survMask, double *state) {
+  using Cfg = T1ACfg<LAB>;
+  constexpr int NQ = Cfg::NQ, NQP = Cfg::NQP, PB = Cfg::PB;
+  extern __shared__ __align__(16) unsigned char t1a_raw[];
+  double *vals = (double *)t1a_raw; /* [PB][16][NQP] */
+  T1ARec *rec = (T1ARec *)(vals + (size_t)PB * 16 * NQP);
+  unsigned short *items = (unsigned short *)(rec + PB);
+  __shared__ int cnt;
+  const int tid = threadIdx.x;
+  const int total = (int)segs.prefix[segs.nseg];
+  const int g0 = blockIdx.x * PB;
+  const int np = min(PB, total - g0);
+  if (np <= 0) return;
+  if (tid < np) {
+    const int g = g0 + tid;
+    int sg = 0;
+    while (segs.prefix[sg + 1] <= g) sg++;
+    const long long pr = segs.start[sg] + (g - segs.prefix[sg]);
+    const T1Rec r = b.t1rec[pr];
+    T1ARec &a = rec[tid];
+    a.z = r.z;
+    a.sS = r.sS;
+    a.Cc = r.CcS;
+    a.UL = t.typeUL + (size_t)r.type * ECP_SMALL_SLOTS;
+    a.Qo = b.Q + r.qoff;
+    a.pr = pr;
+    a.gs = r.gs;
+    a.ge = r.ge;
+    a.wm = a.lm = 0;
+    a.open0 = a.open1 = 0;
+  }
+  if (tid == 0) cnt = 0;
+  for (int i = tid; i < np * 16 * NQP; i += 256) vals[i] = 0.0;
+  __syncthreads();
+  /* (1) window and gate of every (pair, slot); half a warp per pair */
+  for (int i0 = 0; i0 < np * 16; i0 += 256) {
+    const int i = i0 + tid;
+    const int p = i >> 4, sl = i & 15;
+    bool w = false, l = false;
+    if (i < np * 16 && sl != 1) {
+      const int oi = t.small_oidx[sl], gs = rec[p].gs, ge = rec[p].ge;
+      /* the three first points are unconditional (src/gc_integrators.c:175-177); afterwards the left point of a
+       * pair needs idx >= start, the right one idx <= end (:190-197); tabulated range [start,end): src/type1.c:121 */
+      w = (sl < 4) ? true : ((sl & 1) ? (oi <= ge) : (oi >= gs));
+      if (w && oi >= gs && oi < ge) {
+        const double r = t.small_r[sl];
+        l = __dmul_rn(__fma_rn(rec[p].z, r, rec[p].sS), r) >= t.lnAcc1;
+      }
+    }
+    const unsigned bw = __ballot_sync(T1_FULL, w), bl = __ballot_sync(T1_FULL, l);
+    if (i < np * 16 && sl == 0) {
+      const int sh = tid & 16;
+      rec[p].wm = (bw >> sh) & 0xffffu;
+      rec[p].lm = (bl >> sh) & 0xffffu;
+    }
+    if (l) items[atomicAdd(&cnt, 1)] = (unsigned short)i;
+  }
+  __syncthreads();
+  /* (2) one thread per live point */
+  const int nItems = cnt;
+  for (int it = tid; it < nItems; it += 256) {
+    const int i = items[it], p = i >> 4, sl = i & 15;
+    const T1ARec &a = rec[p];
+    const double r = t.small_r[sl];
+    const double e = __dmul_rn(__fma_rn(a.z, r, a.sS), r);
+    T1Point<LAB> pt;
+    pt.live = true;
+    pt.w = t.small_w[sl];
+    pt.u = a.UL[sl];
+    pt.ex = exp(e);
+    t1_fill_point<LAB>(t, r, a.sS * r, pt);
+    t1a_store_vals<LAB>(pt, a.Cc, vals + ((size_t)p * 16 + sl) * NQP, std::make_integer_sequence<int, NQ>{});
+  }
+  __syncthreads();
+  /* (3) bookkeeping of the three first points and levels 0..3, one thread per (pair, quadrature) */
+  for (int i = tid; i < np * NQ; i += 256) {
+    const int p = i / NQ, q = i - p * NQ;
+    const double *v = vals + (size_t)p * 16 * NQP + q;
+    const unsigned wm = rec[p].wm;
+    int N = 0, qq = q; /* quadrature q of the loop nest "for N: for lambda = N, N-2, ..." (src/type1.c:132-146) */
+    while (qq >= N / 2 + 1) {
+      qq -= N / 2 + 1;
+      N++;
+    }
+    double *dst = rec[p].Qo + N * (LAB + 1) + (N - 2 * qq);
+#define T1A_V(s_) v[(s_) * NQP]
+    const double A0 = T1A_V(0) + T1A_V(1), B0 = T1A_V(2) + T1A_V(3), C0 = T1A_V(4) + T1A_V(5), D0 = T1A_V(6) + T1A_V(7);
+    const double A1 = T1A_V(8) + T1A_V(9), B1 = T1A_V(10) + T1A_V(11), C1 = T1A_V(12) + T1A_V(13), D1 = T1A_V(14) + T1A_V(15);
+#undef T1A_V
+    double P = A0, Qv = B0, I = P + Qv, res;
+    bool done = false;
+    I += C0;
+    if (ecp_ps93_update(t.sm.levJ[0], t.sm.levN[0], __popc(wm & 0x30u), t.tolerance, I, &P, &Qv, &res)) done = true;
+    if (!done) {
+      I += D0;
+      if (ecp_ps93_update(t.sm.levJ[1], t.sm.levN[1], __popc(wm & 0xc0u), t.tolerance, I, &P, &Qv, &res)) done = true;
+    }
+    if (!done) {
+      I += (A1 + B1);
+      if (ecp_ps93_update(t.sm.levJ[2], t.sm.levN[2], __popc(wm & 0x0f00u), t.tolerance, I, &P, &Qv, &res)) done = true;
+    }
+    if (!done) {
+      I += (C1 + D1);
+      if (ecp_ps93_update(t.sm.levJ[3], t.sm.levN[3], __popc(wm & 0xf000u), t.tolerance, I, &P, &Qv, &res)) done = true;
+    }
+    if (done) {
+      *dst = res; /* T[l1][l2] += I  (src/type1.c:143) */
+    } else {
+      double *st = state + ((size_t)(g0 + p) * NQ + q) * 3;
+      st[0] = I;
+      st[1] = P;
+      st[2] = Qv;
+      if (q < 32)
+        atomicOr(&rec[p].open0, 1u << q);
+      else
+        atomicOr(&rec[p].open1, 1u << (q - 32));
+    }
+  }
+  __syncthreads();
+  /* (4) pairs with an open quadrature continue level-wise in k_type1S */
+  if (tid < np && (rec[tid].open0 | rec[tid].open1)) {
+    survList[atomicAdd(survCount, 1)] = g0 + tid;
+    survMask[rec[tid].pr] = (unsigned long long)rec[tid].open0 | ((unsigned long long)rec[tid].open1 << 32);
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
 template <int LAB>
 __global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_MINB_MID : 3))) k_type1S(DevT t, DevB b, T1Segs segs, int *workCtr, int *failCount, int *failList,
-                                                unsigned long long *failMask) {
+                                                unsigned long long *failMask, const int *survCount, const int *survList,
+                                                const unsigned long long *survMask, const double *state) {
   using Cfg = T1Cfg<LAB>;
   constexpr int NQ = Cfg::NQ, NQL = Cfg::NQL;
   extern __shared__ __align__(16) double t1_red[];
   const int lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24;
   double *red = t1_red + ((threadIdx.x >> 5) * 4 + (lane >> 3)) * Cfg::GS;
   const unsigned long long dbgT0 = b.dbg ? ecp_gtimer() : 0;
-  const int total = (int)segs.prefix[segs.nseg];
+  /* survCount != NULL: the pairs k_type1A left open, continued from level 4 with its (I, p, q); NULL: every pair of the
+   * launch from its first point (LIBECP_B200_T1=legacy) */
+  const int total = survCount ? *survCount : (int)segs.prefix[segs.nseg];
   bool have = false, drained = false;
   double z = 0.0, sS = 0.0, Cc = 0.0;
   int gs = 0, ge = 0;
@@ -150,6 +332,9 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_M
     qo[k] = t1_qN(q) * (LAB + 1) + t1_qLam(q);
   }
   unsigned open = 0;
+#ifdef T1_STATS
+  int nchunks = 0;
+#endif
   int c = 0;   /* 0, 1: the two fixed chunks (slots 0..15 = first points and levels 0..3); 2: level-wise     */
   int v = 4;   /* level being accumulated once c == 2                                                        */
   int ks = 0;  /* 8-point step inside that level: only the points inside the window are visited              */
@@ -163,6 +348,7 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_M
       g = __shfl_sync(T1_FULL, g, gbase);
       if (need) {
         if (g < total) {
+          if (survCount) g = survList[g];
           int sg = 0;
           while (segs.prefix[sg + 1] <= g) sg++;
           pr = segs.start[sg] + (g - segs.prefix[sg]);
@@ -175,10 +361,26 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_M
           UL = t.typeUL + (size_t)rec.type * ECP_SMALL_SLOTS;
           Qo = b.Q + rec.qoff;
           open = 0;
-#pragma unroll
-          for (int k = 0; k < NQL; k++)
-            if (8 * k + gl < NQ) open |= 1u << k;
           c = 0;
+          if (survCount) {
+            const unsigned long long om = survMask[pr];
+#pragma unroll
+            for (int k = 0; k < NQL; k++) {
+              const int q = 8 * k + gl;
+              if (q < NQ && (om >> q & 1ull)) {
+                const double *st = state + ((size_t)g * NQ + q) * 3;
+                open |= 1u << k;
+                I[k] = st[0];
+                P[k] = st[1];
+                Qv[k] = st[2];
+              }
+            }
+            c = 2;
+          } else {
+#pragma unroll
+            for (int k = 0; k < NQL; k++)
+              if (8 * k + gl < NQ) open |= 1u << k;
+          }
           v = 4;
           ks = 0;
           lv = t1_level(&t.sm, t.small_jL, t.small_jR, 4, gs, ge);
@@ -219,6 +421,27 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_M
       }
     }
     const unsigned bal = (__ballot_sync(T1_FULL, inWin) >> gbase) & 0xffu;
+#ifdef T1_STATS
+    {
+      const unsigned bw = __ballot_sync(T1_FULL, inWin), bl = __ballot_sync(T1_FULL, pt.live);
+      const unsigned bh = __ballot_sync(T1_FULL, have && gl == 0);
+      const unsigned b0 = __ballot_sync(T1_FULL, have && gl == 0 && c == 0), b1 = __ballot_sync(T1_FULL, have && gl == 0 && c == 1);
+      const unsigned l0 = __ballot_sync(T1_FULL, pt.live && c == 0), l1 = __ballot_sync(T1_FULL, pt.live && c == 1);
+      if (lane == 0) {
+        T1_STAT(0, 1);
+        T1_STAT(1, __popc(bh));
+        T1_STAT(2, __popc(b0));
+        T1_STAT(3, __popc(b1));
+        T1_STAT(4, __popc(bh) - __popc(b0) - __popc(b1));
+        T1_STAT(5, __popc(bw));
+        T1_STAT(6, __popc(bl));
+        T1_STAT(7, __popc(l0));
+        T1_STAT(8, __popc(l1));
+        T1_STAT(9, __popc(bl) - __popc(l0) - __popc(l1));
+      }
+      if (have) nchunks++;
+    }
+#endif
     /* ---- products of all quadratures -> tile [q][lane]; owner lane q mod 8 reads its rows back ---- */
     __syncwarp();
     t1_store_vals<LAB>(pt, Cc, red + gl, std::make_integer_sequence<int, NQ>{});
@@ -304,6 +527,18 @@ __global__ void __launch_bounds__(128, (LAB <= 3 ? T1_MINB_LO : (LAB <= 6 ? T1_M
         failList[atomicAdd(failCount, 1)] = (int)pr;
       }
     }
+#ifdef T1_STATS
+    if (fin && gl == 0) {
+      T1_STAT(10, 1);
+      if (ob != 0) {
+        T1_STAT(11, 1);
+        T1_STAT(12, nchunks);
+      } else {
+        T1_STAT(13, nchunks);
+      }
+    }
+    if (fin) nchunks = 0;
+#endif
     if (fin) {
       have = false;
       open = 0;

@@ -411,6 +411,28 @@ def test_link_variants_are_bit_identical():
             assert np.allclose(got, base, rtol=1e-13, atol=1e-15), (name, env)
 
 
+def test_type1_wave_is_bit_identical_to_the_one_kernel_path():
+    """k_type1A (first 16 slots of every primitive pair as a block-wide wave: thread per live point, thread per
+    (pair, quadrature) for the bookkeeping of levels 0..3) + k_type1S on the open pairs from level 4 performs the
+    operations of k_type1S alone (LIBECP_B200_T1=legacy) in the same order: Q must be bit-identical; L = 2, 4 (config 5),
+    4 (Au), g / h stress shapes (LAB up to 10), several batches"""
+    for s, name in ((synth.cfg3(4), "au4"), (synth.cfg4("a"), "cfg4a"), (synth.cfg4("b"), "cfg4b"), (synth.cfg5(24), None),
+                    (synth.cfg2(5), "cfg2_L5")):
+        def run():
+            with capi.Handle(s) as h:
+                rc, M = h.integrals_host()
+                st = h.stats()
+                return M, h.debug_fetch("Q", 2000000), st
+        for env in ({}, {"LIBECP_B200_BATCH_TRIPLES": "700"}):
+            base, q0, st0 = _with_env(dict(env, LIBECP_B200_T1="legacy"), run)
+            got, q1, st1 = _with_env(env, run)
+            assert np.abs(q0).sum() > 0 and np.array_equal(q0, q1), (name, env)
+            assert np.allclose(got, base, rtol=1e-13, atol=1e-15), (name, env)
+            assert st0["t1_large_pairs"] == st1["t1_large_pairs"] if "t1_large_pairs" in st0 else True
+        if name:
+            assert_parity(got, load_matrix(name), name)
+
+
 def test_shift_kernels_are_bit_identical():
     """k_shift2 (default: both binomial-shift passes in one kernel, J in shared memory, factors per (triple, term)) runs
     the terms of k_shiftJ / k_shiftI (LIBECP_B200_SHIFT=two) in the same order with the same fma's: callback blocks
