@@ -1172,6 +1172,7 @@ extern "C" EcpDev *ecpdev_create(const EcpHostTables *h, int device) {
     d->fbocc = e ? atoi(e) : 0;
     e = getenv("LIBECP_B200_T1");
     d->t1legacy = (e && !strcmp(e, "legacy"));
+    t1_upload_qoff();
     e = getenv("LIBECP_B200_T1BLOCK");
     d->t1block = e ? atoi(e) : 64;
     if (d->t1block != 32 && d->t1block != 64 && d->t1block != 96 && d->t1block != 128) d->t1block = 64;

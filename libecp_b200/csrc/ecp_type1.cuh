@@ -68,6 +68,7 @@ struct T1Point {
 /* number of (N, lambda) quadratures: sum_{N<=LAB} (N/2+1) */
 #define T1_NQ(LAB) (((LAB) % 2 == 0) ? ((LAB) / 2 + 1) * ((LAB) / 2 + 1) : ((LAB) / 2 + 1) * ((LAB) / 2 + 2))
 #define T1_FULL 0xffffffffu
+__constant__ unsigned char c_t1qoff[11][36]; /* [LAB][q] -> N (LAB + 1) + lambda; filled by t1_upload_qoff */
 
 /* quadrature q of the loop nest "for N: for lambda = N, N-2, ..." (src/type1.c:132-146) */
 __host__ __device__ constexpr int t1_qN(int q) {
@@ -148,11 +149,17 @@ __device__ __forceinline__ void t1_fill_point(const DevT &t, double r, double za
  * the sums of k_type1S (pairs first, absent points are exact zeros) and either writes the converged Q or leaves
  * (I, p, q) in `state`; (4) pairs with an open quadrature go to the survivor list, which k_type1S continues level-wise
  * from level 4.  Q is bit-identical to the one-kernel path (LIBECP_B200_T1=legacy; test). */
+#ifndef T1A_MINB
+#define T1A_MINB 2
+#endif
+#ifndef T1A_PBNUM
+#define T1A_PBNUM 8 /* eighths of the default number of pairs per block (A/B builds) */
+#endif
 template <int LAB>
 struct T1ACfg {
   static constexpr int NQ = T1_NQ(LAB);
   static constexpr int NQP = NQ | 1;                                 /* odd row: conflict-free stores of a point's products */
-  static constexpr int PB = LAB <= 4 ? 64 : (LAB <= 6 ? 32 : 16);    /* pairs per block: 72 / 68 / 74 KB of values at most */
+  static constexpr int PB = (LAB <= 4 ? 64 : (LAB <= 6 ? 32 : 16)) * T1A_PBNUM / 8; /* pairs per block: 72 / 68 / 74 KB of values at most (T1A_PBNUM = 8) */
 };
 struct T1ARec {
   double z, sS, Cc;
@@ -164,8 +171,14 @@ struct T1ARec {
   unsigned open0, open1;
 };
 static size_t t1a_smem_bytes(int lab) {
-  const int nq = T1_NQ(lab), nqp = nq | 1, pb = lab <= 4 ? 64 : (lab <= 6 ? 32 : 16);
+  const int nq = T1_NQ(lab), nqp = nq | 1, pb = (lab <= 4 ? 64 : (lab <= 6 ? 32 : 16)) * T1A_PBNUM / 8;
   return (size_t)pb * 16 * nqp * sizeof(double) + (size_t)pb * sizeof(T1ARec) + (size_t)pb * 16 * sizeof(unsigned short);
+}
+static void t1_upload_qoff(void) {
+  unsigned char h[11][36] = {{0}};
+  for (int lab = 0; lab <= 10; lab++)
+    for (int q = 0; q < T1_NQ(lab); q++) h[lab][q] = (unsigned char)(t1_qN(q) * (lab + 1) + t1_qLam(q));
+  cudaMemcpyToSymbol(c_t1qoff, h, sizeof(h));
 }
 template <int LAB, int... Q>
 __device__ __forceinline__ void t1a_store_vals(const T1Point<LAB> &pt, double Cc, double *dst, std::integer_sequence<int, Q...>) {
@@ -176,7 +189,7 @@ __device__ __forceinline__ void t1a_store_vals(const T1Point<LAB> &pt, double Cc
   ((dst[Q] = H[t1_qN(Q)] * pt.K[t1_qLam(Q)]), ...);
 }
 template <int LAB>
-__global__ void __launch_bounds__(256, 2) k_type1A(DevT t, DevB b, T1Segs segs, int *survCount, int *survList,
+__global__ void __launch_bounds__(256, T1A_MINB) k_type1A(DevT t, DevB b, T1Segs segs, int *survCount, int *survList,
                                                    unsigned long long *survMask, double *state) {
   using Cfg = T1ACfg<LAB>;
   constexpr int NQ = Cfg::NQ, NQP = Cfg::NQP, PB = Cfg::PB;
@@ -256,12 +269,8 @@ __global__ void __launch_bounds__(256, 2) k_type1A(DevT t, DevB b, T1Segs segs, 
     const int p = i / NQ, q = i - p * NQ;
     const double *v = vals + (size_t)p * 16 * NQP + q;
     const unsigned wm = rec[p].wm;
-    int N = 0, qq = q; /* quadrature q of the loop nest "for N: for lambda = N, N-2, ..." (src/type1.c:132-146) */
-    while (qq >= N / 2 + 1) {
-      qq -= N / 2 + 1;
-      N++;
-    }
-    double *dst = rec[p].Qo + N * (LAB + 1) + (N - 2 * qq);
+    /* quadrature q of the loop nest "for N: for lambda = N, N-2, ..." (src/type1.c:132-146) -> offset of Q[N][lambda] */
+    double *dst = rec[p].Qo + c_t1qoff[LAB][q];
 #define T1A_V(s_) v[(s_) * NQP]
     const double A0 = T1A_V(0) + T1A_V(1), B0 = T1A_V(2) + T1A_V(3), C0 = T1A_V(4) + T1A_V(5), D0 = T1A_V(6) + T1A_V(7);
     const double A1 = T1A_V(8) + T1A_V(9), B1 = T1A_V(10) + T1A_V(11), C1 = T1A_V(12) + T1A_V(13), D1 = T1A_V(14) + T1A_V(15);
