@@ -201,7 +201,7 @@ KERNEL_OF = {"tables": "ms_tables", "fastT": "ms_fastT", "fallback": "ms_fallbac
              "type1": "ms_type1", "chi": "ms_chi", "shift": "ms_shift"}
 KERNEL_NAME = {"tables": "k_enum_fill+k_triprep+k_atomslot+k_omegaX+k_Ftab2", "fastT": "k_fastT+k_fastT2",
                "fallback": "k_fbw_count+k_fbw_units+k_fbw_eval<KO>+k_fbw_book+k_fbw_final",
-               "link": "k_link4<la+1,lb+1,L>+k_link<la+1,lb+1>", "type1": "k_t1prep+k_type1S<LAB>+k_type1L<LAB>", "chi": "k_chi",
+               "link": "k_link4<la+1,lb+1,L>+k_link<la+1,lb+1>", "type1": "k_t1prep+k_type1A<LAB>+k_type1S<LAB>+k_type1L<LAB>", "chi": "k_chi",
                "shift": "k_shift2"}
 # ncu --set full captures kept under profiles/ (DRAM traffic of the dominant kernel family):
 #   Au20 (cfg3): one launch of the family's main kernel, profiles/r*/ncu_full_<kernel>.raw.csv

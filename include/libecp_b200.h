@@ -95,7 +95,9 @@ int libecp_b200_screening(libECPHandle *h, int centre, int *end_l /* [L] */, int
 /* host table access for bit-exactness tests (reference tables: src/libecp.c:147-198):
  * names "fac" "dfac" "poly2sph" "omega" "small_x" "small_w" "large_x" "large_w" "bessel" ; returns length */
 int libecp_b200_host_table(libECPHandle *h, const char *name, const double **ptr);
-/* integer tables for tests: "small_oidx" "large_oidx" "small_meta" "dims" "ijk" "ijkIndex" "atomType"; returns count */
+/* integer tables for tests: "small_oidx" "large_oidx" "small_meta" "dims" "ijk" "ijkIndex" "atomType" "lastCentre" (per atom:
+ * the last ECP centre whose screening can keep one of its shells, -1 = none - the rows of the atom are final once the pass
+ * is beyond it, which is when the host consumer downloads them); returns count */
 int libecp_b200_host_itable(libECPHandle *h, const char *name, int *out, int cap);
 /* executed triples of the whole job in the reference's loop order, rows (A,s1,la,B,s2,lb,C); host only */
 long long libecp_b200_triple_list(libECPHandle *h, int *out, long long cap);

@@ -909,6 +909,12 @@ int libecp_b200_host_itable(libECPHandle *h, const char *name, int *out, int cap
     for (int i = 0; i < v->ijkDim * v->ijkDim * v->ijkDim; i++) PUT(t->ijkIndex[i]);
   else if (!strcmp(name, "atomType"))
     for (int i = 0; i < h->nrAtoms; i++) PUT(t->atomType[i]);
+  else if (!strcmp(name, "lastCentre")) { /* streamed download: last centre that can reach each atom (builder.c) */
+    int *lc = malloc((size_t)(h->nrAtoms + 1) * sizeof(int));
+    ecp_atom_last_centre(t, h->geometry, lc);
+    for (int i = 0; i < h->nrAtoms; i++) PUT(lc[i]);
+    free(lc);
+  }
 #undef PUT
   return n;
 }

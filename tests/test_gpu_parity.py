@@ -277,8 +277,9 @@ def test_sparse_download_equals_dense_download():
     (ecp_cuda.cu: matrix_add_to_host_sparse; LIBECP_B200_D2H=dense keeps the dense upper-triangle panels): the caller's
     matrix is the same (bit for bit on a single centre) - small matrices (rows shorter than a run), a sparse one (distant atoms), row panels,
     a sharded handle, and += into a pre-filled matrix; fewer bytes cross PCIe"""
-    far = synth.assemble("far", [(0.0, 0.0, 0.0), (0.0, 0.0, 40.0), (3.0, 0.5, 0.2)], [synth.tz_basis(2)] * 3,
-                         [synth.ecp_set(3), synth.ecp_set(3), None])
+    # two distant ECP atoms, a neighbour without ECP and an atom no centre reaches (its rows are never downloaded)
+    far = synth.assemble("far", [(0.0, 0.0, 0.0), (0.0, 0.0, 40.0), (3.0, 0.5, 0.2), (60.0, 60.0, 0.0)], [synth.tz_basis(2)] * 4,
+                         [synth.ecp_set(3), synth.ecp_set(3), None, None])
     for s in (synth.cfg1(), synth.cfg3(4), far, synth.cfg5(40)):
         def run(shard=None):
             dim = int(s["dim"])

@@ -668,3 +668,30 @@ def test_derivative_callback_keys_match_reference(name):
         dims = h.host_itable("dims")
     assert np.array_equal(keys, d["keys"][0::2]) and np.array_equal(keys, d["keys"][1::2])
     assert dims[1] == lbs + 1 and dims[2] == lbs + 1 and dims[3] == L - 1 + lbs + 1
+
+
+def test_rows_streamed_out_are_final():
+    """streamed download of the host consumer (api.c: stream_after_batch): the AO rows of an atom leave the device once the
+    pass is beyond lastCentre[atom] (builder.c: ecp_atom_last_centre).  They must be final: no later centre keeps a shell
+    of the atom after screening (src/type2.c:148-180), and an atom with lastCentre = -1 is never touched at all"""
+    far = synth.assemble("far", [(0.0, 0.0, 0.0), (0.0, 0.0, 40.0), (3.0, 0.5, 0.2), (60.0, 60.0, 0.0)], [synth.tz_basis(2)] * 4,
+                         [synth.ecp_set(3), synth.ecp_set(3), None, None])
+    for s in (synth.cfg5(40), synth.cfg3(4), far):
+        with capi.Handle(s, tables_only=True) as h:
+            last = h.host_itable("lastCentre")
+            types = h.host_itable("atomType")
+            first = np.concatenate([[0], np.cumsum(s["shellsBS"])])
+            nat = int(s["nat"])
+            assert len(last) == nat
+            reached = np.full(nat, -1)
+            for c in range(nat):
+                if types[c] < 0:
+                    continue
+                _, st, en, sk = h.screening(c, 8)  # room for end_l of any L <= 6
+                for x in range(nat):
+                    if np.any(sk[first[x]:first[x + 1]] == 0):
+                        reached[x] = c
+            assert np.all(last >= reached), (s.get("name"), last, reached)  # never final too early
+            assert np.all((last >= 0) | (reached < 0))
+        if s is far:
+            assert last[3] == -1 and reached[3] == -1
