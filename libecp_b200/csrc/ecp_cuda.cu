@@ -866,6 +866,7 @@ __global__ void k_unpack_rows(double *__restrict__ M, int n, const int *__restri
  * k_rows_flag: bitmap and number of such runs per listed row; the host turns the counts into row offsets;
  * k_rows_pack_sparse: the flagged runs of every row back to back (a short last run of a row is padded with zeros). */
 #define SPR_RUN 16
+#define SPR_PF 6 /* host add: runs prefetched ahead */
 __global__ void k_rows_flag(const double *__restrict__ M, int n, const int *__restrict__ rows, int words,
                             unsigned *__restrict__ bitmap, int *__restrict__ count) {
   extern __shared__ unsigned spr_bm[];
@@ -1714,27 +1715,44 @@ static int matrix_add_to_host_sparse(EcpDev *d, double *host, int rowdim, const 
       const int k0 = cb[p], k1 = cb[p + 1];
       const double *src = pin[p & 1];
       const long long b0 = base[k0];
-#pragma omp parallel for schedule(dynamic, 8)
-      for (int k = k0; k < k1; k++) {
-        if (!hCount[k]) continue;
-        const int i = rows[k];
-        const double *pr = src + (base[k] - b0) * SPR_RUN;
-        double *dr = host + (size_t)i * rowdim + i;
-        const unsigned *bm = hBits + (size_t)k * words;
-        const int len = n - i;
-        for (int w = 0; w < words; w++) {
-          unsigned bits = bm[w];
-          while (bits) {
-            const int r = w * 32 + __builtin_ctz(bits), j = r * SPR_RUN;
-            bits &= bits - 1;
+      /* the runs of a row land at scattered places of the caller's matrix: every run is two or three cache misses the
+       * hardware prefetcher does not see coming (measured 1.7 GB/s of payload per thread).  The run positions of a row are
+       * decoded from its bitmap first and the destinations of the runs SPR_PF ahead are prefetched for writing. */
+#pragma omp parallel
+      {
+        int *pos = (int *)malloc((size_t)(maxRuns + 1) * sizeof(int));
+#pragma omp for schedule(dynamic, 8)
+        for (int k = k0; k < k1; k++) {
+          if (!hCount[k] || !pos) continue;
+          const int i = rows[k];
+          const double *pr = src + (base[k] - b0) * SPR_RUN;
+          double *dr = host + (size_t)i * rowdim + i;
+          const unsigned *bm = hBits + (size_t)k * words;
+          const int len = n - i;
+          int nr = 0;
+          for (int w = 0; w < words; w++) {
+            unsigned bits = bm[w];
+            while (bits) {
+              pos[nr++] = (w * 32 + __builtin_ctz(bits)) * SPR_RUN;
+              bits &= bits - 1;
+            }
+          }
+          for (int u = 0; u < nr; u++, pr += SPR_RUN) {
+            if (u + SPR_PF < nr) {
+              const double *pn = dr + pos[u + SPR_PF];
+              __builtin_prefetch(pn, 1, 0);
+              __builtin_prefetch(pn + 8, 1, 0);
+              __builtin_prefetch(pn + SPR_RUN - 1, 1, 0);
+            }
+            const int j = pos[u];
             double *dj = dr + j;
             if (j + SPR_RUN <= len)
               for (int q = 0; q < SPR_RUN; q++) dj[q] += pr[q];
             else
               for (int q = 0; j + q < len; q++) dj[q] += pr[q];
-            pr += SPR_RUN;
           }
         }
+        free(pos);
       }
       tAdd += omp_get_wtime() - tw1;
     }
