@@ -420,6 +420,29 @@ def run_b200(args):
            "ms_init": 1e3 * parts[0] / e2e_steps, "ms_integrate_d2h": 1e3 * parts[1] / e2e_steps,
            "ms_free": 1e3 * parts[2] / e2e_steps}
 
+    # ---- result check of the e2e path: the caller's host matrix of the last e2e step (at N > 1 the sum of the ranks'
+    #      matrices - every rank adds its own rows) against the reference, like `parity` below for the resident matrix ----
+    if not args.no_parity and args.workload in ("cfg5", "cfg3", "cfg2", "cfg4b"):
+        from libecp_b200 import parity as parity_
+
+        try:
+            Mh = torch.from_numpy(host).cuda()
+            if dist:
+                dist.all_reduce(Mh)
+            if rank == 0:
+                if args.workload == "cfg5":
+                    r_ = parity_.check_digest(Mh, s)
+                else:
+                    r_ = parity_.check_matrix(Mh, args.workload)
+                e2e["parity"] = {"ok": bool(r_.get("ok")), "max_abs": r_.get("max_abs"),
+                                 "sample_violations": r_.get("sample_violations"),
+                                 "checked": "host matrix filled by libecp_b200_integrals_host in the last e2e step"
+                                            + (f", summed over the {world} ranks" if dist else "")}
+            del Mh
+            torch.cuda.empty_cache()
+        except Exception as ex:  # the check must never cost the bench line
+            e2e["parity"] = {"ok": None, "error": repr(ex)[:200]}
+
     # ---- device-resident consumer at N > 1: the C-ABI collective (libecp_b200_allgather: pack + one in-place
     #      ncclAllGather over NVLink + scatter), timed alone and as part of the step (`gathered`) ----
     allgather = gathered = None

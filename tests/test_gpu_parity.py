@@ -183,6 +183,26 @@ def test_config5_full_digest():
     assert res["ok"], res
 
 
+def test_config5_host_consumer_digest():
+    """the e2e path of the benchmark: libecp_b200_integrals_host on the full 500-centre crystal - sparse download of the
+    non-zero runs, rows streamed out while the pass goes on - fills the caller's host matrix; that matrix against the
+    digest of the full run of the unmodified reference; a third of the dense bytes cross PCIe"""
+    import torch
+
+    from libecp_b200 import parity
+
+    s = synth.cfg5(500)
+    dim = int(s["dim"])
+    host = np.zeros((dim, dim))
+    with capi.Handle(s) as h:
+        rc = capi.lib().libecp_b200_integrals_host(ctypes.c_void_p(h.h), dim, host.ctypes.data_as(capi._pd))
+        st = h.stats()
+    assert rc == 0 and st["batches"] >= 4
+    assert 0 < st["d2h_bytes"] < 0.4 * (dim * (dim + 1) // 2) * 8
+    res = parity.check_digest(torch.from_numpy(host).cuda(), s)
+    assert res["ok"], res
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_config5_sharded_gather_digest(world):
     """multi-GPU decomposition of the benchmarked config on one GPU: `world` handles play the ranks (row ownership,
